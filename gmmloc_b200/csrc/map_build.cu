@@ -1,0 +1,205 @@
+// map_build.cu — K0: per-component constants on the device (one thread per component, fp64).
+//
+// Replaces the GaussianComponent constructor + decompose() (reference gmmloc/include/gmmloc/gmm/gaussian.h:30-39,
+// gmmloc/src/gmm/gaussian.cpp:36-63): cov_inv, det, eigen-decomposition (scale ascending, axis),
+// is_degenerated (scale.x < deg_eps), sqrt_info = LLT(cov_inv).L, is_salient; plus the fp32 whitening
+// table the association scan reads and the scan's rigorous error bound alpha.
+//
+// Every product / sum is an explicit round-to-nearest intrinsic so that results are reproducible to
+// the bit on any IEEE machine that evaluates the same expression trees without contraction.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace gmmloc {
+
+namespace {
+
+__device__ __forceinline__ double& E(double* a, int r, int c) { return a[r * 3 + c]; }
+__device__ __forceinline__ double E(const double* a, int r, int c) { return a[r * 3 + c]; }
+
+__device__ double cof3(const double* m, int i, int j) {
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return dsub(dmul(E(m, i1, j1), E(m, i2, j2)), dmul(E(m, i1, j2), E(m, i2, j1)));
+}
+
+// 3x3 inverse by cofactors: determinant from the first cofactor column, one reciprocal (Eigen's
+// fixed-size 3x3 inverse, which gaussian.h:31 calls).
+__device__ void inv3(const double* m, double* out) {
+  const double c00 = cof3(m, 0, 0), c10 = cof3(m, 1, 0), c20 = cof3(m, 2, 0);
+  const double det = dadd(dadd(dmul(c00, E(m, 0, 0)), dmul(c10, E(m, 1, 0))), dmul(c20, E(m, 2, 0)));
+  const double invdet = __ddiv_rn(1.0, det);
+  E(out, 0, 0) = dmul(c00, invdet);
+  E(out, 0, 1) = dmul(c10, invdet);
+  E(out, 0, 2) = dmul(c20, invdet);
+  E(out, 1, 0) = dmul(cof3(m, 0, 1), invdet);
+  E(out, 1, 1) = dmul(cof3(m, 1, 1), invdet);
+  E(out, 1, 2) = dmul(cof3(m, 2, 1), invdet);
+  E(out, 2, 0) = dmul(cof3(m, 0, 2), invdet);
+  E(out, 2, 1) = dmul(cof3(m, 1, 2), invdet);
+  E(out, 2, 2) = dmul(cof3(m, 2, 2), invdet);
+}
+
+__device__ double det3_term(const double* m, int a, int b, int c) {
+  return dmul(E(m, 0, a), dsub(dmul(E(m, 1, b), E(m, 2, c)), dmul(E(m, 1, c), E(m, 2, b))));
+}
+__device__ double det3(const double* m) {
+  return dadd(dsub(det3_term(m, 0, 1, 2), det3_term(m, 1, 0, 2)), det3_term(m, 2, 0, 1));
+}
+
+// unblocked lower Cholesky; returns false when a pivot is not positive
+__device__ bool chol3(const double* a, double* L) {
+  for (int i = 0; i < 9; ++i) L[i] = 0.0;
+  bool ok = true;
+  for (int k = 0; k < 3; ++k) {
+    double x = E(a, k, k);
+    for (int j = 0; j < k; ++j) x = dsub(x, dmul(E(L, k, j), E(L, k, j)));
+    if (!(x > 0.0)) ok = false;
+    const double d = __dsqrt_rn(x);
+    E(L, k, k) = d;
+    for (int i = k + 1; i < 3; ++i) {
+      double s = E(a, i, k);
+      for (int j = 0; j < k; ++j) s = dsub(s, dmul(E(L, i, j), E(L, k, j)));
+      E(L, i, k) = __ddiv_rn(s, d);
+    }
+  }
+  return ok;
+}
+
+// cyclic Jacobi on a symmetric 3x3 using only + - * / sqrt; eigenvalues ascending, eigenvectors in
+// the columns of `evecs`.  Stand-in for Eigen::SelfAdjointEigenSolver (gaussian.cpp:39-42).
+__device__ void jacobi3(const double* cov, double* evals, double* evecs) {
+  double a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) a[i] = cov[i];
+  E(a, 1, 0) = E(a, 0, 1);
+  E(a, 2, 0) = E(a, 0, 2);
+  E(a, 2, 1) = E(a, 1, 2);
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    const double off = dadd(dadd(fabs(E(a, 0, 1)), fabs(E(a, 0, 2))), fabs(E(a, 1, 2)));
+    if (off == 0.0) break;
+    for (int r = 0; r < 3; ++r) {
+      const int p = (r == 2) ? 1 : 0, q = (r == 0) ? 1 : 2;
+      const double apq = E(a, p, q);
+      if (apq == 0.0) continue;
+      const double app = E(a, p, p), aqq = E(a, q, q);
+      const double g = dmul(100.0, fabs(apq));
+      if (sweep > 3 && dadd(fabs(app), g) == fabs(app) && dadd(fabs(aqq), g) == fabs(aqq)) {
+        E(a, p, q) = 0.0;
+        E(a, q, p) = 0.0;
+        continue;
+      }
+      const double h = dsub(aqq, app);
+      double t;
+      if (dadd(fabs(h), g) == fabs(h)) {
+        t = __ddiv_rn(apq, h);
+      } else {
+        const double theta = __ddiv_rn(dmul(0.5, h), apq);
+        t = __ddiv_rn(1.0, dadd(fabs(theta), __dsqrt_rn(dadd(1.0, dmul(theta, theta)))));
+        if (theta < 0.0) t = -t;
+      }
+      const double c = __ddiv_rn(1.0, __dsqrt_rn(dadd(1.0, dmul(t, t))));
+      const double s = dmul(t, c);
+      const double tau = __ddiv_rn(s, dadd(1.0, c));
+      E(a, p, p) = dsub(app, dmul(t, apq));
+      E(a, q, q) = dadd(aqq, dmul(t, apq));
+      E(a, p, q) = 0.0;
+      E(a, q, p) = 0.0;
+      const int k = 3 - p - q;
+      const double akp = E(a, k, p), akq = E(a, k, q);
+      const double nkp = dsub(akp, dmul(s, dadd(akq, dmul(akp, tau))));
+      const double nkq = dadd(akq, dmul(s, dsub(akp, dmul(akq, tau))));
+      E(a, k, p) = nkp;
+      E(a, p, k) = nkp;
+      E(a, k, q) = nkq;
+      E(a, q, k) = nkq;
+      for (int i = 0; i < 3; ++i) {
+        const double vip = E(v, i, p), viq = E(v, i, q);
+        E(v, i, p) = dsub(vip, dmul(s, dadd(viq, dmul(vip, tau))));
+        E(v, i, q) = dadd(viq, dmul(s, dsub(vip, dmul(viq, tau))));
+      }
+    }
+  }
+  int idx[3] = {0, 1, 2};
+  const double d[3] = {E(a, 0, 0), E(a, 1, 1), E(a, 2, 2)};
+  for (int i = 1; i < 3; ++i)
+    for (int j = i; j > 0 && d[idx[j]] < d[idx[j - 1]]; --j) {
+      const int t = idx[j];
+      idx[j] = idx[j - 1];
+      idx[j - 1] = t;
+    }
+  for (int c = 0; c < 3; ++c) {
+    evals[c] = d[idx[c]];
+    for (int r = 0; r < 3; ++r) E(evecs, r, c) = E(v, r, idx[c]);
+  }
+}
+
+__global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps, double xmax, int* err_flag,
+                                                        unsigned int* alpha_bits) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= m.Kpad) return;
+  float* sp = m.scan + (size_t)k * kScanFloats;
+  if (k >= m.K) {  // padding rows score +inf and can never win
+    for (int i = 0; i < kScanFloats; ++i) sp[i] = 0.f;
+    sp[6] = -CUDART_INF_F;
+    return;
+  }
+  double cov[9], ci[9], L[9], ev[3], ax[9];
+  for (int i = 0; i < 9; ++i) cov[i] = m.cov[(size_t)k * 9 + i];
+  const double mu[3] = {m.mean[(size_t)k * 3], m.mean[(size_t)k * 3 + 1], m.mean[(size_t)k * 3 + 2]};
+  inv3(cov, ci);
+  const double det = det3(cov);
+  jacobi3(cov, ev, ax);
+  const bool ok_l = chol3(ci, L);
+  bool ok = ok_l && (det > 0.0) && (ev[0] > 0.0);
+  for (int i = 0; i < 9; ++i) ok = ok && isfinite(ci[i]) && isfinite(L[i]);
+  for (int i = 0; i < 3; ++i) ok = ok && isfinite(mu[i]);
+  for (int i = 0; i < 9; ++i) {
+    m.cov_inv[(size_t)k * 9 + i] = ci[i];
+    m.axis[(size_t)k * 9 + i] = ax[i];
+    m.sqrt_info[(size_t)k * 9 + i] = L[i];
+  }
+  for (int i = 0; i < 3; ++i) m.scale[(size_t)k * 3 + i] = ev[i];
+  m.det[k] = det;
+  m.is_deg[k] = ev[0] < deg_eps;                // gaussian.cpp:44
+  m.is_sal[k] = (ev[1] > 0.2 && ev[2] > 0.2);   // gaussian.cpp:50-55
+  if (!ok) {
+    atomicOr(err_flag, 1);
+    for (int i = 0; i < kScanFloats; ++i) sp[i] = 0.f;
+    sp[6] = -CUDART_INF_F;
+    return;
+  }
+  // fp32 whitening rows U = L^T, c = U mu
+  const double U[6] = {E(L, 0, 0), E(L, 1, 0), E(L, 2, 0), E(L, 1, 1), E(L, 2, 1), E(L, 2, 2)};
+  const double c0 = U[0] * mu[0] + U[1] * mu[1] + U[2] * mu[2];
+  const double c1 = U[3] * mu[1] + U[4] * mu[2];
+  const double c2 = U[5] * mu[2];
+  for (int i = 0; i < 6; ++i) sp[i] = (float)U[i];
+  sp[6] = (float)(-c0);
+  sp[7] = (float)(-c1);
+  sp[8] = (float)(-c2);
+  // error bound: |sqrt(score32) - d_exact| <= alpha_k for |x|_inf <= xmax,
+  // alpha_k = (6 u32 + sqrt(64 u64)) * | |U| 1 (xmax + |mu|_inf) |_2
+  const double mmax = fmax(fabs(mu[0]), fmax(fabs(mu[1]), fabs(mu[2])));
+  const double ext = xmax + mmax;
+  const double a0 = (fabs(U[0]) + fabs(U[1]) + fabs(U[2])) * ext;
+  const double a1 = (fabs(U[3]) + fabs(U[4])) * ext;
+  const double a2 = fabs(U[5]) * ext;
+  const double A = sqrt(a0 * a0 + a1 * a1 + a2 * a2);
+  const double u32 = 5.9604644775390625e-08, u64 = 1.1102230246251565e-16;
+  const double alpha = (6.0 * u32 + sqrt(64.0 * u64)) * A;
+  float af = (float)alpha;
+  if ((double)af < alpha) af = nextafterf(af, CUDART_INF_F);
+  atomicMax(alpha_bits, __float_as_uint(af));  // non-negative floats order like their bit patterns
+}
+
+}  // namespace
+
+cudaError_t launch_map_build(const MapDev& m, double deg_eps, double xmax, int* d_err, unsigned int* d_alpha_bits,
+                             cudaStream_t stream) {
+  const int threads = 128;
+  const int blocks = (m.Kpad + threads - 1) / threads;
+  map_build_kernel<<<blocks, threads, 0, stream>>>(m, deg_eps, xmax, d_err, d_alpha_bits);
+  return cudaGetLastError();
+}
+
+}  // namespace gmmloc

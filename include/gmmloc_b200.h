@@ -1,0 +1,163 @@
+/*
+ * gmmloc_b200.h — C ABI of the B200-native GMMLoc hot path (GMM map association + the
+ * structure-constrained Gauss-Newton pose/point solve it feeds).
+ *
+ * The reference (HyHuang1995/gmmloc @ 08eb281) has no plugin / FFI interface: callers use C++ member
+ * functions on heap objects.  Each entry point below names the reference member(s) it replaces
+ * (paths relative to the reference root); include/gmmloc_b200.hpp is the header-only C++ shim that
+ * restores the reference's own method names on top of this ABI.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no exceptions cross the ABI; every call returns gmmloc_status_t.
+ *  - pose = 7 doubles  qx qy qz qw tx ty tz  of T_cw (world -> camera), g2o::SE3Quat order.
+ *  - landmarks / observations are fp32 (coalesced HBM reads), poses and map constants fp64.
+ *  - "host" entry points take host pointers (pinned or pageable) and copy inside the call;
+ *    "_async" entry points take DEVICE pointers and only enqueue work on the context's stream.
+ *  - a gmmloc_map_t is immutable and may be shared by any number of contexts / host threads; a
+ *    gmmloc_ctx_t (stream + workspaces) must be used by one host thread at a time (the reference's
+ *    tracking thread and localisation thread each own one).
+ *  - there is no CPU fallback: without a CUDA device every call fails with GMMLOC_ECUDA.
+ */
+#ifndef GMMLOC_B200_H_
+#define GMMLOC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gmmloc_map gmmloc_map_t;
+typedef struct gmmloc_ctx gmmloc_ctx_t;
+
+typedef enum {
+  GMMLOC_OK = 0,
+  GMMLOC_EINVAL = 1,   /* bad argument (NULL, negative size, non-SPD covariance ...)            */
+  GMMLOC_ENOMEM = 2,   /* host or device allocation failed                                      */
+  GMMLOC_ECUDA = 3,    /* CUDA runtime error / no device (see gmmloc_last_error)                */
+  GMMLOC_ENUMERIC = 4, /* reserved: batch-level numeric failure (per-frame failures use status) */
+  GMMLOC_EIO = 5       /* .gmm file could not be read / written / parsed                        */
+} gmmloc_status_t;
+
+/* gmmloc_ros/cfg/v1.yaml:5-17 (camera::fx ... camera::bf, width, height) */
+typedef struct {
+  double fx, fy, cx, cy, bf;
+  int32_t width, height;
+} gmmloc_camera_t;
+
+/* Hot-path parameters; defaults (gmmloc_default_params) are the shipped yaml / literals:
+ *  tri_lambda2 400, ba_lambda2 400, tri_str_thresh 0.0064f, tri_check_str_chi2 1 (v1.yaml:32-37),
+ *  mdist2_gate 9.0 (gmmloc_opt.cpp:230), chi2_mono 5.991, chi2_stereo 7.815, gn_iters 10
+ *  (tracking_opt.cpp:145-147), robust 0, factor_mode 0. */
+typedef struct {
+  double tri_lambda2;
+  double ba_lambda2;
+  double tri_str_thresh;
+  int32_t tri_check_str_chi2;
+  double mdist2_gate;
+  double chi2_mono;
+  double chi2_stereo;
+  int32_t gn_iters;
+  int32_t robust;      /* Huber on reprojection edges (localization_opt.cpp:716,746) */
+  int32_t factor_mode; /* GMMLOC_MODE_* */
+} gmmloc_params_t;
+
+enum { GMMLOC_MODE_JOINT = 0, GMMLOC_MODE_POSE_ONLY = 1, GMMLOC_MODE_POINTS_ONLY = 2 };
+
+/* per-frame status bits written by gmmloc_frames_solve */
+enum { GMMLOC_FRAME_NUMERIC = 1 /* singular Hll / reduced system or non-finite value: frame frozen */ };
+
+/* counters of the last association on a context (evidence for the exact re-rank path) */
+typedef struct {
+  int64_t points;        /* points scanned                                              */
+  int64_t flagged;       /* points whose fp32 top-2 gap was inside the error bound      */
+  int64_t kernel_launches; /* kernels launched by this context since creation           */
+} gmmloc_stats_t;
+
+const char* gmmloc_version(void);
+const char* gmmloc_status_string(gmmloc_status_t s);
+/* last CUDA / IO error text of the calling thread ("" if none) */
+const char* gmmloc_last_error(void);
+void gmmloc_default_params(gmmloc_params_t* p);
+/* frame::sigma2_inv[octave] exactly as the reference computes it in float (init_config.hpp:63-78) */
+float gmmloc_sigma2_inv(int octave);
+
+/* ---- map: replaces GMMUtility::loadGMMModel + GaussianComponent ctor/decompose + GMM ctor ------
+ * gmm_utils.cpp:9-67, gaussian.h:30-39, gaussian.cpp:36-63.  mean K x 3, cov K x 9 row-major (fp64).
+ * All per-component constants (cov_inv, det, eigen-decomposition, is_degenerated, sqrt_info and the
+ * fp32 whitening rows used by the scan) are computed on the device. */
+gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, double deg_eps, int device,
+                                  gmmloc_map_t** out);
+/* .gmm wire format: protobuf_utils.cpp:12-80, GMM.proto:5-14 */
+gmmloc_status_t gmmloc_map_load_gmm(const char* path, double deg_eps, int device, gmmloc_map_t** out);
+/* GMMUtility::saveGMMModel, gmm_utils.cpp:69-119 (same byte stream) */
+gmmloc_status_t gmmloc_map_save_gmm(const gmmloc_map_t* map, const char* path);
+void gmmloc_map_destroy(gmmloc_map_t* map);
+/* GMM::countComponents, gaussian_mixture.h:153 */
+int gmmloc_map_size(const gmmloc_map_t* map);
+int gmmloc_map_device(const gmmloc_map_t* map);
+/* Device-built constants back to the host (any pointer may be NULL). Shapes: mean K x 3, cov K x 9,
+ * cov_inv K x 9, det K, scale K x 3 (ascending), axis K x 9 (axis[r*3+c] = component r of eigenvector c),
+ * sqrt_info K x 9 (lower L, cov_inv = L L^T), is_degenerated K, is_salient K.
+ * ≙ GaussianComponent public fields, gaussian.h:69-90. */
+gmmloc_status_t gmmloc_map_get_components(const gmmloc_map_t* map, double* mean, double* cov, double* cov_inv,
+                                          double* det, double* scale, double* axis, double* sqrt_info,
+                                          uint8_t* is_degenerated, uint8_t* is_salient);
+/* error bound of the fp32 scan in whitened units (|sqrt(s32) - sqrt(d2)| <= alpha for |x|_inf <= xmax) */
+gmmloc_status_t gmmloc_map_scan_bound(const gmmloc_map_t* map, double* alpha, double* xmax);
+
+/* ---- context ------------------------------------------------------------------------------- */
+gmmloc_status_t gmmloc_ctx_create(int device, gmmloc_ctx_t** out);
+void gmmloc_ctx_destroy(gmmloc_ctx_t* ctx);
+/* cudaStream_t of the context (for event timing / interop) */
+void* gmmloc_ctx_stream(gmmloc_ctx_t* ctx);
+gmmloc_status_t gmmloc_ctx_synchronize(gmmloc_ctx_t* ctx);
+gmmloc_status_t gmmloc_ctx_stats(gmmloc_ctx_t* ctx, gmmloc_stats_t* out);
+
+/* page-locked host memory for the host entry points (pageable buffers also work, via staging) */
+gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out);
+void gmmloc_host_free(void* p);
+
+/* ---- association: replaces GaussianComponent::chi2 / MDist2 scanned over all components with the
+ * reference's argmin convention (gaussian.cpp:65-70, gaussian.h:53-56; strict '<' ascending scan =>
+ * lowest index wins ties, gmmloc_opt.cpp:175-197,209-217).  M = B*N points.
+ *  assign[i] = argmin_k d2_k(x_i)   (exact: identical to an fp64 scan), or -1 iff gate > 0 and the
+ *  best d2 > gate (gmmloc_opt.cpp:230).  d2 (optional) = (float) of the fp64 d2 of the winner. */
+gmmloc_status_t gmmloc_associate(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const float* pts_w, int B, int N,
+                                 double gate, int32_t* assign, float* d2);
+gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const float* d_pts_w,
+                                       int64_t M, double gate, int32_t* d_assign, float* d_d2);
+
+/* ---- frame solve: association + single-free-pose specialisation of Localization::jointOptimization
+ * (localization_opt.cpp:456-925; edges EdgeStereoSE3ProjectXYZ / EdgeSE3ProjectXYZ + EdgePt2GaussianDeg /
+ * EdgePt2Gaussian, factors.cpp:5-17,55-64) run with Gauss-Newton for params->gn_iters iterations;
+ * factor_mode POSE_ONLY gives Tracking::optimizeCurrentPose's system (tracking_opt.cpp:21-217),
+ * POINTS_ONLY the per-point structure-constrained solves.  B independent frames of N landmarks.
+ *  pose0 B x 7, pts_w B x N x 3, obs B x N x 3 (u v u_r; u_r < 0 => monocular), octave B x N.
+ *  outputs: pose_out B x 7, pts_out B x N x 3 (optional), assign B x N, outlier B x N (optional),
+ *  status B (GMMLOC_FRAME_* bits). */
+gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                    const gmmloc_params_t* params, const double* pose0, const float* pts_w,
+                                    const float* obs, const uint8_t* octave, int B, int N, double* pose_out,
+                                    float* pts_out, int32_t* assign, uint8_t* outlier, int32_t* status);
+gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                          const gmmloc_params_t* params, const double* d_pose0,
+                                          const float* d_pts_w, const float* d_obs, const uint8_t* d_octave,
+                                          int B, int N, double* d_pose_out, float* d_pts_out, int32_t* d_assign,
+                                          uint8_t* d_outlier, int32_t* d_status);
+
+/* ---- batched point solves: replaces GMMLoc::optimizePoint (gmmloc_opt.cpp:260-342), M independent
+ * 3-DoF GN problems (one stereo reprojection edge + one point-to-plane edge), `iters` iterations (5).
+ *  x0 M x 3 (fp64), obs M x 3 (u v u_r), octave M, pose M x 7, comp M (component index), proj_z2 M.
+ *  outputs: pt_est M x 3, chi2_proj M, chi2_str M, res M (1 = accepted). */
+gmmloc_status_t gmmloc_points_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                    const gmmloc_params_t* params, const double* x0, const float* obs,
+                                    const uint8_t* octave, const double* pose, const int32_t* comp,
+                                    const double* proj_z2, int M, int iters, double* pt_est, double* chi2_proj,
+                                    double* chi2_str, uint8_t* res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GMMLOC_B200_H_ */

@@ -1,0 +1,855 @@
+// gmmloc_oracle.cpp — CPU ORACLE (test infrastructure, NOT product code; see gmmloc_oracle.h).
+//
+// Plain C++17, fp64, no dependencies.  Compile with -ffp-contract=off so every a*b+c below is two
+// IEEE roundings, exactly as written (the GPU fp64 re-rank replays the same operation order).
+// Citations are relative to /root/reference/.  g2o / Eigen arithmetic is restated from their
+// published algorithms (SURVEY.md Appx B): parity unpinned.
+#include "gmmloc_oracle.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <thread>
+#include <vector>
+
+namespace {
+
+// ----------------------------------------------------------------------------------------------
+// small dense helpers (row-major 3x3)
+// ----------------------------------------------------------------------------------------------
+inline double& M(double* a, int r, int c) { return a[r * 3 + c]; }
+inline double M(const double* a, int r, int c) { return a[r * 3 + c]; }
+
+// Eigen's fixed-size 3x3 determinant (Determinant.h, bruteforce_det3_helper):
+//   det = h(0,1,2) - h(1,0,2) + h(2,0,1),  h(a,b,c) = m(0,a) * (m(1,b) m(2,c) - m(1,c) m(2,b))
+inline double det3_helper(const double* m, int a, int b, int c) {
+  return M(m, 0, a) * (M(m, 1, b) * M(m, 2, c) - M(m, 1, c) * M(m, 2, b));
+}
+inline double det3(const double* m) { return det3_helper(m, 0, 1, 2) - det3_helper(m, 1, 0, 2) + det3_helper(m, 2, 0, 1); }
+
+// Eigen's fixed-size 3x3 inverse (InverseImpl.h, compute_inverse<.,.,3>): cofactors, det from the
+// first cofactor column, one reciprocal, nine products.
+inline double cofactor3(const double* m, int i, int j) {
+  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+  return M(m, i1, j1) * M(m, i2, j2) - M(m, i1, j2) * M(m, i2, j1);
+}
+inline bool inverse3(const double* m, double* out, double* det_out = nullptr) {
+  const double c00 = cofactor3(m, 0, 0), c10 = cofactor3(m, 1, 0), c20 = cofactor3(m, 2, 0);
+  const double det = (c00 * M(m, 0, 0) + c10 * M(m, 1, 0)) + c20 * M(m, 2, 0);
+  if (det_out) *det_out = det;
+  const double invdet = 1.0 / det;
+  M(out, 0, 0) = c00 * invdet;
+  M(out, 0, 1) = c10 * invdet;
+  M(out, 0, 2) = c20 * invdet;
+  M(out, 1, 0) = cofactor3(m, 0, 1) * invdet;
+  M(out, 1, 1) = cofactor3(m, 1, 1) * invdet;
+  M(out, 1, 2) = cofactor3(m, 2, 1) * invdet;
+  M(out, 2, 0) = cofactor3(m, 0, 2) * invdet;
+  M(out, 2, 1) = cofactor3(m, 1, 2) * invdet;
+  M(out, 2, 2) = cofactor3(m, 2, 2) * invdet;
+  return std::isfinite(invdet) && det != 0.0;
+}
+
+// Unblocked lower Cholesky of a 3x3 SPD matrix (Eigen LLT llt_inplace::unblocked order).
+inline bool llt3(const double* a, double* L) {
+  for (int i = 0; i < 9; ++i) L[i] = 0.0;
+  bool ok = true;
+  for (int k = 0; k < 3; ++k) {
+    double x = M(a, k, k);
+    for (int j = 0; j < k; ++j) x -= M(L, k, j) * M(L, k, j);
+    if (!(x > 0.0)) ok = false;
+    const double d = std::sqrt(x);
+    M(L, k, k) = d;
+    for (int i = k + 1; i < 3; ++i) {
+      double s = M(a, i, k);
+      for (int j = 0; j < k; ++j) s -= M(L, i, j) * M(L, k, j);
+      M(L, i, k) = s / d;
+    }
+  }
+  return ok;
+}
+
+// Cyclic Jacobi eigen-decomposition of a symmetric 3x3 (only + - * / sqrt so that a GPU replay is
+// bit-identical).  Stand-in for Eigen::SelfAdjointEigenSolver<Matrix3d> (gaussian.cpp:39-42): the
+// eigenvalues agree to rounding, eigenvector signs are arbitrary in both.  Output ascending.
+void eig3_jacobi(const double* cov, double* evals, double* evecs /* evecs[r*3+c]: column c */) {
+  double a[9], v[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  for (int i = 0; i < 9; ++i) a[i] = cov[i];
+  // symmetrise from the upper triangle (the loader keeps Σ as stored; asymmetry ≤ 6e-17 in shipped maps)
+  M(a, 1, 0) = M(a, 0, 1); M(a, 2, 0) = M(a, 0, 2); M(a, 2, 1) = M(a, 1, 2);
+  const int P[3] = {0, 0, 1}, Q[3] = {1, 2, 2};
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    const double off = std::fabs(M(a, 0, 1)) + std::fabs(M(a, 0, 2)) + std::fabs(M(a, 1, 2));
+    if (off == 0.0) break;
+    for (int r = 0; r < 3; ++r) {
+      const int p = P[r], q = Q[r];
+      const double apq = M(a, p, q);
+      if (apq == 0.0) continue;
+      const double app = M(a, p, p), aqq = M(a, q, q);
+      const double g = 100.0 * std::fabs(apq);
+      // after a few sweeps drop off-diagonals that no longer change the diagonal at fp64 precision
+      if (sweep > 3 && std::fabs(app) + g == std::fabs(app) && std::fabs(aqq) + g == std::fabs(aqq)) {
+        M(a, p, q) = 0.0; M(a, q, p) = 0.0;
+        continue;
+      }
+      const double h = aqq - app;
+      double t;
+      if (std::fabs(h) + g == std::fabs(h)) {
+        t = apq / h;
+      } else {
+        const double theta = 0.5 * h / apq;
+        t = 1.0 / (std::fabs(theta) + std::sqrt(1.0 + theta * theta));
+        if (theta < 0.0) t = -t;
+      }
+      const double c = 1.0 / std::sqrt(1.0 + t * t);
+      const double s = t * c;
+      const double tau = s / (1.0 + c);
+      M(a, p, p) = app - t * apq;
+      M(a, q, q) = aqq + t * apq;
+      M(a, p, q) = 0.0; M(a, q, p) = 0.0;
+      const int k = 3 - p - q;  // the remaining index
+      const double akp = M(a, k, p), akq = M(a, k, q);
+      const double nkp = akp - s * (akq + akp * tau);
+      const double nkq = akq + s * (akp - akq * tau);
+      M(a, k, p) = nkp; M(a, p, k) = nkp;
+      M(a, k, q) = nkq; M(a, q, k) = nkq;
+      for (int i = 0; i < 3; ++i) {
+        const double vip = M(v, i, p), viq = M(v, i, q);
+        M(v, i, p) = vip - s * (viq + vip * tau);
+        M(v, i, q) = viq + s * (vip - viq * tau);
+      }
+    }
+  }
+  int idx[3] = {0, 1, 2};
+  double d[3] = {M(a, 0, 0), M(a, 1, 1), M(a, 2, 2)};
+  // stable 3-element insertion sort ascending
+  for (int i = 1; i < 3; ++i)
+    for (int j = i; j > 0 && d[idx[j]] < d[idx[j - 1]]; --j) std::swap(idx[j], idx[j - 1]);
+  for (int c = 0; c < 3; ++c) {
+    evals[c] = d[idx[c]];
+    for (int r = 0; r < 3; ++r) M(evecs, r, c) = M(v, r, idx[c]);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// SE3 (g2o SE3Quat semantics, SURVEY Appx B.1).  pose = qx qy qz qw tx ty tz
+// ----------------------------------------------------------------------------------------------
+void quat_normalize(double q[4]) {
+  // g2o SE3Quat::normalizeRotation: flip to w >= 0, then normalise
+  if (q[3] < 0) for (int i = 0; i < 4; ++i) q[i] = -q[i];
+  const double n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; ++i) q[i] /= n;
+}
+void quat_to_rot(const double q[4], double R[9]) {
+  // Eigen QuaternionBase::toRotationMatrix
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  M(R, 0, 0) = 1 - (tyy + tzz); M(R, 0, 1) = txy - twz;       M(R, 0, 2) = txz + twy;
+  M(R, 1, 0) = txy + twz;       M(R, 1, 1) = 1 - (txx + tzz); M(R, 1, 2) = tyz - twx;
+  M(R, 2, 0) = txz - twy;       M(R, 2, 1) = tyz + twx;       M(R, 2, 2) = 1 - (txx + tyy);
+}
+void rot_to_quat(const double R[9], double q[4]) {
+  // Eigen quaternionbase_assign_impl<Matrix3>: Shepperd's method
+  double t = M(R, 0, 0) + M(R, 1, 1) + M(R, 2, 2);
+  if (t > 0) {
+    t = std::sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (M(R, 2, 1) - M(R, 1, 2)) * t;
+    q[1] = (M(R, 0, 2) - M(R, 2, 0)) * t;
+    q[2] = (M(R, 1, 0) - M(R, 0, 1)) * t;
+  } else {
+    int i = 0;
+    if (M(R, 1, 1) > M(R, 0, 0)) i = 1;
+    if (M(R, 2, 2) > M(R, i, i)) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(M(R, i, i) - M(R, j, j) - M(R, k, k) + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (M(R, k, j) - M(R, j, k)) * t;
+    q[j] = (M(R, j, i) + M(R, i, j)) * t;
+    q[k] = (M(R, k, i) + M(R, i, k)) * t;
+  }
+}
+void quat_mul(const double a[4], const double b[4], double o[4]) {
+  const double ax = a[0], ay = a[1], az = a[2], aw = a[3], bx = b[0], by = b[1], bz = b[2], bw = b[3];
+  o[3] = aw * bw - ax * bx - ay * by - az * bz;
+  o[0] = aw * bx + ax * bw + ay * bz - az * by;
+  o[1] = aw * by + ay * bw + az * bx - ax * bz;
+  o[2] = aw * bz + az * bw + ax * by - ay * bx;
+}
+inline void mat3_vec(const double* A, const double* x, double* y) {
+  for (int r = 0; r < 3; ++r) y[r] = (M(A, r, 0) * x[0] + M(A, r, 1) * x[1]) + M(A, r, 2) * x[2];
+}
+void se3_exp_Rt(const double xi[6], double R[9], double t[3]) {
+  const double w[3] = {xi[0], xi[1], xi[2]}, u[3] = {xi[3], xi[4], xi[5]};
+  const double theta = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+  const double Om[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double Om2[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) M(Om2, r, c) = (M(Om, r, 0) * M(Om, 0, c) + M(Om, r, 1) * M(Om, 1, c)) + M(Om, r, 2) * M(Om, 2, c);
+  double a, b, c2, d;
+  if (theta < 1e-5) {  // series (newer g2o se3quat.h small-angle branch)
+    a = 1.0; b = 0.5; c2 = 0.5; d = 1.0 / 6.0;
+  } else {
+    a = std::sin(theta) / theta;
+    b = (1 - std::cos(theta)) / (theta * theta);
+    c2 = b;
+    d = (theta - std::sin(theta)) / (theta * theta * theta);
+  }
+  double V[9];
+  for (int i = 0; i < 9; ++i) {
+    const double I = (i % 4 == 0) ? 1.0 : 0.0;
+    R[i] = I + a * Om[i] + b * Om2[i];
+    V[i] = I + c2 * Om[i] + d * Om2[i];
+  }
+  mat3_vec(V, u, t);
+}
+void se3_oplus(const double xi[6], const double pose[7], double out[7]) {
+  // VertexSE3Expmap::oplusImpl: estimate <- exp(update) * estimate;   SE3Quat::operator*:
+  // t = t1 + r1 * t2 ; r = r1 * r2 ; normalizeRotation
+  double R[9], t[3], qd[4], q[4];
+  se3_exp_Rt(xi, R, t);
+  rot_to_quat(R, qd);
+  quat_normalize(qd);
+  double Rd[9];
+  quat_to_rot(qd, Rd);
+  double rt[3];
+  mat3_vec(Rd, pose + 4, rt);
+  quat_mul(qd, pose, q);
+  quat_normalize(q);
+  for (int i = 0; i < 4; ++i) out[i] = q[i];
+  for (int i = 0; i < 3; ++i) out[4 + i] = t[i] + rt[i];
+}
+
+// ----------------------------------------------------------------------------------------------
+// frame::sigma2_inv in float (init_config.hpp:63-78, config.cpp:53-55)
+// ----------------------------------------------------------------------------------------------
+struct Sigma2Inv {
+  float v[8];
+  Sigma2Inv() {
+    float sf = 1.0f;
+    v[0] = 1.0f;
+    const float scale_factor = 1.2f;
+    for (int i = 1; i < 8; ++i) {
+      sf = sf * scale_factor;
+      const float s2 = sf * sf;
+      v[i] = 1.0f / s2;
+    }
+  }
+};
+const Sigma2Inv g_sigma2inv;
+
+// ----------------------------------------------------------------------------------------------
+// edges
+// ----------------------------------------------------------------------------------------------
+struct Cam { double fx, fy, cx, cy, bf; };
+
+// reprojection residual + Jacobians at camera-frame point pc = R x + t.
+//  stereo: EdgeStereoSE3ProjectXYZ  (point Jacobian identical to factors.cpp:133-168)
+//  mono:   EdgeSE3ProjectXYZ        (point Jacobian identical to factors.cpp:84-107)
+// Jl[m][3] point Jacobian, Jp[m][6] pose Jacobian ([omega; upsilon], SURVEY Appx B.2), e[m].
+inline void reproj_edge(const Cam& cam, const double* R, const double pc[3], const double obs[3], bool stereo,
+                        double e[3], double Jl[9], double Jp[18]) {
+  const double x = pc[0], y = pc[1], z = pc[2];
+  const double z_2 = z * z;
+  if (stereo) {
+    const double invz = 1.0 / z;  // factors.cpp:117 (float literal, double division)
+    const double u = x * invz * cam.fx + cam.cx;
+    const double v = y * invz * cam.fy + cam.cy;
+    const double ur = u - cam.bf * invz;
+    e[0] = obs[0] - u; e[1] = obs[1] - v; e[2] = obs[2] - ur;
+  } else {
+    const double u = x / z * cam.fx + cam.cx;  // project2d then scale (factors.cpp:66-74)
+    const double v = y / z * cam.fy + cam.cy;
+    e[0] = obs[0] - u; e[1] = obs[1] - v; e[2] = 0.0;
+  }
+  if (Jl) {
+    for (int j = 0; j < 3; ++j) {
+      Jl[0 * 3 + j] = -cam.fx * M(R, 0, j) / z + cam.fx * x * M(R, 2, j) / z_2;
+      Jl[1 * 3 + j] = -cam.fy * M(R, 1, j) / z + cam.fy * y * M(R, 2, j) / z_2;
+      Jl[2 * 3 + j] = stereo ? Jl[0 * 3 + j] - cam.bf * M(R, 2, j) / z_2 : 0.0;
+    }
+  }
+  if (Jp) {
+    Jp[0] = x * y / z_2 * cam.fx;
+    Jp[1] = -(1 + (x * x / z_2)) * cam.fx;
+    Jp[2] = y / z * cam.fx;
+    Jp[3] = -1. / z * cam.fx;
+    Jp[4] = 0;
+    Jp[5] = x / z_2 * cam.fx;
+    Jp[6] = (1 + y * y / z_2) * cam.fy;
+    Jp[7] = -x * y / z_2 * cam.fy;
+    Jp[8] = -x / z * cam.fy;
+    Jp[9] = 0;
+    Jp[10] = -1. / z * cam.fy;
+    Jp[11] = y / z_2 * cam.fy;
+    if (stereo) {
+      Jp[12] = Jp[0] - cam.bf * y / z_2;
+      Jp[13] = Jp[1] + cam.bf * x / z_2;
+      Jp[14] = Jp[2];
+      Jp[15] = Jp[3];
+      Jp[16] = 0;
+      Jp[17] = Jp[5] - cam.bf / z_2;
+    } else {
+      for (int j = 12; j < 18; ++j) Jp[j] = 0;
+    }
+  }
+}
+
+// g2o RobustKernelHuber::robustify -> rho1 (SURVEY Appx B.4); delta stored as float in the callers
+inline double huber_rho1(double e2, double delta) {
+  const double dsqr = delta * delta;
+  if (e2 <= dsqr) return 1.0;
+  return delta / std::sqrt(e2);
+}
+
+// 6x6 SPD solve, plain Cholesky (stand-in for g2o LinearSolverEigen / LinearSolverDense on the
+// reduced pose system, SURVEY Appx B.8).
+bool solve6(const double H[36], const double b[6], double x[6]) {
+  double L[36] = {0};
+  for (int k = 0; k < 6; ++k) {
+    double s = H[k * 6 + k];
+    for (int j = 0; j < k; ++j) s -= L[k * 6 + j] * L[k * 6 + j];
+    if (!(s > 0.0) || !std::isfinite(s)) return false;
+    const double d = std::sqrt(s);
+    L[k * 6 + k] = d;
+    for (int i = k + 1; i < 6; ++i) {
+      double t = H[i * 6 + k];
+      for (int j = 0; j < k; ++j) t -= L[i * 6 + j] * L[k * 6 + j];
+      L[i * 6 + k] = t / d;
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; ++i) {
+    double t = b[i];
+    for (int j = 0; j < i; ++j) t -= L[i * 6 + j] * y[j];
+    y[i] = t / L[i * 6 + i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    double t = y[i];
+    for (int j = i + 1; j < 6; ++j) t -= L[j * 6 + i] * x[j];
+    x[i] = t / L[i * 6 + i];
+  }
+  for (int i = 0; i < 6; ++i)
+    if (!std::isfinite(x[i])) return false;
+  return true;
+}
+
+template <class F>
+void parallel_for(int64_t n, int nthreads, F f) {
+  if (nthreads <= 1 || n <= 1) {
+    f(0, n, 0);
+    return;
+  }
+  nthreads = (int)std::min<int64_t>(nthreads, n);
+  std::vector<std::thread> th;
+  const int64_t chunk = (n + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; ++t) {
+    const int64_t lo = t * chunk, hi = std::min<int64_t>(n, lo + chunk);
+    if (lo >= hi) break;
+    th.emplace_back([=] { f(lo, hi, t); });
+  }
+  for (auto& x : th) x.join();
+}
+
+}  // namespace
+
+extern "C" {
+
+void oracle_default_params(oracle_params_t* p) {
+  p->tri_lambda2 = 400.0;
+  p->ba_lambda2 = 400.0;
+  p->tri_str_thresh = (double)0.0064f;  // loc::tri_str_thresh is a float (config.h / config.cpp:88)
+  p->tri_check_str_chi2 = 1;
+  p->mdist2_gate = 9.0;
+  p->chi2_mono = 5.991;
+  p->chi2_stereo = 7.815;
+  p->gn_iters = 10;
+  p->robust = 0;
+  p->factor_mode = 0;
+}
+
+double oracle_sigma2_inv(int octave) {
+  if (octave < 0) octave = 0;
+  if (octave > 7) octave = 7;
+  return (double)g_sigma2inv.v[octave];
+}
+
+void oracle_map_build(const double* mean, const double* cov, int K, double deg_eps, oracle_comp_t* out) {
+  for (int k = 0; k < K; ++k) {
+    oracle_comp_t& c = out[k];
+    for (int i = 0; i < 3; ++i) c.mean[i] = mean[k * 3 + i];
+    for (int i = 0; i < 9; ++i) c.cov[i] = cov[k * 9 + i];
+    inverse3(c.cov, c.cov_inv);   // gaussian.h:31
+    c.det = det3(c.cov);          // gaussian.h:33
+    eig3_jacobi(c.cov, c.scale, c.axis);       // gaussian.cpp:39-42
+    c.is_degenerated = c.scale[0] < deg_eps;   // gaussian.cpp:44
+    llt3(c.cov_inv, c.sqrt_info);              // gaussian.cpp:49
+    c.is_salient = (c.scale[1] > 0.2 && c.scale[2] > 0.2);  // gaussian.cpp:50-55
+  }
+}
+
+double oracle_chi2(const oracle_comp_t* c, const double x[3]) {
+  // gaussian.cpp:65-70: delta^T * cov_inv * delta, evaluated (delta^T A) then (.) delta, left to right
+  const double d0 = x[0] - c->mean[0], d1 = x[1] - c->mean[1], d2 = x[2] - c->mean[2];
+  const double* A = c->cov_inv;
+  const double r0 = (d0 * A[0] + d1 * A[3]) + d2 * A[6];
+  const double r1 = (d0 * A[1] + d1 * A[4]) + d2 * A[7];
+  const double r2 = (d0 * A[2] + d1 * A[5]) + d2 * A[8];
+  return (r0 * d0 + r1 * d1) + r2 * d2;
+}
+
+void oracle_associate(const oracle_comp_t* comps, int K, const float* pts, int64_t Mpts, double gate,
+                      int32_t* assign, double* d2_out, int nthreads) {
+  // SoA copy so the k loop vectorises; per-k operation order is exactly oracle_chi2's.
+  std::vector<double> mu(3 * (size_t)K), A(9 * (size_t)K);
+  for (int k = 0; k < K; ++k) {
+    for (int i = 0; i < 3; ++i) mu[(size_t)i * K + k] = comps[k].mean[i];
+    for (int i = 0; i < 9; ++i) A[(size_t)i * K + k] = comps[k].cov_inv[i];
+  }
+  const double* m0 = mu.data(); const double* m1 = m0 + K; const double* m2 = m1 + K;
+  const double* a[9];
+  for (int i = 0; i < 9; ++i) a[i] = A.data() + (size_t)i * K;
+  parallel_for(Mpts, nthreads, [&](int64_t lo, int64_t hi, int) {
+    std::vector<double> buf(K);
+    double* s = buf.data();
+    for (int64_t p = lo; p < hi; ++p) {
+      const double x0 = (double)pts[p * 3 + 0], x1 = (double)pts[p * 3 + 1], x2 = (double)pts[p * 3 + 2];
+      for (int k = 0; k < K; ++k) {
+        const double d0 = x0 - m0[k], d1 = x1 - m1[k], d2 = x2 - m2[k];
+        const double r0 = (d0 * a[0][k] + d1 * a[3][k]) + d2 * a[6][k];
+        const double r1 = (d0 * a[1][k] + d1 * a[4][k]) + d2 * a[7][k];
+        const double r2 = (d0 * a[2][k] + d1 * a[5][k]) + d2 * a[8][k];
+        s[k] = (r0 * d0 + r1 * d1) + r2 * d2;
+      }
+      double best = std::numeric_limits<double>::max();  // gmmloc_opt.cpp:176
+      int bi = -1;
+      for (int k = 0; k < K; ++k)
+        if (s[k] < best) { best = s[k]; bi = k; }  // strict '<', ascending index
+      if (gate > 0 && bi >= 0 && best > gate) bi = -1;  // gmmloc_opt.cpp:230
+      assign[p] = bi;
+      if (d2_out) d2_out[p] = best;
+    }
+  });
+}
+
+double oracle_bh3(const oracle_comp_t* g0, const oracle_comp_t* g1) {
+  // gmm_utils.h:30-52
+  double cov[9], inv[9];
+  for (int i = 0; i < 9; ++i) cov[i] = (g0->cov[i] + g1->cov[i]) / 2.0;
+  const double d[3] = {g1->mean[0] - g0->mean[0], g1->mean[1] - g0->mean[1], g1->mean[2] - g0->mean[2]};
+  inverse3(cov, inv);
+  const double r0 = (d[0] * inv[0] + d[1] * inv[3]) + d[2] * inv[6];
+  const double r1 = (d[0] * inv[1] + d[1] * inv[4]) + d[2] * inv[7];
+  const double r2 = (d[0] * inv[2] + d[1] * inv[5]) + d[2] * inv[8];
+  double d0 = (r0 * d[0] + r1 * d[1]) + r2 * d[2];
+  d0 /= 8.0;
+  const double d1 = std::log(det3(cov) / std::sqrt(g0->det * g1->det)) / 2.0;
+  return d0 + d1;
+}
+
+int64_t oracle_neighbors(const oracle_comp_t* comps, int K, double thresh, int64_t* row_ptr, int32_t* col,
+                         double* dist, int64_t cap) {
+  int64_t n = 0;
+  for (int i = 0; i < K; ++i) {
+    row_ptr[i] = n;
+    for (int j = 0; j < K; ++j) {
+      if (i == j) continue;
+      const double d = oracle_bh3(&comps[i], &comps[j]);
+      if (d < thresh) {
+        if (col && n < cap) { col[n] = j; if (dist) dist[n] = d; }
+        ++n;
+      }
+    }
+  }
+  row_ptr[K] = n;
+  return n;
+}
+
+void oracle_se3_exp(const double xi[6], double pose[7]) {
+  const double id[7] = {0, 0, 0, 1, 0, 0, 0};
+  se3_oplus(xi, id, pose);
+}
+void oracle_se3_oplus(const double xi[6], const double pose[7], double pose_out[7]) { se3_oplus(xi, pose, pose_out); }
+
+int oracle_optimize_point(const double x0[3], const double obs[3], int octave, const double pose[7],
+                          const oracle_comp_t* comp, double proj_z2, const oracle_camera_t* camp,
+                          const oracle_params_t* prm, int iters, double pt_est[3], double* chi2_proj,
+                          double* chi2_str) {
+  // gmmloc_opt.cpp:260-342
+  const Cam cam{camp->fx, camp->fy, camp->cx, camp->cy, camp->bf};
+  double q[4] = {pose[0], pose[1], pose[2], pose[3]};
+  quat_normalize(q);
+  double R[9];
+  quat_to_rot(q, R);
+  const double* t = pose + 4;
+  const double w_proj = oracle_sigma2_inv(octave);                 // :266,293
+  const double w_str = prm->tri_lambda2 * proj_z2;                 // :311-312
+  const double n[3] = {comp->axis[0], comp->axis[3], comp->axis[6]};  // axis_.col(0)  :314
+  double x[3] = {x0[0], x0[1], x0[2]};
+  double c2p = 0, c2s = 0;
+  bool ok = true;
+  for (int it = 0; it < iters; ++it) {
+    double pc[3];
+    mat3_vec(R, x, pc);
+    for (int i = 0; i < 3; ++i) pc[i] += t[i];
+    double e[3], Jl[9];
+    reproj_edge(cam, R, pc, obs, true, e, Jl, nullptr);
+    const double es = (n[0] * (x[0] - comp->mean[0]) + n[1] * (x[1] - comp->mean[1])) + n[2] * (x[2] - comp->mean[2]);
+    c2p = w_proj * ((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]);
+    c2s = w_str * (es * es);
+    double H[9], b[3];
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c)
+        M(H, r, c) = w_proj * ((Jl[0 + r] * Jl[0 + c] + Jl[3 + r] * Jl[3 + c]) + Jl[6 + r] * Jl[6 + c]) + w_str * (n[r] * n[c]);
+      b[r] = -(w_proj * ((Jl[0 + r] * e[0] + Jl[3 + r] * e[1]) + Jl[6 + r] * e[2]) + w_str * (n[r] * es));
+    }
+    double Hi[9], dx[3];
+    if (!inverse3(H, Hi)) { ok = false; break; }
+    mat3_vec(Hi, b, dx);
+    for (int i = 0; i < 3; ++i) x[i] += dx[i];
+  }
+  for (int i = 0; i < 3; ++i) pt_est[i] = x[i];
+  *chi2_proj = c2p;  // errors of the last linearisation point (SURVEY Appx B.6)
+  *chi2_str = c2s;
+  int res = ok ? 1 : 0;
+  if (c2p > 7.815) res = 0;                                                            // :332-335
+  if (prm->tri_check_str_chi2 && c2s > prm->tri_str_thresh * prm->tri_lambda2) res = 0;  // :336-339
+  return res;
+}
+
+void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t* camp,
+                        const oracle_params_t* prm, const double pose0[7], const float* pts_w,
+                        const float* obsf, const uint8_t* octave, int N, const int32_t* assign_in,
+                        double pose_out[7], double* pts_out, int32_t* assign_o, uint8_t* outlier,
+                        int32_t* status, double* trace) {
+  const Cam cam{camp->fx, camp->fy, camp->cx, camp->cy, camp->bf};
+  std::vector<int32_t> asg(N);
+  if (assign_in) {
+    for (int i = 0; i < N; ++i) asg[i] = assign_in[i];
+  } else {
+    oracle_associate(comps, K, pts_w, N, 0.0, asg.data(), nullptr, 1);
+  }
+  std::vector<double> x(3 * (size_t)N);
+  for (int i = 0; i < 3 * N; ++i) x[i] = (double)pts_w[i];
+  double pose[7];
+  for (int i = 0; i < 7; ++i) pose[i] = pose0[i];
+  quat_normalize(pose);
+
+  // structure-edge gates, fixed at iteration 0 (SURVEY §7 / Appx A11):
+  //   degenerate: e^2 <= tri_str_thresh     (gmmloc_opt.cpp:336-338, localization_opt.cpp:781)
+  //   otherwise : d^2 <= mdist2_gate (9.0)  (gmmloc_opt.cpp:230)
+  std::vector<uint8_t> str_on(N, 0), free_pt(N, 0), stereo(N, 0);
+  const bool pose_free = prm->factor_mode != 2;
+  const bool pts_free = prm->factor_mode != 1;
+  for (int i = 0; i < N; ++i) {
+    stereo[i] = obsf[i * 3 + 2] >= 0.0f;  // u_right < 0 => monocular (tracking_opt.cpp:67)
+    const int k = asg[i];
+    if (k >= 0 && pts_free) {
+      const oracle_comp_t& c = comps[k];
+      const double* xi = &x[3 * i];
+      if (c.is_degenerated) {
+        const double e = (c.axis[0] * (xi[0] - c.mean[0]) + c.axis[3] * (xi[1] - c.mean[1])) + c.axis[6] * (xi[2] - c.mean[2]);
+        str_on[i] = (e * e <= prm->tri_str_thresh);
+      } else {
+        str_on[i] = (oracle_chi2(&c, xi) <= prm->mdist2_gate);
+      }
+    }
+    // a monocular point without a structure edge has a rank-2 Hll: hold it fixed (== setFixed(true))
+    free_pt[i] = pts_free && (stereo[i] || str_on[i]);
+  }
+  const double delta_mono = (double)(float)std::sqrt(5.991), delta_stereo = (double)(float)std::sqrt(7.815);
+
+  int st = 0;
+  for (int it = 0; it < prm->gn_iters && st == 0; ++it) {
+    double q[4] = {pose[0], pose[1], pose[2], pose[3]}, R[9];
+    quat_to_rot(q, R);
+    const double* t = pose + 4;
+    double Hpp[36] = {0}, bp[6] = {0};
+    // pass 1: edges -> Hpp, bp, and per free point the Schur terms
+    double S[36] = {0}, g[6] = {0};
+    std::vector<double> Dinv(9 * (size_t)N), Hpl(18 * (size_t)N), bl(3 * (size_t)N);
+    for (int i = 0; i < N; ++i) {
+      const double* xi = &x[3 * i];
+      double pc[3];
+      mat3_vec(R, xi, pc);
+      for (int r = 0; r < 3; ++r) pc[r] += t[r];
+      const double obs[3] = {(double)obsf[i * 3], (double)obsf[i * 3 + 1], (double)obsf[i * 3 + 2]};
+      double e[3], Jl[9], Jp[18];
+      const int m = stereo[i] ? 3 : 2;
+      reproj_edge(cam, R, pc, obs, stereo[i], e, Jl, Jp);
+      double w = oracle_sigma2_inv(octave[i]);
+      double e2 = 0;
+      for (int r = 0; r < m; ++r) e2 += e[r] * e[r];
+      e2 *= w;
+      if (prm->robust) w *= huber_rho1(e2, stereo[i] ? delta_stereo : delta_mono);
+      if (pose_free) {
+        for (int a = 0; a < 6; ++a) {
+          for (int b = 0; b < 6; ++b) {
+            double s = 0;
+            for (int r = 0; r < m; ++r) s += Jp[r * 6 + a] * Jp[r * 6 + b];
+            Hpp[a * 6 + b] += w * s;
+          }
+          double s = 0;
+          for (int r = 0; r < m; ++r) s += Jp[r * 6 + a] * e[r];
+          bp[a] -= w * s;
+        }
+      }
+      if (!free_pt[i]) continue;
+      double Hll[9], bli[3], *Hpli = &Hpl[18 * (size_t)i];
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) {
+          double s = 0;
+          for (int r = 0; r < m; ++r) s += Jl[r * 3 + a] * Jl[r * 3 + b];
+          M(Hll, a, b) = w * s;
+        }
+        double s = 0;
+        for (int r = 0; r < m; ++r) s += Jl[r * 3 + a] * e[r];
+        bli[a] = -(w * s);
+      }
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 3; ++b) {
+          double s = 0;
+          for (int r = 0; r < m; ++r) s += Jp[r * 6 + a] * Jl[r * 3 + b];
+          Hpli[a * 3 + b] = w * s;
+        }
+      if (str_on[i]) {
+        const oracle_comp_t& c = comps[asg[i]];
+        const double d[3] = {xi[0] - c.mean[0], xi[1] - c.mean[1], xi[2] - c.mean[2]};
+        if (c.is_degenerated) {  // EdgePt2GaussianDeg, Omega = ba_lambda2  (localization_opt.cpp:657-669)
+          const double n[3] = {c.axis[0], c.axis[3], c.axis[6]};
+          const double es = (n[0] * d[0] + n[1] * d[1]) + n[2] * d[2];
+          for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < 3; ++b) M(Hll, a, b) += prm->ba_lambda2 * (n[a] * n[b]);
+            bli[a] -= prm->ba_lambda2 * (n[a] * es);
+          }
+        } else {  // EdgePt2Gaussian: e = L^T d, J = L^T, Omega = I (factors.cpp:5-17, localization_opt.cpp:670-681)
+          const double* L = c.sqrt_info;
+          double es[3];
+          for (int r = 0; r < 3; ++r) es[r] = (M(L, 0, r) * d[0] + M(L, 1, r) * d[1]) + M(L, 2, r) * d[2];
+          for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < 3; ++b) {
+              double s = 0;
+              for (int r = 0; r < 3; ++r) s += M(L, a, r) * M(L, b, r);
+              M(Hll, a, b) += s;
+            }
+            double s = 0;
+            for (int r = 0; r < 3; ++r) s += M(L, a, r) * es[r];
+            bli[a] -= s;
+          }
+        }
+      }
+      double* Di = &Dinv[9 * (size_t)i];
+      if (!inverse3(Hll, Di)) { st |= 1; break; }
+      for (int r = 0; r < 3; ++r) bl[3 * (size_t)i + r] = bli[r];
+      if (pose_free) {
+        // W = Hpl * Dinv (6x3);  S += W Hpl^T ; g += W bl       (g2o BlockSolver Schur, Appx B.8)
+        double W[18];
+        for (int a = 0; a < 6; ++a)
+          for (int b = 0; b < 3; ++b)
+            W[a * 3 + b] = (Hpli[a * 3 + 0] * M(Di, 0, b) + Hpli[a * 3 + 1] * M(Di, 1, b)) + Hpli[a * 3 + 2] * M(Di, 2, b);
+        for (int a = 0; a < 6; ++a) {
+          for (int b = 0; b < 6; ++b)
+            S[a * 6 + b] += (W[a * 3 + 0] * Hpli[b * 3 + 0] + W[a * 3 + 1] * Hpli[b * 3 + 1]) + W[a * 3 + 2] * Hpli[b * 3 + 2];
+          g[a] += (W[a * 3 + 0] * bli[0] + W[a * 3 + 1] * bli[1]) + W[a * 3 + 2] * bli[2];
+        }
+      }
+    }
+    if (st) break;
+    double dxi[6] = {0, 0, 0, 0, 0, 0};
+    if (pose_free) {
+      double Hs[36], bs[6];
+      for (int i = 0; i < 36; ++i) Hs[i] = Hpp[i] - S[i];
+      for (int i = 0; i < 6; ++i) bs[i] = bp[i] - g[i];
+      if (!solve6(Hs, bs, dxi)) { st |= 1; break; }
+    }
+    if (trace) for (int i = 0; i < 6; ++i) trace[it * 6 + i] = dxi[i];
+    // back-substitution and update
+    bool finite = true;
+    std::vector<double> xn(x);
+    for (int i = 0; i < N; ++i) {
+      if (!free_pt[i]) continue;
+      const double* Hpli = &Hpl[18 * (size_t)i];
+      double c[3];
+      for (int b = 0; b < 3; ++b) {
+        double s = 0;
+        for (int a = 0; a < 6; ++a) s += Hpli[a * 3 + b] * dxi[a];
+        c[b] = bl[3 * (size_t)i + b] - s;
+      }
+      double dx[3];
+      mat3_vec(&Dinv[9 * (size_t)i], c, dx);
+      for (int r = 0; r < 3; ++r) {
+        xn[3 * i + r] = x[3 * i + r] + dx[r];
+        if (!std::isfinite(xn[3 * i + r])) finite = false;
+      }
+    }
+    if (!finite) { st |= 1; break; }
+    x.swap(xn);
+    if (pose_free) {
+      double np[7];
+      se3_oplus(dxi, pose, np);
+      for (int i = 0; i < 7; ++i) pose[i] = np[i];
+    }
+  }
+
+  if (pose_out) for (int i = 0; i < 7; ++i) pose_out[i] = pose[i];
+  if (pts_out) for (int i = 0; i < 3 * N; ++i) pts_out[i] = x[i];
+  if (assign_o) for (int i = 0; i < N; ++i) assign_o[i] = asg[i];
+  if (status) *status = st;
+  if (outlier) {
+    // post-check at the final estimate: chi2 > 5.991 / 7.815 or non-positive depth
+    // (localization_opt.cpp:857-881)
+    double q[4] = {pose[0], pose[1], pose[2], pose[3]}, R[9];
+    quat_to_rot(q, R);
+    for (int i = 0; i < N; ++i) {
+      double pc[3];
+      mat3_vec(R, &x[3 * i], pc);
+      for (int r = 0; r < 3; ++r) pc[r] += pose[4 + r];
+      const double obs[3] = {(double)obsf[i * 3], (double)obsf[i * 3 + 1], (double)obsf[i * 3 + 2]};
+      double e[3];
+      reproj_edge(cam, R, pc, obs, stereo[i], e, nullptr, nullptr);
+      const int m = stereo[i] ? 3 : 2;
+      double e2 = 0;
+      for (int r = 0; r < m; ++r) e2 += e[r] * e[r];
+      e2 *= oracle_sigma2_inv(octave[i]);
+      const double th = stereo[i] ? prm->chi2_stereo : prm->chi2_mono;
+      outlier[i] = (e2 > th || !(pc[2] > 0.0)) ? 1 : 0;
+    }
+  }
+}
+
+void oracle_frames_solve(const oracle_comp_t* comps, int K, const oracle_camera_t* cam,
+                         const oracle_params_t* prm, const double* pose0, const float* pts_w,
+                         const float* obs, const uint8_t* octave, int B, int N, double* pose_out,
+                         double* pts_out, int32_t* assign, uint8_t* outlier, int32_t* status, int nthreads) {
+  parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int) {
+    for (int64_t f = lo; f < hi; ++f) {
+      oracle_frame_solve(comps, K, cam, prm, pose0 + 7 * f, pts_w + 3 * (size_t)N * f, obs + 3 * (size_t)N * f,
+                         octave + (size_t)N * f, N, nullptr, pose_out ? pose_out + 7 * f : nullptr,
+                         pts_out ? pts_out + 3 * (size_t)N * f : nullptr, assign ? assign + (size_t)N * f : nullptr,
+                         outlier ? outlier + (size_t)N * f : nullptr, status ? status + f : nullptr, nullptr);
+    }
+  });
+}
+
+// ----------------------------------------------------------------------------------------------
+// .gmm wire format: varint32 count, then per component varint32 size + ComponentProto bytes
+// (protobuf_utils.cpp:12-101; GMM.proto:5-14: 1 bool is_degenerated, 2 bool is_salient,
+//  3 packed double mean, 4 packed double covariance)
+// ----------------------------------------------------------------------------------------------
+static bool rd_varint(const std::vector<uint8_t>& b, size_t& pos, uint64_t& v) {
+  v = 0;
+  for (int shift = 0; shift < 64; shift += 7) {
+    if (pos >= b.size()) return false;
+    const uint8_t c = b[pos++];
+    v |= (uint64_t)(c & 0x7f) << shift;
+    if (!(c & 0x80)) return true;
+  }
+  return false;
+}
+static void wr_varint(std::vector<uint8_t>& b, uint64_t v) {
+  while (v >= 0x80) { b.push_back((uint8_t)(v | 0x80)); v >>= 7; }
+  b.push_back((uint8_t)v);
+}
+
+int oracle_gmm_read(const char* path, double* mean, double* cov, uint8_t* flags, int cap) {
+  FILE* f = std::fopen(path, "rb");
+  if (!f) return -1;
+  std::vector<uint8_t> b;
+  uint8_t tmp[65536];
+  size_t n;
+  while ((n = std::fread(tmp, 1, sizeof tmp, f)) > 0) b.insert(b.end(), tmp, tmp + n);
+  std::fclose(f);
+  size_t pos = 0;
+  uint64_t cnt;
+  if (!rd_varint(b, pos, cnt)) return -2;
+  if (cnt == 0) return -3;  // "protobuf file empty!" gmm_utils.cpp:32-35
+  const int K = (int)cnt;
+  const bool fill = mean && cov && cap >= K;
+  for (int k = 0; k < K; ++k) {
+    uint64_t sz;
+    if (!rd_varint(b, pos, sz) || sz == 0 || pos + sz > b.size()) return -4;
+    const size_t end = pos + sz;
+    int nm = 0, nc = 0;
+    uint8_t fl[2] = {0, 0};
+    double m[3] = {0, 0, 0}, c[9] = {0};
+    while (pos < end) {
+      uint64_t key;
+      if (!rd_varint(b, pos, key)) return -5;
+      const int field = (int)(key >> 3), wt = (int)(key & 7);
+      if (wt == 0) {
+        uint64_t v;
+        if (!rd_varint(b, pos, v)) return -5;
+        if (field == 1) fl[0] = v != 0;
+        if (field == 2) fl[1] = v != 0;
+      } else if (wt == 2) {
+        uint64_t len;
+        if (!rd_varint(b, pos, len) || pos + len > end) return -5;
+        if ((field == 3 || field == 4) && len % 8 == 0) {
+          for (uint64_t i = 0; i < len / 8; ++i) {
+            double v;
+            std::memcpy(&v, &b[pos + 8 * i], 8);
+            if (field == 3) { if (nm < 3) m[nm] = v; ++nm; }
+            else { if (nc < 9) c[nc] = v; ++nc; }
+          }
+        }
+        pos += len;
+      } else if (wt == 1) {  // non-packed double (proto2 parsers accept both encodings)
+        if (pos + 8 > end) return -5;
+        double v;
+        std::memcpy(&v, &b[pos], 8);
+        if (field == 3) { if (nm < 3) m[nm] = v; ++nm; }
+        if (field == 4) { if (nc < 9) c[nc] = v; ++nc; }
+        pos += 8;
+      } else if (wt == 5) {
+        pos += 4;
+      } else {
+        return -5;
+      }
+    }
+    if (pos != end) return -5;
+    if (nm != 3 || nc != 9) return -6;  // CHECK_EQ gmm_utils.cpp:50-51
+    if (fill) {
+      for (int i = 0; i < 3; ++i) mean[k * 3 + i] = m[i];
+      for (int i = 0; i < 9; ++i) cov[k * 9 + i] = c[i];  // row-major fill, gmm_utils.cpp:55-59
+      if (flags) { flags[2 * k] = fl[0]; flags[2 * k + 1] = fl[1]; }
+    }
+  }
+  return K;
+}
+
+int oracle_gmm_write(const char* path, const double* mean, const double* cov, const uint8_t* flags, int K) {
+  std::vector<uint8_t> b;
+  wr_varint(b, (uint64_t)K);  // gmm_utils.cpp:87-92
+  for (int k = 0; k < K; ++k) {
+    std::vector<uint8_t> m;
+    m.push_back(0x08); m.push_back(flags ? flags[2 * k] : 0);      // field 1 varint  (:97)
+    m.push_back(0x10); m.push_back(flags ? flags[2 * k + 1] : 0);  // field 2 varint  (:99)
+    m.push_back(0x1a); m.push_back(24);                            // field 3 packed 3 doubles (:103-105)
+    for (int i = 0; i < 3; ++i) { uint8_t t[8]; std::memcpy(t, &mean[k * 3 + i], 8); m.insert(m.end(), t, t + 8); }
+    m.push_back(0x22); m.push_back(72);                            // field 4 packed 9 doubles (:106-108)
+    // writer emits cov(i) in Eigen's column-major linear order (:107)
+    for (int i = 0; i < 9; ++i) {
+      const int r = i % 3, c = i / 3;
+      uint8_t t[8];
+      std::memcpy(t, &cov[k * 9 + r * 3 + c], 8);
+      m.insert(m.end(), t, t + 8);
+    }
+    wr_varint(b, m.size());
+    b.insert(b.end(), m.begin(), m.end());
+  }
+  FILE* f = std::fopen(path, "wb");
+  if (!f) return -1;
+  const size_t w = std::fwrite(b.data(), 1, b.size(), f);
+  std::fclose(f);
+  return w == b.size() ? 0 : -2;
+}
+
+}  // extern "C"

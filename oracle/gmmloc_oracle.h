@@ -1,0 +1,124 @@
+/*
+ * gmmloc_oracle.h — CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * A dependency-free fp64 restatement of the reference's arithmetic for the GMMLoc hot path
+ * (GMM map association + structure-constrained Gauss-Newton).  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library; the product library
+ * (gmmloc_b200/csrc) never links, loads or calls it.
+ *
+ * PARITY STATUS: "parity unpinned" for everything that lives in g2o / Eigen (neither is vendored in
+ * /root/reference nor installed here; g2o_catkin is not version-pinned, .gmmloc_https.install:16-18).
+ * Pinned pieces: the is_degenerated flags stored in the shipped .gmm maps (8 395 / 8 395 agree with
+ * oracle_map_build, tests/test_oracle_golden.py) and the .gmm wire format (byte-exact re-encode).
+ *
+ * All citations are relative to /root/reference/.
+ */
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Per-component constants, one row per component (all row-major, fp64).
+ * Follows GaussianComponent ctor + decompose(): gmmloc/include/gmmloc/gmm/gaussian.h:30-39,
+ * gmmloc/src/gmm/gaussian.cpp:36-63. */
+typedef struct {
+  double mean[3];
+  double cov[9];
+  double cov_inv[9];   /* Eigen 3x3 inverse (cofactor form)                           gaussian.h:31 */
+  double det;          /* cov.determinant()                                           gaussian.h:33 */
+  double scale[3];     /* eigenvalues ascending                                       gaussian.cpp:41-42 */
+  double axis[9];      /* axis[r*3+c] = component r of eigenvector c                  gaussian.cpp:41 */
+  double sqrt_info[9]; /* lower L, cov_inv = L L^T                                    gaussian.cpp:49 */
+  int32_t is_degenerated; /* scale[0] < deg_eps (1e-4)                                gaussian.cpp:44 */
+  int32_t is_salient;     /* scale[1] > 0.2 && scale[2] > 0.2                         gaussian.cpp:51-55 */
+} oracle_comp_t;
+
+typedef struct {
+  double fx, fy, cx, cy, bf;
+  int32_t width, height;
+} oracle_camera_t; /* gmmloc_ros/cfg/v1.yaml:5-17 */
+
+typedef struct {
+  double tri_lambda2;    /* loc/tri_lambda2   = 400     v1.yaml:32 */
+  double ba_lambda2;     /* loc/ba_lambda2    = 400     v1.yaml:37 */
+  double tri_str_thresh; /* loc/tri_str_thresh= 0.0064  v1.yaml:35 */
+  int32_t tri_check_str_chi2; /* v1.yaml:34 */
+  double mdist2_gate;    /* 9.0: gmmloc_opt.cpp:230 (non-degenerate structure-edge gate in the frame solve) */
+  double chi2_mono;      /* 5.991  tracking_opt.cpp:145 */
+  double chi2_stereo;    /* 7.815  tracking_opt.cpp:146 */
+  int32_t gn_iters;      /* 10     tracking_opt.cpp:147 */
+  int32_t robust;        /* Huber on reprojection edges (localization_opt.cpp:716,746) */
+  int32_t factor_mode;   /* 0 = J joint pose+points, 1 = P pose only, 2 = S points only */
+} oracle_params_t;
+
+void oracle_default_params(oracle_params_t* p);
+
+/* a1: component constants.  mean K x 3, cov K x 9 row-major. */
+void oracle_map_build(const double* mean, const double* cov, int K, double deg_eps, oracle_comp_t* out);
+
+/* a3: d2 = (x-mu)^T cov_inv (x-mu)     gaussian.cpp:65-70 */
+double oracle_chi2(const oracle_comp_t* c, const double x[3]);
+
+/* a3+a4: brute-force association of M points (fp32 landmarks promoted to fp64) against all K
+ * components; running minimum with strict '<' while scanning ascending index (gmmloc_opt.cpp:209-217,
+ * gaussian_mixture.cpp:464-475) => lowest index wins ties.  assign[i] = -1 iff gate > 0 and
+ * best d2 > gate.  d2_out may be NULL. nthreads <= 1: single thread. */
+void oracle_associate(const oracle_comp_t* comps, int K, const float* pts, int64_t M, double gate,
+                      int32_t* assign, double* d2_out, int nthreads);
+
+/* A3: Bhattacharyya distance between 3-D components (gmm_utils.h:30-52). */
+double oracle_bh3(const oracle_comp_t* a, const oracle_comp_t* b);
+
+/* a2: neighbour lists, ordered pairs i != j with BH < thresh (gaussian_mixture.cpp:61-78).
+ * CSR output: row_ptr[K+1]; returns total count; col/dist written only if non-NULL and cap >= count. */
+int64_t oracle_neighbors(const oracle_comp_t* comps, int K, double thresh, int64_t* row_ptr, int32_t* col,
+                         double* dist, int64_t cap);
+
+/* A7: optimizePoint (gmmloc_opt.cpp:260-342): 3-DoF GN, 5 iterations, one stereo reprojection edge
+ * (factors.cpp:116-168) + one point-to-plane edge (factors.cpp:55-64).
+ * pose = qx qy qz qw tx ty tz (T_cw).  Returns res (1/0). */
+int oracle_optimize_point(const double x0[3], const double obs[3], int octave, const double pose[7],
+                          const oracle_comp_t* comp, double proj_z2, const oracle_camera_t* cam,
+                          const oracle_params_t* prm, int iters, double pt_est[3], double* chi2_proj,
+                          double* chi2_str);
+
+/* A11: the frame solve = single-free-pose specialisation of Localization::jointOptimization
+ * (localization_opt.cpp:456-925) run with Gauss-Newton; association by oracle_associate at
+ * iteration 0, structure-edge gates fixed at iteration 0.
+ *  pose0/pose_out: qx qy qz qw tx ty tz (T_cw) fp64;  pts_w N x 3 fp32;  obs N x 3 fp32 (u v u_r,
+ *  u_r < 0 => mono);  octave N.  assign_in: if non-NULL use these assignments instead of
+ *  associating.  Outputs (any may be NULL): pose_out[7], pts_out N x 3 (fp64), assign N,
+ *  outlier N, status (bit0 numeric failure).  trace (optional): gn_iters x 6 pose increments. */
+void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t* cam,
+                        const oracle_params_t* prm, const double pose0[7], const float* pts_w,
+                        const float* obs, const uint8_t* octave, int N, const int32_t* assign_in,
+                        double pose_out[7], double* pts_out, int32_t* assign, uint8_t* outlier,
+                        int32_t* status, double* trace);
+
+/* Batched driver over B independent frames, sharded over nthreads std::threads (the reference runs
+ * each solve on the caller's thread; sharding over frames is the CPU baseline's "all cores" mode). */
+void oracle_frames_solve(const oracle_comp_t* comps, int K, const oracle_camera_t* cam,
+                         const oracle_params_t* prm, const double* pose0, const float* pts_w,
+                         const float* obs, const uint8_t* octave, int B, int N, double* pose_out,
+                         double* pts_out, int32_t* assign, uint8_t* outlier, int32_t* status, int nthreads);
+
+/* frame::sigma2_inv[octave] as the reference computes it in float (init_config.hpp:63-78). */
+double oracle_sigma2_inv(int octave);
+
+/* SE3 exp (g2o SE3Quat::exp, SURVEY Appx B.1) -> qx qy qz qw tx ty tz. */
+void oracle_se3_exp(const double xi[6], double pose[7]);
+/* pose_out = exp(xi) * pose   (VertexSE3Expmap::oplusImpl) */
+void oracle_se3_oplus(const double xi[6], const double pose[7], double pose_out[7]);
+
+/* .gmm wire format (protobuf_utils.cpp:12-101, GMM.proto:5-14, gmm_utils.cpp:9-119).
+ * read: returns K (<0 on error); if mean/cov non-NULL and cap >= K fills them (cov row-major as the
+ * loader does, gmm_utils.cpp:55-59); flags (optional) K x 2 = stored is_degenerated,is_salient. */
+int oracle_gmm_read(const char* path, double* mean, double* cov, uint8_t* flags, int cap);
+/* write: same byte stream saveGMMModel emits (gmm_utils.cpp:69-119). returns 0 on success. */
+int oracle_gmm_write(const char* path, const double* mean, const double* cov, const uint8_t* flags, int K);
+
+#ifdef __cplusplus
+}
+#endif

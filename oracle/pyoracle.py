@@ -1,0 +1,238 @@
+"""ctypes binding of the CPU ORACLE (oracle/gmmloc_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  Nothing under gmmloc_b200/ imports this module.
+
+The shared object is compiled on demand with the host's own `-march=native` (the reference builds with
+-O3 -march=native, gmmloc/CMakeLists.txt:7) into oracle/_build/, keyed by a hash of the CPU flags so a
+library built in the CPU-only container is never dlopen'ed on a different CPU on the GPU box.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import hashlib
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_SRC = [_HERE / "gmmloc_oracle.cpp", _HERE / "gmmloc_oracle.h"]
+
+
+def _cpu_key() -> str:
+    try:
+        txt = Path("/proc/cpuinfo").read_text()
+        flags = next((l for l in txt.splitlines() if l.startswith("flags")), "")
+        model = next((l for l in txt.splitlines() if l.startswith("model name")), "")
+    except OSError:
+        flags = model = ""
+    return hashlib.sha1((flags + model).encode()).hexdigest()[:10]
+
+
+def build(force: bool = False) -> Path:
+    out_dir = _HERE / "_build"
+    out_dir.mkdir(exist_ok=True)
+    so = out_dir / f"libgmmloc_oracle_{_cpu_key()}.so"
+    newest = max(p.stat().st_mtime for p in _SRC)
+    if force or not so.exists() or so.stat().st_mtime < newest:
+        cxx = os.environ.get("CXX", "g++")
+        cmd = [cxx, "-O3", "-march=native", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math",
+               "-pthread", "-shared", "-o", str(so) + ".tmp", str(_SRC[0])]
+        subprocess.run(cmd, check=True, cwd=_HERE)
+        os.replace(str(so) + ".tmp", so)
+    return so
+
+
+class Comp(C.Structure):
+    _fields_ = [("mean", C.c_double * 3), ("cov", C.c_double * 9), ("cov_inv", C.c_double * 9),
+                ("det", C.c_double), ("scale", C.c_double * 3), ("axis", C.c_double * 9),
+                ("sqrt_info", C.c_double * 9), ("is_degenerated", C.c_int32), ("is_salient", C.c_int32)]
+
+
+COMP_DTYPE = np.dtype([("mean", "f8", 3), ("cov", "f8", 9), ("cov_inv", "f8", 9), ("det", "f8"),
+                       ("scale", "f8", 3), ("axis", "f8", 9), ("sqrt_info", "f8", 9),
+                       ("is_degenerated", "i4"), ("is_salient", "i4")], align=True)
+assert COMP_DTYPE.itemsize == C.sizeof(Comp)
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("bf", C.c_double), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class Params(C.Structure):
+    _fields_ = [("tri_lambda2", C.c_double), ("ba_lambda2", C.c_double), ("tri_str_thresh", C.c_double),
+                ("tri_check_str_chi2", C.c_int32), ("mdist2_gate", C.c_double), ("chi2_mono", C.c_double),
+                ("chi2_stereo", C.c_double), ("gn_iters", C.c_int32), ("robust", C.c_int32),
+                ("factor_mode", C.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(str(build()))
+        L.oracle_chi2.restype = C.c_double
+        L.oracle_bh3.restype = C.c_double
+        L.oracle_sigma2_inv.restype = C.c_double
+        L.oracle_neighbors.restype = C.c_int64
+        L.oracle_optimize_point.restype = C.c_int
+        L.oracle_gmm_read.restype = C.c_int
+        L.oracle_gmm_write.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a, t=None):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    lib().oracle_default_params(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def v1_camera() -> Camera:
+    # gmmloc_ros/cfg/v1.yaml:5-17
+    return Camera(435.2046959714599, 435.2046959714599, 367.4517211914062, 252.2008514404297,
+                  47.90639384423901, 752, 480)
+
+
+def map_build(mean, cov, deg_eps=1e-4) -> np.ndarray:
+    mean = np.ascontiguousarray(mean, np.float64).reshape(-1, 3)
+    cov = np.ascontiguousarray(cov, np.float64).reshape(-1, 9)
+    K = mean.shape[0]
+    out = np.zeros(K, COMP_DTYPE)
+    lib().oracle_map_build(_p(mean), _p(cov), C.c_int(K), C.c_double(deg_eps), _p(out))
+    return out
+
+
+def associate(comps, pts, gate=0.0, nthreads=1):
+    pts = np.ascontiguousarray(pts, np.float32).reshape(-1, 3)
+    M = pts.shape[0]
+    assign = np.empty(M, np.int32)
+    d2 = np.empty(M, np.float64)
+    lib().oracle_associate(_p(comps), C.c_int(len(comps)), _p(pts), C.c_int64(M), C.c_double(gate),
+                           _p(assign), _p(d2), C.c_int(nthreads))
+    return assign, d2
+
+
+def chi2(comps, k, x):
+    x = np.ascontiguousarray(x, np.float64)
+    return lib().oracle_chi2(C.c_void_p(comps.ctypes.data + int(k) * COMP_DTYPE.itemsize), _p(x))
+
+
+def bh3(comps, i, j):
+    base = comps.ctypes.data
+    return lib().oracle_bh3(C.c_void_p(base + int(i) * COMP_DTYPE.itemsize),
+                            C.c_void_p(base + int(j) * COMP_DTYPE.itemsize))
+
+
+def neighbors(comps, thresh):
+    K = len(comps)
+    row_ptr = np.zeros(K + 1, np.int64)
+    n = lib().oracle_neighbors(_p(comps), C.c_int(K), C.c_double(thresh), _p(row_ptr), None, None, C.c_int64(0))
+    col = np.empty(n, np.int32)
+    dist = np.empty(n, np.float64)
+    lib().oracle_neighbors(_p(comps), C.c_int(K), C.c_double(thresh), _p(row_ptr), _p(col), _p(dist), C.c_int64(n))
+    return row_ptr, col, dist
+
+
+def optimize_point(comps, k, x0, obs, octave, pose, proj_z2, cam=None, prm=None, iters=5):
+    cam = cam or v1_camera()
+    prm = prm or default_params()
+    x0 = np.ascontiguousarray(x0, np.float64)
+    obs = np.ascontiguousarray(obs, np.float64)
+    pose = np.ascontiguousarray(pose, np.float64)
+    est = np.zeros(3)
+    c2p, c2s = C.c_double(), C.c_double()
+    res = lib().oracle_optimize_point(_p(x0), _p(obs), C.c_int(int(octave)), _p(pose),
+                                      C.c_void_p(comps.ctypes.data + int(k) * COMP_DTYPE.itemsize),
+                                      C.c_double(proj_z2), C.byref(cam), C.byref(prm), C.c_int(iters), _p(est),
+                                      C.byref(c2p), C.byref(c2s))
+    return bool(res), est, c2p.value, c2s.value
+
+
+def frame_solve(comps, pose0, pts_w, obs, octave, cam=None, prm=None, assign_in=None, want_trace=False):
+    cam = cam or v1_camera()
+    prm = prm or default_params()
+    pose0 = np.ascontiguousarray(pose0, np.float64)
+    pts_w = np.ascontiguousarray(pts_w, np.float32).reshape(-1, 3)
+    obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 3)
+    octave = np.ascontiguousarray(octave, np.uint8)
+    N = pts_w.shape[0]
+    pose_out = np.zeros(7)
+    pts_out = np.zeros((N, 3))
+    assign = np.zeros(N, np.int32)
+    outlier = np.zeros(N, np.uint8)
+    status = C.c_int32(0)
+    trace = np.zeros((prm.gn_iters, 6)) if want_trace else None
+    ai = None if assign_in is None else np.ascontiguousarray(assign_in, np.int32)
+    lib().oracle_frame_solve(_p(comps), C.c_int(len(comps)), C.byref(cam), C.byref(prm), _p(pose0), _p(pts_w),
+                             _p(obs), _p(octave), C.c_int(N), _p(ai), _p(pose_out), _p(pts_out), _p(assign),
+                             _p(outlier), C.byref(status), _p(trace))
+    out = dict(pose=pose_out, pts=pts_out, assign=assign, outlier=outlier, status=status.value)
+    if want_trace:
+        out["trace"] = trace
+    return out
+
+
+def frames_solve(comps, pose0, pts_w, obs, octave, cam=None, prm=None, nthreads=1, want_pts=False):
+    cam = cam or v1_camera()
+    prm = prm or default_params()
+    pose0 = np.ascontiguousarray(pose0, np.float64).reshape(-1, 7)
+    B = pose0.shape[0]
+    pts_w = np.ascontiguousarray(pts_w, np.float32).reshape(B, -1, 3)
+    N = pts_w.shape[1]
+    obs = np.ascontiguousarray(obs, np.float32).reshape(B, N, 3)
+    octave = np.ascontiguousarray(octave, np.uint8).reshape(B, N)
+    pose_out = np.zeros((B, 7))
+    pts_out = np.zeros((B, N, 3)) if want_pts else None
+    assign = np.zeros((B, N), np.int32)
+    outlier = np.zeros((B, N), np.uint8)
+    status = np.zeros(B, np.int32)
+    lib().oracle_frames_solve(_p(comps), C.c_int(len(comps)), C.byref(cam), C.byref(prm), _p(pose0), _p(pts_w),
+                              _p(obs), _p(octave), C.c_int(B), C.c_int(N), _p(pose_out), _p(pts_out), _p(assign),
+                              _p(outlier), _p(status), C.c_int(nthreads))
+    return dict(pose=pose_out, pts=pts_out, assign=assign, outlier=outlier, status=status)
+
+
+def sigma2_inv(octave: int) -> float:
+    return lib().oracle_sigma2_inv(C.c_int(int(octave)))
+
+
+def se3_oplus(xi, pose):
+    xi = np.ascontiguousarray(xi, np.float64)
+    pose = np.ascontiguousarray(pose, np.float64)
+    out = np.zeros(7)
+    lib().oracle_se3_oplus(_p(xi), _p(pose), _p(out))
+    return out
+
+
+def gmm_read(path):
+    K = lib().oracle_gmm_read(str(path).encode(), None, None, None, C.c_int(0))
+    if K < 0:
+        raise IOError(f"oracle_gmm_read({path}) failed: {K}")
+    mean = np.zeros((K, 3))
+    cov = np.zeros((K, 9))
+    flags = np.zeros((K, 2), np.uint8)
+    lib().oracle_gmm_read(str(path).encode(), _p(mean), _p(cov), _p(flags), C.c_int(K))
+    return mean, cov, flags
+
+
+def gmm_write(path, mean, cov, flags=None):
+    mean = np.ascontiguousarray(mean, np.float64).reshape(-1, 3)
+    cov = np.ascontiguousarray(cov, np.float64).reshape(-1, 9)
+    fl = None if flags is None else np.ascontiguousarray(flags, np.uint8).reshape(-1, 2)
+    rc = lib().oracle_gmm_write(str(path).encode(), _p(mean), _p(cov), _p(fl), C.c_int(mean.shape[0]))
+    if rc != 0:
+        raise IOError(f"oracle_gmm_write failed: {rc}")
