@@ -1,0 +1,226 @@
+"""gmmloc_b200 — B200-native GMM map association + structure-constrained Gauss-Newton (GMMLoc hot path).
+
+Host-side mirror of the reference's call surface over the C ABI (include/gmmloc_b200.h):
+
+  GMM                     ≙ gmmloc::GMM + GMMUtility::loadGMMModel / saveGMMModel
+                            (gmmloc/include/gmmloc/gmm/gaussian_mixture.h:98-170, gmm_utils.h:13-16)
+  Context.associate       ≙ GaussianComponent::chi2 scanned over all components with the reference's
+                            argmin convention (gaussian.cpp:65-70, gmmloc_opt.cpp:175-217,230)
+  Context.optimizePoint   ≙ GMMLoc::optimizePoint, batched (gmmloc_opt.cpp:260-342)
+  Context.frames_solve    ≙ single-pose Localization::jointOptimization / Tracking::optimizeCurrentPose
+                            (localization_opt.cpp:456-925, tracking_opt.cpp:21-217)
+
+Everything computes on the GPU through libgmmloc_b200.so; there is no CPU path in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import (Camera, GmmlocError, Params, default_params, v1_camera, MODE_JOINT, MODE_POSE_ONLY,
+                   MODE_POINTS_ONLY, FRAME_NUMERIC)
+
+__all__ = ["GMM", "Context", "Camera", "Params", "GmmlocError", "default_params", "v1_camera", "MODE_JOINT",
+           "MODE_POSE_ONLY", "MODE_POINTS_ONLY", "FRAME_NUMERIC", "version", "sigma2_inv"]
+
+
+def version() -> str:
+    return capi.lib().gmmloc_version().decode()
+
+
+def sigma2_inv(octave: int) -> float:
+    """frame::sigma2_inv[octave] (init_config.hpp:63-78)."""
+    return float(capi.lib().gmmloc_sigma2_inv(int(octave)))
+
+
+def _ptr(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _in(a, dtype, shape=None):
+    a = np.ascontiguousarray(a, dtype=dtype)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+class GMM:
+    """Immutable GMM map resident on one GPU (shareable between contexts / host threads)."""
+
+    def __init__(self, mean, cov, deg_eps: float = 1e-4, device: int = 0):
+        mean = _in(mean, np.float64, (-1, 3))
+        cov = _in(cov, np.float64, (-1, 9))
+        if mean.shape[0] != cov.shape[0]:
+            raise ValueError("mean / cov size mismatch")
+        h = C.c_void_p()
+        capi.check(capi.lib().gmmloc_map_create(_ptr(mean), _ptr(cov), mean.shape[0], float(deg_eps), int(device),
+                                                C.byref(h)))
+        self._h = h
+
+    @classmethod
+    def load(cls, path, deg_eps: float = 1e-4, device: int = 0) -> "GMM":
+        """GMMUtility::loadGMMModel (gmm_utils.cpp:9-67); raises GmmlocError(EIO) where the reference
+        returns false."""
+        h = C.c_void_p()
+        capi.check(capi.lib().gmmloc_map_load_gmm(str(path).encode(), float(deg_eps), int(device), C.byref(h)))
+        self = cls.__new__(cls)
+        self._h = h
+        return self
+
+    def save(self, path) -> None:
+        """GMMUtility::saveGMMModel (gmm_utils.cpp:69-119)."""
+        capi.check(capi.lib().gmmloc_map_save_gmm(self._h, str(path).encode()))
+
+    def countComponents(self) -> int:
+        return int(capi.lib().gmmloc_map_size(self._h))
+
+    __len__ = countComponents
+
+    @property
+    def device(self) -> int:
+        return int(capi.lib().gmmloc_map_device(self._h))
+
+    def getComponents(self) -> dict:
+        """Per-component constants built on the device (≙ GaussianComponent public fields)."""
+        K = self.countComponents()
+        out = dict(mean=np.empty((K, 3)), cov=np.empty((K, 9)), cov_inv=np.empty((K, 9)), det=np.empty(K),
+                   scale=np.empty((K, 3)), axis=np.empty((K, 9)), sqrt_info=np.empty((K, 9)),
+                   is_degenerated=np.empty(K, np.uint8), is_salient=np.empty(K, np.uint8))
+        capi.check(capi.lib().gmmloc_map_get_components(self._h, *[_ptr(out[k]) for k in (
+            "mean", "cov", "cov_inv", "det", "scale", "axis", "sqrt_info", "is_degenerated", "is_salient")]))
+        return out
+
+    def scan_bound(self):
+        a, x = C.c_double(), C.c_double()
+        capi.check(capi.lib().gmmloc_map_scan_bound(self._h, C.byref(a), C.byref(x)))
+        return a.value, x.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().gmmloc_map_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """One CUDA stream + workspaces; use from one host thread at a time."""
+
+    def __init__(self, device: int = 0):
+        h = C.c_void_p()
+        capi.check(capi.lib().gmmloc_ctx_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    @property
+    def stream(self) -> int:
+        """cudaStream_t as an integer (wrap with torch.cuda.ExternalStream for event timing)."""
+        return int(capi.lib().gmmloc_ctx_stream(self._h) or 0)
+
+    def synchronize(self) -> None:
+        capi.check(capi.lib().gmmloc_ctx_synchronize(self._h))
+
+    def stats(self) -> dict:
+        s = capi.Stats()
+        capi.check(capi.lib().gmmloc_ctx_stats(self._h, C.byref(s)))
+        return dict(points=s.points, flagged=s.flagged, kernel_launches=s.kernel_launches)
+
+    def kernel_times(self) -> dict:
+        """Device ms of the last call's kernels (association scan, exact re-rank, frame GN)."""
+        ms = (C.c_float * 3)()
+        capi.check(capi.lib().gmmloc_ctx_kernel_times(self._h, C.byref(ms)))
+        return dict(scan_ms=ms[0], rerank_ms=ms[1], gn_ms=ms[2])
+
+    # ---- host entry points (numpy in, numpy out) ----
+    def associate(self, gmm: GMM, pts_w, gate: float = 0.0, want_d2: bool = True):
+        pts = _in(pts_w, np.float32)
+        if pts.ndim == 2:
+            pts = pts[None]
+        if pts.ndim != 3 or pts.shape[2] != 3:
+            raise ValueError("pts_w must be B x N x 3 or N x 3")
+        B, N = pts.shape[:2]
+        assign = np.empty((B, N), np.int32)
+        d2 = np.empty((B, N), np.float32) if want_d2 else None
+        capi.check(capi.lib().gmmloc_associate(self._h, gmm._h, _ptr(pts), B, N, float(gate), _ptr(assign), _ptr(d2)))
+        return assign, d2
+
+    def frames_solve(self, gmm: GMM, pose0, pts_w, obs, octave, cam: Camera | None = None,
+                     params: Params | None = None, want_pts: bool = True, want_outlier: bool = True) -> dict:
+        cam = cam or v1_camera()
+        params = params or default_params()
+        pose0 = _in(pose0, np.float64, (-1, 7))
+        B = pose0.shape[0]
+        pts = _in(pts_w, np.float32).reshape(B, -1, 3)
+        N = pts.shape[1]
+        obs = _in(obs, np.float32, (B, N, 3))
+        octave = _in(octave, np.uint8, (B, N))
+        pose_out = np.empty((B, 7))
+        pts_out = np.empty((B, N, 3), np.float32) if want_pts else None
+        assign = np.empty((B, N), np.int32)
+        outlier = np.empty((B, N), np.uint8) if want_outlier else None
+        status = np.empty(B, np.int32)
+        capi.check(capi.lib().gmmloc_frames_solve(self._h, gmm._h, C.byref(cam), C.byref(params), _ptr(pose0), _ptr(pts),
+                                                  _ptr(obs), _ptr(octave), B, N, _ptr(pose_out), _ptr(pts_out),
+                                                  _ptr(assign), _ptr(outlier), _ptr(status)))
+        return dict(pose=pose_out, pts=pts_out, assign=assign, outlier=outlier, status=status)
+
+    def frames_solve_into(self, gmm: GMM, cam: Camera, params: Params, pose0, pts_w, obs, octave, pose_out, assign,
+                          status, pts_out=None, outlier=None) -> None:
+        """gmmloc_frames_solve on caller-owned host arrays (e.g. page-locked), no allocation, no conversion."""
+        B, N = pts_w.shape[0], pts_w.shape[1]
+        for a, dt in ((pose0, np.float64), (pts_w, np.float32), (obs, np.float32), (octave, np.uint8),
+                      (pose_out, np.float64), (assign, np.int32), (status, np.int32)):
+            if a.dtype != dt or not a.flags.c_contiguous:
+                raise ValueError("frames_solve_into needs C-contiguous arrays of the ABI dtypes")
+        capi.check(capi.lib().gmmloc_frames_solve(self._h, gmm._h, C.byref(cam), C.byref(params), _ptr(pose0), _ptr(pts_w),
+                                                  _ptr(obs), _ptr(octave), B, N, _ptr(pose_out), _ptr(pts_out),
+                                                  _ptr(assign), _ptr(outlier), _ptr(status)))
+
+    def optimizePoint(self, gmm: GMM, x0, obs, octave, pose, comp, proj_z2, cam: Camera | None = None,
+                      params: Params | None = None, iters: int = 5) -> dict:
+        """Batched GMMLoc::optimizePoint: returns StrOptStat fields (res, chi2_proj, chi2_str, pt_est)."""
+        cam = cam or v1_camera()
+        params = params or default_params()
+        x0 = _in(x0, np.float64, (-1, 3))
+        M = x0.shape[0]
+        obs = _in(obs, np.float32, (M, 3))
+        octave = _in(octave, np.uint8, (M,))
+        pose = _in(np.broadcast_to(np.asarray(pose, np.float64).reshape(-1, 7), (M, 7)), np.float64)
+        comp = _in(comp, np.int32, (M,))
+        proj_z2 = _in(proj_z2, np.float64, (M,))
+        pt_est = np.empty((M, 3))
+        c2p = np.empty(M)
+        c2s = np.empty(M)
+        res = np.empty(M, np.uint8)
+        capi.check(capi.lib().gmmloc_points_solve(self._h, gmm._h, C.byref(cam), C.byref(params), _ptr(x0), _ptr(obs),
+                                                  _ptr(octave), _ptr(pose), _ptr(comp), _ptr(proj_z2), M, int(iters),
+                                                  _ptr(pt_est), _ptr(c2p), _ptr(c2s), _ptr(res)))
+        return dict(res=res.astype(bool), chi2_proj=c2p, chi2_str=c2s, pt_est=pt_est)
+
+    # ---- device entry points (raw device pointers, enqueue only) ----
+    def associate_async(self, gmm: GMM, d_pts: int, M: int, gate: float, d_assign: int, d_d2: int = 0) -> None:
+        capi.check(capi.lib().gmmloc_associate_async(self._h, gmm._h, d_pts, int(M), float(gate), d_assign, d_d2 or None))
+
+    def frames_solve_async(self, gmm: GMM, cam: Camera, params: Params, d_pose0: int, d_pts: int, d_obs: int,
+                           d_octave: int, B: int, N: int, d_pose_out: int, d_pts_out: int, d_assign: int,
+                           d_outlier: int, d_status: int) -> None:
+        capi.check(capi.lib().gmmloc_frames_solve_async(self._h, gmm._h, C.byref(cam), C.byref(params), d_pose0, d_pts,
+                                                        d_obs, d_octave, int(B), int(N), d_pose_out, d_pts_out or None,
+                                                        d_assign, d_outlier or None, d_status))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            capi.lib().gmmloc_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

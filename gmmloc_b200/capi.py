@@ -1,0 +1,112 @@
+"""ctypes binding of libgmmloc_b200.so — exactly the entry points of include/gmmloc_b200.h.
+
+There is no CPU fallback: if the CUDA library is missing this module raises at import of the
+library handle, and every compute call fails with GMMLOC_ECUDA on a box without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libgmmloc_b200.so"
+
+OK, EINVAL, ENOMEM, ECUDA, ENUMERIC, EIO = range(6)
+MODE_JOINT, MODE_POSE_ONLY, MODE_POINTS_ONLY = 0, 1, 2
+FRAME_NUMERIC = 1
+
+
+class Camera(C.Structure):
+    """gmmloc_camera_t (gmmloc_ros/cfg/v1.yaml:5-17)."""
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("bf", C.c_double), ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class Params(C.Structure):
+    """gmmloc_params_t."""
+    _fields_ = [("tri_lambda2", C.c_double), ("ba_lambda2", C.c_double), ("tri_str_thresh", C.c_double),
+                ("tri_check_str_chi2", C.c_int32), ("mdist2_gate", C.c_double), ("chi2_mono", C.c_double),
+                ("chi2_stereo", C.c_double), ("gn_iters", C.c_int32), ("robust", C.c_int32),
+                ("factor_mode", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("points", C.c_int64), ("flagged", C.c_int64), ("kernel_launches", C.c_int64)]
+
+
+class GmmlocError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"gmmloc status {status}: {msg}")
+        self.status = status
+
+
+# every symbol include/gmmloc_b200.h declares: name -> (restype, argtypes)
+_vp, _i, _d, _i64 = C.c_void_p, C.c_int, C.c_double, C.c_int64
+SYMBOLS = {
+    "gmmloc_version": (C.c_char_p, []),
+    "gmmloc_status_string": (C.c_char_p, [_i]),
+    "gmmloc_last_error": (C.c_char_p, []),
+    "gmmloc_default_params": (None, [C.POINTER(Params)]),
+    "gmmloc_sigma2_inv": (C.c_float, [_i]),
+    "gmmloc_map_create": (_i, [_vp, _vp, _i, _d, _i, C.POINTER(_vp)]),
+    "gmmloc_map_load_gmm": (_i, [C.c_char_p, _d, _i, C.POINTER(_vp)]),
+    "gmmloc_map_save_gmm": (_i, [_vp, C.c_char_p]),
+    "gmmloc_map_destroy": (None, [_vp]),
+    "gmmloc_map_size": (_i, [_vp]),
+    "gmmloc_map_device": (_i, [_vp]),
+    "gmmloc_map_get_components": (_i, [_vp] * 10),
+    "gmmloc_map_scan_bound": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
+    "gmmloc_ctx_create": (_i, [_i, C.POINTER(_vp)]),
+    "gmmloc_ctx_destroy": (None, [_vp]),
+    "gmmloc_ctx_stream": (_vp, [_vp]),
+    "gmmloc_ctx_synchronize": (_i, [_vp]),
+    "gmmloc_ctx_stats": (_i, [_vp, C.POINTER(Stats)]),
+    "gmmloc_ctx_kernel_times": (_i, [_vp, C.POINTER(C.c_float * 3)]),
+    "gmmloc_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
+    "gmmloc_host_free": (None, [_vp]),
+    "gmmloc_associate": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp]),
+    "gmmloc_associate_async": (_i, [_vp, _vp, _vp, _i64, _d, _vp, _vp]),
+    "gmmloc_frames_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i] + [_vp] * 5),
+    "gmmloc_frames_solve_async": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i] + [_vp] * 5),
+    "gmmloc_points_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 6 + [_i, _i] + [_vp] * 4),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads the CUDA library; raises (loudly) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m gmmloc_b200.build` "
+                "(gmmloc_b200 has no CPU fallback)")
+        L = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the ABI lost a symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status: int) -> None:
+    if status != OK:
+        raise GmmlocError(status, lib().gmmloc_last_error().decode(errors="replace"))
+
+
+def default_params(**kw) -> Params:
+    p = Params()
+    lib().gmmloc_default_params(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise AttributeError(k)
+        setattr(p, k, v)
+    return p
+
+
+def v1_camera() -> Camera:
+    """Intrinsics shipped with the reference (gmmloc_ros/cfg/v1.yaml:5-17)."""
+    return Camera(435.2046959714599, 435.2046959714599, 367.4517211914062, 252.2008514404297,
+                  47.90639384423901, 752, 480)

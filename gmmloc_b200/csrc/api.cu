@@ -1,0 +1,689 @@
+// api.cu — the C ABI of include/gmmloc_b200.h: handles, workspaces, host<->device staging, launches.
+//
+// No CPU fallback anywhere: every entry point that computes needs a CUDA device and fails with
+// GMMLOC_ECUDA otherwise.  Nothing here links, loads or calls oracle/.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace gmmloc;
+
+namespace {
+
+thread_local std::string g_err;
+
+gmmloc_status_t fail_cuda(cudaError_t e, const char* where) {
+  g_err = std::string(where) + ": " + cudaGetErrorString(e);
+  cudaGetLastError();  // clear the sticky-less error state
+  return e == cudaErrorMemoryAllocation ? GMMLOC_ENOMEM : GMMLOC_ECUDA;
+}
+gmmloc_status_t fail(gmmloc_status_t s, const std::string& msg) {
+  g_err = msg;
+  return s;
+}
+
+#define CU(call)                                            \
+  do {                                                      \
+    cudaError_t e__ = (call);                               \
+    if (e__ != cudaSuccess) return fail_cuda(e__, #call);   \
+  } while (0)
+
+// grow-only device buffer
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return static_cast<T*>(p); }
+};
+
+void fill_params(const gmmloc_camera_t* cam, const gmmloc_params_t* prm, FrameParamsDev& d) {
+  d.fx = cam->fx; d.fy = cam->fy; d.cx = cam->cx; d.cy = cam->cy; d.bf = cam->bf;
+  d.tri_lambda2 = prm->tri_lambda2;
+  d.ba_lambda2 = prm->ba_lambda2;
+  d.tri_str_thresh = prm->tri_str_thresh;
+  d.mdist2_gate = prm->mdist2_gate;
+  d.chi2_mono = prm->chi2_mono;
+  d.chi2_stereo = prm->chi2_stereo;
+  d.delta_mono = (double)(float)std::sqrt(5.991);    // const float deltaMono = sqrt(5.991)  tracking_opt.cpp:57
+  d.delta_stereo = (double)(float)std::sqrt(7.815);  // tracking_opt.cpp:58
+  for (int i = 0; i < 8; ++i) d.s2inv[i] = gmmloc_sigma2_inv(i);
+  d.gn_iters = prm->gn_iters;
+  d.robust = prm->robust;
+  d.factor_mode = prm->factor_mode;
+  d.tri_check_str_chi2 = prm->tri_check_str_chi2;
+}
+
+// ---- .gmm wire format (protobuf_utils.cpp:12-101, GMM.proto:5-14) ------------------------------
+bool get_varint(const std::vector<unsigned char>& buf, size_t& pos, uint64_t& out) {
+  out = 0;
+  int shift = 0;
+  while (pos < buf.size() && shift < 64) {
+    const unsigned char c = buf[pos++];
+    out |= (uint64_t)(c & 0x7fu) << shift;
+    if ((c & 0x80u) == 0) return true;
+    shift += 7;
+  }
+  return false;
+}
+void put_varint(std::string& s, uint64_t v) {
+  while (v > 0x7f) {
+    s.push_back((char)((v & 0x7f) | 0x80));
+    v >>= 7;
+  }
+  s.push_back((char)v);
+}
+void put_double(std::string& s, double v) {
+  char t[8];
+  std::memcpy(t, &v, 8);
+  s.append(t, 8);
+}
+
+struct GmmFile {
+  std::vector<double> mean, cov;
+  std::vector<uint8_t> flags;  // K x 2 as stored
+};
+
+// parses one ComponentProto message occupying buf[pos, end)
+bool parse_component(const std::vector<unsigned char>& buf, size_t pos, size_t end, double* mean, double* cov,
+                     uint8_t* flags) {
+  int nmean = 0, ncov = 0;
+  flags[0] = flags[1] = 0;
+  auto take = [&](int field, double v) {
+    if (field == 3) {
+      if (nmean < 3) mean[nmean] = v;
+      ++nmean;
+    } else if (field == 4) {
+      if (ncov < 9) cov[ncov] = v;  // row-major fill like the loader, gmm_utils.cpp:55-59
+      ++ncov;
+    }
+  };
+  while (pos < end) {
+    uint64_t tag;
+    if (!get_varint(buf, pos, tag)) return false;
+    const int field = (int)(tag >> 3);
+    switch (tag & 7u) {
+      case 0: {
+        uint64_t v;
+        if (!get_varint(buf, pos, v)) return false;
+        if (field == 1) flags[0] = v ? 1 : 0;
+        if (field == 2) flags[1] = v ? 1 : 0;
+        break;
+      }
+      case 1: {
+        if (pos + 8 > end) return false;
+        double v;
+        std::memcpy(&v, &buf[pos], 8);
+        take(field, v);
+        pos += 8;
+        break;
+      }
+      case 2: {
+        uint64_t len;
+        if (!get_varint(buf, pos, len) || pos + len > end) return false;
+        if ((field == 3 || field == 4) && (len & 7u) == 0) {
+          for (uint64_t off = 0; off < len; off += 8) {
+            double v;
+            std::memcpy(&v, &buf[pos + off], 8);
+            take(field, v);
+          }
+        }
+        pos += len;
+        break;
+      }
+      case 5:
+        if (pos + 4 > end) return false;
+        pos += 4;
+        break;
+      default:
+        return false;
+    }
+  }
+  return pos == end && nmean == 3 && ncov == 9;  // CHECK_EQ sizes, gmm_utils.cpp:50-51
+}
+
+gmmloc_status_t read_gmm(const char* path, GmmFile& out) {
+  FILE* fp = std::fopen(path, "rb");
+  if (!fp) return fail(GMMLOC_EIO, std::string("cannot open ") + path);
+  std::vector<unsigned char> buf;
+  unsigned char chunk[1 << 16];
+  size_t got;
+  while ((got = std::fread(chunk, 1, sizeof chunk, fp)) > 0) buf.insert(buf.end(), chunk, chunk + got);
+  std::fclose(fp);
+  size_t pos = 0;
+  uint64_t count;
+  if (!get_varint(buf, pos, count)) return fail(GMMLOC_EIO, "could not read the message count");
+  if (count == 0 || count > (1u << 30)) return fail(GMMLOC_EIO, "protobuf file empty");  // gmm_utils.cpp:32-35
+  out.mean.resize(count * 3);
+  out.cov.resize(count * 9);
+  out.flags.resize(count * 2);
+  for (uint64_t k = 0; k < count; ++k) {
+    uint64_t len;
+    if (!get_varint(buf, pos, len) || len == 0 || pos + len > buf.size())
+      return fail(GMMLOC_EIO, "truncated component message " + std::to_string(k));
+    if (!parse_component(buf, pos, pos + len, &out.mean[k * 3], &out.cov[k * 9], &out.flags[k * 2]))
+      return fail(GMMLOC_EIO, "malformed component message " + std::to_string(k));
+    pos += len;
+  }
+  return GMMLOC_OK;
+}
+
+}  // namespace
+
+struct gmmloc_map {
+  MapDev d;
+  int device = 0;
+  std::vector<double> h_mean, h_cov;  // kept for save / get_components
+};
+
+struct gmmloc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevBuf flag_count, flag_idx, flag_thr;           // association work lists
+  DevBuf in_pts, in_obs, in_oct, in_pose, in_misc; // device copies of host inputs
+  DevBuf out_assign, out_d2, out_pose, out_pts, out_outlier, out_status, out_misc;
+  DevBuf xws, fws;
+  int* h_flag_count = nullptr;                     // pinned
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // scan begin | scan end | re-rank end | GN end
+  bool ev_assoc = false, ev_gn = false;
+  gmmloc_stats_t stats{};
+};
+
+extern "C" {
+
+const char* gmmloc_version(void) { return "gmmloc_b200 0.1 (sm_100a)"; }
+
+const char* gmmloc_status_string(gmmloc_status_t s) {
+  switch (s) {
+    case GMMLOC_OK: return "ok";
+    case GMMLOC_EINVAL: return "invalid argument";
+    case GMMLOC_ENOMEM: return "out of memory";
+    case GMMLOC_ECUDA: return "CUDA error / no device";
+    case GMMLOC_ENUMERIC: return "numeric failure";
+    case GMMLOC_EIO: return "I/O error";
+  }
+  return "unknown";
+}
+
+const char* gmmloc_last_error(void) { return g_err.c_str(); }
+
+void gmmloc_default_params(gmmloc_params_t* p) {
+  if (!p) return;
+  p->tri_lambda2 = 400.0;                 // v1.yaml:32
+  p->ba_lambda2 = 400.0;                  // v1.yaml:37
+  p->tri_str_thresh = (double)0.0064f;    // loc::tri_str_thresh is a float in the reference (config.h)
+  p->tri_check_str_chi2 = 1;              // v1.yaml:34
+  p->mdist2_gate = 9.0;                   // gmmloc_opt.cpp:230
+  p->chi2_mono = 5.991;                   // tracking_opt.cpp:145
+  p->chi2_stereo = 7.815;                 // tracking_opt.cpp:146
+  p->gn_iters = 10;                       // tracking_opt.cpp:147
+  p->robust = 0;
+  p->factor_mode = GMMLOC_MODE_JOINT;
+}
+
+float gmmloc_sigma2_inv(int octave) {
+  // scale_factors[i] = scale_factors[i-1] * 1.2f; sigma2 = sf*sf; sigma2_inv = 1.0f / sigma2   (float)
+  if (octave < 0) octave = 0;
+  if (octave > 7) octave = 7;
+  volatile float sf = 1.0f;
+  float inv = 1.0f;
+  for (int i = 1; i <= octave; ++i) {
+    sf = sf * 1.2f;
+    const float s2 = sf * sf;
+    inv = 1.0f / s2;
+  }
+  return inv;
+}
+
+// ---- map -----------------------------------------------------------------------------------------
+void gmmloc_map_destroy(gmmloc_map_t* m) {
+  if (!m) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(m->device);
+  cudaFree(m->d.mean); cudaFree(m->d.cov); cudaFree(m->d.cov_inv); cudaFree(m->d.det); cudaFree(m->d.scale);
+  cudaFree(m->d.axis); cudaFree(m->d.sqrt_info); cudaFree(m->d.is_deg); cudaFree(m->d.is_sal); cudaFree(m->d.scan);
+  cudaSetDevice(prev);
+  delete m;
+}
+
+gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, double deg_eps, int device,
+                                  gmmloc_map_t** out) {
+  if (!mean || !cov || !out || K <= 0) return fail(GMMLOC_EINVAL, "gmmloc_map_create: null pointer or K <= 0");
+  *out = nullptr;
+  CU(cudaSetDevice(device));
+  gmmloc_map* m = new (std::nothrow) gmmloc_map();
+  if (!m) return fail(GMMLOC_ENOMEM, "host allocation failed");
+  m->device = device;
+  m->h_mean.assign(mean, mean + (size_t)K * 3);
+  m->h_cov.assign(cov, cov + (size_t)K * 9);
+  MapDev& d = m->d;
+  d.K = K;
+  d.Kpad = (K + kChunk - 1) / kChunk * kChunk;
+  double mmax = 0.0;
+  for (size_t i = 0; i < (size_t)K * 3; ++i) {
+    if (!std::isfinite(mean[i])) {
+      delete m;
+      return fail(GMMLOC_EINVAL, "non-finite mean");
+    }
+    mmax = std::fmax(mmax, std::fabs(mean[i]));
+  }
+  // landmarks are certified by the fp32 scan only inside |x|_inf <= xmax; anything farther out takes the
+  // exact fp64 path (still correct, just slower)
+  const double xmax = 1.5 * mmax + 1.0;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+  };
+  alloc((void**)&d.mean, sizeof(double) * 3 * K);
+  alloc((void**)&d.cov, sizeof(double) * 9 * K);
+  alloc((void**)&d.cov_inv, sizeof(double) * 9 * K);
+  alloc((void**)&d.det, sizeof(double) * K);
+  alloc((void**)&d.scale, sizeof(double) * 3 * K);
+  alloc((void**)&d.axis, sizeof(double) * 9 * K);
+  alloc((void**)&d.sqrt_info, sizeof(double) * 9 * K);
+  alloc((void**)&d.is_deg, K);
+  alloc((void**)&d.is_sal, K);
+  alloc((void**)&d.scan, sizeof(float) * kScanFloats * d.Kpad);
+  int* d_err = nullptr;
+  alloc((void**)&d_err, 2 * sizeof(int));
+  if (e != cudaSuccess) {
+    cudaFree(d_err);
+    gmmloc_map_destroy(m);
+    return fail_cuda(e, "cudaMalloc(map)");
+  }
+  auto bail = [&](cudaError_t ce, const char* where) {
+    cudaFree(d_err);
+    gmmloc_map_destroy(m);
+    return fail_cuda(ce, where);
+  };
+  if ((e = cudaMemcpy(d.mean, mean, sizeof(double) * 3 * K, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D mean");
+  if ((e = cudaMemcpy(d.cov, cov, sizeof(double) * 9 * K, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D cov");
+  if ((e = cudaMemset(d_err, 0, 2 * sizeof(int))) != cudaSuccess) return bail(e, "memset");
+  if ((e = launch_map_build(d, deg_eps, xmax, d_err, reinterpret_cast<unsigned int*>(d_err + 1), nullptr)) != cudaSuccess)
+    return bail(e, "map_build launch");
+  int h[2] = {0, 0};
+  if ((e = cudaMemcpy(h, d_err, sizeof h, cudaMemcpyDeviceToHost)) != cudaSuccess) return bail(e, "map_build");
+  cudaFree(d_err);
+  if (h[0] != 0) {
+    gmmloc_map_destroy(m);
+    return fail(GMMLOC_EINVAL, "covariance not symmetric positive definite (or non-finite)");
+  }
+  float alpha;
+  std::memcpy(&alpha, &h[1], 4);
+  d.alpha = alpha;
+  d.xmax = (float)xmax;
+  *out = m;
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_map_load_gmm(const char* path, double deg_eps, int device, gmmloc_map_t** out) {
+  if (!path || !out) return fail(GMMLOC_EINVAL, "gmmloc_map_load_gmm: null pointer");
+  GmmFile f;
+  gmmloc_status_t s = read_gmm(path, f);
+  if (s != GMMLOC_OK) return s;  // bool false + LOG(ERROR) in the reference, gmm_utils.cpp:19-48
+  return gmmloc_map_create(f.mean.data(), f.cov.data(), (int)(f.mean.size() / 3), deg_eps, device, out);
+}
+
+gmmloc_status_t gmmloc_map_save_gmm(const gmmloc_map_t* map, const char* path) {
+  if (!map || !path) return fail(GMMLOC_EINVAL, "gmmloc_map_save_gmm: null pointer");
+  const int K = map->d.K;
+  std::vector<uint8_t> deg(K), sal(K);
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CU(cudaSetDevice(map->device));
+  CU(cudaMemcpy(deg.data(), map->d.is_deg, K, cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(sal.data(), map->d.is_sal, K, cudaMemcpyDeviceToHost));
+  cudaSetDevice(prev);
+  std::string s;
+  put_varint(s, (uint64_t)K);  // writeProtoMsgCountToStream, gmm_utils.cpp:87-92
+  for (int k = 0; k < K; ++k) {
+    std::string msg;
+    msg.push_back(0x08); msg.push_back((char)deg[k]);  // is_degenerated  gmm_utils.cpp:97
+    msg.push_back(0x10); msg.push_back((char)sal[k]);  // is_salient      gmm_utils.cpp:99
+    msg.push_back(0x1a); msg.push_back(24);
+    for (int i = 0; i < 3; ++i) put_double(msg, map->h_mean[(size_t)k * 3 + i]);
+    msg.push_back(0x22); msg.push_back(72);
+    for (int i = 0; i < 9; ++i) put_double(msg, map->h_cov[(size_t)k * 9 + (i % 3) * 3 + i / 3]);  // cov(i): column-major, :107
+    put_varint(s, msg.size());
+    s += msg;
+  }
+  FILE* fp = std::fopen(path, "wb");
+  if (!fp) return fail(GMMLOC_EIO, std::string("cannot open ") + path + " for writing");
+  const size_t w = std::fwrite(s.data(), 1, s.size(), fp);
+  std::fclose(fp);
+  if (w != s.size()) return fail(GMMLOC_EIO, "short write");
+  return GMMLOC_OK;
+}
+
+int gmmloc_map_size(const gmmloc_map_t* map) { return map ? map->d.K : 0; }
+int gmmloc_map_device(const gmmloc_map_t* map) { return map ? map->device : -1; }
+
+gmmloc_status_t gmmloc_map_get_components(const gmmloc_map_t* map, double* mean, double* cov, double* cov_inv,
+                                          double* det, double* scale, double* axis, double* sqrt_info,
+                                          uint8_t* is_degenerated, uint8_t* is_salient) {
+  if (!map) return fail(GMMLOC_EINVAL, "null map");
+  const size_t K = map->d.K;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CU(cudaSetDevice(map->device));
+  if (mean) CU(cudaMemcpy(mean, map->d.mean, 24 * K, cudaMemcpyDeviceToHost));
+  if (cov) CU(cudaMemcpy(cov, map->d.cov, 72 * K, cudaMemcpyDeviceToHost));
+  if (cov_inv) CU(cudaMemcpy(cov_inv, map->d.cov_inv, 72 * K, cudaMemcpyDeviceToHost));
+  if (det) CU(cudaMemcpy(det, map->d.det, 8 * K, cudaMemcpyDeviceToHost));
+  if (scale) CU(cudaMemcpy(scale, map->d.scale, 24 * K, cudaMemcpyDeviceToHost));
+  if (axis) CU(cudaMemcpy(axis, map->d.axis, 72 * K, cudaMemcpyDeviceToHost));
+  if (sqrt_info) CU(cudaMemcpy(sqrt_info, map->d.sqrt_info, 72 * K, cudaMemcpyDeviceToHost));
+  if (is_degenerated) CU(cudaMemcpy(is_degenerated, map->d.is_deg, K, cudaMemcpyDeviceToHost));
+  if (is_salient) CU(cudaMemcpy(is_salient, map->d.is_sal, K, cudaMemcpyDeviceToHost));
+  cudaSetDevice(prev);
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_map_scan_bound(const gmmloc_map_t* map, double* alpha, double* xmax) {
+  if (!map) return fail(GMMLOC_EINVAL, "null map");
+  if (alpha) *alpha = map->d.alpha;
+  if (xmax) *xmax = map->d.xmax;
+  return GMMLOC_OK;
+}
+
+// ---- context -------------------------------------------------------------------------------------
+gmmloc_status_t gmmloc_ctx_create(int device, gmmloc_ctx_t** out) {
+  if (!out) return fail(GMMLOC_EINVAL, "null out");
+  *out = nullptr;
+  CU(cudaSetDevice(device));
+  gmmloc_ctx* c = new (std::nothrow) gmmloc_ctx();
+  if (!c) return fail(GMMLOC_ENOMEM, "host allocation failed");
+  c->device = device;
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_flag_count, sizeof(int));
+  if (e == cudaSuccess) e = c->flag_count.reserve(sizeof(int));
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
+  if (e != cudaSuccess) {
+    gmmloc_ctx_destroy(c);
+    return fail_cuda(e, "gmmloc_ctx_create");
+  }
+  *out = c;
+  return GMMLOC_OK;
+}
+
+void gmmloc_ctx_destroy(gmmloc_ctx_t* c) {
+  if (!c) return;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  DevBuf* bufs[] = {&c->flag_count, &c->flag_idx, &c->flag_thr, &c->in_pts, &c->in_obs, &c->in_oct, &c->in_pose,
+                    &c->in_misc, &c->out_assign, &c->out_d2, &c->out_pose, &c->out_pts, &c->out_outlier,
+                    &c->out_status, &c->out_misc, &c->xws, &c->fws};
+  for (DevBuf* b : bufs) b->release();
+  if (c->h_flag_count) cudaFreeHost(c->h_flag_count);
+  for (cudaEvent_t e : c->ev)
+    if (e) cudaEventDestroy(e);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  cudaSetDevice(prev);
+  delete c;
+}
+
+void* gmmloc_ctx_stream(gmmloc_ctx_t* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+gmmloc_status_t gmmloc_ctx_synchronize(gmmloc_ctx_t* ctx) {
+  if (!ctx) return fail(GMMLOC_EINVAL, "null ctx");
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_ctx_stats(gmmloc_ctx_t* ctx, gmmloc_stats_t* out) {
+  if (!ctx || !out) return fail(GMMLOC_EINVAL, "null pointer");
+  // the flagged count of the last association is read back lazily (stream must be idle for it to be final)
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaMemcpyAsync(ctx->h_flag_count, ctx->flag_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stats.flagged = *ctx->h_flag_count;
+  *out = ctx->stats;
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_ctx_kernel_times(gmmloc_ctx_t* ctx, float ms[3]) {
+  if (!ctx || !ms) return fail(GMMLOC_EINVAL, "null pointer");
+  ms[0] = ms[1] = ms[2] = 0.f;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (ctx->ev_assoc) {
+    CU(cudaEventElapsedTime(&ms[0], ctx->ev[0], ctx->ev[1]));
+    CU(cudaEventElapsedTime(&ms[1], ctx->ev[1], ctx->ev[2]));
+  }
+  if (ctx->ev_gn) CU(cudaEventElapsedTime(&ms[2], ctx->ev[2], ctx->ev[3]));
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(GMMLOC_EINVAL, "null out");
+  *out = nullptr;
+  CU(cudaMallocHost(out, bytes ? bytes : 1));
+  return GMMLOC_OK;
+}
+void gmmloc_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// ---- association ---------------------------------------------------------------------------------
+gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const float* d_pts_w, int64_t M,
+                                       double gate, int32_t* d_assign, float* d_d2) {
+  if (!ctx || !map || !d_assign || M < 0 || (M > 0 && !d_pts_w)) return fail(GMMLOC_EINVAL, "gmmloc_associate: bad argument");
+  if (M >= (int64_t)1 << 31) return fail(GMMLOC_EINVAL, "gmmloc_associate: M must be < 2^31 per call");
+  if (map->device != ctx->device) return fail(GMMLOC_EINVAL, "map and context live on different devices");
+  ctx->stats.points = M;
+  if (M == 0) return GMMLOC_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->flag_idx.reserve(sizeof(int32_t) * (size_t)M));
+  CU(ctx->flag_thr.reserve(sizeof(float) * (size_t)M));
+  CU(cudaMemsetAsync(ctx->flag_count.p, 0, sizeof(int), ctx->stream));
+  int launches = 0;
+  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+  CU(launch_associate(map->d, d_pts_w, M, gate, d_assign, d_d2, ctx->flag_count.as<int>(), ctx->flag_idx.as<int32_t>(),
+                      ctx->flag_thr.as<float>(), 0, ctx->stream, &launches, ctx->ev[1]));
+  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  ctx->ev_assoc = true;
+  ctx->ev_gn = false;
+  ctx->stats.kernel_launches += launches;
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_associate(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const float* pts_w, int B, int N, double gate,
+                                 int32_t* assign, float* d2) {
+  if (!ctx || !map || !assign || B < 0 || N < 0) return fail(GMMLOC_EINVAL, "gmmloc_associate: bad argument");
+  const int64_t M = (int64_t)B * N;
+  if (M == 0) {
+    ctx->stats.points = 0;
+    return GMMLOC_OK;
+  }
+  if (!pts_w) return fail(GMMLOC_EINVAL, "gmmloc_associate: null landmarks");
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->in_pts.reserve(12 * (size_t)M));
+  CU(ctx->out_assign.reserve(4 * (size_t)M));
+  if (d2) CU(ctx->out_d2.reserve(4 * (size_t)M));
+  CU(cudaMemcpyAsync(ctx->in_pts.p, pts_w, 12 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  gmmloc_status_t s = gmmloc_associate_async(ctx, map, ctx->in_pts.as<float>(), M, gate, ctx->out_assign.as<int32_t>(),
+                                             d2 ? ctx->out_d2.as<float>() : nullptr);
+  if (s != GMMLOC_OK) return s;
+  CU(cudaMemcpyAsync(assign, ctx->out_assign.p, 4 * (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
+  if (d2) CU(cudaMemcpyAsync(d2, ctx->out_d2.p, 4 * (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return GMMLOC_OK;
+}
+
+// ---- frame solve ---------------------------------------------------------------------------------
+gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                          const gmmloc_params_t* params, const double* d_pose0, const float* d_pts_w,
+                                          const float* d_obs, const uint8_t* d_octave, int B, int N, double* d_pose_out,
+                                          float* d_pts_out, int32_t* d_assign, uint8_t* d_outlier, int32_t* d_status) {
+  if (!ctx || !map || !cam || !params || B < 0 || N < 0) return fail(GMMLOC_EINVAL, "gmmloc_frames_solve: bad argument");
+  if (B == 0) return GMMLOC_OK;
+  if (!d_pose0 || !d_pose_out || !d_status || (N > 0 && (!d_pts_w || !d_obs || !d_octave || !d_assign)))
+    return fail(GMMLOC_EINVAL, "gmmloc_frames_solve: null pointer");
+  if (params->gn_iters < 0 || params->factor_mode < 0 || params->factor_mode > 2)
+    return fail(GMMLOC_EINVAL, "gmmloc_frames_solve: bad params");
+  if (map->device != ctx->device) return fail(GMMLOC_EINVAL, "map and context live on different devices");
+  CU(cudaSetDevice(ctx->device));
+  const int64_t M = (int64_t)B * N;
+  // association: ungated argmin (the 9.0 gate of gmmloc_opt.cpp:230 applies after refinement;
+  // here it is the structure-edge gate evaluated inside the solve)
+  if (params->factor_mode != GMMLOC_MODE_POSE_ONLY) {
+    gmmloc_status_t s = gmmloc_associate_async(ctx, map, d_pts_w, M, 0.0, d_assign, nullptr);
+    if (s != GMMLOC_OK) return s;
+  } else {
+    ctx->ev_assoc = false;
+    if (M > 0) CU(cudaMemsetAsync(d_assign, 0xff, 4 * (size_t)M, ctx->stream));  // -1: no structure edges in pose-only mode
+  }
+  FrameArgs a;
+  a.mean = map->d.mean;
+  a.cov_inv = map->d.cov_inv;
+  a.axis = map->d.axis;
+  a.is_deg = map->d.is_deg;
+  fill_params(cam, params, a.prm);
+  a.pose0 = d_pose0;
+  a.pts_w = d_pts_w;
+  a.obs = d_obs;
+  a.octave = d_octave;
+  a.assign = d_assign;
+  a.B = B;
+  a.N = N;
+  a.pose_out = d_pose_out;
+  a.pts_out = d_pts_out;
+  a.outlier = d_outlier;
+  a.status = d_status;
+  a.xws = nullptr;
+  a.fws = nullptr;
+  if ((size_t)N > frame_gn_smem_limit_points()) {
+    CU(ctx->xws.reserve(24 * (size_t)M));
+    CU(ctx->fws.reserve((size_t)M));
+    a.xws = ctx->xws.as<double>();
+    a.fws = ctx->fws.as<uint8_t>();
+  }
+  if (!ctx->ev_assoc) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
+  CU(launch_frame_gn(a, ctx->stream));
+  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
+  ctx->ev_gn = true;
+  ctx->stats.kernel_launches += 1;
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                    const gmmloc_params_t* params, const double* pose0, const float* pts_w,
+                                    const float* obs, const uint8_t* octave, int B, int N, double* pose_out, float* pts_out,
+                                    int32_t* assign, uint8_t* outlier, int32_t* status) {
+  if (!ctx || !map || !cam || !params || B < 0 || N < 0) return fail(GMMLOC_EINVAL, "gmmloc_frames_solve: bad argument");
+  if (B == 0) return GMMLOC_OK;
+  if (!pose0 || !pose_out || !status || (N > 0 && (!pts_w || !obs || !octave)))
+    return fail(GMMLOC_EINVAL, "gmmloc_frames_solve: null pointer");
+  CU(cudaSetDevice(ctx->device));
+  const size_t M = (size_t)B * N;
+  CU(ctx->in_pose.reserve(56 * (size_t)B));
+  CU(ctx->in_pts.reserve(12 * M + 16));
+  CU(ctx->in_obs.reserve(12 * M + 16));
+  CU(ctx->in_oct.reserve(M + 16));
+  CU(ctx->out_pose.reserve(56 * (size_t)B));
+  CU(ctx->out_assign.reserve(4 * M + 16));
+  CU(ctx->out_status.reserve(4 * (size_t)B));
+  if (pts_out) CU(ctx->out_pts.reserve(12 * M + 16));
+  if (outlier) CU(ctx->out_outlier.reserve(M + 16));
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(ctx->in_pose.p, pose0, 56 * (size_t)B, cudaMemcpyHostToDevice, st));
+  if (M) {
+    CU(cudaMemcpyAsync(ctx->in_pts.p, pts_w, 12 * M, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->in_obs.p, obs, 12 * M, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->in_oct.p, octave, M, cudaMemcpyHostToDevice, st));
+  }
+  gmmloc_status_t s = gmmloc_frames_solve_async(
+      ctx, map, cam, params, ctx->in_pose.as<double>(), ctx->in_pts.as<float>(), ctx->in_obs.as<float>(),
+      ctx->in_oct.as<uint8_t>(), B, N, ctx->out_pose.as<double>(), pts_out ? ctx->out_pts.as<float>() : nullptr,
+      ctx->out_assign.as<int32_t>(), outlier ? ctx->out_outlier.as<uint8_t>() : nullptr, ctx->out_status.as<int32_t>());
+  if (s != GMMLOC_OK) return s;
+  CU(cudaMemcpyAsync(pose_out, ctx->out_pose.p, 56 * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(status, ctx->out_status.p, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (M) {
+    if (assign) CU(cudaMemcpyAsync(assign, ctx->out_assign.p, 4 * M, cudaMemcpyDeviceToHost, st));
+    if (pts_out) CU(cudaMemcpyAsync(pts_out, ctx->out_pts.p, 12 * M, cudaMemcpyDeviceToHost, st));
+    if (outlier) CU(cudaMemcpyAsync(outlier, ctx->out_outlier.p, M, cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  return GMMLOC_OK;
+}
+
+// ---- batched point solves ------------------------------------------------------------------------
+gmmloc_status_t gmmloc_points_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                    const gmmloc_params_t* params, const double* x0, const float* obs,
+                                    const uint8_t* octave, const double* pose, const int32_t* comp, const double* proj_z2,
+                                    int M, int iters, double* pt_est, double* chi2_proj, double* chi2_str, uint8_t* res) {
+  if (!ctx || !map || !cam || !params || M < 0 || iters < 0) return fail(GMMLOC_EINVAL, "gmmloc_points_solve: bad argument");
+  if (M == 0) return GMMLOC_OK;
+  if (!x0 || !obs || !octave || !pose || !comp || !proj_z2 || !pt_est || !chi2_proj || !chi2_str || !res)
+    return fail(GMMLOC_EINVAL, "gmmloc_points_solve: null pointer");
+  if (map->device != ctx->device) return fail(GMMLOC_EINVAL, "map and context live on different devices");
+  CU(cudaSetDevice(ctx->device));
+  const size_t m = (size_t)M;
+  // one input slab: x0 (24) | pose (56) | proj_z2 (8) | obs (12) | comp (4) | octave (1)
+  const size_t o_x0 = 0, o_pose = o_x0 + 24 * m, o_pz = o_pose + 56 * m, o_obs = o_pz + 8 * m, o_comp = o_obs + 12 * m,
+               o_oct = o_comp + 4 * m, in_bytes = o_oct + m;
+  // one output slab: pt_est (24) | chi2_proj (8) | chi2_str (8) | res (1)
+  const size_t q_pt = 0, q_cp = 24 * m, q_cs = q_cp + 8 * m, q_res = q_cs + 8 * m, out_bytes = q_res + m;
+  CU(ctx->in_misc.reserve(in_bytes));
+  CU(ctx->out_misc.reserve(out_bytes));
+  char* in = ctx->in_misc.as<char>();
+  char* outp = ctx->out_misc.as<char>();
+  cudaStream_t st = ctx->stream;
+  CU(cudaMemcpyAsync(in + o_x0, x0, 24 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_pose, pose, 56 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_pz, proj_z2, 8 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_obs, obs, 12 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_comp, comp, 4 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_oct, octave, m, cudaMemcpyHostToDevice, st));
+  PointArgs a;
+  a.mean = map->d.mean;
+  a.axis = map->d.axis;
+  fill_params(cam, params, a.prm);
+  a.x0 = reinterpret_cast<const double*>(in + o_x0);
+  a.pose = reinterpret_cast<const double*>(in + o_pose);
+  a.proj_z2 = reinterpret_cast<const double*>(in + o_pz);
+  a.obs = reinterpret_cast<const float*>(in + o_obs);
+  a.comp = reinterpret_cast<const int32_t*>(in + o_comp);
+  a.octave = reinterpret_cast<const uint8_t*>(in + o_oct);
+  a.M = M;
+  a.iters = iters;
+  a.K = map->d.K;
+  a.pt_est = reinterpret_cast<double*>(outp + q_pt);
+  a.chi2_proj = reinterpret_cast<double*>(outp + q_cp);
+  a.chi2_str = reinterpret_cast<double*>(outp + q_cs);
+  a.res = reinterpret_cast<uint8_t*>(outp + q_res);
+  CU(launch_point_gn(a, st));
+  ctx->stats.kernel_launches += 1;
+  CU(cudaMemcpyAsync(pt_est, outp + q_pt, 24 * m, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(chi2_proj, outp + q_cp, 8 * m, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(chi2_str, outp + q_cs, 8 * m, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res, outp + q_res, m, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return GMMLOC_OK;
+}
+
+}  // extern "C"

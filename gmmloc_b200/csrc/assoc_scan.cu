@@ -286,7 +286,7 @@ cudaError_t launch_scan_t(const ScanArgs& a, cudaStream_t stream) {
 // flag buffers hold M entries.  Returns the number of kernels launched through *launches.
 cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, double gate, int32_t* d_assign,
                              float* d_d2, int* d_flag_count, int32_t* d_flag_idx, float* d_flag_thr, int variant,
-                             cudaStream_t stream, int* launches) {
+                             cudaStream_t stream, int* launches, cudaEvent_t ev_between) {
   ScanArgs a;
   a.scan = m.scan;
   a.mean = m.mean;
@@ -319,6 +319,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
     default: e = launch_scan_t<1, 128, 4>(a, stream); break;
   }
   if (e != cudaSuccess) return e;
+  if (ev_between != nullptr && (e = cudaEventRecord(ev_between, stream)) != cudaSuccess) return e;
   assoc_rerank_kernel<<<148 * 4, 256, 0, stream>>>(a);
   if (launches) *launches = 2;
   return cudaGetLastError();

@@ -34,10 +34,57 @@ struct MapDev {
 
 struct FrameParamsDev {
   double fx, fy, cx, cy, bf;
-  double ba_lambda2, tri_str_thresh, mdist2_gate, chi2_mono, chi2_stereo;
+  double tri_lambda2, ba_lambda2, tri_str_thresh, mdist2_gate, chi2_mono, chi2_stereo;
   double delta_mono, delta_stereo;  // Huber deltas: (double)(float)sqrt(5.991 / 7.815)  tracking_opt.cpp:57-58
-  int gn_iters, robust, factor_mode;
+  float s2inv[8];                   // frame::sigma2_inv[octave], computed in float on the host (init_config.hpp:63-78)
+  int gn_iters, robust, factor_mode, tri_check_str_chi2;
 };
+
+// Host-side launchers (one per kernel family); every launcher only enqueues on `stream`.
+cudaError_t launch_map_build(const MapDev& m, double deg_eps, double xmax, int* d_err, unsigned int* d_alpha_bits,
+                             cudaStream_t stream);
+cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, double gate, int32_t* d_assign,
+                             float* d_d2, int* d_flag_count, int32_t* d_flag_idx, float* d_flag_thr, int variant,
+                             cudaStream_t stream, int* launches, cudaEvent_t ev_between = nullptr);
+struct FrameArgs {
+  const double* mean;       // map constants (fp64)
+  const double* cov_inv;
+  const double* axis;
+  const uint8_t* is_deg;
+  FrameParamsDev prm;
+  const double* pose0;      // B x 7
+  const float* pts_w;       // B x N x 3
+  const float* obs;         // B x N x 3
+  const uint8_t* octave;    // B x N
+  const int32_t* assign;    // B x N
+  int B, N;
+  double* pose_out;         // B x 7
+  float* pts_out;           // B x N x 3 or null
+  uint8_t* outlier;         // B x N or null
+  int32_t* status;          // B
+  double* xws;              // B x N x 3 fp64 workspace when a frame does not fit in shared memory, else null
+  uint8_t* fws;             // B x N flag workspace (same condition)
+};
+cudaError_t launch_frame_gn(const FrameArgs& a, cudaStream_t stream);
+size_t frame_gn_smem_limit_points();  // largest N whose per-frame state stays in shared memory
+
+struct PointArgs {
+  const double* mean;
+  const double* axis;
+  FrameParamsDev prm;
+  const double* x0;       // M x 3
+  const float* obs;       // M x 3
+  const uint8_t* octave;  // M
+  const double* pose;     // M x 7
+  const int32_t* comp;    // M
+  const double* proj_z2;  // M
+  int M, iters, K;
+  double* pt_est;     // M x 3
+  double* chi2_proj;  // M
+  double* chi2_str;   // M
+  uint8_t* res;       // M
+};
+cudaError_t launch_point_gn(const PointArgs& a, cudaStream_t stream);
 
 // ---- exact (non-contracted) fp64 helpers: the re-rank and the map build must replay the CPU
 // oracle's operation order bit for bit, so every product and sum is an explicit IEEE rn op. ----

@@ -1,0 +1,545 @@
+// frame_gn.cu — K3: per-frame structure-constrained Gauss-Newton (one CTA per frame, fp64).
+//
+// Replaces the single-free-pose specialisation of Localization::jointOptimization (reference
+// gmmloc/src/modules/localization_opt.cpp:456-925): one VertexSE3Expmap + N marginalised
+// VertexSBAPointXYZ, one reprojection edge per point (EdgeStereoSE3ProjectXYZ / EdgeSE3ProjectXYZ,
+// point Jacobians as gmmloc/src/gmm/factors.cpp:84-107,133-168) and one structure edge per associated
+// point (EdgePt2GaussianDeg factors.cpp:55-64, information ba_lambda2, localization_opt.cpp:657-669;
+// EdgePt2Gaussian factors.cpp:5-17, information I, localization_opt.cpp:670-681).  factor_mode
+// POSE_ONLY gives the system of Tracking::optimizeCurrentPose (gmmloc/src/modules/tracking_opt.cpp:21-217),
+// POINTS_ONLY the per-point structure-constrained solves.
+//
+// Formulation.  BlockSolver_6_3's Schur complement is evaluated per point in the
+// CAMERA frame, where every Jacobian factors through the 3x3 projection derivative P = d proj / d pc:
+//     G = w P^T P,  h = w P^T e                       (reprojection, camera frame)
+//     S_c = R S R^T, s_c = R b_s                      (structure edge rotated into the camera frame)
+//     D = G + S_c  (= R Hll R^T),  T = G D^-1
+//     pose block   += A^T (T S_c) A,   pose rhs += A^T (h - T (h + s_c)),   A = d pc / d xi = [-[pc]x  I]
+//     point update  dx_w = R^T D^-1 (h + s_c - G A dxi)
+// which equals Hpp - Hpl Hll^-1 Hpl^T etc. of the reference, with 3x3 work only.  A free point WITHOUT a
+// structure edge has T = I: it absorbs its own reprojection error and contributes exactly nothing to
+// the pose system, so it is skipped in the accumulation pass.
+//
+// Per-frame state (landmarks in fp64, edge flags) lives in shared memory for all iterations: HBM is
+// read once per frame.  Reductions are fixed-shape (per-thread strided sum -> warp shuffle tree ->
+// fixed-order cross-warp sum): deterministic, no float atomics.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace gmmloc {
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kWarps = kThreads / 32;
+constexpr int kAcc = 27;  // 21 upper-triangular entries of the 6x6 + 6 rhs
+
+enum : uint8_t { F_STEREO = 1, F_STR = 2, F_FREE = 4, F_DEG = 8 };
+
+struct Sym3 {
+  double xx, xy, xz, yy, yz, zz;
+};
+struct Vec3 {
+  double x, y, z;
+};
+
+__device__ __forceinline__ Vec3 rot(const double* R, const Vec3& v) {
+  return {R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z};
+}
+__device__ __forceinline__ Vec3 rot_t(const double* R, const Vec3& v) {
+  return {R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z};
+}
+__device__ __forceinline__ Vec3 mul(const Sym3& A, const Vec3& v) {
+  return {A.xx * v.x + A.xy * v.y + A.xz * v.z, A.xy * v.x + A.yy * v.y + A.yz * v.z, A.xz * v.x + A.yz * v.y + A.zz * v.z};
+}
+__device__ __forceinline__ Vec3 cross(const Vec3& a, const Vec3& b) {
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+// inverse of a symmetric 3x3 by cofactors; ok=false when det is zero / non-finite (Hll singular)
+__device__ __forceinline__ Sym3 inv_sym(const Sym3& D, bool& ok) {
+  const double c00 = D.yy * D.zz - D.yz * D.yz;
+  const double c01 = D.xz * D.yz - D.xy * D.zz;
+  const double c02 = D.xy * D.yz - D.xz * D.yy;
+  const double det = D.xx * c00 + D.xy * c01 + D.xz * c02;
+  const double id = 1.0 / det;
+  ok = (det != 0.0) && isfinite(id);
+  return {c00 * id, c01 * id, c02 * id, (D.xx * D.zz - D.xz * D.xz) * id, (D.xy * D.xz - D.xx * D.yz) * id,
+          (D.xx * D.yy - D.xy * D.xy) * id};
+}
+
+__device__ __forceinline__ void reproj(const FrameParamsDev& p, const Vec3& pc, float o0, float o1, float o2, bool stereo,
+                                       double w, Sym3& G, Vec3& h) {
+  const double invz = 1.0 / pc.z;
+  const double a = p.fx * invz, b = p.fy * invz;
+  const double u = pc.x * a + p.cx, v = pc.y * b + p.cy;
+  const double e0 = (double)o0 - u, e1 = (double)o1 - v;
+  const double c0 = -a * pc.x * invz, c1 = -b * pc.y * invz;
+  double e2 = 0.0, c2 = 0.0, a2 = 0.0;
+  if (stereo) {
+    const double bz = p.bf * invz;
+    e2 = (double)o2 - (u - bz);
+    c2 = c0 + bz * invz;
+    a2 = a;
+  }
+  if (p.robust) {  // g2o RobustKernelHuber: weight rho1 = delta / sqrt(e2) beyond delta^2
+    const double chi = w * (e0 * e0 + e1 * e1 + e2 * e2);
+    const double delta = stereo ? p.delta_stereo : p.delta_mono;
+    if (chi > delta * delta) w *= delta / sqrt(chi);
+  }
+  G.xx = w * (a * a + a2 * a2);
+  G.xy = 0.0;
+  G.xz = w * (a * c0 + a2 * c2);
+  G.yy = w * (b * b);
+  G.yz = w * (b * c1);
+  G.zz = w * (c0 * c0 + c1 * c1 + c2 * c2);
+  h.x = w * (a * e0 + a2 * e2);
+  h.y = w * (b * e1);
+  h.z = w * (c0 * e0 + c1 * e1 + c2 * e2);
+}
+
+__device__ __forceinline__ void structure(const FrameArgs& a, const double* R, int k, uint8_t fl, const Vec3& xw, Sym3& S,
+                                          Vec3& s) {
+  const double* mu = a.mean + (size_t)k * 3;
+  const Vec3 d = {xw.x - mu[0], xw.y - mu[1], xw.z - mu[2]};
+  if (fl & F_DEG) {
+    const double* ax = a.axis + (size_t)k * 9;
+    const Vec3 n = {ax[0], ax[3], ax[6]};  // axis_.col(0)
+    const double es = n.x * d.x + n.y * d.y + n.z * d.z;
+    const Vec3 nc = rot(R, n);
+    const double lam = a.prm.ba_lambda2;
+    S = {lam * nc.x * nc.x, lam * nc.x * nc.y, lam * nc.x * nc.z, lam * nc.y * nc.y, lam * nc.y * nc.z, lam * nc.z * nc.z};
+    const double c = -lam * es;
+    s = {c * nc.x, c * nc.y, c * nc.z};
+  } else {
+    // EdgePt2Gaussian: J = L^T, Omega = I  =>  Hessian L L^T = cov_inv, rhs -cov_inv d
+    const double* A = a.cov_inv + (size_t)k * 9;
+    const Sym3 Sw = {A[0], A[1], A[2], A[4], A[5], A[8]};
+    const Vec3 bw = mul(Sw, d);
+    s = rot(R, {-bw.x, -bw.y, -bw.z});
+    // S_c = R Sw R^T
+    double t[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      t[r * 3 + 0] = R[r * 3] * Sw.xx + R[r * 3 + 1] * Sw.xy + R[r * 3 + 2] * Sw.xz;
+      t[r * 3 + 1] = R[r * 3] * Sw.xy + R[r * 3 + 1] * Sw.yy + R[r * 3 + 2] * Sw.yz;
+      t[r * 3 + 2] = R[r * 3] * Sw.xz + R[r * 3 + 1] * Sw.yz + R[r * 3 + 2] * Sw.zz;
+    }
+    S.xx = t[0] * R[0] + t[1] * R[1] + t[2] * R[2];
+    S.xy = t[0] * R[3] + t[1] * R[4] + t[2] * R[5];
+    S.xz = t[0] * R[6] + t[1] * R[7] + t[2] * R[8];
+    S.yy = t[3] * R[3] + t[4] * R[4] + t[5] * R[5];
+    S.yz = t[3] * R[6] + t[4] * R[7] + t[5] * R[8];
+    S.zz = t[6] * R[6] + t[7] * R[7] + t[8] * R[8];
+  }
+}
+
+// ---- SE3 (g2o SE3Quat semantics, SURVEY Appx B.1), thread-0 only ---------------------------------
+__device__ void quat_normalize(double* q) {
+  if (q[3] < 0)
+    for (int i = 0; i < 4; ++i) q[i] = -q[i];
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  for (int i = 0; i < 4; ++i) q[i] /= n;
+}
+__device__ void quat_to_rot(const double* q, double* R) {
+  const double x = q[0], y = q[1], z = q[2], w = q[3];
+  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+  const double twx = tx * w, twy = ty * w, twz = tz * w;
+  const double txx = tx * x, txy = ty * x, txz = tz * x;
+  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+__device__ void rot_to_quat(const double* R, double* q) {
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (R[7] - R[5]) * t;
+    q[1] = (R[2] - R[6]) * t;
+    q[2] = (R[3] - R[1]) * t;
+  } else {
+    int i = 0;
+    if (R[4] > R[0]) i = 1;
+    if (R[8] > R[i * 4]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (R[k * 3 + j] - R[j * 3 + k]) * t;
+    q[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+    q[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+  }
+}
+// pose <- exp(xi) * pose   (VertexSE3Expmap::oplusImpl)
+__device__ void se3_oplus(const double* xi, const double* pose, double* out) {
+  const double w0 = xi[0], w1 = xi[1], w2 = xi[2];
+  const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+  const double Om[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
+  double Om2[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Om2[r * 3 + c] = Om[r * 3] * Om[c] + Om[r * 3 + 1] * Om[3 + c] + Om[r * 3 + 2] * Om[6 + c];
+  double a, b, d;
+  if (theta < 1e-5) {
+    a = 1.0; b = 0.5; d = 1.0 / 6.0;
+  } else {
+    const double st = sin(theta), ct = cos(theta);
+    a = st / theta;
+    b = (1 - ct) / (theta * theta);
+    d = (theta - st) / (theta * theta * theta);
+  }
+  double Rm[9], V[9];
+  for (int i = 0; i < 9; ++i) {
+    const double I = (i % 4 == 0) ? 1.0 : 0.0;
+    Rm[i] = I + a * Om[i] + b * Om2[i];
+    V[i] = I + b * Om[i] + d * Om2[i];
+  }
+  const double t[3] = {V[0] * xi[3] + V[1] * xi[4] + V[2] * xi[5], V[3] * xi[3] + V[4] * xi[4] + V[5] * xi[5],
+                       V[6] * xi[3] + V[7] * xi[4] + V[8] * xi[5]};
+  double qd[4], Rd[9];
+  rot_to_quat(Rm, qd);
+  quat_normalize(qd);
+  quat_to_rot(qd, Rd);
+  const double* p = pose + 4;
+  const double rt[3] = {Rd[0] * p[0] + Rd[1] * p[1] + Rd[2] * p[2], Rd[3] * p[0] + Rd[4] * p[1] + Rd[5] * p[2],
+                        Rd[6] * p[0] + Rd[7] * p[1] + Rd[8] * p[2]};
+  const double ax = qd[0], ay = qd[1], az = qd[2], aw = qd[3], bx = pose[0], by = pose[1], bz = pose[2], bw = pose[3];
+  double q[4];
+  q[3] = aw * bw - ax * bx - ay * by - az * bz;
+  q[0] = aw * bx + ax * bw + ay * bz - az * by;
+  q[1] = aw * by + ay * bw + az * bx - ax * bz;
+  q[2] = aw * bz + az * bw + ax * by - ay * bx;
+  quat_normalize(q);
+  for (int i = 0; i < 4; ++i) out[i] = q[i];
+  for (int i = 0; i < 3; ++i) out[4 + i] = t[i] + rt[i];
+}
+
+// 6x6 SPD solve from the 21 upper-triangular entries (row-major packing) — plain Cholesky.
+__device__ bool solve6(const double* acc, double* x) {
+  double H[36], L[36];
+  int n = 0;
+  for (int r = 0; r < 6; ++r)
+    for (int c = r; c < 6; ++c) {
+      H[r * 6 + c] = acc[n];
+      H[c * 6 + r] = acc[n];
+      ++n;
+    }
+  for (int i = 0; i < 36; ++i) L[i] = 0.0;
+  for (int k = 0; k < 6; ++k) {
+    double s = H[k * 6 + k];
+    for (int j = 0; j < k; ++j) s -= L[k * 6 + j] * L[k * 6 + j];
+    if (!(s > 0.0) || !isfinite(s)) return false;
+    const double d = sqrt(s);
+    L[k * 6 + k] = d;
+    for (int i = k + 1; i < 6; ++i) {
+      double t = H[i * 6 + k];
+      for (int j = 0; j < k; ++j) t -= L[i * 6 + j] * L[k * 6 + j];
+      L[i * 6 + k] = t / d;
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; ++i) {
+    double t = acc[21 + i];
+    for (int j = 0; j < i; ++j) t -= L[i * 6 + j] * y[j];
+    y[i] = t / L[i * 6 + i];
+  }
+  for (int i = 5; i >= 0; --i) {
+    double t = y[i];
+    for (int j = i + 1; j < 6; ++j) t -= L[j * 6 + i] * x[j];
+    x[i] = t / L[i * 6 + i];
+  }
+  for (int i = 0; i < 6; ++i)
+    if (!isfinite(x[i])) return false;
+  return true;
+}
+
+// numeric-failure contract (shared with the oracle): a frame whose solve hits a singular Hll / reduced
+// system or a non-finite value is returned UNSOLVED (normalised pose0, input landmarks) with
+// GMMLOC_FRAME_NUMERIC set.
+__global__ void __launch_bounds__(kThreads) frame_gn_kernel(const FrameArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_red[kWarps][kAcc];
+  __shared__ double s_acc[kAcc];
+  __shared__ double s_pose[7], s_R[9], s_dxi[6];
+  __shared__ int s_fail1, s_fail2;
+
+  const int f = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N;
+  const FrameParamsDev& P = a.prm;
+  double* xs;
+  uint8_t* fl;
+  if (a.xws != nullptr) {
+    xs = a.xws + (size_t)f * N * 3;
+    fl = a.fws + (size_t)f * N;
+  } else {
+    xs = reinterpret_cast<double*>(smem_raw);
+    fl = reinterpret_cast<uint8_t*>(xs + (size_t)N * 3);
+  }
+  const float* pts = a.pts_w + (size_t)f * N * 3;
+  const float* obs = a.obs + (size_t)f * N * 3;
+  const uint8_t* oct = a.octave + (size_t)f * N;
+  const int32_t* asg = a.assign + (size_t)f * N;
+  const bool pose_free = P.factor_mode != GMMLOC_MODE_POINTS_ONLY;
+  const bool pts_free = P.factor_mode != GMMLOC_MODE_POSE_ONLY;
+
+  if (tid == 0) {
+    double q[7];
+    for (int i = 0; i < 7; ++i) q[i] = a.pose0[(size_t)f * 7 + i];
+    quat_normalize(q);
+    for (int i = 0; i < 7; ++i) s_pose[i] = q[i];
+    quat_to_rot(q, s_R);
+    for (int i = 0; i < 6; ++i) s_dxi[i] = 0.0;
+    s_fail1 = 0;
+    s_fail2 = 0;
+  }
+  // ---- landmarks to fp64; structure-edge gates fixed at iteration 0 (exact replay of the oracle's
+  // comparisons so the active edge set is identical) ----
+  for (int i = tid; i < N; i += kThreads) {
+    const double x0 = (double)pts[i * 3], x1 = (double)pts[i * 3 + 1], x2 = (double)pts[i * 3 + 2];
+    xs[i * 3] = x0;
+    xs[i * 3 + 1] = x1;
+    xs[i * 3 + 2] = x2;
+    uint8_t b = (obs[i * 3 + 2] >= 0.0f) ? F_STEREO : 0;  // u_r < 0 => monocular (tracking_opt.cpp:67)
+    const int k = asg[i];
+    if (k >= 0 && pts_free) {
+      if (a.is_deg[k]) {
+        b |= F_DEG;
+        const double* ax = a.axis + (size_t)k * 9;
+        const double* mu = a.mean + (size_t)k * 3;
+        const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
+        if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;  // gmmloc_opt.cpp:336-338, localization_opt.cpp:781
+      } else {
+        if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;  // gmmloc_opt.cpp:230
+      }
+    }
+    // a monocular point without a structure edge has a rank-2 Hll: held fixed
+    if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
+    fl[i] = b;
+  }
+  __syncthreads();
+
+  for (int it = 0; it < P.gn_iters; ++it) {
+    double R[9], t[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = s_R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = s_pose[4 + i];
+
+    // ---- pass 1: accumulate the reduced pose system ----
+    if (pose_free) {
+      double acc[kAcc];
+#pragma unroll
+      for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+      bool bad = false;
+      for (int i = tid; i < N; i += kThreads) {
+        const uint8_t b = fl[i];
+        const bool free_pt = b & F_FREE, str = b & F_STR;
+        if (free_pt && !str) continue;  // contributes exactly zero (see header)
+        const Vec3 xw = {xs[i * 3], xs[i * 3 + 1], xs[i * 3 + 2]};
+        Vec3 pc = rot(R, xw);
+        pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
+        Sym3 G;
+        Vec3 h;
+        reproj(P, pc, obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2], b & F_STEREO, (double)P.s2inv[oct[i] & 7], G, h);
+        Sym3 M;
+        Vec3 v;
+        if (!free_pt) {
+          M = G;
+          v = h;
+        } else {
+          Sym3 S;
+          Vec3 s;
+          structure(a, R, asg[i], b, xw, S, s);
+          const Sym3 D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
+          bool ok;
+          const Sym3 Di = inv_sym(D, ok);
+          if (!ok) bad = true;
+          // T = G Di (general 3x3)
+          const double T00 = G.xx * Di.xx + G.xy * Di.xy + G.xz * Di.xz, T01 = G.xx * Di.xy + G.xy * Di.yy + G.xz * Di.yz,
+                       T02 = G.xx * Di.xz + G.xy * Di.yz + G.xz * Di.zz;
+          const double T10 = G.xy * Di.xx + G.yy * Di.xy + G.yz * Di.xz, T11 = G.xy * Di.xy + G.yy * Di.yy + G.yz * Di.yz,
+                       T12 = G.xy * Di.xz + G.yy * Di.yz + G.yz * Di.zz;
+          const double T20 = G.xz * Di.xx + G.yz * Di.xy + G.zz * Di.xz, T21 = G.xz * Di.xy + G.yz * Di.yy + G.zz * Di.yz,
+                       T22 = G.xz * Di.xz + G.yz * Di.yz + G.zz * Di.zz;
+          const Vec3 bl = {h.x + s.x, h.y + s.y, h.z + s.z};
+          v = {h.x - (T00 * bl.x + T01 * bl.y + T02 * bl.z), h.y - (T10 * bl.x + T11 * bl.y + T12 * bl.z),
+               h.z - (T20 * bl.x + T21 * bl.y + T22 * bl.z)};
+          // M = T S (symmetric in exact arithmetic; upper triangle taken)
+          M.xx = T00 * S.xx + T01 * S.xy + T02 * S.xz;
+          M.xy = T00 * S.xy + T01 * S.yy + T02 * S.yz;
+          M.xz = T00 * S.xz + T01 * S.yz + T02 * S.zz;
+          M.yy = T10 * S.xy + T11 * S.yy + T12 * S.yz;
+          M.yz = T10 * S.xz + T11 * S.yz + T12 * S.zz;
+          M.zz = T20 * S.xz + T21 * S.yz + T22 * S.zz;
+        }
+        // A^T M A and A^T v with A = [-[pc]x  I]:  C = [pc]x M,  [pc]x = [[0,-z,y],[z,0,-x],[-y,x,0]]
+        const double C00 = pc.y * M.xz - pc.z * M.xy, C01 = pc.y * M.yz - pc.z * M.yy, C02 = pc.y * M.zz - pc.z * M.yz;
+        const double C10 = pc.z * M.xx - pc.x * M.xz, C11 = pc.z * M.xy - pc.x * M.yz, C12 = pc.z * M.xz - pc.x * M.zz;
+        const double C20 = pc.x * M.xy - pc.y * M.xx, C21 = pc.x * M.yy - pc.y * M.xy, C22 = pc.x * M.yz - pc.y * M.xz;
+        // rot-rot block = C [pc]x^T,  (C [pc]x^T)_{ab} = sum_c C_ac [pc]x_{bc}
+        acc[0] += C02 * pc.y - C01 * pc.z;   // (0,0)
+        acc[1] += C00 * pc.z - C02 * pc.x;   // (0,1)
+        acc[2] += C01 * pc.x - C00 * pc.y;   // (0,2)
+        acc[3] += C00;                       // (0,3..5): rot-trans block = C
+        acc[4] += C01;
+        acc[5] += C02;
+        acc[6] += C10 * pc.z - C12 * pc.x;   // (1,1)
+        acc[7] += C11 * pc.x - C10 * pc.y;   // (1,2)
+        acc[8] += C10;
+        acc[9] += C11;
+        acc[10] += C12;
+        acc[11] += C21 * pc.x - C20 * pc.y;  // (2,2)
+        acc[12] += C20;
+        acc[13] += C21;
+        acc[14] += C22;
+        acc[15] += M.xx;                     // trans-trans block = M
+        acc[16] += M.xy;
+        acc[17] += M.xz;
+        acc[18] += M.yy;
+        acc[19] += M.yz;
+        acc[20] += M.zz;
+        const Vec3 br = cross(pc, v);        // A^T v = [pc x v ; v]
+        acc[21] += br.x;
+        acc[22] += br.y;
+        acc[23] += br.z;
+        acc[24] += v.x;
+        acc[25] += v.y;
+        acc[26] += v.z;
+      }
+#pragma unroll
+      for (int i = 0; i < kAcc; ++i) {
+        double s = acc[i];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) s_red[warp][i] = s;
+      }
+      if (bad) s_fail1 = 1;
+      __syncthreads();
+      if (tid < kAcc) {
+        double s = s_red[0][tid];
+#pragma unroll
+        for (int w = 1; w < kWarps; ++w) s += s_red[w][tid];
+        s_acc[tid] = s;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        double dxi[6];
+        if (s_fail1 || !solve6(s_acc, dxi)) {
+          s_fail1 = 1;
+        } else {
+          // every thread already holds the old (R, t) in registers: the pose can be advanced now
+          double np[7];
+          se3_oplus(dxi, s_pose, np);
+          for (int i = 0; i < 6; ++i) s_dxi[i] = dxi[i];
+          for (int i = 0; i < 7; ++i) s_pose[i] = np[i];
+          quat_to_rot(np, s_R);
+        }
+      }
+      __syncthreads();
+      if (s_fail1) break;  // uniform
+    }
+
+    // ---- pass 2: back-substitution at the same linearisation point ----
+    if (pts_free) {
+      const Vec3 om = {s_dxi[0], s_dxi[1], s_dxi[2]}, up = {s_dxi[3], s_dxi[4], s_dxi[5]};
+      bool bad = false;
+      for (int i = tid; i < N; i += kThreads) {
+        const uint8_t b = fl[i];
+        if (!(b & F_FREE)) continue;
+        const Vec3 xw = {xs[i * 3], xs[i * 3 + 1], xs[i * 3 + 2]};
+        Vec3 pc = rot(R, xw);
+        pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
+        Sym3 G;
+        Vec3 h;
+        reproj(P, pc, obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2], b & F_STEREO, (double)P.s2inv[oct[i] & 7], G, h);
+        Sym3 D = G;
+        Vec3 bl = h;
+        if (b & F_STR) {
+          Sym3 S;
+          Vec3 s;
+          structure(a, R, asg[i], b, xw, S, s);
+          D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
+          bl = {h.x + s.x, h.y + s.y, h.z + s.z};
+        }
+        bool ok;
+        const Sym3 Di = inv_sym(D, ok);
+        Vec3 ad = cross(om, pc);  // A dxi = omega x pc + upsilon
+        ad.x += up.x; ad.y += up.y; ad.z += up.z;
+        const Vec3 ga = mul(G, ad);
+        const Vec3 dc = mul(Di, {bl.x - ga.x, bl.y - ga.y, bl.z - ga.z});
+        const Vec3 dw = rot_t(R, dc);
+        const double n0 = xw.x + dw.x, n1 = xw.y + dw.y, n2 = xw.z + dw.z;
+        if (!ok || !isfinite(n0) || !isfinite(n1) || !isfinite(n2)) bad = true;
+        xs[i * 3] = n0;
+        xs[i * 3 + 1] = n1;
+        xs[i * 3 + 2] = n2;
+      }
+      if (bad) s_fail2 = 1;
+      __syncthreads();
+      if (s_fail2) break;  // uniform
+    }
+  }
+  __syncthreads();
+  const bool fail = s_fail1 || s_fail2;
+  __syncthreads();
+  if (fail && tid == 0) {  // unsolved frame: back to the normalised input pose
+    double q[7];
+    for (int i = 0; i < 7; ++i) q[i] = a.pose0[(size_t)f * 7 + i];
+    quat_normalize(q);
+    for (int i = 0; i < 7; ++i) s_pose[i] = q[i];
+    quat_to_rot(q, s_R);
+  }
+  __syncthreads();
+  if (tid < 7) a.pose_out[(size_t)f * 7 + tid] = s_pose[tid];
+  if (tid == 0) a.status[f] = fail ? GMMLOC_FRAME_NUMERIC : 0;
+  if (a.pts_out != nullptr) {
+    float* po = a.pts_out + (size_t)f * N * 3;
+    for (int i = tid; i < N * 3; i += kThreads) po[i] = fail ? pts[i] : (float)xs[i];
+  }
+  if (a.outlier != nullptr) {
+    // post-check at the final estimate: chi2 > 5.991 / 7.815 or non-positive depth
+    // (localization_opt.cpp:857-881)
+    double R[9], t[3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) R[i] = s_R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) t[i] = s_pose[4 + i];
+    uint8_t* out = a.outlier + (size_t)f * N;
+    for (int i = tid; i < N; i += kThreads) {
+      Vec3 xw;
+      if (fail) xw = {(double)pts[i * 3], (double)pts[i * 3 + 1], (double)pts[i * 3 + 2]};
+      else xw = {xs[i * 3], xs[i * 3 + 1], xs[i * 3 + 2]};
+      Vec3 pc = rot(R, xw);
+      pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
+      const bool stereo = fl[i] & F_STEREO;
+      const double invz = 1.0 / pc.z;
+      const double u = pc.x * invz * P.fx + P.cx, v = pc.y * invz * P.fy + P.cy;
+      const double e0 = (double)obs[i * 3] - u, e1 = (double)obs[i * 3 + 1] - v;
+      double e2 = 0.0;
+      if (stereo) e2 = (double)obs[i * 3 + 2] - (u - P.bf * invz);
+      const double chi = (double)P.s2inv[oct[i] & 7] * (e0 * e0 + e1 * e1 + e2 * e2);
+      const double th = stereo ? P.chi2_stereo : P.chi2_mono;
+      out[i] = (chi > th || !(pc.z > 0.0)) ? 1 : 0;
+    }
+  }
+}
+
+}  // namespace
+
+size_t frame_gn_smem_limit_points() { return (size_t)(200 * 1024) / 25; }
+
+cudaError_t launch_frame_gn(const FrameArgs& a, cudaStream_t stream) {
+  size_t smem = 0;
+  if (a.xws == nullptr) {
+    smem = (size_t)a.N * 25 + 16;
+    cudaError_t e = cudaFuncSetAttribute(frame_gn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024);
+    if (e != cudaSuccess) return e;
+  }
+  frame_gn_kernel<<<a.B, kThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace gmmloc

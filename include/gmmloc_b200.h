@@ -24,6 +24,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define GMMLOC_API __attribute__((visibility("default")))
+#else
+#define GMMLOC_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -75,58 +81,64 @@ typedef struct {
   int64_t kernel_launches; /* kernels launched by this context since creation           */
 } gmmloc_stats_t;
 
-const char* gmmloc_version(void);
-const char* gmmloc_status_string(gmmloc_status_t s);
+GMMLOC_API const char* gmmloc_version(void);
+GMMLOC_API const char* gmmloc_status_string(gmmloc_status_t s);
 /* last CUDA / IO error text of the calling thread ("" if none) */
-const char* gmmloc_last_error(void);
-void gmmloc_default_params(gmmloc_params_t* p);
+GMMLOC_API const char* gmmloc_last_error(void);
+GMMLOC_API void gmmloc_default_params(gmmloc_params_t* p);
 /* frame::sigma2_inv[octave] exactly as the reference computes it in float (init_config.hpp:63-78) */
-float gmmloc_sigma2_inv(int octave);
+GMMLOC_API float gmmloc_sigma2_inv(int octave);
 
 /* ---- map: replaces GMMUtility::loadGMMModel + GaussianComponent ctor/decompose + GMM ctor ------
  * gmm_utils.cpp:9-67, gaussian.h:30-39, gaussian.cpp:36-63.  mean K x 3, cov K x 9 row-major (fp64).
  * All per-component constants (cov_inv, det, eigen-decomposition, is_degenerated, sqrt_info and the
  * fp32 whitening rows used by the scan) are computed on the device. */
-gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, double deg_eps, int device,
+GMMLOC_API gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, double deg_eps, int device,
                                   gmmloc_map_t** out);
 /* .gmm wire format: protobuf_utils.cpp:12-80, GMM.proto:5-14 */
-gmmloc_status_t gmmloc_map_load_gmm(const char* path, double deg_eps, int device, gmmloc_map_t** out);
+GMMLOC_API gmmloc_status_t gmmloc_map_load_gmm(const char* path, double deg_eps, int device, gmmloc_map_t** out);
 /* GMMUtility::saveGMMModel, gmm_utils.cpp:69-119 (same byte stream) */
-gmmloc_status_t gmmloc_map_save_gmm(const gmmloc_map_t* map, const char* path);
-void gmmloc_map_destroy(gmmloc_map_t* map);
+GMMLOC_API gmmloc_status_t gmmloc_map_save_gmm(const gmmloc_map_t* map, const char* path);
+GMMLOC_API void gmmloc_map_destroy(gmmloc_map_t* map);
 /* GMM::countComponents, gaussian_mixture.h:153 */
-int gmmloc_map_size(const gmmloc_map_t* map);
-int gmmloc_map_device(const gmmloc_map_t* map);
+GMMLOC_API int gmmloc_map_size(const gmmloc_map_t* map);
+GMMLOC_API int gmmloc_map_device(const gmmloc_map_t* map);
 /* Device-built constants back to the host (any pointer may be NULL). Shapes: mean K x 3, cov K x 9,
  * cov_inv K x 9, det K, scale K x 3 (ascending), axis K x 9 (axis[r*3+c] = component r of eigenvector c),
  * sqrt_info K x 9 (lower L, cov_inv = L L^T), is_degenerated K, is_salient K.
  * ≙ GaussianComponent public fields, gaussian.h:69-90. */
-gmmloc_status_t gmmloc_map_get_components(const gmmloc_map_t* map, double* mean, double* cov, double* cov_inv,
+GMMLOC_API gmmloc_status_t gmmloc_map_get_components(const gmmloc_map_t* map, double* mean, double* cov, double* cov_inv,
                                           double* det, double* scale, double* axis, double* sqrt_info,
                                           uint8_t* is_degenerated, uint8_t* is_salient);
 /* error bound of the fp32 scan in whitened units (|sqrt(s32) - sqrt(d2)| <= alpha for |x|_inf <= xmax) */
-gmmloc_status_t gmmloc_map_scan_bound(const gmmloc_map_t* map, double* alpha, double* xmax);
+GMMLOC_API gmmloc_status_t gmmloc_map_scan_bound(const gmmloc_map_t* map, double* alpha, double* xmax);
 
 /* ---- context ------------------------------------------------------------------------------- */
-gmmloc_status_t gmmloc_ctx_create(int device, gmmloc_ctx_t** out);
-void gmmloc_ctx_destroy(gmmloc_ctx_t* ctx);
+GMMLOC_API gmmloc_status_t gmmloc_ctx_create(int device, gmmloc_ctx_t** out);
+GMMLOC_API void gmmloc_ctx_destroy(gmmloc_ctx_t* ctx);
 /* cudaStream_t of the context (for event timing / interop) */
-void* gmmloc_ctx_stream(gmmloc_ctx_t* ctx);
-gmmloc_status_t gmmloc_ctx_synchronize(gmmloc_ctx_t* ctx);
-gmmloc_status_t gmmloc_ctx_stats(gmmloc_ctx_t* ctx, gmmloc_stats_t* out);
+GMMLOC_API void* gmmloc_ctx_stream(gmmloc_ctx_t* ctx);
+GMMLOC_API gmmloc_status_t gmmloc_ctx_synchronize(gmmloc_ctx_t* ctx);
+GMMLOC_API gmmloc_status_t gmmloc_ctx_stats(gmmloc_ctx_t* ctx, gmmloc_stats_t* out);
+/* device time (ms, CUDA events on the context's stream) of the kernels of the LAST association / frame
+ * solve enqueued on ctx: ms[0] association scan (K1), ms[1] exact re-rank (K2), ms[2] frame GN (K3; 0 if
+ * the last call was an association only).  Synchronises the stream.  The reference's counterpart is its
+ * timing::Timer registry ("loc/render_view", "map/search_corr", "loc/ba": gmmloc_opt.cpp:123,130,
+ * localization.cpp:101). */
+GMMLOC_API gmmloc_status_t gmmloc_ctx_kernel_times(gmmloc_ctx_t* ctx, float ms[3]);
 
 /* page-locked host memory for the host entry points (pageable buffers also work, via staging) */
-gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out);
-void gmmloc_host_free(void* p);
+GMMLOC_API gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out);
+GMMLOC_API void gmmloc_host_free(void* p);
 
 /* ---- association: replaces GaussianComponent::chi2 / MDist2 scanned over all components with the
  * reference's argmin convention (gaussian.cpp:65-70, gaussian.h:53-56; strict '<' ascending scan =>
  * lowest index wins ties, gmmloc_opt.cpp:175-197,209-217).  M = B*N points.
  *  assign[i] = argmin_k d2_k(x_i)   (exact: identical to an fp64 scan), or -1 iff gate > 0 and the
  *  best d2 > gate (gmmloc_opt.cpp:230).  d2 (optional) = (float) of the fp64 d2 of the winner. */
-gmmloc_status_t gmmloc_associate(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const float* pts_w, int B, int N,
+GMMLOC_API gmmloc_status_t gmmloc_associate(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const float* pts_w, int B, int N,
                                  double gate, int32_t* assign, float* d2);
-gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const float* d_pts_w,
+GMMLOC_API gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const float* d_pts_w,
                                        int64_t M, double gate, int32_t* d_assign, float* d_d2);
 
 /* ---- frame solve: association + single-free-pose specialisation of Localization::jointOptimization
@@ -137,11 +149,11 @@ gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* ma
  *  pose0 B x 7, pts_w B x N x 3, obs B x N x 3 (u v u_r; u_r < 0 => monocular), octave B x N.
  *  outputs: pose_out B x 7, pts_out B x N x 3 (optional), assign B x N, outlier B x N (optional),
  *  status B (GMMLOC_FRAME_* bits). */
-gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+GMMLOC_API gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
                                     const gmmloc_params_t* params, const double* pose0, const float* pts_w,
                                     const float* obs, const uint8_t* octave, int B, int N, double* pose_out,
                                     float* pts_out, int32_t* assign, uint8_t* outlier, int32_t* status);
-gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+GMMLOC_API gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
                                           const gmmloc_params_t* params, const double* d_pose0,
                                           const float* d_pts_w, const float* d_obs, const uint8_t* d_octave,
                                           int B, int N, double* d_pose_out, float* d_pts_out, int32_t* d_assign,
@@ -151,7 +163,7 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
  * 3-DoF GN problems (one stereo reprojection edge + one point-to-plane edge), `iters` iterations (5).
  *  x0 M x 3 (fp64), obs M x 3 (u v u_r), octave M, pose M x 7, comp M (component index), proj_z2 M.
  *  outputs: pt_est M x 3, chi2_proj M, chi2_str M, res M (1 = accepted). */
-gmmloc_status_t gmmloc_points_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+GMMLOC_API gmmloc_status_t gmmloc_points_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
                                     const gmmloc_params_t* params, const double* x0, const float* obs,
                                     const uint8_t* octave, const double* pose, const int32_t* comp,
                                     const double* proj_z2, int M, int iters, double* pt_est, double* chi2_proj,

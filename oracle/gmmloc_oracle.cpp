@@ -699,6 +699,13 @@ void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t
     }
   }
 
+  if (st) {
+    // numeric-failure contract of the build (g2o ignores solver failures): the frame is
+    // returned UNSOLVED — normalised input pose, input landmarks — with the status bit set.
+    for (int i = 0; i < 7; ++i) pose[i] = pose0[i];
+    quat_normalize(pose);
+    for (int i = 0; i < 3 * N; ++i) x[i] = (double)pts_w[i];
+  }
   if (pose_out) for (int i = 0; i < 7; ++i) pose_out[i] = pose[i];
   if (pts_out) for (int i = 0; i < 3 * N; ++i) pts_out[i] = x[i];
   if (assign_o) for (int i = 0; i < N; ++i) assign_o[i] = asg[i];

@@ -90,7 +90,9 @@ int oracle_optimize_point(const double x0[3], const double obs[3], int octave, c
  *  pose0/pose_out: qx qy qz qw tx ty tz (T_cw) fp64;  pts_w N x 3 fp32;  obs N x 3 fp32 (u v u_r,
  *  u_r < 0 => mono);  octave N.  assign_in: if non-NULL use these assignments instead of
  *  associating.  Outputs (any may be NULL): pose_out[7], pts_out N x 3 (fp64), assign N,
- *  outlier N, status (bit0 numeric failure).  trace (optional): gn_iters x 6 pose increments. */
+ *  outlier N, status (bit0 numeric failure: singular Hll / reduced system or non-finite value; such a
+ *  frame is returned unsolved = normalised pose0 + input landmarks).  trace (optional): gn_iters x 6
+ *  pose increments. */
 void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t* cam,
                         const oracle_params_t* prm, const double pose0[7], const float* pts_w,
                         const float* obs, const uint8_t* octave, int N, const int32_t* assign_in,

@@ -1,0 +1,330 @@
+"""GPU parity tests proper: every call goes through the C ABI (libgmmloc_b200.so) and is compared with
+the CPU oracle on the same seeded inputs.  Bars: integer outputs bit-exact; map constants and point
+solves bit-exact (same fp64 expression trees); poses within 1e-5 rad / 1e-4 m (BASELINE.json)."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from gmmloc_b200 import synth
+from tests import np_reference as ref
+
+pytestmark = pytest.mark.gpu
+
+TOL_RAD, TOL_M = 1e-5, 1e-4
+
+
+def _bits(a):
+    return np.ascontiguousarray(a).view(np.uint64)
+
+
+# ---------------------------------------------------------------- map build (a1)
+@pytest.mark.parametrize("name", ["v1", "v2", "synthetic"])
+def test_map_constants_bit_exact(gpu, oracle, golden_maps, name):
+    g, _ = gpu
+    if name == "synthetic":
+        mean, cov = synth.make_map(2500, 0.5, seed=9)
+    else:
+        mean, cov = golden_maps[name]["mean"], golden_maps[name]["cov"]
+    m = g.GMM(mean, cov)
+    c = m.getComponents()
+    o = oracle.map_build(mean, cov)
+    assert len(m) == len(o)
+    for f in ("mean", "cov", "cov_inv", "det", "scale", "axis", "sqrt_info"):
+        assert np.array_equal(_bits(c[f]), _bits(o[f].reshape(c[f].shape))), f
+    assert np.array_equal(c["is_degenerated"], o["is_degenerated"].astype(np.uint8))
+    assert np.array_equal(c["is_salient"], o["is_salient"].astype(np.uint8))
+    if name != "synthetic":  # the reference's own stored flags
+        assert np.array_equal(c["is_degenerated"], golden_maps[name]["flags"][:, 0])
+
+
+def test_map_rejects_non_spd(gpu):
+    g, _ = gpu
+    cov = np.tile(np.eye(3).ravel(), (5, 1))
+    cov[3] = np.diag([1.0, -1.0, 1.0]).ravel()
+    with pytest.raises(g.GmmlocError) as ei:
+        g.GMM(np.zeros((5, 3)), cov)
+    assert ei.value.status == g.capi.EINVAL
+
+
+def test_gmm_file_roundtrip_through_the_abi(gpu, oracle, golden_maps, tmp_path):
+    g, _ = gpu
+    for name, gm in golden_maps.items():
+        src = tmp_path / f"{name}_src.gmm"
+        oracle.gmm_write(src, gm["mean"], gm["cov"], gm["flags"])  # = shipped file with transposed covariances
+        m = g.GMM.load(src)
+        assert m.countComponents() == len(gm["mean"])
+        c = m.getComponents()
+        assert np.array_equal(c["cov"].reshape(-1, 3, 3), gm["cov"].reshape(-1, 3, 3).transpose(0, 2, 1))
+        out = tmp_path / f"{name}_out.gmm"
+        m.save(out)  # load -> save transposes back: byte-identical to the shipped map
+        raw = out.read_bytes()
+        assert len(raw) == gm["nbytes"] and hashlib.sha256(raw).hexdigest() == gm["sha256"]
+
+
+# ---------------------------------------------------------------- association (a3, a4)
+def _check_assoc(g, ctx, oracle, mean, cov, pts, gate=0.0):
+    m = g.GMM(mean, cov)
+    comps = oracle.map_build(mean, cov)
+    a, d2 = ctx.associate(m, pts, gate=gate)
+    ao, d2o = oracle.associate(comps, pts, gate=gate, nthreads=8)
+    a, d2 = a.reshape(-1), d2.reshape(-1)
+    assert np.array_equal(a, ao)
+    fin = np.isfinite(d2o) & (d2o < 1e30)
+    assert np.array_equal(d2[fin], d2o[fin].astype(np.float32))
+    return ctx.stats()
+
+
+def test_associate_c1_config(gpu, oracle):
+    # BASELINE configs[0]: 500 landmarks x 1 000 components
+    g, ctx = gpu
+    mean, cov = synth.make_map(1000, 0.5)
+    fr = synth.make_frames(mean, cov, 4, 500, seed=1)
+    st = _check_assoc(g, ctx, oracle, mean, cov, fr["pts_w"])
+    assert st["points"] == 2000
+
+
+@pytest.mark.parametrize("name", ["v1", "v2"])
+def test_associate_shipped_maps(gpu, oracle, golden_maps, name):
+    g, ctx = gpu
+    gm = golden_maps[name]
+    pts, _ = synth.make_points_near(gm["mean"], gm["cov"], 20000, seed=2, spread=1.5)
+    st = _check_assoc(g, ctx, oracle, gm["mean"], gm["cov"], pts)
+    assert 0 <= st["flagged"] <= st["points"]
+    _check_assoc(g, ctx, oracle, gm["mean"], gm["cov"], pts[:5000], gate=9.0)
+
+
+def test_associate_c2_frames_and_gate(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(10000, 0.5)
+    fr = synth.make_frames(mean, cov, 3, 2000, seed=3)
+    _check_assoc(g, ctx, oracle, mean, cov, fr["pts_w"])
+    _check_assoc(g, ctx, oracle, mean, cov, fr["pts_w"][0], gate=9.0)
+
+
+def test_associate_c5_planar_mix(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(50000, 0.95, seed=5)
+    fr = synth.make_frames(mean, cov, 1, 1000, seed=5)
+    _check_assoc(g, ctx, oracle, mean, cov, fr["pts_w"])
+
+
+@pytest.mark.parametrize("K,M", [(1, 7), (15, 33), (16, 1), (17, 129), (383, 1000), (385, 257), (1153, 4097)])
+def test_associate_ragged_sizes(gpu, oracle, K, M):
+    g, ctx = gpu
+    mean, cov = synth.make_map(K, 0.5, seed=K)
+    pts, _ = synth.make_points_near(mean, cov, M, seed=M, spread=3.0)
+    _check_assoc(g, ctx, oracle, mean, cov, pts)
+
+
+def test_associate_empty(gpu):
+    g, ctx = gpu
+    mean, cov = synth.make_map(32, 0.5)
+    m = g.GMM(mean, cov)
+    a, d2 = ctx.associate(m, np.zeros((0, 3), np.float32))
+    assert a.size == 0 and d2.size == 0
+
+
+def test_associate_exact_ties_lowest_index_wins(gpu, oracle):
+    # duplicated components: the fp32 scores tie exactly; the reference's strict '<' ascending scan keeps
+    # the lowest index (gmmloc_opt.cpp:209-217)
+    g, ctx = gpu
+    mean, cov = synth.make_map(500, 0.5, seed=21)
+    mean = np.concatenate([mean, mean[:100], mean[:50]])
+    cov = np.concatenate([cov, cov[:100], cov[:50]])
+    pts, _ = synth.make_points_near(mean[:500], cov[:500], 5000, seed=4)
+    st = _check_assoc(g, ctx, oracle, mean, cov, pts)
+    a, _ = ctx.associate(g.GMM(mean, cov), pts)
+    assert a.max() < 500
+    assert st["flagged"] > 0
+
+
+def test_associate_far_nonfinite_and_huge_points(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(777, 0.5, seed=8)
+    pts, _ = synth.make_points_near(mean, cov, 64, seed=8)
+    pts[3] = [1e3, -2e3, 5e2]          # beyond the certified range -> exact path
+    pts[5] = [np.nan, 0, 0]
+    pts[9] = [np.inf, 1, 1]
+    pts[11] = [3e18, 3e18, -3e18]
+    pts[13] = mean[100].astype(np.float32)
+    m = g.GMM(mean, cov)
+    comps = oracle.map_build(mean, cov)
+    a, d2 = ctx.associate(m, pts)
+    ao, _ = oracle.associate(comps, pts)
+    assert np.array_equal(a.reshape(-1), ao)
+    assert ao[5] == -1 and ao[9] == -1
+
+
+def test_associate_permutation_and_split_invariance_full_size(gpu):
+    # size-independent property at the C2 size (B frames x 2 000 x 10 000): the assignment of a landmark
+    # depends on nothing but the landmark
+    g, ctx = gpu
+    mean, cov = synth.make_map(10000, 0.5)
+    m = g.GMM(mean, cov)
+    fr = synth.make_frames(mean, cov, 32, 2000, seed=6)
+    pts = fr["pts_w"].reshape(-1, 3)
+    a, d2 = ctx.associate(m, pts)
+    perm = np.random.default_rng(0).permutation(len(pts))
+    ap, d2p = ctx.associate(m, pts[perm])
+    assert np.array_equal(ap.reshape(-1), a.reshape(-1)[perm]) and np.array_equal(d2p.reshape(-1), d2.reshape(-1)[perm])
+    a1, _ = ctx.associate(m, pts[:12345])
+    a2, _ = ctx.associate(m, pts[12345:])
+    assert np.array_equal(np.concatenate([a1.reshape(-1), a2.reshape(-1)]), a.reshape(-1))
+
+
+# ---------------------------------------------------------------- point solves (a8)
+def test_optimize_point_bit_exact(gpu, oracle, golden_maps):
+    g, ctx = gpu
+    gm = golden_maps["v1"]
+    m = g.GMM(gm["mean"], gm["cov"])
+    comps = oracle.map_build(gm["mean"], gm["cov"])
+    fr = synth.make_frames(gm["mean"], gm["cov"], 2, 300, seed=7)
+    deg = np.flatnonzero(comps["is_degenerated"])
+    rng = np.random.default_rng(7)
+    for f in range(2):
+        pose = fr["pose0"][f]
+        a, _ = oracle.associate(comps, fr["pts_w"][f])
+        comp = np.where(comps["is_degenerated"][a] != 0, a, rng.choice(deg, a.size)).astype(np.int32)
+        comp[5] = -1  # no candidate
+        x0 = fr["pts_w"][f].astype(np.float64)
+        R = synth.quat_to_rot(pose[:4])
+        pz = np.minimum((x0 @ R.T + pose[4:])[:, 2], 1.0)
+        out = ctx.optimizePoint(m, x0, fr["obs"][f], fr["octave"][f], pose, comp, pz * pz)
+        n_ok = 0
+        for i in range(300):
+            if comp[i] < 0:
+                assert not out["res"][i] and np.array_equal(out["pt_est"][i], x0[i])
+                continue
+            res, est, c2p, c2s = oracle.optimize_point(comps, comp[i], x0[i], fr["obs"][f, i], fr["octave"][f, i], pose, pz[i] * pz[i])
+            assert np.array_equal(_bits(out["pt_est"][i]), _bits(est)), i
+            assert out["chi2_proj"][i] == c2p and out["chi2_str"][i] == c2s
+            assert bool(out["res"][i]) == res
+            n_ok += res
+        assert n_ok > 10
+
+
+# ---------------------------------------------------------------- frame solve (a11/a12)
+def _pose_err(p, q):
+    ang = ref.rot_angle(synth.quat_to_rot(p[:4]), synth.quat_to_rot(q[:4]))
+    return ang, float(np.abs(p[4:] - q[4:]).max())
+
+
+def _check_frames(g, ctx, oracle, mean, cov, fr, **kw):
+    m = g.GMM(mean, cov)
+    comps = oracle.map_build(mean, cov)
+    prm_g = g.default_params(**kw)
+    prm_o = oracle.default_params(**kw)
+    out = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=prm_g)
+    exp = oracle.frames_solve(comps, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], prm=prm_o, nthreads=8, want_pts=True)
+    assert np.array_equal(out["assign"], exp["assign"]) or kw.get("factor_mode") == 1
+    assert np.array_equal(out["status"], exp["status"])
+    worst = (0.0, 0.0)
+    for f in range(len(fr["pose0"])):
+        ang, dt = _pose_err(out["pose"][f], exp["pose"][f])
+        worst = (max(worst[0], ang), max(worst[1], dt))
+    assert worst[0] < TOL_RAD and worst[1] < TOL_M, worst
+    np.testing.assert_allclose(out["pts"], exp["pts"], atol=TOL_M)
+    mism = int((out["outlier"] != exp["outlier"]).sum())
+    assert mism == 0
+    return out, exp, worst
+
+
+def test_frames_solve_c1(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(1000, 0.5)
+    fr = synth.make_frames(mean, cov, 6, 500, seed=1)
+    out, exp, worst = _check_frames(g, ctx, oracle, mean, cov, fr)
+    assert np.all(out["status"] == 0)
+    moved = max(_pose_err(out["pose"][f], fr["pose0"][f])[1] for f in range(6))
+    assert moved > 1e-3  # the solve really moved the poses
+
+
+def test_frames_solve_c2(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(10000, 0.5)
+    fr = synth.make_frames(mean, cov, 8, 2000, seed=2)
+    _check_frames(g, ctx, oracle, mean, cov, fr)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_frames_solve_pose_only_and_points_only(gpu, oracle, mode):
+    g, ctx = gpu
+    mean, cov = synth.make_map(2000, 0.6, seed=3)
+    fr = synth.make_frames(mean, cov, 4, 700, seed=3, mono_frac=0.25)
+    _check_frames(g, ctx, oracle, mean, cov, fr, factor_mode=mode)
+
+
+def test_frames_solve_c5_style_planar_mono_huber(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(20000, 0.95, seed=4)
+    fr = synth.make_frames(mean, cov, 3, 1500, seed=4, mono_frac=0.3)
+    _check_frames(g, ctx, oracle, mean, cov, fr, robust=1)
+
+
+def test_frames_solve_shipped_map_v1_03_poses(gpu, oracle, golden_maps, gt_v1_03):
+    # BASELINE configs[2] in miniature: shipped map; the synthetic frames stand in for ORB landmarks
+    g, ctx = gpu
+    gm = golden_maps["v1"]
+    fr = synth.make_frames(gm["mean"], gm["cov"], 4, 1200, seed=5)
+    _check_frames(g, ctx, oracle, gm["mean"], gm["cov"], fr)
+
+
+def test_frames_solve_iteration_counts(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(1500, 0.5, seed=6)
+    fr = synth.make_frames(mean, cov, 2, 400, seed=6)
+    for it in (0, 1, 3):
+        _check_frames(g, ctx, oracle, mean, cov, fr, gn_iters=it)
+
+
+def test_frames_solve_numeric_failure_flag(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(1000, 0.5, seed=7)
+    fr = synth.make_frames(mean, cov, 3, 300, seed=7)
+    fr["pts_w"][1, 17] = np.nan
+    out, exp, _ = _check_frames(g, ctx, oracle, mean, cov, fr)
+    assert list(out["status"]) == [0, g.FRAME_NUMERIC, 0]
+    assert out["assign"][1, 17] == -1
+
+
+def test_frames_solve_large_n_uses_global_workspace(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(500, 0.5, seed=8)
+    fr = synth.make_frames(mean, cov, 1, 9000, seed=8)
+    _check_frames(g, ctx, oracle, mean, cov, fr)
+
+
+def test_frames_solve_deterministic(gpu):
+    g, ctx = gpu
+    mean, cov = synth.make_map(3000, 0.5, seed=9)
+    m = g.GMM(mean, cov)
+    fr = synth.make_frames(mean, cov, 16, 1000, seed=9)
+    a = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
+    b = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
+    assert np.array_equal(_bits(a["pose"]), _bits(b["pose"])) and np.array_equal(a["pts"], b["pts"])
+    # batching does not change a frame's result
+    c = ctx.frames_solve(m, fr["pose0"][5:6], fr["pts_w"][5:6], fr["obs"][5:6], fr["octave"][5:6])
+    assert np.array_equal(_bits(a["pose"][5]), _bits(c["pose"][0]))
+
+
+def test_two_contexts_share_one_map(gpu, oracle):
+    # the reference's tracking and localisation threads each own a context (SURVEY §8b threading)
+    import threading
+    g, ctx = gpu
+    mean, cov = synth.make_map(2000, 0.5, seed=10)
+    m = g.GMM(mean, cov)
+    pts, _ = synth.make_points_near(mean, cov, 30000, seed=10)
+    ref_a, _ = ctx.associate(m, pts)
+    res = [None, None]
+
+    def work(j):
+        c = g.Context(0)
+        for _ in range(3):
+            res[j], _ = c.associate(m, pts)
+        c.close()
+
+    th = [threading.Thread(target=work, args=(j,)) for j in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert np.array_equal(res[0], ref_a) and np.array_equal(res[1], ref_a)

@@ -1,0 +1,128 @@
+"""Oracle GN solves vs the independent dense NumPy restatement (CPU only)."""
+import numpy as np
+import pytest
+from scipy.linalg import expm
+
+from gmmloc_b200 import synth
+from tests import np_reference as ref
+
+
+@pytest.fixture(scope="module")
+def small_scene(oracle):
+    mean, cov = synth.make_map(400, 0.6, seed=11)
+    comps = oracle.map_build(mean, cov)
+    fr = synth.make_frames(mean, cov, 3, 60, seed=4, mono_frac=0.3)
+    return comps, fr
+
+
+def test_se3_exp_matches_matrix_exponential(oracle):
+    rng = np.random.default_rng(1)
+    for scale in (1e-7, 1e-3, 0.3, 2.0):
+        xi = rng.normal(size=6) * scale
+        pose = oracle.se3_oplus(xi, np.array([0, 0, 0, 1.0, 0, 0, 0]))
+        tw = np.zeros((4, 4))
+        tw[:3, :3] = ref.skew(xi[:3])
+        tw[:3, 3] = xi[3:]
+        T = expm(tw)
+        np.testing.assert_allclose(synth.quat_to_rot(pose[:4]), T[:3, :3], atol=1e-12)
+        np.testing.assert_allclose(pose[4:], T[:3, 3], atol=1e-12)
+
+
+def test_se3_oplus_is_left_multiplication(oracle):
+    rng = np.random.default_rng(2)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    pose = np.concatenate([q, rng.normal(size=3)])
+    xi = rng.normal(size=6) * 0.1
+    out = oracle.se3_oplus(xi, pose)
+    dR, dt = ref.se3_exp(xi)
+    np.testing.assert_allclose(synth.quat_to_rot(out[:4]), dR @ synth.quat_to_rot(pose[:4]), atol=1e-12)
+    np.testing.assert_allclose(out[4:], dR @ pose[4:] + dt, atol=1e-12)
+    assert out[3] >= 0 and abs(np.linalg.norm(out[:4]) - 1) < 1e-14
+
+
+def test_sigma2_inv_table(oracle):
+    for o in range(8):
+        assert oracle.sigma2_inv(o) == ref.s2inv(o)
+    assert abs(oracle.sigma2_inv(3) - 1.2 ** -6) < 1e-6
+
+
+def test_projection_jacobians_vs_finite_differences():
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        pc = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(0.6, 4)])
+        P = ref.dproj(pc, True)
+        num = np.empty((3, 3))
+        for j in range(3):
+            d = np.zeros(3); d[j] = 1e-6
+            num[:, j] = (ref.project(pc + d, True) - ref.project(pc - d, True)) / 2e-6
+        np.testing.assert_allclose(P, num, rtol=1e-5, atol=1e-4)
+
+
+def test_optimize_point_vs_numpy(oracle, small_scene):
+    comps, fr = small_scene
+    deg = np.flatnonzero(comps["is_degenerated"])
+    rng = np.random.default_rng(5)
+    n_acc = 0
+    for f in range(3):
+        pose = fr["pose0"][f]
+        R = synth.quat_to_rot(pose[:4]); t = pose[4:]
+        a, _ = oracle.associate(comps, fr["pts_w"][f])
+        for i in range(0, 60, 3):
+            if fr["obs"][f, i, 2] < 0:
+                continue
+            k = a[i] if comps["is_degenerated"][a[i]] else int(rng.choice(deg))
+            x0 = fr["pts_w"][f, i].astype(np.float64)
+            pz = min((R @ x0 + t)[2], 1.0)
+            res, est, c2p, c2s = oracle.optimize_point(comps, k, x0, fr["obs"][f, i], fr["octave"][f, i], pose, pz * pz)
+            c = comps[k]
+            x, r2p, r2s = ref.optimize_point(x0, fr["obs"][f, i].astype(np.float64), fr["octave"][f, i], R, t, c["mean"],
+                                             c["axis"].reshape(3, 3)[:, 0], 400.0 * pz * pz)
+            np.testing.assert_allclose(est, x, atol=1e-9)
+            np.testing.assert_allclose([c2p, c2s], [r2p, r2s], rtol=1e-7, atol=1e-9)
+            assert res == (not (r2p > 7.815) and not (r2s > float(np.float32(0.0064)) * 400.0))
+            n_acc += res
+    assert n_acc > 0
+
+
+@pytest.mark.parametrize("mode,robust", [(0, False), (0, True), (1, False), (2, False)])
+def test_frame_solve_vs_dense_numpy(oracle, small_scene, mode, robust):
+    comps, fr = small_scene
+    prm = oracle.default_params(factor_mode=mode, robust=int(robust))
+    for f in range(3):
+        r = oracle.frame_solve(comps, fr["pose0"][f], fr["pts_w"][f], fr["obs"][f], fr["octave"][f], prm=prm)
+        assert r["status"] == 0
+        R, t, x, str_on, free = ref.frame_solve_dense(comps, fr["pose0"][f], fr["pts_w"][f], fr["obs"][f], fr["octave"][f],
+                                                      r["assign"], mode=mode, robust=robust)
+        assert ref.rot_angle(R, synth.quat_to_rot(r["pose"][:4])) < 1e-8
+        np.testing.assert_allclose(r["pose"][4:], t, atol=1e-8)
+        np.testing.assert_allclose(r["pts"], x, atol=1e-7)
+        if mode != 1:
+            assert str_on.sum() > 0  # the structure edges are really exercised
+
+
+def test_frame_solve_gates_fix_the_active_set(oracle, small_scene):
+    comps, fr = small_scene
+    r = oracle.frame_solve(comps, fr["pose0"][0], fr["pts_w"][0], fr["obs"][0], fr["octave"][0], want_trace=True)
+    inc = np.abs(r["trace"]).max(axis=1)
+    assert inc[-1] < 1e-6 * max(inc[0], 1e-12) + 1e-9  # converges to a fixed point
+
+
+def test_frame_solve_numeric_failure_returns_frame_unsolved(oracle, small_scene):
+    comps, fr = small_scene
+    pts = fr["pts_w"][0].copy()
+    pts[7] = np.nan
+    r = oracle.frame_solve(comps, fr["pose0"][0], pts, fr["obs"][0], fr["octave"][0])
+    assert r["status"] == 1
+    q = fr["pose0"][0][:4] / np.linalg.norm(fr["pose0"][0][:4])
+    np.testing.assert_allclose(r["pose"][:4], q if q[3] >= 0 else -q, atol=1e-15)
+    np.testing.assert_array_equal(r["pose"][4:], fr["pose0"][0][4:])
+    assert r["assign"][7] == -1
+
+
+def test_batched_driver_equals_single_calls(oracle, small_scene):
+    comps, fr = small_scene
+    rb = oracle.frames_solve(comps, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], nthreads=3, want_pts=True)
+    for f in range(3):
+        r = oracle.frame_solve(comps, fr["pose0"][f], fr["pts_w"][f], fr["obs"][f], fr["octave"][f])
+        assert np.array_equal(rb["pose"][f], r["pose"]) and np.array_equal(rb["assign"][f], r["assign"])
+        assert np.array_equal(rb["pts"][f], r["pts"]) and np.array_equal(rb["outlier"][f], r["outlier"])
