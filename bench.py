@@ -217,13 +217,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None  # nvidia-smi takes ~1 s to start: begin before the warm-up
     for _ in range(args.warmup):
         step()
     ctx.synchronize()
     launches0 = ctx.stats()["kernel_launches"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kt = []
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):

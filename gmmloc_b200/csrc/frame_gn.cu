@@ -295,6 +295,12 @@ __global__ void __launch_bounds__(kThreads) frame_gn_kernel(const FrameArgs a) {
     s_fail1 = 0;
     s_fail2 = 0;
   }
+  __syncthreads();
+  // camera centre at the initial pose, t_w_c = -(R^T t)  (gaussian_mixture.cpp:289)
+  const double twc0 = -(s_R[0] * s_pose[4] + s_R[3] * s_pose[5] + s_R[6] * s_pose[6]);
+  const double twc1 = -(s_R[1] * s_pose[4] + s_R[4] * s_pose[5] + s_R[7] * s_pose[6]);
+  const double twc2 = -(s_R[2] * s_pose[4] + s_R[5] * s_pose[5] + s_R[8] * s_pose[6]);
+  const double view_cos_thresh = cos(78.0 * 3.14159265358979323846 / 180.0);  // gaussian_mixture.cpp:284
   // ---- landmarks to fp64; structure-edge gates fixed at iteration 0 (exact replay of the oracle's
   // comparisons so the active edge set is identical) ----
   for (int i = tid; i < N; i += kThreads) {
@@ -311,6 +317,10 @@ __global__ void __launch_bounds__(kThreads) frame_gn_kernel(const FrameArgs a) {
         const double* mu = a.mean + (size_t)k * 3;
         const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
         if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;  // gmmloc_opt.cpp:336-338, localization_opt.cpp:781
+        // view-cos cull of planes seen closer than 12 deg to edge-on (GMM::renderView, gaussian_mixture.cpp:283-302)
+        const double p0 = mu[0] - twc0, p1 = mu[1] - twc1, p2 = mu[2] - twc2;
+        const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
+        if (view_cos < view_cos_thresh) b &= ~F_STR;
       } else {
         if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;  // gmmloc_opt.cpp:230
       }

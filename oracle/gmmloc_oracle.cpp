@@ -545,10 +545,16 @@ void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t
 
   // structure-edge gates, fixed at iteration 0 (SURVEY §7 / Appx A11):
   //   degenerate: e^2 <= tri_str_thresh     (gmmloc_opt.cpp:336-338, localization_opt.cpp:781)
+  //               and the component passes renderView's view-cos cull at the initial pose
   //   otherwise : d^2 <= mdist2_gate (9.0)  (gmmloc_opt.cpp:230)
   std::vector<uint8_t> str_on(N, 0), free_pt(N, 0), stereo(N, 0);
   const bool pose_free = prm->factor_mode != 2;
   const bool pts_free = prm->factor_mode != 1;
+  // camera centre at the initial pose: t_w_c = -(rot_c_w.inverse() * t_c_w)   gaussian_mixture.cpp:289
+  double R0[9], twc[3];
+  quat_to_rot(pose, R0);
+  for (int r = 0; r < 3; ++r) twc[r] = -((M(R0, 0, r) * pose[4] + M(R0, 1, r) * pose[5]) + M(R0, 2, r) * pose[6]);
+  const double view_cos_thresh = std::cos(78.0 * M_PI / 180.0);  // gaussian_mixture.cpp:284
   for (int i = 0; i < N; ++i) {
     stereo[i] = obsf[i * 3 + 2] >= 0.0f;  // u_right < 0 => monocular (tracking_opt.cpp:67)
     const int k = asg[i];
@@ -558,6 +564,12 @@ void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t
       if (c.is_degenerated) {
         const double e = (c.axis[0] * (xi[0] - c.mean[0]) + c.axis[3] * (xi[1] - c.mean[1])) + c.axis[6] * (xi[2] - c.mean[2]);
         str_on[i] = (e * e <= prm->tri_str_thresh);
+        // view-cos cull of planar components seen closer than 12 deg to edge-on (GMM::renderView,
+        // gaussian_mixture.cpp:283-302): po = (mu - t_w_c).normalized(), |po . axis0| < cos 78 deg => culled
+        const double po[3] = {c.mean[0] - twc[0], c.mean[1] - twc[1], c.mean[2] - twc[2]};
+        const double pn = std::sqrt((po[0] * po[0] + po[1] * po[1]) + po[2] * po[2]);
+        const double view_cos = std::fabs((po[0] * c.axis[0] + po[1] * c.axis[3]) + po[2] * c.axis[6]) / pn;
+        if (view_cos < view_cos_thresh) str_on[i] = 0;
       } else {
         str_on[i] = (oracle_chi2(&c, xi) <= prm->mdist2_gate);
       }

@@ -85,7 +85,10 @@ def frame_solve_dense(comps, pose0, pts_w, obs, octave, assign, iters=10, mode=0
             c = comps[k]
             d = x[i] - c["mean"]
             if c["is_degenerated"]:
-                str_on[i] = (c["axis"].reshape(3, 3)[:, 0] @ d) ** 2 <= tri_str_thresh
+                n = c["axis"].reshape(3, 3)[:, 0]
+                po = c["mean"] - (-R.T @ t)
+                view_cos = abs(po @ n) / np.linalg.norm(po)
+                str_on[i] = (n @ d) ** 2 <= tri_str_thresh and not view_cos < np.cos(np.deg2rad(78.0))
             else:
                 str_on[i] = d @ c["cov_inv"].reshape(3, 3) @ d <= gate
     free = pts_free & (stereo | str_on)
@@ -144,5 +147,8 @@ def frame_solve_dense(comps, pose0, pts_w, obs, octave, assign, iters=10, mode=0
 
 
 def rot_angle(Ra, Rb):
-    c = (np.trace(Ra.T @ Rb) - 1) / 2
-    return float(np.arccos(np.clip(c, -1, 1)))
+    """geodesic angle between two rotations (atan2 form: accurate for tiny angles, unlike arccos)."""
+    M = Ra.T @ Rb
+    sin = 0.5 * np.linalg.norm([M[2, 1] - M[1, 2], M[0, 2] - M[2, 0], M[1, 0] - M[0, 1]])
+    cos = 0.5 * (np.trace(M) - 1)
+    return float(np.arctan2(sin, cos))
