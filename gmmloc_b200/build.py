@@ -52,7 +52,9 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     hdr_m = _deps_mtime()
     jobs = []
     objs = []
+    env_extra = os.environ.get("GMMLOC_NVCC_EXTRA", "").split()
     for src, extra in SOURCES.items():
+        extra = list(extra) + env_extra
         s = CSRC / src
         o = OBJ_DIR / (src + ".o")
         objs.append(o)

@@ -5,12 +5,14 @@
 // reference's argmin convention (strict '<' on an ascending scan => lowest index wins ties,
 // gmmloc/src/gmmloc_opt.cpp:175-197,209-217) and optional gate (gmmloc_opt.cpp:230).
 //
-// K1: point-stationary.  Each thread keeps P landmarks in registers; the whitened component table
-//     (9 floats / component: U = L^T rows and -U mu) streams through shared memory in TMA bulk-copy
-//     tiles (cp.async.bulk + mbarrier, 3 stages) and is read with warp-broadcast LDS.128.  Per pair:
-//     9 FMA-pipe instructions (d2 = |U x - c|^2) + 1/2 FMNMX3.  The running best / second best are
-//     tracked per chunk of 16 components (5 ALU ops per chunk), the winning chunk is re-scanned once at
-//     the end to recover the index and the in-chunk runner-up.
+// K1: point-stationary.  Each thread keeps P landmarks in registers (each coordinate duplicated into a
+//     64-bit pair); the whitened component table (9 floats / component: U = L^T rows and -U mu, stored
+//     4 components x 9 coefficients per group) streams through shared memory in TMA bulk-copy tiles
+//     (cp.async.bulk + mbarrier, 3 stages) and is read with warp-broadcast LDS.128.  The score of TWO
+//     components is evaluated per instruction with the packed fma.rn.f32x2 (SASS FFMA2): per (landmark,
+//     component) pair 4.5 FFMA2 + 1/2 FMNMX3 issue slots (d2 = |U x - c|^2).  The running best / second
+//     best are tracked per chunk of 16 components (5 ALU ops per chunk); the winning chunk is re-scanned
+//     once at the end to recover the index and the in-chunk runner-up.
 // Exactness: the scan certifies an assignment when sqrt(second) - sqrt(best) exceeds twice the
 //     rigorous fp32 error bound alpha; everything else is pushed to a flag list.
 // K2: one warp per flagged landmark replays the fp32 scores (bit-identical: same score32()), and
@@ -29,6 +31,40 @@ constexpr int kTileFloats = kTileComps * kScanFloats;
 constexpr int kTileBytes = kTileFloats * 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2): elementwise IEEE rn, so each half equals the
+// scalar __fmaf_rn / __fmul_rn of score32() bit for bit ----
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// scores of the two components held in the halves of the coefficient pairs, for one (duplicated) landmark
+__device__ __forceinline__ uint64_t score2(const uint64_t* u, uint64_t X0, uint64_t X1, uint64_t X2) {
+  const uint64_t y0 = fma2(u[0], X0, fma2(u[1], X1, fma2(u[2], X2, u[6])));
+  const uint64_t y1 = fma2(u[3], X1, fma2(u[4], X2, u[7]));
+  const uint64_t y2 = fma2(u[5], X2, u[8]);
+  return fma2(y2, y2, fma2(y1, y1, mul2(y0, y0)));
+}
+// scalar score of component k read from the global table (epilogue / re-rank)
+__device__ __forceinline__ float score_of(const float* __restrict__ scan, int k, float x0, float x1, float x2) {
+  const float* f = scan + ((size_t)(k / kGroup) * kScanFloats) * kGroup + (k % kGroup);
+  return score32(__ldg(f + 0), __ldg(f + 4), __ldg(f + 8), __ldg(f + 12), __ldg(f + 16), __ldg(f + 20), __ldg(f + 24),
+                 __ldg(f + 28), __ldg(f + 32), x0, x1, x2);
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -96,18 +132,21 @@ __global__ void __launch_bounds__(THREADS, MINB) assoc_scan_kernel(const ScanArg
     }
   }
 
-  float x0[P], x1[P], x2[P], b1[P], b2[P];
+  uint64_t X0[P], X1[P], X2[P];  // landmark coordinates, duplicated into both halves
+  float b1[P], b2[P];
   int cid[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) {
     const long long i = base + (long long)p * THREADS + tid;
+    float x0 = 0.f, x1 = 0.f, x2 = 0.f;
     if (i < a.M) {
-      x0[p] = __ldg(a.pts + i * 3 + 0);
-      x1[p] = __ldg(a.pts + i * 3 + 1);
-      x2[p] = __ldg(a.pts + i * 3 + 2);
-    } else {
-      x0[p] = x1[p] = x2[p] = 0.f;
+      x0 = __ldg(a.pts + i * 3 + 0);
+      x1 = __ldg(a.pts + i * 3 + 1);
+      x2 = __ldg(a.pts + i * 3 + 2);
     }
+    X0[p] = pack2(x0, x0);
+    X1[p] = pack2(x1, x1);
+    X2[p] = pack2(x2, x2);
     b1[p] = CUDART_INF_F;
     b2[p] = CUDART_INF_F;
     cid[p] = 0;
@@ -117,7 +156,7 @@ __global__ void __launch_bounds__(THREADS, MINB) assoc_scan_kernel(const ScanArg
   for (int t = 0; t < ntiles; ++t) {
     const int stage = t % kStages;
     mbar_wait(&full[stage], (uint32_t)((t / kStages) & 1));
-    const float4* sp = reinterpret_cast<const float4*>(tiles + (size_t)stage * kTileFloats);
+    const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(tiles + (size_t)stage * kTileFloats);
     const int nchunks = min(kTileComps, a.Kpad - t * kTileComps) / kChunk;
     const int chunk0 = t * (kTileComps / kChunk);
     for (int c = 0; c < nchunks; ++c) {
@@ -125,27 +164,22 @@ __global__ void __launch_bounds__(THREADS, MINB) assoc_scan_kernel(const ScanArg
 #pragma unroll
       for (int p = 0; p < P; ++p) mch[p] = CUDART_INF_F;
 #pragma unroll
-      for (int q = 0; q < kChunk / 4; ++q) {
-        // 4 components = 36 floats = 9 broadcast LDS.128
-        float f[36];
+      for (int q = 0; q < kChunk / kGroup; ++q) {
+        // one group = 4 components = 9 broadcast LDS.128; .x = coefficient pair of components (0,1), .y = (2,3)
+        uint64_t ua[9], ub[9];
 #pragma unroll
         for (int v = 0; v < 9; ++v) {
-          const float4 w = sp[(c * (kChunk / 4) + q) * 9 + v];
-          f[4 * v + 0] = w.x;
-          f[4 * v + 1] = w.y;
-          f[4 * v + 2] = w.z;
-          f[4 * v + 3] = w.w;
+          const ulonglong2 w = sp[(c * (kChunk / kGroup) + q) * 9 + v];
+          ua[v] = w.x;
+          ub[v] = w.y;
         }
 #pragma unroll
-        for (int j = 0; j < 4; j += 2) {
-          const float* fa = f + 9 * j;
-          const float* fb = f + 9 * (j + 1);
-#pragma unroll
-          for (int p = 0; p < P; ++p) {
-            const float sa = score32(fa[0], fa[1], fa[2], fa[3], fa[4], fa[5], fa[6], fa[7], fa[8], x0[p], x1[p], x2[p]);
-            const float sb = score32(fb[0], fb[1], fb[2], fb[3], fb[4], fb[5], fb[6], fb[7], fb[8], x0[p], x1[p], x2[p]);
-            mch[p] = fminf(fminf(mch[p], sa), sb);  // FMNMX3
-          }
+        for (int p = 0; p < P; ++p) {
+          float s0, s1, s2, s3;
+          unpack2(score2(ua, X0[p], X1[p], X2[p]), s0, s1);
+          unpack2(score2(ub, X0[p], X1[p], X2[p]), s2, s3);
+          mch[p] = fminf(fminf(mch[p], s0), s1);  // FMNMX3
+          mch[p] = fminf(fminf(mch[p], s2), s3);
         }
       }
       const int chunk = chunk0 + c;
@@ -172,15 +206,15 @@ __global__ void __launch_bounds__(THREADS, MINB) assoc_scan_kernel(const ScanArg
   for (int p = 0; p < P; ++p) {
     const long long i = base + (long long)p * THREADS + tid;
     if (i >= a.M) continue;
-    const float px = x0[p], py = x1[p], pz = x2[p];
+    float px, py, pz, dup;
+    unpack2(X0[p], px, dup);
+    unpack2(X1[p], py, dup);
+    unpack2(X2[p], pz, dup);
     const bool finite_in = (fabsf(px) <= a.xmax) && (fabsf(py) <= a.xmax) && (fabsf(pz) <= a.xmax);  // false for NaN
-    const float* cp = a.scan + (size_t)cid[p] * kChunk * kScanFloats;
     int jbest = -1;
     float second = CUDART_INF_F;
     for (int j = 0; j < kChunk; ++j) {
-      const float* f = cp + j * kScanFloats;
-      const float s = score32(__ldg(f + 0), __ldg(f + 1), __ldg(f + 2), __ldg(f + 3), __ldg(f + 4), __ldg(f + 5),
-                              __ldg(f + 6), __ldg(f + 7), __ldg(f + 8), px, py, pz);
+      const float s = score_of(a.scan, cid[p] * kChunk + j, px, py, pz);
       if (jbest < 0 && s == b1[p]) {
         jbest = j;
       } else {
@@ -219,52 +253,134 @@ __global__ void __launch_bounds__(THREADS, MINB) assoc_scan_kernel(const ScanArg
   }
 }
 
-// K2: one warp per flagged landmark.
-__global__ void __launch_bounds__(256) assoc_rerank_kernel(const ScanArgs a) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+// K2: exact re-rank of the flagged landmarks.  Same point-stationary structure as K1 (P flagged landmarks
+// per thread, table streamed through the TMA tile pipeline, FFMA2 chunk minima), persistent over the
+// flag list whose length is only known on the device.  A chunk whose fp32 minimum is within the
+// landmark's threshold takes the slow path: every component of the chunk whose fp32 score (bit-identical
+// to K1's) is within the threshold is evaluated in fp64 with the oracle's operation order; strict '<' on
+// an ascending scan keeps the lowest index, exactly like the reference's loop (gmmloc_opt.cpp:209-217).
+template <int P, int THREADS>
+__global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tiles = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + kStages * kTileBytes);
+
+  const int tid = threadIdx.x;
   const int nflag = *a.flag_count;
-  for (int w = warp; w < nflag; w += nwarps) {
-    const long long i = a.flag_idx[w];
-    const float thr = a.flag_thr[w];
-    const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
-    const double dx = (double)px, dy = (double)py, dz = (double)pz;
-    double best = CUDART_INF;  // stands for numeric_limits<double>::max(): any finite d2 is smaller
-    int bi = -1;
-    const bool full = !(thr < CUDART_INF_F);
-    for (int k = lane; k < a.K; k += 32) {
-      bool cand = full;
-      if (!full) {
-        const float* f = a.scan + (size_t)k * kScanFloats;
-        const float s = score32(__ldg(f + 0), __ldg(f + 1), __ldg(f + 2), __ldg(f + 3), __ldg(f + 4), __ldg(f + 5),
-                                __ldg(f + 6), __ldg(f + 7), __ldg(f + 8), px, py, pz);
-        cand = s <= thr;
+  const int per = THREADS * P;
+  if ((long long)blockIdx.x * per >= nflag) return;
+  const int ntiles = (a.Kpad + kTileComps - 1) / kTileComps;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  int g = 0;  // tiles consumed so far by this CTA (stage = g % kStages, parity = (g / kStages) & 1)
+  for (long long base = (long long)blockIdx.x * per; base < nflag; base += (long long)gridDim.x * per) {
+    if (tid == 0) {
+      for (int t = 0; t < kStages && t < ntiles; ++t) {
+        const int st = (g + t) % kStages;
+        const int ncomp = min(kTileComps, a.Kpad - t * kTileComps);
+        const uint32_t bytes = (uint32_t)ncomp * kScanFloats * 4u;
+        mbar_expect_tx(&full[st], bytes);
+        tma_bulk_g2s(tiles + (size_t)st * kTileFloats, a.scan + (size_t)t * kTileFloats, bytes, &full[st]);
       }
-      if (cand) {
-        const double d = chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, dx, dy, dz);
-        if (d < best) {  // strict '<': ascending k within a lane keeps the lowest index
-          best = d;
-          bi = k;
+    }
+    uint64_t X0[P], X1[P], X2[P];
+    float thr[P];
+    double best[P];
+    int bi[P];
+    long long pi[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      const long long w = base + (long long)p * THREADS + tid;
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+      pi[p] = -1;
+      thr[p] = -1.f;  // nothing passes: idle slot
+      if (w < nflag) {
+        pi[p] = a.flag_idx[w];
+        thr[p] = a.flag_thr[w];
+        x0 = __ldg(a.pts + pi[p] * 3 + 0);
+        x1 = __ldg(a.pts + pi[p] * 3 + 1);
+        x2 = __ldg(a.pts + pi[p] * 3 + 2);
+      }
+      X0[p] = pack2(x0, x0);
+      X1[p] = pack2(x1, x1);
+      X2[p] = pack2(x2, x2);
+      best[p] = CUDART_INF;  // stands for numeric_limits<double>::max(): any finite d2 is smaller
+      bi[p] = -1;
+    }
+    for (int t = 0; t < ntiles; ++t) {
+      const int stage = (g + t) % kStages;
+      mbar_wait(&full[stage], (uint32_t)(((g + t) / kStages) & 1));
+      const float* tf = tiles + (size_t)stage * kTileFloats;
+      const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(tf);
+      const int nchunks = min(kTileComps, a.Kpad - t * kTileComps) / kChunk;
+      const int chunk0 = t * (kTileComps / kChunk);
+      for (int c = 0; c < nchunks; ++c) {
+        float mch[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) mch[p] = CUDART_INF_F;
+#pragma unroll
+        for (int q = 0; q < kChunk / kGroup; ++q) {
+          uint64_t ua[9], ub[9];
+#pragma unroll
+          for (int v = 0; v < 9; ++v) {
+            const ulonglong2 w = sp[(c * (kChunk / kGroup) + q) * 9 + v];
+            ua[v] = w.x;
+            ub[v] = w.y;
+          }
+#pragma unroll
+          for (int p = 0; p < P; ++p) {
+            float s0, s1, s2, s3;
+            unpack2(score2(ua, X0[p], X1[p], X2[p]), s0, s1);
+            unpack2(score2(ub, X0[p], X1[p], X2[p]), s2, s3);
+            mch[p] = fminf(fminf(mch[p], s0), s1);
+            mch[p] = fminf(fminf(mch[p], s2), s3);
+          }
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          if (pi[p] >= 0 && !(mch[p] > thr[p])) {  // rare: a candidate (or a non-finite landmark) in this chunk
+            float px, py, pz, dup;
+            unpack2(X0[p], px, dup);
+            unpack2(X1[p], py, dup);
+            unpack2(X2[p], pz, dup);
+            for (int j = 0; j < kChunk; ++j) {
+              const int k = (chunk0 + c) * kChunk + j;
+              if (k >= a.K) break;
+              const float* f = tf + ((size_t)(c * (kChunk / kGroup) + j / kGroup) * kScanFloats) * kGroup + (j % kGroup);
+              const float s = score32(f[0], f[4], f[8], f[12], f[16], f[20], f[24], f[28], f[32], px, py, pz);
+              if (!(s > thr[p])) {
+                const double d = chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, (double)px, (double)py, (double)pz);
+                if (d < best[p]) {
+                  best[p] = d;
+                  bi[p] = k;
+                }
+              }
+            }
+          }
         }
       }
-    }
-    // warp argmin, ties -> lowest index
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      const bool take = (oi >= 0) && (bi < 0 || ob < best || (ob == best && oi < bi));
-      if (take) {
-        best = ob;
-        bi = oi;
+      __syncthreads();  // every warp is done with this stage
+      if (tid == 0 && t + kStages < ntiles) {
+        const int tn = t + kStages;
+        const int ncomp = min(kTileComps, a.Kpad - tn * kTileComps);
+        const uint32_t bytes = (uint32_t)ncomp * kScanFloats * 4u;
+        mbar_expect_tx(&full[stage], bytes);
+        tma_bulk_g2s(tiles + (size_t)stage * kTileFloats, a.scan + (size_t)tn * kTileFloats, bytes, &full[stage]);
       }
     }
-    if (lane == 0) {
-      int idx = bi;
-      if (a.gate > 0.0 && idx >= 0 && best > a.gate) idx = -1;
-      a.assign[i] = idx;
-      if (a.d2 != nullptr) a.d2[i] = (bi >= 0) ? (float)best : CUDART_INF_F;
+    g += ntiles;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      if (pi[p] < 0) continue;
+      int idx = bi[p];
+      if (a.gate > 0.0 && idx >= 0 && best[p] > a.gate) idx = -1;
+      a.assign[pi[p]] = idx;
+      if (a.d2 != nullptr) a.d2[pi[p]] = (bi[p] >= 0) ? (float)best[p] : CUDART_INF_F;
     }
   }
 }
@@ -320,7 +436,18 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
   }
   if (e != cudaSuccess) return e;
   if (ev_between != nullptr && (e = cudaEventRecord(ev_between, stream)) != cudaSuccess) return e;
-  assoc_rerank_kernel<<<148 * 4, 256, 0, stream>>>(a);
+  {
+    const size_t smem = (size_t)kStages * kTileBytes + kStages * sizeof(uint64_t);
+    static bool attr_set = false;  // idempotent; a benign race between host threads
+    if (!attr_set) {
+      if ((e = cudaFuncSetAttribute(assoc_rerank_kernel<4, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+      attr_set = true;
+    }
+    // persistent over the flag list (length known only on the device); no more CTAs than the list can use
+    const long long max_ctas = (M + 511) / 512;
+    const unsigned grid = (unsigned)(max_ctas < 148 * 4 ? max_ctas : 148 * 4);
+    assoc_rerank_kernel<4, 128><<<grid, 128, smem, stream>>>(a);
+  }
   if (launches) *launches = 2;
   return cudaGetLastError();
 }

@@ -7,10 +7,17 @@
 
 namespace gmmloc {
 
-// Number of floats per component in the fp32 scan table:
-//   [0..5] = rows of U = L^T (upper triangular, cov_inv = L L^T):  U00 U01 U02 U11 U12 U22
-//   [6..8] = -c, c = U * mean       so that  y = U x - c  and  d2 = |y|^2
+// fp32 scan table: 9 floats per component,
+//   c = 0..5 : rows of U = L^T (upper triangular, cov_inv = L L^T):  U00 U01 U02 U11 U12 U22
+//   c = 6..8 : -(U * mean)            so that  y = U x - U mean  and  d2 = |y|^2
+// stored in groups of 4 components, coefficient-major inside a group: scan[(g * 9 + c) * 4 + j] is
+// coefficient c of component 4 g + j.  One LDS.128 then yields one coefficient of 4 components = two
+// aligned 64-bit register pairs, the operand format of the packed fma.rn.f32x2 (FFMA2) the scan issues.
 constexpr int kScanFloats = 9;
+constexpr int kGroup = 4;
+__host__ __device__ __forceinline__ size_t scan_index(int k, int c) {
+  return ((size_t)(k / kGroup) * kScanFloats + c) * kGroup + (k % kGroup);
+}
 // Components are tracked in chunks of kChunk inside the scan (second-best bookkeeping granularity);
 // the table is padded to a multiple of kChunk with +inf-scoring rows.
 constexpr int kChunk = 16;

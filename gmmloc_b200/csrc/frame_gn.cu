@@ -31,7 +31,13 @@ namespace gmmloc {
 
 namespace {
 
-constexpr int kThreads = 128;
+#ifndef GMMLOC_GN_THREADS
+#define GMMLOC_GN_THREADS 128
+#endif
+#ifndef GMMLOC_GN_MINB
+#define GMMLOC_GN_MINB 3
+#endif
+constexpr int kThreads = GMMLOC_GN_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kAcc = 27;  // 21 upper-triangular entries of the 6x6 + 6 rhs
 
@@ -258,7 +264,7 @@ __device__ bool solve6(const double* acc, double* x) {
 // numeric-failure contract (shared with the oracle): a frame whose solve hits a singular Hll / reduced
 // system or a non-finite value is returned UNSOLVED (normalised pose0, input landmarks) with
 // GMMLOC_FRAME_NUMERIC set.
-__global__ void __launch_bounds__(kThreads) frame_gn_kernel(const FrameArgs a) {
+__global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(const FrameArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[kWarps][kAcc];
   __shared__ double s_acc[kAcc];
@@ -462,6 +468,10 @@ __global__ void __launch_bounds__(kThreads) frame_gn_kernel(const FrameArgs a) {
         const Vec3 xw = {xs[i * 3], xs[i * 3 + 1], xs[i * 3 + 2]};
         Vec3 pc = rot(R, xw);
         pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
+        Vec3 ad = cross(om, pc);  // A dxi = omega x pc + upsilon
+        ad.x += up.x; ad.y += up.y; ad.z += up.z;
+        // (a free stereo point without a structure edge has the closed form dc = P^-1 e - ad, but taking
+        //  it as a separate branch diverges nearly every warp; measured slower than the uniform path)
         Sym3 G;
         Vec3 h;
         reproj(P, pc, obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2], b & F_STEREO, (double)P.s2inv[oct[i] & 7], G, h);
@@ -476,8 +486,6 @@ __global__ void __launch_bounds__(kThreads) frame_gn_kernel(const FrameArgs a) {
         }
         bool ok;
         const Sym3 Di = inv_sym(D, ok);
-        Vec3 ad = cross(om, pc);  // A dxi = omega x pc + upsilon
-        ad.x += up.x; ad.y += up.y; ad.z += up.z;
         const Vec3 ga = mul(G, ad);
         const Vec3 dc = mul(Di, {bl.x - ga.x, bl.y - ga.y, bl.z - ga.z});
         const Vec3 dw = rot_t(R, dc);

@@ -137,10 +137,10 @@ __global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps
                                                         unsigned int* alpha_bits) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= m.Kpad) return;
-  float* sp = m.scan + (size_t)k * kScanFloats;
+  float* sp = m.scan;
   if (k >= m.K) {  // padding rows score +inf and can never win
-    for (int i = 0; i < kScanFloats; ++i) sp[i] = 0.f;
-    sp[6] = -CUDART_INF_F;
+    for (int i = 0; i < kScanFloats; ++i) sp[scan_index(k, i)] = 0.f;
+    sp[scan_index(k, 6)] = -CUDART_INF_F;
     return;
   }
   double cov[9], ci[9], L[9], ev[3], ax[9];
@@ -164,8 +164,8 @@ __global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps
   m.is_sal[k] = (ev[1] > 0.2 && ev[2] > 0.2);   // gaussian.cpp:50-55
   if (!ok) {
     atomicOr(err_flag, 1);
-    for (int i = 0; i < kScanFloats; ++i) sp[i] = 0.f;
-    sp[6] = -CUDART_INF_F;
+    for (int i = 0; i < kScanFloats; ++i) sp[scan_index(k, i)] = 0.f;
+    sp[scan_index(k, 6)] = -CUDART_INF_F;
     return;
   }
   // fp32 whitening rows U = L^T, c = U mu
@@ -173,10 +173,10 @@ __global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps
   const double c0 = U[0] * mu[0] + U[1] * mu[1] + U[2] * mu[2];
   const double c1 = U[3] * mu[1] + U[4] * mu[2];
   const double c2 = U[5] * mu[2];
-  for (int i = 0; i < 6; ++i) sp[i] = (float)U[i];
-  sp[6] = (float)(-c0);
-  sp[7] = (float)(-c1);
-  sp[8] = (float)(-c2);
+  for (int i = 0; i < 6; ++i) sp[scan_index(k, i)] = (float)U[i];
+  sp[scan_index(k, 6)] = (float)(-c0);
+  sp[scan_index(k, 7)] = (float)(-c1);
+  sp[scan_index(k, 8)] = (float)(-c2);
   // error bound: |sqrt(score32) - d_exact| <= alpha_k for |x|_inf <= xmax,
   // alpha_k = (6 u32 + sqrt(64 u64)) * | |U| 1 (xmax + |mu|_inf) |_2
   const double mmax = fmax(fabs(mu[0]), fmax(fabs(mu[1]), fabs(mu[2])));
