@@ -2,6 +2,7 @@
 //
 // No CPU fallback anywhere: every entry point that computes needs a CUDA device and fails with
 // GMMLOC_ECUDA otherwise.  Nothing here links, loads or calls oracle/.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -204,6 +205,8 @@ struct gmmloc_ctx {
   DevBuf out_assign, out_d2, out_pose, out_pts, out_outlier, out_status, out_misc;
   DevBuf xws, fws;
   int* h_flag_count = nullptr;                     // pinned
+  cudaStream_t h2d = nullptr, d2h = nullptr;       // copy streams of the pipelined host entry point
+  std::vector<cudaEvent_t> ev_in, ev_done;         // per-chunk events (inputs landed / results ready)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // scan begin | scan end | re-rank end | GN end
   bool ev_assoc = false, ev_gn = false;
   gmmloc_stats_t stats{};
@@ -416,6 +419,8 @@ gmmloc_status_t gmmloc_ctx_create(int device, gmmloc_ctx_t** out) {
   if (!c) return fail(GMMLOC_ENOMEM, "host allocation failed");
   c->device = device;
   cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_flag_count, sizeof(int));
   if (e == cudaSuccess) e = c->flag_count.reserve(sizeof(int));
   for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
@@ -440,6 +445,10 @@ void gmmloc_ctx_destroy(gmmloc_ctx_t* c) {
   if (c->h_flag_count) cudaFreeHost(c->h_flag_count);
   for (cudaEvent_t e : c->ev)
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : c->ev_done) cudaEventDestroy(e);
+  if (c->h2d) cudaStreamDestroy(c->h2d);
+  if (c->d2h) cudaStreamDestroy(c->d2h);
   if (c->stream) cudaStreamDestroy(c->stream);
   cudaSetDevice(prev);
   delete c;
@@ -608,25 +617,51 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   CU(ctx->out_status.reserve(4 * (size_t)B));
   if (pts_out) CU(ctx->out_pts.reserve(12 * M + 16));
   if (outlier) CU(ctx->out_outlier.reserve(M + 16));
+  // Pipelined over chunks of frames: H2D of chunk c+1 (copy stream) overlaps the kernels of chunk c
+  // (compute stream) and the D2H of chunk c-1 (second copy stream); PCIe is full duplex.  With
+  // page-locked caller buffers the copies are truly asynchronous; pageable buffers still work.
+  const int chunk = (B >= 1024) ? 512 : B;
+  const int nchunks = (B + chunk - 1) / chunk;
+  while ((int)ctx->ev_in.size() < nchunks) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    ctx->ev_in.push_back(a);
+    CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    ctx->ev_done.push_back(b);
+  }
   cudaStream_t st = ctx->stream;
-  CU(cudaMemcpyAsync(ctx->in_pose.p, pose0, 56 * (size_t)B, cudaMemcpyHostToDevice, st));
-  if (M) {
-    CU(cudaMemcpyAsync(ctx->in_pts.p, pts_w, 12 * M, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->in_obs.p, obs, 12 * M, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ctx->in_oct.p, octave, M, cudaMemcpyHostToDevice, st));
+  for (int c = 0; c < nchunks; ++c) {
+    const size_t f0 = (size_t)c * chunk, nb = (size_t)std::min(chunk, B - c * chunk), m0 = f0 * N, nm = nb * N;
+    CU(cudaMemcpyAsync(ctx->in_pose.as<double>() + 7 * f0, pose0 + 7 * f0, 56 * nb, cudaMemcpyHostToDevice, ctx->h2d));
+    if (nm) {
+      CU(cudaMemcpyAsync(ctx->in_pts.as<float>() + 3 * m0, pts_w + 3 * m0, 12 * nm, cudaMemcpyHostToDevice, ctx->h2d));
+      CU(cudaMemcpyAsync(ctx->in_obs.as<float>() + 3 * m0, obs + 3 * m0, 12 * nm, cudaMemcpyHostToDevice, ctx->h2d));
+      CU(cudaMemcpyAsync(ctx->in_oct.as<uint8_t>() + m0, octave + m0, nm, cudaMemcpyHostToDevice, ctx->h2d));
+    }
+    CU(cudaEventRecord(ctx->ev_in[c], ctx->h2d));
+    CU(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
+    gmmloc_status_t s = gmmloc_frames_solve_async(
+        ctx, map, cam, params, ctx->in_pose.as<double>() + 7 * f0, ctx->in_pts.as<float>() + 3 * m0,
+        ctx->in_obs.as<float>() + 3 * m0, ctx->in_oct.as<uint8_t>() + m0, (int)nb, N, ctx->out_pose.as<double>() + 7 * f0,
+        pts_out ? ctx->out_pts.as<float>() + 3 * m0 : nullptr, ctx->out_assign.as<int32_t>() + m0,
+        outlier ? ctx->out_outlier.as<uint8_t>() + m0 : nullptr, ctx->out_status.as<int32_t>() + f0);
+    if (s != GMMLOC_OK) {
+      cudaStreamSynchronize(ctx->h2d);
+      cudaStreamSynchronize(st);
+      cudaStreamSynchronize(ctx->d2h);
+      return s;
+    }
+    CU(cudaEventRecord(ctx->ev_done[c], st));
+    CU(cudaStreamWaitEvent(ctx->d2h, ctx->ev_done[c], 0));
+    CU(cudaMemcpyAsync(pose_out + 7 * f0, ctx->out_pose.as<double>() + 7 * f0, 56 * nb, cudaMemcpyDeviceToHost, ctx->d2h));
+    CU(cudaMemcpyAsync(status + f0, ctx->out_status.as<int32_t>() + f0, 4 * nb, cudaMemcpyDeviceToHost, ctx->d2h));
+    if (nm) {
+      if (assign) CU(cudaMemcpyAsync(assign + m0, ctx->out_assign.as<int32_t>() + m0, 4 * nm, cudaMemcpyDeviceToHost, ctx->d2h));
+      if (pts_out) CU(cudaMemcpyAsync(pts_out + 3 * m0, ctx->out_pts.as<float>() + 3 * m0, 12 * nm, cudaMemcpyDeviceToHost, ctx->d2h));
+      if (outlier) CU(cudaMemcpyAsync(outlier + m0, ctx->out_outlier.as<uint8_t>() + m0, nm, cudaMemcpyDeviceToHost, ctx->d2h));
+    }
   }
-  gmmloc_status_t s = gmmloc_frames_solve_async(
-      ctx, map, cam, params, ctx->in_pose.as<double>(), ctx->in_pts.as<float>(), ctx->in_obs.as<float>(),
-      ctx->in_oct.as<uint8_t>(), B, N, ctx->out_pose.as<double>(), pts_out ? ctx->out_pts.as<float>() : nullptr,
-      ctx->out_assign.as<int32_t>(), outlier ? ctx->out_outlier.as<uint8_t>() : nullptr, ctx->out_status.as<int32_t>());
-  if (s != GMMLOC_OK) return s;
-  CU(cudaMemcpyAsync(pose_out, ctx->out_pose.p, 56 * (size_t)B, cudaMemcpyDeviceToHost, st));
-  CU(cudaMemcpyAsync(status, ctx->out_status.p, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
-  if (M) {
-    if (assign) CU(cudaMemcpyAsync(assign, ctx->out_assign.p, 4 * M, cudaMemcpyDeviceToHost, st));
-    if (pts_out) CU(cudaMemcpyAsync(pts_out, ctx->out_pts.p, 12 * M, cudaMemcpyDeviceToHost, st));
-    if (outlier) CU(cudaMemcpyAsync(outlier, ctx->out_outlier.p, M, cudaMemcpyDeviceToHost, st));
-  }
+  CU(cudaStreamSynchronize(ctx->d2h));
   CU(cudaStreamSynchronize(st));
   return GMMLOC_OK;
 }

@@ -25,6 +25,15 @@ namespace gmmloc {
 
 namespace {
 
+#ifndef GMMLOC_SCAN_P
+#define GMMLOC_SCAN_P 8
+#endif
+#ifndef GMMLOC_SCAN_THREADS
+#define GMMLOC_SCAN_THREADS 256
+#endif
+#ifndef GMMLOC_SCAN_MINB
+#define GMMLOC_SCAN_MINB 2
+#endif
 constexpr int kStages = 3;
 constexpr int kTileComps = 384;  // 384 * 36 B = 13.5 KB per stage
 constexpr int kTileFloats = kTileComps * kScanFloats;
@@ -423,13 +432,13 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
   // Fill the machine: 148 SMs x 2 CTAs; shrink the per-thread landmark count for small batches.
   int P = variant;
   if (P <= 0) {
-    if (M >= 148LL * 2 * 256 * 8) P = 8;
+    if (M >= 148LL * GMMLOC_SCAN_MINB * GMMLOC_SCAN_THREADS * GMMLOC_SCAN_P) P = 8;
     else if (M >= 148LL * 2 * 256 * 4) P = 4;
     else if (M >= 148LL * 2 * 128 * 2) P = 2;
     else P = 1;
   }
   switch (P) {
-    case 8: e = launch_scan_t<8, 256, 2>(a, stream); break;
+    case 8: e = launch_scan_t<GMMLOC_SCAN_P, GMMLOC_SCAN_THREADS, GMMLOC_SCAN_MINB>(a, stream); break;
     case 4: e = launch_scan_t<4, 256, 2>(a, stream); break;
     case 2: e = launch_scan_t<2, 128, 4>(a, stream); break;
     default: e = launch_scan_t<1, 128, 4>(a, stream); break;

@@ -20,7 +20,10 @@ __host__ __device__ __forceinline__ size_t scan_index(int k, int c) {
 }
 // Components are tracked in chunks of kChunk inside the scan (second-best bookkeeping granularity);
 // the table is padded to a multiple of kChunk with +inf-scoring rows.
-constexpr int kChunk = 16;
+#ifndef GMMLOC_CHUNK
+#define GMMLOC_CHUNK 16
+#endif
+constexpr int kChunk = GMMLOC_CHUNK;
 
 struct MapDev {
   int K = 0;      // real components

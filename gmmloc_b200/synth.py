@@ -104,9 +104,11 @@ def _se3_exp(xi):
     return Rm, V @ u
 
 
-def make_frames(mean, cov, B: int, N: int, seed: int = 0, mono_frac: float = 0.0, first_frame: int = 0):
+def make_frames(mean, cov, B: int, N: int, seed: int = 0, mono_frac: float = 0.0, first_frame: int = 0, poses_wc=None):
     """B frames of N landmarks.  Returns dict(pose0 Bx7 (T_cw: qx qy qz qw tx ty tz), pts_w BxNx3 f32,
-    obs BxNx3 f32 (u v u_r; u_r = -1 => mono), octave BxN u8, pose_gt Bx7)."""
+    obs BxNx3 f32 (u v u_r; u_r = -1 => mono), octave BxN u8, pose_gt Bx7).
+    poses_wc (optional, B x 7: x y z qx qy qz qw of T_wc, the layout of the reference's gt_sync files,
+    dataloader.cpp:118-138) replaces the random ground-truth poses (EuRoC replay)."""
     mean = np.asarray(mean, np.float64).reshape(-1, 3)
     cov = np.asarray(cov, np.float64).reshape(-1, 3, 3)
     K = mean.shape[0]
@@ -118,8 +120,18 @@ def make_frames(mean, cov, B: int, N: int, seed: int = 0, mono_frac: float = 0.0
     octave = np.empty((B, N), np.uint8)
     for f in range(B):
         rng = _rng(2, seed, first_frame + f)
-        for _ in range(64):
-            R_wc, t_wc = _sample_pose(rng)
+        for attempt in range(64):
+            if poses_wc is not None and attempt == 0:
+                t_wc = np.asarray(poses_wc[f][:3], np.float64)
+                R_wc = quat_to_rot(np.asarray(poses_wc[f][3:7], np.float64) / np.linalg.norm(poses_wc[f][3:7]))
+            elif poses_wc is not None:
+                # the recorded pose sees (almost) no component in the stereo depth range: relax the range
+                vis = np.flatnonzero((z > 0.2) & (u >= 0) & (u < W) & (v >= 0) & (v < H))
+                if vis.size == 0:
+                    vis = np.argsort(np.linalg.norm(mean - t_wc, axis=1))[:64]
+                break
+            else:
+                R_wc, t_wc = _sample_pose(rng)
             R_cw = R_wc.T
             t_cw = -R_cw @ t_wc
             mc = mean @ R_cw.T + t_cw

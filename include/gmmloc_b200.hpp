@@ -1,0 +1,245 @@
+// gmmloc_b200.hpp — header-only C++17 shim that restores the reference's own names on top of the C ABI
+// (include/gmmloc_b200.h).  Host code stays C++/ROS; this header needs neither Eigen nor g2o — vectors are
+// std::array so that Eigen users pass `.data()` (see INTEGRATION.md for the exact call-site patches).
+//
+// Reference surface mirrored (paths relative to the reference root):
+//   gmmloc::GMM                         gmmloc/include/gmmloc/gmm/gaussian_mixture.h:98-170
+//   gmmloc::GMMUtility::load/saveGMMModel  gmmloc/include/gmmloc/gmm/gmm_utils.h:13-16
+//   gmmloc::GaussianComponent (fields)  gmmloc/include/gmmloc/gmm/gaussian.h:60-92
+//   gmmloc::StrOptStat                  gmmloc/include/gmmloc/types/map.h:30-35
+//   GMMLoc::optimizePoint               gmmloc/include/gmmloc/gmmloc.h:43-46
+//   Tracking::optimizeCurrentPose       gmmloc/include/gmmloc/modules/tracking.h:51
+//   Localization::jointOptimization     gmmloc/include/gmmloc/modules/localization.h:61 (single free pose)
+#pragma once
+#include <array>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "gmmloc_b200.h"
+
+namespace gmmloc_b200 {
+
+using Vector3d = std::array<double, 3>;
+using Matrix3d = std::array<double, 9>;  // row-major
+
+// g2o::SE3Quat storage order: rotation quaternion (x y z w) then translation; T_cw maps world -> camera
+struct SE3Quat {
+  std::array<double, 7> v{0, 0, 0, 1, 0, 0, 0};
+  const double* data() const { return v.data(); }
+  double* data() { return v.data(); }
+};
+
+// the fields of gmmloc::Feature the hot path reads (feature.h:7-41): undistorted keypoint, right-image
+// column (< 0 => monocular) and pyramid octave
+struct Feature {
+  double u = 0, v = 0, u_right = -1;
+  int octave = 0;
+};
+
+// gmmloc::StrOptStat (map.h:30-35)
+struct StrOptStat {
+  bool res = false;
+  double chi2_proj = 0, chi2_str = 0;
+  Vector3d pt_est{0, 0, 0};
+};
+
+// host copy of one component's constants (public fields of gmmloc::GaussianComponent, gaussian.h:69-90)
+struct GaussianComponent {
+  Vector3d mean_{}, scale_{};
+  Matrix3d cov_{}, cov_inv_{}, sqrt_info_{}, axis_{};
+  double det_ = 0;
+  bool is_degenerated = false, is_salient = false;
+  int id = -1;
+  const Vector3d& mean() const { return mean_; }
+  const Matrix3d& cov_inv() const { return cov_inv_; }
+  const double& det() const { return det_; }
+};
+
+class Error : public std::runtime_error {
+ public:
+  Error(gmmloc_status_t s, const std::string& what) : std::runtime_error(what), status(s) {}
+  gmmloc_status_t status;
+};
+inline void check(gmmloc_status_t s) {
+  if (s != GMMLOC_OK) throw Error(s, std::string(gmmloc_status_string(s)) + ": " + gmmloc_last_error());
+}
+
+// ---- gmmloc::GMM ------------------------------------------------------------------------------------
+class GMM {
+ public:
+  using Ptr = std::shared_ptr<GMM>;
+  using ConstPtr = std::shared_ptr<const GMM>;
+
+  // ≙ explicit GMM(const GaussianComponents&): mean K x 3, cov K x 9 row-major
+  GMM(const double* mean, const double* cov, int K, int device = 0, double deg_eps = 1e-4) {
+    check(gmmloc_map_create(mean, cov, K, deg_eps, device, &h_));
+  }
+  explicit GMM(gmmloc_map_t* adopt) : h_(adopt) {}
+  GMM(const GMM&) = delete;
+  void operator=(const GMM&) = delete;
+  ~GMM() { gmmloc_map_destroy(h_); }
+
+  size_t countComponents() const { return (size_t)gmmloc_map_size(h_); }
+
+  // ≙ getComponents(): constants built on the device, fetched once and cached
+  const std::vector<GaussianComponent>& getComponents() const {
+    if (comps_.empty()) {
+      const size_t K = countComponents();
+      std::vector<double> mean(3 * K), cov(9 * K), ci(9 * K), det(K), sc(3 * K), ax(9 * K), sq(9 * K);
+      std::vector<uint8_t> dg(K), sl(K);
+      check(gmmloc_map_get_components(h_, mean.data(), cov.data(), ci.data(), det.data(), sc.data(), ax.data(), sq.data(),
+                                      dg.data(), sl.data()));
+      comps_.resize(K);
+      for (size_t k = 0; k < K; ++k) {
+        GaussianComponent& c = comps_[k];
+        for (int i = 0; i < 3; ++i) { c.mean_[i] = mean[3 * k + i]; c.scale_[i] = sc[3 * k + i]; }
+        for (int i = 0; i < 9; ++i) {
+          c.cov_[i] = cov[9 * k + i]; c.cov_inv_[i] = ci[9 * k + i]; c.sqrt_info_[i] = sq[9 * k + i]; c.axis_[i] = ax[9 * k + i];
+        }
+        c.det_ = det[k];
+        c.is_degenerated = dg[k] != 0;
+        c.is_salient = sl[k] != 0;
+        c.id = (int)k;
+      }
+    }
+    return comps_;
+  }
+  const GaussianComponent& getComponent3d(size_t idx) const { return getComponents().at(idx); }
+
+  gmmloc_map_t* handle() const { return h_; }
+
+ private:
+  gmmloc_map_t* h_ = nullptr;
+  mutable std::vector<GaussianComponent> comps_;
+};
+
+// ---- gmmloc::GMMUtility -----------------------------------------------------------------------------
+struct GMMUtility {
+  // returns false (message in gmmloc_last_error()) where the reference returns false + LOG(ERROR)
+  static bool loadGMMModel(const std::string& file_path, GMM::Ptr& model, int device = 0) {
+    gmmloc_map_t* h = nullptr;
+    if (gmmloc_map_load_gmm(file_path.c_str(), 1e-4, device, &h) != GMMLOC_OK) return false;
+    model = std::make_shared<GMM>(h);
+    return true;
+  }
+  static bool saveGMMModel(const std::string& file_path, GMM::Ptr& model, bool /*clear_file*/ = true) {
+    return model && gmmloc_map_save_gmm(model->handle(), file_path.c_str()) == GMMLOC_OK;
+  }
+};
+
+struct FrameResult {
+  std::vector<double> pose;      // B x 7
+  std::vector<float> pts;        // B x N x 3
+  std::vector<int32_t> assign;   // B x N
+  std::vector<uint8_t> outlier;  // B x N
+  std::vector<int32_t> status;   // B
+};
+
+// ---- per-thread solver context (the tracking thread and the localisation thread each own one) -------
+class Optimizer {
+ public:
+  explicit Optimizer(GMM::Ptr model, const gmmloc_camera_t& cam, int device = 0) : model_(std::move(model)), cam_(cam) {
+    check(gmmloc_ctx_create(device, &ctx_));
+    gmmloc_default_params(&params_);
+  }
+  Optimizer(const Optimizer&) = delete;
+  void operator=(const Optimizer&) = delete;
+  ~Optimizer() { gmmloc_ctx_destroy(ctx_); }
+
+  gmmloc_params_t& params() { return params_; }
+  gmmloc_ctx_t* handle() const { return ctx_; }
+
+  // brute-force association of N world points; -1 where gate > 0 and best d2 > gate (gmmloc_opt.cpp:230)
+  std::vector<int32_t> associate(const float* pts_w, int N, double gate = 0.0, std::vector<float>* d2 = nullptr) {
+    std::vector<int32_t> a((size_t)N);
+    if (d2) d2->resize((size_t)N);
+    check(gmmloc_associate(ctx_, model_->handle(), pts_w, 1, N, gate, a.data(), d2 ? d2->data() : nullptr));
+    return a;
+  }
+
+  // ≙ static StrOptStat GMMLoc::optimizePoint(pt3d, kp, Tcw, comp, proj_z)   (one problem)
+  StrOptStat optimizePoint(const Vector3d& pt3d, const Feature& kp, const SE3Quat& Tcw, int comp, double proj_z2, int iters = 5) {
+    const float obs[3] = {(float)kp.u, (float)kp.v, (float)kp.u_right};
+    const uint8_t oct = (uint8_t)kp.octave;
+    const int32_t c = comp;
+    StrOptStat r;
+    uint8_t res = 0;
+    check(gmmloc_points_solve(ctx_, model_->handle(), &cam_, &params_, pt3d.data(), obs, &oct, Tcw.data(), &c, &proj_z2, 1, iters,
+                              r.pt_est.data(), &r.chi2_proj, &r.chi2_str, &res));
+    r.res = res != 0;
+    return r;
+  }
+  // batched form: every (feature, candidate component) problem of a keyframe in one launch
+  // (the loop of GMMLoc::checkMapAssociation, gmmloc_opt.cpp:179-197)
+  std::vector<StrOptStat> optimizePoints(const std::vector<Vector3d>& pt3d, const std::vector<Feature>& kp,
+                                         const std::vector<SE3Quat>& Tcw, const std::vector<int32_t>& comp,
+                                         const std::vector<double>& proj_z2, int iters = 5) {
+    const size_t M = pt3d.size();
+    if (kp.size() != M || Tcw.size() != M || comp.size() != M || proj_z2.size() != M) throw Error(GMMLOC_EINVAL, "size mismatch");
+    std::vector<float> obs(3 * M);
+    std::vector<uint8_t> oct(M), res(M);
+    std::vector<double> x0(3 * M), pose(7 * M), est(3 * M), c2p(M), c2s(M);
+    for (size_t i = 0; i < M; ++i) {
+      obs[3 * i] = (float)kp[i].u; obs[3 * i + 1] = (float)kp[i].v; obs[3 * i + 2] = (float)kp[i].u_right;
+      oct[i] = (uint8_t)kp[i].octave;
+      for (int j = 0; j < 3; ++j) x0[3 * i + j] = pt3d[i][j];
+      for (int j = 0; j < 7; ++j) pose[7 * i + j] = Tcw[i].v[j];
+    }
+    check(gmmloc_points_solve(ctx_, model_->handle(), &cam_, &params_, x0.data(), obs.data(), oct.data(), pose.data(), comp.data(),
+                              proj_z2.data(), (int)M, iters, est.data(), c2p.data(), c2s.data(), res.data()));
+    std::vector<StrOptStat> out(M);
+    for (size_t i = 0; i < M; ++i) {
+      out[i].res = res[i] != 0;
+      out[i].chi2_proj = c2p[i];
+      out[i].chi2_str = c2s[i];
+      out[i].pt_est = {est[3 * i], est[3 * i + 1], est[3 * i + 2]};
+    }
+    return out;
+  }
+
+  // association + structure-constrained GN for B independent frames of N landmarks
+  // (single-free-pose Localization::jointOptimization; params().factor_mode selects P / S / J)
+  FrameResult optimizeFrames(const double* pose0, const float* pts_w, const float* obs, const uint8_t* octave, int B, int N) {
+    FrameResult r;
+    r.pose.resize(7 * (size_t)B);
+    r.pts.resize(3 * (size_t)B * N);
+    r.assign.resize((size_t)B * N);
+    r.outlier.resize((size_t)B * N);
+    r.status.resize((size_t)B);
+    check(gmmloc_frames_solve(ctx_, model_->handle(), &cam_, &params_, pose0, pts_w, obs, octave, B, N, r.pose.data(), r.pts.data(),
+                              r.assign.data(), r.outlier.data(), r.status.data()));
+    return r;
+  }
+
+  // ≙ int Tracking::optimizeCurrentPose(): pose-only system of one frame, Gauss-Newton for
+  // params().gn_iters iterations; updates Tcw, fills is_outlier, returns the inlier count
+  // (0 when fewer than 3 correspondences, tracking_opt.cpp:139-140)
+  int optimizeCurrentPose(SE3Quat& Tcw, const float* pts_w, const float* obs, const uint8_t* octave, int N,
+                          std::vector<uint8_t>* is_outlier = nullptr) {
+    if (N < 3) return 0;
+    gmmloc_params_t p = params_;
+    p.factor_mode = GMMLOC_MODE_POSE_ONLY;
+    std::vector<int32_t> assign((size_t)N);
+    std::vector<uint8_t> outl((size_t)N);
+    int32_t status = 0;
+    SE3Quat out;
+    check(gmmloc_frames_solve(ctx_, model_->handle(), &cam_, &p, Tcw.data(), pts_w, obs, octave, 1, N, out.data(), nullptr,
+                              assign.data(), outl.data(), &status));
+    Tcw = out;
+    int bad = 0;
+    for (uint8_t o : outl) bad += o;
+    if (is_outlier) *is_outlier = outl;
+    return N - bad;
+  }
+
+ private:
+  GMM::Ptr model_;
+  gmmloc_camera_t cam_;
+  gmmloc_params_t params_;
+  gmmloc_ctx_t* ctx_ = nullptr;
+};
+
+}  // namespace gmmloc_b200

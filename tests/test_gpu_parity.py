@@ -266,8 +266,10 @@ def test_frames_solve_shipped_map_v1_03_poses(gpu, oracle, golden_maps, gt_v1_03
     # BASELINE configs[2] in miniature: shipped map; the synthetic frames stand in for ORB landmarks
     g, ctx = gpu
     gm = golden_maps["v1"]
-    fr = synth.make_frames(gm["mean"], gm["cov"], 4, 1200, seed=5)
-    _check_frames(g, ctx, oracle, gm["mean"], gm["cov"], fr)
+    idx = np.arange(0, len(gt_v1_03), 307)  # 7 poses spread over the 2 149-frame sequence
+    fr = synth.make_frames(gm["mean"], gm["cov"], len(idx), 1200, seed=5, poses_wc=gt_v1_03[idx, 1:8])
+    out, exp, _ = _check_frames(g, ctx, oracle, gm["mean"], gm["cov"], fr)
+    assert np.all(out["status"] == 0)
 
 
 def test_frames_solve_iteration_counts(gpu, oracle):
@@ -293,6 +295,20 @@ def test_frames_solve_large_n_uses_global_workspace(gpu, oracle):
     mean, cov = synth.make_map(500, 0.5, seed=8)
     fr = synth.make_frames(mean, cov, 1, 9000, seed=8)
     _check_frames(g, ctx, oracle, mean, cov, fr)
+
+
+def test_frames_solve_pipelined_host_path_equals_single_chunks(gpu):
+    # B >= 1024 takes the chunked H2D / compute / D2H pipeline of gmmloc_frames_solve: same results as
+    # frame-by-frame calls (and therefore as the oracle, checked above)
+    g, ctx = gpu
+    mean, cov = synth.make_map(800, 0.5, seed=12)
+    m = g.GMM(mean, cov)
+    fr = synth.make_frames(mean, cov, 1100, 40, seed=12)
+    big = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
+    for lo, hi in ((0, 3), (510, 515), (1023, 1100)):
+        part = ctx.frames_solve(m, fr["pose0"][lo:hi], fr["pts_w"][lo:hi], fr["obs"][lo:hi], fr["octave"][lo:hi])
+        for k in ("pose", "pts", "assign", "outlier", "status"):
+            assert np.array_equal(big[k][lo:hi], part[k]), (k, lo)
 
 
 def test_frames_solve_deterministic(gpu):
