@@ -197,18 +197,27 @@ struct gmmloc_map {
   std::vector<double> h_mean, h_cov;  // kept for save / get_components
 };
 
-struct gmmloc_ctx {
-  int device = 0;
+// one compute stream with the work lists / workspaces / timing events its kernels use
+struct Lane {
   cudaStream_t stream = nullptr;
-  DevBuf flag_count, flag_idx, flag_thr;           // association work lists
-  DevBuf in_pts, in_obs, in_oct, in_pose, in_misc; // device copies of host inputs
-  DevBuf out_assign, out_d2, out_pose, out_pts, out_outlier, out_status, out_misc;
-  DevBuf xws, fws;
-  int* h_flag_count = nullptr;                     // pinned
-  cudaStream_t h2d = nullptr, d2h = nullptr;       // copy streams of the pipelined host entry point
-  std::vector<cudaEvent_t> ev_in, ev_done;         // per-chunk events (inputs landed / results ready)
+  DevBuf flag_count, flag_idx, flag_thr;  // association work lists
+  DevBuf xws, fws;                        // frame-GN global workspaces (N too large for shared memory)
+  int* h_flag_count = nullptr;            // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // scan begin | scan end | re-rank end | GN end
   bool ev_assoc = false, ev_gn = false;
+};
+
+struct gmmloc_ctx {
+  int device = 0;
+  // lane 0 serves the _async entry points; the pipelined host entry point alternates chunks between the
+  // two lanes so that the tail wave of one chunk's kernels overlaps the head of the next chunk's
+  Lane lanes[2];
+  int active = 0;
+  Lane& L() { return lanes[active]; }
+  DevBuf in_pts, in_obs, in_oct, in_pose, in_misc;  // device copies of host inputs
+  DevBuf out_assign, out_d2, out_pose, out_pts, out_outlier, out_status, out_misc;
+  cudaStream_t h2d = nullptr, d2h = nullptr;        // copy streams of the pipelined host entry point
+  std::vector<cudaEvent_t> ev_in, ev_done;          // per-chunk events (inputs landed / results ready)
   gmmloc_stats_t stats{};
 };
 
@@ -418,12 +427,16 @@ gmmloc_status_t gmmloc_ctx_create(int device, gmmloc_ctx_t** out) {
   gmmloc_ctx* c = new (std::nothrow) gmmloc_ctx();
   if (!c) return fail(GMMLOC_ENOMEM, "host allocation failed");
   c->device = device;
-  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  cudaError_t e = cudaSuccess;
+  for (Lane& l : c->lanes) {
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&l.h_flag_count, sizeof(int));
+    if (e == cudaSuccess) e = l.flag_count.reserve(sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(l.flag_count.p, 0, sizeof(int));
+    for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&l.ev[i]);
+  }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaMallocHost((void**)&c->h_flag_count, sizeof(int));
-  if (e == cudaSuccess) e = c->flag_count.reserve(sizeof(int));
-  for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&c->ev[i]);
   if (e != cudaSuccess) {
     gmmloc_ctx_destroy(c);
     return fail_cuda(e, "gmmloc_ctx_create");
@@ -437,28 +450,31 @@ void gmmloc_ctx_destroy(gmmloc_ctx_t* c) {
   int prev = 0;
   cudaGetDevice(&prev);
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamSynchronize(c->stream);
-  DevBuf* bufs[] = {&c->flag_count, &c->flag_idx, &c->flag_thr, &c->in_pts, &c->in_obs, &c->in_oct, &c->in_pose,
-                    &c->in_misc, &c->out_assign, &c->out_d2, &c->out_pose, &c->out_pts, &c->out_outlier,
-                    &c->out_status, &c->out_misc, &c->xws, &c->fws};
+  for (Lane& l : c->lanes) {
+    if (l.stream) cudaStreamSynchronize(l.stream);
+    DevBuf* lb[] = {&l.flag_count, &l.flag_idx, &l.flag_thr, &l.xws, &l.fws};
+    for (DevBuf* b : lb) b->release();
+    if (l.h_flag_count) cudaFreeHost(l.h_flag_count);
+    for (cudaEvent_t e : l.ev)
+      if (e) cudaEventDestroy(e);
+    if (l.stream) cudaStreamDestroy(l.stream);
+  }
+  DevBuf* bufs[] = {&c->in_pts, &c->in_obs, &c->in_oct, &c->in_pose, &c->in_misc, &c->out_assign, &c->out_d2, &c->out_pose,
+                    &c->out_pts, &c->out_outlier, &c->out_status, &c->out_misc};
   for (DevBuf* b : bufs) b->release();
-  if (c->h_flag_count) cudaFreeHost(c->h_flag_count);
-  for (cudaEvent_t e : c->ev)
-    if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_done) cudaEventDestroy(e);
   if (c->h2d) cudaStreamDestroy(c->h2d);
   if (c->d2h) cudaStreamDestroy(c->d2h);
-  if (c->stream) cudaStreamDestroy(c->stream);
   cudaSetDevice(prev);
   delete c;
 }
 
-void* gmmloc_ctx_stream(gmmloc_ctx_t* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+void* gmmloc_ctx_stream(gmmloc_ctx_t* ctx) { return ctx ? (void*)ctx->lanes[0].stream : nullptr; }
 
 gmmloc_status_t gmmloc_ctx_synchronize(gmmloc_ctx_t* ctx) {
   if (!ctx) return fail(GMMLOC_EINVAL, "null ctx");
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaStreamSynchronize(ctx->L().stream));
   return GMMLOC_OK;
 }
 
@@ -466,9 +482,9 @@ gmmloc_status_t gmmloc_ctx_stats(gmmloc_ctx_t* ctx, gmmloc_stats_t* out) {
   if (!ctx || !out) return fail(GMMLOC_EINVAL, "null pointer");
   // the flagged count of the last association is read back lazily (stream must be idle for it to be final)
   CU(cudaSetDevice(ctx->device));
-  CU(cudaMemcpyAsync(ctx->h_flag_count, ctx->flag_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  ctx->stats.flagged = *ctx->h_flag_count;
+  CU(cudaMemcpyAsync(ctx->L().h_flag_count, ctx->L().flag_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->L().stream));
+  CU(cudaStreamSynchronize(ctx->L().stream));
+  ctx->stats.flagged = *ctx->L().h_flag_count;
   *out = ctx->stats;
   return GMMLOC_OK;
 }
@@ -477,12 +493,12 @@ gmmloc_status_t gmmloc_ctx_kernel_times(gmmloc_ctx_t* ctx, float ms[3]) {
   if (!ctx || !ms) return fail(GMMLOC_EINVAL, "null pointer");
   ms[0] = ms[1] = ms[2] = 0.f;
   CU(cudaSetDevice(ctx->device));
-  CU(cudaStreamSynchronize(ctx->stream));
-  if (ctx->ev_assoc) {
-    CU(cudaEventElapsedTime(&ms[0], ctx->ev[0], ctx->ev[1]));
-    CU(cudaEventElapsedTime(&ms[1], ctx->ev[1], ctx->ev[2]));
+  CU(cudaStreamSynchronize(ctx->L().stream));
+  if (ctx->L().ev_assoc) {
+    CU(cudaEventElapsedTime(&ms[0], ctx->L().ev[0], ctx->L().ev[1]));
+    CU(cudaEventElapsedTime(&ms[1], ctx->L().ev[1], ctx->L().ev[2]));
   }
-  if (ctx->ev_gn) CU(cudaEventElapsedTime(&ms[2], ctx->ev[2], ctx->ev[3]));
+  if (ctx->L().ev_gn) CU(cudaEventElapsedTime(&ms[2], ctx->L().ev[2], ctx->L().ev[3]));
   return GMMLOC_OK;
 }
 
@@ -505,16 +521,16 @@ gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* ma
   ctx->stats.points = M;
   if (M == 0) return GMMLOC_OK;
   CU(cudaSetDevice(ctx->device));
-  CU(ctx->flag_idx.reserve(sizeof(int32_t) * (size_t)M));
-  CU(ctx->flag_thr.reserve(sizeof(float) * (size_t)M));
-  CU(cudaMemsetAsync(ctx->flag_count.p, 0, sizeof(int), ctx->stream));
+  CU(ctx->L().flag_idx.reserve(sizeof(int32_t) * (size_t)M));
+  CU(ctx->L().flag_thr.reserve(sizeof(float) * (size_t)M));
+  CU(cudaMemsetAsync(ctx->L().flag_count.p, 0, sizeof(int), ctx->L().stream));
   int launches = 0;
-  CU(cudaEventRecord(ctx->ev[0], ctx->stream));
-  CU(launch_associate(map->d, d_pts_w, M, gate, d_assign, d_d2, ctx->flag_count.as<int>(), ctx->flag_idx.as<int32_t>(),
-                      ctx->flag_thr.as<float>(), 0, ctx->stream, &launches, ctx->ev[1]));
-  CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-  ctx->ev_assoc = true;
-  ctx->ev_gn = false;
+  CU(cudaEventRecord(ctx->L().ev[0], ctx->L().stream));
+  CU(launch_associate(map->d, d_pts_w, M, gate, d_assign, d_d2, ctx->L().flag_count.as<int>(), ctx->L().flag_idx.as<int32_t>(),
+                      ctx->L().flag_thr.as<float>(), 0, ctx->L().stream, &launches, ctx->L().ev[1]));
+  CU(cudaEventRecord(ctx->L().ev[2], ctx->L().stream));
+  ctx->L().ev_assoc = true;
+  ctx->L().ev_gn = false;
   ctx->stats.kernel_launches += launches;
   return GMMLOC_OK;
 }
@@ -532,13 +548,13 @@ gmmloc_status_t gmmloc_associate(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, con
   CU(ctx->in_pts.reserve(12 * (size_t)M));
   CU(ctx->out_assign.reserve(4 * (size_t)M));
   if (d2) CU(ctx->out_d2.reserve(4 * (size_t)M));
-  CU(cudaMemcpyAsync(ctx->in_pts.p, pts_w, 12 * (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->in_pts.p, pts_w, 12 * (size_t)M, cudaMemcpyHostToDevice, ctx->L().stream));
   gmmloc_status_t s = gmmloc_associate_async(ctx, map, ctx->in_pts.as<float>(), M, gate, ctx->out_assign.as<int32_t>(),
                                              d2 ? ctx->out_d2.as<float>() : nullptr);
   if (s != GMMLOC_OK) return s;
-  CU(cudaMemcpyAsync(assign, ctx->out_assign.p, 4 * (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
-  if (d2) CU(cudaMemcpyAsync(d2, ctx->out_d2.p, 4 * (size_t)M, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaMemcpyAsync(assign, ctx->out_assign.p, 4 * (size_t)M, cudaMemcpyDeviceToHost, ctx->L().stream));
+  if (d2) CU(cudaMemcpyAsync(d2, ctx->out_d2.p, 4 * (size_t)M, cudaMemcpyDeviceToHost, ctx->L().stream));
+  CU(cudaStreamSynchronize(ctx->L().stream));
   return GMMLOC_OK;
 }
 
@@ -562,8 +578,8 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
     gmmloc_status_t s = gmmloc_associate_async(ctx, map, d_pts_w, M, 0.0, d_assign, nullptr);
     if (s != GMMLOC_OK) return s;
   } else {
-    ctx->ev_assoc = false;
-    if (M > 0) CU(cudaMemsetAsync(d_assign, 0xff, 4 * (size_t)M, ctx->stream));  // -1: no structure edges in pose-only mode
+    ctx->L().ev_assoc = false;
+    if (M > 0) CU(cudaMemsetAsync(d_assign, 0xff, 4 * (size_t)M, ctx->L().stream));  // -1: no structure edges in pose-only mode
   }
   FrameArgs a;
   a.mean = map->d.mean;
@@ -585,15 +601,15 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
   a.xws = nullptr;
   a.fws = nullptr;
   if ((size_t)N > frame_gn_smem_limit_points()) {
-    CU(ctx->xws.reserve(24 * (size_t)M));
-    CU(ctx->fws.reserve((size_t)M));
-    a.xws = ctx->xws.as<double>();
-    a.fws = ctx->fws.as<uint8_t>();
+    CU(ctx->L().xws.reserve(24 * (size_t)M));
+    CU(ctx->L().fws.reserve((size_t)M));
+    a.xws = ctx->L().xws.as<double>();
+    a.fws = ctx->L().fws.as<uint8_t>();
   }
-  if (!ctx->ev_assoc) CU(cudaEventRecord(ctx->ev[2], ctx->stream));
-  CU(launch_frame_gn(a, ctx->stream));
-  CU(cudaEventRecord(ctx->ev[3], ctx->stream));
-  ctx->ev_gn = true;
+  if (!ctx->L().ev_assoc) CU(cudaEventRecord(ctx->L().ev[2], ctx->L().stream));
+  CU(launch_frame_gn(a, ctx->L().stream));
+  CU(cudaEventRecord(ctx->L().ev[3], ctx->L().stream));
+  ctx->L().ev_gn = true;
   ctx->stats.kernel_launches += 1;
   return GMMLOC_OK;
 }
@@ -629,8 +645,21 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
     ctx->ev_done.push_back(b);
   }
-  cudaStream_t st = ctx->stream;
-  for (int c = 0; c < nchunks; ++c) {
+  // work lists of both lanes sized up front (a growing reserve() frees, which would synchronise mid-pipeline)
+  for (int l = 0; l < (nchunks > 1 ? 2 : 1); ++l) {
+    Lane& ln = ctx->lanes[l];
+    const size_t mc = (size_t)chunk * N;
+    CU(ln.flag_idx.reserve(sizeof(int32_t) * mc));
+    CU(ln.flag_thr.reserve(sizeof(float) * mc));
+    if ((size_t)N > frame_gn_smem_limit_points()) {
+      CU(ln.xws.reserve(24 * mc));
+      CU(ln.fws.reserve(mc));
+    }
+  }
+  gmmloc_status_t rc = GMMLOC_OK;
+  for (int c = 0; c < nchunks && rc == GMMLOC_OK; ++c) {
+    ctx->active = (nchunks > 1) ? (c & 1) : 0;
+    cudaStream_t st = ctx->L().stream;
     const size_t f0 = (size_t)c * chunk, nb = (size_t)std::min(chunk, B - c * chunk), m0 = f0 * N, nm = nb * N;
     CU(cudaMemcpyAsync(ctx->in_pose.as<double>() + 7 * f0, pose0 + 7 * f0, 56 * nb, cudaMemcpyHostToDevice, ctx->h2d));
     if (nm) {
@@ -640,17 +669,12 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     }
     CU(cudaEventRecord(ctx->ev_in[c], ctx->h2d));
     CU(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
-    gmmloc_status_t s = gmmloc_frames_solve_async(
+    rc = gmmloc_frames_solve_async(
         ctx, map, cam, params, ctx->in_pose.as<double>() + 7 * f0, ctx->in_pts.as<float>() + 3 * m0,
         ctx->in_obs.as<float>() + 3 * m0, ctx->in_oct.as<uint8_t>() + m0, (int)nb, N, ctx->out_pose.as<double>() + 7 * f0,
         pts_out ? ctx->out_pts.as<float>() + 3 * m0 : nullptr, ctx->out_assign.as<int32_t>() + m0,
         outlier ? ctx->out_outlier.as<uint8_t>() + m0 : nullptr, ctx->out_status.as<int32_t>() + f0);
-    if (s != GMMLOC_OK) {
-      cudaStreamSynchronize(ctx->h2d);
-      cudaStreamSynchronize(st);
-      cudaStreamSynchronize(ctx->d2h);
-      return s;
-    }
+    if (rc != GMMLOC_OK) break;
     CU(cudaEventRecord(ctx->ev_done[c], st));
     CU(cudaStreamWaitEvent(ctx->d2h, ctx->ev_done[c], 0));
     CU(cudaMemcpyAsync(pose_out + 7 * f0, ctx->out_pose.as<double>() + 7 * f0, 56 * nb, cudaMemcpyDeviceToHost, ctx->d2h));
@@ -661,8 +685,14 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
       if (outlier) CU(cudaMemcpyAsync(outlier + m0, ctx->out_outlier.as<uint8_t>() + m0, nm, cudaMemcpyDeviceToHost, ctx->d2h));
     }
   }
-  CU(cudaStreamSynchronize(ctx->d2h));
-  CU(cudaStreamSynchronize(st));
+  ctx->active = 0;
+  const cudaError_t e0 = cudaStreamSynchronize(ctx->h2d), e1 = cudaStreamSynchronize(ctx->lanes[0].stream),
+                    e2 = cudaStreamSynchronize(ctx->lanes[1].stream), e3 = cudaStreamSynchronize(ctx->d2h);
+  if (rc != GMMLOC_OK) return rc;
+  CU(e0);
+  CU(e1);
+  CU(e2);
+  CU(e3);
   return GMMLOC_OK;
 }
 
@@ -687,7 +717,7 @@ gmmloc_status_t gmmloc_points_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   CU(ctx->out_misc.reserve(out_bytes));
   char* in = ctx->in_misc.as<char>();
   char* outp = ctx->out_misc.as<char>();
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->L().stream;
   CU(cudaMemcpyAsync(in + o_x0, x0, 24 * m, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(in + o_pose, pose, 56 * m, cudaMemcpyHostToDevice, st));
   CU(cudaMemcpyAsync(in + o_pz, proj_z2, 8 * m, cudaMemcpyHostToDevice, st));

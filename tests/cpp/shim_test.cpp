@@ -17,14 +17,21 @@ using namespace gmmloc_b200;
   } while (0)
 
 int main(int argc, char** argv) {
-  // a 4 x 4 x 2 lattice of planar components (normal = z, sigma_z = 1 mm, in-plane 10 cm)
+  // a room corner seen from the origin (camera looks along +z): 16 planar components on the wall z = 3
+  // (normal z), 8 on the wall x = 2 (normal x), 8 on the floor y = 1.5 (normal y); sigma_n = 1 mm,
+  // in-plane 10 cm.  Three plane orientations make the 6-DoF reduced system full rank.
   const int K = 32;
   std::vector<double> mean(3 * K), cov(9 * K, 0.0);
   for (int k = 0; k < K; ++k) {
-    mean[3 * k] = (k % 4) * 1.0 - 1.5;
-    mean[3 * k + 1] = ((k / 4) % 4) * 1.0 - 1.5;
-    mean[3 * k + 2] = 3.0 + (k / 16) * 1.0;
-    cov[9 * k] = 1e-2; cov[9 * k + 4] = 1e-2; cov[9 * k + 8] = 1e-6;
+    int nrm;
+    if (k < 16) {
+      mean[3 * k] = (k % 4) * 0.8 - 1.2; mean[3 * k + 1] = (k / 4) * 0.6 - 0.9; mean[3 * k + 2] = 3.0; nrm = 2;
+    } else if (k < 24) {
+      mean[3 * k] = 2.0; mean[3 * k + 1] = ((k - 16) % 4) * 0.5 - 0.75; mean[3 * k + 2] = 2.6 + ((k - 16) / 4) * 0.8; nrm = 0;
+    } else {
+      mean[3 * k] = ((k - 24) % 4) * 0.7 - 1.05; mean[3 * k + 1] = 1.5; mean[3 * k + 2] = 3.0 + ((k - 24) / 4) * 0.8; nrm = 1;
+    }
+    for (int a = 0; a < 3; ++a) cov[9 * k + 4 * a] = (a == nrm) ? 1e-6 : 1e-2;
   }
   auto gmm = std::make_shared<GMM>(mean.data(), cov.data(), K);
   REQUIRE(gmm->countComponents() == (size_t)K);
@@ -32,6 +39,7 @@ int main(int argc, char** argv) {
   REQUIRE(c5.is_degenerated && !c5.is_salient);
   REQUIRE(std::fabs(c5.cov_inv()[8] - 1e6) < 1e-3 && std::fabs(c5.scale_[0] - 1e-6) < 1e-12);
   REQUIRE(std::fabs(std::fabs(c5.axis_[6]) - 1.0) < 1e-12);  // axis_.col(0) = +-z
+  REQUIRE(std::fabs(std::fabs(gmm->getComponent3d(20).axis_[0]) - 1.0) < 1e-12);  // +-x on the side wall
 
   gmmloc_camera_t cam{435.2046959714599, 435.2046959714599, 367.4517211914062, 252.2008514404297, 47.90639384423901, 752, 480};
   Optimizer opt(gmm, cam);
@@ -64,12 +72,16 @@ int main(int argc, char** argv) {
   REQUIRE(rb[0].res && !rb[1].res && rb[0].pt_est == r.pt_est);
 
   // frame solve: perfect observations of points on the planes, pose perturbed by 1 cm: GN recovers identity
-  const int N = 64;
+  const int N = 96;
   std::vector<float> P(3 * N), O(3 * N);
   std::vector<uint8_t> oct(N, 0);
   for (int i = 0; i < N; ++i) {
-    const int k = i % 16;  // front layer
-    const double x = mean[3 * k] + 0.05 * ((i * 7) % 5 - 2), y = mean[3 * k + 1] + 0.04 * ((i * 3) % 5 - 2), z = mean[3 * k + 2];
+    const int k = i % K;
+    const GaussianComponent& c = gmm->getComponent3d(k);
+    // offsets inside the plane of component k (its two large-variance axes)
+    const double o1 = 0.05 * ((i * 7) % 5 - 2), o2 = 0.04 * ((i * 3) % 5 - 2);
+    double x = c.mean()[0], y = c.mean()[1], z = c.mean()[2];
+    if (k < 16) { x += o1; y += o2; } else if (k < 24) { y += o1; z += o2; } else { x += o1; z += o2; }
     P[3 * i] = (float)x; P[3 * i + 1] = (float)y; P[3 * i + 2] = (float)z;
     const double u = cam.fx * x / z + cam.cx, v = cam.fy * y / z + cam.cy;
     O[3 * i] = (float)u; O[3 * i + 1] = (float)v; O[3 * i + 2] = (float)(u - cam.bf / z);
@@ -78,7 +90,7 @@ int main(int argc, char** argv) {
   T0.v[4] = 0.01; T0.v[5] = -0.01;
   FrameResult fr = opt.optimizeFrames(T0.data(), P.data(), O.data(), oct.data(), 1, N);
   REQUIRE(fr.status[0] == 0);
-  for (int i = 0; i < N; ++i) REQUIRE(fr.assign[i] == i % 16 && fr.outlier[i] == 0);
+  for (int i = 0; i < N; ++i) REQUIRE(fr.assign[i] == i % K && fr.outlier[i] == 0);
   REQUIRE(std::fabs(fr.pose[4]) < 2e-3 && std::fabs(fr.pose[5]) < 2e-3 && std::fabs(fr.pose[3] - 1.0) < 1e-5);
 
   // pose-only (Tracking::optimizeCurrentPose): all inliers, pose pulled back to identity
