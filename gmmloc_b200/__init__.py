@@ -92,6 +92,19 @@ class GMM:
             "mean", "cov", "cov_inv", "det", "scale", "axis", "sqrt_info", "is_degenerated", "is_salient")]))
         return out
 
+    def neighbors(self, thresh: float = 2.5):
+        """nbs_ of every component (GMM::GMM, gaussian_mixture.cpp:61-78) as CSR: (row_ptr K+1, col, dist)."""
+        K = self.countComponents()
+        row_ptr = np.zeros(K + 1, np.int64)
+        n = C.c_int64(0)
+        capi.check(capi.lib().gmmloc_map_neighbors(self._h, float(thresh), _ptr(row_ptr), None, None, 0, C.byref(n)))
+        col = np.empty(n.value, np.int32)
+        dist = np.empty(n.value, np.float64)
+        if n.value:
+            capi.check(capi.lib().gmmloc_map_neighbors(self._h, float(thresh), _ptr(row_ptr), _ptr(col), _ptr(dist), n.value,
+                                                       C.byref(n)))
+        return row_ptr, col, dist
+
     def scan_bound(self):
         a, x = C.c_double(), C.c_double()
         capi.check(capi.lib().gmmloc_map_scan_bound(self._h, C.byref(a), C.byref(x)))
@@ -181,6 +194,24 @@ class Context:
         capi.check(capi.lib().gmmloc_frames_solve(self._h, gmm._h, C.byref(cam), C.byref(params), _ptr(pose0), _ptr(pts_w),
                                                   _ptr(obs), _ptr(octave), B, N, _ptr(pose_out), _ptr(pts_out),
                                                   _ptr(assign), _ptr(outlier), _ptr(status)))
+
+    def optimizeCurrentPose(self, pose0, pts_w, obs, octave, valid=None, cam: Camera | None = None) -> dict:
+        """Batched Tracking::optimizeCurrentPose (exact 4-round LM schedule): pose B x 7, is_outlier B x N,
+        inliers B."""
+        cam = cam or v1_camera()
+        pose0 = _in(pose0, np.float64, (-1, 7))
+        B = pose0.shape[0]
+        pts = _in(pts_w, np.float32).reshape(B, -1, 3)
+        N = pts.shape[1]
+        obs = _in(obs, np.float32, (B, N, 3))
+        octave = _in(octave, np.uint8, (B, N))
+        v = None if valid is None else _in(valid, np.uint8, (B, N))
+        pose_out = np.empty((B, 7))
+        outlier = np.empty((B, N), np.uint8)
+        inliers = np.empty(B, np.int32)
+        capi.check(capi.lib().gmmloc_poses_optimize(self._h, C.byref(cam), _ptr(pose0), _ptr(pts), _ptr(obs), _ptr(octave),
+                                                    _ptr(v), B, N, _ptr(pose_out), _ptr(outlier), _ptr(inliers)))
+        return dict(pose=pose_out, outlier=outlier, inliers=inliers)
 
     def optimizePoint(self, gmm: GMM, x0, obs, octave, pose, comp, proj_z2, cam: Camera | None = None,
                       params: Params | None = None, iters: int = 5) -> dict:

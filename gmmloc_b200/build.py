@@ -30,6 +30,7 @@ SOURCES = {
     "map_build.cu": [],
     "assoc_scan.cu": [],
     "frame_gn.cu": [],
+    "pose_lm.cu": [],
     "point_gn.cu": ["-fmad=false"],
 }
 

@@ -55,6 +55,7 @@ SYMBOLS = {
     "gmmloc_map_size": (_i, [_vp]),
     "gmmloc_map_device": (_i, [_vp]),
     "gmmloc_map_get_components": (_i, [_vp] * 10),
+    "gmmloc_map_neighbors": (_i, [_vp, _d, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
     "gmmloc_map_scan_bound": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "gmmloc_ctx_create": (_i, [_i, C.POINTER(_vp)]),
     "gmmloc_ctx_destroy": (None, [_vp]),
@@ -68,6 +69,7 @@ SYMBOLS = {
     "gmmloc_associate_async": (_i, [_vp, _vp, _vp, _i64, _d, _vp, _vp]),
     "gmmloc_frames_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i] + [_vp] * 5),
     "gmmloc_frames_solve_async": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i] + [_vp] * 5),
+    "gmmloc_poses_optimize": (_i, [_vp, C.POINTER(Camera)] + [_vp] * 5 + [_i, _i] + [_vp] * 3),
     "gmmloc_points_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 6 + [_i, _i] + [_vp] * 4),
 }
 

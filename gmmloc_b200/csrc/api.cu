@@ -412,6 +412,47 @@ gmmloc_status_t gmmloc_map_get_components(const gmmloc_map_t* map, double* mean,
   return GMMLOC_OK;
 }
 
+gmmloc_status_t gmmloc_map_neighbors(const gmmloc_map_t* map, double thresh, int64_t* row_ptr, int32_t* col, double* dist,
+                                     int64_t cap, int64_t* count) {
+  if (!map || !row_ptr || !count) return fail(GMMLOC_EINVAL, "gmmloc_map_neighbors: null pointer");
+  const int K = map->d.K;
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CU(cudaSetDevice(map->device));
+  DevBuf counts, rp, dcol, ddist;
+  auto done = [&](gmmloc_status_t s) {
+    counts.release(); rp.release(); dcol.release(); ddist.release();
+    cudaSetDevice(prev);
+    return s;
+  };
+  cudaError_t e;
+  if ((e = counts.reserve(sizeof(int) * (size_t)K)) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(counts)"));
+  if ((e = launch_bh_neighbors(map->d, thresh, counts.as<int>(), nullptr, nullptr, nullptr, nullptr)) != cudaSuccess)
+    return done(fail_cuda(e, "bh_neighbors (count)"));
+  std::vector<int> h_counts((size_t)K);
+  if ((e = cudaMemcpy(h_counts.data(), counts.p, sizeof(int) * (size_t)K, cudaMemcpyDeviceToHost)) != cudaSuccess)
+    return done(fail_cuda(e, "bh_neighbors (count)"));
+  std::vector<long long> h_rp((size_t)K + 1);
+  h_rp[0] = 0;
+  for (int i = 0; i < K; ++i) h_rp[i + 1] = h_rp[i] + h_counts[i];
+  for (int i = 0; i <= K; ++i) row_ptr[i] = h_rp[i];
+  *count = h_rp[K];
+  if (col == nullptr || cap < h_rp[K] || h_rp[K] == 0) return done(GMMLOC_OK);
+  const size_t n = (size_t)h_rp[K];
+  if ((e = rp.reserve(sizeof(long long) * ((size_t)K + 1))) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(row_ptr)"));
+  if ((e = dcol.reserve(sizeof(int32_t) * n)) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(col)"));
+  if (dist && (e = ddist.reserve(sizeof(double) * n)) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(dist)"));
+  if ((e = cudaMemcpy(rp.p, h_rp.data(), sizeof(long long) * ((size_t)K + 1), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return done(fail_cuda(e, "H2D row_ptr"));
+  if ((e = launch_bh_neighbors(map->d, thresh, nullptr, rp.as<long long>(), dcol.as<int32_t>(), dist ? ddist.as<double>() : nullptr,
+                               nullptr)) != cudaSuccess)
+    return done(fail_cuda(e, "bh_neighbors (fill)"));
+  if ((e = cudaMemcpy(col, dcol.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost)) != cudaSuccess) return done(fail_cuda(e, "D2H col"));
+  if (dist && (e = cudaMemcpy(dist, ddist.p, sizeof(double) * n, cudaMemcpyDeviceToHost)) != cudaSuccess)
+    return done(fail_cuda(e, "D2H dist"));
+  return done(GMMLOC_OK);
+}
+
 gmmloc_status_t gmmloc_map_scan_bound(const gmmloc_map_t* map, double* alpha, double* xmax) {
   if (!map) return fail(GMMLOC_EINVAL, "null map");
   if (alpha) *alpha = map->d.alpha;
@@ -693,6 +734,64 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   CU(e1);
   CU(e2);
   CU(e3);
+  return GMMLOC_OK;
+}
+
+// ---- pose-only LM (Tracking::optimizeCurrentPose) --------------------------------------------------
+gmmloc_status_t gmmloc_poses_optimize(gmmloc_ctx_t* ctx, const gmmloc_camera_t* cam, const double* pose0, const float* pts_w,
+                                      const float* obs, const uint8_t* octave, const uint8_t* valid, int B, int N,
+                                      double* pose_out, uint8_t* outlier, int32_t* inliers) {
+  if (!ctx || !cam || B < 0 || N < 0) return fail(GMMLOC_EINVAL, "gmmloc_poses_optimize: bad argument");
+  if (B == 0) return GMMLOC_OK;
+  if (!pose0 || !pose_out || !inliers || (N > 0 && (!pts_w || !obs || !octave)))
+    return fail(GMMLOC_EINVAL, "gmmloc_poses_optimize: null pointer");
+  CU(cudaSetDevice(ctx->device));
+  ctx->active = 0;
+  const size_t M = (size_t)B * N;
+  CU(ctx->in_pose.reserve(56 * (size_t)B));
+  CU(ctx->in_pts.reserve(12 * M + 16));
+  CU(ctx->in_obs.reserve(12 * M + 16));
+  CU(ctx->in_oct.reserve(M + 16));
+  if (valid) CU(ctx->in_misc.reserve(M + 16));
+  CU(ctx->out_pose.reserve(56 * (size_t)B));
+  CU(ctx->out_status.reserve(4 * (size_t)B));
+  if (outlier) CU(ctx->out_outlier.reserve(M + 16));
+  cudaStream_t st = ctx->L().stream;
+  CU(cudaMemcpyAsync(ctx->in_pose.p, pose0, 56 * (size_t)B, cudaMemcpyHostToDevice, st));
+  if (M) {
+    CU(cudaMemcpyAsync(ctx->in_pts.p, pts_w, 12 * M, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->in_obs.p, obs, 12 * M, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->in_oct.p, octave, M, cudaMemcpyHostToDevice, st));
+    if (valid) CU(cudaMemcpyAsync(ctx->in_misc.p, valid, M, cudaMemcpyHostToDevice, st));
+  }
+  PoseLmArgs a;
+  gmmloc_params_t prm;
+  gmmloc_default_params(&prm);
+  fill_params(cam, &prm, a.prm);
+  a.pose0 = ctx->in_pose.as<double>();
+  a.pts_w = ctx->in_pts.as<float>();
+  a.obs = ctx->in_obs.as<float>();
+  a.octave = ctx->in_oct.as<uint8_t>();
+  a.valid = valid ? ctx->in_misc.as<uint8_t>() : nullptr;
+  a.B = B;
+  a.N = N;
+  a.pose_out = ctx->out_pose.as<double>();
+  a.outlier = outlier ? ctx->out_outlier.as<uint8_t>() : nullptr;
+  a.inliers = ctx->out_status.as<int32_t>();
+  a.ws_c2 = nullptr;
+  a.ws_st = nullptr;
+  if ((size_t)N > pose_lm_smem_limit_points()) {
+    CU(ctx->L().xws.reserve(8 * M));
+    CU(ctx->L().fws.reserve(M));
+    a.ws_c2 = ctx->L().xws.as<double>();
+    a.ws_st = ctx->L().fws.as<uint8_t>();
+  }
+  CU(launch_pose_lm(a, st));
+  ctx->stats.kernel_launches += 1;
+  CU(cudaMemcpyAsync(pose_out, ctx->out_pose.p, 56 * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(inliers, ctx->out_status.p, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (outlier && M) CU(cudaMemcpyAsync(outlier, ctx->out_outlier.p, M, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return GMMLOC_OK;
 }
 

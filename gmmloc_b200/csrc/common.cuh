@@ -53,6 +53,8 @@ struct FrameParamsDev {
 // Host-side launchers (one per kernel family); every launcher only enqueues on `stream`.
 cudaError_t launch_map_build(const MapDev& m, double deg_eps, double xmax, int* d_err, unsigned int* d_alpha_bits,
                              cudaStream_t stream);
+cudaError_t launch_bh_neighbors(const MapDev& m, double thresh, int* d_counts, const long long* d_row_ptr, int32_t* d_col,
+                                double* d_dist, cudaStream_t stream);
 cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, double gate, int32_t* d_assign,
                              float* d_d2, int* d_flag_count, int32_t* d_flag_idx, float* d_flag_thr, int variant,
                              cudaStream_t stream, int* launches, cudaEvent_t ev_between = nullptr);
@@ -77,6 +79,23 @@ struct FrameArgs {
 };
 cudaError_t launch_frame_gn(const FrameArgs& a, cudaStream_t stream);
 size_t frame_gn_smem_limit_points();  // largest N whose per-frame state stays in shared memory
+
+struct PoseLmArgs {
+  FrameParamsDev prm;
+  const double* pose0;    // B x 7
+  const float* pts_w;     // B x N x 3
+  const float* obs;       // B x N x 3
+  const uint8_t* octave;  // B x N
+  const uint8_t* valid;   // B x N or null
+  int B, N;
+  double* pose_out;       // B x 7
+  uint8_t* outlier;       // B x N or null
+  int32_t* inliers;       // B
+  double* ws_c2;          // B x N workspace when a frame does not fit in shared memory, else null
+  uint8_t* ws_st;
+};
+cudaError_t launch_pose_lm(const PoseLmArgs& a, cudaStream_t stream);
+size_t pose_lm_smem_limit_points();
 
 struct PointArgs {
   const double* mean;

@@ -26,6 +26,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "gn_common.cuh"
 
 namespace gmmloc {
 
@@ -42,67 +43,6 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kAcc = 27;  // 21 upper-triangular entries of the 6x6 + 6 rhs
 
 enum : uint8_t { F_STEREO = 1, F_STR = 2, F_FREE = 4, F_DEG = 8 };
-
-struct Sym3 {
-  double xx, xy, xz, yy, yz, zz;
-};
-struct Vec3 {
-  double x, y, z;
-};
-
-__device__ __forceinline__ Vec3 rot(const double* R, const Vec3& v) {
-  return {R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z};
-}
-__device__ __forceinline__ Vec3 rot_t(const double* R, const Vec3& v) {
-  return {R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z};
-}
-__device__ __forceinline__ Vec3 mul(const Sym3& A, const Vec3& v) {
-  return {A.xx * v.x + A.xy * v.y + A.xz * v.z, A.xy * v.x + A.yy * v.y + A.yz * v.z, A.xz * v.x + A.yz * v.y + A.zz * v.z};
-}
-__device__ __forceinline__ Vec3 cross(const Vec3& a, const Vec3& b) {
-  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
-}
-// inverse of a symmetric 3x3 by cofactors; ok=false when det is zero / non-finite (Hll singular)
-__device__ __forceinline__ Sym3 inv_sym(const Sym3& D, bool& ok) {
-  const double c00 = D.yy * D.zz - D.yz * D.yz;
-  const double c01 = D.xz * D.yz - D.xy * D.zz;
-  const double c02 = D.xy * D.yz - D.xz * D.yy;
-  const double det = D.xx * c00 + D.xy * c01 + D.xz * c02;
-  const double id = 1.0 / det;
-  ok = (det != 0.0) && isfinite(id);
-  return {c00 * id, c01 * id, c02 * id, (D.xx * D.zz - D.xz * D.xz) * id, (D.xy * D.xz - D.xx * D.yz) * id,
-          (D.xx * D.yy - D.xy * D.xy) * id};
-}
-
-__device__ __forceinline__ void reproj(const FrameParamsDev& p, const Vec3& pc, float o0, float o1, float o2, bool stereo,
-                                       double w, Sym3& G, Vec3& h) {
-  const double invz = 1.0 / pc.z;
-  const double a = p.fx * invz, b = p.fy * invz;
-  const double u = pc.x * a + p.cx, v = pc.y * b + p.cy;
-  const double e0 = (double)o0 - u, e1 = (double)o1 - v;
-  const double c0 = -a * pc.x * invz, c1 = -b * pc.y * invz;
-  double e2 = 0.0, c2 = 0.0, a2 = 0.0;
-  if (stereo) {
-    const double bz = p.bf * invz;
-    e2 = (double)o2 - (u - bz);
-    c2 = c0 + bz * invz;
-    a2 = a;
-  }
-  if (p.robust) {  // g2o RobustKernelHuber: weight rho1 = delta / sqrt(e2) beyond delta^2
-    const double chi = w * (e0 * e0 + e1 * e1 + e2 * e2);
-    const double delta = stereo ? p.delta_stereo : p.delta_mono;
-    if (chi > delta * delta) w *= delta / sqrt(chi);
-  }
-  G.xx = w * (a * a + a2 * a2);
-  G.xy = 0.0;
-  G.xz = w * (a * c0 + a2 * c2);
-  G.yy = w * (b * b);
-  G.yz = w * (b * c1);
-  G.zz = w * (c0 * c0 + c1 * c1 + c2 * c2);
-  h.x = w * (a * e0 + a2 * e2);
-  h.y = w * (b * e1);
-  h.z = w * (c0 * e0 + c1 * e1 + c2 * e2);
-}
 
 __device__ __forceinline__ void structure(const FrameArgs& a, const double* R, int k, uint8_t fl, const Vec3& xw, Sym3& S,
                                           Vec3& s) {
@@ -138,127 +78,6 @@ __device__ __forceinline__ void structure(const FrameArgs& a, const double* R, i
     S.yz = t[3] * R[6] + t[4] * R[7] + t[5] * R[8];
     S.zz = t[6] * R[6] + t[7] * R[7] + t[8] * R[8];
   }
-}
-
-// ---- SE3 (g2o SE3Quat semantics, SURVEY Appx B.1), thread-0 only ---------------------------------
-__device__ void quat_normalize(double* q) {
-  if (q[3] < 0)
-    for (int i = 0; i < 4; ++i) q[i] = -q[i];
-  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  for (int i = 0; i < 4; ++i) q[i] /= n;
-}
-__device__ void quat_to_rot(const double* q, double* R) {
-  const double x = q[0], y = q[1], z = q[2], w = q[3];
-  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
-  const double twx = tx * w, twy = ty * w, twz = tz * w;
-  const double txx = tx * x, txy = ty * x, txz = tz * x;
-  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
-  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
-  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
-}
-__device__ void rot_to_quat(const double* R, double* q) {
-  double t = R[0] + R[4] + R[8];
-  if (t > 0) {
-    t = sqrt(t + 1.0);
-    q[3] = 0.5 * t;
-    t = 0.5 / t;
-    q[0] = (R[7] - R[5]) * t;
-    q[1] = (R[2] - R[6]) * t;
-    q[2] = (R[3] - R[1]) * t;
-  } else {
-    int i = 0;
-    if (R[4] > R[0]) i = 1;
-    if (R[8] > R[i * 4]) i = 2;
-    const int j = (i + 1) % 3, k = (j + 1) % 3;
-    t = sqrt(R[i * 4] - R[j * 4] - R[k * 4] + 1.0);
-    q[i] = 0.5 * t;
-    t = 0.5 / t;
-    q[3] = (R[k * 3 + j] - R[j * 3 + k]) * t;
-    q[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
-    q[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
-  }
-}
-// pose <- exp(xi) * pose   (VertexSE3Expmap::oplusImpl)
-__device__ void se3_oplus(const double* xi, const double* pose, double* out) {
-  const double w0 = xi[0], w1 = xi[1], w2 = xi[2];
-  const double theta = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
-  const double Om[9] = {0, -w2, w1, w2, 0, -w0, -w1, w0, 0};
-  double Om2[9];
-  for (int r = 0; r < 3; ++r)
-    for (int c = 0; c < 3; ++c) Om2[r * 3 + c] = Om[r * 3] * Om[c] + Om[r * 3 + 1] * Om[3 + c] + Om[r * 3 + 2] * Om[6 + c];
-  double a, b, d;
-  if (theta < 1e-5) {
-    a = 1.0; b = 0.5; d = 1.0 / 6.0;
-  } else {
-    const double st = sin(theta), ct = cos(theta);
-    a = st / theta;
-    b = (1 - ct) / (theta * theta);
-    d = (theta - st) / (theta * theta * theta);
-  }
-  double Rm[9], V[9];
-  for (int i = 0; i < 9; ++i) {
-    const double I = (i % 4 == 0) ? 1.0 : 0.0;
-    Rm[i] = I + a * Om[i] + b * Om2[i];
-    V[i] = I + b * Om[i] + d * Om2[i];
-  }
-  const double t[3] = {V[0] * xi[3] + V[1] * xi[4] + V[2] * xi[5], V[3] * xi[3] + V[4] * xi[4] + V[5] * xi[5],
-                       V[6] * xi[3] + V[7] * xi[4] + V[8] * xi[5]};
-  double qd[4], Rd[9];
-  rot_to_quat(Rm, qd);
-  quat_normalize(qd);
-  quat_to_rot(qd, Rd);
-  const double* p = pose + 4;
-  const double rt[3] = {Rd[0] * p[0] + Rd[1] * p[1] + Rd[2] * p[2], Rd[3] * p[0] + Rd[4] * p[1] + Rd[5] * p[2],
-                        Rd[6] * p[0] + Rd[7] * p[1] + Rd[8] * p[2]};
-  const double ax = qd[0], ay = qd[1], az = qd[2], aw = qd[3], bx = pose[0], by = pose[1], bz = pose[2], bw = pose[3];
-  double q[4];
-  q[3] = aw * bw - ax * bx - ay * by - az * bz;
-  q[0] = aw * bx + ax * bw + ay * bz - az * by;
-  q[1] = aw * by + ay * bw + az * bx - ax * bz;
-  q[2] = aw * bz + az * bw + ax * by - ay * bx;
-  quat_normalize(q);
-  for (int i = 0; i < 4; ++i) out[i] = q[i];
-  for (int i = 0; i < 3; ++i) out[4 + i] = t[i] + rt[i];
-}
-
-// 6x6 SPD solve from the 21 upper-triangular entries (row-major packing) — plain Cholesky.
-__device__ bool solve6(const double* acc, double* x) {
-  double H[36], L[36];
-  int n = 0;
-  for (int r = 0; r < 6; ++r)
-    for (int c = r; c < 6; ++c) {
-      H[r * 6 + c] = acc[n];
-      H[c * 6 + r] = acc[n];
-      ++n;
-    }
-  for (int i = 0; i < 36; ++i) L[i] = 0.0;
-  for (int k = 0; k < 6; ++k) {
-    double s = H[k * 6 + k];
-    for (int j = 0; j < k; ++j) s -= L[k * 6 + j] * L[k * 6 + j];
-    if (!(s > 0.0) || !isfinite(s)) return false;
-    const double d = sqrt(s);
-    L[k * 6 + k] = d;
-    for (int i = k + 1; i < 6; ++i) {
-      double t = H[i * 6 + k];
-      for (int j = 0; j < k; ++j) t -= L[i * 6 + j] * L[k * 6 + j];
-      L[i * 6 + k] = t / d;
-    }
-  }
-  double y[6];
-  for (int i = 0; i < 6; ++i) {
-    double t = acc[21 + i];
-    for (int j = 0; j < i; ++j) t -= L[i * 6 + j] * y[j];
-    y[i] = t / L[i * 6 + i];
-  }
-  for (int i = 5; i >= 0; --i) {
-    double t = y[i];
-    for (int j = i + 1; j < 6; ++j) t -= L[j * 6 + i] * x[j];
-    x[i] = t / L[i * 6 + i];
-  }
-  for (int i = 0; i < 6; ++i)
-    if (!isfinite(x[i])) return false;
-  return true;
 }
 
 // numeric-failure contract (shared with the oracle): a frame whose solve hits a singular Hll / reduced
@@ -359,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(cons
         pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
         Sym3 G;
         Vec3 h;
-        reproj(P, pc, obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2], b & F_STEREO, (double)P.s2inv[oct[i] & 7], G, h);
+        reproj(P, pc, obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2], b & F_STEREO, (double)P.s2inv[oct[i] & 7], P.robust != 0, G, h);
         Sym3 M;
         Vec3 v;
         if (!free_pt) {
@@ -391,39 +210,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(cons
           M.yz = T10 * S.xz + T11 * S.yz + T12 * S.zz;
           M.zz = T20 * S.xz + T21 * S.yz + T22 * S.zz;
         }
-        // A^T M A and A^T v with A = [-[pc]x  I]:  C = [pc]x M,  [pc]x = [[0,-z,y],[z,0,-x],[-y,x,0]]
-        const double C00 = pc.y * M.xz - pc.z * M.xy, C01 = pc.y * M.yz - pc.z * M.yy, C02 = pc.y * M.zz - pc.z * M.yz;
-        const double C10 = pc.z * M.xx - pc.x * M.xz, C11 = pc.z * M.xy - pc.x * M.yz, C12 = pc.z * M.xz - pc.x * M.zz;
-        const double C20 = pc.x * M.xy - pc.y * M.xx, C21 = pc.x * M.yy - pc.y * M.xy, C22 = pc.x * M.yz - pc.y * M.xz;
-        // rot-rot block = C [pc]x^T,  (C [pc]x^T)_{ab} = sum_c C_ac [pc]x_{bc}
-        acc[0] += C02 * pc.y - C01 * pc.z;   // (0,0)
-        acc[1] += C00 * pc.z - C02 * pc.x;   // (0,1)
-        acc[2] += C01 * pc.x - C00 * pc.y;   // (0,2)
-        acc[3] += C00;                       // (0,3..5): rot-trans block = C
-        acc[4] += C01;
-        acc[5] += C02;
-        acc[6] += C10 * pc.z - C12 * pc.x;   // (1,1)
-        acc[7] += C11 * pc.x - C10 * pc.y;   // (1,2)
-        acc[8] += C10;
-        acc[9] += C11;
-        acc[10] += C12;
-        acc[11] += C21 * pc.x - C20 * pc.y;  // (2,2)
-        acc[12] += C20;
-        acc[13] += C21;
-        acc[14] += C22;
-        acc[15] += M.xx;                     // trans-trans block = M
-        acc[16] += M.xy;
-        acc[17] += M.xz;
-        acc[18] += M.yy;
-        acc[19] += M.yz;
-        acc[20] += M.zz;
-        const Vec3 br = cross(pc, v);        // A^T v = [pc x v ; v]
-        acc[21] += br.x;
-        acc[22] += br.y;
-        acc[23] += br.z;
-        acc[24] += v.x;
-        acc[25] += v.y;
-        acc[26] += v.z;
+        accumulate_pose(acc, pc, M, v);
       }
 #pragma unroll
       for (int i = 0; i < kAcc; ++i) {
@@ -474,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(cons
         //  it as a separate branch diverges nearly every warp; measured slower than the uniform path)
         Sym3 G;
         Vec3 h;
-        reproj(P, pc, obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2], b & F_STEREO, (double)P.s2inv[oct[i] & 7], G, h);
+        reproj(P, pc, obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2], b & F_STEREO, (double)P.s2inv[oct[i] & 7], P.robust != 0, G, h);
         Sym3 D = G;
         Vec3 bl = h;
         if (b & F_STR) {

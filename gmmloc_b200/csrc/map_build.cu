@@ -192,7 +192,71 @@ __global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps
   atomicMax(alpha_bits, __float_as_uint(af));  // non-negative floats order like their bit patterns
 }
 
+// ---- K5: Bhattacharyya neighbour lists (GMM::GMM, gaussian_mixture.cpp:61-78; BHCoefficient,
+// gmm_utils.h:30-52).  One warp per row i, lanes stride over j in ascending order; a ballot-based
+// ordered compaction keeps the reference's construction order (ascending component index).  Run twice:
+// counting pass (col == nullptr), then the fill pass with the exclusive-scanned row offsets.
+__device__ __forceinline__ double bh3(const double* cov0, const double* mu0, double det0, const double* cov1,
+                                      const double* mu1, double det1) {
+  double cov[9], inv[9];
+  for (int i = 0; i < 9; ++i) cov[i] = dmul(dadd(cov0[i], cov1[i]), 0.5);  // (cov0 + cov1) / 2.0
+  const double d[3] = {dsub(mu1[0], mu0[0]), dsub(mu1[1], mu0[1]), dsub(mu1[2], mu0[2])};
+  inv3(cov, inv);
+  const double r0 = dadd(dadd(dmul(d[0], inv[0]), dmul(d[1], inv[3])), dmul(d[2], inv[6]));
+  const double r1 = dadd(dadd(dmul(d[0], inv[1]), dmul(d[1], inv[4])), dmul(d[2], inv[7]));
+  const double r2 = dadd(dadd(dmul(d[0], inv[2]), dmul(d[1], inv[5])), dmul(d[2], inv[8]));
+  const double d0 = dmul(dadd(dadd(dmul(r0, d[0]), dmul(r1, d[1])), dmul(r2, d[2])), 0.125);  // / 8.0
+  const double d1 = dmul(log(__ddiv_rn(det3(cov), __dsqrt_rn(dmul(det0, det1)))), 0.5);          // / 2.0
+  return dadd(d0, d1);
+}
+
+__global__ void __launch_bounds__(256) bh_neighbors_kernel(MapDev m, double thresh, int* counts, const long long* row_ptr,
+                                                           int32_t* col, double* dist) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int i = warp; i < m.K; i += nwarps) {
+    double cov0[9], mu0[3];
+    for (int q = 0; q < 9; ++q) cov0[q] = m.cov[(size_t)i * 9 + q];
+    for (int q = 0; q < 3; ++q) mu0[q] = m.mean[(size_t)i * 3 + q];
+    const double det0 = m.det[i];
+    long long base = (col != nullptr) ? row_ptr[i] : 0;
+    int cnt = 0;
+    for (int j0 = 0; j0 < m.K; j0 += 32) {
+      const int j = j0 + lane;
+      bool hit = false;
+      double dd = 0.0;
+      if (j < m.K && j != i) {
+        double cov1[9], mu1[3];
+        for (int q = 0; q < 9; ++q) cov1[q] = m.cov[(size_t)j * 9 + q];
+        for (int q = 0; q < 3; ++q) mu1[q] = m.mean[(size_t)j * 3 + q];
+        dd = bh3(cov0, mu0, det0, cov1, mu1, m.det[j]);
+        hit = dd < thresh;  // gaussian_mixture.cpp:68
+      }
+      const unsigned ballot = __ballot_sync(0xffffffffu, hit);
+      if (col != nullptr && hit) {
+        const long long pos = base + __popc(ballot & ((1u << lane) - 1u));
+        col[pos] = j;
+        if (dist != nullptr) dist[pos] = dd;
+      }
+      const int n = __popc(ballot);
+      base += n;
+      cnt += n;
+    }
+    if (col == nullptr && lane == 0) counts[i] = cnt;
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_bh_neighbors(const MapDev& m, double thresh, int* d_counts, const long long* d_row_ptr, int32_t* d_col,
+                                double* d_dist, cudaStream_t stream) {
+  const int warps_needed = m.K;
+  int blocks = (warps_needed + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  bh_neighbors_kernel<<<blocks, 256, 0, stream>>>(m, thresh, d_counts, d_row_ptr, d_col, d_dist);
+  return cudaGetLastError();
+}
 
 cudaError_t launch_map_build(const MapDev& m, double deg_eps, double xmax, int* d_err, unsigned int* d_alpha_bits,
                              cudaStream_t stream) {

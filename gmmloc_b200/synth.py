@@ -187,3 +187,36 @@ def make_points_near(mean, cov, M: int, seed: int = 0, spread: float = 1.0):
     Lc = np.linalg.cholesky(cov)
     x = mean[k] + spread * np.einsum("nij,nj->ni", Lc[k], rng.normal(size=(M, 3)))
     return x.astype(np.float32), k
+
+
+def make_tracking_frames(mean, cov, B: int, N: int, seed: int = 0, mono_frac: float = 0.2, outlier_frac: float = 0.1,
+                         lm_noise: float = 0.01):
+    """Frames for the pose-only solve (Tracking::optimizeCurrentPose): landmarks are MAP POINTS (true point
+    + lm_noise), observations are noisy projections at the ground-truth pose with a fraction of gross
+    outliers (wrong matches), the initial pose is the ground truth perturbed by ~1 deg / 5 cm."""
+    fr = make_frames(mean, cov, B, N, seed=seed, mono_frac=1.0)  # mono branch: landmark = true point + 2 cm
+    rng = _rng(4, seed)
+    pts = fr["pts_w"].astype(np.float64)
+    pts += rng.normal(size=pts.shape) * (lm_noise - 0.02 if lm_noise > 0.02 else 0.0)
+    obs = np.empty_like(fr["obs"])
+    pose0 = np.empty_like(fr["pose0"])
+    for f in range(B):
+        q, t = fr["pose_gt"][f, :4], fr["pose_gt"][f, 4:]
+        R = quat_to_rot(q)
+        pc = pts[f] @ R.T + t
+        z = np.maximum(pc[:, 2], 0.2)
+        sig = 1.2 ** fr["octave"][f].astype(np.float64)
+        u = FX * pc[:, 0] / z + CX + rng.normal(size=N) * sig
+        v = FY * pc[:, 1] / z + CY + rng.normal(size=N) * sig
+        ur = u - BF / z + rng.normal(size=N) * 0.25
+        bad = rng.random(N) < outlier_frac
+        u = np.where(bad, u + rng.normal(size=N) * 30.0, u)
+        v = np.where(bad, v + rng.normal(size=N) * 30.0, v)
+        mono = rng.random(N) < mono_frac
+        ur = np.where(mono, -1.0, ur)
+        obs[f, :, 0], obs[f, :, 1], obs[f, :, 2] = u, v, ur
+        xi = np.concatenate([rng.normal(size=3) * np.deg2rad(1.0), rng.normal(size=3) * 0.05])
+        dR, dt = _se3_exp(xi)
+        pose0[f, :4] = rot_to_quat(dR @ R)
+        pose0[f, 4:] = dR @ t + dt
+    return dict(pose0=pose0, pts_w=pts.astype(np.float32), obs=obs, octave=fr["octave"], pose_gt=fr["pose_gt"])

@@ -110,6 +110,14 @@ GMMLOC_API int gmmloc_map_device(const gmmloc_map_t* map);
 GMMLOC_API gmmloc_status_t gmmloc_map_get_components(const gmmloc_map_t* map, double* mean, double* cov, double* cov_inv,
                                           double* det, double* scale, double* axis, double* sqrt_info,
                                           uint8_t* is_degenerated, uint8_t* is_salient);
+/* Neighbour lists of GMM::GMM (gaussian_mixture.cpp:61-78): for every component i the components j != i
+ * with Bhattacharyya distance BH(i, j) < thresh (GMMUtility::BHCoefficient, gmm_utils.h:30-52;
+ * thresh = gmmmap::neighbor_dist_thresh, 2.5 in v1.yaml:27), in ascending j (the reference's construction
+ * order), as CSR.  All K x K pairs are evaluated on the device.  row_ptr has K+1 entries; *count receives
+ * the total; col / dist (dist optional) are filled only when col != NULL and cap >= *count, so callers
+ * size them with a first call passing col = NULL. */
+GMMLOC_API gmmloc_status_t gmmloc_map_neighbors(const gmmloc_map_t* map, double thresh, int64_t* row_ptr, int32_t* col,
+                                                double* dist, int64_t cap, int64_t* count);
 /* error bound of the fp32 scan in whitened units (|sqrt(s32) - sqrt(d2)| <= alpha for |x|_inf <= xmax) */
 GMMLOC_API gmmloc_status_t gmmloc_map_scan_bound(const gmmloc_map_t* map, double* alpha, double* xmax);
 
@@ -158,6 +166,18 @@ GMMLOC_API gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gm
                                           const float* d_pts_w, const float* d_obs, const uint8_t* d_octave,
                                           int B, int N, double* d_pose_out, float* d_pts_out, int32_t* d_assign,
                                           uint8_t* d_outlier, int32_t* d_status);
+
+/* ---- pose-only solve with the reference's exact schedule: replaces Tracking::optimizeCurrentPose
+ * (tracking_opt.cpp:21-217) for B independent frames: g2o Levenberg-Marquardt on one SE3 vertex, one mono
+ * (u_r < 0) or stereo reprojection edge per feature that has a map point (valid[i] != 0; valid == NULL =>
+ * all), Huber sqrt(5.991) / sqrt(7.815), 4 rounds x 10 iterations each restarted from pose0, inlier
+ * reclassification by chi2 > 5.991 / 7.815 after every round, robust kernel dropped for the last round.
+ *  outputs: pose_out B x 7, outlier B x N (Frame::is_outlier_, optional), inliers B (the function's return
+ *  value: correspondences - outliers; 0 and pose_out = pose0 when fewer than 3 correspondences). */
+GMMLOC_API gmmloc_status_t gmmloc_poses_optimize(gmmloc_ctx_t* ctx, const gmmloc_camera_t* cam, const double* pose0,
+                                                 const float* pts_w, const float* obs, const uint8_t* octave,
+                                                 const uint8_t* valid, int B, int N, double* pose_out, uint8_t* outlier,
+                                                 int32_t* inliers);
 
 /* ---- batched point solves: replaces GMMLoc::optimizePoint (gmmloc_opt.cpp:260-342), M independent
  * 3-DoF GN problems (one stereo reprojection edge + one point-to-plane edge), `iters` iterations (5).

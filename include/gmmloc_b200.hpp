@@ -214,25 +214,19 @@ class Optimizer {
     return r;
   }
 
-  // ≙ int Tracking::optimizeCurrentPose(): pose-only system of one frame, Gauss-Newton for
-  // params().gn_iters iterations; updates Tcw, fills is_outlier, returns the inlier count
-  // (0 when fewer than 3 correspondences, tracking_opt.cpp:139-140)
+  // ≙ int Tracking::optimizeCurrentPose() with the reference's exact schedule (4-round Levenberg-
+  // Marquardt, Huber, inlier reclassification; tracking_opt.cpp:21-217): updates Tcw, fills is_outlier
+  // (Frame::is_outlier_), returns the inlier count (0 when fewer than 3 correspondences).
+  // valid[i] != 0 marks features that have a map point (nullptr: all).
   int optimizeCurrentPose(SE3Quat& Tcw, const float* pts_w, const float* obs, const uint8_t* octave, int N,
-                          std::vector<uint8_t>* is_outlier = nullptr) {
-    if (N < 3) return 0;
-    gmmloc_params_t p = params_;
-    p.factor_mode = GMMLOC_MODE_POSE_ONLY;
-    std::vector<int32_t> assign((size_t)N);
+                          std::vector<uint8_t>* is_outlier = nullptr, const uint8_t* valid = nullptr) {
     std::vector<uint8_t> outl((size_t)N);
-    int32_t status = 0;
+    int32_t inliers = 0;
     SE3Quat out;
-    check(gmmloc_frames_solve(ctx_, model_->handle(), &cam_, &p, Tcw.data(), pts_w, obs, octave, 1, N, out.data(), nullptr,
-                              assign.data(), outl.data(), &status));
+    check(gmmloc_poses_optimize(ctx_, &cam_, Tcw.data(), pts_w, obs, octave, valid, 1, N, out.data(), outl.data(), &inliers));
     Tcw = out;
-    int bad = 0;
-    for (uint8_t o : outl) bad += o;
     if (is_outlier) *is_outlier = outl;
-    return N - bad;
+    return inliers;
   }
 
  private:

@@ -744,6 +744,167 @@ void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t
   }
 }
 
+int oracle_optimize_pose_lm(const oracle_camera_t* camp, const double pose0[7], const float* pts_w, const float* obsf,
+                            const uint8_t* octave, const uint8_t* valid, int N, double pose_out[7], uint8_t* outlier) {
+  const Cam cam{camp->fx, camp->fy, camp->cx, camp->cy, camp->bf};
+  std::vector<int> idx;  // features with a map point (tracking_opt.cpp:63-64)
+  for (int i = 0; i < N; ++i) {
+    if (outlier) outlier[i] = 0;
+    if (!valid || valid[i]) idx.push_back(i);
+  }
+  const int E = (int)idx.size();
+  for (int i = 0; i < 7; ++i) pose_out[i] = pose0[i];
+  if (E < 3) return 0;  // :139-140
+  const double delta_mono = (double)(float)std::sqrt(5.991), delta_stereo = (double)(float)std::sqrt(7.815);  // :57-58
+  const float chi2_mono = 5.991f, chi2_stereo = 7.815f;                                                      // :145-146
+  std::vector<uint8_t> level(E, 0), is_out(E, 0), stereo(E);
+  std::vector<double> err(3 * (size_t)E, 0.0), w(E);
+  for (int e = 0; e < E; ++e) {
+    stereo[e] = obsf[idx[e] * 3 + 2] >= 0.0f;  // u_right < 0 => monocular (:67)
+    w[e] = oracle_sigma2_inv(octave[idx[e]]);
+  }
+  bool robust = true;
+  double pose[7];
+  // errors of every ACTIVE edge at `T` (computeActiveErrors) and their robustified sum (activeRobustChi2)
+  auto active_errors = [&](const double* T) {
+    double R[9];
+    quat_to_rot(T, R);
+    double chi = 0.0;
+    for (int e = 0; e < E; ++e) {
+      if (level[e]) continue;
+      const int i = idx[e];
+      const double X[3] = {(double)pts_w[3 * i], (double)pts_w[3 * i + 1], (double)pts_w[3 * i + 2]};
+      double pc[3];
+      mat3_vec(R, X, pc);
+      for (int r = 0; r < 3; ++r) pc[r] += T[4 + r];
+      const double ob[3] = {(double)obsf[3 * i], (double)obsf[3 * i + 1], (double)obsf[3 * i + 2]};
+      reproj_edge(cam, R, pc, ob, stereo[e], &err[3 * (size_t)e], nullptr, nullptr);
+      const double* er = &err[3 * (size_t)e];
+      const double c2 = w[e] * ((er[0] * er[0] + er[1] * er[1]) + er[2] * er[2]);
+      if (robust) {
+        const double d = stereo[e] ? delta_stereo : delta_mono, dsqr = d * d;
+        chi += (c2 <= dsqr) ? c2 : 2 * std::sqrt(c2) * d - dsqr;  // RobustKernelHuber rho[0]
+      } else {
+        chi += c2;
+      }
+    }
+    return chi;
+  };
+  int n_bad = 0;
+  for (int round = 0; round < 4; ++round) {
+    for (int i = 0; i < 7; ++i) pose[i] = pose0[i];  // vertex_se3->setEstimate(curr_frame_->getTcw())  :152
+    quat_normalize(pose);
+    double lambda = 0.0, ni = 2.0;
+    bool ok = true;
+    for (int it = 0; it < 10 && ok; ++it) {  // optimizer.optimize(its[it])  :154
+      double cur_chi = active_errors(pose);
+      // buildSystem at the current estimate
+      double R[9], H[36] = {0}, b[6] = {0};
+      quat_to_rot(pose, R);
+      for (int e = 0; e < E; ++e) {
+        if (level[e]) continue;
+        const int i = idx[e];
+        const double X[3] = {(double)pts_w[3 * i], (double)pts_w[3 * i + 1], (double)pts_w[3 * i + 2]};
+        double pc[3], er[3], Jp[18];
+        mat3_vec(R, X, pc);
+        for (int r = 0; r < 3; ++r) pc[r] += pose[4 + r];
+        const double ob[3] = {(double)obsf[3 * i], (double)obsf[3 * i + 1], (double)obsf[3 * i + 2]};
+        reproj_edge(cam, R, pc, ob, stereo[e], er, nullptr, Jp);
+        const int m = stereo[e] ? 3 : 2;
+        double rho1 = 1.0;
+        if (robust) {
+          double c2 = 0;
+          for (int r = 0; r < m; ++r) c2 += er[r] * er[r];
+          c2 *= w[e];
+          rho1 = huber_rho1(c2, stereo[e] ? delta_stereo : delta_mono);
+        }
+        for (int a = 0; a < 6; ++a) {
+          for (int c = 0; c < 6; ++c) {
+            double s = 0;
+            for (int r = 0; r < m; ++r) s += Jp[r * 6 + a] * Jp[r * 6 + c];
+            H[a * 6 + c] += rho1 * w[e] * s;
+          }
+          double s = 0;
+          for (int r = 0; r < m; ++r) s += Jp[r * 6 + a] * er[r];
+          b[a] -= rho1 * w[e] * s;
+        }
+      }
+      if (it == 0) {  // computeLambdaInit: tau * max diagonal, tau = 1e-5
+        double md = 0;
+        for (int a = 0; a < 6; ++a) md = std::max(md, std::fabs(H[a * 6 + a]));
+        lambda = 1e-5 * md;
+        ni = 2.0;
+      }
+      double rho = 0;
+      int qmax = 0;
+      do {
+        double Hl[36], dx[6], trial[7];
+        for (int a = 0; a < 36; ++a) Hl[a] = H[a];
+        for (int a = 0; a < 6; ++a) Hl[a * 6 + a] += lambda;
+        const bool ok2 = solve6(Hl, b, dx);
+        double tmp_chi;
+        if (ok2) {
+          se3_oplus(dx, pose, trial);
+          tmp_chi = active_errors(trial);
+        } else {
+          for (int a = 0; a < 6; ++a) dx[a] = 0;
+          tmp_chi = std::numeric_limits<double>::max();
+        }
+        rho = cur_chi - tmp_chi;
+        double scale = 0;
+        for (int a = 0; a < 6; ++a) scale += dx[a] * (lambda * dx[a] + b[a]);
+        scale += 1e-3;
+        rho /= scale;
+        if (rho > 0 && std::isfinite(tmp_chi) && ok2) {  // good step
+          double alpha = 1. - std::pow(2 * rho - 1, 3);
+          alpha = std::min(alpha, 2. / 3.);
+          lambda *= std::max(1. / 3., alpha);
+          ni = 2;
+          cur_chi = tmp_chi;
+          for (int a = 0; a < 7; ++a) pose[a] = trial[a];
+        } else {
+          lambda *= ni;
+          ni *= 2;
+          if (!std::isfinite(lambda)) break;
+        }
+        ++qmax;
+      } while (rho < 0 && qmax < 10);
+      if (qmax == 10 || rho == 0 || !std::isfinite(lambda)) ok = false;  // OptimizationAlgorithm::Terminate
+    }
+    // classification (:157-203)
+    double R[9];
+    quat_to_rot(pose, R);
+    n_bad = 0;
+    for (int e = 0; e < E; ++e) {
+      const int i = idx[e];
+      if (is_out[e]) {  // e->computeError() at the current estimate
+        const double X[3] = {(double)pts_w[3 * i], (double)pts_w[3 * i + 1], (double)pts_w[3 * i + 2]};
+        double pc[3];
+        mat3_vec(R, X, pc);
+        for (int r = 0; r < 3; ++r) pc[r] += pose[4 + r];
+        const double ob[3] = {(double)obsf[3 * i], (double)obsf[3 * i + 1], (double)obsf[3 * i + 2]};
+        reproj_edge(cam, R, pc, ob, stereo[e], &err[3 * (size_t)e], nullptr, nullptr);
+      }
+      const double* er = &err[3 * (size_t)e];
+      const float chi2 = (float)(w[e] * ((er[0] * er[0] + er[1] * er[1]) + er[2] * er[2]));
+      if (chi2 > (stereo[e] ? chi2_stereo : chi2_mono)) {
+        is_out[e] = 1;
+        level[e] = 1;
+        ++n_bad;
+      } else {
+        is_out[e] = 0;
+        level[e] = 0;
+      }
+    }
+    if (round == 2) robust = false;  // e->setRobustKernel(0)
+    if (E < 10) break;               // optimizer.edges().size() < 10
+  }
+  for (int i = 0; i < 7; ++i) pose_out[i] = pose[i];
+  if (outlier)
+    for (int e = 0; e < E; ++e) outlier[idx[e]] = is_out[e];
+  return E - n_bad;
+}
+
 void oracle_frames_solve(const oracle_comp_t* comps, int K, const oracle_camera_t* cam,
                          const oracle_params_t* prm, const double* pose0, const float* pts_w,
                          const float* obs, const uint8_t* octave, int B, int N, double* pose_out,

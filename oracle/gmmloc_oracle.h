@@ -99,6 +99,17 @@ void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t
                         double pose_out[7], double* pts_out, int32_t* assign, uint8_t* outlier,
                         int32_t* status, double* trace);
 
+/* A10 / f1: Tracking::optimizeCurrentPose (tracking_opt.cpp:21-217) restated with g2o's Levenberg-
+ * Marquardt (SURVEY Appx B.7): pose-only, 4 rounds x 10 iterations, each round restarted from pose0
+ * (:152), Huber on all edges until the end of round 3 (:177-178,201-202), inlier reclassification by
+ * (float)chi2 > 5.991f / 7.815f after every round (:157-203; current outliers are re-evaluated at the
+ * round's final estimate, inliers keep the error of the last LM trial, accepted or not), early exit when
+ * fewer than 10 edges exist (:205-206).  valid (optional) marks features that have a map point.
+ * Returns num_init_correspondences - num_bad (0 when fewer than 3 correspondences, :139-140; pose_out =
+ * pose0 then).  pts_w N x 3 fp32, obs N x 3 fp32 (u v u_r; u_r < 0 => mono). */
+int oracle_optimize_pose_lm(const oracle_camera_t* cam, const double pose0[7], const float* pts_w, const float* obs,
+                            const uint8_t* octave, const uint8_t* valid, int N, double pose_out[7], uint8_t* outlier);
+
 /* Batched driver over B independent frames, sharded over nthreads std::threads (the reference runs
  * each solve on the caller's thread; sharding over frames is the CPU baseline's "all cores" mode). */
 void oracle_frames_solve(const oracle_comp_t* comps, int K, const oracle_camera_t* cam,

@@ -81,6 +81,7 @@ def lib():
         L.oracle_sigma2_inv.restype = C.c_double
         L.oracle_neighbors.restype = C.c_int64
         L.oracle_optimize_point.restype = C.c_int
+        L.oracle_optimize_pose_lm.restype = C.c_int
         L.oracle_gmm_read.restype = C.c_int
         L.oracle_gmm_write.restype = C.c_int
         _lib = L
@@ -204,6 +205,21 @@ def frames_solve(comps, pose0, pts_w, obs, octave, cam=None, prm=None, nthreads=
                               _p(obs), _p(octave), C.c_int(B), C.c_int(N), _p(pose_out), _p(pts_out), _p(assign),
                               _p(outlier), _p(status), C.c_int(nthreads))
     return dict(pose=pose_out, pts=pts_out, assign=assign, outlier=outlier, status=status)
+
+
+def optimize_pose_lm(pose0, pts_w, obs, octave, valid=None, cam=None):
+    """Tracking::optimizeCurrentPose (4-round LM): returns (n_inliers, pose, is_outlier)."""
+    cam = cam or v1_camera()
+    pose0 = np.ascontiguousarray(pose0, np.float64)
+    pts_w = np.ascontiguousarray(pts_w, np.float32).reshape(-1, 3)
+    N = pts_w.shape[0]
+    obs = np.ascontiguousarray(obs, np.float32).reshape(N, 3)
+    octave = np.ascontiguousarray(octave, np.uint8)
+    v = None if valid is None else np.ascontiguousarray(valid, np.uint8)
+    pose = np.zeros(7)
+    outl = np.zeros(N, np.uint8)
+    n = lib().oracle_optimize_pose_lm(C.byref(cam), _p(pose0), _p(pts_w), _p(obs), _p(octave), _p(v), C.c_int(N), _p(pose), _p(outl))
+    return n, pose, outl
 
 
 def sigma2_inv(octave: int) -> float:

@@ -49,7 +49,7 @@ int main(int argc, char** argv) {
   for (int i = 0; i < 3 * K; ++i) pts[i] = (float)mean[i];
   std::vector<float> d2;
   auto a = opt.associate(pts.data(), K, 0.0, &d2);
-  for (int k = 0; k < K; ++k) REQUIRE(a[k] == k && d2[k] == 0.0f);
+  for (int k = 0; k < K; ++k) REQUIRE(a[k] == k && d2[k] < 1e-6f);  // the fp32 landmark is the mean rounded to float
   float off[3] = {(float)mean[15], (float)mean[16], (float)(mean[17] + 0.002)};
   auto a1 = opt.associate(off, 1, 0.0, &d2);
   REQUIRE(a1[0] == 5 && std::fabs(d2[0] - 4.0f) < 1e-2f);

@@ -152,3 +152,105 @@ def rot_angle(Ra, Rb):
     sin = 0.5 * np.linalg.norm([M[2, 1] - M[1, 2], M[0, 2] - M[2, 0], M[1, 0] - M[0, 1]])
     cos = 0.5 * (np.trace(M) - 1)
     return float(np.arctan2(sin, cos))
+
+
+def huber(c2, delta):
+    """g2o RobustKernelHuber: (rho0, rho1)."""
+    if c2 <= delta * delta:
+        return c2, 1.0
+    s = np.sqrt(c2)
+    return 2 * s * delta - delta * delta, delta / s
+
+
+def optimize_pose_lm(pose0, pts_w, obs, octave, valid=None):
+    """Independent NumPy restatement of Tracking::optimizeCurrentPose (tracking_opt.cpp:21-217) with g2o's
+    Levenberg-Marquardt (SURVEY Appx B.7).  Returns (n_inliers, R, t, is_outlier)."""
+    N = len(pts_w)
+    idx = [i for i in range(N) if valid is None or valid[i]]
+    q0 = np.asarray(pose0[:4], float)
+    q0 = q0 / np.linalg.norm(q0) * (1 if q0[3] >= 0 else -1)
+    R0, t0 = synth.quat_to_rot(q0), np.asarray(pose0[4:], float)
+    outl = np.zeros(N, np.uint8)
+    if len(idx) < 3:
+        return 0, R0, t0, outl
+    X = np.asarray(pts_w, np.float64)
+    ob = np.asarray(obs, np.float64)
+    st = {i: bool(obs[i][2] >= 0) for i in idx}
+    w = {i: s2inv(octave[i]) for i in idx}
+    dl = {True: float(np.float32(np.sqrt(7.815))), False: float(np.float32(np.sqrt(5.991)))}
+    th = {True: np.float32(7.815), False: np.float32(5.991)}
+    level = {i: 0 for i in idx}
+    is_out = {i: False for i in idx}
+    err = {i: np.zeros(3) for i in idx}
+    robust = True
+
+    def resid(i, R, t):
+        m = 3 if st[i] else 2
+        return ob[i, :m] - project(R @ X[i] + t, st[i])
+
+    def active(R, t):
+        chi = 0.0
+        for i in idx:
+            if level[i]:
+                continue
+            e = resid(i, R, t)
+            err[i] = e
+            c2 = w[i] * (e @ e)
+            chi += huber(c2, dl[st[i]])[0] if robust else c2
+        return chi
+
+    n_bad = 0
+    for rnd in range(4):
+        R, t = R0.copy(), t0.copy()
+        lam, ni, ok = 0.0, 2.0, True
+        for it in range(10):
+            if not ok:
+                break
+            cur = active(R, t)
+            H, b = np.zeros((6, 6)), np.zeros(6)
+            for i in idx:
+                if level[i]:
+                    continue
+                pc = R @ X[i] + t
+                e = resid(i, R, t)
+                J = -dproj(pc, st[i]) @ np.hstack([-skew(pc), np.eye(3)])
+                r1 = huber(w[i] * (e @ e), dl[st[i]])[1] if robust else 1.0
+                H += r1 * w[i] * J.T @ J
+                b -= r1 * w[i] * J.T @ e
+            if it == 0:
+                lam, ni = 1e-5 * np.abs(np.diag(H)).max(), 2.0
+            q = 0
+            while True:
+                dx = np.linalg.solve(H + lam * np.eye(6), b)
+                dR, dt = se3_exp(dx)
+                Rt, tt = dR @ R, dR @ t + dt
+                tmp = active(Rt, tt)
+                rho = (cur - tmp) / (dx @ (lam * dx + b) + 1e-3)
+                if rho > 0 and np.isfinite(tmp):
+                    lam *= max(1 / 3, min(1 - (2 * rho - 1) ** 3, 2 / 3))
+                    ni, cur, R, t = 2.0, tmp, Rt, tt
+                else:
+                    lam *= ni
+                    ni *= 2
+                q += 1
+                if not (rho < 0 and q < 10):
+                    break
+            if q == 10 or rho == 0:
+                ok = False
+        n_bad = 0
+        for i in idx:
+            if is_out[i]:
+                err[i] = resid(i, R, t)
+            c2 = np.float32(w[i] * (err[i] @ err[i]))
+            if c2 > th[st[i]]:
+                is_out[i], level[i] = True, 1
+                n_bad += 1
+            else:
+                is_out[i], level[i] = False, 0
+        if rnd == 2:
+            robust = False
+        if len(idx) < 10:
+            break
+    for i in idx:
+        outl[i] = is_out[i]
+    return len(idx) - n_bad, R, t, outl

@@ -62,6 +62,29 @@ def test_gmm_file_roundtrip_through_the_abi(gpu, oracle, golden_maps, tmp_path):
         assert len(raw) == gm["nbytes"] and hashlib.sha256(raw).hexdigest() == gm["sha256"]
 
 
+# ---------------------------------------------------------------- neighbour lists (a2)
+@pytest.mark.parametrize("name", ["v1", "synthetic"])
+def test_bhattacharyya_neighbour_lists(gpu, oracle, golden_maps, name):
+    g, _ = gpu
+    if name == "synthetic":
+        mean, cov = synth.make_map(1500, 0.5, seed=13)
+        mean = mean * 0.3  # denser map => more neighbours
+    else:
+        mean, cov = golden_maps[name]["mean"], golden_maps[name]["cov"]
+    m = g.GMM(mean, cov)
+    comps = oracle.map_build(mean, cov)
+    thr = 2.5  # map/neighbor_dist_thresh, v1.yaml:27
+    row_ptr, col, dist = m.neighbors(thr)
+    rp, c, d = oracle.neighbors(comps, thr)
+    assert len(col) > len(mean)  # the lists are not trivially empty
+    # membership and order are integer outputs: identical (a flip needs |BH - thresh| < 1 ulp of log())
+    assert np.array_equal(row_ptr, rp) and np.array_equal(col, c)
+    np.testing.assert_allclose(dist, d, rtol=1e-13, atol=1e-13)  # device log() vs glibc log(): <= 1-2 ulp
+    # empty result protocol
+    rp0, c0, d0 = m.neighbors(-1e9)
+    assert rp0[-1] == 0 and c0.size == 0
+
+
 # ---------------------------------------------------------------- association (a3, a4)
 def _check_assoc(g, ctx, oracle, mean, cov, pts, gate=0.0):
     m = g.GMM(mean, cov)
@@ -309,6 +332,49 @@ def test_frames_solve_pipelined_host_path_equals_single_chunks(gpu):
         part = ctx.frames_solve(m, fr["pose0"][lo:hi], fr["pts_w"][lo:hi], fr["obs"][lo:hi], fr["octave"][lo:hi])
         for k in ("pose", "pts", "assign", "outlier", "status"):
             assert np.array_equal(big[k][lo:hi], part[k]), (k, lo)
+
+
+# ---------------------------------------------------------------- pose-only LM (a11 / f1)
+def test_optimize_current_pose_lm(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(3000, 0.5, seed=31)
+    B, N = 12, 1200  # v1.yaml:24 feature count
+    fr = synth.make_tracking_frames(mean, cov, B, N, seed=31)
+    valid = np.ones((B, N), np.uint8)
+    valid[:, ::7] = 0
+    valid[3] = 0
+    valid[3, :2] = 1   # < 3 correspondences
+    valid[4] = 0
+    valid[4, :9] = 1   # < 10 edges: single round
+    out = ctx.optimizeCurrentPose(fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], valid)
+    worst = (0.0, 0.0)
+    for f in range(B):
+        n, pose, outl = oracle.optimize_pose_lm(fr["pose0"][f], fr["pts_w"][f], fr["obs"][f], fr["octave"][f], valid[f])
+        assert out["inliers"][f] == n, f
+        assert np.array_equal(out["outlier"][f], outl), f
+        ang, dt = _pose_err(out["pose"][f], pose)
+        worst = (max(worst[0], ang), max(worst[1], dt))
+    assert worst[0] < TOL_RAD and worst[1] < TOL_M, worst
+    assert out["inliers"][3] == 0 and np.array_equal(out["pose"][3], fr["pose0"][3])
+    # the solve pulls the perturbed poses back to the ground truth
+    d0 = np.abs(fr["pose0"][0][4:] - fr["pose_gt"][0][4:]).max()
+    d1 = np.abs(out["pose"][0][4:] - fr["pose_gt"][0][4:]).max()
+    assert d1 < 0.2 * d0
+    # valid == NULL means every feature has a map point
+    out2 = ctx.optimizeCurrentPose(fr["pose0"][:2], fr["pts_w"][:2], fr["obs"][:2], fr["octave"][:2])
+    n, pose, outl = oracle.optimize_pose_lm(fr["pose0"][1], fr["pts_w"][1], fr["obs"][1], fr["octave"][1])
+    assert out2["inliers"][1] == n and np.array_equal(out2["outlier"][1], outl)
+
+
+def test_optimize_current_pose_lm_large_n(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(800, 0.5, seed=32)
+    fr = synth.make_tracking_frames(mean, cov, 1, 25000, seed=32)  # beyond the shared-memory limit
+    out = ctx.optimizeCurrentPose(fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
+    n, pose, outl = oracle.optimize_pose_lm(fr["pose0"][0], fr["pts_w"][0], fr["obs"][0], fr["octave"][0])
+    assert out["inliers"][0] == n and np.array_equal(out["outlier"][0], outl)
+    ang, dt = _pose_err(out["pose"][0], pose)
+    assert ang < TOL_RAD and dt < TOL_M
 
 
 def test_frames_solve_deterministic(gpu):

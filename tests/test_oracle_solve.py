@@ -126,3 +126,35 @@ def test_batched_driver_equals_single_calls(oracle, small_scene):
         r = oracle.frame_solve(comps, fr["pose0"][f], fr["pts_w"][f], fr["obs"][f], fr["octave"][f])
         assert np.array_equal(rb["pose"][f], r["pose"]) and np.array_equal(rb["assign"][f], r["assign"])
         assert np.array_equal(rb["pts"][f], r["pts"]) and np.array_equal(rb["outlier"][f], r["outlier"])
+
+
+def test_optimize_pose_lm_vs_independent_numpy(oracle):
+    """f1: the 4-round Levenberg-Marquardt of Tracking::optimizeCurrentPose (oracle) against an independent
+    NumPy restatement; poses agree to 1e-8, inlier sets exactly; the solve really recovers the GT pose."""
+    mean, cov = synth.make_map(1500, 0.5, seed=21)
+    fr = synth.make_tracking_frames(mean, cov, 3, 120, seed=21)
+    for f in range(3):
+        valid = np.ones(120, np.uint8)
+        valid[::11] = 0
+        n, pose, outl = oracle.optimize_pose_lm(fr["pose0"][f], fr["pts_w"][f], fr["obs"][f], fr["octave"][f], valid)
+        n2, R, t, o2 = ref.optimize_pose_lm(fr["pose0"][f], fr["pts_w"][f], fr["obs"][f], fr["octave"][f], valid)
+        assert n == n2 and np.array_equal(outl, o2)
+        assert ref.rot_angle(R, synth.quat_to_rot(pose[:4])) < 1e-8
+        np.testing.assert_allclose(pose[4:], t, atol=1e-8)
+        assert not outl[::11].any() and 0 < outl.sum() < 60  # gross outliers found, unmatched features untouched
+        d0 = np.abs(fr["pose0"][f][4:] - fr["pose_gt"][f][4:]).max()
+        d1 = np.abs(pose[4:] - fr["pose_gt"][f][4:]).max()
+        assert d1 < 0.2 * d0
+
+
+def test_optimize_pose_lm_degenerate_inputs(oracle):
+    mean, cov = synth.make_map(500, 0.5, seed=22)
+    fr = synth.make_tracking_frames(mean, cov, 1, 40, seed=22)
+    valid = np.zeros(40, np.uint8)
+    valid[:2] = 1  # fewer than 3 correspondences: returns 0, pose untouched (tracking_opt.cpp:139-140)
+    n, pose, outl = oracle.optimize_pose_lm(fr["pose0"][0], fr["pts_w"][0], fr["obs"][0], fr["octave"][0], valid)
+    assert n == 0 and np.array_equal(pose, fr["pose0"][0]) and not outl.any()
+    valid[:8] = 1  # fewer than 10 edges: a single round (tracking_opt.cpp:205-206)
+    n, pose, outl = oracle.optimize_pose_lm(fr["pose0"][0], fr["pts_w"][0], fr["obs"][0], fr["octave"][0], valid)
+    n2, R, t, o2 = ref.optimize_pose_lm(fr["pose0"][0], fr["pts_w"][0], fr["obs"][0], fr["octave"][0], valid)
+    assert n == n2 and np.array_equal(outl, o2) and ref.rot_angle(R, synth.quat_to_rot(pose[:4])) < 1e-8
