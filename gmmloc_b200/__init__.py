@@ -234,6 +234,50 @@ class Context:
                                                   _ptr(pt_est), _ptr(c2p), _ptr(c2s), _ptr(res)))
         return dict(res=res.astype(bool), chi2_proj=c2p, chi2_str=c2s, pt_est=pt_est)
 
+    def optimizeTriangulation(self, gmm: GMM, x0, obs1, obs2, octave1, pose1, pose2, comp, cam: Camera | None = None,
+                              params: Params | None = None, iters: int = 20) -> dict:
+        """Batched candidate solves of Localization::optimizeTriangulationVec (localization_opt.cpp:27-204):
+        one problem per (match, candidate component)."""
+        cam = cam or v1_camera()
+        params = params or default_params()
+        x0 = _in(x0, np.float64, (-1, 3))
+        M = x0.shape[0]
+        obs1 = _in(obs1, np.float32, (M, 3))
+        obs2 = _in(obs2, np.float32, (M, 3))
+        octave1 = _in(octave1, np.uint8, (M,))
+        pose1 = _in(np.broadcast_to(np.asarray(pose1, np.float64).reshape(-1, 7), (M, 7)), np.float64)
+        pose2 = _in(np.broadcast_to(np.asarray(pose2, np.float64).reshape(-1, 7), (M, 7)), np.float64)
+        comp = _in(comp, np.int32, (M,))
+        pt_est = np.empty((M, 3))
+        e1, e2, cs = np.empty(M), np.empty(M), np.empty(M)
+        res = np.empty(M, np.uint8)
+        capi.check(capi.lib().gmmloc_triangulation_solve(self._h, gmm._h, C.byref(cam), C.byref(params), _ptr(x0), _ptr(obs1),
+                                                         _ptr(obs2), _ptr(octave1), _ptr(pose1), _ptr(pose2), _ptr(comp), M,
+                                                         int(iters), _ptr(pt_est), _ptr(e1), _ptr(e2), _ptr(cs), _ptr(res)))
+        return dict(res=res.astype(bool), err1=e1, err2=e2, chi2_str=cs, pt_est=pt_est)
+
+    def optimizeTriangulationVec(self, gmm: GMM, x3d, obs1, obs2, octave1, pose1, pose2, candidates, is_degenerated,
+                                 **kw):
+        """Localization::optimizeTriangulationVec for one match: tries every DEGENERATE candidate component
+        (ascending index; the reference iterates an unordered_set, SURVEY Appx A9), keeps the accepted one with
+        the smallest err1 + err2 (strict '<').  Returns (component index or -1, point)."""
+        cand = sorted({int(c) for c in candidates if c >= 0 and is_degenerated[int(c)]})
+        x3d = np.asarray(x3d, np.float64)
+        if not cand:
+            return -1, x3d
+        M = len(cand)
+        r = self.optimizeTriangulation(gmm, np.tile(x3d, (M, 1)), np.tile(np.asarray(obs1, np.float32), (M, 1)),
+                                       np.tile(np.asarray(obs2, np.float32), (M, 1)), np.full(M, octave1, np.uint8), pose1,
+                                       pose2, np.asarray(cand, np.int32), **kw)
+        best, best_v = -1, np.finfo(np.float64).max
+        for j in range(M):
+            s = r["err1"][j] + r["err2"][j]
+            if r["res"][j] and s < best_v:
+                best, best_v = j, s
+        if best < 0:
+            return -1, x3d
+        return cand[best], r["pt_est"][best]
+
     # ---- device entry points (raw device pointers, enqueue only) ----
     def associate_async(self, gmm: GMM, d_pts: int, M: int, gate: float, d_assign: int, d_d2: int = 0) -> None:
         capi.check(capi.lib().gmmloc_associate_async(self._h, gmm._h, d_pts, int(M), float(gate), d_assign, d_d2 or None))

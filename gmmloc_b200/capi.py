@@ -70,6 +70,7 @@ SYMBOLS = {
     "gmmloc_frames_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i] + [_vp] * 5),
     "gmmloc_frames_solve_async": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i] + [_vp] * 5),
     "gmmloc_poses_optimize": (_i, [_vp, C.POINTER(Camera)] + [_vp] * 5 + [_i, _i] + [_vp] * 3),
+    "gmmloc_triangulation_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 7 + [_i, _i] + [_vp] * 5),
     "gmmloc_points_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 6 + [_i, _i] + [_vp] * 4),
 }
 

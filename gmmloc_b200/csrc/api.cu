@@ -850,4 +850,65 @@ gmmloc_status_t gmmloc_points_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   return GMMLOC_OK;
 }
 
+// ---- batched triangulation solves -----------------------------------------------------------------
+gmmloc_status_t gmmloc_triangulation_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                           const gmmloc_params_t* params, const double* x0, const float* obs1, const float* obs2,
+                                           const uint8_t* octave1, const double* pose1, const double* pose2, const int32_t* comp,
+                                           int M, int iters, double* pt_est, double* err1, double* err2, double* chi2_str,
+                                           uint8_t* res) {
+  if (!ctx || !map || !cam || !params || M < 0 || iters < 0) return fail(GMMLOC_EINVAL, "gmmloc_triangulation_solve: bad argument");
+  if (M == 0) return GMMLOC_OK;
+  if (!x0 || !obs1 || !obs2 || !octave1 || !pose1 || !pose2 || !comp || !pt_est || !err1 || !err2 || !chi2_str || !res)
+    return fail(GMMLOC_EINVAL, "gmmloc_triangulation_solve: null pointer");
+  if (map->device != ctx->device) return fail(GMMLOC_EINVAL, "map and context live on different devices");
+  CU(cudaSetDevice(ctx->device));
+  ctx->active = 0;
+  const size_t m = (size_t)M;
+  // input slab: x0 (24) | pose1 (56) | pose2 (56) | obs1 (12) | obs2 (12) | comp (4) | octave1 (1)
+  const size_t o_x0 = 0, o_p1 = 24 * m, o_p2 = o_p1 + 56 * m, o_o1 = o_p2 + 56 * m, o_o2 = o_o1 + 12 * m, o_c = o_o2 + 12 * m,
+               o_oc = o_c + 4 * m, in_bytes = o_oc + m;
+  // output slab: pt_est (24) | err1 (8) | err2 (8) | chi2_str (8) | res (1)
+  const size_t q_pt = 0, q_e1 = 24 * m, q_e2 = q_e1 + 8 * m, q_cs = q_e2 + 8 * m, q_r = q_cs + 8 * m, out_bytes = q_r + m;
+  CU(ctx->in_misc.reserve(in_bytes));
+  CU(ctx->out_misc.reserve(out_bytes));
+  char* in = ctx->in_misc.as<char>();
+  char* outp = ctx->out_misc.as<char>();
+  cudaStream_t st = ctx->L().stream;
+  CU(cudaMemcpyAsync(in + o_x0, x0, 24 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_p1, pose1, 56 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_p2, pose2, 56 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_o1, obs1, 12 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_o2, obs2, 12 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_c, comp, 4 * m, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(in + o_oc, octave1, m, cudaMemcpyHostToDevice, st));
+  TriArgs a;
+  a.mean = map->d.mean;
+  a.axis = map->d.axis;
+  fill_params(cam, params, a.prm);
+  a.x0 = reinterpret_cast<const double*>(in + o_x0);
+  a.pose1 = reinterpret_cast<const double*>(in + o_p1);
+  a.pose2 = reinterpret_cast<const double*>(in + o_p2);
+  a.obs1 = reinterpret_cast<const float*>(in + o_o1);
+  a.obs2 = reinterpret_cast<const float*>(in + o_o2);
+  a.comp = reinterpret_cast<const int32_t*>(in + o_c);
+  a.octave1 = reinterpret_cast<const uint8_t*>(in + o_oc);
+  a.M = M;
+  a.iters = iters;
+  a.K = map->d.K;
+  a.pt_est = reinterpret_cast<double*>(outp + q_pt);
+  a.err1 = reinterpret_cast<double*>(outp + q_e1);
+  a.err2 = reinterpret_cast<double*>(outp + q_e2);
+  a.chi2_str = reinterpret_cast<double*>(outp + q_cs);
+  a.res = reinterpret_cast<uint8_t*>(outp + q_r);
+  CU(launch_tri_gn(a, st));
+  ctx->stats.kernel_launches += 1;
+  CU(cudaMemcpyAsync(pt_est, outp + q_pt, 24 * m, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(err1, outp + q_e1, 8 * m, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(err2, outp + q_e2, 8 * m, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(chi2_str, outp + q_cs, 8 * m, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(res, outp + q_r, m, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return GMMLOC_OK;
+}
+
 }  // extern "C"

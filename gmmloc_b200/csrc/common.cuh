@@ -115,6 +115,26 @@ struct PointArgs {
 };
 cudaError_t launch_point_gn(const PointArgs& a, cudaStream_t stream);
 
+struct TriArgs {
+  const double* mean;
+  const double* axis;
+  FrameParamsDev prm;
+  const double* x0;        // M x 3
+  const float* obs1;       // M x 3
+  const float* obs2;       // M x 3
+  const uint8_t* octave1;  // M
+  const double* pose1;     // M x 7
+  const double* pose2;     // M x 7
+  const int32_t* comp;     // M
+  int M, iters, K;
+  double* pt_est;          // M x 3
+  double* err1;            // M
+  double* err2;            // M
+  double* chi2_str;        // M
+  uint8_t* res;            // M
+};
+cudaError_t launch_tri_gn(const TriArgs& a, cudaStream_t stream);
+
 // ---- exact (non-contracted) fp64 helpers: the re-rank and the map build must replay the CPU
 // oracle's operation order bit for bit, so every product and sum is an explicit IEEE rn op. ----
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }

@@ -220,3 +220,47 @@ def make_tracking_frames(mean, cov, B: int, N: int, seed: int = 0, mono_frac: fl
         pose0[f, :4] = rot_to_quat(dR @ R)
         pose0[f, 4:] = dR @ t + dt
     return dict(pose0=pose0, pts_w=pts.astype(np.float32), obs=obs, octave=fr["octave"], pose_gt=fr["pose_gt"])
+
+
+def make_triangulation_problems(mean, cov, M: int, seed: int = 0, mono_frac: float = 0.5):
+    """M two-view problems for Localization::optimizeTriangulationVec: a true point on a planar component,
+    seen from a keyframe pair ~20 cm apart; view 1 / view 2 stereo or mono; x0 = true point + 3 cm noise.
+    Returns dict(x0 Mx3 f64, obs1/obs2 Mx3 f32, octave1 M u8, pose1/pose2 Mx7, comp M i32 (generating comp))."""
+    mean = np.asarray(mean, np.float64).reshape(-1, 3)
+    cov = np.asarray(cov, np.float64).reshape(-1, 3, 3)
+    rng = _rng(5, seed)
+    w_, _v = np.linalg.eigh(cov)
+    planar = np.flatnonzero(w_[:, 0] < 1e-4)
+    Lc = np.linalg.cholesky(cov)
+    out = dict(x0=np.empty((M, 3)), obs1=np.empty((M, 3), np.float32), obs2=np.empty((M, 3), np.float32),
+               octave1=np.empty(M, np.uint8), pose1=np.empty((M, 7)), pose2=np.empty((M, 7)), comp=np.empty(M, np.int32))
+    i = 0
+    while i < M:
+        R_wc, t_wc = _sample_pose(rng)
+        R1 = R_wc.T
+        t1 = -R1 @ t_wc
+        dR, dt = _se3_exp(np.concatenate([rng.normal(size=3) * np.deg2rad(3.0), rng.normal(size=3) * 0.15]))
+        R2, t2 = dR @ R1, dR @ t1 + dt
+        mc = mean[planar] @ R1.T + t1
+        vis = planar[(mc[:, 2] > Z_NEAR) & (mc[:, 2] < Z_FAR) & (np.abs(mc[:, 0] / mc[:, 2]) < 0.7) & (np.abs(mc[:, 1] / mc[:, 2]) < 0.45)]
+        if vis.size == 0:
+            continue
+        for k in vis[rng.integers(0, vis.size, min(8, M - i))]:
+            x = mean[k] + Lc[k] @ rng.normal(size=3)
+            oc = int(rng.integers(0, 8))
+            sig = 1.2 ** oc
+            obs = []
+            for (R, t) in ((R1, t1), (R2, t2)):
+                pc = R @ x + t
+                u = FX * pc[0] / pc[2] + CX + rng.normal() * sig
+                v = FY * pc[1] / pc[2] + CY + rng.normal() * sig
+                ur = u - BF / pc[2] + rng.normal() * 0.25 if rng.random() >= mono_frac else -1.0
+                obs.append((u, v, ur))
+            out["x0"][i] = x + rng.normal(size=3) * 0.03
+            out["obs1"][i], out["obs2"][i] = obs
+            out["octave1"][i] = oc
+            out["pose1"][i, :4], out["pose1"][i, 4:] = rot_to_quat(R1), t1
+            out["pose2"][i, :4], out["pose2"][i, 4:] = rot_to_quat(R2), t2
+            out["comp"][i] = k
+            i += 1
+    return out

@@ -189,6 +189,22 @@ GMMLOC_API gmmloc_status_t gmmloc_points_solve(gmmloc_ctx_t* ctx, const gmmloc_m
                                     const double* proj_z2, int M, int iters, double* pt_est, double* chi2_proj,
                                     double* chi2_str, uint8_t* res);
 
+/* ---- batched two-view triangulation solves: replaces the per-candidate body of
+ * Localization::optimizeTriangulationVec (localization_opt.cpp:27-204): M independent 3-DoF GN problems, two
+ * view edges (u_r >= 0: stereo 3-D, factors.cpp:116-168; else mono 2-D, factors.cpp:70-107; both weighted
+ * with sigma2_inv[octave1], :126-135) + one point-to-plane edge (information tri_lambda2), `iters` (20).
+ *  x0 M x 3 (fp64), obs1 / obs2 M x 3 (u v u_r), octave1 M, pose1 / pose2 M x 7 (T_cw of the two
+ *  keyframes), comp M (candidate component index; the reference only tries degenerate components).
+ *  outputs: pt_est M x 3, err1 / err2 / chi2_str M (chi2 of the three edges), res M (1 = accepted:
+ *  chi2_str <= tri_str_thresh * tri_lambda2 and err <= 7.8 (stereo view) / 5.991 (mono view)).
+ *  The caller keeps, per match, the accepted candidate with the smallest err1 + err2 (:189-195). */
+GMMLOC_API gmmloc_status_t gmmloc_triangulation_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                                      const gmmloc_params_t* params, const double* x0, const float* obs1,
+                                                      const float* obs2, const uint8_t* octave1, const double* pose1,
+                                                      const double* pose2, const int32_t* comp, int M, int iters,
+                                                      double* pt_est, double* err1, double* err2, double* chi2_str,
+                                                      uint8_t* res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -525,6 +525,66 @@ int oracle_optimize_point(const double x0[3], const double obs[3], int octave, c
   return res;
 }
 
+int oracle_optimize_triangulation(const double x0[3], const double obs1[3], const double obs2[3], int octave1,
+                                  const double pose1[7], const double pose2[7], const oracle_comp_t* comp,
+                                  const oracle_camera_t* camp, const oracle_params_t* prm, int iters, double pt_est[3],
+                                  double* err1, double* err2, double* chi2_str) {
+  // localization_opt.cpp:27-204, one candidate component
+  const Cam cam{camp->fx, camp->fy, camp->cx, camp->cy, camp->bf};
+  const double* poses[2] = {pose1, pose2};
+  const double* obs[2] = {obs1, obs2};
+  double R[2][9];
+  bool stereo[2];
+  for (int v = 0; v < 2; ++v) {
+    double q[4] = {poses[v][0], poses[v][1], poses[v][2], poses[v][3]};
+    quat_normalize(q);
+    quat_to_rot(q, R[v]);
+    stereo[v] = obs[v][2] >= 0.0;  // kp.depth > 0  <=>  a right-image match exists
+  }
+  const double w = oracle_sigma2_inv(octave1);  // sigma2_inv1 for BOTH views (:126-135)
+  const double w_str = prm->tri_lambda2;        // :106-107
+  const double n[3] = {comp->axis[0], comp->axis[3], comp->axis[6]};
+  double x[3] = {x0[0], x0[1], x0[2]};
+  double c2v[2] = {0, 0}, c2s = 0;
+  bool ok = true;
+  for (int it = 0; it < iters; ++it) {
+    double e[2][3], Jl[2][9];
+    for (int v = 0; v < 2; ++v) {
+      double pc[3];
+      mat3_vec(R[v], x, pc);
+      for (int i = 0; i < 3; ++i) pc[i] += poses[v][4 + i];
+      reproj_edge(cam, R[v], pc, obs[v], stereo[v], e[v], Jl[v], nullptr);
+      c2v[v] = w * ((e[v][0] * e[v][0] + e[v][1] * e[v][1]) + e[v][2] * e[v][2]);
+    }
+    const double es = (n[0] * (x[0] - comp->mean[0]) + n[1] * (x[1] - comp->mean[1])) + n[2] * (x[2] - comp->mean[2]);
+    c2s = w_str * (es * es);
+    double H[9], b[3];
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) {
+        const double h1 = (Jl[0][r] * Jl[0][c] + Jl[0][3 + r] * Jl[0][3 + c]) + Jl[0][6 + r] * Jl[0][6 + c];
+        const double h2 = (Jl[1][r] * Jl[1][c] + Jl[1][3 + r] * Jl[1][3 + c]) + Jl[1][6 + r] * Jl[1][6 + c];
+        M(H, r, c) = (w * h1 + w * h2) + w_str * (n[r] * n[c]);
+      }
+      const double g1 = (Jl[0][r] * e[0][0] + Jl[0][3 + r] * e[0][1]) + Jl[0][6 + r] * e[0][2];
+      const double g2 = (Jl[1][r] * e[1][0] + Jl[1][3 + r] * e[1][1]) + Jl[1][6 + r] * e[1][2];
+      b[r] = -((w * g1 + w * g2) + w_str * (n[r] * es));
+    }
+    double Hi[9], dx[3];
+    if (!inverse3(H, Hi)) { ok = false; break; }
+    mat3_vec(Hi, b, dx);
+    for (int i = 0; i < 3; ++i) x[i] += dx[i];
+  }
+  for (int i = 0; i < 3; ++i) pt_est[i] = x[i];
+  *err1 = c2v[0];
+  *err2 = c2v[1];
+  *chi2_str = c2s;
+  int res = ok ? 1 : 0;
+  if (prm->tri_check_str_chi2 && c2s > prm->tri_str_thresh * prm->tri_lambda2) res = 0;  // :176-179
+  const double th1 = stereo[0] ? 7.8 : 5.991, th2 = stereo[1] ? 7.8 : 5.991;             // :118,127,133
+  if (c2v[0] > th1 || c2v[1] > th2) res = 0;                                             // :184-186
+  return res;
+}
+
 void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t* camp,
                         const oracle_params_t* prm, const double pose0[7], const float* pts_w,
                         const float* obsf, const uint8_t* octave, int N, const int32_t* assign_in,

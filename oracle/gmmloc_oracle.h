@@ -84,6 +84,17 @@ int oracle_optimize_point(const double x0[3], const double obs[3], int octave, c
                           const oracle_params_t* prm, int iters, double pt_est[3], double* chi2_proj,
                           double* chi2_str);
 
+/* A9: one candidate of Localization::optimizeTriangulationVec (localization_opt.cpp:27-204): 3-DoF GN,
+ * `iters` (20, :169) iterations from x0, two view edges (stereo 3-D when u_r >= 0, factors.cpp:116-168, else
+ * mono 2-D, factors.cpp:70-107), BOTH weighted with sigma2_inv[octave of view 1] (:126-135), plus one
+ * point-to-plane edge with information tri_lambda2 (:106-107).  Outputs the estimate, err1 / err2 / chi2_str at
+ * the last linearisation point; res = !(tri_check_str_chi2 && chi2_str > tri_str_thresh * tri_lambda2) &&
+ * !(err1 > th1 || err2 > th2), th = 7.8 for a stereo view, 5.991 for a mono view (:118,127,133,176-186). */
+int oracle_optimize_triangulation(const double x0[3], const double obs1[3], const double obs2[3], int octave1,
+                                  const double pose1[7], const double pose2[7], const oracle_comp_t* comp,
+                                  const oracle_camera_t* cam, const oracle_params_t* prm, int iters, double pt_est[3],
+                                  double* err1, double* err2, double* chi2_str);
+
 /* A11: the frame solve = single-free-pose specialisation of Localization::jointOptimization
  * (localization_opt.cpp:456-925) run with Gauss-Newton; association by oracle_associate at
  * iteration 0, structure-edge gates fixed at iteration 0.

@@ -82,6 +82,7 @@ def lib():
         L.oracle_neighbors.restype = C.c_int64
         L.oracle_optimize_point.restype = C.c_int
         L.oracle_optimize_pose_lm.restype = C.c_int
+        L.oracle_optimize_triangulation.restype = C.c_int
         L.oracle_gmm_read.restype = C.c_int
         L.oracle_gmm_write.restype = C.c_int
         _lib = L
@@ -205,6 +206,19 @@ def frames_solve(comps, pose0, pts_w, obs, octave, cam=None, prm=None, nthreads=
                               _p(obs), _p(octave), C.c_int(B), C.c_int(N), _p(pose_out), _p(pts_out), _p(assign),
                               _p(outlier), _p(status), C.c_int(nthreads))
     return dict(pose=pose_out, pts=pts_out, assign=assign, outlier=outlier, status=status)
+
+
+def optimize_triangulation(comps, k, x0, obs1, obs2, octave1, pose1, pose2, cam=None, prm=None, iters=20):
+    """One candidate of Localization::optimizeTriangulationVec: (res, pt_est, err1, err2, chi2_str)."""
+    cam = cam or v1_camera()
+    prm = prm or default_params()
+    a = [np.ascontiguousarray(v, np.float64) for v in (x0, obs1, obs2, pose1, pose2)]
+    est = np.zeros(3)
+    e1, e2, cs = C.c_double(), C.c_double(), C.c_double()
+    res = lib().oracle_optimize_triangulation(_p(a[0]), _p(a[1]), _p(a[2]), C.c_int(int(octave1)), _p(a[3]), _p(a[4]),
+                                              C.c_void_p(comps.ctypes.data + int(k) * COMP_DTYPE.itemsize), C.byref(cam),
+                                              C.byref(prm), C.c_int(iters), _p(est), C.byref(e1), C.byref(e2), C.byref(cs))
+    return bool(res), est, e1.value, e2.value, cs.value
 
 
 def optimize_pose_lm(pose0, pts_w, obs, octave, valid=None, cam=None):

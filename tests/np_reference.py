@@ -254,3 +254,27 @@ def optimize_pose_lm(pose0, pts_w, obs, octave, valid=None):
     for i in idx:
         outl[i] = is_out[i]
     return len(idx) - n_bad, R, t, outl
+
+
+def optimize_triangulation(x0, obs1, obs2, octave1, R1, t1, R2, t2, mu, n, w_str=400.0, iters=20):
+    """Independent restatement of one optimizeTriangulationVec candidate (localization_opt.cpp:27-204)."""
+    x = np.array(x0, float)
+    w = s2inv(octave1)
+    views = [(R1, t1, np.asarray(obs1, float)), (R2, t2, np.asarray(obs2, float))]
+    errs = [0.0, 0.0]
+    for _ in range(iters):
+        H = w_str * np.outer(n, n)
+        es = n @ (x - mu)
+        b = -w_str * n * es
+        for v, (R, t, ob) in enumerate(views):
+            st = ob[2] >= 0
+            m = 3 if st else 2
+            pc = R @ x + t
+            e = ob[:m] - project(pc, st)
+            J = -dproj(pc, st) @ R
+            errs[v] = w * e @ e
+            H = H + w * J.T @ J
+            b = b - w * J.T @ e
+        c2s = w_str * es * es
+        x = x + np.linalg.solve(H, b)
+    return x, errs[0], errs[1], c2s

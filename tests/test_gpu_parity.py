@@ -334,6 +334,45 @@ def test_frames_solve_pipelined_host_path_equals_single_chunks(gpu):
             assert np.array_equal(big[k][lo:hi], part[k]), (k, lo)
 
 
+# ---------------------------------------------------------------- triangulation solves (a10)
+def test_optimize_triangulation_bit_exact(gpu, oracle, golden_maps):
+    g, ctx = gpu
+    gm = golden_maps["v2"]
+    m = g.GMM(gm["mean"], gm["cov"])
+    comps = oracle.map_build(gm["mean"], gm["cov"])
+    pr = synth.make_triangulation_problems(gm["mean"], gm["cov"], 400, seed=42)
+    comp = pr["comp"].copy()
+    comp[7] = -1
+    out = ctx.optimizeTriangulation(m, pr["x0"], pr["obs1"], pr["obs2"], pr["octave1"], pr["pose1"], pr["pose2"], comp)
+    n_ok = 0
+    for i in range(400):
+        if comp[i] < 0:
+            assert not out["res"][i] and np.array_equal(out["pt_est"][i], pr["x0"][i])
+            continue
+        res, est, e1, e2, cs = oracle.optimize_triangulation(comps, comp[i], pr["x0"][i], pr["obs1"][i], pr["obs2"][i],
+                                                             pr["octave1"][i], pr["pose1"][i], pr["pose2"][i])
+        assert np.array_equal(_bits(out["pt_est"][i]), _bits(est)), i
+        assert out["err1"][i] == e1 and out["err2"][i] == e2 and out["chi2_str"][i] == cs
+        assert bool(out["res"][i]) == res
+        n_ok += res
+    assert n_ok > 100
+    # candidate selection of optimizeTriangulationVec: degenerate candidates only, min err1 + err2
+    deg = comps["is_degenerated"] != 0
+    for i in (0, 11, 23):
+        cands = [int(pr["comp"][i]), 5, 17, 1234, int(np.flatnonzero(~deg)[0])]
+        k, x = ctx.optimizeTriangulationVec(m, pr["x0"][i], pr["obs1"][i], pr["obs2"][i], pr["octave1"][i], pr["pose1"][i],
+                                            pr["pose2"][i], cands, deg)
+        best, best_v, best_x = -1, np.finfo(np.float64).max, pr["x0"][i]
+        for c in sorted(set(cands)):
+            if not deg[c]:
+                continue
+            res, est, e1, e2, cs = oracle.optimize_triangulation(comps, c, pr["x0"][i], pr["obs1"][i], pr["obs2"][i],
+                                                                 pr["octave1"][i], pr["pose1"][i], pr["pose2"][i])
+            if res and e1 + e2 < best_v:
+                best, best_v, best_x = c, e1 + e2, est
+        assert k == best and np.array_equal(x, best_x)
+
+
 # ---------------------------------------------------------------- pose-only LM (a11 / f1)
 def test_optimize_current_pose_lm(gpu, oracle):
     g, ctx = gpu

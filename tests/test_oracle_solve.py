@@ -158,3 +158,26 @@ def test_optimize_pose_lm_degenerate_inputs(oracle):
     n, pose, outl = oracle.optimize_pose_lm(fr["pose0"][0], fr["pts_w"][0], fr["obs"][0], fr["octave"][0], valid)
     n2, R, t, o2 = ref.optimize_pose_lm(fr["pose0"][0], fr["pts_w"][0], fr["obs"][0], fr["octave"][0], valid)
     assert n == n2 and np.array_equal(outl, o2) and ref.rot_angle(R, synth.quat_to_rot(pose[:4])) < 1e-8
+
+
+def test_optimize_triangulation_vs_numpy(oracle):
+    mean, cov = synth.make_map(1500, 0.7, seed=41)
+    comps = oracle.map_build(mean, cov)
+    pr = synth.make_triangulation_problems(mean, cov, 60, seed=41)
+    n_ok = 0
+    for i in range(60):
+        k = pr["comp"][i]
+        res, est, e1, e2, cs = oracle.optimize_triangulation(comps, k, pr["x0"][i], pr["obs1"][i], pr["obs2"][i],
+                                                             pr["octave1"][i], pr["pose1"][i], pr["pose2"][i])
+        c = comps[k]
+        x, r1, r2, rs = ref.optimize_triangulation(pr["x0"][i], pr["obs1"][i].astype(np.float64), pr["obs2"][i].astype(np.float64),
+                                                   pr["octave1"][i], synth.quat_to_rot(pr["pose1"][i][:4]), pr["pose1"][i][4:],
+                                                   synth.quat_to_rot(pr["pose2"][i][:4]), pr["pose2"][i][4:], c["mean"],
+                                                   c["axis"].reshape(3, 3)[:, 0])
+        np.testing.assert_allclose(est, x, atol=1e-8)
+        np.testing.assert_allclose([e1, e2, cs], [r1, r2, rs], rtol=1e-6, atol=1e-9)
+        th1 = 7.8 if pr["obs1"][i][2] >= 0 else 5.991
+        th2 = 7.8 if pr["obs2"][i][2] >= 0 else 5.991
+        assert res == (not rs > float(np.float32(0.0064)) * 400.0 and not (r1 > th1 or r2 > th2))
+        n_ok += res
+    assert n_ok > 20
