@@ -105,6 +105,12 @@ class GMM:
                                                        C.byref(n)))
         return row_ptr, col, dist
 
+    def buildNeighbors(self, thresh: float = 2.5) -> int:
+        """Builds nbs_ once and keeps it on the device (needed by checkMapAssociation); returns the pair count."""
+        n = C.c_int64(0)
+        capi.check(capi.lib().gmmloc_map_build_neighbors(self._h, float(thresh), C.byref(n)))
+        return int(n.value)
+
     def scan_bound(self):
         a, x = C.c_double(), C.c_double()
         capi.check(capi.lib().gmmloc_map_scan_bound(self._h, C.byref(a), C.byref(x)))
@@ -277,6 +283,77 @@ class Context:
         if best < 0:
             return -1, x3d
         return cand[best], r["pt_est"][best]
+
+    # ---- keyframe association pipeline ----
+    def renderView(self, gmm: GMM, pose, cap: int | None = None, cam: Camera | None = None) -> dict:
+        """Batched GMM::renderView (gaussian_mixture.cpp:271-371): per view the depth-sorted 2-D components
+        (count B, ids / mean / cov / depth padded to cap).  The views stay on this context for
+        searchCorrespondence."""
+        cam = cam or v1_camera()
+        pose = _in(pose, np.float64, (-1, 7))
+        B = pose.shape[0]
+        cap = min(int(cap or len(gmm)), len(gmm))
+        out = dict(count=np.zeros(B, np.int32), status=np.zeros(B, np.int32), ids=np.full((B, cap), -1, np.int32),
+                   mean=np.zeros((B, cap, 2)), cov=np.zeros((B, cap, 4)), depth=np.zeros((B, cap)))
+        capi.check(capi.lib().gmmloc_render_views(self._h, gmm._h, C.byref(cam), _ptr(pose), B, cap, _ptr(out["count"]),
+                                                  _ptr(out["status"]), _ptr(out["ids"]), _ptr(out["mean"]), _ptr(out["cov"]),
+                                                  _ptr(out["depth"])))
+        for b in range(B):
+            out["ids"][b, out["count"][b]:] = -1
+        return out
+
+    def searchCorrespondence(self, obs, num: int = 5, want_pos: bool = False):
+        """Batched GMM::searchCorrespondence on the views last rendered here: cand B x N x num (component ids)."""
+        obs = _in(obs, np.float32)
+        if obs.ndim == 2:
+            obs = obs[None]
+        B, N = obs.shape[:2]
+        cand = np.empty((B, N, num), np.int32)
+        pos = np.empty((B, N, num), np.int32) if want_pos else None
+        capi.check(capi.lib().gmmloc_search_correspondence(self._h, _ptr(obs), B, N, int(num), _ptr(cand), _ptr(pos)))
+        return (cand, pos) if want_pos else cand
+
+    def checkMapAssociation(self, gmm: GMM, pose, obs, octave, cand, pt3d, cam: Camera | None = None,
+                            params: Params | None = None):
+        """Batched GMMLoc::checkMapAssociation: returns (assoc B x N, pt3d B x N x 3 after the call)."""
+        cam = cam or v1_camera()
+        params = params or default_params()
+        pose = _in(pose, np.float64, (-1, 7))
+        B = pose.shape[0]
+        obs = _in(obs, np.float32).reshape(B, -1, 3)
+        N = obs.shape[1]
+        octave = _in(octave, np.uint8, (B, N))
+        cand = _in(cand, np.int32).reshape(B, N, -1)
+        num = cand.shape[2]
+        pt = np.array(pt3d, np.float64).reshape(B, N, 3).copy()
+        assoc = np.empty((B, N), np.int32)
+        capi.check(capi.lib().gmmloc_check_map_association(self._h, gmm._h, C.byref(cam), C.byref(params), _ptr(pose),
+                                                           _ptr(obs), _ptr(octave), _ptr(cand), B, N, num, _ptr(pt),
+                                                           _ptr(assoc)))
+        return assoc, pt
+
+    def associateMapElements(self, gmm: GMM, pose, obs, depth, octave, num: int = 5, cap: int | None = None,
+                             cam: Camera | None = None, params: Params | None = None) -> dict:
+        """GMMLoc::associateMapElements + the per-feature association of createMapPointsFromStereo for B
+        keyframes, chained on the device (render -> search -> unproject3 -> checkMapAssociation)."""
+        cam = cam or v1_camera()
+        params = params or default_params()
+        pose = _in(pose, np.float64, (-1, 7))
+        B = pose.shape[0]
+        obs = _in(obs, np.float32)
+        if obs.ndim != 3:
+            obs = obs.reshape(B, -1, 3)
+        N = obs.shape[1]
+        depth = _in(depth, np.float32, (B, N))
+        octave = _in(octave, np.uint8, (B, N))
+        cap = min(int(cap or len(gmm)), len(gmm))
+        out = dict(assoc=np.empty((B, N), np.int32), pt3d=np.empty((B, N, 3)), cand=np.empty((B, N, num), np.int32),
+                   nview=np.empty(B, np.int32), vstatus=np.empty(B, np.int32))
+        capi.check(capi.lib().gmmloc_keyframes_associate(self._h, gmm._h, C.byref(cam), C.byref(params), _ptr(pose), _ptr(obs),
+                                                         _ptr(depth), _ptr(octave), B, N, int(num), cap, _ptr(out["assoc"]),
+                                                         _ptr(out["pt3d"]), _ptr(out["cand"]), _ptr(out["nview"]),
+                                                         _ptr(out["vstatus"])))
+        return out
 
     # ---- device entry points (raw device pointers, enqueue only) ----
     def associate_async(self, gmm: GMM, d_pts: int, M: int, gate: float, d_assign: int, d_d2: int = 0) -> None:

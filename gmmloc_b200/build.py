@@ -3,7 +3,7 @@
     python -m gmmloc_b200.build [--force] [--verbose]
 
 The library travels to the GPU box inside the repo snapshot (git-ignored, not gpurun-ignored).  nvcc
-cross-compiles sm_100a without a GPU.  point_gn.cu is compiled with -fmad=false (it replays the CPU
+cross-compiles sm_100a without a GPU.  point_gn.cu and view.cu are compiled with -fmad=false (they replay the CPU
 oracle's fp64 expression trees bit for bit); the other kernels use explicit intrinsics where exactness
 matters and free FMA contraction elsewhere.
 """
@@ -32,6 +32,7 @@ SOURCES = {
     "frame_gn.cu": [],
     "pose_lm.cu": [],
     "point_gn.cu": ["-fmad=false"],
+    "view.cu": ["-fmad=false"],
 }
 
 

@@ -14,6 +14,7 @@ LIB_PATH = PKG / "lib" / "libgmmloc_b200.so"
 OK, EINVAL, ENOMEM, ECUDA, ENUMERIC, EIO = range(6)
 MODE_JOINT, MODE_POSE_ONLY, MODE_POINTS_ONLY = 0, 1, 2
 FRAME_NUMERIC = 1
+VIEW_OVERFLOW = 1
 
 
 class Camera(C.Structure):
@@ -56,6 +57,7 @@ SYMBOLS = {
     "gmmloc_map_device": (_i, [_vp]),
     "gmmloc_map_get_components": (_i, [_vp] * 10),
     "gmmloc_map_neighbors": (_i, [_vp, _d, _vp, _vp, _vp, _i64, C.POINTER(_i64)]),
+    "gmmloc_map_build_neighbors": (_i, [_vp, _d, C.POINTER(_i64)]),
     "gmmloc_map_scan_bound": (_i, [_vp, C.POINTER(_d), C.POINTER(_d)]),
     "gmmloc_ctx_create": (_i, [_i, C.POINTER(_vp)]),
     "gmmloc_ctx_destroy": (None, [_vp]),
@@ -71,6 +73,10 @@ SYMBOLS = {
     "gmmloc_frames_solve_async": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i] + [_vp] * 5),
     "gmmloc_poses_optimize": (_i, [_vp, C.POINTER(Camera)] + [_vp] * 5 + [_i, _i] + [_vp] * 3),
     "gmmloc_triangulation_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 7 + [_i, _i] + [_vp] * 5),
+    "gmmloc_render_views": (_i, [_vp, _vp, C.POINTER(Camera), _vp, _i, _i] + [_vp] * 6),
+    "gmmloc_search_correspondence": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "gmmloc_check_map_association": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i, _i, _vp, _vp]),
+    "gmmloc_keyframes_associate": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i, _i, _i] + [_vp] * 5),
     "gmmloc_points_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 6 + [_i, _i] + [_vp] * 4),
 }
 

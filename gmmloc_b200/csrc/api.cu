@@ -216,6 +216,10 @@ struct gmmloc_ctx {
   Lane& L() { return lanes[active]; }
   DevBuf in_pts, in_obs, in_oct, in_pose, in_misc;  // device copies of host inputs
   DevBuf out_assign, out_d2, out_pose, out_pts, out_outlier, out_status, out_misc;
+  // rendered views of the last gmmloc_render_views (≙ GMM::components2d_) + keyframe-association staging
+  DevBuf view_pose, view_count, view_status, view_ids, view_rec, view_wids, view_wrec;
+  DevBuf kf_obs, kf_depth, kf_oct, kf_cand, kf_cand_pos, kf_pt3d, kf_assoc;
+  int view_B = 0, view_cap = 0;
   cudaStream_t h2d = nullptr, d2h = nullptr;        // copy streams of the pipelined host entry point
   std::vector<cudaEvent_t> ev_in, ev_done;          // per-chunk events (inputs landed / results ready)
   gmmloc_stats_t stats{};
@@ -275,6 +279,7 @@ void gmmloc_map_destroy(gmmloc_map_t* m) {
   cudaSetDevice(m->device);
   cudaFree(m->d.mean); cudaFree(m->d.cov); cudaFree(m->d.cov_inv); cudaFree(m->d.det); cudaFree(m->d.scale);
   cudaFree(m->d.axis); cudaFree(m->d.sqrt_info); cudaFree(m->d.is_deg); cudaFree(m->d.is_sal); cudaFree(m->d.scan);
+  cudaFree(m->d.nbr_row_ptr); cudaFree(m->d.nbr_col);
   cudaSetDevice(prev);
   delete m;
 }
@@ -412,6 +417,39 @@ gmmloc_status_t gmmloc_map_get_components(const gmmloc_map_t* map, double* mean,
   return GMMLOC_OK;
 }
 
+// counting pass + host prefix sum + fill pass; on success rp / dcol (/ ddist) hold the CSR lists on the device
+static gmmloc_status_t neighbors_device(const gmmloc_map_t* map, double thresh, bool want_dist, DevBuf& rp, DevBuf& dcol,
+                                        DevBuf& ddist, std::vector<long long>& h_rp) {
+  const int K = map->d.K;
+  DevBuf counts;
+  cudaError_t e;
+  if ((e = counts.reserve(sizeof(int) * (size_t)K)) != cudaSuccess) return fail_cuda(e, "cudaMalloc(counts)");
+  auto done = [&](gmmloc_status_t s) {
+    counts.release();
+    return s;
+  };
+  if ((e = launch_bh_neighbors(map->d, thresh, counts.as<int>(), nullptr, nullptr, nullptr, nullptr)) != cudaSuccess)
+    return done(fail_cuda(e, "bh_neighbors (count)"));
+  std::vector<int> h_counts((size_t)K);
+  if ((e = cudaMemcpy(h_counts.data(), counts.p, sizeof(int) * (size_t)K, cudaMemcpyDeviceToHost)) != cudaSuccess)
+    return done(fail_cuda(e, "bh_neighbors (count)"));
+  h_rp.assign((size_t)K + 1, 0);
+  for (int i = 0; i < K; ++i) h_rp[i + 1] = h_rp[i] + h_counts[i];
+  const size_t n = (size_t)h_rp[K];
+  if ((e = rp.reserve(sizeof(long long) * ((size_t)K + 1))) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(row_ptr)"));
+  if ((e = cudaMemcpy(rp.p, h_rp.data(), sizeof(long long) * ((size_t)K + 1), cudaMemcpyHostToDevice)) != cudaSuccess)
+    return done(fail_cuda(e, "H2D row_ptr"));
+  if ((e = dcol.reserve(sizeof(int32_t) * (n ? n : 1))) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(col)"));
+  if (want_dist && (e = ddist.reserve(sizeof(double) * (n ? n : 1))) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(dist)"));
+  if (n > 0) {
+    if ((e = launch_bh_neighbors(map->d, thresh, nullptr, rp.as<long long>(), dcol.as<int32_t>(),
+                                 want_dist ? ddist.as<double>() : nullptr, nullptr)) != cudaSuccess)
+      return done(fail_cuda(e, "bh_neighbors (fill)"));
+    if ((e = cudaDeviceSynchronize()) != cudaSuccess) return done(fail_cuda(e, "bh_neighbors (fill)"));
+  }
+  return done(GMMLOC_OK);
+}
+
 gmmloc_status_t gmmloc_map_neighbors(const gmmloc_map_t* map, double thresh, int64_t* row_ptr, int32_t* col, double* dist,
                                      int64_t cap, int64_t* count) {
   if (!map || !row_ptr || !count) return fail(GMMLOC_EINVAL, "gmmloc_map_neighbors: null pointer");
@@ -419,38 +457,48 @@ gmmloc_status_t gmmloc_map_neighbors(const gmmloc_map_t* map, double thresh, int
   int prev = 0;
   cudaGetDevice(&prev);
   CU(cudaSetDevice(map->device));
-  DevBuf counts, rp, dcol, ddist;
+  DevBuf rp, dcol, ddist;
+  std::vector<long long> h_rp;
   auto done = [&](gmmloc_status_t s) {
-    counts.release(); rp.release(); dcol.release(); ddist.release();
+    rp.release(); dcol.release(); ddist.release();
     cudaSetDevice(prev);
     return s;
   };
-  cudaError_t e;
-  if ((e = counts.reserve(sizeof(int) * (size_t)K)) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(counts)"));
-  if ((e = launch_bh_neighbors(map->d, thresh, counts.as<int>(), nullptr, nullptr, nullptr, nullptr)) != cudaSuccess)
-    return done(fail_cuda(e, "bh_neighbors (count)"));
-  std::vector<int> h_counts((size_t)K);
-  if ((e = cudaMemcpy(h_counts.data(), counts.p, sizeof(int) * (size_t)K, cudaMemcpyDeviceToHost)) != cudaSuccess)
-    return done(fail_cuda(e, "bh_neighbors (count)"));
-  std::vector<long long> h_rp((size_t)K + 1);
-  h_rp[0] = 0;
-  for (int i = 0; i < K; ++i) h_rp[i + 1] = h_rp[i] + h_counts[i];
+  gmmloc_status_t st = neighbors_device(map, thresh, dist != nullptr, rp, dcol, ddist, h_rp);
+  if (st != GMMLOC_OK) return done(st);
   for (int i = 0; i <= K; ++i) row_ptr[i] = h_rp[i];
   *count = h_rp[K];
   if (col == nullptr || cap < h_rp[K] || h_rp[K] == 0) return done(GMMLOC_OK);
   const size_t n = (size_t)h_rp[K];
-  if ((e = rp.reserve(sizeof(long long) * ((size_t)K + 1))) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(row_ptr)"));
-  if ((e = dcol.reserve(sizeof(int32_t) * n)) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(col)"));
-  if (dist && (e = ddist.reserve(sizeof(double) * n)) != cudaSuccess) return done(fail_cuda(e, "cudaMalloc(dist)"));
-  if ((e = cudaMemcpy(rp.p, h_rp.data(), sizeof(long long) * ((size_t)K + 1), cudaMemcpyHostToDevice)) != cudaSuccess)
-    return done(fail_cuda(e, "H2D row_ptr"));
-  if ((e = launch_bh_neighbors(map->d, thresh, nullptr, rp.as<long long>(), dcol.as<int32_t>(), dist ? ddist.as<double>() : nullptr,
-                               nullptr)) != cudaSuccess)
-    return done(fail_cuda(e, "bh_neighbors (fill)"));
+  cudaError_t e;
   if ((e = cudaMemcpy(col, dcol.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost)) != cudaSuccess) return done(fail_cuda(e, "D2H col"));
   if (dist && (e = cudaMemcpy(dist, ddist.p, sizeof(double) * n, cudaMemcpyDeviceToHost)) != cudaSuccess)
     return done(fail_cuda(e, "D2H dist"));
   return done(GMMLOC_OK);
+}
+
+gmmloc_status_t gmmloc_map_build_neighbors(gmmloc_map_t* map, double thresh, int64_t* count) {
+  if (!map) return fail(GMMLOC_EINVAL, "gmmloc_map_build_neighbors: null map");
+  int prev = 0;
+  cudaGetDevice(&prev);
+  CU(cudaSetDevice(map->device));
+  DevBuf rp, dcol, ddist;
+  std::vector<long long> h_rp;
+  gmmloc_status_t st = neighbors_device(map, thresh, false, rp, dcol, ddist, h_rp);
+  if (st != GMMLOC_OK) {
+    rp.release(); dcol.release();
+    cudaSetDevice(prev);
+    return st;
+  }
+  cudaFree(map->d.nbr_row_ptr);
+  cudaFree(map->d.nbr_col);
+  map->d.nbr_row_ptr = rp.as<long long>();  // ownership moves into the map
+  map->d.nbr_col = dcol.as<int32_t>();
+  map->d.nbr_count = h_rp[map->d.K];
+  map->d.nbr_thresh = thresh;
+  if (count) *count = map->d.nbr_count;
+  cudaSetDevice(prev);
+  return GMMLOC_OK;
 }
 
 gmmloc_status_t gmmloc_map_scan_bound(const gmmloc_map_t* map, double* alpha, double* xmax) {
@@ -501,7 +549,9 @@ void gmmloc_ctx_destroy(gmmloc_ctx_t* c) {
     if (l.stream) cudaStreamDestroy(l.stream);
   }
   DevBuf* bufs[] = {&c->in_pts, &c->in_obs, &c->in_oct, &c->in_pose, &c->in_misc, &c->out_assign, &c->out_d2, &c->out_pose,
-                    &c->out_pts, &c->out_outlier, &c->out_status, &c->out_misc};
+                    &c->out_pts, &c->out_outlier, &c->out_status, &c->out_misc, &c->view_pose, &c->view_count, &c->view_status,
+                    &c->view_ids, &c->view_rec, &c->view_wids, &c->view_wrec, &c->kf_obs, &c->kf_depth, &c->kf_oct, &c->kf_cand,
+                    &c->kf_cand_pos, &c->kf_pt3d, &c->kf_assoc};
   for (DevBuf* b : bufs) b->release();
   for (cudaEvent_t e : c->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : c->ev_done) cudaEventDestroy(e);
@@ -907,6 +957,241 @@ gmmloc_status_t gmmloc_triangulation_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t
   CU(cudaMemcpyAsync(err2, outp + q_e2, 8 * m, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(chi2_str, outp + q_cs, 8 * m, cudaMemcpyDeviceToHost, st));
   CU(cudaMemcpyAsync(res, outp + q_r, m, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return GMMLOC_OK;
+}
+
+// ---- keyframe association pipeline ------------------------------------------------------------------
+namespace {
+
+// enqueue K6 on the context's stream for poses already on the device (ctx->view_pose)
+gmmloc_status_t render_enqueue(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam, int B, int cap) {
+  const size_t n = (size_t)B * cap;
+  CU(ctx->view_count.reserve(4 * (size_t)B));
+  CU(ctx->view_status.reserve(4 * (size_t)B));
+  CU(ctx->view_ids.reserve(4 * n));
+  CU(ctx->view_wids.reserve(4 * n));
+  CU(ctx->view_rec.reserve(8 * kViewRec * n));
+  CU(ctx->view_wrec.reserve(8 * kViewRec * n));
+  ViewArgs a;
+  a.mean = map->d.mean;
+  a.cov = map->d.cov;
+  a.axis = map->d.axis;
+  a.is_deg = map->d.is_deg;
+  a.K = map->d.K;
+  a.fx = cam->fx; a.fy = cam->fy; a.cx = cam->cx; a.cy = cam->cy;
+  a.width = (double)cam->width;
+  a.height = (double)cam->height;
+  a.view_cos_thresh = std::cos(78.0 * M_PI / 180.0);  // gaussian_mixture.cpp:283
+  a.pose = ctx->view_pose.as<double>();
+  a.B = B;
+  a.cap = cap;
+  a.count = ctx->view_count.as<int32_t>();
+  a.ids = ctx->view_ids.as<int32_t>();
+  a.rec = ctx->view_rec.as<double>();
+  a.wids = ctx->view_wids.as<int32_t>();
+  a.wrec = ctx->view_wrec.as<double>();
+  a.status = ctx->view_status.as<int32_t>();
+  CU(launch_render_views(a, ctx->L().stream));
+  ctx->stats.kernel_launches += 1;
+  ctx->view_B = B;
+  ctx->view_cap = cap;
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t search_enqueue(gmmloc_ctx_t* ctx, const float* d_obs, int B, int N, int num, bool want_pos) {
+  CU(ctx->kf_cand.reserve(4 * (size_t)B * N * num));
+  if (want_pos) CU(ctx->kf_cand_pos.reserve(4 * (size_t)B * N * num));
+  SearchArgs a;
+  a.count = ctx->view_count.as<int32_t>();
+  a.ids = ctx->view_ids.as<int32_t>();
+  a.rec = ctx->view_rec.as<double>();
+  a.cap = ctx->view_cap;
+  a.obs = d_obs;
+  a.B = B;
+  a.N = N;
+  a.num = num;
+  a.cand = ctx->kf_cand.as<int32_t>();
+  a.cand_pos = want_pos ? ctx->kf_cand_pos.as<int32_t>() : nullptr;
+  CU(launch_search_corr(a, ctx->L().stream));
+  ctx->stats.kernel_launches += 1;
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t check_enqueue(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                              const gmmloc_params_t* params, const double* d_pose, const float* d_obs, const float* d_depth,
+                              const uint8_t* d_oct, const int32_t* d_cand, int B, int N, int num, double* d_pt3d,
+                              int32_t* d_assoc) {
+  CheckArgs a;
+  a.mean = map->d.mean;
+  a.cov_inv = map->d.cov_inv;
+  a.axis = map->d.axis;
+  a.is_deg = map->d.is_deg;
+  a.K = map->d.K;
+  a.nbr_row_ptr = map->d.nbr_row_ptr;
+  a.nbr_col = map->d.nbr_col;
+  fill_params(cam, params, a.prm);
+  a.pose = d_pose;
+  a.obs = d_obs;
+  a.depth = d_depth;
+  a.octave = d_oct;
+  a.cand = d_cand;
+  a.B = B;
+  a.N = N;
+  a.num = num;
+  a.pt3d = d_pt3d;
+  a.assoc = d_assoc;
+  CU(launch_check_assoc(a, ctx->L().stream));
+  ctx->stats.kernel_launches += 1;
+  return GMMLOC_OK;
+}
+
+}  // namespace
+
+gmmloc_status_t gmmloc_render_views(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam, const double* pose,
+                                    int B, int cap, int32_t* count, int32_t* status, int32_t* ids, double* mean2d,
+                                    double* cov2d, double* depth) {
+  if (!ctx || !map || !cam || B < 0 || cap <= 0) return fail(GMMLOC_EINVAL, "gmmloc_render_views: bad argument");
+  if (map->device != ctx->device) return fail(GMMLOC_EINVAL, "map and context live on different devices");
+  if (B == 0) {
+    ctx->view_B = 0;
+    return GMMLOC_OK;
+  }
+  if (!pose) return fail(GMMLOC_EINVAL, "gmmloc_render_views: null pose");
+  CU(cudaSetDevice(ctx->device));
+  ctx->active = 0;
+  if (cap > map->d.K) cap = map->d.K;
+  cudaStream_t st = ctx->L().stream;
+  CU(ctx->view_pose.reserve(56 * (size_t)B));
+  CU(cudaMemcpyAsync(ctx->view_pose.p, pose, 56 * (size_t)B, cudaMemcpyHostToDevice, st));
+  gmmloc_status_t rc = render_enqueue(ctx, map, cam, B, cap);
+  if (rc != GMMLOC_OK) return rc;
+  if (count) CU(cudaMemcpyAsync(count, ctx->view_count.p, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (status) CU(cudaMemcpyAsync(status, ctx->view_status.p, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (ids) CU(cudaMemcpyAsync(ids, ctx->view_ids.p, 4 * (size_t)B * cap, cudaMemcpyDeviceToHost, st));
+  std::vector<double> rec;
+  if (mean2d || cov2d || depth) {
+    rec.resize((size_t)B * cap * kViewRec);
+    CU(cudaMemcpyAsync(rec.data(), ctx->view_rec.p, 8 * rec.size(), cudaMemcpyDeviceToHost, st));
+  }
+  CU(cudaStreamSynchronize(st));
+  if (!rec.empty()) {
+    // entries past a view's count are unspecified on the device: zero them on the way out
+    std::vector<int32_t> cnt((size_t)B);
+    CU(cudaMemcpy(cnt.data(), ctx->view_count.p, 4 * (size_t)B, cudaMemcpyDeviceToHost));
+    for (size_t b = 0; b < (size_t)B; ++b)
+      for (size_t j = 0; j < (size_t)cap; ++j) {
+        const size_t e = b * cap + j;
+        const bool live = (int)j < cnt[b];
+        const double* r = &rec[e * kViewRec];
+        if (mean2d) { mean2d[e * 2] = live ? r[0] : 0.0; mean2d[e * 2 + 1] = live ? r[1] : 0.0; }
+        if (cov2d) for (int q = 0; q < 4; ++q) cov2d[e * 4 + q] = live ? r[2 + q] : 0.0;
+        if (depth) depth[e] = live ? r[7] : 0.0;
+      }
+  }
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_search_correspondence(gmmloc_ctx_t* ctx, const float* obs, int B, int N, int num, int32_t* cand,
+                                             int32_t* cand_pos) {
+  if (!ctx || B < 0 || N < 0) return fail(GMMLOC_EINVAL, "gmmloc_search_correspondence: bad argument");
+  if (num < 1 || num > search_corr_max_num()) return fail(GMMLOC_EINVAL, "gmmloc_search_correspondence: num must be in [1, 8]");
+  if (B != ctx->view_B) return fail(GMMLOC_EINVAL, "gmmloc_search_correspondence: B differs from the views rendered on this context");
+  if (B == 0 || N == 0) return GMMLOC_OK;
+  if (!obs || !cand) return fail(GMMLOC_EINVAL, "gmmloc_search_correspondence: null pointer");
+  CU(cudaSetDevice(ctx->device));
+  ctx->active = 0;
+  cudaStream_t st = ctx->L().stream;
+  const size_t M = (size_t)B * N;
+  CU(ctx->kf_obs.reserve(12 * M));
+  CU(cudaMemcpyAsync(ctx->kf_obs.p, obs, 12 * M, cudaMemcpyHostToDevice, st));
+  gmmloc_status_t rc = search_enqueue(ctx, ctx->kf_obs.as<float>(), B, N, num, cand_pos != nullptr);
+  if (rc != GMMLOC_OK) return rc;
+  CU(cudaMemcpyAsync(cand, ctx->kf_cand.p, 4 * M * num, cudaMemcpyDeviceToHost, st));
+  if (cand_pos) CU(cudaMemcpyAsync(cand_pos, ctx->kf_cand_pos.p, 4 * M * num, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_check_map_association(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                             const gmmloc_params_t* params, const double* pose, const float* obs,
+                                             const uint8_t* octave, const int32_t* cand, int B, int N, int num, double* pt3d,
+                                             int32_t* assoc) {
+  if (!ctx || !map || !cam || !params || B < 0 || N < 0 || num < 1)
+    return fail(GMMLOC_EINVAL, "gmmloc_check_map_association: bad argument");
+  if (map->device != ctx->device) return fail(GMMLOC_EINVAL, "map and context live on different devices");
+  if (!map->d.nbr_row_ptr) return fail(GMMLOC_EINVAL, "gmmloc_check_map_association: call gmmloc_map_build_neighbors first");
+  if (B == 0 || N == 0) return GMMLOC_OK;
+  if (!pose || !obs || !octave || !cand || !pt3d || !assoc) return fail(GMMLOC_EINVAL, "gmmloc_check_map_association: null pointer");
+  CU(cudaSetDevice(ctx->device));
+  ctx->active = 0;
+  cudaStream_t st = ctx->L().stream;
+  const size_t M = (size_t)B * N;
+  CU(ctx->in_pose.reserve(56 * (size_t)B));
+  CU(ctx->kf_obs.reserve(12 * M));
+  CU(ctx->kf_oct.reserve(M));
+  CU(ctx->kf_cand.reserve(4 * M * num));
+  CU(ctx->kf_pt3d.reserve(24 * M));
+  CU(ctx->kf_assoc.reserve(4 * M));
+  CU(cudaMemcpyAsync(ctx->in_pose.p, pose, 56 * (size_t)B, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->kf_obs.p, obs, 12 * M, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->kf_oct.p, octave, M, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->kf_cand.p, cand, 4 * M * num, cudaMemcpyHostToDevice, st));
+  CU(cudaMemcpyAsync(ctx->kf_pt3d.p, pt3d, 24 * M, cudaMemcpyHostToDevice, st));
+  gmmloc_status_t rc = check_enqueue(ctx, map, cam, params, ctx->in_pose.as<double>(), ctx->kf_obs.as<float>(), nullptr,
+                                     ctx->kf_oct.as<uint8_t>(), ctx->kf_cand.as<int32_t>(), B, N, num, ctx->kf_pt3d.as<double>(),
+                                     ctx->kf_assoc.as<int32_t>());
+  if (rc != GMMLOC_OK) return rc;
+  CU(cudaMemcpyAsync(pt3d, ctx->kf_pt3d.p, 24 * M, cudaMemcpyDeviceToHost, st));
+  CU(cudaMemcpyAsync(assoc, ctx->kf_assoc.p, 4 * M, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_keyframes_associate(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                           const gmmloc_params_t* params, const double* pose, const float* obs,
+                                           const float* depth, const uint8_t* octave, int B, int N, int num, int cap,
+                                           int32_t* assoc, double* pt3d, int32_t* cand, int32_t* nview, int32_t* vstatus) {
+  if (!ctx || !map || !cam || !params || B < 0 || N < 0 || cap <= 0)
+    return fail(GMMLOC_EINVAL, "gmmloc_keyframes_associate: bad argument");
+  if (num < 1 || num > search_corr_max_num()) return fail(GMMLOC_EINVAL, "gmmloc_keyframes_associate: num must be in [1, 8]");
+  if (map->device != ctx->device) return fail(GMMLOC_EINVAL, "map and context live on different devices");
+  if (!map->d.nbr_row_ptr) return fail(GMMLOC_EINVAL, "gmmloc_keyframes_associate: call gmmloc_map_build_neighbors first");
+  if (B == 0) return GMMLOC_OK;
+  if (!pose || (N > 0 && (!obs || !depth || !octave || !assoc || !pt3d)))
+    return fail(GMMLOC_EINVAL, "gmmloc_keyframes_associate: null pointer");
+  CU(cudaSetDevice(ctx->device));
+  ctx->active = 0;
+  if (cap > map->d.K) cap = map->d.K;
+  cudaStream_t st = ctx->L().stream;
+  const size_t M = (size_t)B * N;
+  CU(ctx->view_pose.reserve(56 * (size_t)B));
+  CU(cudaMemcpyAsync(ctx->view_pose.p, pose, 56 * (size_t)B, cudaMemcpyHostToDevice, st));
+  if (M) {
+    CU(ctx->kf_obs.reserve(12 * M));
+    CU(ctx->kf_depth.reserve(4 * M));
+    CU(ctx->kf_oct.reserve(M));
+    CU(ctx->kf_pt3d.reserve(24 * M));
+    CU(ctx->kf_assoc.reserve(4 * M));
+    CU(cudaMemcpyAsync(ctx->kf_obs.p, obs, 12 * M, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->kf_depth.p, depth, 4 * M, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->kf_oct.p, octave, M, cudaMemcpyHostToDevice, st));
+  }
+  gmmloc_status_t rc = render_enqueue(ctx, map, cam, B, cap);  // gmmloc_opt.cpp:122-126
+  if (rc != GMMLOC_OK) return rc;
+  if (M) {
+    rc = search_enqueue(ctx, ctx->kf_obs.as<float>(), B, N, num, false);  // :128-134
+    if (rc != GMMLOC_OK) return rc;
+    rc = check_enqueue(ctx, map, cam, params, ctx->view_pose.as<double>(), ctx->kf_obs.as<float>(), ctx->kf_depth.as<float>(),
+                       ctx->kf_oct.as<uint8_t>(), ctx->kf_cand.as<int32_t>(), B, N, num, ctx->kf_pt3d.as<double>(),
+                       ctx->kf_assoc.as<int32_t>());  // :73-77
+    if (rc != GMMLOC_OK) return rc;
+    CU(cudaMemcpyAsync(assoc, ctx->kf_assoc.p, 4 * M, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(pt3d, ctx->kf_pt3d.p, 24 * M, cudaMemcpyDeviceToHost, st));
+    if (cand) CU(cudaMemcpyAsync(cand, ctx->kf_cand.p, 4 * M * num, cudaMemcpyDeviceToHost, st));
+  }
+  if (nview) CU(cudaMemcpyAsync(nview, ctx->view_count.p, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (vstatus) CU(cudaMemcpyAsync(vstatus, ctx->view_status.p, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return GMMLOC_OK;
 }

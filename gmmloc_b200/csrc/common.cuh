@@ -38,6 +38,10 @@ struct MapDev {
   uint8_t* is_deg = nullptr;    // K
   uint8_t* is_sal = nullptr;    // K
   float* scan = nullptr;        // Kpad x kScanFloats
+  long long* nbr_row_ptr = nullptr;  // K + 1: CSR neighbour lists (gmmloc_map_build_neighbors), else null
+  int32_t* nbr_col = nullptr;
+  long long nbr_count = 0;
+  double nbr_thresh = 0.0;
   float alpha = 0.f;            // error bound of sqrt(score32) vs sqrt(exact d2), whitened units
   float xmax = 0.f;             // |x|_inf bound under which alpha holds
 };
@@ -134,6 +138,61 @@ struct TriArgs {
   uint8_t* res;            // M
 };
 cudaError_t launch_tri_gn(const TriArgs& a, cudaStream_t stream);
+
+// ---- keyframe association pipeline (view.cu) ----------------------------------------------------------
+// one rendered 2-D component = kViewRec doubles: mean(2) cov(4, row-major as computed) det depth
+constexpr int kViewRec = 8;
+struct ViewArgs {
+  const double* mean;  // map constants
+  const double* cov;
+  const double* axis;
+  const uint8_t* is_deg;
+  int K;
+  double fx, fy, cx, cy, width, height;
+  double view_cos_thresh;  // cos(78 deg), computed on the host (gaussian_mixture.cpp:283)
+  const double* pose;      // B x 7
+  int B, cap;
+  int32_t* count;          // B
+  int32_t* ids;            // B x cap   depth-sorted parent component ids
+  double* rec;             // B x cap x kViewRec, depth-sorted
+  int32_t* wids;           // B x cap   working kept list (insertion order)
+  double* wrec;            // B x cap x kViewRec
+  int32_t* status;         // B   GMMLOC_VIEW_* bits
+};
+cudaError_t launch_render_views(const ViewArgs& a, cudaStream_t stream);
+
+struct SearchArgs {
+  const int32_t* count;  // rendered views (output of launch_render_views)
+  const int32_t* ids;
+  const double* rec;
+  int cap;
+  const float* obs;      // B x N x 3 (u v u_r; only u v are read)
+  int B, N, num;
+  int32_t* cand;         // B x N x num parent component ids, -1 padded
+  int32_t* cand_pos;     // B x N x num positions in the view list (optional)
+};
+cudaError_t launch_search_corr(const SearchArgs& a, cudaStream_t stream);
+int search_corr_max_num();
+
+struct CheckArgs {
+  const double* mean;
+  const double* cov_inv;
+  const double* axis;
+  const uint8_t* is_deg;
+  int K;
+  const long long* nbr_row_ptr;  // K + 1
+  const int32_t* nbr_col;
+  FrameParamsDev prm;
+  const double* pose;     // B x 7
+  const float* obs;       // B x N x 3
+  const float* depth;     // B x N, or null when pt3d is an input
+  const uint8_t* octave;  // B x N
+  const int32_t* cand;    // B x N x num
+  int B, N, num;
+  double* pt3d;           // B x N x 3 (in/out)
+  int32_t* assoc;         // B x N
+};
+cudaError_t launch_check_assoc(const CheckArgs& a, cudaStream_t stream);
 
 // ---- exact (non-contracted) fp64 helpers: the re-rank and the map build must replay the CPU
 // oracle's operation order bit for bit, so every product and sum is an explicit IEEE rn op. ----

@@ -13,29 +13,11 @@
 // same expression order as the CPU oracle (which is built -ffp-contract=off), so pt_est / chi2 come out
 // bit-identical.
 #include "common.cuh"
+#include "point_gn.cuh"
 
 namespace gmmloc {
 
 namespace {
-
-__device__ __forceinline__ void quat_to_rot_n(const double* pose, double* R) {
-  double x = pose[0], y = pose[1], z = pose[2], w = pose[3];
-  if (w < 0) { x = -x; y = -y; z = -z; w = -w; }
-  const double n = sqrt(x * x + y * y + z * z + w * w);
-  x /= n; y /= n; z /= n; w /= n;
-  const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
-  const double twx = tx * w, twy = ty * w, twz = tz * w;
-  const double txx = tx * x, txy = ty * x, txz = tz * x;
-  const double tyy = ty * y, tyz = tz * y, tzz = tz * z;
-  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
-  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
-  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
-}
-
-__device__ __forceinline__ double cof(const double* m, int i, int j) {
-  const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-  return m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
-}
 
 __global__ void __launch_bounds__(128) point_gn_kernel(const PointArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -60,61 +42,13 @@ __global__ void __launch_bounds__(128) point_gn_kernel(const PointArgs a) {
   const double* ax = a.axis + (size_t)k * 9;
   const double n[3] = {ax[0], ax[3], ax[6]};  // axis_.col(0), gmmloc_opt.cpp:314
   const double* mu = a.mean + (size_t)k * 3;
-  double x[3] = {a.x0[(size_t)i * 3], a.x0[(size_t)i * 3 + 1], a.x0[(size_t)i * 3 + 2]};
-  double c2p = 0, c2s = 0;
-  bool ok = true;
-  for (int it = 0; it < a.iters; ++it) {
-    const double px = ((R[0] * x[0] + R[1] * x[1]) + R[2] * x[2]) + t0;
-    const double py = ((R[3] * x[0] + R[4] * x[1]) + R[5] * x[2]) + t1;
-    const double pz = ((R[6] * x[0] + R[7] * x[1]) + R[8] * x[2]) + t2;
-    const double z_2 = pz * pz;
-    const double invz = 1.0 / pz;
-    const double u = px * invz * P.fx + P.cx;
-    const double v = py * invz * P.fy + P.cy;
-    const double ur = u - P.bf * invz;
-    const double e[3] = {o0 - u, o1 - v, o2 - ur};
-    double Jl[9];
-    for (int j = 0; j < 3; ++j) {
-      Jl[j] = -P.fx * R[j] / pz + P.fx * px * R[6 + j] / z_2;
-      Jl[3 + j] = -P.fy * R[3 + j] / pz + P.fy * py * R[6 + j] / z_2;
-      Jl[6 + j] = Jl[j] - P.bf * R[6 + j] / z_2;
-    }
-    const double es = (n[0] * (x[0] - mu[0]) + n[1] * (x[1] - mu[1])) + n[2] * (x[2] - mu[2]);
-    c2p = w_proj * ((e[0] * e[0] + e[1] * e[1]) + e[2] * e[2]);
-    c2s = w_str * (es * es);
-    double H[9], b[3];
-    for (int r = 0; r < 3; ++r) {
-      for (int c = 0; c < 3; ++c)
-        H[r * 3 + c] = w_proj * ((Jl[r] * Jl[c] + Jl[3 + r] * Jl[3 + c]) + Jl[6 + r] * Jl[6 + c]) + w_str * (n[r] * n[c]);
-      b[r] = -(w_proj * ((Jl[r] * e[0] + Jl[3 + r] * e[1]) + Jl[6 + r] * e[2]) + w_str * (n[r] * es));
-    }
-    // 3x3 inverse by cofactors (same tree as the map build / oracle)
-    const double c00 = cof(H, 0, 0), c10 = cof(H, 1, 0), c20 = cof(H, 2, 0);
-    const double det = (c00 * H[0] + c10 * H[3]) + c20 * H[6];
-    const double invdet = 1.0 / det;
-    if (!(isfinite(invdet) && det != 0.0)) {
-      ok = false;
-      break;
-    }
-    double Hi[9];
-    Hi[0] = c00 * invdet;
-    Hi[1] = c10 * invdet;
-    Hi[2] = c20 * invdet;
-    Hi[3] = cof(H, 0, 1) * invdet;
-    Hi[4] = cof(H, 1, 1) * invdet;
-    Hi[5] = cof(H, 2, 1) * invdet;
-    Hi[6] = cof(H, 0, 2) * invdet;
-    Hi[7] = cof(H, 1, 2) * invdet;
-    Hi[8] = cof(H, 2, 2) * invdet;
-    for (int r = 0; r < 3; ++r) x[r] += (Hi[r * 3] * b[0] + Hi[r * 3 + 1] * b[1]) + Hi[r * 3 + 2] * b[2];
-  }
-  for (int r = 0; r < 3; ++r) a.pt_est[(size_t)i * 3 + r] = x[r];
-  a.chi2_proj[i] = c2p;
-  a.chi2_str[i] = c2s;
-  uint8_t res = ok ? 1 : 0;
-  if (c2p > 7.815) res = 0;                                                        // gmmloc_opt.cpp:332-335
-  if (P.tri_check_str_chi2 && c2s > P.tri_str_thresh * P.tri_lambda2) res = 0;     // gmmloc_opt.cpp:336-339
-  a.res[i] = res;
+  const double x0[3] = {a.x0[(size_t)i * 3], a.x0[(size_t)i * 3 + 1], a.x0[(size_t)i * 3 + 2]};
+  const double t[3] = {t0, t1, t2}, o[3] = {o0, o1, o2};
+  const PointSolve s = optimize_point_d(P, R, t, o, w_proj, w_str, n, mu, x0, a.iters);
+  for (int r = 0; r < 3; ++r) a.pt_est[(size_t)i * 3 + r] = s.x[r];
+  a.chi2_proj[i] = s.chi2_proj;
+  a.chi2_str[i] = s.chi2_str;
+  a.res[i] = s.res ? 1 : 0;
 }
 
 // ---- K4b: one candidate of Localization::optimizeTriangulationVec (localization_opt.cpp:27-204): two view
@@ -199,23 +133,11 @@ __global__ void __launch_bounds__(128) tri_gn_kernel(const TriArgs a) {
       const double g2 = (J2[r] * e2[0] + J2[3 + r] * e2[1]) + J2[6 + r] * e2[2];
       b[r] = -((w * g1 + w * g2) + w_str * (n[r] * es));
     }
-    const double c00 = cof(H, 0, 0), c10 = cof(H, 1, 0), c20 = cof(H, 2, 0);
-    const double det = (c00 * H[0] + c10 * H[3]) + c20 * H[6];
-    const double invdet = 1.0 / det;
-    if (!(isfinite(invdet) && det != 0.0)) {
+    double Hi[9];
+    if (!inverse3_d(H, Hi)) {
       ok = false;
       break;
     }
-    double Hi[9];
-    Hi[0] = c00 * invdet;
-    Hi[1] = c10 * invdet;
-    Hi[2] = c20 * invdet;
-    Hi[3] = cof(H, 0, 1) * invdet;
-    Hi[4] = cof(H, 1, 1) * invdet;
-    Hi[5] = cof(H, 2, 1) * invdet;
-    Hi[6] = cof(H, 0, 2) * invdet;
-    Hi[7] = cof(H, 1, 2) * invdet;
-    Hi[8] = cof(H, 2, 2) * invdet;
     for (int r = 0; r < 3; ++r) x[r] += (Hi[r * 3] * b[0] + Hi[r * 3 + 1] * b[1]) + Hi[r * 3 + 2] * b[2];
   }
   for (int r = 0; r < 3; ++r) a.pt_est[(size_t)i * 3 + r] = x[r];

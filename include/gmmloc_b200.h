@@ -74,6 +74,9 @@ enum { GMMLOC_MODE_JOINT = 0, GMMLOC_MODE_POSE_ONLY = 1, GMMLOC_MODE_POINTS_ONLY
 /* per-frame status bits written by gmmloc_frames_solve */
 enum { GMMLOC_FRAME_NUMERIC = 1 /* singular Hll / reduced system or non-finite value: frame frozen */ };
 
+/* per-view status bits written by gmmloc_render_views */
+enum { GMMLOC_VIEW_OVERFLOW = 1 /* more than `cap` 2-D components survived: the list was truncated */ };
+
 /* counters of the last association on a context (evidence for the exact re-rank path) */
 typedef struct {
   int64_t points;        /* points scanned                                              */
@@ -118,6 +121,11 @@ GMMLOC_API gmmloc_status_t gmmloc_map_get_components(const gmmloc_map_t* map, do
  * size them with a first call passing col = NULL. */
 GMMLOC_API gmmloc_status_t gmmloc_map_neighbors(const gmmloc_map_t* map, double thresh, int64_t* row_ptr, int32_t* col,
                                                 double* dist, int64_t cap, int64_t* count);
+/* Builds the neighbour lists above once and keeps them on the device inside the map (the reference builds
+ * GaussianComponent::nbs_ in the GMM constructor, gaussian_mixture.cpp:61-78); required by
+ * gmmloc_check_map_association / gmmloc_keyframes_associate.  Not thread-safe: call it before the map is
+ * shared.  *count (optional) receives the number of (i, j) pairs. */
+GMMLOC_API gmmloc_status_t gmmloc_map_build_neighbors(gmmloc_map_t* map, double thresh, int64_t* count);
 /* error bound of the fp32 scan in whitened units (|sqrt(s32) - sqrt(d2)| <= alpha for |x|_inf <= xmax) */
 GMMLOC_API gmmloc_status_t gmmloc_map_scan_bound(const gmmloc_map_t* map, double* alpha, double* xmax);
 
@@ -204,6 +212,55 @@ GMMLOC_API gmmloc_status_t gmmloc_triangulation_solve(gmmloc_ctx_t* ctx, const g
                                                       const double* pose2, const int32_t* comp, int M, int iters,
                                                       double* pt_est, double* err1, double* err2, double* chi2_str,
                                                       uint8_t* res);
+
+
+/* ---- keyframe association pipeline: GMMLoc::associateMapElements (gmmloc_opt.cpp:115-154) + the
+ * per-feature association inside GMMLoc::createMapPointsFromStereo (:36-113), batched over B keyframes. ---- */
+
+/* GMM::renderView(rot_c_w, t_c_w) (gaussian_mixture.cpp:271-371) for B views: view-cos cull of degenerate
+ * components, GMMUtility::projectGaussian (gmm_utils.cpp:121-146), 2-D covariance cull, greedy occlusion
+ * dedupe in ascending component order (2-D Bhattacharyya < 0.8 => the nearer one keeps the slot), sort by depth
+ * descending.  The rendered views stay on the context (the reference keeps them in GMM::components2d_) for
+ * gmmloc_search_correspondence; `cap` bounds the 2-D components kept per view (cap >= map size can never
+ * overflow; a view that overflows is truncated and flagged GMMLOC_VIEW_OVERFLOW in status).
+ *  pose B x 7 (T_cw).  Host outputs (each optional): count B, status B, ids B x cap (parent component index,
+ *  GaussianComponent2d::id_), mean2d B x cap x 2, cov2d B x cap x 4 (row-major), depth B x cap (proj_d_). */
+GMMLOC_API gmmloc_status_t gmmloc_render_views(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                               const double* pose, int B, int cap, int32_t* count, int32_t* status,
+                                               int32_t* ids, double* mean2d, double* cov2d, double* depth);
+
+/* GMM::searchCorrespondence(kpts, comps, num) (gaussian_mixture.cpp:484-534) on the views last rendered on
+ * ctx: per keypoint the `num` (<= 8; the reference uses 5) nearest 2-D means in ascending distance (brute
+ * force instead of the nanoflann kd-tree; equal distances -> lower view position first), keeping those with
+ * 2-D MDist2 < 9.0.   obs B x N x 3 (u v u_r; only u v are read).
+ *  cand B x N x num: parent component indices (gc2d->parent_), -1 padded;  cand_pos (optional): positions in
+ *  the rendered view list. */
+GMMLOC_API gmmloc_status_t gmmloc_search_correspondence(gmmloc_ctx_t* ctx, const float* obs, int B, int N, int num,
+                                                        int32_t* cand, int32_t* cand_pos);
+
+/* GMMLoc::checkMapAssociation (gmmloc_opt.cpp:156-258), B x N features: optimizePoint against every candidate,
+ * smallest accepted chi2_proj wins, Mahalanobis scan of the winner's neighbour list, optional re-solve, 9.0
+ * gate; when no candidate is accepted: kd fallback (nearest mean, degenerate only), which may move the point
+ * but never associates.   Needs gmmloc_map_build_neighbors.
+ *  pose B x 7, obs B x N x 3 (u v u_r), octave B x N, cand B x N x num (component indices, -1 = none).
+ *  pt3d B x N x 3 in/out (fp64): updated exactly where the reference mutates its argument.
+ *  assoc B x N: associated component index or -1 (nullptr). */
+GMMLOC_API gmmloc_status_t gmmloc_check_map_association(gmmloc_ctx_t* ctx, const gmmloc_map_t* map,
+                                                        const gmmloc_camera_t* cam, const gmmloc_params_t* params,
+                                                        const double* pose, const float* obs, const uint8_t* octave,
+                                                        const int32_t* cand, int B, int N, int num, double* pt3d,
+                                                        int32_t* assoc);
+
+/* The three steps above chained on the device for B keyframes of N features: render, search (num candidates),
+ * Frame::unproject3 (frame.cpp:27-36) of every feature with depth > 0, checkMapAssociation.
+ *  depth B x N (Feature::depth; <= 0: no stereo depth => assoc -1, pt3d NaN).
+ *  outputs: assoc B x N, pt3d B x N x 3 (fp64), cand B x N x num (optional), nview B (optional: rendered 2-D
+ *  components per keyframe), vstatus B (optional: GMMLOC_VIEW_* bits). */
+GMMLOC_API gmmloc_status_t gmmloc_keyframes_associate(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                                      const gmmloc_params_t* params, const double* pose, const float* obs,
+                                                      const float* depth, const uint8_t* octave, int B, int N, int num,
+                                                      int cap, int32_t* assoc, double* pt3d, int32_t* cand,
+                                                      int32_t* nview, int32_t* vstatus);
 
 #ifdef __cplusplus
 }

@@ -1092,4 +1092,291 @@ int oracle_gmm_write(const char* path, const double* mean, const double* cov, co
   return w == b.size() ? 0 : -2;
 }
 
+// ----------------------------------------------------------------------------------------------
+// keyframe association pipeline: projectGaussian, renderView, searchCorrespondence, checkMapAssociation
+// ----------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// Eigen QuaternionBase::_transformVector: uv = q.vec x v; uv += uv; v + w * uv + q.vec x uv
+inline void quat_rotate(const double q[4], const double v[3], double out[3]) {
+  double uv[3] = {q[1] * v[2] - q[2] * v[1], q[2] * v[0] - q[0] * v[2], q[0] * v[1] - q[1] * v[0]};
+  for (int i = 0; i < 3; ++i) uv[i] += uv[i];
+  const double c[3] = {q[1] * uv[2] - q[2] * uv[1], q[2] * uv[0] - q[0] * uv[2], q[0] * uv[1] - q[1] * uv[0]};
+  for (int i = 0; i < 3; ++i) out[i] = (v[i] + q[3] * uv[i]) + c[i];
+}
+
+inline double det2(const double* m) { return m[0] * m[3] - m[2] * m[1]; }  // Eigen: m(0,0) m(1,1) - m(1,0) m(0,1)
+inline void inverse2(const double* m, double* out) {
+  // Eigen compute_inverse_size2_helper
+  const double invdet = 1.0 / det2(m);
+  out[0] = m[3] * invdet;
+  out[2] = -m[2] * invdet;
+  out[1] = -m[1] * invdet;
+  out[3] = m[0] * invdet;
+}
+inline double quad2(const double* A, const double* d) {
+  // delta^T * A * delta: (delta^T A) first, then . delta
+  const double r0 = d[0] * A[0] + d[1] * A[2];
+  const double r1 = d[0] * A[1] + d[1] * A[3];
+  return r0 * d[0] + r1 * d[1];
+}
+
+}  // namespace
+
+extern "C" {
+
+int oracle_project_gaussian(const oracle_comp_t* c, int id, const oracle_camera_t* cam, const double pose[7],
+                            oracle_comp2d_t* out) {
+  // gmm_utils.cpp:121-146
+  double q[4] = {pose[0], pose[1], pose[2], pose[3]};
+  quat_normalize(q);
+  const double* t = pose + 4;
+  double pc[3];
+  quat_rotate(q, c->mean, pc);  // rot_c_w * mu3d + t_c_w
+  for (int i = 0; i < 3; ++i) pc[i] += t[i];
+  // PinholeCamera::project3 with Jacobian (pinhole_camera.cpp:68-125)
+  const double x = pc[0], y = pc[1], z = pc[2];
+  const double rz = 1.0 / z;
+  const double kx = x * rz, ky = y * rz;
+  const double rz2 = rz * rz;
+  const double J[6] = {cam->fx * rz, 0.0, -cam->fx * x * rz2, 0.0, cam->fy * rz, -cam->fy * y * rz2};
+  const double u = cam->fx * kx + cam->cx;
+  const double v = cam->fy * ky + cam->cy;
+  // evaluateProjectionResult / isKeypointVisible (pinhole_camera.cpp:127-150), kMinimumDepth = 0
+  const bool vis = u >= 0.0 && v >= 0.0 && u < (double)cam->width && v < (double)cam->height;
+  if (!(vis && z > 0.0)) return 0;
+  double R[9];
+  quat_to_rot(q, R);
+  // jacob_proj * rot * cov3d * rot^T * jacob_proj^T, left to right
+  double T1[6], T2[6], T3[6];
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) T1[i * 3 + j] = (J[i * 3] * M(R, 0, j) + J[i * 3 + 1] * M(R, 1, j)) + J[i * 3 + 2] * M(R, 2, j);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j)
+      T2[i * 3 + j] = (T1[i * 3] * M(c->cov, 0, j) + T1[i * 3 + 1] * M(c->cov, 1, j)) + T1[i * 3 + 2] * M(c->cov, 2, j);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 3; ++j) T3[i * 3 + j] = (T2[i * 3] * M(R, j, 0) + T2[i * 3 + 1] * M(R, j, 1)) + T2[i * 3 + 2] * M(R, j, 2);
+  for (int i = 0; i < 2; ++i)
+    for (int j = 0; j < 2; ++j) out->cov[i * 2 + j] = (T3[i * 3] * J[j * 3] + T3[i * 3 + 1] * J[j * 3 + 1]) + T3[i * 3 + 2] * J[j * 3 + 2];
+  out->id = id;
+  out->pad_ = 0;
+  out->mean[0] = u;
+  out->mean[1] = v;
+  inverse2(out->cov, out->cov_inv);  // gaussian.h:109
+  out->det = det2(out->cov);         // gaussian.h:111
+  // SelfAdjointEigenSolver<Matrix2d> (lower triangle), closed form; ascending (gaussian.cpp:20-23)
+  const double a = out->cov[0], b = out->cov[2], d = out->cov[3];
+  const double tr = 0.5 * (a + d), h = 0.5 * (a - d);
+  const double r = std::sqrt(h * h + b * b);
+  out->scale[0] = tr - r;
+  out->scale[1] = tr + r;
+  out->depth = pc[2];
+  return 1;
+}
+
+double oracle_bh2(const oracle_comp2d_t* g0, const oracle_comp2d_t* g1) {
+  // gmm_utils.h:30-52 with 2-D types
+  double cov[4], inv[4];
+  for (int i = 0; i < 4; ++i) cov[i] = (g0->cov[i] + g1->cov[i]) / 2.0;
+  const double d[2] = {g1->mean[0] - g0->mean[0], g1->mean[1] - g0->mean[1]};
+  inverse2(cov, inv);
+  double d0 = quad2(inv, d);
+  d0 /= 8.0;
+  const double d1 = std::log(det2(cov) / std::sqrt(g0->det * g1->det)) / 2.0;
+  return d0 + d1;
+}
+
+double oracle_mdist2_2d(const oracle_comp2d_t* c, const double uv[2]) {
+  const double d[2] = {uv[0] - c->mean[0], uv[1] - c->mean[1]};  // gaussian.h:123-126
+  return quad2(c->cov_inv, d);
+}
+
+int oracle_render_view(const oracle_comp_t* comps, int K, const oracle_camera_t* cam, const double pose[7],
+                       oracle_comp2d_t* out) {
+  // gaussian_mixture.cpp:271-371
+  double q[4] = {pose[0], pose[1], pose[2], pose[3]};
+  quat_normalize(q);
+  // t_w_c = -(rot_c_w.inverse() * t_c_w); Eigen inverse() = conjugate / squaredNorm
+  const double n2 = ((q[0] * q[0] + q[1] * q[1]) + q[2] * q[2]) + q[3] * q[3];
+  const double qi[4] = {-q[0] / n2, -q[1] / n2, -q[2] / n2, q[3] / n2};
+  double twc[3];
+  quat_rotate(qi, pose + 4, twc);
+  for (int i = 0; i < 3; ++i) twc[i] = -twc[i];
+  const double view_cos_thresh = std::cos(78.0 * M_PI / 180.0);  // :283
+  int V = 0;
+  for (int k = 0; k < K; ++k) {
+    const oracle_comp_t& c = comps[k];
+    if (c.is_degenerated) {  // STEP.0 check view cos (:285-302)
+      double po[3] = {c.mean[0] - twc[0], c.mean[1] - twc[1], c.mean[2] - twc[2]};
+      const double z = (po[0] * po[0] + po[1] * po[1]) + po[2] * po[2];
+      if (z > 0.0) {  // Eigen normalized()
+        const double nrm = std::sqrt(z);
+        for (int i = 0; i < 3; ++i) po[i] /= nrm;
+      }
+      const double view_cos = std::fabs((po[0] * c.axis[0] + po[1] * c.axis[3]) + po[2] * c.axis[6]);
+      if (view_cos < view_cos_thresh) continue;
+    }
+    oracle_comp2d_t g;
+    if (!oracle_project_gaussian(&c, k, cam, pose, &g)) continue;
+    if (g.scale[0] < 4.0 && g.scale[1] < 4.0) continue;  // STEP. check cov (:311-317)
+    if (V > 0) {  // STEP. check near far (:327-355)
+      int min_idx = 0;
+      double min_dist = std::numeric_limits<double>::max();
+      for (int j = 0; j < V; ++j) {
+        const double dist = oracle_bh2(&out[j], &g);
+        if (dist < min_dist) { min_dist = dist; min_idx = j; }
+      }
+      if (min_dist < 0.8) {
+        if (g.depth < out[min_idx].depth) out[min_idx] = g;
+      } else {
+        out[V++] = g;
+      }
+    } else {
+      out[V++] = g;
+    }
+  }
+  std::stable_sort(out, out + V, [](const oracle_comp2d_t& a, const oracle_comp2d_t& b) { return a.depth > b.depth; });  // :362-364
+  return V;
+}
+
+void oracle_search_correspondence(const oracle_comp2d_t* view, int V, const double* uv, int N, int num, int32_t* cand) {
+  // gaussian_mixture.cpp:484-534
+  std::vector<double> bd(num);
+  std::vector<int> bi(num);
+  for (int i = 0; i < N; ++i) {
+    int n = 0;
+    for (int j = 0; j < V; ++j) {
+      const double dx = uv[i * 2] - view[j].mean[0], dy = uv[i * 2 + 1] - view[j].mean[1];
+      const double d = dx * dx + dy * dy;  // nanoflann L2_Simple_Adaptor
+      if (n == num && !(d < bd[num - 1])) continue;
+      int pos = (n < num) ? n : num - 1;
+      while (pos > 0 && d < bd[pos - 1]) {
+        bd[pos] = bd[pos - 1];
+        bi[pos] = bi[pos - 1];
+        --pos;
+      }
+      bd[pos] = d;
+      bi[pos] = j;
+      if (n < num) ++n;
+    }
+    int m = 0;
+    for (int r = 0; r < n; ++r)
+      if (oracle_mdist2_2d(&view[bi[r]], &uv[i * 2]) < 9.0) cand[i * num + m++] = bi[r];  // :518-522
+    for (; m < num; ++m) cand[i * num + m] = -1;
+  }
+}
+
+void oracle_unproject3(const oracle_camera_t* cam, const double pose[7], const double uv[2], double depth, double pt_w[3]) {
+  // pinhole_camera.cpp:20-33 then getTwc().map (SE3Quat::inverse: r = conj, t = r * (t * -1))
+  const double pc[3] = {depth * (uv[0] - cam->cx) / cam->fx, depth * (uv[1] - cam->cy) / cam->fy, depth};
+  double q[4] = {pose[0], pose[1], pose[2], pose[3]};
+  quat_normalize(q);
+  const double qc[4] = {-q[0], -q[1], -q[2], q[3]};
+  const double tn[3] = {pose[4] * -1.0, pose[5] * -1.0, pose[6] * -1.0};
+  double twc[3], r[3];
+  quat_rotate(qc, tn, twc);
+  quat_rotate(qc, pc, r);
+  for (int i = 0; i < 3; ++i) pt_w[i] = r[i] + twc[i];
+}
+
+int oracle_check_map_association(const oracle_comp_t* comps, int K, const int64_t* nbr_row_ptr, const int32_t* nbr_col,
+                                 const oracle_camera_t* cam, const oracle_params_t* prm, const double pose[7],
+                                 const double obs[3], int octave, const int32_t* cand, int ncand, double pt3d[3]) {
+  // gmmloc_opt.cpp:156-258
+  int nc = 0;
+  for (int i = 0; i < ncand; ++i)
+    if (cand[i] >= 0) ++nc;
+  if (nc == 0) return -1;  // comps.empty()  :162-164
+  const double pt_init[3] = {pt3d[0], pt3d[1], pt3d[2]};
+  double q[4] = {pose[0], pose[1], pose[2], pose[3]};
+  quat_normalize(q);
+  double ptc[3];
+  quat_rotate(q, pt3d, ptc);  // Tcw.map(pt3d)
+  double proj_z = ptc[2] + pose[6];
+  proj_z = proj_z > 1.0 ? 1.0 : proj_z;  // :171
+  const double proj_z2 = proj_z * proj_z;
+  int min_idx = -1;
+  double min_value = std::numeric_limits<double>::max();
+  double min_res[3] = {0, 0, 0};
+  for (int i = 0; i < ncand; ++i) {
+    if (cand[i] < 0) continue;
+    double est[3], c2p, c2s;
+    const int res = oracle_optimize_point(pt_init, obs, octave, pose, &comps[cand[i]], proj_z2, cam, prm, 5, est, &c2p, &c2s);
+    if (res && c2p < min_value) {  // :192-196
+      min_idx = i;
+      min_value = c2p;
+      for (int r = 0; r < 3; ++r) min_res[r] = est[r];
+    }
+  }
+  if (min_idx != -1) {
+    const int g3d = cand[min_idx];
+    double ll = oracle_chi2(&comps[g3d], min_res);
+    int str = g3d;
+    for (int64_t e = nbr_row_ptr[g3d]; e < nbr_row_ptr[g3d + 1]; ++e) {  // :209-217
+      const double ln = oracle_chi2(&comps[nbr_col[e]], min_res);
+      if (ln < ll) { ll = ln; str = nbr_col[e]; }
+    }
+    if (str != g3d) {  // :219-228
+      double est[3], c2p, c2s;
+      const int res = oracle_optimize_point(pt_init, obs, octave, pose, &comps[str], proj_z2, cam, prm, 5, est, &c2p, &c2s);
+      if (res) {
+        for (int r = 0; r < 3; ++r) min_res[r] = est[r];
+      } else {
+        str = g3d;
+        ll = oracle_chi2(&comps[g3d], min_res);
+      }
+    }
+    if (ll > 9.0) return -1;  // :230-232
+    for (int r = 0; r < 3; ++r) pt3d[r] = min_res[r];
+    return str;
+  }
+  // use_nn3d (:237-256): GMM::queryPoint -> nearest mean (Euclid), result discarded except for pt3d
+  int nn = -1;
+  double best = std::numeric_limits<double>::max();
+  for (int k = 0; k < K; ++k) {
+    const double d0 = pt_init[0] - comps[k].mean[0], d1 = pt_init[1] - comps[k].mean[1], d2 = pt_init[2] - comps[k].mean[2];
+    const double d = (d0 * d0 + d1 * d1) + d2 * d2;
+    if (d < best) { best = d; nn = k; }
+  }
+  if (nn < 0 || !comps[nn].is_degenerated) return -1;
+  double est[3], c2p, c2s;
+  if (oracle_optimize_point(pt_init, obs, octave, pose, &comps[nn], proj_z2, cam, prm, 5, est, &c2p, &c2s))
+    for (int r = 0; r < 3; ++r) pt3d[r] = est[r];
+  return -1;
+}
+
+void oracle_keyframe_associate(const oracle_comp_t* comps, int K, const int64_t* nbr_row_ptr, const int32_t* nbr_col,
+                               const oracle_camera_t* cam, const oracle_params_t* prm, const double pose[7],
+                               const float* obs, const float* depth, const uint8_t* octave, int N, int num,
+                               int32_t* assoc, double* pt3d, int32_t* cand_out, int32_t* nview, int nthreads) {
+  std::vector<oracle_comp2d_t> view((size_t)K);
+  const int V = oracle_render_view(comps, K, cam, pose, view.data());  // gmmloc_opt.cpp:122-126
+  if (nview) *nview = V;
+  std::vector<double> uv(2 * (size_t)N);
+  for (int i = 0; i < N; ++i) {
+    uv[2 * i] = (double)obs[3 * i];
+    uv[2 * i + 1] = (double)obs[3 * i + 1];
+  }
+  std::vector<int32_t> cand((size_t)N * num);
+  oracle_search_correspondence(view.data(), V, uv.data(), N, num, cand.data());  // :128-134
+  for (size_t i = 0; i < cand.size(); ++i)
+    if (cand[i] >= 0) cand[i] = view[cand[i]].id;  // gc2d->parent_
+  if (cand_out) std::memcpy(cand_out, cand.data(), sizeof(int32_t) * cand.size());
+  parallel_for(N, nthreads, [&](int64_t lo, int64_t hi, int) {
+    for (int64_t i = lo; i < hi; ++i) {
+      assoc[i] = -1;
+      if (!(depth[i] > 0.0f)) {  // gmmloc_opt.cpp:42,68
+        pt3d[3 * i] = pt3d[3 * i + 1] = pt3d[3 * i + 2] = std::numeric_limits<double>::quiet_NaN();
+        continue;
+      }
+      oracle_unproject3(cam, pose, &uv[2 * i], (double)depth[i], &pt3d[3 * i]);  // :73
+      const double o[3] = {(double)obs[3 * i], (double)obs[3 * i + 1], (double)obs[3 * i + 2]};
+      assoc[i] = oracle_check_map_association(comps, K, nbr_row_ptr, nbr_col, cam, prm, pose, o, octave[i],
+                                              &cand[(size_t)i * num], num, &pt3d[3 * i]);  // :76-77
+    }
+  });
+}
+
 }  // extern "C"

@@ -128,6 +128,65 @@ void oracle_frames_solve(const oracle_comp_t* comps, int K, const oracle_camera_
                          const float* obs, const uint8_t* octave, int B, int N, double* pose_out,
                          double* pts_out, int32_t* assign, uint8_t* outlier, int32_t* status, int nthreads);
 
+/* ---- keyframe association pipeline (a5, a6, a7, a9) ---------------------------------------------- */
+
+/* a5: GaussianComponent2d as GMMUtility::projectGaussian builds it (gmm_utils.cpp:121-146, gaussian.h:107-117,
+ * gaussian.cpp:17-32).  cov is the 2x2 product J R S R^T J^T as computed (row-major, not symmetrised). */
+typedef struct {
+  int32_t id;       /* g2d->id_: index of the parent 3-D component       gaussian_mixture.cpp:319 */
+  int32_t pad_;
+  double mean[2];
+  double cov[4];
+  double cov_inv[4];
+  double det;
+  double scale[2];  /* eigenvalues ascending (gaussian.cpp:20-23) */
+  double depth;     /* proj_d_ = (R mu + t).z                             gaussian_mixture.cpp:322-325 */
+} oracle_comp2d_t;
+
+/* a5: returns 1 and fills *out iff the projected mean is KEYPOINT_VISIBLE (pinhole_camera.cpp:127-150). */
+int oracle_project_gaussian(const oracle_comp_t* c, int id, const oracle_camera_t* cam, const double pose[7],
+                            oracle_comp2d_t* out);
+/* 2-D Bhattacharyya distance (gmm_utils.h:30-52 instantiated for GaussianComponent2d). */
+double oracle_bh2(const oracle_comp2d_t* a, const oracle_comp2d_t* b);
+/* 2-D Mahalanobis distance (gaussian.h:123-126). */
+double oracle_mdist2_2d(const oracle_comp2d_t* c, const double uv[2]);
+
+/* a6: GMM::renderView(rot_c_w, t_c_w) (gaussian_mixture.cpp:271-371): view-cos cull of degenerate components
+ * (|n . ray| < cos 78 deg), projection, 2-D covariance cull (both eigenvalues < 4), greedy occlusion dedupe in
+ * ascending component order (min-BH kept neighbour; < 0.8 => the nearer one keeps the slot, else append), then
+ * sort by depth descending (std::sort in the reference; here stable, ties keep insertion order).
+ * out must hold K entries; returns the number of 2-D components. */
+int oracle_render_view(const oracle_comp_t* comps, int K, const oracle_camera_t* cam, const double pose[7],
+                       oracle_comp2d_t* out);
+
+/* a7: GMM::searchCorrespondence(kpts, comps, num) (gaussian_mixture.cpp:484-534): per keypoint the `num`
+ * nearest 2-D means (Euclid, ascending; brute force stands in for the nanoflann kd-tree, ties -> lower view
+ * position), keeping those with 2-D MDist2 < 9.0.  cand N x num: positions in the view list, -1 padded. */
+void oracle_search_correspondence(const oracle_comp2d_t* view, int V, const double* uv, int N, int num, int32_t* cand);
+
+/* a13: Frame::unproject3 (frame.cpp:27-36, pinhole_camera.cpp:20-33): pt_w = T_wc * [z (u-cx)/fx, z (v-cy)/fy, z]. */
+void oracle_unproject3(const oracle_camera_t* cam, const double pose[7], const double uv[2], double depth, double pt_w[3]);
+
+/* a9: GMMLoc::checkMapAssociation (gmmloc_opt.cpp:156-258) for one feature.  cand: 3-D component ids of the
+ * feature's 2-D candidates (KeyFrame::comps_[idx], in order), ncand of them.  nbr_row_ptr / nbr_col: CSR
+ * neighbour lists (oracle_neighbors).  pt3d is updated exactly where the reference mutates its argument
+ * (accepted association: the optimised point; kd fallback with an accepted solve: the optimised point).
+ * Returns the associated component id or -1 (nullptr). */
+int oracle_check_map_association(const oracle_comp_t* comps, int K, const int64_t* nbr_row_ptr, const int32_t* nbr_col,
+                                 const oracle_camera_t* cam, const oracle_params_t* prm, const double pose[7],
+                                 const double obs[3], int octave, const int32_t* cand, int ncand, double pt3d[3]);
+
+/* GMMLoc::associateMapElements (gmmloc_opt.cpp:115-154) + the per-feature association of
+ * createMapPointsFromStereo (:36-113) for one keyframe: render, search (num candidates), then for every
+ * feature with depth > 0: unproject3 and, when it has candidates, checkMapAssociation.
+ *  obs N x 3 (u v u_r) fp32, depth N fp32, octave N.  Outputs: assoc N (component id, -1 none), pt3d N x 3
+ *  (fp64; NaN for features without depth), cand N x num (3-D component ids, -1 padded; optional),
+ *  *nview = number of rendered 2-D components (optional).  nthreads shards the features. */
+void oracle_keyframe_associate(const oracle_comp_t* comps, int K, const int64_t* nbr_row_ptr, const int32_t* nbr_col,
+                               const oracle_camera_t* cam, const oracle_params_t* prm, const double pose[7],
+                               const float* obs, const float* depth, const uint8_t* octave, int N, int num,
+                               int32_t* assoc, double* pt3d, int32_t* cand, int32_t* nview, int nthreads);
+
 /* frame::sigma2_inv[octave] as the reference computes it in float (init_config.hpp:63-78). */
 double oracle_sigma2_inv(int octave);
 

@@ -266,3 +266,91 @@ def gmm_write(path, mean, cov, flags=None):
     rc = lib().oracle_gmm_write(str(path).encode(), _p(mean), _p(cov), _p(fl), C.c_int(mean.shape[0]))
     if rc != 0:
         raise IOError(f"oracle_gmm_write failed: {rc}")
+
+
+# ---- keyframe association pipeline (renderView / searchCorrespondence / checkMapAssociation) -------------
+COMP2D_DTYPE = np.dtype([("id", "i4"), ("pad_", "i4"), ("mean", "f8", 2), ("cov", "f8", 4), ("cov_inv", "f8", 4),
+                         ("det", "f8"), ("scale", "f8", 2), ("depth", "f8")], align=True)
+
+
+def render_view(comps, pose, cam=None) -> np.ndarray:
+    """GMM::renderView: the depth-sorted (descending) list of 2-D components of one view."""
+    cam = cam or v1_camera()
+    pose = np.ascontiguousarray(pose, np.float64)
+    out = np.zeros(len(comps), COMP2D_DTYPE)
+    L = lib()
+    L.oracle_render_view.restype = C.c_int
+    V = L.oracle_render_view(_p(comps), C.c_int(len(comps)), C.byref(cam), _p(pose), _p(out))
+    return out[:V].copy()
+
+
+def project_gaussian(comps, k, pose, cam=None):
+    cam = cam or v1_camera()
+    pose = np.ascontiguousarray(pose, np.float64)
+    out = np.zeros(1, COMP2D_DTYPE)
+    L = lib()
+    L.oracle_project_gaussian.restype = C.c_int
+    ok = L.oracle_project_gaussian(C.c_void_p(comps.ctypes.data + int(k) * COMP_DTYPE.itemsize), C.c_int(int(k)),
+                                   C.byref(cam), _p(pose), _p(out))
+    return (out[0] if ok else None)
+
+
+def bh2(view, i, j) -> float:
+    L = lib()
+    L.oracle_bh2.restype = C.c_double
+    base = view.ctypes.data
+    return L.oracle_bh2(C.c_void_p(base + int(i) * COMP2D_DTYPE.itemsize), C.c_void_p(base + int(j) * COMP2D_DTYPE.itemsize))
+
+
+def search_correspondence(view, uv, num=5) -> np.ndarray:
+    """GMM::searchCorrespondence: N x num positions in `view` (-1 padded)."""
+    view = np.ascontiguousarray(view)
+    uv = np.ascontiguousarray(uv, np.float64).reshape(-1, 2)
+    cand = np.full((uv.shape[0], num), -1, np.int32)
+    lib().oracle_search_correspondence(_p(view), C.c_int(len(view)), _p(uv), C.c_int(uv.shape[0]), C.c_int(num), _p(cand))
+    return cand
+
+
+def unproject3(pose, uv, depth, cam=None) -> np.ndarray:
+    cam = cam or v1_camera()
+    pose = np.ascontiguousarray(pose, np.float64)
+    uv = np.ascontiguousarray(uv, np.float64)
+    out = np.zeros(3)
+    lib().oracle_unproject3(C.byref(cam), _p(pose), _p(uv), C.c_double(float(depth)), _p(out))
+    return out
+
+
+def check_map_association(comps, nbr, pose, obs, octave, cand, pt3d, cam=None, prm=None):
+    """GMMLoc::checkMapAssociation for one feature: (component id or -1, pt3d after the call)."""
+    cam = cam or v1_camera()
+    prm = prm or default_params()
+    row_ptr, col = np.ascontiguousarray(nbr[0], np.int64), np.ascontiguousarray(nbr[1], np.int32)
+    pose = np.ascontiguousarray(pose, np.float64)
+    obs = np.ascontiguousarray(obs, np.float64)
+    cand = np.ascontiguousarray(cand, np.int32)
+    pt = np.array(pt3d, np.float64)
+    L = lib()
+    L.oracle_check_map_association.restype = C.c_int
+    k = L.oracle_check_map_association(_p(comps), C.c_int(len(comps)), _p(row_ptr), _p(col), C.byref(cam), C.byref(prm),
+                                       _p(pose), _p(obs), C.c_int(int(octave)), _p(cand), C.c_int(len(cand)), _p(pt))
+    return k, pt
+
+
+def keyframe_associate(comps, nbr, pose, obs, depth, octave, num=5, cam=None, prm=None, nthreads=1):
+    """associateMapElements + per-feature checkMapAssociation of one keyframe."""
+    cam = cam or v1_camera()
+    prm = prm or default_params()
+    row_ptr, col = np.ascontiguousarray(nbr[0], np.int64), np.ascontiguousarray(nbr[1], np.int32)
+    pose = np.ascontiguousarray(pose, np.float64)
+    obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 3)
+    N = obs.shape[0]
+    depth = np.ascontiguousarray(depth, np.float32)
+    octave = np.ascontiguousarray(octave, np.uint8)
+    assoc = np.zeros(N, np.int32)
+    pt3d = np.zeros((N, 3))
+    cand = np.zeros((N, num), np.int32)
+    nview = C.c_int32(0)
+    lib().oracle_keyframe_associate(_p(comps), C.c_int(len(comps)), _p(row_ptr), _p(col), C.byref(cam), C.byref(prm),
+                                    _p(pose), _p(obs), _p(depth), _p(octave), C.c_int(N), C.c_int(num), _p(assoc),
+                                    _p(pt3d), _p(cand), C.byref(nview), C.c_int(nthreads))
+    return dict(assoc=assoc, pt3d=pt3d, cand=cand, nview=nview.value)

@@ -278,3 +278,136 @@ def optimize_triangulation(x0, obs1, obs2, octave1, R1, t1, R2, t2, mu, n, w_str
         c2s = w_str * es * es
         x = x + np.linalg.solve(H, b)
     return x, errs[0], errs[1], c2s
+
+
+# ---------------------------------------------------------------- keyframe association pipeline
+# Independent NumPy restatement of renderView / searchCorrespondence / checkMapAssociation: matrix algebra
+# with numpy.linalg (eigvalsh, inv, det, argsort), no shared code with oracle/ or the CUDA kernels.
+W_IMG, H_IMG = synth.W, synth.H
+
+
+def pose_Rt(pose):
+    q = np.asarray(pose[:4], float) / np.linalg.norm(pose[:4])
+    if q[3] < 0:
+        q = -q
+    return synth.quat_to_rot(q), np.asarray(pose[4:], float)
+
+
+def project_gaussian(mean, cov, pose):
+    """(visible, mean2 (2), cov2 (2x2), depth) of one component."""
+    R, t = pose_Rt(pose)
+    pc = R @ mean + t
+    if not pc[2] > 0:
+        return False, None, None, pc[2]
+    uv = project(pc, False)
+    if not (0 <= uv[0] < W_IMG and 0 <= uv[1] < H_IMG):
+        return False, None, None, pc[2]
+    J = dproj(pc, False)
+    return True, uv, J @ R @ cov.reshape(3, 3) @ R.T @ J.T, pc[2]
+
+
+def bh(mu0, c0, mu1, c1):
+    c = 0.5 * (c0 + c1)
+    d = mu1 - mu0
+    return d @ np.linalg.inv(c) @ d / 8.0 + 0.5 * np.log(np.linalg.det(c) / np.sqrt(np.linalg.det(c0) * np.linalg.det(c1)))
+
+
+def render_view(comps, pose):
+    """list of dict(id, mean, cov, depth), depth descending."""
+    R, t = pose_Rt(pose)
+    cam_pos = -R.T @ t
+    kept = []
+    for k in range(len(comps)):
+        c = comps[k]
+        if c["is_degenerated"]:
+            po = c["mean"] - cam_pos
+            if abs(po @ c["axis"].reshape(3, 3)[:, 0]) / np.linalg.norm(po) < np.cos(np.deg2rad(78.0)):
+                continue
+        vis, m2, c2, depth = project_gaussian(c["mean"], c["cov"], pose)
+        if not vis:
+            continue
+        ev = np.linalg.eigvalsh(0.5 * (c2 + c2.T))
+        if ev[0] < 4.0 and ev[1] < 4.0:
+            continue
+        g = dict(id=k, mean=m2, cov=c2, depth=depth)
+        if kept:
+            d = np.array([bh(h["mean"], h["cov"], m2, c2) for h in kept])
+            j = int(np.argmin(d))
+            if d[j] < 0.8:
+                if depth < kept[j]["depth"]:
+                    kept[j] = g
+                continue
+        kept.append(g)
+    order = np.argsort([-g["depth"] for g in kept], kind="stable")
+    return [kept[i] for i in order]
+
+
+def search_correspondence(view, uv, num=5):
+    """N x num positions in `view` (-1 padded)."""
+    uv = np.asarray(uv, float).reshape(-1, 2)
+    out = np.full((len(uv), num), -1, np.int32)
+    if not view:
+        return out
+    means = np.array([g["mean"] for g in view])
+    for i, p in enumerate(uv):
+        d = ((p - means) ** 2).sum(1)
+        nn = np.argsort(d, kind="stable")[:num]
+        m = 0
+        for j in nn:
+            dl = p - view[j]["mean"]
+            if dl @ np.linalg.inv(view[j]["cov"]) @ dl < 9.0:
+                out[i, m] = j
+                m += 1
+    return out
+
+
+def check_map_association(comps, nbr, pose, obs, octave, cand, pt3d, tri_lambda2=400.0,
+                          tri_str_thresh=float(np.float32(0.0064))):
+    """(component id or -1, point after the call)."""
+    row_ptr, col = nbr[0], nbr[1]
+    cand = [int(c) for c in cand if c >= 0]
+    pt_init = np.array(pt3d, float)
+    if not cand:
+        return -1, pt_init
+    R, t = pose_Rt(pose)
+    obs = np.asarray(obs, float)
+    pz = min((R @ pt_init + t)[2], 1.0)
+    w_str = tri_lambda2 * pz * pz
+
+    def solve(k):
+        c = comps[k]
+        x, c2p, c2s = optimize_point(pt_init, obs, octave, R, t, c["mean"], c["axis"].reshape(3, 3)[:, 0], w_str)
+        ok = not (c2p > 7.815) and not (c2s > tri_str_thresh * tri_lambda2)
+        return ok, x, c2p
+
+    def chi2(k, x):
+        d = x - comps[k]["mean"]
+        return d @ comps[k]["cov_inv"].reshape(3, 3) @ d
+
+    best, best_v, best_x = -1, np.inf, None
+    for k in cand:
+        ok, x, c2p = solve(k)
+        if ok and c2p < best_v:
+            best, best_v, best_x = k, c2p, x
+    if best >= 0:
+        ll, s = chi2(best, best_x), best
+        for e in range(row_ptr[best], row_ptr[best + 1]):
+            ln = chi2(col[e], best_x)
+            if ln < ll:
+                ll, s = ln, int(col[e])
+        if s != best:
+            ok, x, _ = solve(s)
+            if ok:
+                best_x = x
+            else:
+                s, ll = best, chi2(best, best_x)
+        if ll > 9.0:
+            return -1, pt_init
+        return s, best_x
+    means = np.array([c["mean"] for c in comps]) if not isinstance(comps, np.ndarray) else comps["mean"]
+    nn = int(np.argmin(((pt_init - means) ** 2).sum(1)))
+    if comps[nn]["is_degenerated"]:
+        ok, x, _ = solve(nn)
+        if ok:
+            return -1, x
+    return -1, pt_init

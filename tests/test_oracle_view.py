@@ -1,0 +1,136 @@
+"""CPU tests of the oracle's keyframe association pipeline (renderView / searchCorrespondence /
+checkMapAssociation restatements) against an independent NumPy implementation (tests/np_reference.py) on the
+reference's own shipped map and recorded poses, plus known-answer properties.  The reference has no tests
+or golden vectors for these functions: parity unpinned."""
+import numpy as np
+import pytest
+
+from gmmloc_b200 import synth
+from tests import np_reference as ref
+
+
+@pytest.fixture(scope="module")
+def v1(oracle, golden_maps):
+    comps = oracle.map_build(golden_maps["v1"]["mean"], golden_maps["v1"]["cov"])
+    nbr = oracle.neighbors(comps, 2.5)
+    return comps, nbr
+
+
+def _frames(golden_maps, gt, rows, N, seed=3):
+    g = golden_maps["v1"]
+    fr = synth.make_frames(g["mean"], g["cov"], len(rows), N, seed=seed, poses_wc=gt[rows, 1:8])
+    fr["depth"] = (synth.BF / (fr["obs"][..., 0] - fr["obs"][..., 2])).astype(np.float32)
+    return fr
+
+
+def test_project_gaussian_matches_matrix_algebra(oracle, v1, golden_maps, gt_v1_03):
+    comps, _ = v1
+    fr = _frames(golden_maps, gt_v1_03, [50, 900], 8)
+    seen = 0
+    for pose in fr["pose0"]:
+        for k in range(0, len(comps), 7):
+            g = oracle.project_gaussian(comps, k, pose)
+            vis, m2, c2, depth = ref.project_gaussian(comps[k]["mean"], comps[k]["cov"], pose)
+            assert (g is not None) == vis
+            if not vis:
+                continue
+            seen += 1
+            assert g["id"] == k
+            np.testing.assert_allclose(g["mean"], m2, rtol=0, atol=1e-9)
+            np.testing.assert_allclose(g["cov"].reshape(2, 2), c2, rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(g["cov_inv"].reshape(2, 2) @ c2, np.eye(2), atol=1e-6)
+            assert g["det"] == pytest.approx(np.linalg.det(c2), rel=1e-9)
+            np.testing.assert_allclose(g["scale"], np.linalg.eigvalsh(0.5 * (c2 + c2.T)), rtol=1e-7, atol=1e-9)
+            assert g["depth"] == pytest.approx(depth, abs=1e-12)
+    assert seen > 50
+
+
+def test_bh2_known_answers(oracle, v1, golden_maps, gt_v1_03):
+    comps, _ = v1
+    fr = _frames(golden_maps, gt_v1_03, [400], 8)
+    view = oracle.render_view(comps, fr["pose0"][0])
+    assert len(view) > 20
+    for i in range(0, len(view), 9):
+        assert abs(oracle.bh2(view, i, i)) < 1e-12  # BH(g, g) = 0
+        j = (i + 5) % len(view)
+        assert oracle.bh2(view, i, j) == pytest.approx(oracle.bh2(view, j, i), rel=1e-9)  # symmetric
+        assert oracle.bh2(view, i, j) == pytest.approx(
+            ref.bh(view[i]["mean"], view[i]["cov"].reshape(2, 2), view[j]["mean"], view[j]["cov"].reshape(2, 2)), rel=1e-9)
+
+
+@pytest.mark.parametrize("row", [100, 600, 1200, 1900])
+def test_render_view_matches_numpy(oracle, v1, golden_maps, gt_v1_03, row):
+    comps, _ = v1
+    fr = _frames(golden_maps, gt_v1_03, [row], 8)
+    pose = fr["pose0"][0]
+    view = oracle.render_view(comps, pose)
+    want = ref.render_view(comps, pose)
+    assert len(view) > 50
+    assert [int(i) for i in view["id"]] == [g["id"] for g in want]
+    np.testing.assert_allclose(view["mean"], np.array([g["mean"] for g in want]), atol=1e-9)
+    np.testing.assert_allclose(view["depth"], np.array([g["depth"] for g in want]), atol=1e-12)
+    # properties of the reference's algorithm
+    assert np.all(np.diff(view["depth"]) <= 0)                       # sorted far -> near (:362-364)
+    assert len(set(view["id"].tolist())) == len(view)
+    assert np.all((view["mean"][:, 0] >= 0) & (view["mean"][:, 0] < synth.W) & (view["mean"][:, 1] >= 0) & (view["mean"][:, 1] < synth.H))
+    assert np.all(view["depth"] > 0) and np.all(view["scale"][:, 1] >= 4.0)
+
+
+def test_render_view_empty_when_nothing_is_in_front(oracle, v1):
+    comps, _ = v1
+    pose = np.array([0, 0, 0, 1, 0, 0, -100.0])  # every component 100 m behind the camera
+    assert len(oracle.render_view(comps, pose)) == 0
+
+
+@pytest.mark.parametrize("num", [1, 5, 8])
+def test_search_correspondence_matches_numpy(oracle, v1, golden_maps, gt_v1_03, num):
+    comps, _ = v1
+    fr = _frames(golden_maps, gt_v1_03, [700], 300)
+    pose = fr["pose0"][0]
+    view = oracle.render_view(comps, pose)
+    want_view = ref.render_view(comps, pose)
+    uv = fr["obs"][0, :, :2].astype(np.float64)
+    cand = oracle.search_correspondence(view, uv, num)
+    want = ref.search_correspondence(want_view, uv, num)
+    assert np.array_equal(cand, want)
+    assert (cand >= 0).any() and (cand < 0).any()
+    # empty view and fewer components than requested
+    assert np.all(oracle.search_correspondence(view[:0], uv, num) == -1)
+    few = oracle.search_correspondence(view[:2], uv, 5)
+    assert np.all(few[:, 2:] == -1)
+
+
+def test_check_map_association_matches_numpy(oracle, v1, golden_maps, gt_v1_03):
+    comps, nbr = v1
+    fr = _frames(golden_maps, gt_v1_03, [300, 1500], 250)
+    n_assoc = n_moved = n_none = 0
+    for f in range(2):
+        pose = fr["pose0"][f]
+        out = oracle.keyframe_associate(comps, nbr, pose, fr["obs"][f], fr["depth"][f], fr["octave"][f])
+        for i in range(250):
+            uv = fr["obs"][f, i, :2].astype(np.float64)
+            p0 = oracle.unproject3(pose, uv, fr["depth"][f, i])
+            Rm, t = ref.pose_Rt(pose)
+            z = float(fr["depth"][f, i])
+            pc = np.array([z * (uv[0] - synth.CX) / synth.FX, z * (uv[1] - synth.CY) / synth.FY, z])
+            np.testing.assert_allclose(p0, Rm.T @ (pc - t), atol=1e-9)  # Frame::unproject3
+            k, x = ref.check_map_association(comps, nbr, pose, fr["obs"][f, i], fr["octave"][f, i], out["cand"][i], p0)
+            assert k == out["assoc"][i], (f, i)
+            np.testing.assert_allclose(out["pt3d"][i], x, atol=1e-7)
+            n_assoc += k >= 0
+            n_none += k < 0
+            n_moved += (k < 0) and not np.allclose(x, p0)
+    assert n_assoc > 300 and n_none > 20
+
+
+def test_keyframe_associate_edge_cases(oracle, v1, golden_maps, gt_v1_03):
+    comps, nbr = v1
+    fr = _frames(golden_maps, gt_v1_03, [800], 64)
+    depth = fr["depth"][0].copy()
+    depth[::4] = -1.0  # features without a stereo match (Feature::depth = -1, feature.h:12)
+    out = oracle.keyframe_associate(comps, nbr, fr["pose0"][0], fr["obs"][0], depth, fr["octave"][0])
+    assert np.all(out["assoc"][::4] == -1) and np.all(np.isnan(out["pt3d"][::4]))
+    assert np.all(np.isfinite(out["pt3d"][1::4]))
+    # threads only shard the features
+    out2 = oracle.keyframe_associate(comps, nbr, fr["pose0"][0], fr["obs"][0], depth, fr["octave"][0], nthreads=4)
+    assert np.array_equal(out["assoc"], out2["assoc"]) and np.array_equal(out["pt3d"], out2["pt3d"], equal_nan=True)
