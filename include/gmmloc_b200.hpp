@@ -10,7 +10,11 @@
 //   GMMLoc::optimizePoint               gmmloc/include/gmmloc/gmmloc.h:43-46
 //   Tracking::optimizeCurrentPose       gmmloc/include/gmmloc/modules/tracking.h:51
 //   Localization::jointOptimization     gmmloc/include/gmmloc/modules/localization.h:61 (single free pose)
+//   GMM::renderView / getComponents2d / searchCorrespondence   gaussian_mixture.h:122,135-137,147
+//   GMMLoc::checkMapAssociation / associateMapElements          gmmloc/include/gmmloc/gmmloc.h:48-51
+//   Localization::optimizeTriangulationVec                      modules/localization.h:58-59
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <memory>
@@ -33,11 +37,24 @@ struct SE3Quat {
 };
 
 // the fields of gmmloc::Feature the hot path reads (feature.h:7-41): undistorted keypoint, right-image
-// column (< 0 => monocular) and pyramid octave
+// column (< 0 => monocular), stereo depth (<= 0: none) and pyramid octave
 struct Feature {
   double u = 0, v = 0, u_right = -1;
   int octave = 0;
+  float depth = -1.0f;
 };
+
+// gmmloc::GaussianComponent2d as renderView leaves it in GMM::components2d_ (gaussian.h:95-150): id_ is the
+// index of the parent 3-D component (parent_ in the reference), proj_d_ its camera-frame depth
+struct GaussianComponent2d {
+  uint32_t id_ = 0;
+  double proj_d_ = 0.0;
+  std::array<double, 2> mean_{};
+  std::array<double, 4> cov_{};  // row-major
+  const std::array<double, 2>& mean() const { return mean_; }
+  const std::array<double, 4>& cov() const { return cov_; }
+};
+using GaussianComponents2d = std::vector<GaussianComponent2d>;
 
 // gmmloc::StrOptStat (map.h:30-35)
 struct StrOptStat {
@@ -109,6 +126,14 @@ class GMM {
   }
   const GaussianComponent& getComponent3d(size_t idx) const { return getComponents().at(idx); }
 
+  // ≙ the nbs_ construction in GMM::GMM (gaussian_mixture.cpp:61-78, gmmmap::neighbor_dist_thresh): call once,
+  // before checkMapAssociation / associateMapElements; returns the number of neighbour pairs
+  int64_t buildNeighbors(double neighbor_dist_thresh = 2.5) {
+    int64_t n = 0;
+    check(gmmloc_map_build_neighbors(h_, neighbor_dist_thresh, &n));
+    return n;
+  }
+
   gmmloc_map_t* handle() const { return h_; }
 
  private:
@@ -128,6 +153,14 @@ struct GMMUtility {
   static bool saveGMMModel(const std::string& file_path, GMM::Ptr& model, bool /*clear_file*/ = true) {
     return model && gmmloc_map_save_gmm(model->handle(), file_path.c_str()) == GMMLOC_OK;
   }
+};
+
+// result of the batched keyframe association (one entry per feature)
+struct KeyFrameAssociation {
+  std::vector<int32_t> assoc;            // associated component index, -1 = nullptr
+  std::vector<Vector3d> pt3d;            // the (possibly optimised) world point; NaN when the feature has no depth
+  std::vector<std::vector<int>> comps;   // KeyFrame::comps_: candidate parent components per feature
+  int num_components2d = 0;              // size of the rendered view
 };
 
 struct FrameResult {
@@ -229,11 +262,120 @@ class Optimizer {
     return inliers;
   }
 
+  // ---- keyframe association (main thread of the reference, gmmloc_opt.cpp:115-258) ----------------------
+  // ≙ void GMM::renderView(const Quaterniond& rot_c_w, const Vector3d& t_c_w): the view stays on this context
+  // (the reference mutates GMM::components2d_) and is mirrored on the host for getComponents2d()
+  void renderView(const SE3Quat& Tcw) {
+    const int cap = (int)model_->countComponents();
+    int32_t count = 0, status = 0;
+    std::vector<int32_t> ids((size_t)cap);
+    std::vector<double> mean(2 * (size_t)cap), cov(4 * (size_t)cap), depth((size_t)cap);
+    check(gmmloc_render_views(ctx_, model_->handle(), &cam_, Tcw.data(), 1, cap, &count, &status, ids.data(), mean.data(),
+                              cov.data(), depth.data()));
+    components2d_.resize((size_t)count);
+    for (int j = 0; j < count; ++j) {
+      GaussianComponent2d& g = components2d_[j];
+      g.id_ = (uint32_t)ids[j];
+      g.proj_d_ = depth[j];
+      g.mean_ = {mean[2 * j], mean[2 * j + 1]};
+      g.cov_ = {cov[4 * j], cov[4 * j + 1], cov[4 * j + 2], cov[4 * j + 3]};
+    }
+  }
+  const GaussianComponents2d& getComponents2d() const { return components2d_; }
+
+  // ≙ void GMM::searchCorrespondence(const std::vector<Feature>&, std::vector<GaussianComponents2d>&, int num):
+  // comps[i] = parent component indices of feature i's candidates (KeyFrame::comps_), on the last rendered view
+  void searchCorrespondence(const std::vector<Feature>& kpts, std::vector<std::vector<int>>& comps, int num = 5) {
+    const size_t N = kpts.size();
+    std::vector<float> obs(3 * N);
+    for (size_t i = 0; i < N; ++i) { obs[3 * i] = (float)kpts[i].u; obs[3 * i + 1] = (float)kpts[i].v; obs[3 * i + 2] = (float)kpts[i].u_right; }
+    std::vector<int32_t> cand(N * (size_t)num);
+    check(gmmloc_search_correspondence(ctx_, obs.data(), 1, (int)N, num, cand.data(), nullptr));
+    comps.assign(N, {});
+    for (size_t i = 0; i < N; ++i)
+      for (int r = 0; r < num && cand[i * num + r] >= 0; ++r) comps[i].push_back(cand[i * num + r]);
+  }
+
+  // ≙ GaussianComponent::ConstPtr GMMLoc::checkMapAssociation(Vector3d& pt3d, KeyFrame*, size_t idx): returns the
+  // associated component index or -1 (nullptr); pt3d is updated where the reference mutates it
+  int checkMapAssociation(Vector3d& pt3d, const Feature& kp, const SE3Quat& Tcw, const std::vector<int>& comps) {
+    if (comps.empty()) return -1;
+    const float obs[3] = {(float)kp.u, (float)kp.v, (float)kp.u_right};
+    const uint8_t oct = (uint8_t)kp.octave;
+    std::vector<int32_t> cand(comps.begin(), comps.end());
+    int32_t assoc = -1;
+    check(gmmloc_check_map_association(ctx_, model_->handle(), &cam_, &params_, Tcw.data(), obs, &oct, cand.data(), 1, 1,
+                                       (int)cand.size(), pt3d.data(), &assoc));
+    return assoc;
+  }
+
+  // ≙ GMMLoc::associateMapElements(kf) followed by the unproject3 + checkMapAssociation of every feature with
+  // depth > 0 in GMMLoc::createMapPointsFromStereo (gmmloc_opt.cpp:36-154), one keyframe, chained on the device.
+  // The caller replays createMapPointsFromStereo's bookkeeping loop (depth order, th_depth early exit) on the result.
+  KeyFrameAssociation associateMapElements(const SE3Quat& Tcw, const std::vector<Feature>& kpts, int num = 5) {
+    const size_t N = kpts.size();
+    std::vector<float> obs(3 * N), depth(N);
+    std::vector<uint8_t> oct(N);
+    for (size_t i = 0; i < N; ++i) {
+      obs[3 * i] = (float)kpts[i].u; obs[3 * i + 1] = (float)kpts[i].v; obs[3 * i + 2] = (float)kpts[i].u_right;
+      depth[i] = kpts[i].depth;
+      oct[i] = (uint8_t)kpts[i].octave;
+    }
+    KeyFrameAssociation r;
+    r.assoc.resize(N);
+    r.pt3d.resize(N);
+    std::vector<int32_t> cand(N * (size_t)num);
+    int32_t nview = 0;
+    check(gmmloc_keyframes_associate(ctx_, model_->handle(), &cam_, &params_, Tcw.data(), obs.data(), depth.data(), oct.data(), 1,
+                                     (int)N, num, (int)model_->countComponents(), r.assoc.data(),
+                                     N ? r.pt3d[0].data() : nullptr, cand.data(), &nview, nullptr));
+    r.num_components2d = nview;
+    r.comps.assign(N, {});
+    for (size_t i = 0; i < N; ++i)
+      for (int c = 0; c < num && cand[i * num + c] >= 0; ++c) r.comps[i].push_back(cand[i * num + c]);
+    return r;
+  }
+
+  // ≙ GaussianComponent* Localization::optimizeTriangulationVec(Vector3d& x3d, KeyFrame* pKF1, idx1, idx2)
+  // (localization_opt.cpp:27-204): every DEGENERATE candidate of the two views is solved (20 GN iterations) in one
+  // launch; the accepted candidate with the smallest err1 + err2 wins (strict '<'; candidates in ascending index,
+  // the reference iterates an unordered_set).  Returns its index or -1 and updates x3d.
+  int optimizeTriangulationVec(Vector3d& x3d, const Feature& kp1, const Feature& kp2, const SE3Quat& Tcw1, const SE3Quat& Tcw2,
+                               const std::vector<int>& candidates, int iters = 20) {
+    const auto& comps = model_->getComponents();
+    std::vector<int32_t> cand;
+    for (int c : candidates)
+      if (c >= 0 && (size_t)c < comps.size() && comps[(size_t)c].is_degenerated) cand.push_back(c);
+    std::sort(cand.begin(), cand.end());
+    cand.erase(std::unique(cand.begin(), cand.end()), cand.end());
+    const size_t M = cand.size();
+    if (M == 0) return -1;
+    std::vector<double> x0(3 * M), p1(7 * M), p2(7 * M), est(3 * M), e1(M), e2(M), cs(M);
+    std::vector<float> o1(3 * M), o2(3 * M);
+    std::vector<uint8_t> oc(M, (uint8_t)kp1.octave), res(M);
+    for (size_t i = 0; i < M; ++i) {
+      for (int j = 0; j < 3; ++j) x0[3 * i + j] = x3d[j];
+      for (int j = 0; j < 7; ++j) { p1[7 * i + j] = Tcw1.v[j]; p2[7 * i + j] = Tcw2.v[j]; }
+      o1[3 * i] = (float)kp1.u; o1[3 * i + 1] = (float)kp1.v; o1[3 * i + 2] = (float)kp1.u_right;
+      o2[3 * i] = (float)kp2.u; o2[3 * i + 1] = (float)kp2.v; o2[3 * i + 2] = (float)kp2.u_right;
+    }
+    check(gmmloc_triangulation_solve(ctx_, model_->handle(), &cam_, &params_, x0.data(), o1.data(), o2.data(), oc.data(), p1.data(),
+                                     p2.data(), cand.data(), (int)M, iters, est.data(), e1.data(), e2.data(), cs.data(), res.data()));
+    int best = -1;
+    double best_v = 1.7976931348623157e308;
+    for (size_t i = 0; i < M; ++i)
+      if (res[i] && e1[i] + e2[i] < best_v) { best = (int)i; best_v = e1[i] + e2[i]; }
+    if (best < 0) return -1;
+    x3d = {est[3 * best], est[3 * best + 1], est[3 * best + 2]};
+    return cand[(size_t)best];
+  }
+
  private:
   GMM::Ptr model_;
   gmmloc_camera_t cam_;
   gmmloc_params_t params_;
   gmmloc_ctx_t* ctx_ = nullptr;
+  GaussianComponents2d components2d_;
 };
 
 }  // namespace gmmloc_b200

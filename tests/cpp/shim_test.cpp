@@ -100,6 +100,52 @@ int main(int argc, char** argv) {
   REQUIRE(inl == N && std::fabs(T1.v[4]) < 1e-4 && std::fabs(T1.v[5]) < 1e-4);
   REQUIRE(opt.optimizeCurrentPose(T1, P.data(), O.data(), oct.data(), 2) == 0);
 
+  // keyframe association: render the room from the origin, search candidates for a keypoint on wall component 5,
+  // associate it (the structure edge pulls the unprojected point onto the wall z = 3)
+  REQUIRE(gmm->buildNeighbors(2.5) >= 0);
+  opt.renderView(Tcw);
+  const GaussianComponents2d& v2d = opt.getComponents2d();
+  REQUIRE(!v2d.empty() && v2d.size() <= (size_t)K);
+  for (size_t j = 1; j < v2d.size(); ++j) REQUIRE(v2d[j - 1].proj_d_ >= v2d[j].proj_d_);  // far -> near
+  bool saw5 = false;
+  for (const auto& g2 : v2d) {
+    REQUIRE(g2.id_ < (uint32_t)K && g2.mean()[0] >= 0 && g2.mean()[0] < 752 && g2.mean()[1] >= 0 && g2.mean()[1] < 480);
+    if (g2.id_ == 5) {
+      saw5 = true;
+      REQUIRE(std::fabs(g2.proj_d_ - 3.0) < 1e-12);
+      REQUIRE(std::fabs(g2.mean()[0] - (cam.fx * mean[15] / 3.0 + cam.cx)) < 1e-9);
+      const double jz = cam.fx * mean[15] / 9.0;  // J S J^T of a fronto-parallel patch: (fx/z)^2 s_x + (fx x/z^2)^2 s_z
+      REQUIRE(std::fabs(g2.cov()[0] - (cam.fx * cam.fx * 1e-2 / 9.0 + jz * jz * 1e-6)) < 1e-6);
+    }
+  }
+  REQUIRE(saw5);
+  Feature kf_kp = kp;
+  kf_kp.depth = (float)(X[2] + 0.04);  // stereo depth 4 cm too deep
+  kf_kp.u_right = kf_kp.u - cam.bf / (X[2] + 0.04);
+  std::vector<std::vector<int>> comps2;
+  opt.searchCorrespondence({kf_kp}, comps2);
+  REQUIRE(comps2.size() == 1 && !comps2[0].empty() && comps2[0][0] == 5);  // nearest 2-D mean first
+  Vector3d p3{X[0] * (X[2] + 0.04) / X[2], X[1] * (X[2] + 0.04) / X[2], X[2] + 0.04};  // unproject3 at the identity pose
+  const int as = opt.checkMapAssociation(p3, kf_kp, Tcw, comps2[0]);
+  REQUIRE(as == 5 && std::fabs(p3[2] - 3.0) < 5e-3);  // pulled from z = 3.04 onto the wall
+  REQUIRE(opt.checkMapAssociation(p3, kf_kp, Tcw, {}) == -1);
+  Feature nodepth = kf_kp;
+  nodepth.depth = -1.0f;
+  KeyFrameAssociation ka = opt.associateMapElements(Tcw, {kf_kp, nodepth});
+  REQUIRE(ka.num_components2d == (int)v2d.size() && ka.assoc[0] == 5 && ka.assoc[1] == -1);
+  REQUIRE(std::fabs(ka.pt3d[0][2] - 3.0) < 5e-3 && std::isnan(ka.pt3d[1][0]) && ka.comps[0] == comps2[0]);
+
+  // two-view triangulation against candidate planes: the right wall component wins, the point lands on z = 3
+  SE3Quat Tcw2;
+  Tcw2.v[4] = -0.2;  // second keyframe 20 cm to the right
+  Feature kp2;
+  kp2.u = cam.fx * (X[0] - 0.2) / X[2] + cam.cx;
+  kp2.v = kp.v;
+  kp2.u_right = -1;  // monocular in view 2
+  Vector3d x3{X[0], X[1], X[2] + 0.03};
+  const int tri = opt.optimizeTriangulationVec(x3, kp, kp2, Tcw, Tcw2, {5, 20, 5, -1});
+  REQUIRE(tri == 5 && std::fabs(x3[2] - 3.0) < 2e-3);
+
   // .gmm round trip through GMMUtility
   if (argc > 1) {
     GMM::Ptr g2;
