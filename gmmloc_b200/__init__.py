@@ -355,6 +355,41 @@ class Context:
                                                          _ptr(out["vstatus"])))
         return out
 
+    def jointOptimization(self, gmm: GMM, windows, cam: Camera | None = None, params: Params | None = None):
+        """Batched Localization::jointOptimization (local BA, 3-stage LM; localization_opt.cpp:456-925).
+        `windows`: list of dicts with pose P x 7, fixed P, pts L x 3, assoc L, obs_pt / obs_kf E (window-local,
+        obs_pt non-decreasing), obs E x 3, octave E and optionally prior_idx.  Returns one dict per window:
+        pose, pts, obs_outlier, assoc_cleared, iters (3), status."""
+        cam = cam or v1_camera()
+        params = params or default_params()
+        B = len(windows)
+        cat = lambda k, dt, shape: (np.concatenate([_in(w[k], dt, shape) for w in windows]) if B else np.zeros((0,) + shape[1:], dt))
+        pose = np.ascontiguousarray(cat("pose", np.float64, (-1, 7)))
+        fixed = np.ascontiguousarray(cat("fixed", np.uint8, (-1,)))
+        pts = np.ascontiguousarray(cat("pts", np.float64, (-1, 3)))
+        assoc = np.ascontiguousarray(cat("assoc", np.int32, (-1,)))
+        obs_pt = np.ascontiguousarray(cat("obs_pt", np.int32, (-1,)))
+        obs_kf = np.ascontiguousarray(cat("obs_kf", np.int32, (-1,)))
+        obs = np.ascontiguousarray(cat("obs", np.float32, (-1, 3)))
+        octave = np.ascontiguousarray(cat("octave", np.uint8, (-1,)))
+        ptr = lambda k: np.concatenate([[0], np.cumsum([len(np.asarray(w[k]).reshape(len(w[k]), -1)) for w in windows])]).astype(np.int32)
+        pose_ptr, pt_ptr, obs_ptr = ptr("pose"), ptr("pts"), ptr("obs_pt")
+        prior = np.array([int(w.get("prior_idx", -1)) for w in windows], np.int32)
+        outl = np.zeros(len(obs_pt), np.uint8)
+        cleared = np.zeros(len(pts), np.uint8)
+        iters = np.zeros((B, 3), np.int32)
+        status = np.zeros(B, np.int32)
+        capi.check(capi.lib().gmmloc_local_ba(self._h, gmm._h, C.byref(cam), C.byref(params), B, _ptr(pose_ptr), _ptr(pose),
+                                              _ptr(fixed), _ptr(prior), _ptr(pt_ptr), _ptr(pts), _ptr(assoc), _ptr(obs_ptr),
+                                              _ptr(obs_pt), _ptr(obs_kf), _ptr(obs), _ptr(octave), _ptr(outl), _ptr(cleared),
+                                              _ptr(iters), _ptr(status)))
+        out = []
+        for b in range(B):
+            out.append(dict(pose=pose[pose_ptr[b]:pose_ptr[b + 1]], pts=pts[pt_ptr[b]:pt_ptr[b + 1]],
+                            obs_outlier=outl[obs_ptr[b]:obs_ptr[b + 1]], assoc_cleared=cleared[pt_ptr[b]:pt_ptr[b + 1]],
+                            iters=iters[b], status=int(status[b])))
+        return out
+
     # ---- device entry points (raw device pointers, enqueue only) ----
     def associate_async(self, gmm: GMM, d_pts: int, M: int, gate: float, d_assign: int, d_d2: int = 0) -> None:
         capi.check(capi.lib().gmmloc_associate_async(self._h, gmm._h, d_pts, int(M), float(gate), d_assign, d_d2 or None))

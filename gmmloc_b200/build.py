@@ -31,6 +31,7 @@ SOURCES = {
     "assoc_scan.cu": [],
     "frame_gn.cu": [],
     "pose_lm.cu": [],
+    "local_ba.cu": [],
     "point_gn.cu": ["-fmad=false"],
     "view.cu": ["-fmad=false"],
 }

@@ -77,6 +77,7 @@ SYMBOLS = {
     "gmmloc_search_correspondence": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "gmmloc_check_map_association": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i, _i, _vp, _vp]),
     "gmmloc_keyframes_associate": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i, _i, _i] + [_vp] * 5),
+    "gmmloc_local_ba": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params), _i] + [_vp] * 16),
     "gmmloc_points_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 6 + [_i, _i] + [_vp] * 4),
 }
 

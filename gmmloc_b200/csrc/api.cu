@@ -1196,4 +1196,179 @@ gmmloc_status_t gmmloc_keyframes_associate(gmmloc_ctx_t* ctx, const gmmloc_map_t
   return GMMLOC_OK;
 }
 
+// ---- local bundle adjustment ------------------------------------------------------------------------
+gmmloc_status_t gmmloc_local_ba(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                const gmmloc_params_t* params, int B, const int32_t* pose_ptr, double* pose, const uint8_t* fixed,
+                                const int32_t* prior_idx, const int32_t* pt_ptr, double* pts, const int32_t* assoc,
+                                const int32_t* obs_ptr, const int32_t* obs_pt, const int32_t* obs_kf, const float* obs,
+                                const uint8_t* octave, uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters,
+                                int32_t* status) {
+  if (!ctx || !map || !cam || !params || B < 0) return fail(GMMLOC_EINVAL, "gmmloc_local_ba: bad argument");
+  if (B == 0) return GMMLOC_OK;
+  if (!pose_ptr || !pose || !fixed || !pt_ptr || !pts || !assoc || !obs_ptr || !obs_pt || !obs_kf || !obs || !octave)
+    return fail(GMMLOC_EINVAL, "gmmloc_local_ba: null pointer");
+  if (map->device != ctx->device) return fail(GMMLOC_EINVAL, "map and context live on different devices");
+  const long long sumP = pose_ptr[B] - pose_ptr[0], sumL = pt_ptr[B] - pt_ptr[0], sumE = obs_ptr[B] - obs_ptr[0];
+  if (pose_ptr[0] != 0 || pt_ptr[0] != 0 || obs_ptr[0] != 0) return fail(GMMLOC_EINVAL, "gmmloc_local_ba: *_ptr[0] must be 0");
+  // ---- host-side graph preparation (the reference builds a g2o hyper-graph here, :528-766) ----
+  std::vector<BaProb> prob((size_t)B);
+  std::vector<int32_t> fidx((size_t)sumP), h_pt_ptr((size_t)(sumL + B)), h_kf_ptr, h_kf_obs, h_blk_ptr;
+  std::vector<int2> h_contrib;
+  long long free_off = 0, S_off = 0;
+  for (int b = 0; b < B; ++b) {
+    BaProb& d = prob[b];
+    const long long p0 = pose_ptr[b], l0 = pt_ptr[b], e0 = obs_ptr[b];
+    d.P = (int)(pose_ptr[b + 1] - p0);
+    d.L = (int)(pt_ptr[b + 1] - l0);
+    d.E = (int)(obs_ptr[b + 1] - e0);
+    if (d.P < 0 || d.L < 0 || d.E < 0) return fail(GMMLOC_EINVAL, "gmmloc_local_ba: *_ptr must be non-decreasing");
+    d.pose_off = p0; d.pt_off = l0; d.obs_off = e0;
+    d.prior = prior_idx ? prior_idx[b] : -1;
+    if (d.prior >= d.P || d.prior < -1) return fail(GMMLOC_EINVAL, "gmmloc_local_ba: prior_idx out of range");
+    d.nf = 0;
+    for (int i = 0; i < d.P; ++i) fidx[p0 + i] = fixed[p0 + i] ? -1 : d.nf++;
+    d.n = 6 * d.nf;
+    d.free_off = free_off;
+    d.S_off = S_off;
+    for (int l = 0; l < d.L; ++l)
+      if (assoc[l0 + l] >= map->d.K) return fail(GMMLOC_EINVAL, "gmmloc_local_ba: assoc out of range");
+    // CSR of the observations of every point (obs_pt non-decreasing)
+    int32_t* pp = &h_pt_ptr[(size_t)(l0 + b)];
+    int e = 0;
+    for (int l = 0; l <= d.L; ++l) {
+      while (e < d.E && obs_pt[e0 + e] < l) ++e;
+      pp[l] = e;
+    }
+    for (int q = 0; q < d.E; ++q) {
+      const int l = obs_pt[e0 + q], i = obs_kf[e0 + q];
+      if (l < 0 || l >= d.L || i < 0 || i >= d.P) return fail(GMMLOC_EINVAL, "gmmloc_local_ba: observation index out of range");
+      if (q > 0 && l < obs_pt[e0 + q - 1]) return fail(GMMLOC_EINVAL, "gmmloc_local_ba: obs_pt must be non-decreasing inside a window");
+    }
+    // observations of every free pose
+    d.kfo_off = (long long)h_kf_obs.size();
+    std::vector<int32_t> cnt((size_t)d.nf + 1, 0);
+    for (int q = 0; q < d.E; ++q) {
+      const int f = fidx[p0 + obs_kf[e0 + q]];
+      if (f >= 0) ++cnt[(size_t)f + 1];
+    }
+    for (int f = 0; f < d.nf; ++f) cnt[(size_t)f + 1] += cnt[f];
+    h_kf_ptr.insert(h_kf_ptr.end(), cnt.begin(), cnt.end());
+    const size_t kbase = h_kf_obs.size();
+    h_kf_obs.resize(kbase + (size_t)cnt[d.nf]);
+    {
+      std::vector<int32_t> cur(cnt.begin(), cnt.end() - 1);
+      for (int q = 0; q < d.E; ++q) {
+        const int f = fidx[p0 + obs_kf[e0 + q]];
+        if (f >= 0) h_kf_obs[kbase + (size_t)cur[f]++] = q;
+      }
+    }
+    // Schur contributions, grouped by lower block (fi >= fj), point order kept inside a block
+    const int nblk = d.nf * (d.nf + 1) / 2;
+    d.blk_off = (long long)h_blk_ptr.size();
+    d.c_off = (long long)h_contrib.size();
+    std::vector<int32_t> bc((size_t)nblk + 1, 0);
+    for (int pass = 0; pass < 2; ++pass) {
+      std::vector<int32_t> cur;
+      if (pass == 1) {
+        for (int k = 0; k < nblk; ++k) bc[(size_t)k + 1] += bc[k];
+        h_blk_ptr.insert(h_blk_ptr.end(), bc.begin(), bc.end());
+        h_contrib.resize((size_t)d.c_off + (size_t)bc[nblk]);
+        cur.assign(bc.begin(), bc.end() - 1);
+      }
+      for (int l = 0; l < d.L; ++l)
+        for (int qa = pp[l]; qa < pp[l + 1]; ++qa) {
+          const int fa = fidx[p0 + obs_kf[e0 + qa]];
+          if (fa < 0) continue;
+          for (int qb = pp[l]; qb < pp[l + 1]; ++qb) {
+            const int fb = fidx[p0 + obs_kf[e0 + qb]];
+            if (fb < 0 || fb > fa) continue;
+            const int blk = fa * (fa + 1) / 2 + fb;
+            if (pass == 0) ++bc[(size_t)blk + 1];
+            else h_contrib[(size_t)d.c_off + (size_t)cur[blk]++] = make_int2(qa, qb);
+          }
+        }
+    }
+    free_off += d.nf;
+    S_off += (long long)d.n * d.n + 3LL * d.n;
+  }
+  // ---- device staging ----
+  CU(cudaSetDevice(ctx->device));
+  ctx->active = 0;
+  cudaStream_t st = ctx->L().stream;
+  const int ows = local_ba_obs_ws(), pws = local_ba_pt_ws(), qws = local_ba_pose_ws(), fws = local_ba_free_ws();
+  struct Slab { size_t off, bytes; };
+  size_t total = 0;
+  auto take = [&](size_t bytes) { Slab s{total, bytes}; total += (bytes + 255) / 256 * 256; return s; };
+  const Slab s_prob = take(sizeof(BaProb) * (size_t)B), s_pose = take(56 * (size_t)sumP), s_fidx = take(4 * (size_t)sumP),
+             s_pts = take(24 * (size_t)sumL), s_assoc = take(4 * (size_t)sumL), s_opt = take(4 * (size_t)sumE),
+             s_okf = take(4 * (size_t)sumE), s_obs = take(12 * (size_t)sumE), s_oct = take((size_t)sumE),
+             s_ptp = take(4 * h_pt_ptr.size()), s_kfp = take(4 * h_kf_ptr.size()), s_kfo = take(4 * h_kf_obs.size() + 4),
+             s_blk = take(4 * h_blk_ptr.size()), s_con = take(8 * h_contrib.size() + 8),
+             s_wo = take(8 * (size_t)ows * (size_t)sumE), s_lvl = take((size_t)sumE), s_wp = take(8 * (size_t)pws * (size_t)sumL),
+             s_slv = take((size_t)sumL), s_wq = take(8 * (size_t)qws * (size_t)sumP), s_wf = take(8 * (size_t)fws * (size_t)free_off + 8),
+             s_S = take(8 * (size_t)S_off + 8), s_out = take((size_t)sumE), s_clr = take((size_t)sumL), s_it = take(12 * (size_t)B),
+             s_st = take(4 * (size_t)B);
+  CU(ctx->in_misc.reserve(total));
+  char* base = ctx->in_misc.as<char>();
+  auto up = [&](const Slab& s, const void* src, size_t bytes) {
+    return bytes ? cudaMemcpyAsync(base + s.off, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+  };
+  CU(up(s_prob, prob.data(), sizeof(BaProb) * (size_t)B));
+  CU(up(s_pose, pose, 56 * (size_t)sumP));
+  CU(up(s_fidx, fidx.data(), 4 * (size_t)sumP));
+  CU(up(s_pts, pts, 24 * (size_t)sumL));
+  CU(up(s_assoc, assoc, 4 * (size_t)sumL));
+  CU(up(s_opt, obs_pt, 4 * (size_t)sumE));
+  CU(up(s_okf, obs_kf, 4 * (size_t)sumE));
+  CU(up(s_obs, obs, 12 * (size_t)sumE));
+  CU(up(s_oct, octave, (size_t)sumE));
+  CU(up(s_ptp, h_pt_ptr.data(), 4 * h_pt_ptr.size()));
+  CU(up(s_kfp, h_kf_ptr.data(), 4 * h_kf_ptr.size()));
+  CU(up(s_kfo, h_kf_obs.data(), 4 * h_kf_obs.size()));
+  CU(up(s_blk, h_blk_ptr.data(), 4 * h_blk_ptr.size()));
+  CU(up(s_con, h_contrib.data(), 8 * h_contrib.size()));
+  BaArgs a;
+  a.prob = reinterpret_cast<const BaProb*>(base + s_prob.off);
+  a.B = B;
+  a.mean = map->d.mean;
+  a.axis = map->d.axis;
+  a.sqrt_info = map->d.sqrt_info;
+  a.is_deg = map->d.is_deg;
+  fill_params(cam, params, a.prm);
+  a.pose = reinterpret_cast<double*>(base + s_pose.off);
+  a.fidx = reinterpret_cast<const int32_t*>(base + s_fidx.off);
+  a.pts = reinterpret_cast<double*>(base + s_pts.off);
+  a.assoc = reinterpret_cast<const int32_t*>(base + s_assoc.off);
+  a.obs_pt = reinterpret_cast<const int32_t*>(base + s_opt.off);
+  a.obs_kf = reinterpret_cast<const int32_t*>(base + s_okf.off);
+  a.obs = reinterpret_cast<const float*>(base + s_obs.off);
+  a.octave = reinterpret_cast<const uint8_t*>(base + s_oct.off);
+  a.pt_ptr = reinterpret_cast<const int32_t*>(base + s_ptp.off);
+  a.kf_ptr = reinterpret_cast<const int32_t*>(base + s_kfp.off);
+  a.kf_obs = reinterpret_cast<const int32_t*>(base + s_kfo.off);
+  a.blk_ptr = reinterpret_cast<const int32_t*>(base + s_blk.off);
+  a.contrib = reinterpret_cast<const int2*>(base + s_con.off);
+  a.w_obs = reinterpret_cast<double*>(base + s_wo.off);
+  a.level = reinterpret_cast<uint8_t*>(base + s_lvl.off);
+  a.w_pt = reinterpret_cast<double*>(base + s_wp.off);
+  a.str_level = reinterpret_cast<uint8_t*>(base + s_slv.off);
+  a.w_pose = reinterpret_cast<double*>(base + s_wq.off);
+  a.w_free = reinterpret_cast<double*>(base + s_wf.off);
+  a.S = reinterpret_cast<double*>(base + s_S.off);
+  a.obs_outlier = reinterpret_cast<uint8_t*>(base + s_out.off);
+  a.assoc_cleared = reinterpret_cast<uint8_t*>(base + s_clr.off);
+  a.iters = reinterpret_cast<int32_t*>(base + s_it.off);
+  a.status = reinterpret_cast<int32_t*>(base + s_st.off);
+  CU(launch_local_ba(a, st));
+  ctx->stats.kernel_launches += 1;
+  CU(cudaMemcpyAsync(pose, base + s_pose.off, 56 * (size_t)sumP, cudaMemcpyDeviceToHost, st));
+  if (sumL) CU(cudaMemcpyAsync(pts, base + s_pts.off, 24 * (size_t)sumL, cudaMemcpyDeviceToHost, st));
+  if (obs_outlier && sumE) CU(cudaMemcpyAsync(obs_outlier, base + s_out.off, (size_t)sumE, cudaMemcpyDeviceToHost, st));
+  if (assoc_cleared && sumL) CU(cudaMemcpyAsync(assoc_cleared, base + s_clr.off, (size_t)sumL, cudaMemcpyDeviceToHost, st));
+  if (iters) CU(cudaMemcpyAsync(iters, base + s_it.off, 12 * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (status) CU(cudaMemcpyAsync(status, base + s_st.off, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
+  return GMMLOC_OK;
+}
+
 }  // extern "C"

@@ -194,6 +194,52 @@ struct CheckArgs {
 };
 cudaError_t launch_check_assoc(const CheckArgs& a, cudaStream_t stream);
 
+// ---- local bundle adjustment (local_ba.cu) ------------------------------------------------------------
+struct BaProb {
+  int P, L, E, nf, n;  // poses, points, observations, free poses, n = 6 nf
+  int prior;           // local index of the pose carrying the EdgeSE3QuatPrior, or -1
+  long long pose_off, pt_off, obs_off, free_off;  // element offsets of this window in the flattened arrays
+  long long kfo_off, blk_off, c_off, S_off;       // pose-observation lists, block pointers, contributions, S workspace
+};
+struct BaArgs {
+  const BaProb* prob;
+  int B;
+  const double* mean;       // map constants
+  const double* axis;
+  const double* sqrt_info;
+  const uint8_t* is_deg;
+  FrameParamsDev prm;
+  double* pose;             // sum P x 7 (in/out)
+  const int32_t* fidx;      // sum P: free index or -1
+  double* pts;              // sum L x 3 (in/out)
+  const int32_t* assoc;     // sum L
+  const int32_t* obs_pt;    // sum E (window-local point index, non-decreasing)
+  const int32_t* obs_kf;    // sum E (window-local pose index)
+  const float* obs;         // sum E x 3
+  const uint8_t* octave;    // sum E
+  const int32_t* pt_ptr;    // sum (L + 1): CSR of the observations of every point
+  const int32_t* kf_ptr;    // sum (nf + 1): CSR of the observations of every free pose ...
+  const int32_t* kf_obs;    // ... and their (window-local) observation indices
+  const int32_t* blk_ptr;   // per window nf (nf + 1) / 2 + 1: CSR of the Schur contributions of every lower block
+  const int2* contrib;      // (observation on pose fi, observation on pose fj) of one point, fi >= fj
+  double* w_obs;            // workspaces
+  uint8_t* level;
+  double* w_pt;
+  uint8_t* str_level;
+  double* w_pose;
+  double* w_free;
+  double* S;
+  uint8_t* obs_outlier;     // outputs (optional)
+  uint8_t* assoc_cleared;
+  int32_t* iters;           // B x 3
+  int32_t* status;          // B
+};
+cudaError_t launch_local_ba(const BaArgs& a, cudaStream_t stream);
+int local_ba_obs_ws();
+int local_ba_pt_ws();
+int local_ba_pose_ws();
+int local_ba_free_ws();
+
 // ---- exact (non-contracted) fp64 helpers: the re-rank and the map build must replay the CPU
 // oracle's operation order bit for bit, so every product and sum is an explicit IEEE rn op. ----
 __device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }

@@ -264,3 +264,68 @@ def make_triangulation_problems(mean, cov, M: int, seed: int = 0, mono_frac: flo
             out["comp"][i] = k
             i += 1
     return out
+
+
+def make_ba_problem(mean, cov, n_kf: int = 6, n_fixed: int = 2, n_pts: int = 300, seed: int = 0, mono_frac: float = 0.2,
+                    outlier_frac: float = 0.03, wrong_assoc_frac: float = 0.05, assoc_frac: float = 0.8):
+    """A local-BA window (Localization::jointOptimization): n_kf keyframes along a short trajectory looking at the
+    same part of the map (the last n_fixed are "fixed_kfs"), n_pts map points drawn from visible components and
+    observed where visible.  Returns dict(pose P x 7 initial T_cw (free ones perturbed ~0.5 deg / 2 cm), pose_gt,
+    fixed P u8, pts L x 3 initial (true + 2 cm), pts_gt, assoc L i32, obs_pt / obs_kf E i32 (sorted by point),
+    obs E x 3 f32, octave E u8)."""
+    mean = np.asarray(mean, np.float64).reshape(-1, 3)
+    cov = np.asarray(cov, np.float64).reshape(-1, 3, 3)
+    rng = _rng(6, seed)
+    Lc = np.linalg.cholesky(cov)
+    while True:
+        R_wc, t_wc = _sample_pose(rng)
+        R0 = R_wc.T
+        t0 = -R0 @ t_wc
+        mc = mean @ R0.T + t0
+        vis = np.flatnonzero((mc[:, 2] > Z_NEAR + 0.3) & (mc[:, 2] < Z_FAR) & (np.abs(mc[:, 0] / mc[:, 2]) < 0.6) &
+                             (np.abs(mc[:, 1] / mc[:, 2]) < 0.4))
+        if vis.size >= 8:
+            break
+    poses_gt = []
+    for j in range(n_kf):  # a short arc: ~8 cm and ~1.5 deg per keyframe
+        xi = np.concatenate([rng.normal(size=3) * np.deg2rad(1.5), rng.normal(size=3) * 0.08]) * j
+        dR, dt = _se3_exp(xi)
+        poses_gt.append((dR @ R0, dR @ t0 + dt))
+    k = vis[rng.integers(0, vis.size, n_pts)]
+    pts_gt = mean[k] + np.einsum("nij,nj->ni", Lc[k], rng.normal(size=(n_pts, 3)))
+    assoc = np.where(rng.random(n_pts) < assoc_frac, k, -1).astype(np.int32)
+    wrong = (rng.random(n_pts) < wrong_assoc_frac) & (assoc >= 0)
+    assoc[wrong] = rng.integers(0, mean.shape[0], int(wrong.sum()))
+    obs_pt, obs_kf, obs, octave = [], [], [], []
+    for l in range(n_pts):
+        for j, (R, t) in enumerate(poses_gt):
+            pc = R @ pts_gt[l] + t
+            if pc[2] < 0.3:
+                continue
+            oc = int(rng.integers(0, 8))
+            sig = 1.2 ** oc
+            u = FX * pc[0] / pc[2] + CX + rng.normal() * sig
+            v = FY * pc[1] / pc[2] + CY + rng.normal() * sig
+            if not (0 <= u < W and 0 <= v < H) or rng.random() < 0.15:
+                continue
+            ur = u - BF / pc[2] + rng.normal() * 0.25 if rng.random() >= mono_frac else -1.0
+            if rng.random() < outlier_frac:
+                u += rng.normal() * 25.0
+                v += rng.normal() * 25.0
+            obs_pt.append(l); obs_kf.append(j); obs.append((u, v, ur)); octave.append(oc)
+    P = n_kf
+    pose = np.empty((P, 7))
+    pose_gt = np.empty((P, 7))
+    fixed = np.zeros(P, np.uint8)
+    fixed[P - n_fixed:] = 1
+    for j, (R, t) in enumerate(poses_gt):
+        pose_gt[j, :4], pose_gt[j, 4:] = rot_to_quat(R), t
+        if fixed[j]:
+            pose[j] = pose_gt[j]
+        else:
+            dR, dt = _se3_exp(np.concatenate([rng.normal(size=3) * np.deg2rad(0.5), rng.normal(size=3) * 0.02]))
+            pose[j, :4], pose[j, 4:] = rot_to_quat(dR @ R), dR @ t + dt
+    pts = pts_gt + rng.normal(size=pts_gt.shape) * 0.02
+    return dict(pose=pose, pose_gt=pose_gt, fixed=fixed, pts=pts, pts_gt=pts_gt, assoc=assoc,
+                obs_pt=np.asarray(obs_pt, np.int32), obs_kf=np.asarray(obs_kf, np.int32),
+                obs=np.asarray(obs, np.float32).reshape(-1, 3), octave=np.asarray(octave, np.uint8))

@@ -262,6 +262,31 @@ GMMLOC_API gmmloc_status_t gmmloc_keyframes_associate(gmmloc_ctx_t* ctx, const g
                                                       int cap, int32_t* assoc, double* pt3d, int32_t* cand,
                                                       int32_t* nview, int32_t* vstatus);
 
+/* ---- local bundle adjustment: replaces Localization::jointOptimization (localization_opt.cpp:456-925) for B
+ * independent covisibility windows (the reference solves one per new keyframe on the localisation thread).
+ * g2o Levenberg-Marquardt with BlockSolver_6_3 (Schur complement over the map points), stages optimize(5) /
+ * optimize(5) / optimize(40) with the reference's gating: degenerate structure edges with chi2 > tri_str_thresh *
+ * ba_lambda2 leave after stage 1 (:774-786); reprojection edges with chi2 > 5.991 (mono) / 7.815 (stereo) or
+ * non-positive depth leave after stage 2, when the Huber kernels are dropped (:797-823).
+ * Window b owns poses [pose_ptr[b], pose_ptr[b+1]), points [pt_ptr[b], pt_ptr[b+1]) and observations
+ * [obs_ptr[b], obs_ptr[b+1]); obs_pt / obs_kf are window-local indices and obs_pt must be non-decreasing inside a
+ * window (observations grouped by point, the order of the reference's loop over local_mappts, :642-766).
+ *  pose sum P x 7 in/out (T_cw; fixed[i] != 0: setFixed(true), i.e. the fixed_kfs and keyframe 0 without
+ *  ba_first_as_prior; fixed poses are only normalised);  prior_idx B (optional): window-local pose that carries the
+ *  EdgeSE3QuatPrior of :560-578 (measurement = its initial estimate, sigma_rot 2 deg, sigma_t 1 cm), -1 = none;
+ *  pts sum L x 3 in/out (fp64);  assoc sum L: MapPoint::asscociations_ as a component index, -1 = none
+ *  (EdgePt2GaussianDeg with information ba_lambda2 for degenerate components, EdgePt2Gaussian otherwise);
+ *  obs sum E x 3 (u v u_r; u_r < 0 => EdgeSE3ProjectXYZ, else EdgeStereoSE3ProjectXYZ), octave sum E.
+ * Outputs (optional): obs_outlier sum E (the vToErase test, :857-881), assoc_cleared sum L (associations the
+ * reference clears, :842-855), iters B x 3 (LM iterations run per stage), status B (GMMLOC_FRAME_NUMERIC when a
+ * linear solve failed inside the LM loop; g2o carries on, and so does this). */
+GMMLOC_API gmmloc_status_t gmmloc_local_ba(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                           const gmmloc_params_t* params, int B, const int32_t* pose_ptr, double* pose,
+                                           const uint8_t* fixed, const int32_t* prior_idx, const int32_t* pt_ptr, double* pts,
+                                           const int32_t* assoc, const int32_t* obs_ptr, const int32_t* obs_pt,
+                                           const int32_t* obs_kf, const float* obs, const uint8_t* octave,
+                                           uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

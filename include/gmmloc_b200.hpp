@@ -9,7 +9,8 @@
 //   gmmloc::StrOptStat                  gmmloc/include/gmmloc/types/map.h:30-35
 //   GMMLoc::optimizePoint               gmmloc/include/gmmloc/gmmloc.h:43-46
 //   Tracking::optimizeCurrentPose       gmmloc/include/gmmloc/modules/tracking.h:51
-//   Localization::jointOptimization     gmmloc/include/gmmloc/modules/localization.h:61 (single free pose)
+//   Localization::jointOptimization     gmmloc/include/gmmloc/modules/localization.h:61 (single free pose: optimizeFrames;
+//                                       full covisibility window: jointOptimization(LocalWindow&))
 //   GMM::renderView / getComponents2d / searchCorrespondence   gaussian_mixture.h:122,135-137,147
 //   GMMLoc::checkMapAssociation / associateMapElements          gmmloc/include/gmmloc/gmmloc.h:48-51
 //   Localization::optimizeTriangulationVec                      modules/localization.h:58-59
@@ -161,6 +162,22 @@ struct KeyFrameAssociation {
   std::vector<Vector3d> pt3d;            // the (possibly optimised) world point; NaN when the feature has no depth
   std::vector<std::vector<int>> comps;   // KeyFrame::comps_: candidate parent components per feature
   int num_components2d = 0;              // size of the rendered view
+};
+
+// one covisibility window of Localization::jointOptimization (localization_opt.cpp:456-925) in flat form:
+// the local + fixed keyframes, the local map points and one entry per (map point, keyframe) observation
+struct LocalWindow {
+  std::vector<SE3Quat> poses;          // local_kfs then fixed_kfs (in/out)
+  std::vector<uint8_t> fixed;          // VertexSE3Expmap::setFixed
+  int prior_idx = -1;                  // keyframe 0 when loc::ba_first_as_prior (EdgeSE3QuatPrior), else -1
+  std::vector<Vector3d> points;        // MapPoint::getPosition() (in/out)
+  std::vector<int32_t> assoc;          // MapPoint::asscociations_[0] as a component index, -1 = none
+  std::vector<int32_t> obs_pt, obs_kf; // observation -> point / keyframe index (grouped by point)
+  std::vector<Feature> obs;            // the observing keyframe's feature (uv, u_right, octave)
+  // results
+  std::vector<uint8_t> erase;          // vToErase (:857-881): observation is an outlier
+  std::vector<uint8_t> assoc_cleared;  // :842-855: the point loses its association
+  std::array<int32_t, 3> iters{0, 0, 0};
 };
 
 struct FrameResult {
@@ -334,6 +351,35 @@ class Optimizer {
     for (size_t i = 0; i < N; ++i)
       for (int c = 0; c < num && cand[i * num + c] >= 0; ++c) r.comps[i].push_back(cand[i * num + c]);
     return r;
+  }
+
+  // ≙ void Localization::jointOptimization(KeyFrame*, bool* stop, Map*): the caller flattens the window (the
+  // reference's graph construction, :460-766) and applies the results (:842-925); the 3-stage LM runs on the GPU.
+  void jointOptimization(LocalWindow& w) {
+    const int32_t P = (int32_t)w.poses.size(), L = (int32_t)w.points.size(), E = (int32_t)w.obs_pt.size();
+    if ((int32_t)w.fixed.size() != P || (int32_t)w.assoc.size() != L || (int32_t)w.obs_kf.size() != E || (int32_t)w.obs.size() != E)
+      throw Error(GMMLOC_EINVAL, "LocalWindow: size mismatch");
+    std::vector<double> pose(7 * (size_t)P), pts(3 * (size_t)L);
+    std::vector<float> obs(3 * (size_t)E);
+    std::vector<uint8_t> oct((size_t)E);
+    for (int32_t i = 0; i < P; ++i)
+      for (int j = 0; j < 7; ++j) pose[7 * (size_t)i + j] = w.poses[i].v[j];
+    for (int32_t l = 0; l < L; ++l)
+      for (int j = 0; j < 3; ++j) pts[3 * (size_t)l + j] = w.points[l][j];
+    for (int32_t e = 0; e < E; ++e) {
+      obs[3 * (size_t)e] = (float)w.obs[e].u; obs[3 * (size_t)e + 1] = (float)w.obs[e].v; obs[3 * (size_t)e + 2] = (float)w.obs[e].u_right;
+      oct[e] = (uint8_t)w.obs[e].octave;
+    }
+    const int32_t pp[2] = {0, P}, lp[2] = {0, L}, ep[2] = {0, E};
+    w.erase.assign((size_t)E, 0);
+    w.assoc_cleared.assign((size_t)L, 0);
+    int32_t status = 0;
+    check(gmmloc_local_ba(ctx_, model_->handle(), &cam_, &params_, 1, pp, pose.data(), w.fixed.data(), &w.prior_idx, lp, pts.data(),
+                          w.assoc.data(), ep, w.obs_pt.data(), w.obs_kf.data(), obs.data(), oct.data(), w.erase.data(),
+                          w.assoc_cleared.data(), w.iters.data(), &status));
+    for (int32_t i = 0; i < P; ++i)
+      for (int j = 0; j < 7; ++j) w.poses[i].v[j] = pose[7 * (size_t)i + j];
+    for (int32_t l = 0; l < L; ++l) w.points[l] = {pts[3 * (size_t)l], pts[3 * (size_t)l + 1], pts[3 * (size_t)l + 2]};
   }
 
   // ≙ GaussianComponent* Localization::optimizeTriangulationVec(Vector3d& x3d, KeyFrame* pKF1, idx1, idx2)

@@ -1379,4 +1379,513 @@ void oracle_keyframe_associate(const oracle_comp_t* comps, int K, const int64_t*
   });
 }
 
+// ----------------------------------------------------------------------------------------------
+// local bundle adjustment: Localization::jointOptimization (localization_opt.cpp:456-925)
+// ----------------------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// g2o SE3Quat::inverse: r = conj(r), t = r * (t * -1)
+void se3_inverse(const double T[7], double out[7]) {
+  const double qc[4] = {-T[0], -T[1], -T[2], T[3]};
+  const double tn[3] = {T[4] * -1.0, T[5] * -1.0, T[6] * -1.0};
+  quat_rotate(qc, tn, out + 4);
+  for (int i = 0; i < 4; ++i) out[i] = qc[i];
+}
+// g2o SE3Quat::operator*: t = t1 + r1 * t2, r = r1 * r2, normalizeRotation
+void se3_mul(const double A[7], const double B[7], double out[7]) {
+  double rt[3], q[4];
+  quat_rotate(A, B + 4, rt);
+  quat_mul(A, B, q);
+  quat_normalize(q);
+  for (int i = 0; i < 4; ++i) out[i] = q[i];
+  for (int i = 0; i < 3; ++i) out[4 + i] = A[4 + i] + rt[i];
+}
+// g2o SE3Quat::log (se3quat.h): [omega; upsilon]
+void se3_log(const double T[7], double xi[6]) {
+  double R[9];
+  quat_to_rot(T, R);
+  const double d = 0.5 * (M(R, 0, 0) + M(R, 1, 1) + M(R, 2, 2) - 1);
+  const double dR[3] = {M(R, 2, 1) - M(R, 1, 2), M(R, 0, 2) - M(R, 2, 0), M(R, 1, 0) - M(R, 0, 1)};
+  double om[3], Vi[9];
+  double coef;
+  if (std::fabs(d) > 0.99999) {
+    for (int i = 0; i < 3; ++i) om[i] = 0.5 * dR[i];
+    coef = 1. / 12.;
+  } else {
+    const double theta = std::acos(d);
+    for (int i = 0; i < 3; ++i) om[i] = theta / (2 * std::sqrt(1 - d * d)) * dR[i];
+    coef = (1 - theta / (2 * std::tan(theta / 2))) / (theta * theta);
+  }
+  const double Om[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      const double o2 = (M(Om, r, 0) * M(Om, 0, c) + M(Om, r, 1) * M(Om, 1, c)) + M(Om, r, 2) * M(Om, 2, c);
+      M(Vi, r, c) = ((r == c) ? 1.0 : 0.0) - 0.5 * M(Om, r, c) + coef * o2;
+    }
+  mat3_vec(Vi, T + 4, xi + 3);
+  for (int i = 0; i < 3; ++i) xi[i] = om[i];
+}
+// g2o SE3Quat::adj: [[R, 0], [skew(t) R, R]]  (row-major 6x6)
+void se3_adj(const double T[7], double A[36]) {
+  double R[9];
+  quat_to_rot(T, R);
+  const double* t = T + 4;
+  const double St[9] = {0, -t[2], t[1], t[2], 0, -t[0], -t[1], t[0], 0};
+  for (int i = 0; i < 36; ++i) A[i] = 0;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      A[r * 6 + c] = M(R, r, c);
+      A[(3 + r) * 6 + 3 + c] = M(R, r, c);
+      A[(3 + r) * 6 + c] = (M(St, r, 0) * M(R, 0, c) + M(St, r, 1) * M(R, 1, c)) + M(St, r, 2) * M(R, 2, c);
+    }
+}
+
+// dense SPD solve (in place Cholesky), n x n row-major
+bool solve_dense_spd(std::vector<double>& A, std::vector<double>& b, int n) {
+  for (int k = 0; k < n; ++k) {
+    double s = A[(size_t)k * n + k];
+    for (int j = 0; j < k; ++j) s -= A[(size_t)k * n + j] * A[(size_t)k * n + j];
+    if (!(s > 0.0) || !std::isfinite(s)) return false;
+    const double d = std::sqrt(s);
+    A[(size_t)k * n + k] = d;
+    for (int i = k + 1; i < n; ++i) {
+      double t = A[(size_t)i * n + k];
+      for (int j = 0; j < k; ++j) t -= A[(size_t)i * n + j] * A[(size_t)k * n + j];
+      A[(size_t)i * n + k] = t / d;
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    double t = b[i];
+    for (int j = 0; j < i; ++j) t -= A[(size_t)i * n + j] * b[j];
+    b[i] = t / A[(size_t)i * n + i];
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double t = b[i];
+    for (int j = i + 1; j < n; ++j) t -= A[(size_t)j * n + i] * b[j];
+    b[i] = t / A[(size_t)i * n + i];
+  }
+  for (int i = 0; i < n; ++i)
+    if (!std::isfinite(b[i])) return false;
+  return true;
+}
+
+struct LocalBA {
+  const oracle_comp_t* comps;
+  Cam cam;
+  const oracle_params_t* prm;
+  int P, L, E, nf;
+  const uint8_t* fixed;
+  const int32_t *assoc, *obs_pt, *obs_kf;
+  const float* obs;
+  std::vector<int> fidx;              // pose -> free index or -1
+  std::vector<double> w;              // per observation information
+  std::vector<uint8_t> stereo, level; // per observation
+  std::vector<double> err;            // E x 3, errors of the last computeActiveErrors
+  std::vector<uint8_t> str_type, str_level;  // per point: 0 none, 1 EdgePt2GaussianDeg, 2 EdgePt2Gaussian
+  std::vector<double> str_err;        // L x 3
+  std::vector<std::vector<int>> pt_obs;
+  int prior_idx;
+  double prior_inv[7], prior_info[6], prior_err[6];
+  bool robust = true;
+  double delta_mono, delta_stereo;
+  // linear system of the current linearisation point
+  std::vector<double> Hpp, bp, Hll, bl, Hpl;
+  // last solution
+  std::vector<double> dxp, dxl;
+
+  void structure_error(const double* x, int l, double* e) const {
+    const oracle_comp_t& c = comps[assoc[l]];
+    const double d[3] = {x[0] - c.mean[0], x[1] - c.mean[1], x[2] - c.mean[2]};
+    if (str_type[l] == 1) {  // factors.cpp:55-64
+      e[0] = (c.axis[0] * d[0] + c.axis[3] * d[1]) + c.axis[6] * d[2];
+      e[1] = e[2] = 0.0;
+    } else {  // factors.cpp:5-17: sqrt_info^T * d
+      const double* Lm = c.sqrt_info;
+      for (int r = 0; r < 3; ++r) e[r] = (M(Lm, 0, r) * d[0] + M(Lm, 1, r) * d[1]) + M(Lm, 2, r) * d[2];
+    }
+  }
+  double structure_chi2(int l, const double* e) const {
+    if (str_type[l] == 1) return prm->ba_lambda2 * (e[0] * e[0]);
+    return (e[0] * e[0] + e[1] * e[1]) + e[2] * e[2];
+  }
+
+  // computeActiveErrors + activeRobustChi2 at (pose, pts)
+  double active_errors(const std::vector<double>& pose, const std::vector<double>& pts) {
+    std::vector<double> R(9 * (size_t)P);
+    for (int i = 0; i < P; ++i) quat_to_rot(&pose[7 * (size_t)i], &R[9 * (size_t)i]);
+    double chi = 0.0;
+    for (int e = 0; e < E; ++e) {
+      if (level[e]) continue;
+      const int i = obs_kf[e];
+      double pc[3];
+      mat3_vec(&R[9 * (size_t)i], &pts[3 * (size_t)obs_pt[e]], pc);
+      for (int r = 0; r < 3; ++r) pc[r] += pose[7 * (size_t)i + 4 + r];
+      const double ob[3] = {(double)obs[3 * e], (double)obs[3 * e + 1], (double)obs[3 * e + 2]};
+      double* er = &err[3 * (size_t)e];
+      reproj_edge(cam, &R[9 * (size_t)i], pc, ob, stereo[e], er, nullptr, nullptr);
+      const double c2 = w[e] * ((er[0] * er[0] + er[1] * er[1]) + er[2] * er[2]);
+      if (robust) {
+        const double d = stereo[e] ? delta_stereo : delta_mono, dsqr = d * d;
+        chi += (c2 <= dsqr) ? c2 : 2 * std::sqrt(c2) * d - dsqr;
+      } else {
+        chi += c2;
+      }
+    }
+    for (int l = 0; l < L; ++l) {
+      if (!str_type[l] || str_level[l]) continue;
+      structure_error(&pts[3 * (size_t)l], l, &str_err[3 * (size_t)l]);
+      chi += structure_chi2(l, &str_err[3 * (size_t)l]);
+    }
+    if (prior_idx >= 0) {  // factors.cpp:19-29
+      double delta[7];
+      se3_mul(prior_inv, &pose[7 * (size_t)prior_idx], delta);
+      se3_log(delta, prior_err);
+      for (int a = 0; a < 6; ++a) chi += prior_info[a] * (prior_err[a] * prior_err[a]);
+    }
+    return chi;
+  }
+
+  // buildSystem: linearizeOplus + constructQuadraticForm of every active edge
+  void build(const std::vector<double>& pose, const std::vector<double>& pts) {
+    Hpp.assign(36 * (size_t)nf, 0.0);
+    bp.assign(6 * (size_t)nf, 0.0);
+    Hll.assign(9 * (size_t)L, 0.0);
+    bl.assign(3 * (size_t)L, 0.0);
+    Hpl.assign(18 * (size_t)E, 0.0);
+    std::vector<double> R(9 * (size_t)P);
+    for (int i = 0; i < P; ++i) quat_to_rot(&pose[7 * (size_t)i], &R[9 * (size_t)i]);
+    for (int e = 0; e < E; ++e) {
+      if (level[e]) continue;
+      const int i = obs_kf[e], l = obs_pt[e], f = fidx[i];
+      const double* Ri = &R[9 * (size_t)i];
+      double pc[3], er[3], Jl[9], Jp[18];
+      mat3_vec(Ri, &pts[3 * (size_t)l], pc);
+      for (int r = 0; r < 3; ++r) pc[r] += pose[7 * (size_t)i + 4 + r];
+      const double ob[3] = {(double)obs[3 * e], (double)obs[3 * e + 1], (double)obs[3 * e + 2]};
+      reproj_edge(cam, Ri, pc, ob, stereo[e], er, Jl, Jp);
+      const int m = stereo[e] ? 3 : 2;
+      double we = w[e];
+      if (robust) {
+        double c2 = 0;
+        for (int r = 0; r < m; ++r) c2 += er[r] * er[r];
+        c2 *= w[e];
+        we *= huber_rho1(c2, stereo[e] ? delta_stereo : delta_mono);
+      }
+      for (int a = 0; a < 3; ++a) {
+        for (int b = 0; b < 3; ++b) {
+          double s = 0;
+          for (int r = 0; r < m; ++r) s += Jl[r * 3 + a] * Jl[r * 3 + b];
+          Hll[9 * (size_t)l + a * 3 + b] += we * s;
+        }
+        double s = 0;
+        for (int r = 0; r < m; ++r) s += Jl[r * 3 + a] * er[r];
+        bl[3 * (size_t)l + a] -= we * s;
+      }
+      if (f < 0) continue;
+      for (int a = 0; a < 6; ++a) {
+        for (int b = 0; b < 6; ++b) {
+          double s = 0;
+          for (int r = 0; r < m; ++r) s += Jp[r * 6 + a] * Jp[r * 6 + b];
+          Hpp[36 * (size_t)f + a * 6 + b] += we * s;
+        }
+        double s = 0;
+        for (int r = 0; r < m; ++r) s += Jp[r * 6 + a] * er[r];
+        bp[6 * (size_t)f + a] -= we * s;
+        for (int b = 0; b < 3; ++b) {
+          double s2 = 0;
+          for (int r = 0; r < m; ++r) s2 += Jp[r * 6 + a] * Jl[r * 3 + b];
+          Hpl[18 * (size_t)e + a * 3 + b] = we * s2;
+        }
+      }
+    }
+    for (int l = 0; l < L; ++l) {
+      if (!str_type[l] || str_level[l]) continue;
+      const oracle_comp_t& c = comps[assoc[l]];
+      double es[3];
+      structure_error(&pts[3 * (size_t)l], l, es);
+      double* H = &Hll[9 * (size_t)l];
+      double* b = &bl[3 * (size_t)l];
+      if (str_type[l] == 1) {  // Omega = ba_lambda2, J = n^T   (localization_opt.cpp:657-669)
+        const double n[3] = {c.axis[0], c.axis[3], c.axis[6]};
+        for (int a = 0; a < 3; ++a) {
+          for (int bb = 0; bb < 3; ++bb) H[a * 3 + bb] += prm->ba_lambda2 * (n[a] * n[bb]);
+          b[a] -= prm->ba_lambda2 * (n[a] * es[0]);
+        }
+      } else {  // Omega = I, J = sqrt_info^T   (:670-681)
+        const double* Lm = c.sqrt_info;
+        for (int a = 0; a < 3; ++a) {
+          for (int bb = 0; bb < 3; ++bb) {
+            double s = 0;
+            for (int r = 0; r < 3; ++r) s += M(Lm, a, r) * M(Lm, bb, r);
+            H[a * 3 + bb] += s;
+          }
+          double s = 0;
+          for (int r = 0; r < 3; ++r) s += M(Lm, a, r) * es[r];
+          b[a] -= s;
+        }
+      }
+    }
+    if (prior_idx >= 0 && fidx[prior_idx] >= 0) {  // factors.cpp:31-53
+      const int f = fidx[prior_idx];
+      double delta[7], dv[6], Jr[36], Tinv[7], Ad[36], J[36];
+      se3_mul(prior_inv, &pose[7 * (size_t)prior_idx], delta);
+      se3_log(delta, dv);
+      for (int i = 0; i < 36; ++i) Jr[i] = 0;
+      const double ph[9] = {0, -dv[2], dv[1], dv[2], 0, -dv[0], -dv[1], dv[0], 0};
+      const double lu[9] = {0, -dv[5], dv[4], dv[5], 0, -dv[3], -dv[4], dv[3], 0};
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) {
+          Jr[r * 6 + c] = 0.5 * M(ph, r, c);
+          Jr[(3 + r) * 6 + 3 + c] = 0.5 * M(ph, r, c);
+          Jr[r * 6 + 3 + c] = 0.5 * M(lu, r, c);
+        }
+      for (int a = 0; a < 6; ++a) Jr[a * 6 + a] += 1.0;
+      se3_inverse(&pose[7 * (size_t)prior_idx], Tinv);
+      se3_adj(Tinv, Ad);
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b) {
+          double s2 = 0;
+          for (int k = 0; k < 6; ++k) s2 += Jr[a * 6 + k] * Ad[k * 6 + b];
+          J[a * 6 + b] = s2;
+        }
+      for (int a = 0; a < 6; ++a) {
+        for (int b = 0; b < 6; ++b) {
+          double s2 = 0;
+          for (int k = 0; k < 6; ++k) s2 += J[k * 6 + a] * prior_info[k] * J[k * 6 + b];
+          Hpp[36 * (size_t)f + a * 6 + b] += s2;
+        }
+        double s2 = 0;
+        for (int k = 0; k < 6; ++k) s2 += J[k * 6 + a] * prior_info[k] * dv[k];
+        bp[6 * (size_t)f + a] -= s2;
+      }
+    }
+  }
+
+  double max_diag() const {
+    double md = 0;
+    for (int f = 0; f < nf; ++f)
+      for (int a = 0; a < 6; ++a) md = std::max(md, std::fabs(Hpp[36 * (size_t)f + a * 7]));
+    for (int l = 0; l < L; ++l)
+      for (int a = 0; a < 3; ++a) md = std::max(md, std::fabs(Hll[9 * (size_t)l + a * 4]));
+    return md;
+  }
+
+  // BlockSolver_6_3::solve with Schur complement at damping lambda
+  bool solve(double lambda) {
+    const int n = 6 * nf;
+    std::vector<double> S((size_t)n * n, 0.0), rhs(bp);
+    std::vector<double> Hinv(9 * (size_t)L);
+    for (int f = 0; f < nf; ++f)
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b) S[(size_t)(6 * f + a) * n + 6 * f + b] = Hpp[36 * (size_t)f + a * 6 + b] + (a == b ? lambda : 0.0);
+    bool ok = true;
+    for (int l = 0; l < L; ++l) {
+      double Hl[9];
+      for (int i = 0; i < 9; ++i) Hl[i] = Hll[9 * (size_t)l + i];
+      for (int a = 0; a < 3; ++a) Hl[a * 4] += lambda;
+      if (!inverse3(Hl, &Hinv[9 * (size_t)l])) ok = false;
+      const double* Hi = &Hinv[9 * (size_t)l];
+      for (int ea : pt_obs[l]) {
+        if (level[ea]) continue;
+        const int fa = fidx[obs_kf[ea]];
+        if (fa < 0) continue;
+        const double* Wa = &Hpl[18 * (size_t)ea];
+        double T[18];  // Hpl_a * Hll^-1
+        for (int a = 0; a < 6; ++a)
+          for (int b = 0; b < 3; ++b) T[a * 3 + b] = (Wa[a * 3] * M(Hi, 0, b) + Wa[a * 3 + 1] * M(Hi, 1, b)) + Wa[a * 3 + 2] * M(Hi, 2, b);
+        for (int a = 0; a < 6; ++a)
+          rhs[6 * (size_t)fa + a] -= (T[a * 3] * bl[3 * (size_t)l] + T[a * 3 + 1] * bl[3 * (size_t)l + 1]) + T[a * 3 + 2] * bl[3 * (size_t)l + 2];
+        for (int eb : pt_obs[l]) {
+          if (level[eb]) continue;
+          const int fb = fidx[obs_kf[eb]];
+          if (fb < 0) continue;
+          const double* Wb = &Hpl[18 * (size_t)eb];
+          for (int a = 0; a < 6; ++a)
+            for (int b = 0; b < 6; ++b)
+              S[(size_t)(6 * fa + a) * n + 6 * fb + b] -= (T[a * 3] * Wb[b * 3] + T[a * 3 + 1] * Wb[b * 3 + 1]) + T[a * 3 + 2] * Wb[b * 3 + 2];
+        }
+      }
+    }
+    if (!ok) return false;
+    if (n > 0 && !solve_dense_spd(S, rhs, n)) return false;
+    dxp = rhs;
+    dxl.assign(3 * (size_t)L, 0.0);
+    for (int l = 0; l < L; ++l) {
+      double c[3] = {bl[3 * (size_t)l], bl[3 * (size_t)l + 1], bl[3 * (size_t)l + 2]};
+      for (int ea : pt_obs[l]) {
+        if (level[ea]) continue;
+        const int fa = fidx[obs_kf[ea]];
+        if (fa < 0) continue;
+        const double* Wa = &Hpl[18 * (size_t)ea];
+        for (int b = 0; b < 3; ++b) {
+          double s2 = 0;
+          for (int a = 0; a < 6; ++a) s2 += Wa[a * 3 + b] * dxp[6 * (size_t)fa + a];
+          c[b] -= s2;
+        }
+      }
+      mat3_vec(&Hinv[9 * (size_t)l], c, &dxl[3 * (size_t)l]);
+      for (int r = 0; r < 3; ++r)
+        if (!std::isfinite(dxl[3 * (size_t)l + r])) return false;
+    }
+    return true;
+  }
+
+  // OptimizationAlgorithmLevenberg, `iters` iterations (SURVEY Appx B.7); returns the iterations run
+  int optimize(int iters, std::vector<double>& pose, std::vector<double>& pts) {
+    double lambda = 0.0, ni = 2.0;
+    bool ok = true;
+    int it = 0;
+    for (; it < iters && ok; ++it) {
+      double cur_chi = active_errors(pose, pts);
+      build(pose, pts);
+      if (it == 0) {
+        lambda = 1e-5 * max_diag();
+        ni = 2.0;
+      }
+      double rho = 0;
+      int qmax = 0;
+      do {
+        std::vector<double> tp(pose), tx(pts);
+        const bool ok2 = solve(lambda);
+        double tmp_chi;
+        if (ok2) {
+          for (int i = 0; i < P; ++i)
+            if (fidx[i] >= 0) se3_oplus(&dxp[6 * (size_t)fidx[i]], &pose[7 * (size_t)i], &tp[7 * (size_t)i]);
+          for (size_t i = 0; i < tx.size(); ++i) tx[i] += dxl[i];
+          tmp_chi = active_errors(tp, tx);
+        } else {
+          dxp.assign(6 * (size_t)nf, 0.0);
+          dxl.assign(3 * (size_t)L, 0.0);
+          tmp_chi = std::numeric_limits<double>::max();
+        }
+        rho = cur_chi - tmp_chi;
+        double scale = 0;
+        for (size_t a = 0; a < dxp.size(); ++a) scale += dxp[a] * (lambda * dxp[a] + bp[a]);
+        for (size_t a = 0; a < dxl.size(); ++a) scale += dxl[a] * (lambda * dxl[a] + bl[a]);
+        scale += 1e-3;
+        rho /= scale;
+        if (rho > 0 && std::isfinite(tmp_chi) && ok2) {
+          double alpha = 1. - std::pow(2 * rho - 1, 3);
+          alpha = std::min(alpha, 2. / 3.);
+          lambda *= std::max(1. / 3., alpha);
+          ni = 2;
+          cur_chi = tmp_chi;
+          pose.swap(tp);
+          pts.swap(tx);
+        } else {
+          lambda *= ni;
+          ni *= 2;
+          if (!std::isfinite(lambda)) break;
+        }
+        ++qmax;
+      } while (rho < 0 && qmax < 10);
+      if (qmax == 10 || rho == 0 || !std::isfinite(lambda)) ok = false;
+    }
+    return it;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void oracle_se3_log(const double pose[7], double xi[6]) {
+  double q[7];
+  for (int i = 0; i < 7; ++i) q[i] = pose[i];
+  quat_normalize(q);
+  se3_log(q, xi);
+}
+
+int oracle_local_ba(const oracle_comp_t* comps, int K, const oracle_camera_t* camp, const oracle_params_t* prm, int P,
+                    double* pose_io, const uint8_t* fixed, int prior_idx, int L, double* pts_io, const int32_t* assoc, int E,
+                    const int32_t* obs_pt, const int32_t* obs_kf, const float* obs, const uint8_t* octave,
+                    uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters) {
+  for (int e = 0; e < E; ++e)
+    if (obs_pt[e] < 0 || obs_pt[e] >= L || obs_kf[e] < 0 || obs_kf[e] >= P) return -1;
+  for (int l = 0; l < L; ++l)
+    if (assoc[l] >= K) return -1;
+  if (prior_idx >= P) return -1;
+  LocalBA ba;
+  ba.comps = comps;
+  ba.cam = Cam{camp->fx, camp->fy, camp->cx, camp->cy, camp->bf};
+  ba.prm = prm;
+  ba.P = P; ba.L = L; ba.E = E;
+  ba.fixed = fixed;
+  ba.assoc = assoc; ba.obs_pt = obs_pt; ba.obs_kf = obs_kf; ba.obs = obs;
+  ba.fidx.assign(P, -1);
+  ba.nf = 0;
+  for (int i = 0; i < P; ++i)
+    if (!fixed[i]) ba.fidx[i] = ba.nf++;
+  ba.w.resize(E); ba.stereo.resize(E); ba.level.assign(E, 0); ba.err.assign(3 * (size_t)E, 0.0);
+  ba.pt_obs.assign(L, {});
+  for (int e = 0; e < E; ++e) {
+    ba.w[e] = oracle_sigma2_inv(octave[e]);
+    ba.stereo[e] = !(obs[3 * e + 2] < 0.0f);  // u_right < 0 => monocular (:702)
+    ba.pt_obs[obs_pt[e]].push_back(e);
+  }
+  ba.str_type.assign(L, 0); ba.str_level.assign(L, 0); ba.str_err.assign(3 * (size_t)L, 0.0);
+  for (int l = 0; l < L; ++l)
+    if (assoc[l] >= 0) ba.str_type[l] = comps[assoc[l]].is_degenerated ? 1 : 2;  // :655-682
+  ba.delta_mono = (double)(float)std::sqrt(5.991);    // thHuberMono   :637
+  ba.delta_stereo = (double)(float)std::sqrt(7.815);  // thHuberStereo :638
+  std::vector<double> pose(pose_io, pose_io + 7 * (size_t)P), pts(pts_io, pts_io + 3 * (size_t)L);
+  for (int i = 0; i < P; ++i) quat_normalize(&pose[7 * (size_t)i]);
+  ba.prior_idx = prior_idx;
+  if (prior_idx >= 0) {
+    se3_inverse(&pose[7 * (size_t)prior_idx], ba.prior_inv);  // setMeasurement(kfi_ptr->getTcw())  :566
+    const double sigma_rot = 2.0 * M_PI / 180.0;
+    for (int a = 0; a < 3; ++a) {
+      ba.prior_info[a] = 1.0 / (sigma_rot * sigma_rot);   // :568-575
+      ba.prior_info[3 + a] = 1.0 / (0.01 * 0.01);
+    }
+  }
+  int its[3] = {0, 0, 0};
+  // stage 1: optimize(5)  (:770-771)
+  ba.robust = true;
+  its[0] = ba.optimize(5, pose, pts);
+  // degenerate structure edges: computeError at the current estimate, reject above the threshold (:774-786)
+  for (int l = 0; l < L; ++l) {
+    if (ba.str_type[l] != 1) continue;
+    double es[3];
+    ba.structure_error(&pts[3 * (size_t)l], l, es);
+    if (ba.structure_chi2(l, es) > prm->tri_str_thresh * prm->ba_lambda2) ba.str_level[l] = 1;
+  }
+  // stage 2: optimize(5)  (:788-789)
+  its[1] = ba.optimize(5, pose, pts);
+  // reprojection edges: chi2 of the last computeActiveErrors; isDepthPositive at the current estimate (:799-823)
+  auto depth_positive = [&](int e) {
+    const int i = obs_kf[e];
+    double R[9], pc[3];
+    quat_to_rot(&pose[7 * (size_t)i], R);
+    mat3_vec(R, &pts[3 * (size_t)obs_pt[e]], pc);
+    return pc[2] + pose[7 * (size_t)i + 6] > 0.0;
+  };
+  auto edge_chi2 = [&](int e) {
+    const double* er = &ba.err[3 * (size_t)e];
+    return ba.w[e] * ((er[0] * er[0] + er[1] * er[1]) + er[2] * er[2]);
+  };
+  for (int e = 0; e < E; ++e)
+    if (edge_chi2(e) > (ba.stereo[e] ? 7.815 : 5.991) || !depth_positive(e)) ba.level[e] = 1;
+  ba.robust = false;  // e->setRobustKernel(0)
+  // stage 3: optimize(40)  (:826-828)
+  its[2] = ba.optimize(40, pose, pts);
+  // results (:834-881)
+  if (assoc_cleared)
+    for (int l = 0; l < L; ++l) {
+      assoc_cleared[l] = 0;
+      if (ba.str_type[l] != 1) continue;
+      double es[3];
+      ba.structure_error(&pts[3 * (size_t)l], l, es);
+      assoc_cleared[l] = ba.structure_chi2(l, es) > prm->tri_str_thresh * prm->ba_lambda2;
+    }
+  if (obs_outlier)
+    for (int e = 0; e < E; ++e) obs_outlier[e] = (edge_chi2(e) > (ba.stereo[e] ? 7.815 : 5.991) || !depth_positive(e)) ? 1 : 0;
+  for (size_t i = 0; i < pose.size(); ++i) pose_io[i] = pose[i];
+  for (size_t i = 0; i < pts.size(); ++i) pts_io[i] = pts[i];
+  if (iters) for (int s2 = 0; s2 < 3; ++s2) iters[s2] = its[s2];
+  return 0;
+}
+
 }  // extern "C"

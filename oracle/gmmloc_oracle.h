@@ -187,6 +187,31 @@ void oracle_keyframe_associate(const oracle_comp_t* comps, int K, const int64_t*
                                const float* obs, const float* depth, const uint8_t* octave, int N, int num,
                                int32_t* assoc, double* pt3d, int32_t* cand, int32_t* nview, int nthreads);
 
+/* a12 / f4: Localization::jointOptimization (localization_opt.cpp:456-925) — local bundle adjustment over P
+ * keyframe poses (fixed[i] != 0: VertexSE3Expmap::setFixed, the "fixed_kfs" and keyframe 0 when
+ * !ba_first_as_prior) and L marginalised points, g2o Levenberg-Marquardt with BlockSolver_6_3 (Schur
+ * complement over the points, SURVEY Appx B.7-8; the reduced pose system is solved with a dense Cholesky in
+ * place of LinearSolverEigen's sparse one), three stages:
+ *   optimize(5): every reprojection edge Huber-robustified (sqrt 5.991 / sqrt 7.815), structure edges plain;
+ *   then degenerate structure edges with chi2 > tri_str_thresh * ba_lambda2 move to level 1 (:774-786);
+ *   optimize(5);  then reprojection edges with chi2 > 5.991 / 7.815 (errors of the last LM trial) or
+ *   non-positive depth move to level 1 and all robust kernels are dropped (:797-823);  optimize(40).
+ * Edges: one per observation (point obs_pt[e] seen by keyframe obs_kf[e]; obs u v u_r, u_r < 0 => mono
+ * EdgeSE3ProjectXYZ, else EdgeStereoSE3ProjectXYZ; information sigma2_inv[octave]); per associated point
+ * (assoc[l] >= 0) EdgePt2GaussianDeg (information ba_lambda2) or EdgePt2Gaussian (information I);
+ * prior_idx >= 0: EdgeSE3QuatPrior on that pose, measurement = its initial estimate, information
+ * diag(sigma_rot^-2 I, sigma_t^-2 I), sigma_rot = 2 deg, sigma_t = 1 cm (:560-578, factors.cpp:19-53).
+ * In/out: pose P x 7 (fixed poses are only normalised), pts L x 3.  Outputs (optional): obs_outlier E (the
+ * vToErase test, :857-881), assoc_cleared L (structure edge rejected at the end, :842-855), iters[3] = LM
+ * iterations run per stage.  Returns 0, or -1 on invalid indices. */
+int oracle_local_ba(const oracle_comp_t* comps, int K, const oracle_camera_t* cam, const oracle_params_t* prm, int P,
+                    double* pose, const uint8_t* fixed, int prior_idx, int L, double* pts, const int32_t* assoc, int E,
+                    const int32_t* obs_pt, const int32_t* obs_kf, const float* obs, const uint8_t* octave,
+                    uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters);
+
+/* g2o SE3Quat::log (se3quat.h) of pose = qx qy qz qw tx ty tz -> [omega; upsilon] */
+void oracle_se3_log(const double pose[7], double xi[6]);
+
 /* frame::sigma2_inv[octave] as the reference computes it in float (init_config.hpp:63-78). */
 double oracle_sigma2_inv(int octave);
 

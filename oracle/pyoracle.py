@@ -354,3 +354,36 @@ def keyframe_associate(comps, nbr, pose, obs, depth, octave, num=5, cam=None, pr
                                     _p(pose), _p(obs), _p(depth), _p(octave), C.c_int(N), C.c_int(num), _p(assoc),
                                     _p(pt3d), _p(cand), C.byref(nview), C.c_int(nthreads))
     return dict(assoc=assoc, pt3d=pt3d, cand=cand, nview=nview.value)
+
+
+def local_ba(comps, pose, fixed, pts, assoc, obs_pt, obs_kf, obs, octave, prior_idx=-1, cam=None, prm=None):
+    """Localization::jointOptimization (3-stage LM local BA): dict(pose, pts, obs_outlier, assoc_cleared, iters)."""
+    cam = cam or v1_camera()
+    prm = prm or default_params()
+    pose = np.array(pose, np.float64).reshape(-1, 7).copy()
+    pts = np.array(pts, np.float64).reshape(-1, 3).copy()
+    fixed = np.ascontiguousarray(fixed, np.uint8)
+    assoc = np.ascontiguousarray(assoc, np.int32)
+    obs_pt = np.ascontiguousarray(obs_pt, np.int32)
+    obs_kf = np.ascontiguousarray(obs_kf, np.int32)
+    obs = np.ascontiguousarray(obs, np.float32).reshape(-1, 3)
+    octave = np.ascontiguousarray(octave, np.uint8)
+    E, L, P = len(obs_pt), len(pts), len(pose)
+    outl = np.zeros(E, np.uint8)
+    cleared = np.zeros(L, np.uint8)
+    iters = np.zeros(3, np.int32)
+    fn = lib().oracle_local_ba
+    fn.restype = C.c_int
+    rc = fn(_p(comps), C.c_int(len(comps)), C.byref(cam), C.byref(prm), C.c_int(P), _p(pose), _p(fixed), C.c_int(int(prior_idx)),
+            C.c_int(L), _p(pts), _p(assoc), C.c_int(E), _p(obs_pt), _p(obs_kf), _p(obs), _p(octave), _p(outl), _p(cleared),
+            _p(iters))
+    if rc != 0:
+        raise ValueError("oracle_local_ba: invalid indices")
+    return dict(pose=pose, pts=pts, obs_outlier=outl, assoc_cleared=cleared, iters=iters)
+
+
+def se3_log(pose):
+    pose = np.ascontiguousarray(pose, np.float64)
+    out = np.zeros(6)
+    lib().oracle_se3_log(_p(pose), _p(out))
+    return out

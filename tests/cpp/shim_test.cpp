@@ -146,6 +146,29 @@ int main(int argc, char** argv) {
   const int tri = opt.optimizeTriangulationVec(x3, kp, kp2, Tcw, Tcw2, {5, 20, 5, -1});
   REQUIRE(tri == 5 && std::fabs(x3[2] - 3.0) < 2e-3);
 
+  // local BA over two keyframes (second one fixed): perfect observations, first pose perturbed by 1 cm -> recovered
+  {
+    LocalWindow w;
+    w.poses = {T0, Tcw2};
+    w.fixed = {0, 1};
+    for (int i = 0; i < N; ++i) {
+      const double x = P[3 * i], y = P[3 * i + 1], z = P[3 * i + 2];
+      w.points.push_back({x, y, z});
+      w.assoc.push_back(i % K);
+      Feature f0, f1;
+      f0.u = cam.fx * x / z + cam.cx; f0.v = cam.fy * y / z + cam.cy; f0.u_right = f0.u - cam.bf / z;
+      f1.u = cam.fx * (x - 0.2) / z + cam.cx; f1.v = f0.v; f1.u_right = f1.u - cam.bf / z;
+      w.obs_pt.push_back(i); w.obs_kf.push_back(0); w.obs.push_back(f0);
+      w.obs_pt.push_back(i); w.obs_kf.push_back(1); w.obs.push_back(f1);
+    }
+    opt.jointOptimization(w);
+    REQUIRE(w.iters[0] == 5 && w.iters[1] == 5 && w.iters[2] >= 1);
+    REQUIRE(std::fabs(w.poses[0].v[4]) < 1e-4 && std::fabs(w.poses[0].v[5]) < 1e-4 && w.poses[1].v[4] == -0.2);
+    int erased = 0;
+    for (uint8_t e : w.erase) erased += e;
+    REQUIRE(erased == 0);
+  }
+
   // .gmm round trip through GMMUtility
   if (argc > 1) {
     GMM::Ptr g2;

@@ -411,3 +411,195 @@ def check_map_association(comps, nbr, pose, obs, octave, cand, pt3d, tri_lambda2
         if ok:
             return -1, x
     return -1, pt_init
+
+
+# ---------------------------------------------------------------- local bundle adjustment (dense, no Schur)
+def se3_log_np(R, t):
+    """log of (R, t) -> [omega; upsilon] via scipy-free closed form (Rodrigues)."""
+    c = 0.5 * (np.trace(R) - 1)
+    w = 0.5 * np.array([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]])
+    s = np.linalg.norm(w)
+    th = np.arctan2(s, c)
+    om = w if th < 1e-10 else w * (th / s)
+    Om = skew(om)
+    if th < 1e-5:
+        Vi = np.eye(3) - 0.5 * Om + Om @ Om / 12
+    else:
+        Vi = np.eye(3) - 0.5 * Om + (1 - th / (2 * np.tan(th / 2))) / th ** 2 * Om @ Om
+    return np.concatenate([om, Vi @ t])
+
+
+def local_ba_dense(comps, pose, fixed, pts, assoc, obs_pt, obs_kf, obs, octave, prior_idx=-1, ba_lambda2=400.0,
+                   tri_str_thresh=float(np.float32(0.0064))):
+    """Independent NumPy restatement of Localization::jointOptimization (localization_opt.cpp:456-925): the FULL
+    (6 nf + 3 L) normal equations are assembled and solved with numpy.linalg (no Schur complement), g2o's
+    Levenberg-Marquardt schedule (SURVEY Appx B.7), stages 5 / 5 / 40 with the reference's edge gating.
+    Returns dict(R list, t list, pts, obs_outlier, assoc_cleared, iters)."""
+    P, L, E = len(pose), len(pts), len(obs_pt)
+    Rs, ts = [], []
+    for p in pose:
+        R, t = pose_Rt(p)
+        Rs.append(R); ts.append(t)
+    x = np.array(pts, float)
+    fidx = np.full(P, -1)
+    free = [i for i in range(P) if not fixed[i]]
+    fidx[free] = np.arange(len(free))
+    nf = len(free)
+    dim = 6 * nf + 3 * L
+    st = [bool(obs[e][2] >= 0) for e in range(E)]
+    w = [s2inv(octave[e]) for e in range(E)]
+    ob = np.asarray(obs, np.float64)
+    dl = {True: float(np.float32(np.sqrt(7.815))), False: float(np.float32(np.sqrt(5.991)))}
+    level = np.zeros(E, int)
+    err = [np.zeros(3) for _ in range(E)]
+    stype = [0 if assoc[l] < 0 else (1 if comps[assoc[l]]["is_degenerated"] else 2) for l in range(L)]
+    slevel = np.zeros(L, int)
+    state = dict(robust=True)
+    if prior_idx >= 0:
+        Rm, tm = Rs[prior_idx].copy(), ts[prior_idx].copy()
+        sr = np.deg2rad(2.0)
+        Om_prior = np.diag([1 / sr ** 2] * 3 + [1 / 0.01 ** 2] * 3)
+
+    def str_resid(l, xl):
+        c = comps[assoc[l]]
+        d = xl - c["mean"]
+        if stype[l] == 1:
+            n = c["axis"].reshape(3, 3)[:, 0]
+            return np.array([n @ d]), n[None, :], np.array([[ba_lambda2]])
+        Lm = c["sqrt_info"].reshape(3, 3)
+        return Lm.T @ d, Lm.T, np.eye(3)
+
+    def prior_resid(R, t):
+        dR, dt = Rm.T @ R, Rm.T @ (t - tm)
+        return se3_log_np(dR, dt)
+
+    def active(Rs_, ts_, x_):
+        chi = 0.0
+        for e in range(E):
+            if level[e]:
+                continue
+            i, l = obs_kf[e], obs_pt[e]
+            m = 3 if st[e] else 2
+            r = ob[e, :m] - project(Rs_[i] @ x_[l] + ts_[i], st[e])
+            err[e] = r
+            c2 = w[e] * (r @ r)
+            chi += huber(c2, dl[st[e]])[0] if state["robust"] else c2
+        for l in range(L):
+            if stype[l] and not slevel[l]:
+                r, _, Om = str_resid(l, x_[l])
+                chi += r @ Om @ r
+        if prior_idx >= 0:
+            r = prior_resid(Rs_[prior_idx], ts_[prior_idx])
+            chi += r @ Om_prior @ r
+        return chi
+
+    def build():
+        H = np.zeros((dim, dim))
+        b = np.zeros(dim)
+        for e in range(E):
+            if level[e]:
+                continue
+            i, l = obs_kf[e], obs_pt[e]
+            pc = Rs[i] @ x[l] + ts[i]
+            m = 3 if st[e] else 2
+            r = ob[e, :m] - project(pc, st[e])
+            we = w[e]
+            if state["robust"]:
+                we *= huber(w[e] * (r @ r), dl[st[e]])[1]
+            Pm = dproj(pc, st[e])
+            cols, Js = [], []
+            if fidx[i] >= 0:
+                Js.append(-Pm @ np.hstack([-skew(pc), np.eye(3)]))
+                cols.append(6 * fidx[i] + np.arange(6))
+            Js.append(-Pm @ Rs[i])
+            cols.append(6 * nf + 3 * l + np.arange(3))
+            J = np.hstack(Js)
+            c = np.concatenate(cols)
+            H[np.ix_(c, c)] += we * J.T @ J
+            b[c] -= we * J.T @ r
+        for l in range(L):
+            if stype[l] and not slevel[l]:
+                r, J, Om = str_resid(l, x[l])
+                c = 6 * nf + 3 * l + np.arange(3)
+                H[np.ix_(c, c)] += J.T @ Om @ J
+                b[c] -= J.T @ Om @ r
+        if prior_idx >= 0 and fidx[prior_idx] >= 0:
+            # numerical Jacobian of log(M^-1 exp(d) T) wrt d (independent of the analytic form in factors.cpp:31-53)
+            R, t = Rs[prior_idx], ts[prior_idx]
+            r0 = prior_resid(R, t)
+            J = np.zeros((6, 6))
+            for a in range(6):
+                d = np.zeros(6); d[a] = 1e-6
+                dRp, dtp = se3_exp(d)
+                dRm, dtm = se3_exp(-d)
+                J[:, a] = (prior_resid(dRp @ R, dRp @ t + dtp) - prior_resid(dRm @ R, dRm @ t + dtm)) / 2e-6
+            c = 6 * fidx[prior_idx] + np.arange(6)
+            H[np.ix_(c, c)] += J.T @ Om_prior @ J
+            b[c] -= J.T @ Om_prior @ r0
+        return H, b
+
+    def optimize(n):
+        nonlocal Rs, ts, x
+        lam, ni, ok, it = 0.0, 2.0, True, 0
+        while it < n and ok:
+            cur = active(Rs, ts, x)
+            H, b = build()
+            if it == 0:
+                lam, ni = 1e-5 * np.abs(np.diag(H)).max(), 2.0
+            rho, q = 0.0, 0
+            while True:
+                try:
+                    dx = np.linalg.solve(H + lam * np.eye(dim), b)
+                    good = bool(np.all(np.isfinite(dx)))
+                except np.linalg.LinAlgError:
+                    good = False
+                if good:
+                    Rt, tt = list(Rs), list(ts)
+                    for i in free:
+                        dR, dt = se3_exp(dx[6 * fidx[i]: 6 * fidx[i] + 6])
+                        Rt[i], tt[i] = dR @ Rs[i], dR @ ts[i] + dt
+                    xt = x + dx[6 * nf:].reshape(L, 3)
+                    tmp = active(Rt, tt, xt)
+                else:
+                    dx = np.zeros(dim)
+                    tmp = np.finfo(float).max
+                rho = (cur - tmp) / (dx @ (lam * dx + b) + 1e-3)
+                if rho > 0 and np.isfinite(tmp) and good:
+                    lam *= max(1 / 3, min(1 - (2 * rho - 1) ** 3, 2 / 3))
+                    ni = 2.0
+                    cur, Rs, ts, x = tmp, Rt, tt, xt
+                else:
+                    lam *= ni
+                    ni *= 2
+                    if not np.isfinite(lam):
+                        break
+                q += 1
+                if not (rho < 0 and q < 10):
+                    break
+            if q == 10 or rho == 0 or not np.isfinite(lam):
+                ok = False
+            it += 1
+        return it
+
+    def str_chi2(l):
+        r, _, Om = str_resid(l, x[l])
+        return r @ Om @ r
+
+    iters = [optimize(5)]
+    for l in range(L):
+        if stype[l] == 1 and str_chi2(l) > tri_str_thresh * ba_lambda2:
+            slevel[l] = 1
+    iters.append(optimize(5))
+
+    def bad(e):
+        i, l = obs_kf[e], obs_pt[e]
+        return w[e] * (err[e] @ err[e]) > (7.815 if st[e] else 5.991) or not (Rs[i] @ x[l] + ts[i])[2] > 0
+
+    for e in range(E):
+        if bad(e):
+            level[e] = 1
+    state["robust"] = False
+    iters.append(optimize(40))
+    cleared = np.array([1 if stype[l] == 1 and str_chi2(l) > tri_str_thresh * ba_lambda2 else 0 for l in range(L)], np.uint8)
+    outl = np.array([1 if bad(e) else 0 for e in range(E)], np.uint8)
+    return dict(R=Rs, t=ts, pts=x, obs_outlier=outl, assoc_cleared=cleared, iters=iters)

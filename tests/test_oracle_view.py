@@ -134,3 +134,36 @@ def test_keyframe_associate_edge_cases(oracle, v1, golden_maps, gt_v1_03):
     # threads only shard the features
     out2 = oracle.keyframe_associate(comps, nbr, fr["pose0"][0], fr["obs"][0], depth, fr["octave"][0], nthreads=4)
     assert np.array_equal(out["assoc"], out2["assoc"]) and np.array_equal(out["pt3d"], out2["pt3d"], equal_nan=True)
+
+
+# ---------------------------------------------------------------- local bundle adjustment (oracle vs dense NumPy)
+@pytest.mark.parametrize("shape", [(4, 1, 60, -1, 1e-8, 1e-6), (5, 2, 80, 0, 1e-4, 1e-3)])
+def test_local_ba_oracle_matches_dense_numpy(oracle, shape):
+    """The oracle's Schur-complement LM agrees with a dense (no Schur) NumPy LM on the full normal equations.
+    With the prior edge the NumPy side uses a finite-difference Jacobian, so LM may stop a step apart."""
+    nk, nfix, npt, prior, tol_pose, tol_pts = shape
+    mean, cov = synth.make_map(3000, 0.7, seed=5)
+    comps = oracle.map_build(mean, cov)
+    pb = synth.make_ba_problem(mean, cov, nk, nfix, npt, seed=1 if prior < 0 else 2)
+    r = oracle.local_ba(comps, pb["pose"], pb["fixed"], pb["pts"], pb["assoc"], pb["obs_pt"], pb["obs_kf"], pb["obs"],
+                        pb["octave"], prior_idx=prior)
+    d = ref.local_ba_dense(comps, pb["pose"], pb["fixed"], pb["pts"], pb["assoc"], pb["obs_pt"], pb["obs_kf"], pb["obs"],
+                           pb["octave"], prior_idx=prior)
+    assert list(r["iters"][:2]) == d["iters"][:2] == [5, 5]
+    if prior < 0:
+        assert list(r["iters"]) == d["iters"]
+    for i in range(nk):
+        Ro, to = ref.pose_Rt(r["pose"][i])
+        assert ref.rot_angle(Ro, d["R"][i]) < tol_pose and np.abs(to - d["t"][i]).max() < tol_pose
+    assert np.abs(r["pts"] - d["pts"]).max() < tol_pts
+    assert np.array_equal(r["obs_outlier"], d["obs_outlier"]) and np.array_equal(r["assoc_cleared"], d["assoc_cleared"])
+    assert r["obs_outlier"].sum() > 0
+
+
+def test_se3_log_inverts_exp(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        xi = np.concatenate([rng.normal(size=3) * 0.3, rng.normal(size=3)])
+        pose = oracle.se3_oplus(xi, np.array([0, 0, 0, 1, 0, 0, 0.0]))
+        np.testing.assert_allclose(oracle.se3_log(pose), xi, atol=1e-12)
+    np.testing.assert_allclose(oracle.se3_log(np.array([0, 0, 0, 1, 1, 2, 3.0])), [0, 0, 0, 1, 2, 3], atol=1e-15)
