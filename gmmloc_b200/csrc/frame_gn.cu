@@ -44,13 +44,29 @@ constexpr int kAcc = 27;  // 21 upper-triangular entries of the 6x6 + 6 rhs
 
 enum : uint8_t { F_STEREO = 1, F_STR = 2, F_FREE = 4, F_DEG = 8 };
 
-__device__ __forceinline__ void structure(const FrameArgs& a, const double* R, int k, uint8_t fl, const Vec3& xw, Sym3& S,
-                                          Vec3& s) {
+// component constants of one structure edge, gathered ONCE per point and sweep (L2 latency is what bounds
+// this kernel): planar => n = axis_.col(0) in c[0..2]; otherwise the 6 unique entries of cov_inv in c[0..5]
+struct StrConst {
+  double mu[3];
+  double c[6];
+};
+__device__ __forceinline__ void load_structure(const FrameArgs& a, int k, uint8_t fl, StrConst& sc) {
   const double* mu = a.mean + (size_t)k * 3;
-  const Vec3 d = {xw.x - mu[0], xw.y - mu[1], xw.z - mu[2]};
+  sc.mu[0] = mu[0]; sc.mu[1] = mu[1]; sc.mu[2] = mu[2];
   if (fl & F_DEG) {
     const double* ax = a.axis + (size_t)k * 9;
-    const Vec3 n = {ax[0], ax[3], ax[6]};  // axis_.col(0)
+    sc.c[0] = ax[0]; sc.c[1] = ax[3]; sc.c[2] = ax[6];  // axis_.col(0)
+    sc.c[3] = sc.c[4] = sc.c[5] = 0.0;
+  } else {
+    const double* A = a.cov_inv + (size_t)k * 9;
+    sc.c[0] = A[0]; sc.c[1] = A[1]; sc.c[2] = A[2]; sc.c[3] = A[4]; sc.c[4] = A[5]; sc.c[5] = A[8];
+  }
+}
+__device__ __forceinline__ void structure(const FrameArgs& a, const double* R, const StrConst& sc, uint8_t fl, const Vec3& xw,
+                                          Sym3& S, Vec3& s) {
+  const Vec3 d = {xw.x - sc.mu[0], xw.y - sc.mu[1], xw.z - sc.mu[2]};
+  if (fl & F_DEG) {
+    const Vec3 n = {sc.c[0], sc.c[1], sc.c[2]};
     const double es = n.x * d.x + n.y * d.y + n.z * d.z;
     const Vec3 nc = rot(R, n);
     const double lam = a.prm.ba_lambda2;
@@ -59,8 +75,7 @@ __device__ __forceinline__ void structure(const FrameArgs& a, const double* R, i
     s = {c * nc.x, c * nc.y, c * nc.z};
   } else {
     // EdgePt2Gaussian: J = L^T, Omega = I  =>  Hessian L L^T = cov_inv, rhs -cov_inv d
-    const double* A = a.cov_inv + (size_t)k * 9;
-    const Sym3 Sw = {A[0], A[1], A[2], A[4], A[5], A[8]};
+    const Sym3 Sw = {sc.c[0], sc.c[1], sc.c[2], sc.c[3], sc.c[4], sc.c[5]};
     const Vec3 bw = mul(Sw, d);
     s = rot(R, {-bw.x, -bw.y, -bw.z});
     // S_c = R Sw R^T
@@ -80,6 +95,81 @@ __device__ __forceinline__ void structure(const FrameArgs& a, const double* R, i
   }
 }
 
+// Schur contribution of one point to the reduced pose system at linearisation point (R, t, xw)
+// (pass-1 body): acc += A^T M A, A^T v.  Returns false when Hll is singular.
+__device__ __forceinline__ bool pose_contribution(const FrameArgs& a, const double* R, const double* t, const StrConst& sc,
+                                                  uint8_t b, const Vec3& xw, const float* ob, double w, double* acc) {
+  const FrameParamsDev& P = a.prm;
+  Vec3 pc = rot(R, xw);
+  pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
+  Sym3 G;
+  Vec3 h;
+  reproj(P, pc, ob[0], ob[1], ob[2], b & F_STEREO, w, P.robust != 0, G, h);
+  Sym3 M;
+  Vec3 v;
+  bool ok = true;
+  if (!(b & F_FREE)) {
+    M = G;
+    v = h;
+  } else {
+    Sym3 S;
+    Vec3 s;
+    structure(a, R, sc, b, xw, S, s);
+    const Sym3 D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
+    const Sym3 Di = inv_sym(D, ok);
+    // T = G Di (general 3x3)
+    const double T00 = G.xx * Di.xx + G.xy * Di.xy + G.xz * Di.xz, T01 = G.xx * Di.xy + G.xy * Di.yy + G.xz * Di.yz,
+                 T02 = G.xx * Di.xz + G.xy * Di.yz + G.xz * Di.zz;
+    const double T10 = G.xy * Di.xx + G.yy * Di.xy + G.yz * Di.xz, T11 = G.xy * Di.xy + G.yy * Di.yy + G.yz * Di.yz,
+                 T12 = G.xy * Di.xz + G.yy * Di.yz + G.yz * Di.zz;
+    const double T20 = G.xz * Di.xx + G.yz * Di.xy + G.zz * Di.xz, T21 = G.xz * Di.xy + G.yz * Di.yy + G.zz * Di.yz,
+                 T22 = G.xz * Di.xz + G.yz * Di.yz + G.zz * Di.zz;
+    const Vec3 bl = {h.x + s.x, h.y + s.y, h.z + s.z};
+    v = {h.x - (T00 * bl.x + T01 * bl.y + T02 * bl.z), h.y - (T10 * bl.x + T11 * bl.y + T12 * bl.z),
+         h.z - (T20 * bl.x + T21 * bl.y + T22 * bl.z)};
+    // M = T S (symmetric in exact arithmetic; upper triangle taken)
+    M.xx = T00 * S.xx + T01 * S.xy + T02 * S.xz;
+    M.xy = T00 * S.xy + T01 * S.yy + T02 * S.yz;
+    M.xz = T00 * S.xz + T01 * S.yz + T02 * S.zz;
+    M.yy = T10 * S.xy + T11 * S.yy + T12 * S.yz;
+    M.yz = T10 * S.xz + T11 * S.yz + T12 * S.zz;
+    M.zz = T20 * S.xz + T21 * S.yz + T22 * S.zz;
+  }
+  accumulate_pose(acc, pc, M, v);
+  return ok;
+}
+
+// point update at linearisation point (R, t, xw) for the pose step (om, up) (pass-2 body)
+__device__ __forceinline__ bool point_update(const FrameArgs& a, const double* R, const double* t, const StrConst& sc, uint8_t b,
+                                             const Vec3& om, const Vec3& up, const float* ob, double w, Vec3& xw) {
+  const FrameParamsDev& P = a.prm;
+  Vec3 pc = rot(R, xw);
+  pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
+  Vec3 ad = cross(om, pc);  // A dxi = omega x pc + upsilon
+  ad.x += up.x; ad.y += up.y; ad.z += up.z;
+  // (a free stereo point without a structure edge has the closed form dc = P^-1 e - ad, but taking
+  //  it as a separate branch diverges nearly every warp; measured slower than the uniform path)
+  Sym3 G;
+  Vec3 h;
+  reproj(P, pc, ob[0], ob[1], ob[2], b & F_STEREO, w, P.robust != 0, G, h);
+  Sym3 D = G;
+  Vec3 bl = h;
+  if (b & F_STR) {
+    Sym3 S;
+    Vec3 s;
+    structure(a, R, sc, b, xw, S, s);
+    D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
+    bl = {h.x + s.x, h.y + s.y, h.z + s.z};
+  }
+  bool ok;
+  const Sym3 Di = inv_sym(D, ok);
+  const Vec3 ga = mul(G, ad);
+  const Vec3 dc = mul(Di, {bl.x - ga.x, bl.y - ga.y, bl.z - ga.z});
+  const Vec3 dw = rot_t(R, dc);
+  xw.x += dw.x; xw.y += dw.y; xw.z += dw.z;
+  return ok && isfinite(xw.x) && isfinite(xw.y) && isfinite(xw.z);
+}
+
 // numeric-failure contract (shared with the oracle): a frame whose solve hits a singular Hll / reduced
 // system or a non-finite value is returned UNSOLVED (normalised pose0, input landmarks) with
 // GMMLOC_FRAME_NUMERIC set.
@@ -87,7 +177,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(cons
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[kWarps][kAcc];
   __shared__ double s_acc[kAcc];
-  __shared__ double s_pose[7], s_R[9], s_dxi[6];
+  __shared__ double s_pose[7], s_R[9], s_dxi[6], s_Ro[9], s_to[3];
   __shared__ int s_fail1, s_fail2;
 
   const int f = blockIdx.x;
@@ -117,6 +207,8 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(cons
     for (int i = 0; i < 7; ++i) s_pose[i] = q[i];
     quat_to_rot(q, s_R);
     for (int i = 0; i < 6; ++i) s_dxi[i] = 0.0;
+    for (int i = 0; i < 9; ++i) s_Ro[i] = s_R[i];
+    for (int i = 0; i < 3; ++i) s_to[i] = q[4 + i];
     s_fail1 = 0;
     s_fail2 = 0;
   }
@@ -156,62 +248,51 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(cons
   }
   __syncthreads();
 
-  for (int it = 0; it < P.gn_iters; ++it) {
-    double R[9], t[3];
+  // Sweep schedule.  Iteration i of the reference is: linearise at state_i -> solve the reduced pose system ->
+  // back-substitute the points (same linearisation point).  The back-substitution of iteration i and the
+  // linearisation of iteration i+1 visit the same point with the same component constants, so they are FUSED
+  // into one sweep: per point  [update x with dxi_i at (R_i, t_i)]  then  [accumulate at (R_{i+1}, t_{i+1}, x_{i+1})].
+  // gn_iters + 1 sweeps instead of 2 gn_iters, half the component gathers and barriers; per-point arithmetic and
+  // the reduction order are unchanged.
+  //   sweep 0           : accumulate only (state_0)
+  //   sweep 1..iters-1  : update with dxi_{s-1}, accumulate at state_s
+  //   sweep iters       : update only
+  const int iters = P.gn_iters;
+  const int sweeps = (iters > 0) ? iters + 1 : 0;
+  for (int sw = 0; sw < sweeps; ++sw) {
+    const bool do_update = pts_free && sw > 0;
+    const bool do_acc = pose_free && sw < iters;
+    if (!do_update && !do_acc) continue;
+    // s_Ro / s_to: linearisation point of the update (state sw-1); s_R / s_pose: state sw
+    const Vec3 om = {s_dxi[0], s_dxi[1], s_dxi[2]}, up = {s_dxi[3], s_dxi[4], s_dxi[5]};
+    double acc[kAcc];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = s_R[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) t[i] = s_pose[4 + i];
-
-    // ---- pass 1: accumulate the reduced pose system ----
-    if (pose_free) {
-      double acc[kAcc];
-#pragma unroll
-      for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
-      bool bad = false;
-      for (int i = tid; i < N; i += kThreads) {
-        const uint8_t b = fl[i];
-        const bool free_pt = b & F_FREE, str = b & F_STR;
-        if (free_pt && !str) continue;  // contributes exactly zero (see header)
-        const Vec3 xw = {xs[i * 3], xs[i * 3 + 1], xs[i * 3 + 2]};
-        Vec3 pc = rot(R, xw);
-        pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
-        Sym3 G;
-        Vec3 h;
-        reproj(P, pc, obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2], b & F_STEREO, (double)P.s2inv[oct[i] & 7], P.robust != 0, G, h);
-        Sym3 M;
-        Vec3 v;
-        if (!free_pt) {
-          M = G;
-          v = h;
-        } else {
-          Sym3 S;
-          Vec3 s;
-          structure(a, R, asg[i], b, xw, S, s);
-          const Sym3 D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
-          bool ok;
-          const Sym3 Di = inv_sym(D, ok);
-          if (!ok) bad = true;
-          // T = G Di (general 3x3)
-          const double T00 = G.xx * Di.xx + G.xy * Di.xy + G.xz * Di.xz, T01 = G.xx * Di.xy + G.xy * Di.yy + G.xz * Di.yz,
-                       T02 = G.xx * Di.xz + G.xy * Di.yz + G.xz * Di.zz;
-          const double T10 = G.xy * Di.xx + G.yy * Di.xy + G.yz * Di.xz, T11 = G.xy * Di.xy + G.yy * Di.yy + G.yz * Di.yz,
-                       T12 = G.xy * Di.xz + G.yy * Di.yz + G.yz * Di.zz;
-          const double T20 = G.xz * Di.xx + G.yz * Di.xy + G.zz * Di.xz, T21 = G.xz * Di.xy + G.yz * Di.yy + G.zz * Di.yz,
-                       T22 = G.xz * Di.xz + G.yz * Di.yz + G.zz * Di.zz;
-          const Vec3 bl = {h.x + s.x, h.y + s.y, h.z + s.z};
-          v = {h.x - (T00 * bl.x + T01 * bl.y + T02 * bl.z), h.y - (T10 * bl.x + T11 * bl.y + T12 * bl.z),
-               h.z - (T20 * bl.x + T21 * bl.y + T22 * bl.z)};
-          // M = T S (symmetric in exact arithmetic; upper triangle taken)
-          M.xx = T00 * S.xx + T01 * S.xy + T02 * S.xz;
-          M.xy = T00 * S.xy + T01 * S.yy + T02 * S.yz;
-          M.xz = T00 * S.xz + T01 * S.yz + T02 * S.zz;
-          M.yy = T10 * S.xy + T11 * S.yy + T12 * S.yz;
-          M.yz = T10 * S.xz + T11 * S.yz + T12 * S.zz;
-          M.zz = T20 * S.xz + T21 * S.yz + T22 * S.zz;
-        }
-        accumulate_pose(acc, pc, M, v);
+    for (int i = 0; i < kAcc; ++i) acc[i] = 0.0;
+    bool bad1 = false, bad2 = false;
+    for (int i = tid; i < N; i += kThreads) {
+      const uint8_t b = fl[i];
+      const bool free_pt = b & F_FREE, str = b & F_STR;
+      const bool upd = do_update && free_pt;
+      const bool accp = do_acc && !(free_pt && !str);  // a free point without a structure edge contributes exactly zero
+      if (!upd && !accp) continue;
+      Vec3 xw = {xs[i * 3], xs[i * 3 + 1], xs[i * 3 + 2]};
+      const float ob[3] = {obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2]};
+      const double w = (double)P.s2inv[oct[i] & 7];
+      StrConst sc;
+      if (str) load_structure(a, asg[i], b, sc);
+      if (upd) {
+        if (!point_update(a, s_Ro, s_to, sc, b, om, up, ob, w, xw)) bad2 = true;
+        xs[i * 3] = xw.x;
+        xs[i * 3 + 1] = xw.y;
+        xs[i * 3 + 2] = xw.z;
       }
+      if (accp) {
+        if (!pose_contribution(a, s_R, s_pose + 4, sc, b, xw, ob, w, acc)) bad1 = true;
+      }
+    }
+    if (bad2) s_fail2 = 1;
+    if (bad1) s_fail1 = 1;
+    if (do_acc) {
 #pragma unroll
       for (int i = 0; i < kAcc; ++i) {
         double s = acc[i];
@@ -219,8 +300,10 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(cons
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
         if (lane == 0) s_red[warp][i] = s;
       }
-      if (bad) s_fail1 = 1;
-      __syncthreads();
+    }
+    __syncthreads();
+    if (s_fail2) break;  // uniform: the update of iteration sw-1 failed
+    if (do_acc) {
       if (tid < kAcc) {
         double s = s_red[0][tid];
 #pragma unroll
@@ -233,9 +316,10 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(cons
         if (s_fail1 || !solve6(s_acc, dxi)) {
           s_fail1 = 1;
         } else {
-          // every thread already holds the old (R, t) in registers: the pose can be advanced now
           double np[7];
           se3_oplus(dxi, s_pose, np);
+          for (int i = 0; i < 9; ++i) s_Ro[i] = s_R[i];
+          for (int i = 0; i < 3; ++i) s_to[i] = s_pose[4 + i];
           for (int i = 0; i < 6; ++i) s_dxi[i] = dxi[i];
           for (int i = 0; i < 7; ++i) s_pose[i] = np[i];
           quat_to_rot(np, s_R);
@@ -243,48 +327,6 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(cons
       }
       __syncthreads();
       if (s_fail1) break;  // uniform
-    }
-
-    // ---- pass 2: back-substitution at the same linearisation point ----
-    if (pts_free) {
-      const Vec3 om = {s_dxi[0], s_dxi[1], s_dxi[2]}, up = {s_dxi[3], s_dxi[4], s_dxi[5]};
-      bool bad = false;
-      for (int i = tid; i < N; i += kThreads) {
-        const uint8_t b = fl[i];
-        if (!(b & F_FREE)) continue;
-        const Vec3 xw = {xs[i * 3], xs[i * 3 + 1], xs[i * 3 + 2]};
-        Vec3 pc = rot(R, xw);
-        pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
-        Vec3 ad = cross(om, pc);  // A dxi = omega x pc + upsilon
-        ad.x += up.x; ad.y += up.y; ad.z += up.z;
-        // (a free stereo point without a structure edge has the closed form dc = P^-1 e - ad, but taking
-        //  it as a separate branch diverges nearly every warp; measured slower than the uniform path)
-        Sym3 G;
-        Vec3 h;
-        reproj(P, pc, obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2], b & F_STEREO, (double)P.s2inv[oct[i] & 7], P.robust != 0, G, h);
-        Sym3 D = G;
-        Vec3 bl = h;
-        if (b & F_STR) {
-          Sym3 S;
-          Vec3 s;
-          structure(a, R, asg[i], b, xw, S, s);
-          D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
-          bl = {h.x + s.x, h.y + s.y, h.z + s.z};
-        }
-        bool ok;
-        const Sym3 Di = inv_sym(D, ok);
-        const Vec3 ga = mul(G, ad);
-        const Vec3 dc = mul(Di, {bl.x - ga.x, bl.y - ga.y, bl.z - ga.z});
-        const Vec3 dw = rot_t(R, dc);
-        const double n0 = xw.x + dw.x, n1 = xw.y + dw.y, n2 = xw.z + dw.z;
-        if (!ok || !isfinite(n0) || !isfinite(n1) || !isfinite(n2)) bad = true;
-        xs[i * 3] = n0;
-        xs[i * 3 + 1] = n1;
-        xs[i * 3 + 2] = n2;
-      }
-      if (bad) s_fail2 = 1;
-      __syncthreads();
-      if (s_fail2) break;  // uniform
     }
   }
   __syncthreads();
