@@ -150,6 +150,13 @@ class Context:
         capi.check(capi.lib().gmmloc_ctx_stats(self._h, C.byref(s)))
         return dict(points=s.points, flagged=s.flagged, kernel_launches=s.kernel_launches)
 
+    def set_assoc_kernel(self, kind: int) -> None:
+        """capi.ASSOC_AUTO / ASSOC_FFMA2 / ASSOC_TENSOR (tcgen05 pruning scan; identical results)."""
+        capi.check(capi.lib().gmmloc_ctx_set_assoc_kernel(self._h, int(kind)))
+
+    def last_assoc_kernel(self) -> str:
+        return "tensor" if capi.lib().gmmloc_ctx_last_assoc_kernel(self._h) else "ffma2"
+
     def kernel_times(self) -> dict:
         """Device ms of the last call's kernels (association scan, exact re-rank, frame GN)."""
         ms = (C.c_float * 3)()

@@ -15,6 +15,7 @@ OK, EINVAL, ENOMEM, ECUDA, ENUMERIC, EIO = range(6)
 MODE_JOINT, MODE_POSE_ONLY, MODE_POINTS_ONLY = 0, 1, 2
 FRAME_NUMERIC = 1
 VIEW_OVERFLOW = 1
+ASSOC_AUTO, ASSOC_FFMA2, ASSOC_TENSOR = 0, 1, 2
 
 
 class Camera(C.Structure):
@@ -65,6 +66,8 @@ SYMBOLS = {
     "gmmloc_ctx_synchronize": (_i, [_vp]),
     "gmmloc_ctx_stats": (_i, [_vp, C.POINTER(Stats)]),
     "gmmloc_ctx_kernel_times": (_i, [_vp, C.POINTER(C.c_float * 3)]),
+    "gmmloc_ctx_set_assoc_kernel": (_i, [_vp, _i]),
+    "gmmloc_ctx_last_assoc_kernel": (_i, [_vp]),
     "gmmloc_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "gmmloc_host_free": (None, [_vp]),
     "gmmloc_associate": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp]),

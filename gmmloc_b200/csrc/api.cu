@@ -223,6 +223,8 @@ struct gmmloc_ctx {
   cudaStream_t h2d = nullptr, d2h = nullptr;        // copy streams of the pipelined host entry point
   std::vector<cudaEvent_t> ev_in, ev_done;          // per-chunk events (inputs landed / results ready)
   gmmloc_stats_t stats{};
+  int assoc_kind = GMMLOC_ASSOC_AUTO;
+  int last_assoc_tc = 0;
 };
 
 extern "C" {
@@ -279,7 +281,7 @@ void gmmloc_map_destroy(gmmloc_map_t* m) {
   cudaSetDevice(m->device);
   cudaFree(m->d.mean); cudaFree(m->d.cov); cudaFree(m->d.cov_inv); cudaFree(m->d.det); cudaFree(m->d.scale);
   cudaFree(m->d.axis); cudaFree(m->d.sqrt_info); cudaFree(m->d.is_deg); cudaFree(m->d.is_sal); cudaFree(m->d.scan);
-  cudaFree(m->d.nbr_row_ptr); cudaFree(m->d.nbr_col);
+  cudaFree(m->d.nbr_row_ptr); cudaFree(m->d.nbr_col); cudaFree(m->d.tc_table);
   cudaSetDevice(prev);
   delete m;
 }
@@ -297,14 +299,17 @@ gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, 
   MapDev& d = m->d;
   d.K = K;
   d.Kpad = (K + kChunk - 1) / kChunk * kChunk;
-  double mmax = 0.0;
+  double mmax = 0.0, lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   for (size_t i = 0; i < (size_t)K * 3; ++i) {
     if (!std::isfinite(mean[i])) {
       delete m;
       return fail(GMMLOC_EINVAL, "non-finite mean");
     }
     mmax = std::fmax(mmax, std::fabs(mean[i]));
+    lo[i % 3] = std::fmin(lo[i % 3], mean[i]);
+    hi[i % 3] = std::fmax(hi[i % 3], mean[i]);
   }
+  for (int i = 0; i < 3; ++i) d.tc_centre[i] = (float)(0.5 * (lo[i] + hi[i]));  // tensor-core scan works on centred landmarks
   // landmarks are certified by the fp32 scan only inside |x|_inf <= xmax; anything farther out takes the
   // exact fp64 path (still correct, just slower)
   const double xmax = 1.5 * mmax + 1.0;
@@ -322,8 +327,9 @@ gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, 
   alloc((void**)&d.is_deg, K);
   alloc((void**)&d.is_sal, K);
   alloc((void**)&d.scan, sizeof(float) * kScanFloats * d.Kpad);
+  if (kChunk == 16) alloc((void**)&d.tc_table, (size_t)((d.Kpad + kTcTileComps - 1) / kTcTileComps) * kTcTileBytes);
   int* d_err = nullptr;
-  alloc((void**)&d_err, 2 * sizeof(int));
+  alloc((void**)&d_err, 4 * sizeof(int));
   if (e != cudaSuccess) {
     cudaFree(d_err);
     gmmloc_map_destroy(m);
@@ -336,10 +342,10 @@ gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, 
   };
   if ((e = cudaMemcpy(d.mean, mean, sizeof(double) * 3 * K, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D mean");
   if ((e = cudaMemcpy(d.cov, cov, sizeof(double) * 9 * K, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "H2D cov");
-  if ((e = cudaMemset(d_err, 0, 2 * sizeof(int))) != cudaSuccess) return bail(e, "memset");
+  if ((e = cudaMemset(d_err, 0, 4 * sizeof(int))) != cudaSuccess) return bail(e, "memset");
   if ((e = launch_map_build(d, deg_eps, xmax, d_err, reinterpret_cast<unsigned int*>(d_err + 1), nullptr)) != cudaSuccess)
     return bail(e, "map_build launch");
-  int h[2] = {0, 0};
+  int h[4] = {0, 0, 0, 0};
   if ((e = cudaMemcpy(h, d_err, sizeof h, cudaMemcpyDeviceToHost)) != cudaSuccess) return bail(e, "map_build");
   cudaFree(d_err);
   if (h[0] != 0) {
@@ -350,6 +356,8 @@ gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, 
   std::memcpy(&alpha, &h[1], 4);
   d.alpha = alpha;
   d.xmax = (float)xmax;
+  std::memcpy(&d.tc_err, &h[2], 4);
+  d.tc_ok = (d.tc_table != nullptr && h[3] == 0) ? 1 : 0;
   *out = m;
   return GMMLOC_OK;
 }
@@ -593,6 +601,13 @@ gmmloc_status_t gmmloc_ctx_kernel_times(gmmloc_ctx_t* ctx, float ms[3]) {
   return GMMLOC_OK;
 }
 
+gmmloc_status_t gmmloc_ctx_set_assoc_kernel(gmmloc_ctx_t* ctx, int kind) {
+  if (!ctx || kind < GMMLOC_ASSOC_AUTO || kind > GMMLOC_ASSOC_TENSOR) return fail(GMMLOC_EINVAL, "gmmloc_ctx_set_assoc_kernel: bad argument");
+  ctx->assoc_kind = kind;
+  return GMMLOC_OK;
+}
+int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx) { return ctx ? ctx->last_assoc_tc : 0; }
+
 gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out) {
   if (!out) return fail(GMMLOC_EINVAL, "null out");
   *out = nullptr;
@@ -617,8 +632,12 @@ gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* ma
   CU(cudaMemsetAsync(ctx->L().flag_count.p, 0, sizeof(int), ctx->L().stream));
   int launches = 0;
   CU(cudaEventRecord(ctx->L().ev[0], ctx->L().stream));
+  // kernel choice: variant 16 = tensor-core pruning scan, -1 = FFMA2 scan, 0 = launcher default
+  const int variant = ctx->assoc_kind == GMMLOC_ASSOC_TENSOR ? 16 : (ctx->assoc_kind == GMMLOC_ASSOC_FFMA2 ? -1 : 0);
+  int used_tc = 0;
   CU(launch_associate(map->d, d_pts_w, M, gate, d_assign, d_d2, ctx->L().flag_count.as<int>(), ctx->L().flag_idx.as<int32_t>(),
-                      ctx->L().flag_thr.as<float>(), 0, ctx->L().stream, &launches, ctx->L().ev[1]));
+                      ctx->L().flag_thr.as<float>(), variant, ctx->L().stream, &launches, ctx->L().ev[1], &used_tc));
+  ctx->last_assoc_tc = used_tc;
   CU(cudaEventRecord(ctx->L().ev[2], ctx->L().stream));
   ctx->L().ev_assoc = true;
   ctx->L().ev_gn = false;

@@ -17,7 +17,12 @@
 //     rigorous fp32 error bound alpha; everything else is pushed to a flag list.
 // K2: one warp per flagged landmark replays the fp32 scores (bit-identical: same score32()), and
 //     evaluates every candidate within the bound in fp64 with the oracle's operation order.
+#include <cuda_fp16.h>
 #include <math_constants.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -117,7 +122,47 @@ struct ScanArgs {
   int* flag_count;
   int32_t* flag_idx;
   float* flag_thr;
+  // tensor-core pruning scan only
+  const uint16_t* tc_table;
+  float cen[3];
+  float tc_err;    // bound of |sqrt(score_tc) - true distance|
+  float tc_delta;  // candidate margin in sqrt(score) units
+  float tc_slack;  // tc_delta - 2 (tc_err + alpha): guaranteed gap of every non-candidate component
 };
+
+// Certificate on exact fp32 scores: s1 = score32 of the candidate winner idx, sec = a lower bound of
+// the score32 of every other component.  Certified => the assignment is written; otherwise the landmark goes to the
+// exact re-rank list with the squared radius inside which K2 must evaluate in fp64.
+__device__ __forceinline__ void finish_landmark(const ScanArgs& a, long long i, float px, float py, float pz, bool have_best,
+                                                int idx, float s1, float sec) {
+  bool certified = have_best;
+  double rt = CUDART_INF;
+  if (certified) {
+    const double r1 = sqrt((double)s1), r2 = sqrt((double)sec);
+    const double hi1 = r1 * (1.0 + kRelEps) + (double)a.alpha;  // upper bound of the winner's true distance
+    const double lo2 = r2 * (1.0 - kRelEps) - (double)a.alpha;  // lower bound of every other component's
+    certified = lo2 > hi1;
+    rt = (hi1 + (double)a.alpha) / (1.0 - kRelEps);
+  }
+  if (certified) {
+    if (a.d2 != nullptr || a.gate > 0.0) {
+      const double d = chi2_exact(a.mean + (size_t)idx * 3, a.cov_inv + (size_t)idx * 9, (double)px, (double)py, (double)pz);
+      if (a.gate > 0.0 && d > a.gate) idx = -1;
+      if (a.d2 != nullptr) a.d2[i] = (float)d;
+    }
+    a.assign[i] = idx;
+  } else {
+    float thr = CUDART_INF_F;
+    if (have_best) {
+      const double t2 = rt * rt;
+      thr = (float)t2;
+      if ((double)thr < t2) thr = nextafterf(thr, CUDART_INF_F);
+    }
+    const int pos = atomicAdd(a.flag_count, 1);
+    a.flag_idx[pos] = (int32_t)i;  // flag list is sized M; callers keep M < 2^31
+    a.flag_thr[pos] = thr;
+  }
+}
 
 template <int P, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) assoc_scan_kernel(const ScanArgs a) {
@@ -230,35 +275,8 @@ __global__ void __launch_bounds__(THREADS, MINB) assoc_scan_kernel(const ScanArg
         second = fminf(second, s);
       }
     }
-    const float sec = fminf(b2[p], second);
-    bool certified = finite_in && (jbest >= 0);
-    int idx = cid[p] * kChunk + (jbest < 0 ? 0 : jbest);
-    double rt = CUDART_INF;
-    if (certified) {
-      const double r1 = sqrt((double)b1[p]), r2 = sqrt((double)sec);
-      const double hi1 = r1 * (1.0 + kRelEps) + (double)a.alpha;  // upper bound of the winner's true distance
-      const double lo2 = r2 * (1.0 - kRelEps) - (double)a.alpha;  // lower bound of every other component's
-      certified = lo2 > hi1;
-      rt = (hi1 + (double)a.alpha) / (1.0 - kRelEps);
-    }
-    if (certified) {
-      if (a.d2 != nullptr || a.gate > 0.0) {
-        const double d = chi2_exact(a.mean + (size_t)idx * 3, a.cov_inv + (size_t)idx * 9, (double)px, (double)py, (double)pz);
-        if (a.gate > 0.0 && d > a.gate) idx = -1;
-        if (a.d2 != nullptr) a.d2[i] = (float)d;
-      }
-      a.assign[i] = idx;
-    } else {
-      float thr = CUDART_INF_F;
-      if (finite_in && jbest >= 0) {
-        const double t2 = rt * rt;
-        thr = (float)t2;
-        if ((double)thr < t2) thr = nextafterf(thr, CUDART_INF_F);
-      }
-      const int pos = atomicAdd(a.flag_count, 1);
-      a.flag_idx[pos] = (int32_t)i;  // flag list is sized M; callers keep M < 2^31
-      a.flag_thr[pos] = thr;
-    }
+    finish_landmark(a, i, px, py, pz, finite_in && (jbest >= 0), cid[p] * kChunk + (jbest < 0 ? 0 : jbest), b1[p],
+                    fminf(b2[p], second));
   }
 }
 
@@ -394,6 +412,419 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
   }
 }
 
+
+// ======================================================================================================
+// K1-TC: tensor-core pruning scan (tcgen05 / TMEM).
+//
+// The whitened coordinates y = U x - U mu of every (landmark, component) pair are a dense contraction with
+// K = 4 ([x y z 1] against [U | -U mu]); with fp16 operands and a 3-way hi/lo split folded into the K dimension
+// (hi*hi + lo*hi + hi*lo, 11 of 16 K slots) one tcgen05.mma kind::f16 M128 N48 K16 produces the three whitened
+// coordinates of 128 landmarks x 16 components (one chunk) to ~2^-21 relative accuracy, fp32 accumulators in
+// TMEM.  The CUDA cores then only square-and-add (3 packed FMA-pipe lane-ops per pair instead of 9) and fold the
+// chunk minimum.
+//
+// The tensor-core scores are used for PRUNING only, so exactness is untouched: per landmark the kernel keeps the
+// chunks whose minimum is within tc_delta (in sqrt-score units) of the running best; afterwards those candidate
+// chunks (typically 1-3 of K/16) are re-scored with the exact fp32 score32() of the FFMA2 scan and go through the
+// same certificate / exact re-rank path (finish_landmark, K2).  Every other component is farther than
+// tc_delta - 2 (tc_err + alpha) from the winner in exact fp32 scores, where tc_err is the rigorous bound of the
+// split / accumulation error computed at map build (map_build.cu) — that value enters the certificate as the
+// lower bound of the non-candidates.
+//
+// CTA = 6 warps: warp 0 streams the B tiles (TMA bulk copies of the pre-laid-out UMMA table) — lane 0;
+// warp 1 allocates TMEM and issues the MMAs (lane 0); warps 2-5 are the epilogue (thread = landmark row, TMEM lane
+// quadrant = warp % 4).  kTcATiles landmark tiles of 128 stay in shared memory as A operands, so every B chunk
+// is used kTcATiles times; kTcBufs accumulator buffers of 48 TMEM columns keep that many MMAs in flight (the
+// MMA -> commit -> mbarrier round trip is ~600 cycles, far longer than one 128 x 48 x 16 MMA).
+constexpr bool kTcAutoDefault = false;  // flipped once the kernel has been validated and measured on the GPU
+constexpr int kTcATiles = 8;                 // landmark tiles of 128 per CTA (every B tile is used 8 times)
+constexpr int kTcLm = 128 * kTcATiles;       // landmarks per CTA
+constexpr int kTcBufs = 2;                   // 2 x 192 = 384 of the 512 TMEM columns (one CTA per SM)
+constexpr int kTcTmemCols = 512;
+constexpr int kTcStageTiles = 4;             // 64-component tiles per B stage
+constexpr int kTcStageBytes = kTcStageTiles * kTcTileBytes;  // 24 KB
+constexpr int kTcStages = 2;
+constexpr int kTcCand = 4;                   // candidate chunks remembered per (landmark, tile half)
+constexpr int kTcEpiWarps = 8;               // two per TMEM lane quadrant: each takes 32 of a tile's 64 components
+constexpr int kTcThreads = 64 + 32 * kTcEpiWarps;
+constexpr int kTcABytes = 128 * kTcK * 2;    // one A tile: 4 KB
+// dynamic shared memory layout
+constexpr int kTcOffA = 0;
+constexpr int kTcOffB = kTcOffA + kTcATiles * kTcABytes;
+constexpr int kTcOffBar = kTcOffB + kTcStages * kTcStageBytes;
+constexpr int kTcOffCandId = kTcOffBar + 128;  // barriers: bfull[2] bempty[2] tfull[2] tempty[2]
+constexpr int kTcOffCandM = kTcOffCandId + kTcLm * 2 * kTcCand * 2;
+constexpr int kTcOffState = kTcOffCandM + kTcLm * 2 * kTcCand * 4;  // per (landmark, half): b1, evmin, ncand
+constexpr int kTcSmem = kTcOffState + kTcLm * 2 * 12;
+
+// kind::f16 (fp16 x fp16 -> fp32), A and B K-major, M = 128, N = 192 (cute::UMMA::InstrDescriptor bit layout)
+constexpr uint32_t kTcIdesc = (1u << 4) | ((uint32_t)(kTcRows >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// K-major, no-swizzle UMMA shared-memory descriptor: canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kTcIdesc), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+
+// slow path of the epilogue (rare): chunk `c` with tensor-core minimum `mch` is within the margin of the running
+// best of list `li` (one list per landmark and tile half).  The list stays in ascending chunk order; when it is full
+// the entry with the largest minimum is dropped and the smallest dropped value is remembered (evmin): the landmark
+// stays certifiable iff that value ends up outside the final margin.
+__device__ __noinline__ void tc_candidate(float mch, int c, int li, float delta, uint16_t* cand_id, float* cand_m, float& b1,
+                                          float& thr, int& ncand, float& evmin) {
+  if (mch < b1) {
+    b1 = mch;
+    const float r = sqrtf(mch) * (1.f + 1e-6f) + delta;
+    thr = r * r * (1.f + 1e-6f);
+  }
+  uint16_t* id = cand_id + li * kTcCand;
+  float* cm = cand_m + li * kTcCand;
+  if (ncand == kTcCand) {  // drop the entries the improved best has pushed out of the margin
+    int n = 0;
+    for (int q = 0; q < kTcCand; ++q)
+      if (cm[q] <= thr) {
+        cm[n] = cm[q];
+        id[n] = id[q];
+        ++n;
+      }
+    ncand = n;
+  }
+  if (ncand == kTcCand) {
+    int w = 0;
+    for (int q = 1; q < kTcCand; ++q)
+      if (cm[q] > cm[w]) w = q;
+    if (mch >= cm[w]) {
+      evmin = fminf(evmin, mch);  // the new chunk itself is the worst: it is the one dropped
+    } else {
+      evmin = fminf(evmin, cm[w]);
+      for (int q = w; q + 1 < kTcCand; ++q) {
+        cm[q] = cm[q + 1];
+        id[q] = id[q + 1];
+      }
+      cm[kTcCand - 1] = mch;
+      id[kTcCand - 1] = (uint16_t)c;
+    }
+  } else {
+    cm[ncand] = mch;
+    id[ncand] = (uint16_t)c;
+    ++ncand;
+  }
+}
+
+#ifdef GMMLOC_TC_DEBUG
+#define TC_T0() const long long t_dbg0 = clock64()
+#define TC_ACC(var) var += clock64() - t_dbg0
+#else
+#define TC_T0()
+#define TC_ACC(var)
+#endif
+__global__ void __launch_bounds__(kTcThreads, 1) assoc_scan_tc_kernel(const ScanArgs a) {
+  long long dbg_wait_full = 0, dbg_wait_empty = 0, dbg_wait_ld = 0;
+  const long long dbg_start = clock64();
+  (void)dbg_wait_full; (void)dbg_wait_empty; (void)dbg_wait_ld; (void)dbg_start;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + kTcOffBar);
+  uint64_t* bfull = bars;
+  uint64_t* bempty = bars + kTcStages;
+  uint64_t* tfull = bars + 2 * kTcStages;
+  uint64_t* tempty = tfull + kTcBufs;
+  uint16_t* cand_id = reinterpret_cast<uint16_t*>(smem_raw + kTcOffCandId);
+  float* cand_m = reinterpret_cast<float*>(smem_raw + kTcOffCandM);
+  float* st_b1 = reinterpret_cast<float*>(smem_raw + kTcOffState);  // [kTcLm * 2]
+  float* st_ev = st_b1 + kTcLm * 2;
+  int* st_n = reinterpret_cast<int*>(st_ev + kTcLm * 2);
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long base = (long long)blockIdx.x * kTcLm;
+  const int ntiles = (a.Kpad + kTcTileComps - 1) / kTcTileComps;
+  const int nstages = (ntiles + kTcStageTiles - 1) / kTcStageTiles;
+
+  if (tid == 0) {
+    for (int i = 0; i < kTcStages; ++i) {
+      mbar_init(&bfull[i], 1);
+      mbar_init(&bempty[i], 1);
+    }
+    for (int i = 0; i < kTcBufs; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], kTcEpiWarps);  // one arrival per epilogue warp (per-thread arrivals serialise on the barrier)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTcTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // ---- the 256 epilogue threads write the A operand rows: thread (row, hh) does the tiles t = hh, hh + 2, ... ----
+  const int row = (warp & 3) * 32 + lane;            // TMEM lane = landmark row of a tile (epilogue warps only)
+  const int hh = (warp >= 2) ? ((warp - 2) >> 2) : 0;  // which 32 components of every tile this warp folds
+  if (warp >= 2) {
+    for (int t = hh; t < kTcATiles; t += 2) {
+      const long long i = base + t * 128 + row;
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (i < a.M) {
+        x = __ldg(a.pts + i * 3 + 0);
+        y = __ldg(a.pts + i * 3 + 1);
+        z = __ldg(a.pts + i * 3 + 2);
+      }
+      const float v[3] = {x - a.cen[0], y - a.cen[1], z - a.cen[2]};
+      __half hi[3], lo[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        hi[c] = __float2half_rn(v[c]);
+        lo[c] = __float2half_rn(v[c] - __half2float(hi[c]));
+      }
+      const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+      // K slots 0..7: v_hi(3) 1 v_lo(3) 1      K slots 8..15: v_hi(3) 0 0 0 0 0
+      const __half k0[8] = {hi[0], hi[1], hi[2], one, lo[0], lo[1], lo[2], one};
+      const __half k1[8] = {hi[0], hi[1], hi[2], zero, zero, zero, zero, zero};
+      unsigned char* At = smem_raw + kTcOffA + t * kTcABytes;
+      *reinterpret_cast<uint4*>(At + row * 16) = *reinterpret_cast<const uint4*>(k0);
+      *reinterpret_cast<uint4*>(At + 128 * 16 + row * 16) = *reinterpret_cast<const uint4*>(k1);
+    }
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // A rows visible to the tensor core's async proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = s_tmem;
+
+  if (warp == 0) {
+    // ===== B producer: one TMA bulk copy per stage of kTcStageTiles tiles =====
+    if (lane == 0) {
+      for (int st = 0; st < nstages; ++st) {
+        const int slot = st % kTcStages;
+        if (st >= kTcStages) mbar_wait(&bempty[slot], (uint32_t)(((st / kTcStages) - 1) & 1));
+        const int nt = min(kTcStageTiles, ntiles - st * kTcStageTiles);
+        const uint32_t bytes = (uint32_t)nt * kTcTileBytes;
+        mbar_expect_tx(&bfull[slot], bytes);
+        tma_bulk_g2s(smem_raw + kTcOffB + slot * kTcStageBytes,
+                     reinterpret_cast<const unsigned char*>(a.tc_table) + (size_t)st * kTcStageBytes, bytes, &bfull[slot]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulator s = tile * kTcATiles + t lives in TMEM buffer s % 2 =====
+    if (lane == 0) {
+      const uint32_t a0 = smem_u32(smem_raw + kTcOffA), b0 = smem_u32(smem_raw + kTcOffB);
+      uint32_t buf = 0, use = 0;  // use = s / kTcBufs
+      for (int st = 0; st < nstages; ++st) {
+        const int slot = st % kTcStages;
+        mbar_wait(&bfull[slot], (uint32_t)((st / kTcStages) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int nt = min(kTcStageTiles, ntiles - st * kTcStageTiles);
+        for (int c = 0; c < nt; ++c) {
+          const uint64_t bd = tc_desc(b0 + slot * kTcStageBytes + c * kTcTileBytes, kTcRows * 16, 128);
+#pragma unroll
+          for (int t = 0; t < kTcATiles; ++t) {
+            if (use > 0) {
+              TC_T0();
+              mbar_wait(&tempty[buf], (use - 1) & 1);
+              TC_ACC(dbg_wait_empty);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            tc_mma(tmem + buf * 256, tc_desc(a0 + t * kTcABytes, 128 * 16, 128), bd);
+            tc_commit(&tfull[buf]);
+            if (++buf == kTcBufs) {
+              buf = 0;
+              ++use;
+            }
+          }
+        }
+        tc_commit(&bempty[slot]);  // fires when every MMA reading this stage has completed
+      }
+#ifdef GMMLOC_TC_DEBUG
+      if (blockIdx.x == 100) printf("issuer: total %lld wait_empty %lld\n", clock64() - dbg_start, dbg_wait_empty);
+#endif
+    }
+  } else {
+    // ===== epilogue: warp (q, hh) folds components [32 hh, 32 hh + 32) of every tile for the landmark rows of TMEM
+    // lane quadrant q = warp % 4 =====
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    float b1[kTcATiles], thr[kTcATiles], evmin[kTcATiles];
+    int ncand[kTcATiles];
+#pragma unroll
+    for (int t = 0; t < kTcATiles; ++t) {
+      b1[t] = CUDART_INF_F;
+      thr[t] = CUDART_INF_F;
+      evmin[t] = CUDART_INF_F;  // smallest chunk minimum ever evicted from the candidate list
+      ncand[t] = 0;
+    }
+    // Per accumulator: drain this warp's 96 TMEM columns into registers at once and hand the buffer straight back
+    // to the MMA issuer (the MMA -> commit -> wake round trip bounds this kernel, so a buffer must not be held
+    // while the arithmetic runs).
+    uint32_t buf = 0, use = 0;
+    for (int c = 0; c < ntiles; ++c) {
+#pragma unroll
+      for (int t = 0; t < kTcATiles; ++t) {
+        uint32_t y[96];
+        {
+          TC_T0();
+          mbar_wait(&tfull[buf], use & 1);
+          TC_ACC(dbg_wait_full);
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tb = tmem + lane_base + buf * 256 + hh * 32;
+        {
+          TC_T0();
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            tc_ld16(tb + r * kTcTileComps, y + r * 32);
+            tc_ld16(tb + r * kTcTileComps + 16, y + r * 32 + 16);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          TC_ACC(dbg_wait_ld);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[buf]);
+        if (++buf == kTcBufs) {
+          buf = 0;
+          ++use;
+        }
+        TC_T0();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          // registers [0,32) y0 | [32,64) y1 | [64,96) y2 of this warp's 32 components; chunk h = 16 of them
+          uint64_t acc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint64_t u0 = pack2u(y[16 * h + 2 * j], y[16 * h + 2 * j + 1]);
+            const uint64_t u1 = pack2u(y[32 + 16 * h + 2 * j], y[32 + 16 * h + 2 * j + 1]);
+            const uint64_t u2 = pack2u(y[64 + 16 * h + 2 * j], y[64 + 16 * h + 2 * j + 1]);
+            acc[j] = fma2(u2, u2, fma2(u1, u1, mul2(u0, u0)));
+          }
+          float mch = CUDART_INF_F;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float s0, s1;
+            unpack2(acc[j], s0, s1);
+            mch = fminf(fminf(mch, s0), s1);
+          }
+          if (mch <= thr[t])  // rare: this chunk is within the margin of the running best
+            tc_candidate(mch, 4 * c + 2 * hh + h, (t * 128 + row) * 2 + hh, a.tc_delta, cand_id, cand_m, b1[t], thr[t], ncand[t],
+                         evmin[t]);
+        }
+        TC_ACC(dbg_wait_empty);
+      }
+    }
+#ifdef GMMLOC_TC_DEBUG
+    if (blockIdx.x == 100 && tid == 64)
+      printf("epilogue main loop: %lld cycles, wait_full %lld ld %lld compute %lld\n", clock64() - dbg_start, dbg_wait_full, dbg_wait_ld, dbg_wait_empty);
+#endif
+#pragma unroll
+    for (int t = 0; t < kTcATiles; ++t) {
+      const int li = (t * 128 + row) * 2 + hh;
+      st_b1[li] = b1[t];
+      st_ev[li] = evmin[t];
+      st_n[li] = ncand[t];
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols));
+  }
+  if (warp < 2) return;
+  // ---- merge the two halves of every landmark, exact fp32 re-score of the candidate chunks, usual certificate.
+  // thread (row, hh) finishes the tiles t = hh, hh + 2, ... ----
+  for (int t = hh; t < kTcATiles; t += 2) {
+    const long long i = base + t * 128 + row;
+    if (i >= a.M) continue;
+    const int l2 = (t * 128 + row) * 2;
+    const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
+    const bool finite_in = (fabsf(px) <= a.xmax) && (fabsf(py) <= a.xmax) && (fabsf(pz) <= a.xmax);  // false for NaN
+    const float bb = fminf(st_b1[l2], st_b1[l2 + 1]);  // tensor-core best over all components
+    float thr = CUDART_INF_F;
+    if (bb < CUDART_INF_F) {
+      const float r = sqrtf(bb) * (1.f + 1e-6f) + a.tc_delta;
+      thr = r * r * (1.f + 1e-6f);
+    }
+    const float ev = fminf(st_ev[l2], st_ev[l2 + 1]);
+    float s1 = CUDART_INF_F, s2 = CUDART_INF_F;
+    int idx = -1;
+    if (finite_in && !(ev <= thr)) {  // an evicted chunk inside the final margin: not certifiable here
+      // ascending component order over both lists (each list is ascending; chunks of the two halves interleave)
+      int q0 = 0, q1 = 0;
+      const int n0 = st_n[l2], n1 = st_n[l2 + 1];
+      while (q0 < n0 || q1 < n1) {
+        const int c0 = q0 < n0 ? (int)cand_id[l2 * kTcCand + q0] : 0x7fffffff;
+        const int c1 = q1 < n1 ? (int)cand_id[(l2 + 1) * kTcCand + q1] : 0x7fffffff;
+        int ch;
+        float cm;
+        if (c0 < c1) {
+          ch = c0;
+          cm = cand_m[l2 * kTcCand + q0++];
+        } else {
+          ch = c1;
+          cm = cand_m[(l2 + 1) * kTcCand + q1++];
+        }
+        if (!(cm <= thr) || ch * kChunk >= a.Kpad) continue;  // outside the final margin / chunk of the table padding
+        for (int j = 0; j < kChunk; ++j) {
+          const float sc = score_of(a.scan, ch * kChunk + j, px, py, pz);
+          if (sc < s1) {  // ascending component order, strict '<'
+            s2 = s1;
+            s1 = sc;
+            idx = ch * kChunk + j;
+          } else {
+            s2 = fminf(s2, sc);
+          }
+        }
+      }
+    }
+    if (idx >= 0) {
+      // every non-candidate component is farther than tc_slack (sqrt-score units) from the winner in exact fp32 scores
+      const float r = sqrtf(s1) * (1.f - 1e-6f) + a.tc_slack;
+      finish_landmark(a, i, px, py, pz, true, idx, s1, fminf(s2, r * r * (1.f - 1e-6f)));
+    } else {
+      // not certifiable here (candidate list overflowed, or the landmark is outside the certified box): exact
+      // re-rank.  Inside the box the tensor-core best still bounds the winner's true distance, which keeps the
+      // radius K2 has to search finite.
+      float thr2 = CUDART_INF_F;
+      if (finite_in && bb < CUDART_INF_F) {
+        const double rt = (sqrt((double)bb) * (1.0 + 1e-6) + (double)a.tc_err + 2.0 * (double)a.alpha) / (1.0 - kRelEps);
+        const double t2 = rt * rt;
+        thr2 = (float)t2;
+        if ((double)thr2 < t2) thr2 = nextafterf(thr2, CUDART_INF_F);
+      }
+      const int pos = atomicAdd(a.flag_count, 1);
+      a.flag_idx[pos] = (int32_t)i;
+      a.flag_thr[pos] = thr2;
+    }
+  }
+}
+
+cudaError_t launch_scan_tc(const ScanArgs& a, cudaStream_t stream) {
+  cudaError_t e = cudaFuncSetAttribute(assoc_scan_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+  if (e != cudaSuccess) return e;
+  const long long grid = (a.M + kTcLm - 1) / kTcLm;
+  assoc_scan_tc_kernel<<<(unsigned)grid, kTcThreads, kTcSmem, stream>>>(a);
+  return cudaGetLastError();
+}
+
 template <int P, int THREADS, int MINB>
 cudaError_t launch_scan_t(const ScanArgs& a, cudaStream_t stream) {
   const size_t smem = (size_t)kStages * kTileBytes + kStages * sizeof(uint64_t);
@@ -411,7 +842,7 @@ cudaError_t launch_scan_t(const ScanArgs& a, cudaStream_t stream) {
 // flag buffers hold M entries.  Returns the number of kernels launched through *launches.
 cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, double gate, int32_t* d_assign,
                              float* d_d2, int* d_flag_count, int32_t* d_flag_idx, float* d_flag_thr, int variant,
-                             cudaStream_t stream, int* launches, cudaEvent_t ev_between) {
+                             cudaStream_t stream, int* launches, cudaEvent_t ev_between, int* used_tc) {
   ScanArgs a;
   a.scan = m.scan;
   a.mean = m.mean;
@@ -428,20 +859,50 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
   a.flag_count = d_flag_count;
   a.flag_idx = d_flag_idx;
   a.flag_thr = d_flag_thr;
+  a.tc_table = m.tc_table;
+  a.cen[0] = m.tc_centre[0]; a.cen[1] = m.tc_centre[1]; a.cen[2] = m.tc_centre[2];
+  {
+    // candidate margin: wide enough that the certificate's gap 2 alpha (1 + eps) fits inside the guaranteed slack
+    const float need = 2.0f * (m.tc_err + m.alpha);
+    a.tc_err = m.tc_err;
+    a.tc_delta = fmaxf(1.0f, 1.25f * need + 8.0f * m.alpha);
+    a.tc_slack = a.tc_delta - need;
+  }
   cudaError_t e;
+  // variant: 0 auto, -1 FFMA2 scan, 1/2/4/8 FFMA2 scan with that many landmarks per thread, 16 tensor-core scan.
+  // GMMLOC_ASSOC_KERNEL=tc|ffma2 overrides the automatic choice (A/B runs of the bench).
+  static const int forced = [] {
+    const char* v = std::getenv("GMMLOC_ASSOC_KERNEL");
+    if (v == nullptr) return 0;
+    if (std::strcmp(v, "tc") == 0) return 16;
+    if (std::strcmp(v, "ffma2") == 0) return -1;
+    return 0;
+  }();
+  if (variant == 0) variant = forced;
+  const bool tc_possible = m.tc_ok && m.Kpad / kChunk < 65000;
+  // automatic: the tensor-core scan needs enough landmarks to fill 148 SMs x 2 CTAs x 512 landmarks
+  const bool use_tc = tc_possible && (variant == 16 || (variant == 0 && kTcAutoDefault && M >= 148LL * 4 * kTcLm));
+  if (used_tc) *used_tc = use_tc ? 1 : 0;
+  if (use_tc) {
+    if ((e = launch_scan_tc(a, stream)) != cudaSuccess) return e;
+  }
   // Fill the machine: 148 SMs x 2 CTAs; shrink the per-thread landmark count for small batches.
-  int P = variant;
+  int P = (variant == 16 || variant < 0) ? 0 : variant;
   if (P <= 0) {
     if (M >= 148LL * GMMLOC_SCAN_MINB * GMMLOC_SCAN_THREADS * GMMLOC_SCAN_P) P = 8;
     else if (M >= 148LL * 2 * 256 * 4) P = 4;
     else if (M >= 148LL * 2 * 128 * 2) P = 2;
     else P = 1;
   }
-  switch (P) {
-    case 8: e = launch_scan_t<GMMLOC_SCAN_P, GMMLOC_SCAN_THREADS, GMMLOC_SCAN_MINB>(a, stream); break;
-    case 4: e = launch_scan_t<4, 256, 2>(a, stream); break;
-    case 2: e = launch_scan_t<2, 128, 4>(a, stream); break;
-    default: e = launch_scan_t<1, 128, 4>(a, stream); break;
+  if (use_tc) {
+    e = cudaSuccess;
+  } else {
+    switch (P) {
+      case 8: e = launch_scan_t<GMMLOC_SCAN_P, GMMLOC_SCAN_THREADS, GMMLOC_SCAN_MINB>(a, stream); break;
+      case 4: e = launch_scan_t<4, 256, 2>(a, stream); break;
+      case 2: e = launch_scan_t<2, 128, 4>(a, stream); break;
+      default: e = launch_scan_t<1, 128, 4>(a, stream); break;
+    }
   }
   if (e != cudaSuccess) return e;
   if (ev_between != nullptr && (e = cudaEventRecord(ev_between, stream)) != cudaSuccess) return e;

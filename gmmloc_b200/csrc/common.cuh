@@ -24,6 +24,10 @@ __host__ __device__ __forceinline__ size_t scan_index(int k, int c) {
 #define GMMLOC_CHUNK 16
 #endif
 constexpr int kChunk = GMMLOC_CHUNK;
+constexpr int kTcK = 16;                         // fp16 K extent of one tcgen05.mma kind::f16
+constexpr int kTcTileComps = 4 * kChunk;         // components per UMMA B tile (four chunks)
+constexpr int kTcRows = 3 * kTcTileComps;        // UMMA N of one tile: [0,64) y0 | [64,128) y1 | [128,192) y2
+constexpr int kTcTileBytes = kTcRows * kTcK * 2; // 6144 B for kChunk = 16
 
 struct MapDev {
   int K = 0;      // real components
@@ -42,6 +46,13 @@ struct MapDev {
   int32_t* nbr_col = nullptr;
   long long nbr_count = 0;
   double nbr_thresh = 0.0;
+  // tensor-core pruning table (assoc_scan_tc_kernel): per kTcTileComps components one UMMA B tile of kTcRows rows
+  // x kTcK fp16 (K-major, no swizzle: byte (k / 8) * (kTcRows * 16) + row * 16 + (k % 8) * 2),
+  // row r * kTcTileComps + j = whitening row r of component j of the tile, 3-way hi/lo split folded into K
+  uint16_t* tc_table = nullptr;  // ceil(Kpad / kTcTileComps) x kTcTileBytes
+  float tc_centre[3] = {0.f, 0.f, 0.f};  // landmarks are centred with these fp32 values before the fp16 split
+  float tc_err = 0.f;           // bound of |sqrt(score_tc) - sqrt(score32)| for |x|_inf <= xmax
+  int tc_ok = 0;                // 0: some coefficient does not fit fp16 / chunk size unsupported -> FFMA2 scan only
   float alpha = 0.f;            // error bound of sqrt(score32) vs sqrt(exact d2), whitened units
   float xmax = 0.f;             // |x|_inf bound under which alpha holds
 };
@@ -56,12 +67,12 @@ struct FrameParamsDev {
 
 // Host-side launchers (one per kernel family); every launcher only enqueues on `stream`.
 cudaError_t launch_map_build(const MapDev& m, double deg_eps, double xmax, int* d_err, unsigned int* d_alpha_bits,
-                             cudaStream_t stream);
+                             cudaStream_t stream);  // d_err: [0] error flag, [1] alpha bits, [2] tc_err bits, [3] tc overflow flag
 cudaError_t launch_bh_neighbors(const MapDev& m, double thresh, int* d_counts, const long long* d_row_ptr, int32_t* d_col,
                                 double* d_dist, cudaStream_t stream);
 cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, double gate, int32_t* d_assign,
                              float* d_d2, int* d_flag_count, int32_t* d_flag_idx, float* d_flag_thr, int variant,
-                             cudaStream_t stream, int* launches, cudaEvent_t ev_between = nullptr);
+                             cudaStream_t stream, int* launches, cudaEvent_t ev_between = nullptr, int* used_tc = nullptr);
 struct FrameArgs {
   const double* mean;       // map constants (fp64)
   const double* cov_inv;

@@ -7,6 +7,7 @@
 //
 // Every product / sum is an explicit round-to-nearest intrinsic so that results are reproducible to
 // the bit on any IEEE machine that evaluates the same expression trees without contraction.
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -133,14 +134,50 @@ __device__ void jacobi3(const double* cov, double* evals, double* evecs) {
   }
 }
 
+// one whitening row (3 coefficients + constant) of component j of its tile into the UMMA B tile:
+// K slots  0..2 w_hi | 3 c_hi | 4..6 w_hi (pairs with the landmark's lo part) | 7 c_lo | 8..10 w_lo | 11..15 zero
+// against the landmark row  0..2 v_hi | 3 one | 4..6 v_lo | 7 one | 8..10 v_hi | 11..15 zero.
+__device__ void tc_write_row(uint16_t* tile, int row, const double* w, double c, bool& fits) {
+  __half h[kTcK];
+  for (int i = 0; i < kTcK; ++i) h[i] = __float2half_rn(0.f);
+  for (int i = 0; i < 3; ++i) {
+    const __half hi = __double2half(w[i]);
+    const __half lo = __double2half(w[i] - (double)__half2float(hi));
+    h[i] = hi;
+    h[4 + i] = hi;
+    h[8 + i] = lo;
+    if (!(fabs(w[i]) < 60000.0)) fits = false;
+  }
+  const __half chi = __double2half(c);
+  h[3] = chi;
+  h[7] = __double2half(c - (double)__half2float(chi));
+  if (!(fabs(c) < 60000.0)) fits = false;
+  for (int i = 0; i < kTcK; ++i) {
+    const size_t off = (size_t)(i / 8) * (kTcRows * 8) + (size_t)row * 8 + (i % 8);
+    tile[off] = __half_as_ushort(h[i]);
+  }
+}
+
 __global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps, double xmax, int* err_flag,
                                                         unsigned int* alpha_bits) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= m.Kpad) return;
+  const int ktc = (m.Kpad + kTcTileComps - 1) / kTcTileComps * kTcTileComps;  // the tensor-core table is padded to whole tiles
+  if (k >= ktc) return;
   float* sp = m.scan;
+  uint16_t* tc_tile = m.tc_table ? m.tc_table + (size_t)(k / kTcTileComps) * (kTcTileBytes / 2) : nullptr;
+  const int tj = k % kTcTileComps;
   if (k >= m.K) {  // padding rows score +inf and can never win
-    for (int i = 0; i < kScanFloats; ++i) sp[scan_index(k, i)] = 0.f;
-    sp[scan_index(k, 6)] = -CUDART_INF_F;
+    if (k < m.Kpad) {
+      for (int i = 0; i < kScanFloats; ++i) sp[scan_index(k, i)] = 0.f;
+      sp[scan_index(k, 6)] = -CUDART_INF_F;
+    }
+    if (tc_tile) {  // tensor-core table: a constant whitened coordinate of 6e4 (score 3.6e9), finite in fp16
+      bool fits = true;
+      const double z[3] = {0.0, 0.0, 0.0};
+      tc_write_row(tc_tile, 0 * kTcTileComps + tj, z, 59999.0, fits);
+      tc_write_row(tc_tile, 1 * kTcTileComps + tj, z, 0.0, fits);
+      tc_write_row(tc_tile, 2 * kTcTileComps + tj, z, 0.0, fits);
+    }
     return;
   }
   double cov[9], ci[9], L[9], ev[3], ax[9];
@@ -166,6 +203,7 @@ __global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps
     atomicOr(err_flag, 1);
     for (int i = 0; i < kScanFloats; ++i) sp[scan_index(k, i)] = 0.f;
     sp[scan_index(k, 6)] = -CUDART_INF_F;
+    if (tc_tile) atomicOr(err_flag + 3, 1);
     return;
   }
   // fp32 whitening rows U = L^T, c = U mu
@@ -190,6 +228,35 @@ __global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps
   float af = (float)alpha;
   if ((double)af < alpha) af = nextafterf(af, CUDART_INF_F);
   atomicMax(alpha_bits, __float_as_uint(af));  // non-negative floats order like their bit patterns
+  // ---- tensor-core pruning table (assoc_scan_tc_kernel): y = U (x - centre) - U (mu - centre) ----
+  if (tc_tile) {
+    const double cen[3] = {(double)m.tc_centre[0], (double)m.tc_centre[1], (double)m.tc_centre[2]};
+    const double mc[3] = {mu[0] - cen[0], mu[1] - cen[1], mu[2] - cen[2]};
+    const double w0[3] = {U[0], U[1], U[2]}, w1[3] = {0.0, U[3], U[4]}, w2[3] = {0.0, 0.0, U[5]};
+    const double k0 = -(U[0] * mc[0] + U[1] * mc[1] + U[2] * mc[2]), k1 = -(U[3] * mc[1] + U[4] * mc[2]), k2 = -(U[5] * mc[2]);
+    bool fits = true;
+    tc_write_row(tc_tile, 0 * kTcTileComps + tj, w0, k0, fits);
+    tc_write_row(tc_tile, 1 * kTcTileComps + tj, w1, k1, fits);
+    tc_write_row(tc_tile, 2 * kTcTileComps + tj, w2, k2, fits);
+    if (!fits) atomicOr(err_flag + 3, 1);
+    // |y_tc - y_exact| <= eps_tc * (sum_i |w_i| vmax_i + |c|) + abs_tc per row, with
+    //   eps_tc: hi/lo split residuals of w and v (2^-22 each, fp16 rounding of the lo parts), the dropped lo*lo term
+    //           (2^-22), <= 11 fp32 accumulations in the tensor core (taken as 2^-22 each: covers truncating adders),
+    //           the fp32 centring of the landmark (2^-24): 3 + 11 + 1/4 = 14.25 units of 2^-22, taken as 24 (6e-6);
+    //   abs_tc: fp16 subnormal spacing of the lo parts (2^-24) times the partner magnitude, folded in below.
+    const double vm[3] = {xmax + fabs(cen[0]), xmax + fabs(cen[1]), xmax + fabs(cen[2])};
+    const double eps_tc = 24.0 * 2.384185791015625e-07, sub = 5.9604644775390625e-08;
+    const double r0 = (fabs(U[0]) * vm[0] + fabs(U[1]) * vm[1] + fabs(U[2]) * vm[2]) + fabs(k0);
+    const double r1 = (fabs(U[3]) * vm[1] + fabs(U[4]) * vm[2]) + fabs(k1);
+    const double r2 = fabs(U[5]) * vm[2] + fabs(k2);
+    const double e0 = eps_tc * r0 + sub * (fabs(U[0]) + fabs(U[1]) + fabs(U[2]) + vm[0] + vm[1] + vm[2] + 1.0);
+    const double e1 = eps_tc * r1 + sub * (fabs(U[3]) + fabs(U[4]) + vm[1] + vm[2] + 1.0);
+    const double e2 = eps_tc * r2 + sub * (fabs(U[5]) + vm[2] + 1.0);
+    const double et = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+    float ef = (float)et;
+    if ((double)ef < et) ef = nextafterf(ef, CUDART_INF_F);
+    atomicMax(alpha_bits + 1, __float_as_uint(ef));
+  }
 }
 
 // ---- K5: Bhattacharyya neighbour lists (GMM::GMM, gaussian_mixture.cpp:61-78; BHCoefficient,
@@ -261,7 +328,8 @@ cudaError_t launch_bh_neighbors(const MapDev& m, double thresh, int* d_counts, c
 cudaError_t launch_map_build(const MapDev& m, double deg_eps, double xmax, int* d_err, unsigned int* d_alpha_bits,
                              cudaStream_t stream) {
   const int threads = 128;
-  const int blocks = (m.Kpad + threads - 1) / threads;
+  const int ktc = (m.Kpad + kTcTileComps - 1) / kTcTileComps * kTcTileComps;
+  const int blocks = (ktc + threads - 1) / threads;
   map_build_kernel<<<blocks, threads, 0, stream>>>(m, deg_eps, xmax, d_err, d_alpha_bits);
   return cudaGetLastError();
 }

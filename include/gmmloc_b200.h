@@ -143,6 +143,14 @@ GMMLOC_API gmmloc_status_t gmmloc_ctx_stats(gmmloc_ctx_t* ctx, gmmloc_stats_t* o
  * localization.cpp:101). */
 GMMLOC_API gmmloc_status_t gmmloc_ctx_kernel_times(gmmloc_ctx_t* ctx, float ms[3]);
 
+/* Association scan kernel of this context: GMMLOC_ASSOC_AUTO picks the tensor-core pruning scan (tcgen05; results
+ * identical, candidates re-scored exactly) for large batches on maps whose whitening coefficients fit fp16, else
+ * the FFMA2 scan; the other two values force one kernel (FFMA2 is used when the tensor-core table is unavailable). */
+enum { GMMLOC_ASSOC_AUTO = 0, GMMLOC_ASSOC_FFMA2 = 1, GMMLOC_ASSOC_TENSOR = 2 };
+GMMLOC_API gmmloc_status_t gmmloc_ctx_set_assoc_kernel(gmmloc_ctx_t* ctx, int kind);
+/* 1 when the last association on ctx ran the tensor-core pruning scan, else 0 */
+GMMLOC_API int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx);
+
 /* page-locked host memory for the host entry points (pageable buffers also work, via staging) */
 GMMLOC_API gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out);
 GMMLOC_API void gmmloc_host_free(void* p);

@@ -449,3 +449,63 @@ def test_two_contexts_share_one_map(gpu, oracle):
     [t.start() for t in th]
     [t.join() for t in th]
     assert np.array_equal(res[0], ref_a) and np.array_equal(res[1], ref_a)
+
+
+# ---------------------------------------------------------------- tensor-core pruning scan (tcgen05, opt-in)
+def _assoc_with(ctx, g, kind, m, pts, gate=0.0):
+    ctx.set_assoc_kernel(kind)
+    try:
+        a, d = ctx.associate(m, pts, gate=gate)
+        return a, d, ctx.last_assoc_kernel(), ctx.stats()["flagged"]
+    finally:
+        ctx.set_assoc_kernel(g.capi.ASSOC_AUTO)
+
+
+@pytest.mark.parametrize("case", ["c2", "v1", "c5", "ragged"])
+def test_tensor_core_scan_gives_identical_assignments(gpu, oracle, golden_maps, case):
+    """The tcgen05 pruning scan only selects candidate chunks; winners are re-scored with the exact fp32 score and go
+    through the same certificate / exact re-rank, so every output must equal the FFMA2 scan's (and the oracle's)."""
+    g, ctx = gpu
+    if case == "v1":
+        mean, cov = golden_maps["v1"]["mean"], golden_maps["v1"]["cov"]
+        M = 150000
+    elif case == "c5":
+        mean, cov = synth.make_map(50000, 0.95, seed=5)
+        M = 200000
+    elif case == "ragged":
+        mean, cov = synth.make_map(1153, 0.5, seed=6)  # K not a multiple of the 64-component tile
+        M = 70001
+    else:
+        mean, cov = synth.make_map(10000, 0.5)
+        M = 300000
+    m = g.GMM(mean, cov)
+    pts, _ = synth.make_points_near(mean, cov, M, seed=11, spread=2.0)
+    pts[::1000] += 50.0          # far outside the certified box
+    pts[5::5000] = np.nan        # non-finite landmarks
+    a0, d0, k0, _ = _assoc_with(ctx, g, g.capi.ASSOC_FFMA2, m, pts)
+    a1, d1, k1, flagged = _assoc_with(ctx, g, g.capi.ASSOC_TENSOR, m, pts)
+    assert k0 == "ffma2" and k1 == "tensor"
+    assert np.array_equal(a0, a1)
+    assert np.array_equal(d0, d1, equal_nan=True)
+    assert flagged < 0.2 * M
+    # spot-check against the oracle as well
+    sel = np.arange(0, M, 97)
+    comps = oracle.map_build(mean, cov)
+    ao, _ = oracle.associate(comps, pts[sel], nthreads=8)
+    assert np.array_equal(a1.reshape(-1)[sel], ao)
+    # the gate is applied identically
+    g0 = _assoc_with(ctx, g, g.capi.ASSOC_FFMA2, m, pts[:20000], gate=9.0)[0]
+    g1 = _assoc_with(ctx, g, g.capi.ASSOC_TENSOR, m, pts[:20000], gate=9.0)[0]
+    assert np.array_equal(g0, g1) and (g1 == -1).any()
+
+
+def test_tensor_core_scan_falls_back_when_coefficients_do_not_fit_fp16(gpu):
+    g, ctx = gpu
+    mean, cov = synth.make_map(256, 0.5, seed=8)
+    cov = cov.copy()
+    cov[0] = (np.eye(3) * 1e-11).ravel()  # sigma = 3 um: whitening coefficients ~3e5 overflow fp16
+    m = g.GMM(mean, cov)
+    pts, _ = synth.make_points_near(mean, cov, 5000, seed=8)
+    a1, _, kind, _ = _assoc_with(ctx, g, g.capi.ASSOC_TENSOR, m, pts)
+    a0, _, _, _ = _assoc_with(ctx, g, g.capi.ASSOC_FFMA2, m, pts)
+    assert kind == "ffma2" and np.array_equal(a0, a1)
