@@ -148,14 +148,14 @@ class Context:
     def stats(self) -> dict:
         s = capi.Stats()
         capi.check(capi.lib().gmmloc_ctx_stats(self._h, C.byref(s)))
-        return dict(points=s.points, flagged=s.flagged, kernel_launches=s.kernel_launches)
+        return dict(points=s.points, flagged=s.flagged, kernel_launches=s.kernel_launches, flagged_brute=s.flagged_brute)
 
     def set_assoc_kernel(self, kind: int) -> None:
-        """capi.ASSOC_AUTO / ASSOC_FFMA2 / ASSOC_TENSOR (tcgen05 pruning scan; identical results)."""
+        """capi.ASSOC_AUTO / ASSOC_FFMA2 / ASSOC_TENSOR (tcgen05 pruning scan) / ASSOC_GRID (grid-indexed scan); identical results."""
         capi.check(capi.lib().gmmloc_ctx_set_assoc_kernel(self._h, int(kind)))
 
     def last_assoc_kernel(self) -> str:
-        return "tensor" if capi.lib().gmmloc_ctx_last_assoc_kernel(self._h) else "ffma2"
+        return ("ffma2", "tensor", "grid")[capi.lib().gmmloc_ctx_last_assoc_kernel(self._h)]
 
     def kernel_times(self) -> dict:
         """Device ms of the last call's kernels (association scan, exact re-rank, frame GN)."""

@@ -28,6 +28,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 SOURCES = {
     "api.cu": [],
     "map_build.cu": [],
+    "grid_build.cu": [],
     "assoc_scan.cu": [],
     "frame_gn.cu": [],
     "pose_lm.cu": [],

@@ -15,7 +15,7 @@ OK, EINVAL, ENOMEM, ECUDA, ENUMERIC, EIO = range(6)
 MODE_JOINT, MODE_POSE_ONLY, MODE_POINTS_ONLY = 0, 1, 2
 FRAME_NUMERIC = 1
 VIEW_OVERFLOW = 1
-ASSOC_AUTO, ASSOC_FFMA2, ASSOC_TENSOR = 0, 1, 2
+ASSOC_AUTO, ASSOC_FFMA2, ASSOC_TENSOR, ASSOC_GRID = 0, 1, 2, 3
 
 
 class Camera(C.Structure):
@@ -33,7 +33,7 @@ class Params(C.Structure):
 
 
 class Stats(C.Structure):
-    _fields_ = [("points", C.c_int64), ("flagged", C.c_int64), ("kernel_launches", C.c_int64)]
+    _fields_ = [("points", C.c_int64), ("flagged", C.c_int64), ("kernel_launches", C.c_int64), ("flagged_brute", C.c_int64)]
 
 
 class GmmlocError(RuntimeError):

@@ -281,7 +281,8 @@ void gmmloc_map_destroy(gmmloc_map_t* m) {
   cudaSetDevice(m->device);
   cudaFree(m->d.mean); cudaFree(m->d.cov); cudaFree(m->d.cov_inv); cudaFree(m->d.det); cudaFree(m->d.scale);
   cudaFree(m->d.axis); cudaFree(m->d.sqrt_info); cudaFree(m->d.is_deg); cudaFree(m->d.is_sal); cudaFree(m->d.scan);
-  cudaFree(m->d.nbr_row_ptr); cudaFree(m->d.nbr_col); cudaFree(m->d.tc_table);
+  cudaFree(m->d.nbr_row_ptr); cudaFree(m->d.nbr_col); cudaFree(m->d.tc_table); cudaFree(m->d.rec);
+  free_assoc_grid(m->d);
   cudaSetDevice(prev);
   delete m;
 }
@@ -327,6 +328,7 @@ gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, 
   alloc((void**)&d.is_deg, K);
   alloc((void**)&d.is_sal, K);
   alloc((void**)&d.scan, sizeof(float) * kScanFloats * d.Kpad);
+  alloc((void**)&d.rec, sizeof(float) * 12 * (size_t)K);
   if (kChunk == 16) alloc((void**)&d.tc_table, (size_t)((d.Kpad + kTcTileComps - 1) / kTcTileComps) * kTcTileBytes);
   int* d_err = nullptr;
   alloc((void**)&d_err, 4 * sizeof(int));
@@ -358,6 +360,11 @@ gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, 
   d.xmax = (float)xmax;
   std::memcpy(&d.tc_err, &h[2], 4);
   d.tc_ok = (d.tc_table != nullptr && h[3] == 0) ? 1 : 0;
+  // exact spatial index for the association (grid_build.cu); a map it cannot index keeps the brute-force scan
+  if ((e = build_assoc_grid(d, lo, hi)) != cudaSuccess) {
+    gmmloc_map_destroy(m);
+    return fail_cuda(e, "build_assoc_grid");
+  }
   *out = m;
   return GMMLOC_OK;
 }
@@ -527,9 +534,9 @@ gmmloc_status_t gmmloc_ctx_create(int device, gmmloc_ctx_t** out) {
   cudaError_t e = cudaSuccess;
   for (Lane& l : c->lanes) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&l.h_flag_count, sizeof(int));
-    if (e == cudaSuccess) e = l.flag_count.reserve(sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(l.flag_count.p, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&l.h_flag_count, 2 * sizeof(int));
+    if (e == cudaSuccess) e = l.flag_count.reserve(2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(l.flag_count.p, 0, 2 * sizeof(int));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&l.ev[i]);
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking);
@@ -581,9 +588,10 @@ gmmloc_status_t gmmloc_ctx_stats(gmmloc_ctx_t* ctx, gmmloc_stats_t* out) {
   if (!ctx || !out) return fail(GMMLOC_EINVAL, "null pointer");
   // the flagged count of the last association is read back lazily (stream must be idle for it to be final)
   CU(cudaSetDevice(ctx->device));
-  CU(cudaMemcpyAsync(ctx->L().h_flag_count, ctx->L().flag_count.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->L().stream));
+  CU(cudaMemcpyAsync(ctx->L().h_flag_count, ctx->L().flag_count.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->L().stream));
   CU(cudaStreamSynchronize(ctx->L().stream));
-  ctx->stats.flagged = *ctx->L().h_flag_count;
+  ctx->stats.flagged = (int64_t)ctx->L().h_flag_count[0] + ctx->L().h_flag_count[1];  // grid re-rank list + brute-force list
+  ctx->stats.flagged_brute = ctx->L().h_flag_count[1];
   *out = ctx->stats;
   return GMMLOC_OK;
 }
@@ -602,7 +610,7 @@ gmmloc_status_t gmmloc_ctx_kernel_times(gmmloc_ctx_t* ctx, float ms[3]) {
 }
 
 gmmloc_status_t gmmloc_ctx_set_assoc_kernel(gmmloc_ctx_t* ctx, int kind) {
-  if (!ctx || kind < GMMLOC_ASSOC_AUTO || kind > GMMLOC_ASSOC_TENSOR) return fail(GMMLOC_EINVAL, "gmmloc_ctx_set_assoc_kernel: bad argument");
+  if (!ctx || kind < GMMLOC_ASSOC_AUTO || kind > GMMLOC_ASSOC_GRID) return fail(GMMLOC_EINVAL, "gmmloc_ctx_set_assoc_kernel: bad argument");
   ctx->assoc_kind = kind;
   return GMMLOC_OK;
 }
@@ -627,13 +635,16 @@ gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* ma
   ctx->stats.points = M;
   if (M == 0) return GMMLOC_OK;
   CU(cudaSetDevice(ctx->device));
-  CU(ctx->L().flag_idx.reserve(sizeof(int32_t) * (size_t)M));
-  CU(ctx->L().flag_thr.reserve(sizeof(float) * (size_t)M));
-  CU(cudaMemsetAsync(ctx->L().flag_count.p, 0, sizeof(int), ctx->L().stream));
+  CU(ctx->L().flag_idx.reserve(sizeof(int32_t) * 2 * (size_t)M));  // list A | list B (launch_associate)
+  CU(ctx->L().flag_thr.reserve(sizeof(float) * 2 * (size_t)M));
+  CU(cudaMemsetAsync(ctx->L().flag_count.p, 0, 2 * sizeof(int), ctx->L().stream));
   int launches = 0;
   CU(cudaEventRecord(ctx->L().ev[0], ctx->L().stream));
   // kernel choice: variant 16 = tensor-core pruning scan, -1 = FFMA2 scan, 0 = launcher default
-  const int variant = ctx->assoc_kind == GMMLOC_ASSOC_TENSOR ? 16 : (ctx->assoc_kind == GMMLOC_ASSOC_FFMA2 ? -1 : 0);
+  const int variant = ctx->assoc_kind == GMMLOC_ASSOC_TENSOR ? 16
+                      : ctx->assoc_kind == GMMLOC_ASSOC_FFMA2 ? -1
+                      : ctx->assoc_kind == GMMLOC_ASSOC_GRID  ? 32
+                                                              : 0;
   int used_tc = 0;
   CU(launch_associate(map->d, d_pts_w, M, gate, d_assign, d_d2, ctx->L().flag_count.as<int>(), ctx->L().flag_idx.as<int32_t>(),
                       ctx->L().flag_thr.as<float>(), variant, ctx->L().stream, &launches, ctx->L().ev[1], &used_tc));
@@ -759,8 +770,8 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   for (int l = 0; l < (nchunks > 1 ? 2 : 1); ++l) {
     Lane& ln = ctx->lanes[l];
     const size_t mc = (size_t)chunk * N;
-    CU(ln.flag_idx.reserve(sizeof(int32_t) * mc));
-    CU(ln.flag_thr.reserve(sizeof(float) * mc));
+    CU(ln.flag_idx.reserve(sizeof(int32_t) * 2 * mc));
+    CU(ln.flag_thr.reserve(sizeof(float) * 2 * mc));
     if ((size_t)N > frame_gn_smem_limit_points()) {
       CU(ln.xws.reserve(24 * mc));
       CU(ln.fws.reserve(mc));

@@ -122,6 +122,12 @@ struct ScanArgs {
   int* flag_count;
   int32_t* flag_idx;
   float* flag_thr;
+  // association grid kernels only: list A = landmarks whose exact re-rank can stay inside a grid cell list
+  GridDev grid;
+  const float4* rec;
+  int* ga_count;
+  int32_t* ga_idx;
+  float* ga_thr;   // sign bit = grid level of the re-rank
   // tensor-core pruning scan only
   const uint16_t* tc_table;
   float cen[3];
@@ -412,6 +418,161 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
   }
 }
 
+
+// ======================================================================================================
+// K1-G / K2-G: association through the exact grid index (GridDev, grid_build.cu).
+//
+// One thread per landmark.  The landmark's cell list holds every component whose d2 can be <= tmax in that cell, so
+// after scoring the list (plus the short `big` list) with the SAME score32() as the brute-force scan:
+//   * winner's true distance provably <= sqrt(tmax)  =>  every unlisted component is farther than the winner: the
+//     usual certificate (fp32 gap vs the error bound alpha) on best / second-best of the list decides, exactly as
+//     in K1; near-ties go to list A and are re-ranked in fp64 over the same cell list (K2-G), lowest index first;
+//   * otherwise the next (coarser, larger tmax) level is tried; what no level can decide — landmarks outside the
+//     grid, non-finite ones, winners farther than the last tmax — goes to list B, the brute-force exact re-rank (K2).
+// Results are therefore identical to the brute-force scan's; the work per landmark drops from K to ~30 scores.
+__device__ __forceinline__ float score_rec(const float4* __restrict__ rec, int k, float x0, float x1, float x2) {
+  const float4 r0 = __ldg(rec + 3 * (size_t)k), r1 = __ldg(rec + 3 * (size_t)k + 1);
+  const float r2 = __ldg(reinterpret_cast<const float*>(rec + 3 * (size_t)k + 2));
+  return score32(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2, x0, x1, x2);
+}
+__device__ __forceinline__ long long grid_cell(const GridLevel& G, float x0, float x1, float x2) {
+  const float fx = __fmul_rn(__fsub_rn(x0, G.lo[0]), G.inv_h), fy = __fmul_rn(__fsub_rn(x1, G.lo[1]), G.inv_h),
+              fz = __fmul_rn(__fsub_rn(x2, G.lo[2]), G.inv_h);
+  if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f && fx < (float)G.nx && fy < (float)G.ny && fz < (float)G.nz)) return -1;  // NaN too
+  return ((long long)(int)fz * G.ny + (int)fy) * G.nx + (int)fx;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
+  const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
+  if (i >= a.M) return;
+  const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
+  const bool finite_in = (fabsf(px) <= a.xmax) && (fabsf(py) <= a.xmax) && (fabsf(pz) <= a.xmax);  // false for NaN
+  float g1 = CUDART_INF_F, g2 = CUDART_INF_F;  // best / second best over the big list
+  int gi = -1;
+  for (int e = 0; e < a.grid.nbig; ++e) {
+    const int k = __ldg(a.grid.big + e);
+    const float s = score_rec(a.rec, k, px, py, pz);
+    if (s < g1) {
+      g2 = g1;
+      g1 = s;
+      gi = k;
+    } else {
+      g2 = fminf(g2, s);
+    }
+  }
+  float b1 = g1, b2 = g2;
+  int idx = gi, lev_ok = -1;
+  double hi1 = CUDART_INF;
+  if (finite_in) {
+    for (int lev = 0; lev < a.grid.nlev; ++lev) {
+      const GridLevel& G = a.grid.lev[lev];
+      const long long cell = grid_cell(G, px, py, pz);
+      if (cell < 0) continue;
+      b1 = g1;
+      b2 = g2;
+      idx = gi;
+      const int e0 = __ldg(G.start + cell), e1 = __ldg(G.start + cell + 1);
+      for (int e = e0; e < e1; ++e) {
+        const int k = __ldg(G.list + e);
+        const float s = score_rec(a.rec, k, px, py, pz);
+        if (s < b1) {
+          b2 = b1;
+          b1 = s;
+          idx = k;
+        } else {
+          b2 = fminf(b2, s);
+        }
+      }
+      if (idx >= 0) {
+        hi1 = sqrt((double)b1) * (1.0 + kRelEps) + (double)a.alpha;  // upper bound of the winner's true distance
+        if (hi1 * hi1 <= (double)G.tmax) {  // every unlisted component is farther than that
+          lev_ok = lev;
+          break;
+        }
+      }
+    }
+  }
+  if (lev_ok >= 0) {
+    const double lo2 = sqrt((double)b2) * (1.0 - kRelEps) - (double)a.alpha;  // lower bound of every other listed component's
+    if (lo2 > hi1) {
+      if (a.d2 != nullptr || a.gate > 0.0) {
+        const double d = chi2_exact(a.mean + (size_t)idx * 3, a.cov_inv + (size_t)idx * 9, (double)px, (double)py, (double)pz);
+        if (a.gate > 0.0 && d > a.gate) idx = -1;
+        if (a.d2 != nullptr) a.d2[i] = (float)d;
+      }
+      a.assign[i] = idx;
+      return;
+    }
+  }
+  // not certified: exact re-rank with the squared radius inside which it must evaluate in fp64
+  float thr = CUDART_INF_F;
+  int lev_rr = -1;
+  if (finite_in && idx >= 0) {
+    const double rt = (sqrt((double)b1) * (1.0 + kRelEps) + 2.0 * (double)a.alpha) / (1.0 - kRelEps);
+    const double t2 = rt * rt;
+    thr = (float)t2;
+    if ((double)thr < t2) thr = nextafterf(thr, CUDART_INF_F);
+    // every component with score32 <= thr has a true distance <= hit: the grid re-rank needs them all listed
+    const double hit = sqrt((double)thr) * (1.0 + kRelEps) + (double)a.alpha;
+    for (int lev = max(lev_ok, 0); lev < a.grid.nlev && lev_rr < 0; ++lev)
+      if (hit * hit <= (double)a.grid.lev[lev].tmax && grid_cell(a.grid.lev[lev], px, py, pz) >= 0) lev_rr = lev;
+  }
+  if (lev_rr >= 0) {
+    const int pos = atomicAdd(a.ga_count, 1);
+    a.ga_idx[pos] = (int32_t)i;
+    a.ga_thr[pos] = lev_rr ? -thr : thr;
+  } else {
+    const int pos = atomicAdd(a.flag_count, 1);
+    a.flag_idx[pos] = (int32_t)i;
+    a.flag_thr[pos] = thr;
+  }
+}
+
+// K2-G: exact re-rank of list A over the landmark's cell list (ascending ids; the big list interleaves, hence the
+// lexicographic (d2, id) minimum = the reference's strict '<' on an ascending scan, gmmloc_opt.cpp:209-217).
+__global__ void __launch_bounds__(128) assoc_grid_rerank_kernel(const ScanArgs a) {
+  const int n = *a.ga_count;
+  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+    const long long i = a.ga_idx[w];
+    const float t = a.ga_thr[w];
+    const int lev = signbit(t) ? 1 : 0;
+    const float thr = fabsf(t);
+    const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
+    const GridLevel& G = a.grid.lev[lev];
+    const long long cell = grid_cell(G, px, py, pz);
+    double best = CUDART_INF;
+    int bi = -1;
+    const int e0 = __ldg(G.start + cell), e1 = __ldg(G.start + cell + 1);
+    const int nl = e1 - e0;
+    for (int e = 0; e < nl + a.grid.nbig; ++e) {
+      const int k = e < nl ? __ldg(G.list + e0 + e) : __ldg(a.grid.big + (e - nl));
+      const float s = score_rec(a.rec, k, px, py, pz);
+      if (!(s > thr)) {
+        const double d = chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, (double)px, (double)py, (double)pz);
+        if (d < best || (d == best && k < bi)) {
+          best = d;
+          bi = k;
+        }
+      }
+    }
+    int idx = bi;
+    if (a.gate > 0.0 && idx >= 0 && best > a.gate) idx = -1;
+    a.assign[i] = idx;
+    if (a.d2 != nullptr) a.d2[i] = (bi >= 0) ? (float)best : CUDART_INF_F;
+  }
+}
+
+cudaError_t launch_scan_grid(const ScanArgs& a, cudaStream_t stream) {
+  const long long grid = (a.M + 255) / 256;
+  assoc_grid_kernel<256><<<(unsigned)grid, 256, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+cudaError_t launch_rerank_grid(const ScanArgs& a, cudaStream_t stream) {
+  const long long want = (a.M + 127) / 128;
+  assoc_grid_rerank_kernel<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
 
 // ======================================================================================================
 // K1-TC: tensor-core pruning scan (tcgen05 / TMEM).
@@ -856,9 +1017,16 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
   a.gate = gate;
   a.assign = d_assign;
   a.d2 = d_d2;
-  a.flag_count = d_flag_count;
-  a.flag_idx = d_flag_idx;
-  a.flag_thr = d_flag_thr;
+  // work lists: d_flag_count = {list A count, list B count}; entries [0, M) = list A (grid re-rank), [M, 2 M) = list B
+  // (brute-force exact re-rank)
+  a.flag_count = d_flag_count + 1;
+  a.flag_idx = d_flag_idx + M;
+  a.flag_thr = d_flag_thr + M;
+  a.ga_count = d_flag_count;
+  a.ga_idx = d_flag_idx;
+  a.ga_thr = d_flag_thr;
+  a.grid = m.grid;
+  a.rec = reinterpret_cast<const float4*>(m.rec);
   a.tc_table = m.tc_table;
   a.cen[0] = m.tc_centre[0]; a.cen[1] = m.tc_centre[1]; a.cen[2] = m.tc_centre[2];
   {
@@ -869,32 +1037,41 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
     a.tc_slack = a.tc_delta - need;
   }
   cudaError_t e;
-  // variant: 0 auto, -1 FFMA2 scan, 1/2/4/8 FFMA2 scan with that many landmarks per thread, 16 tensor-core scan.
-  // GMMLOC_ASSOC_KERNEL=tc|ffma2 overrides the automatic choice (A/B runs of the bench).
+  // variant: 0 auto, -1 FFMA2 scan, 1/2/4/8 FFMA2 scan with that many landmarks per thread, 16 tensor-core scan,
+  // 32 grid-indexed scan.  GMMLOC_ASSOC_KERNEL=grid|tc|ffma2 overrides the automatic choice (A/B runs of the bench).
   static const int forced = [] {
     const char* v = std::getenv("GMMLOC_ASSOC_KERNEL");
     if (v == nullptr) return 0;
     if (std::strcmp(v, "tc") == 0) return 16;
     if (std::strcmp(v, "ffma2") == 0) return -1;
+    if (std::strcmp(v, "grid") == 0) return 32;
     return 0;
   }();
   if (variant == 0) variant = forced;
+  // automatic: the grid-indexed scan whenever the map has a grid (identical results, ~K/30 of the work)
+  const bool use_grid = m.grid.nlev > 0 && (variant == 32 || variant == 0);
   const bool tc_possible = m.tc_ok && m.Kpad / kChunk < 65000;
-  // automatic: the tensor-core scan needs enough landmarks to fill 148 SMs x 2 CTAs x 512 landmarks
-  const bool use_tc = tc_possible && (variant == 16 || (variant == 0 && kTcAutoDefault && M >= 148LL * 4 * kTcLm));
-  if (used_tc) *used_tc = use_tc ? 1 : 0;
+  // the tensor-core scan needs enough landmarks to fill 148 SMs x 2 CTAs x 512 landmarks
+  const bool use_tc = !use_grid && tc_possible && (variant == 16 || (variant == 0 && kTcAutoDefault && M >= 148LL * 4 * kTcLm));
+  if (used_tc) *used_tc = use_grid ? 2 : (use_tc ? 1 : 0);
+  if (use_grid) {
+    if ((e = launch_scan_grid(a, stream)) != cudaSuccess) return e;
+    if (ev_between != nullptr && (e = cudaEventRecord(ev_between, stream)) != cudaSuccess) return e;
+    ev_between = nullptr;
+    if ((e = launch_rerank_grid(a, stream)) != cudaSuccess) return e;
+  }
   if (use_tc) {
     if ((e = launch_scan_tc(a, stream)) != cudaSuccess) return e;
   }
   // Fill the machine: 148 SMs x 2 CTAs; shrink the per-thread landmark count for small batches.
-  int P = (variant == 16 || variant < 0) ? 0 : variant;
+  int P = (variant == 16 || variant == 32 || variant < 0) ? 0 : variant;
   if (P <= 0) {
     if (M >= 148LL * GMMLOC_SCAN_MINB * GMMLOC_SCAN_THREADS * GMMLOC_SCAN_P) P = 8;
     else if (M >= 148LL * 2 * 256 * 4) P = 4;
     else if (M >= 148LL * 2 * 128 * 2) P = 2;
     else P = 1;
   }
-  if (use_tc) {
+  if (use_tc || use_grid) {
     e = cudaSuccess;
   } else {
     switch (P) {
@@ -918,7 +1095,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
     const unsigned grid = (unsigned)(max_ctas < 148 * 4 ? max_ctas : 148 * 4);
     assoc_rerank_kernel<4, 128><<<grid, 128, smem, stream>>>(a);
   }
-  if (launches) *launches = 2;
+  if (launches) *launches = use_grid ? 3 : 2;
   return cudaGetLastError();
 }
 

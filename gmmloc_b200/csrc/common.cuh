@@ -29,6 +29,29 @@ constexpr int kTcTileComps = 4 * kChunk;         // components per UMMA B tile (
 constexpr int kTcRows = 3 * kTcTileComps;        // UMMA N of one tile: [0,64) y0 | [64,128) y1 | [128,192) y2
 constexpr int kTcTileBytes = kTcRows * kTcK * 2; // 6144 B for kChunk = 16
 
+// ---- association grid (assoc_grid kernels) --------------------------------------------------
+// Exact spatial index of the map for the association: cell c of level l lists every component k whose
+// ellipsoid {x : d2_k(x) <= tmax_l} can touch the cell (conservative separating-axis test at map build), so a
+// landmark that falls into c only has to score list(c): every other component has d2 > tmax_l.  Level 1 is a
+// coarser grid with a larger tmax for the landmarks level 0 cannot decide; what level 1 cannot decide takes the
+// brute-force exact path.  `big` lists the components too large to bin (scored for every landmark).
+constexpr int kGridLevels = 2;
+struct GridLevel {
+  float lo[3] = {0.f, 0.f, 0.f};
+  float inv_h = 0.f;
+  int nx = 0, ny = 0, nz = 0;
+  float tmax = 0.f;                 // squared Mahalanobis radius covered by the lists of this level
+  int32_t* start = nullptr;         // nx * ny * nz + 1
+  int32_t* list = nullptr;          // component ids, ascending inside a cell
+  long long entries = 0;
+};
+struct GridDev {
+  int nlev = 0;                     // 0: no grid (brute-force scan only)
+  GridLevel lev[kGridLevels];
+  int32_t* big = nullptr;
+  int nbig = 0;
+};
+
 struct MapDev {
   int K = 0;      // real components
   int Kpad = 0;   // padded to a multiple of kChunk
@@ -42,6 +65,8 @@ struct MapDev {
   uint8_t* is_deg = nullptr;    // K
   uint8_t* is_sal = nullptr;    // K
   float* scan = nullptr;        // Kpad x kScanFloats
+  float* rec = nullptr;         // K x 12: the same nine fp32 coefficients per component, contiguous (grid kernels gather them)
+  GridDev grid;
   long long* nbr_row_ptr = nullptr;  // K + 1: CSR neighbour lists (gmmloc_map_build_neighbors), else null
   int32_t* nbr_col = nullptr;
   long long nbr_count = 0;
@@ -68,6 +93,10 @@ struct FrameParamsDev {
 // Host-side launchers (one per kernel family); every launcher only enqueues on `stream`.
 cudaError_t launch_map_build(const MapDev& m, double deg_eps, double xmax, int* d_err, unsigned int* d_alpha_bits,
                              cudaStream_t stream);  // d_err: [0] error flag, [1] alpha bits, [2] tc_err bits, [3] tc overflow flag
+// builds m.grid (levels, lists, big list) from the component constants already on the device; lo / hi = bounding box
+// of the means.  On any resource limit the grid is left empty (nlev = 0) and cudaSuccess is returned.
+cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3]);
+void free_assoc_grid(MapDev& m);
 cudaError_t launch_bh_neighbors(const MapDev& m, double thresh, int* d_counts, const long long* d_row_ptr, int32_t* d_col,
                                 double* d_dist, cudaStream_t stream);
 cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, double gate, int32_t* d_assign,

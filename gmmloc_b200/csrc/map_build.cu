@@ -203,6 +203,10 @@ __global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps
     atomicOr(err_flag, 1);
     for (int i = 0; i < kScanFloats; ++i) sp[scan_index(k, i)] = 0.f;
     sp[scan_index(k, 6)] = -CUDART_INF_F;
+    if (m.rec) {
+      for (int i = 0; i < 12; ++i) m.rec[(size_t)k * 12 + i] = 0.f;
+      m.rec[(size_t)k * 12 + 6] = -CUDART_INF_F;
+    }
     if (tc_tile) atomicOr(err_flag + 3, 1);
     return;
   }
@@ -215,6 +219,14 @@ __global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps
   sp[scan_index(k, 6)] = (float)(-c0);
   sp[scan_index(k, 7)] = (float)(-c1);
   sp[scan_index(k, 8)] = (float)(-c2);
+  if (m.rec) {  // the same nine values, contiguous per component (association grid kernels)
+    float* r = m.rec + (size_t)k * 12;
+    for (int i = 0; i < 6; ++i) r[i] = (float)U[i];
+    r[6] = (float)(-c0);
+    r[7] = (float)(-c1);
+    r[8] = (float)(-c2);
+    r[9] = r[10] = r[11] = 0.f;
+  }
   // error bound: |sqrt(score32) - d_exact| <= alpha_k for |x|_inf <= xmax,
   // alpha_k = (6 u32 + sqrt(64 u64)) * | |U| 1 (xmax + |mu|_inf) |_2
   const double mmax = fmax(fabs(mu[0]), fmax(fabs(mu[1]), fabs(mu[2])));

@@ -82,6 +82,7 @@ typedef struct {
   int64_t points;        /* points scanned                                              */
   int64_t flagged;       /* points whose fp32 top-2 gap was inside the error bound      */
   int64_t kernel_launches; /* kernels launched by this context since creation           */
+  int64_t flagged_brute; /* of `flagged`: points the grid index could not decide (brute-force exact re-rank) */
 } gmmloc_stats_t;
 
 GMMLOC_API const char* gmmloc_version(void);
@@ -143,12 +144,18 @@ GMMLOC_API gmmloc_status_t gmmloc_ctx_stats(gmmloc_ctx_t* ctx, gmmloc_stats_t* o
  * localization.cpp:101). */
 GMMLOC_API gmmloc_status_t gmmloc_ctx_kernel_times(gmmloc_ctx_t* ctx, float ms[3]);
 
-/* Association scan kernel of this context: GMMLOC_ASSOC_AUTO picks the tensor-core pruning scan (tcgen05; results
- * identical, candidates re-scored exactly) for large batches on maps whose whitening coefficients fit fp16, else
- * the FFMA2 scan; the other two values force one kernel (FFMA2 is used when the tensor-core table is unavailable). */
-enum { GMMLOC_ASSOC_AUTO = 0, GMMLOC_ASSOC_FFMA2 = 1, GMMLOC_ASSOC_TENSOR = 2 };
+/* Association scan kernel of this context.  All of them return identical assignments (the exact argmin of the
+ * reference's d2 over ALL components, lowest index on ties):
+ *   GMMLOC_ASSOC_GRID   grid-indexed scan: an exact spatial index built at map creation lists, per cell, every
+ *                       component whose d2 can be <= a radius anywhere in the cell; a landmark scores its cell list
+ *                       only (~K/300 of the work) and falls back to the brute-force path when the index cannot decide;
+ *   GMMLOC_ASSOC_FFMA2  brute-force FFMA2 scan over all K components (TMA-staged table);
+ *   GMMLOC_ASSOC_TENSOR tensor-core pruning scan (tcgen05) over all K components, candidates re-scored exactly;
+ *   GMMLOC_ASSOC_AUTO   GRID when the map has an index, else FFMA2.
+ * A forced kind that is unavailable for the map falls back to FFMA2. */
+enum { GMMLOC_ASSOC_AUTO = 0, GMMLOC_ASSOC_FFMA2 = 1, GMMLOC_ASSOC_TENSOR = 2, GMMLOC_ASSOC_GRID = 3 };
 GMMLOC_API gmmloc_status_t gmmloc_ctx_set_assoc_kernel(gmmloc_ctx_t* ctx, int kind);
-/* 1 when the last association on ctx ran the tensor-core pruning scan, else 0 */
+/* kernel the last association on ctx ran: 0 FFMA2 scan, 1 tensor-core pruning scan, 2 grid-indexed scan */
 GMMLOC_API int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx);
 
 /* page-locked host memory for the host entry points (pageable buffers also work, via staging) */

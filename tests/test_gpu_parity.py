@@ -509,3 +509,78 @@ def test_tensor_core_scan_falls_back_when_coefficients_do_not_fit_fp16(gpu):
     a1, _, kind, _ = _assoc_with(ctx, g, g.capi.ASSOC_TENSOR, m, pts)
     a0, _, _, _ = _assoc_with(ctx, g, g.capi.ASSOC_FFMA2, m, pts)
     assert kind == "ffma2" and np.array_equal(a0, a1)
+
+
+# ---------------------------------------------------------------- grid-indexed scan (the default association kernel)
+@pytest.mark.parametrize("case", ["c2", "v1", "v2", "c5", "ragged", "tiny", "flat"])
+def test_grid_scan_gives_identical_assignments(gpu, oracle, golden_maps, case):
+    """The grid index is exact: a cell lists every component whose d2 can be <= tmax inside the cell, undecidable
+    landmarks fall back to the brute-force exact path.  Every output must equal the brute-force FFMA2 scan's (bit for
+    bit, d2 included) and the oracle's."""
+    g, ctx = gpu
+    spread = 2.0
+    if case in ("v1", "v2"):
+        mean, cov = golden_maps[case]["mean"], golden_maps[case]["cov"]
+        M = 150000
+    elif case == "c5":
+        mean, cov = synth.make_map(50000, 0.95, seed=5)
+        M = 200000
+    elif case == "ragged":
+        mean, cov = synth.make_map(1153, 0.5, seed=6)
+        M = 70001
+    elif case == "tiny":
+        mean, cov = synth.make_map(3, 0.5, seed=7)
+        M = 5000
+        spread = 30.0
+    elif case == "flat":  # all means in one plane (degenerate bounding box) + one huge component (big list)
+        mean, cov = synth.make_map(2000, 0.9, seed=9)
+        mean = mean.copy()
+        mean[:, 2] = 1.25
+        cov = cov.copy()
+        cov[7] = (np.diag([400.0, 900.0, 1e-4])).ravel()
+        M = 60000
+    else:
+        mean, cov = synth.make_map(10000, 0.5)
+        M = 300000
+    m = g.GMM(mean, cov)
+    pts, _ = synth.make_points_near(mean, cov, M, seed=11, spread=spread)
+    pts[::1000] += 50.0          # far outside the grid
+    pts[5::5000] = np.nan        # non-finite landmarks
+    pts[7::5000] = np.inf
+    pts[11::3000] += 1.7         # sparse regions: second level / brute-force fallback
+    a0, d0, k0, _ = _assoc_with(ctx, g, g.capi.ASSOC_FFMA2, m, pts)
+    a1, d1, k1, flagged = _assoc_with(ctx, g, g.capi.ASSOC_GRID, m, pts)
+    assert k0 == "ffma2" and k1 == "grid"
+    assert np.array_equal(a0, a1)
+    assert np.array_equal(d0, d1, equal_nan=True)
+    a2, d2, k2, _ = _assoc_with(ctx, g, g.capi.ASSOC_AUTO, m, pts)
+    assert k2 == "grid" and np.array_equal(a2, a1) and np.array_equal(d2, d1, equal_nan=True)
+    sel = np.arange(0, M, 97)
+    comps = oracle.map_build(mean, cov)
+    ao, _ = oracle.associate(comps, pts[sel], nthreads=8)
+    assert np.array_equal(a1.reshape(-1)[sel], ao)
+    g0 = _assoc_with(ctx, g, g.capi.ASSOC_FFMA2, m, pts[:20000], gate=9.0)[0]
+    g1 = _assoc_with(ctx, g, g.capi.ASSOC_GRID, m, pts[:20000], gate=9.0)[0]
+    assert np.array_equal(g0, g1) and (g1 == -1).any()
+
+
+def test_grid_scan_exact_ties_and_frames(gpu, oracle):
+    g, ctx = gpu
+    mean, cov = synth.make_map(500, 0.5, seed=21)
+    mean = np.concatenate([mean, mean[:100], mean[:50]])
+    cov = np.concatenate([cov, cov[:100], cov[:50]])
+    pts, _ = synth.make_points_near(mean[:500], cov[:500], 20000, seed=4)
+    m = g.GMM(mean, cov)
+    a1, d1, k1, flagged = _assoc_with(ctx, g, g.capi.ASSOC_GRID, m, pts)
+    ao, d2o = oracle.associate(oracle.map_build(mean, cov), pts, nthreads=8)
+    assert k1 == "grid" and np.array_equal(a1.reshape(-1), ao) and a1.max() < 500 and flagged > 0
+    assert np.array_equal(d1.reshape(-1), d2o.astype(np.float32))
+    # real frames of the bench workload: few landmarks may need the brute-force fallback
+    mean, cov = synth.make_map(10000, 0.5)
+    fr = synth.make_frames(mean, cov, 64, 2000, seed=12)
+    m = g.GMM(mean, cov)
+    a0 = _assoc_with(ctx, g, g.capi.ASSOC_FFMA2, m, fr["pts_w"])[0]
+    a1 = _assoc_with(ctx, g, g.capi.ASSOC_GRID, m, fr["pts_w"])[0]
+    st = ctx.stats()
+    assert np.array_equal(a0, a1)
+    assert st["flagged_brute"] < 0.01 * st["points"], st
