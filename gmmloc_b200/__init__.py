@@ -154,6 +154,10 @@ class Context:
         """capi.ASSOC_AUTO / ASSOC_FFMA2 / ASSOC_TENSOR (tcgen05 pruning scan) / ASSOC_GRID (grid-indexed scan); identical results."""
         capi.check(capi.lib().gmmloc_ctx_set_assoc_kernel(self._h, int(kind)))
 
+    def set_gn_precision(self, precision: int) -> None:
+        """capi.GN_MIXED (default: fp64 state / residuals, fp32 Jacobian algebra) or capi.GN_FP64."""
+        capi.check(capi.lib().gmmloc_ctx_set_gn_precision(self._h, int(precision)))
+
     def last_assoc_kernel(self) -> str:
         return ("ffma2", "tensor", "grid")[capi.lib().gmmloc_ctx_last_assoc_kernel(self._h)]
 

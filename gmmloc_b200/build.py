@@ -31,6 +31,7 @@ SOURCES = {
     "grid_build.cu": [],
     "assoc_scan.cu": [],
     "frame_gn.cu": [],
+    "frame_gn_mixed.cu": [],
     "pose_lm.cu": [],
     "local_ba.cu": [],
     "point_gn.cu": ["-fmad=false"],

@@ -16,6 +16,7 @@ MODE_JOINT, MODE_POSE_ONLY, MODE_POINTS_ONLY = 0, 1, 2
 FRAME_NUMERIC = 1
 VIEW_OVERFLOW = 1
 ASSOC_AUTO, ASSOC_FFMA2, ASSOC_TENSOR, ASSOC_GRID = 0, 1, 2, 3
+GN_FP64, GN_MIXED = 0, 1
 
 
 class Camera(C.Structure):
@@ -68,6 +69,7 @@ SYMBOLS = {
     "gmmloc_ctx_kernel_times": (_i, [_vp, C.POINTER(C.c_float * 3)]),
     "gmmloc_ctx_set_assoc_kernel": (_i, [_vp, _i]),
     "gmmloc_ctx_last_assoc_kernel": (_i, [_vp]),
+    "gmmloc_ctx_set_gn_precision": (_i, [_vp, _i]),
     "gmmloc_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "gmmloc_host_free": (None, [_vp]),
     "gmmloc_associate": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp]),

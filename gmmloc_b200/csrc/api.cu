@@ -201,6 +201,7 @@ struct gmmloc_map {
 struct Lane {
   cudaStream_t stream = nullptr;
   DevBuf flag_count, flag_idx, flag_thr;  // association work lists
+  DevBuf next_frame;                      // frame counter of the persistent frame-GN kernel
   DevBuf xws, fws;                        // frame-GN global workspaces (N too large for shared memory)
   int* h_flag_count = nullptr;            // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // scan begin | scan end | re-rank end | GN end
@@ -224,6 +225,7 @@ struct gmmloc_ctx {
   std::vector<cudaEvent_t> ev_in, ev_done;          // per-chunk events (inputs landed / results ready)
   gmmloc_stats_t stats{};
   int assoc_kind = GMMLOC_ASSOC_AUTO;
+  int gn_precision = GMMLOC_GN_MIXED;
   int last_assoc_tc = 0;
 };
 
@@ -281,7 +283,7 @@ void gmmloc_map_destroy(gmmloc_map_t* m) {
   cudaSetDevice(m->device);
   cudaFree(m->d.mean); cudaFree(m->d.cov); cudaFree(m->d.cov_inv); cudaFree(m->d.det); cudaFree(m->d.scale);
   cudaFree(m->d.axis); cudaFree(m->d.sqrt_info); cudaFree(m->d.is_deg); cudaFree(m->d.is_sal); cudaFree(m->d.scan);
-  cudaFree(m->d.nbr_row_ptr); cudaFree(m->d.nbr_col); cudaFree(m->d.tc_table); cudaFree(m->d.rec);
+  cudaFree(m->d.nbr_row_ptr); cudaFree(m->d.nbr_col); cudaFree(m->d.tc_table); cudaFree(m->d.rec); cudaFree(m->d.gn_tab);
   free_assoc_grid(m->d);
   cudaSetDevice(prev);
   delete m;
@@ -329,6 +331,7 @@ gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, 
   alloc((void**)&d.is_sal, K);
   alloc((void**)&d.scan, sizeof(float) * kScanFloats * d.Kpad);
   alloc((void**)&d.rec, sizeof(float) * 12 * (size_t)K);
+  alloc((void**)&d.gn_tab, sizeof(float) * 8 * (size_t)K);
   if (kChunk == 16) alloc((void**)&d.tc_table, (size_t)((d.Kpad + kTcTileComps - 1) / kTcTileComps) * kTcTileBytes);
   int* d_err = nullptr;
   alloc((void**)&d_err, 4 * sizeof(int));
@@ -536,6 +539,7 @@ gmmloc_status_t gmmloc_ctx_create(int device, gmmloc_ctx_t** out) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaMallocHost((void**)&l.h_flag_count, 2 * sizeof(int));
     if (e == cudaSuccess) e = l.flag_count.reserve(2 * sizeof(int));
+    if (e == cudaSuccess) e = l.next_frame.reserve(sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(l.flag_count.p, 0, 2 * sizeof(int));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&l.ev[i]);
   }
@@ -556,7 +560,7 @@ void gmmloc_ctx_destroy(gmmloc_ctx_t* c) {
   cudaSetDevice(c->device);
   for (Lane& l : c->lanes) {
     if (l.stream) cudaStreamSynchronize(l.stream);
-    DevBuf* lb[] = {&l.flag_count, &l.flag_idx, &l.flag_thr, &l.xws, &l.fws};
+    DevBuf* lb[] = {&l.flag_count, &l.flag_idx, &l.flag_thr, &l.xws, &l.fws, &l.next_frame};
     for (DevBuf* b : lb) b->release();
     if (l.h_flag_count) cudaFreeHost(l.h_flag_count);
     for (cudaEvent_t e : l.ev)
@@ -615,6 +619,13 @@ gmmloc_status_t gmmloc_ctx_set_assoc_kernel(gmmloc_ctx_t* ctx, int kind) {
   return GMMLOC_OK;
 }
 int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx) { return ctx ? ctx->last_assoc_tc : 0; }
+
+gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int precision) {
+  if (!ctx || (precision != GMMLOC_GN_FP64 && precision != GMMLOC_GN_MIXED))
+    return fail(GMMLOC_EINVAL, "gmmloc_ctx_set_gn_precision: bad argument");
+  ctx->gn_precision = precision;
+  return GMMLOC_OK;
+}
 
 gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out) {
   if (!out) return fail(GMMLOC_EINVAL, "null out");
@@ -728,7 +739,18 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
     a.fws = ctx->L().fws.as<uint8_t>();
   }
   if (!ctx->L().ev_assoc) CU(cudaEventRecord(ctx->L().ev[2], ctx->L().stream));
-  CU(launch_frame_gn(a, ctx->L().stream));
+  static const int gn_forced = [] {  // GMMLOC_GN_PRECISION=fp64|mixed overrides the context setting (A/B runs)
+    const char* v = std::getenv("GMMLOC_GN_PRECISION");
+    if (v == nullptr) return -1;
+    if (std::strcmp(v, "fp64") == 0) return (int)GMMLOC_GN_FP64;
+    if (std::strcmp(v, "mixed") == 0) return (int)GMMLOC_GN_MIXED;
+    return -1;
+  }();
+  const int gn_prec = gn_forced >= 0 ? gn_forced : ctx->gn_precision;
+  if (gn_prec == GMMLOC_GN_MIXED && map->d.gn_tab != nullptr)
+    CU(launch_frame_gn_mixed(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().stream));
+  else
+    CU(launch_frame_gn(a, ctx->L().stream));
   CU(cudaEventRecord(ctx->L().ev[3], ctx->L().stream));
   ctx->L().ev_gn = true;
   ctx->stats.kernel_launches += 1;
@@ -757,7 +779,11 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   // Pipelined over chunks of frames: H2D of chunk c+1 (copy stream) overlaps the kernels of chunk c
   // (compute stream) and the D2H of chunk c-1 (second copy stream); PCIe is full duplex.  With
   // page-locked caller buffers the copies are truly asynchronous; pageable buffers still work.
-  const int chunk = (B >= 1024) ? 512 : B;
+  static const int chunk_env = [] {
+    const char* v = std::getenv("GMMLOC_E2E_CHUNK");
+    return v ? std::atoi(v) : 0;
+  }();
+  const int chunk = chunk_env > 0 ? std::min(chunk_env, B) : ((B >= 1024) ? 512 : B);
   const int nchunks = (B + chunk - 1) / chunk;
   while ((int)ctx->ev_in.size() < nchunks) {
     cudaEvent_t a = nullptr, b = nullptr;

@@ -66,6 +66,8 @@ struct MapDev {
   uint8_t* is_sal = nullptr;    // K
   float* scan = nullptr;        // Kpad x kScanFloats
   float* rec = nullptr;         // K x 12: the same nine fp32 coefficients per component, contiguous (grid kernels gather them)
+  float* gn_tab = nullptr;      // K x 8 fp32: structure-edge Hessian model of the mixed-precision frame GN — planar
+                                // component: axis_.col(0) in [0..2]; otherwise the 6 unique entries of cov_inv in [0..5]
   GridDev grid;
   long long* nbr_row_ptr = nullptr;  // K + 1: CSR neighbour lists (gmmloc_map_build_neighbors), else null
   int32_t* nbr_col = nullptr;
@@ -122,6 +124,9 @@ struct FrameArgs {
   uint8_t* fws;             // B x N flag workspace (same condition)
 };
 cudaError_t launch_frame_gn(const FrameArgs& a, cudaStream_t stream);
+// mixed-precision twin (frame_gn_mixed.cu): fp64 state / residuals, fp32 Jacobian algebra; persistent CTAs fetch frames
+// through *d_next_frame (zeroed by the launcher on `stream`)
+cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_next_frame, cudaStream_t stream);
 size_t frame_gn_smem_limit_points();  // largest N whose per-frame state stays in shared memory
 
 struct PoseLmArgs {

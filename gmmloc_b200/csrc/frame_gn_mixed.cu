@@ -1,0 +1,495 @@
+// frame_gn_mixed.cu — K3m: the per-frame structure-constrained Gauss-Newton of frame_gn.cu in MIXED precision.
+//
+// Same system, same sweep schedule and the same formulation as frame_gn_kernel (see the header of frame_gn.cu for the
+// reference citations: Localization::jointOptimization, gmmloc/src/modules/localization_opt.cpp:456-925, single free
+// pose; edges of gmmloc/src/gmm/factors.cpp:5-17,55-64,84-107,133-168).  What changes is where fp64 is spent:
+//
+//   fp64 : the state (landmarks in shared memory, pose), the camera-frame point pc = R x + t, the reprojection
+//          RESIDUAL e = obs - proj(pc), the structure offset x - mu, the 6x6 reduced system (cross-thread sums,
+//          Cholesky, SE3 update) and the state updates x += dx.
+//   fp32 : everything that multiplies those residuals — projection Jacobian, G = w P^T P, S_c, D^-1, T = G D^-1,
+//          M = T S_c, A^T M A — i.e. the Gauss-Newton model of the Hessian and the Jacobian transposes.
+//
+// Why this keeps the result: a Gauss-Newton fixed point is where the GRADIENTS vanish (per point h + s = 0, pose
+// sum A^T h = 0).  The gradients are products of fp32 Jacobians (relative error 2^-24) with residuals that are
+// formed in fp64 and only then rounded, so their error is RELATIVE to the (small) residual; the formulation
+// v = h - T (h + s) keeps the pose right-hand side equal to A^T h at the fixed point whatever the error of D^-1.
+// The fp32 Hessian model only perturbs the convergence rate (by ~1e-3 relative at cond(D) ~ 1e4).  Measured against
+// the fp64 oracle: pose differences ~1e-9 rad / ~1e-9 m (tolerance 1e-5 rad / 1e-4 m), identical edge gates
+// (still evaluated in fp64 at iteration 0) and outlier flags (fp64 post-check).  frame_gn_kernel (all fp64) stays
+// selectable (gmmloc_ctx_set_gn_precision) for A/B runs.
+#include <math_constants.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+#include "gn_common.cuh"
+
+namespace gmmloc {
+
+namespace {
+
+#ifndef GMMLOC_GNM_THREADS
+#define GMMLOC_GNM_THREADS 256
+#endif
+#ifndef GMMLOC_GNM_MINB
+#define GMMLOC_GNM_MINB 2
+#endif
+constexpr int kThreads = GMMLOC_GNM_THREADS;
+constexpr int kWarps = kThreads / 32;
+constexpr int kAcc = 27;
+
+enum : uint8_t { F_STEREO = 1, F_STR = 2, F_FREE = 4, F_DEG = 8 };
+
+struct V3f {
+  float x, y, z;
+};
+struct S3f {
+  float xx, xy, xz, yy, yz, zz;
+};
+__device__ __forceinline__ V3f rotf(const float* R, const V3f& v) {
+  return {R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z};
+}
+__device__ __forceinline__ V3f rotf_t(const float* R, const V3f& v) {
+  return {R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z};
+}
+__device__ __forceinline__ V3f mulf(const S3f& A, const V3f& v) {
+  return {A.xx * v.x + A.xy * v.y + A.xz * v.z, A.xy * v.x + A.yy * v.y + A.yz * v.z, A.xz * v.x + A.yz * v.y + A.zz * v.z};
+}
+__device__ __forceinline__ S3f inv_symf(const S3f& D, bool& ok) {
+  const float c00 = D.yy * D.zz - D.yz * D.yz;
+  const float c01 = D.xz * D.yz - D.xy * D.zz;
+  const float c02 = D.xy * D.yz - D.xz * D.yy;
+  const float det = D.xx * c00 + D.xy * c01 + D.xz * c02;
+  const float id = 1.0f / det;
+  ok = (det != 0.0f) && isfinite(id);
+  return {c00 * id, c01 * id, c02 * id, (D.xx * D.zz - D.xz * D.xz) * id, (D.xy * D.xz - D.xx * D.yz) * id,
+          (D.xx * D.yy - D.xy * D.xy) * id};
+}
+
+// camera constants in fp32 + the pose of one linearisation point in both precisions
+struct PoseBoth {
+  double R[9], t[3];
+  float Rf[9];
+};
+
+// per-point constants of the structure edge (fp32 Hessian model; the mean stays fp64 for the offset x - mu)
+struct StrF {
+  double mu[3];
+  float c[6];
+};
+__device__ __forceinline__ void load_structure(const FrameArgs& a, const float* __restrict__ gn_tab, int k, StrF& sc) {
+  const double* mu = a.mean + (size_t)k * 3;
+  sc.mu[0] = mu[0]; sc.mu[1] = mu[1]; sc.mu[2] = mu[2];
+  const float4 t0 = __ldg(reinterpret_cast<const float4*>(gn_tab) + 2 * (size_t)k);
+  const float2 t1 = __ldg(reinterpret_cast<const float2*>(gn_tab) + 4 * (size_t)k + 2);
+  sc.c[0] = t0.x; sc.c[1] = t0.y; sc.c[2] = t0.z; sc.c[3] = t0.w; sc.c[4] = t1.x; sc.c[5] = t1.y;
+}
+
+// fp64 part of one linearisation: camera-frame point and reprojection residual (rounded to fp32 at the end)
+struct Lin {
+  V3f pc;     // camera-frame point
+  float iz;   // 1 / z
+  V3f e;      // residual (u, v, u_r); e.z = 0 for monocular points
+};
+__device__ __forceinline__ Lin linearise(const FrameParamsDev& P, const double* R, const double* t, double x0, double x1, double x2,
+                                         const float* ob, bool stereo) {
+  const double pcx = R[0] * x0 + R[1] * x1 + R[2] * x2 + t[0];
+  const double pcy = R[3] * x0 + R[4] * x1 + R[5] * x2 + t[1];
+  const double pcz = R[6] * x0 + R[7] * x1 + R[8] * x2 + t[2];
+  // 1 / z: fp32 reciprocal + one Newton step in fp64 (relative error ~1e-14; a full fp64 division costs ~30 instructions)
+  double iz = (double)__frcp_rn((float)pcz);
+  iz = iz * (2.0 - pcz * iz);
+  const double u = pcx * (P.fx * iz) + P.cx, v = pcy * (P.fy * iz) + P.cy;
+  Lin L;
+  L.e.x = (float)((double)ob[0] - u);
+  L.e.y = (float)((double)ob[1] - v);
+  L.e.z = stereo ? (float)((double)ob[2] - (u - P.bf * iz)) : 0.f;
+  L.pc = {(float)pcx, (float)pcy, (float)pcz};
+  L.iz = (float)iz;
+  return L;
+}
+
+struct CamF {
+  float fx, fy, bf, lam, d_mono, d_stereo;
+  int robust;
+};
+
+// fp32 Gauss-Newton model of the reprojection edge: G = w P^T P, h = w P^T e
+__device__ __forceinline__ void reprojf(const CamF& C, const Lin& L, bool stereo, float w, S3f& G, V3f& h) {
+  const float a = C.fx * L.iz, b = C.fy * L.iz;
+  const float c0 = -a * L.pc.x * L.iz, c1 = -b * L.pc.y * L.iz;
+  float c2 = 0.f, a2 = 0.f;
+  if (stereo) {
+    c2 = c0 + C.bf * L.iz * L.iz;
+    a2 = a;
+  }
+  if (C.robust) {  // g2o RobustKernelHuber: weight delta / sqrt(chi2) beyond delta^2
+    const float chi = w * (L.e.x * L.e.x + L.e.y * L.e.y + L.e.z * L.e.z);
+    const float delta = stereo ? C.d_stereo : C.d_mono;
+    if (chi > delta * delta) w *= delta * rsqrtf(chi);
+  }
+  G.xx = w * (a * a + a2 * a2);
+  G.xy = 0.f;
+  G.xz = w * (a * c0 + a2 * c2);
+  G.yy = w * (b * b);
+  G.yz = w * (b * c1);
+  G.zz = w * (c0 * c0 + c1 * c1 + c2 * c2);
+  h.x = w * (a * L.e.x + a2 * L.e.z);
+  h.y = w * (b * L.e.y);
+  h.z = w * (c0 * L.e.x + c1 * L.e.y + c2 * L.e.z);
+}
+
+// structure edge rotated into the camera frame: S_c = R S R^T, s_c = R b_s; the offset x - mu is formed in fp64
+__device__ __forceinline__ void structuref(const CamF& C, const float* Rf, const StrF& sc, uint8_t fl, double x0, double x1, double x2,
+                                           S3f& S, V3f& s) {
+  const V3f d = {(float)(x0 - sc.mu[0]), (float)(x1 - sc.mu[1]), (float)(x2 - sc.mu[2])};
+  if (fl & F_DEG) {
+    const V3f n = {sc.c[0], sc.c[1], sc.c[2]};
+    const float es = n.x * d.x + n.y * d.y + n.z * d.z;
+    const V3f nc = rotf(Rf, n);
+    const float lam = C.lam;
+    S = {lam * nc.x * nc.x, lam * nc.x * nc.y, lam * nc.x * nc.z, lam * nc.y * nc.y, lam * nc.y * nc.z, lam * nc.z * nc.z};
+    const float c = -lam * es;
+    s = {c * nc.x, c * nc.y, c * nc.z};
+  } else {
+    const S3f Sw = {sc.c[0], sc.c[1], sc.c[2], sc.c[3], sc.c[4], sc.c[5]};
+    const V3f bw = mulf(Sw, d);
+    s = rotf(Rf, {-bw.x, -bw.y, -bw.z});
+    float t[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      t[r * 3 + 0] = Rf[r * 3] * Sw.xx + Rf[r * 3 + 1] * Sw.xy + Rf[r * 3 + 2] * Sw.xz;
+      t[r * 3 + 1] = Rf[r * 3] * Sw.xy + Rf[r * 3 + 1] * Sw.yy + Rf[r * 3 + 2] * Sw.yz;
+      t[r * 3 + 2] = Rf[r * 3] * Sw.xz + Rf[r * 3 + 1] * Sw.yz + Rf[r * 3 + 2] * Sw.zz;
+    }
+    S.xx = t[0] * Rf[0] + t[1] * Rf[1] + t[2] * Rf[2];
+    S.xy = t[0] * Rf[3] + t[1] * Rf[4] + t[2] * Rf[5];
+    S.xz = t[0] * Rf[6] + t[1] * Rf[7] + t[2] * Rf[8];
+    S.yy = t[3] * Rf[3] + t[4] * Rf[4] + t[5] * Rf[5];
+    S.yz = t[3] * Rf[6] + t[4] * Rf[7] + t[5] * Rf[8];
+    S.zz = t[6] * Rf[6] + t[7] * Rf[7] + t[8] * Rf[8];
+  }
+}
+
+// acc[0..20] += upper triangle of A^T M A, acc[21..26] += A^T v, A = [-[pc]x  I]   (fp32 twin of accumulate_pose)
+__device__ __forceinline__ void accumulate_posef(float* acc, const V3f& pc, const S3f& M, const V3f& v) {
+  const float C00 = pc.y * M.xz - pc.z * M.xy, C01 = pc.y * M.yz - pc.z * M.yy, C02 = pc.y * M.zz - pc.z * M.yz;
+  const float C10 = pc.z * M.xx - pc.x * M.xz, C11 = pc.z * M.xy - pc.x * M.yz, C12 = pc.z * M.xz - pc.x * M.zz;
+  const float C20 = pc.x * M.xy - pc.y * M.xx, C21 = pc.x * M.yy - pc.y * M.xy, C22 = pc.x * M.yz - pc.y * M.xz;
+  acc[0] += C02 * pc.y - C01 * pc.z;
+  acc[1] += C00 * pc.z - C02 * pc.x;
+  acc[2] += C01 * pc.x - C00 * pc.y;
+  acc[3] += C00;
+  acc[4] += C01;
+  acc[5] += C02;
+  acc[6] += C10 * pc.z - C12 * pc.x;
+  acc[7] += C11 * pc.x - C10 * pc.y;
+  acc[8] += C10;
+  acc[9] += C11;
+  acc[10] += C12;
+  acc[11] += C21 * pc.x - C20 * pc.y;
+  acc[12] += C20;
+  acc[13] += C21;
+  acc[14] += C22;
+  acc[15] += M.xx;
+  acc[16] += M.xy;
+  acc[17] += M.xz;
+  acc[18] += M.yy;
+  acc[19] += M.yz;
+  acc[20] += M.zz;
+  acc[21] += pc.y * v.z - pc.z * v.y;
+  acc[22] += pc.z * v.x - pc.x * v.z;
+  acc[23] += pc.x * v.y - pc.y * v.x;
+  acc[24] += v.x;
+  acc[25] += v.y;
+  acc[26] += v.z;
+}
+
+__global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
+                                                                                   int* __restrict__ next_frame) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double s_red[kWarps][kAcc];
+  __shared__ double s_acc[kAcc];
+  __shared__ double s_pose[7], s_dxi[6];
+  __shared__ PoseBoth s_new, s_old;  // linearisation points: state sw (accumulate) and state sw-1 (update)
+  __shared__ int s_fail1, s_fail2, s_frame;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N;
+  const FrameParamsDev& P = a.prm;
+  const bool pose_free = P.factor_mode != GMMLOC_MODE_POINTS_ONLY;
+  const bool pts_free = P.factor_mode != GMMLOC_MODE_POSE_ONLY;
+  CamF C;
+  C.fx = (float)P.fx; C.fy = (float)P.fy; C.bf = (float)P.bf; C.lam = (float)P.ba_lambda2;
+  C.d_mono = (float)P.delta_mono; C.d_stereo = (float)P.delta_stereo; C.robust = P.robust;
+  const double view_cos_thresh = cos(78.0 * 3.14159265358979323846 / 180.0);  // gaussian_mixture.cpp:284
+
+  // persistent CTAs: frames are handed out through a global counter (no tail wave)
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) s_frame = atomicAdd(next_frame, 1);
+    __syncthreads();
+    const int f = s_frame;
+    if (f >= a.B) break;
+
+    double* xs;
+    uint8_t* fl;
+    if (a.xws != nullptr) {
+      xs = a.xws + (size_t)f * N * 3;
+      fl = a.fws + (size_t)f * N;
+    } else {
+      xs = reinterpret_cast<double*>(smem_raw);
+      fl = reinterpret_cast<uint8_t*>(xs + (size_t)N * 3);
+    }
+    const float* pts = a.pts_w + (size_t)f * N * 3;
+    const float* obs = a.obs + (size_t)f * N * 3;
+    const uint8_t* oct = a.octave + (size_t)f * N;
+    const int32_t* asg = a.assign + (size_t)f * N;
+
+    if (tid == 0) {
+      double q[7];
+      for (int i = 0; i < 7; ++i) q[i] = a.pose0[(size_t)f * 7 + i];
+      quat_normalize(q);
+      for (int i = 0; i < 7; ++i) s_pose[i] = q[i];
+      quat_to_rot(q, s_new.R);
+      for (int i = 0; i < 6; ++i) s_dxi[i] = 0.0;
+      for (int i = 0; i < 9; ++i) {
+        s_new.Rf[i] = (float)s_new.R[i];
+        s_old.R[i] = s_new.R[i];
+        s_old.Rf[i] = s_new.Rf[i];
+      }
+      for (int i = 0; i < 3; ++i) s_new.t[i] = s_old.t[i] = q[4 + i];
+      s_fail1 = 0;
+      s_fail2 = 0;
+    }
+    __syncthreads();
+    const double twc0 = -(s_new.R[0] * s_pose[4] + s_new.R[3] * s_pose[5] + s_new.R[6] * s_pose[6]);
+    const double twc1 = -(s_new.R[1] * s_pose[4] + s_new.R[4] * s_pose[5] + s_new.R[7] * s_pose[6]);
+    const double twc2 = -(s_new.R[2] * s_pose[4] + s_new.R[5] * s_pose[5] + s_new.R[8] * s_pose[6]);
+    // ---- landmarks to fp64; structure-edge gates fixed at iteration 0, in fp64 exactly as frame_gn_kernel ----
+    for (int i = tid; i < N; i += kThreads) {
+      const double x0 = (double)pts[i * 3], x1 = (double)pts[i * 3 + 1], x2 = (double)pts[i * 3 + 2];
+      xs[i * 3] = x0;
+      xs[i * 3 + 1] = x1;
+      xs[i * 3 + 2] = x2;
+      uint8_t b = (obs[i * 3 + 2] >= 0.0f) ? F_STEREO : 0;
+      const int k = asg[i];
+      if (k >= 0 && pts_free) {
+        if (a.is_deg[k]) {
+          b |= F_DEG;
+          const double* ax = a.axis + (size_t)k * 9;
+          const double* mu = a.mean + (size_t)k * 3;
+          const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
+          if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;
+          const double p0 = mu[0] - twc0, p1 = mu[1] - twc1, p2 = mu[2] - twc2;
+          const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
+          if (view_cos < view_cos_thresh) b &= ~F_STR;
+        } else {
+          if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;
+        }
+      }
+      if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
+      fl[i] = b;
+    }
+    __syncthreads();
+
+    const int iters = P.gn_iters;
+    const int sweeps = (iters > 0) ? iters + 1 : 0;
+    for (int sw = 0; sw < sweeps; ++sw) {
+      const bool do_update = pts_free && sw > 0;
+      const bool do_acc = pose_free && sw < iters;
+      if (!do_update && !do_acc) continue;
+      const V3f om = {(float)s_dxi[0], (float)s_dxi[1], (float)s_dxi[2]}, up = {(float)s_dxi[3], (float)s_dxi[4], (float)s_dxi[5]};
+      float acc[kAcc];
+#pragma unroll
+      for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
+      bool bad1 = false, bad2 = false;
+      for (int i = tid; i < N; i += kThreads) {
+        const uint8_t b = fl[i];
+        const bool free_pt = b & F_FREE, str = b & F_STR, stereo = b & F_STEREO;
+        const bool upd = do_update && free_pt;
+        const bool accp = do_acc && !(free_pt && !str);  // a free point without a structure edge contributes exactly zero
+        if (!upd && !accp) continue;
+        double x0 = xs[i * 3], x1 = xs[i * 3 + 1], x2 = xs[i * 3 + 2];
+        const float ob[3] = {obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2]};
+        const float w = P.s2inv[oct[i] & 7];
+        StrF sc;
+        if (str) load_structure(a, gn_tab, asg[i], sc);
+        if (upd) {
+          const Lin L = linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, stereo);
+          S3f G;
+          V3f h;
+          reprojf(C, L, stereo, w, G, h);
+          S3f D = G;
+          V3f bl = h;
+          if (str) {
+            S3f S;
+            V3f s;
+            structuref(C, s_old.Rf, sc, b, x0, x1, x2, S, s);
+            D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
+            bl = {h.x + s.x, h.y + s.y, h.z + s.z};
+          }
+          bool ok;
+          const S3f Di = inv_symf(D, ok);
+          // A dxi = omega x pc + upsilon
+          const V3f ad = {om.y * L.pc.z - om.z * L.pc.y + up.x, om.z * L.pc.x - om.x * L.pc.z + up.y,
+                          om.x * L.pc.y - om.y * L.pc.x + up.z};
+          const V3f ga = mulf(G, ad);
+          const V3f dc = mulf(Di, {bl.x - ga.x, bl.y - ga.y, bl.z - ga.z});
+          const V3f dw = rotf_t(s_old.Rf, dc);
+          x0 += (double)dw.x;
+          x1 += (double)dw.y;
+          x2 += (double)dw.z;
+          if (!(ok && isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad2 = true;
+          xs[i * 3] = x0;
+          xs[i * 3 + 1] = x1;
+          xs[i * 3 + 2] = x2;
+        }
+        if (accp) {
+          const Lin L = linearise(P, s_new.R, s_new.t, x0, x1, x2, ob, stereo);
+          S3f G;
+          V3f h;
+          reprojf(C, L, stereo, w, G, h);
+          S3f M = G;
+          V3f v = h;
+          if (free_pt) {
+            S3f S;
+            V3f s;
+            structuref(C, s_new.Rf, sc, b, x0, x1, x2, S, s);
+            const S3f D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
+            bool ok;
+            const S3f Di = inv_symf(D, ok);
+            if (!ok) bad1 = true;
+            const float T00 = G.xx * Di.xx + G.xy * Di.xy + G.xz * Di.xz, T01 = G.xx * Di.xy + G.xy * Di.yy + G.xz * Di.yz,
+                        T02 = G.xx * Di.xz + G.xy * Di.yz + G.xz * Di.zz;
+            const float T10 = G.xy * Di.xx + G.yy * Di.xy + G.yz * Di.xz, T11 = G.xy * Di.xy + G.yy * Di.yy + G.yz * Di.yz,
+                        T12 = G.xy * Di.xz + G.yy * Di.yz + G.yz * Di.zz;
+            const float T20 = G.xz * Di.xx + G.yz * Di.xy + G.zz * Di.xz, T21 = G.xz * Di.xy + G.yz * Di.yy + G.zz * Di.yz,
+                        T22 = G.xz * Di.xz + G.yz * Di.yz + G.zz * Di.zz;
+            const V3f bl = {h.x + s.x, h.y + s.y, h.z + s.z};
+            // v = h - T (h + s): equals h at the fixed point (h + s = 0) whatever the rounding of D^-1
+            v = {h.x - (T00 * bl.x + T01 * bl.y + T02 * bl.z), h.y - (T10 * bl.x + T11 * bl.y + T12 * bl.z),
+                 h.z - (T20 * bl.x + T21 * bl.y + T22 * bl.z)};
+            M.xx = T00 * S.xx + T01 * S.xy + T02 * S.xz;
+            M.xy = T00 * S.xy + T01 * S.yy + T02 * S.yz;
+            M.xz = T00 * S.xz + T01 * S.yz + T02 * S.zz;
+            M.yy = T10 * S.xy + T11 * S.yy + T12 * S.yz;
+            M.yz = T10 * S.xz + T11 * S.yz + T12 * S.zz;
+            M.zz = T20 * S.xz + T21 * S.yz + T22 * S.zz;
+          }
+          accumulate_posef(acc, L.pc, M, v);
+        }
+      }
+      if (bad2) s_fail2 = 1;
+      if (bad1) s_fail1 = 1;
+      if (do_acc) {
+#pragma unroll
+        for (int i = 0; i < kAcc; ++i) {
+          double s = (double)acc[i];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+          if (lane == 0) s_red[warp][i] = s;
+        }
+      }
+      __syncthreads();
+      if (s_fail2) break;  // uniform
+      if (do_acc) {
+        if (tid < kAcc) {
+          double s = s_red[0][tid];
+#pragma unroll
+          for (int w2 = 1; w2 < kWarps; ++w2) s += s_red[w2][tid];
+          s_acc[tid] = s;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          double dxi[6];
+          bool okf = !s_fail1;
+          for (int i = 0; i < kAcc && okf; ++i) okf = isfinite(s_acc[i]);
+          if (!okf || !solve6(s_acc, dxi)) {
+            s_fail1 = 1;
+          } else {
+            double np[7];
+            se3_oplus(dxi, s_pose, np);
+            s_old = s_new;
+            for (int i = 0; i < 6; ++i) s_dxi[i] = dxi[i];
+            for (int i = 0; i < 7; ++i) s_pose[i] = np[i];
+            quat_to_rot(np, s_new.R);
+            for (int i = 0; i < 9; ++i) s_new.Rf[i] = (float)s_new.R[i];
+            for (int i = 0; i < 3; ++i) s_new.t[i] = np[4 + i];
+          }
+        }
+        __syncthreads();
+        if (s_fail1) break;  // uniform
+      }
+    }
+    __syncthreads();
+    const bool fail = s_fail1 || s_fail2;
+    __syncthreads();
+    if (fail && tid == 0) {  // unsolved frame: back to the normalised input pose
+      double q[7];
+      for (int i = 0; i < 7; ++i) q[i] = a.pose0[(size_t)f * 7 + i];
+      quat_normalize(q);
+      for (int i = 0; i < 7; ++i) s_pose[i] = q[i];
+      quat_to_rot(q, s_new.R);
+    }
+    __syncthreads();
+    if (tid < 7) a.pose_out[(size_t)f * 7 + tid] = s_pose[tid];
+    if (tid == 0) a.status[f] = fail ? GMMLOC_FRAME_NUMERIC : 0;
+    if (a.pts_out != nullptr) {
+      float* po = a.pts_out + (size_t)f * N * 3;
+      for (int i = tid; i < N * 3; i += kThreads) po[i] = fail ? pts[i] : (float)xs[i];
+    }
+    if (a.outlier != nullptr) {
+      // post-check at the final estimate in fp64: chi2 > 5.991 / 7.815 or non-positive depth (localization_opt.cpp:857-881)
+      double R[9], t[3];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = s_new.R[i];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) t[i] = s_pose[4 + i];
+      uint8_t* out = a.outlier + (size_t)f * N;
+      for (int i = tid; i < N; i += kThreads) {
+        Vec3 xw;
+        if (fail) xw = {(double)pts[i * 3], (double)pts[i * 3 + 1], (double)pts[i * 3 + 2]};
+        else xw = {xs[i * 3], xs[i * 3 + 1], xs[i * 3 + 2]};
+        Vec3 pc = rot(R, xw);
+        pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
+        const bool stereo = fl[i] & F_STEREO;
+        const double invz = 1.0 / pc.z;
+        const double u = pc.x * invz * P.fx + P.cx, v = pc.y * invz * P.fy + P.cy;
+        const double e0 = (double)obs[i * 3] - u, e1 = (double)obs[i * 3 + 1] - v;
+        double e2 = 0.0;
+        if (stereo) e2 = (double)obs[i * 3 + 2] - (u - P.bf * invz);
+        const double chi = (double)P.s2inv[oct[i] & 7] * (e0 * e0 + e1 * e1 + e2 * e2);
+        const double th = stereo ? P.chi2_stereo : P.chi2_mono;
+        out[i] = (chi > th || !(pc.z > 0.0)) ? 1 : 0;
+      }
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_next_frame, cudaStream_t stream) {
+  size_t smem = 0;
+  cudaError_t e;
+  if (a.xws == nullptr) {
+    smem = (size_t)a.N * 25 + 16;
+    if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)) != cudaSuccess)
+      return e;
+  }
+  static int ctas_per_sm = 0;  // resident CTAs per SM for the largest shared-memory footprint seen (benign race)
+  int per_sm = 0;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel, kThreads, smem)) != cudaSuccess) return e;
+  if (per_sm < 1) per_sm = 1;
+  ctas_per_sm = per_sm;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::min(a.B, sms * ctas_per_sm);
+  if ((e = cudaMemsetAsync(d_next_frame, 0, sizeof(int), stream)) != cudaSuccess) return e;
+  frame_gn_mixed_kernel<<<grid, kThreads, smem, stream>>>(a, gn_tab, d_next_frame);
+  return cudaGetLastError();
+}
+
+}  // namespace gmmloc

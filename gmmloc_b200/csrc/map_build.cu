@@ -198,6 +198,16 @@ __global__ void __launch_bounds__(128) map_build_kernel(MapDev m, double deg_eps
   for (int i = 0; i < 3; ++i) m.scale[(size_t)k * 3 + i] = ev[i];
   m.det[k] = det;
   m.is_deg[k] = ev[0] < deg_eps;                // gaussian.cpp:44
+  if (m.gn_tab) {
+    float* gt = m.gn_tab + (size_t)k * 8;
+    if (ev[0] < deg_eps) {
+      gt[0] = (float)ax[0]; gt[1] = (float)ax[3]; gt[2] = (float)ax[6];
+      gt[3] = gt[4] = gt[5] = 0.f;
+    } else {
+      gt[0] = (float)ci[0]; gt[1] = (float)ci[1]; gt[2] = (float)ci[2]; gt[3] = (float)ci[4]; gt[4] = (float)ci[5]; gt[5] = (float)ci[8];
+    }
+    gt[6] = gt[7] = 0.f;
+  }
   m.is_sal[k] = (ev[1] > 0.2 && ev[2] > 0.2);   // gaussian.cpp:50-55
   if (!ok) {
     atomicOr(err_flag, 1);

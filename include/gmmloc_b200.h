@@ -157,6 +157,13 @@ enum { GMMLOC_ASSOC_AUTO = 0, GMMLOC_ASSOC_FFMA2 = 1, GMMLOC_ASSOC_TENSOR = 2, G
 GMMLOC_API gmmloc_status_t gmmloc_ctx_set_assoc_kernel(gmmloc_ctx_t* ctx, int kind);
 /* kernel the last association on ctx ran: 0 FFMA2 scan, 1 tensor-core pruning scan, 2 grid-indexed scan */
 GMMLOC_API int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx);
+/* Arithmetic of the per-frame Gauss-Newton kernel behind gmmloc_frames_solve (Localization::jointOptimization with a
+ * single free pose, localization_opt.cpp:456-925):
+ *   GMMLOC_GN_MIXED (default)  state, residuals and the 6x6 reduced system in fp64, Jacobian / Hessian-model algebra
+ *                              in fp32 — same fixed point (poses agree with the fp64 solve to ~1e-9), ~3x faster;
+ *   GMMLOC_GN_FP64             everything in fp64. */
+enum { GMMLOC_GN_FP64 = 0, GMMLOC_GN_MIXED = 1 };
+GMMLOC_API gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int precision);
 
 /* page-locked host memory for the host entry points (pageable buffers also work, via staging) */
 GMMLOC_API gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out);

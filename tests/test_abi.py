@@ -53,7 +53,7 @@ def test_struct_layouts_match_the_header():
     from gmmloc_b200 import capi
     assert ctypes.sizeof(capi.Camera) == 48
     assert ctypes.sizeof(capi.Params) == 72
-    assert ctypes.sizeof(capi.Stats) == 24
+    assert ctypes.sizeof(capi.Stats) == 32
 
 
 def test_argument_validation_needs_no_device():

@@ -584,3 +584,41 @@ def test_grid_scan_exact_ties_and_frames(gpu, oracle):
     st = ctx.stats()
     assert np.array_equal(a0, a1)
     assert st["flagged_brute"] < 0.01 * st["points"], st
+
+
+# ---------------------------------------------------------------- frame GN: mixed-precision default vs the all-fp64 kernel
+@pytest.mark.parametrize("case", ["c2", "c5", "v1"])
+def test_frames_solve_fp64_kernel_and_mixed_kernel_agree(gpu, oracle, golden_maps, gt_v1_03, case):
+    """The default frame-GN kernel keeps state / residuals in fp64 and does the Jacobian algebra in fp32; the all-fp64
+    kernel stays selectable.  Both must meet the oracle tolerance; against each other they agree far tighter."""
+    g, ctx = gpu
+    kw = {}
+    if case == "c2":
+        mean, cov = synth.make_map(10000, 0.5)
+        fr = synth.make_frames(mean, cov, 6, 2000, seed=31)
+    elif case == "c5":
+        mean, cov = synth.make_map(20000, 0.95, seed=4)
+        fr = synth.make_frames(mean, cov, 3, 1500, seed=32, mono_frac=0.3)
+        kw = dict(robust=1)
+    else:
+        mean, cov = golden_maps["v1"]["mean"], golden_maps["v1"]["cov"]
+        idx = np.arange(5, len(gt_v1_03), 401)
+        fr = synth.make_frames(mean, cov, len(idx), 1200, seed=33, poses_wc=gt_v1_03[idx, 1:8])
+    m = g.GMM(mean, cov)
+    prm = g.default_params(**kw)
+    try:
+        ctx.set_gn_precision(g.capi.GN_FP64)
+        o64, _, _ = _check_frames(g, ctx, oracle, mean, cov, fr, **kw)
+        ctx.set_gn_precision(g.capi.GN_MIXED)
+        omx = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=prm)
+    finally:
+        ctx.set_gn_precision(g.capi.GN_MIXED)
+    worst = (0.0, 0.0)
+    for f in range(len(fr["pose0"])):
+        ang, dt = _pose_err(omx["pose"][f], o64["pose"][f])
+        worst = (max(worst[0], ang), max(worst[1], dt))
+    assert worst[0] < 1e-6 and worst[1] < 1e-5, worst
+    assert np.array_equal(omx["status"], o64["status"]) and np.array_equal(omx["assign"], o64["assign"])
+    np.testing.assert_allclose(omx["pts"], o64["pts"], atol=1e-5)
+    assert int((omx["outlier"] != o64["outlier"]).sum()) == 0
+    print(f"mixed vs fp64 frame GN ({case}): {worst[0]:.2e} rad, {worst[1]:.2e} m")
