@@ -38,6 +38,7 @@ namespace {
 constexpr int kThreads = GMMLOC_GNM_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kAcc = 27;
+constexpr double kFarZ = 6.0;  // metres; cond(G) ~ (z fx / bf)^2 ~ 3e3 at the shipped camera (v1.yaml:5-17)
 
 enum : uint8_t { F_STEREO = 1, F_STR = 2, F_FREE = 4, F_DEG = 8 };
 
@@ -207,7 +208,7 @@ __device__ __forceinline__ void accumulate_posef(float* acc, const V3f& pc, cons
 }
 
 __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
-                                                                                   int* __restrict__ next_frame) {
+                                                                                   int* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[kWarps][kAcc];
   __shared__ double s_acc[kAcc];
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
   // persistent CTAs: frames are handed out through a global counter (no tail wave)
   for (;;) {
     __syncthreads();
-    if (tid == 0) s_frame = atomicAdd(next_frame, 1);
+    if (tid == 0) s_frame = atomicAdd(counters, 1);
     __syncthreads();
     const int f = s_frame;
     if (f >= a.B) break;
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
     const double twc1 = -(s_new.R[1] * s_pose[4] + s_new.R[4] * s_pose[5] + s_new.R[7] * s_pose[6]);
     const double twc2 = -(s_new.R[2] * s_pose[4] + s_new.R[5] * s_pose[5] + s_new.R[8] * s_pose[6]);
     // ---- landmarks to fp64; structure-edge gates fixed at iteration 0, in fp64 exactly as frame_gn_kernel ----
+    bool need64 = false;
     for (int i = tid; i < N; i += kThreads) {
       const double x0 = (double)pts[i * 3], x1 = (double)pts[i * 3 + 1], x2 = (double)pts[i * 3 + 2];
       xs[i * 3] = x0;
@@ -291,8 +293,18 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
       }
       if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
       fl[i] = b;
+      // Point blocks the fp32 Hessian model cannot represent: a free MONOCULAR point (G has rank 2, Hll gets its third
+      // direction from the structure edge alone: cond ~1e5) and free points beyond kFarZ (stereo depth information
+      // ~ (bf / z^2)^2 against (fx / z)^2: cond ~ (z fx / bf)^2).  A frame that has one is solved by the fp64 kernel.
+      if (b & F_FREE) {
+        const double pz = s_new.R[6] * x0 + s_new.R[7] * x1 + s_new.R[8] * x2 + s_new.t[2];
+        if (!(b & F_STEREO) || !(pz < kFarZ)) need64 = true;
+      }
     }
-    __syncthreads();
+    if (__syncthreads_or(need64 ? 1 : 0)) {
+      if (tid == 0) a.frame_list[atomicAdd(counters + 1, 1)] = f;
+      continue;
+    }
 
     const int iters = P.gn_iters;
     const int sweeps = (iters > 0) ? iters + 1 : 0;
@@ -470,7 +482,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
 
 }  // namespace
 
-cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_next_frame, cudaStream_t stream) {
+cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, cudaStream_t stream) {
   size_t smem = 0;
   cudaError_t e;
   if (a.xws == nullptr) {
@@ -487,8 +499,8 @@ cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(a.B, sms * ctas_per_sm);
-  if ((e = cudaMemsetAsync(d_next_frame, 0, sizeof(int), stream)) != cudaSuccess) return e;
-  frame_gn_mixed_kernel<<<grid, kThreads, smem, stream>>>(a, gn_tab, d_next_frame);
+  if ((e = cudaMemsetAsync(d_counters, 0, 2 * sizeof(int), stream)) != cudaSuccess) return e;
+  frame_gn_mixed_kernel<<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters);
   return cudaGetLastError();
 }
 
