@@ -747,15 +747,9 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
     return -1;
   }();
   const int gn_prec = gn_forced >= 0 ? gn_forced : ctx->gn_precision;
-  if (gn_prec == GMMLOC_GN_MIXED && map->d.gn_tab != nullptr) {
-    // mixed-precision kernel first; the frames it routes away (ill-conditioned point blocks) go to the fp64 kernel
-    CU(ctx->L().next_frame.reserve(2 * sizeof(int) + sizeof(int32_t) * (size_t)B));
-    int* counters = ctx->L().next_frame.as<int>();
-    a.frame_list = counters + 2;
-    a.frame_count = counters + 1;
-    CU(launch_frame_gn_mixed(a, map->d.gn_tab, counters, ctx->L().stream));
-    CU(launch_frame_gn(a, ctx->L().stream));
-    ctx->stats.kernel_launches += 1;
+  if (gn_prec == GMMLOC_GN_MIXED && map->d.gn_tab != nullptr && (size_t)N <= frame_gn_mixed_limit_points()) {
+    CU(ctx->L().next_frame.reserve(sizeof(int)));
+    CU(launch_frame_gn_mixed(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().stream));
   } else {
     CU(launch_frame_gn(a, ctx->L().stream));
   }
@@ -806,7 +800,7 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     const size_t mc = (size_t)chunk * N;
     CU(ln.flag_idx.reserve(sizeof(int32_t) * 2 * mc));
     CU(ln.flag_thr.reserve(sizeof(float) * 2 * mc));
-    CU(ln.next_frame.reserve(2 * sizeof(int) + sizeof(int32_t) * (size_t)chunk));
+    CU(ln.next_frame.reserve(sizeof(int)));
     if ((size_t)N > frame_gn_smem_limit_points()) {
       CU(ln.xws.reserve(24 * mc));
       CU(ln.fws.reserve(mc));

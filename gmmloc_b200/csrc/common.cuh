@@ -122,17 +122,12 @@ struct FrameArgs {
   int32_t* status;          // B
   double* xws;              // B x N x 3 fp64 workspace when a frame does not fit in shared memory, else null
   uint8_t* fws;             // B x N flag workspace (same condition)
-  // frame routing between the mixed-precision and the fp64 kernel: the mixed kernel appends the frames it must not
-  // solve (ill-conditioned point blocks) to frame_list / frame_count; the fp64 kernel, given the list, solves only those
-  int32_t* frame_list = nullptr;
-  int* frame_count = nullptr;
 };
 cudaError_t launch_frame_gn(const FrameArgs& a, cudaStream_t stream);
 // mixed-precision twin (frame_gn_mixed.cu): fp64 state / residuals, fp32 Jacobian algebra; persistent CTAs fetch frames
 // through *d_next_frame (zeroed by the launcher on `stream`)
-// d_counters: [0] frame fetch counter, [1] number of frames routed to the fp64 kernel (both zeroed by the launcher);
-// a.frame_list must hold a.B entries.  Follow with launch_frame_gn(a with frame_list / frame_count set).
-cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, cudaStream_t stream);
+cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_next_frame, cudaStream_t stream);
+size_t frame_gn_mixed_limit_points();  // largest N the mixed kernel takes (class-sorted frame state in shared memory)
 size_t frame_gn_smem_limit_points();  // largest N whose per-frame state stays in shared memory
 
 struct PoseLmArgs {

@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "gn_common.cuh"
+#include "frame_gn_point.cuh"
 
 namespace gmmloc {
 
@@ -39,8 +40,20 @@ constexpr int kThreads = GMMLOC_GNM_THREADS;
 constexpr int kWarps = kThreads / 32;
 constexpr int kAcc = 27;
 constexpr double kFarZ = 6.0;  // metres; cond(G) ~ (z fx / bf)^2 ~ 3e3 at the shipped camera (v1.yaml:5-17)
+// Point classes (bits 4..6 of the per-point flag byte).  The points of a frame are stably sorted by class when the
+// frame is loaded, so that a warp runs ONE code path per sweep (the unsorted fp64 kernel executes with ~25 of 32
+// lanes active) and the rare ill-conditioned blocks cost a few warp-iterations per sweep instead of stalling every warp.
+enum : int {
+  C_OFF = 0,    // takes no part (a held point when the pose is fixed)
+  C_FIXED = 1,  // held point: contributes G, h to the pose system
+  C_PLAIN = 2,  // free stereo point without structure edge: closed-form update, contributes exactly nothing to the pose
+  C_STR = 3,    // free stereo point with structure edge: update + Schur contribution, fp32 Hessian model
+  C_F64 = 4,    // free point whose block the fp32 model cannot represent (monocular: G has rank 2; beyond kFarZ): fp64
+  C_COUNT = 5
+};
+constexpr int kMaxChunks = 18;                        // N <= kMaxChunks * kThreads
+constexpr int kBytesPerPoint = 24 + 12 + 4 + 2 + 1 + 1 + 1;  // xs, obs, asg, perm, oct, flags, tmp
 
-enum : uint8_t { F_STEREO = 1, F_STR = 2, F_FREE = 4, F_DEG = 8 };
 
 struct V3f {
   float x, y, z;
@@ -207,6 +220,31 @@ __device__ __forceinline__ void accumulate_posef(float* acc, const V3f& pc, cons
   acc[26] += v.z;
 }
 
+
+// fp64 treatment of one ill-conditioned point (class C_F64): the update and the Schur terms of frame_gn_kernel.
+// Deliberately not inlined: it runs for a few warp-iterations per sweep and must not raise the register count of
+// the fp32 path.
+__device__ __noinline__ void point_fp64(const FrameArgs& a, const PoseBoth& oldp, const PoseBoth& newp, const double* dxi,
+                                        uint8_t b, int k, bool upd, bool accp, const float* ob, double w, double* x, V3f& pcf,
+                                        S3f& Mf, V3f& vf, int& bad) {
+  StrConst sc;
+  if (b & F_STR) load_structure(a, k, b, sc);
+  Vec3 xw = {x[0], x[1], x[2]};
+  if (upd) {
+    const Vec3 om = {dxi[0], dxi[1], dxi[2]}, up = {dxi[3], dxi[4], dxi[5]};
+    if (!point_update(a, oldp.R, oldp.t, sc, b, om, up, ob, w, xw)) bad |= 2;
+    x[0] = xw.x; x[1] = xw.y; x[2] = xw.z;
+  }
+  if (accp) {
+    Vec3 pc, v;
+    Sym3 M;
+    if (!pose_terms(a, newp.R, newp.t, sc, b, xw, ob, w, pc, M, v)) bad |= 1;
+    pcf = {(float)pc.x, (float)pc.y, (float)pc.z};
+    Mf = {(float)M.xx, (float)M.xy, (float)M.xz, (float)M.yy, (float)M.yz, (float)M.zz};
+    vf = {(float)v.x, (float)v.y, (float)v.z};
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
                                                                                    int* __restrict__ counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -215,6 +253,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
   __shared__ double s_pose[7], s_dxi[6];
   __shared__ PoseBoth s_new, s_old;  // linearisation points: state sw (accumulate) and state sw-1 (update)
   __shared__ int s_fail1, s_fail2, s_frame;
+  __shared__ int s_cnt[C_COUNT * kMaxChunks * kWarps];  // class histogram per (class, chunk, warp) -> exclusive offsets
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
@@ -225,6 +264,16 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
   C.fx = (float)P.fx; C.fy = (float)P.fy; C.bf = (float)P.bf; C.lam = (float)P.ba_lambda2;
   C.d_mono = (float)P.delta_mono; C.d_stereo = (float)P.delta_stereo; C.robust = P.robust;
   const double view_cos_thresh = cos(78.0 * 3.14159265358979323846 / 180.0);  // gaussian_mixture.cpp:284
+  const int nchunks = (N + kThreads - 1) / kThreads;
+
+  // per-frame state, class-sorted position j: landmark (fp64), observation, component id, original index, octave, flags
+  double* xs = reinterpret_cast<double*>(smem_raw);
+  float* so = reinterpret_cast<float*>(xs + (size_t)N * 3);
+  int32_t* sk = reinterpret_cast<int32_t*>(so + (size_t)N * 3);
+  uint16_t* perm = reinterpret_cast<uint16_t*>(sk + N);
+  uint8_t* soct = reinterpret_cast<uint8_t*>(perm + N);
+  uint8_t* fl = soct + N;
+  uint8_t* tmp = fl + N;  // flags by ORIGINAL index while the frame is being sorted
 
   // persistent CTAs: frames are handed out through a global counter (no tail wave)
   for (;;) {
@@ -234,15 +283,6 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
     const int f = s_frame;
     if (f >= a.B) break;
 
-    double* xs;
-    uint8_t* fl;
-    if (a.xws != nullptr) {
-      xs = a.xws + (size_t)f * N * 3;
-      fl = a.fws + (size_t)f * N;
-    } else {
-      xs = reinterpret_cast<double*>(smem_raw);
-      fl = reinterpret_cast<uint8_t*>(xs + (size_t)N * 3);
-    }
     const float* pts = a.pts_w + (size_t)f * N * 3;
     const float* obs = a.obs + (size_t)f * N * 3;
     const uint8_t* oct = a.octave + (size_t)f * N;
@@ -268,43 +308,96 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
     const double twc0 = -(s_new.R[0] * s_pose[4] + s_new.R[3] * s_pose[5] + s_new.R[6] * s_pose[6]);
     const double twc1 = -(s_new.R[1] * s_pose[4] + s_new.R[4] * s_pose[5] + s_new.R[7] * s_pose[6]);
     const double twc2 = -(s_new.R[2] * s_pose[4] + s_new.R[5] * s_pose[5] + s_new.R[8] * s_pose[6]);
-    // ---- landmarks to fp64; structure-edge gates fixed at iteration 0, in fp64 exactly as frame_gn_kernel ----
-    bool need64 = false;
-    for (int i = tid; i < N; i += kThreads) {
-      const double x0 = (double)pts[i * 3], x1 = (double)pts[i * 3 + 1], x2 = (double)pts[i * 3 + 2];
-      xs[i * 3] = x0;
-      xs[i * 3 + 1] = x1;
-      xs[i * 3 + 2] = x2;
-      uint8_t b = (obs[i * 3 + 2] >= 0.0f) ? F_STEREO : 0;
-      const int k = asg[i];
-      if (k >= 0 && pts_free) {
-        if (a.is_deg[k]) {
-          b |= F_DEG;
-          const double* ax = a.axis + (size_t)k * 9;
-          const double* mu = a.mean + (size_t)k * 3;
-          const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
-          if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;
-          const double p0 = mu[0] - twc0, p1 = mu[1] - twc1, p2 = mu[2] - twc2;
-          const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
-          if (view_cos < view_cos_thresh) b &= ~F_STR;
+    // ---- pass A: flags and class of every point (structure-edge gates fixed at iteration 0, in fp64 exactly as
+    // frame_gn_kernel), class histogram per (chunk, warp) ----
+    for (int c = 0; c < nchunks; ++c) {
+      const int i = c * kThreads + tid;
+      int cls = -1;
+      if (i < N) {
+        const double x0 = (double)pts[i * 3], x1 = (double)pts[i * 3 + 1], x2 = (double)pts[i * 3 + 2];
+        uint8_t b = (obs[i * 3 + 2] >= 0.0f) ? F_STEREO : 0;
+        const int k = asg[i];
+        if (k >= 0 && pts_free) {
+          if (a.is_deg[k]) {
+            b |= F_DEG;
+            const double* ax = a.axis + (size_t)k * 9;
+            const double* mu = a.mean + (size_t)k * 3;
+            const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
+            if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;
+            const double p0 = mu[0] - twc0, p1 = mu[1] - twc1, p2 = mu[2] - twc2;
+            const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
+            if (view_cos < view_cos_thresh) b &= ~F_STR;
+          } else {
+            if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;
+          }
+        }
+        if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
+        if (!(b & F_FREE)) {
+          cls = pose_free ? C_FIXED : C_OFF;
         } else {
-          if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;
+          const double pz = s_new.R[6] * x0 + s_new.R[7] * x1 + s_new.R[8] * x2 + s_new.t[2];
+          if (!(b & F_STEREO) || !(pz < kFarZ)) cls = C_F64;
+          else cls = (b & F_STR) ? C_STR : C_PLAIN;
+        }
+        tmp[i] = (uint8_t)(b | (cls << 4));
+      }
+#pragma unroll
+      for (int q = 0; q < C_COUNT; ++q) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == q);
+        if (lane == 0) s_cnt[(q * kMaxChunks + c) * kWarps + warp] = __popc(m);
+      }
+    }
+    __syncthreads();
+    // exclusive scan of the histogram in (class, chunk, warp) order = stable counting sort offsets (one warp)
+    if (warp == 0) {
+      int run = 0;
+      for (int q = 0; q < C_COUNT; ++q) {
+        const int n = nchunks * kWarps;
+        for (int b0 = 0; b0 < n; b0 += 32) {
+          const int e = b0 + lane;
+          const int idx = q * kMaxChunks * kWarps + e;
+          const int v = (e < n) ? s_cnt[idx] : 0;
+          int inc = v;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+          }
+          if (e < n) s_cnt[idx] = run + inc - v;
+          run += __shfl_sync(0xffffffffu, inc, 31);
         }
       }
-      if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
-      fl[i] = b;
-      // Point blocks the fp32 Hessian model cannot represent: a free MONOCULAR point (G has rank 2, Hll gets its third
-      // direction from the structure edge alone: cond ~1e5) and free points beyond kFarZ (stereo depth information
-      // ~ (bf / z^2)^2 against (fx / z)^2: cond ~ (z fx / bf)^2).  A frame that has one is solved by the fp64 kernel.
-      if (b & F_FREE) {
-        const double pz = s_new.R[6] * x0 + s_new.R[7] * x1 + s_new.R[8] * x2 + s_new.t[2];
-        if (!(b & F_STEREO) || !(pz < kFarZ)) need64 = true;
+    }
+    __syncthreads();
+    // ---- pass B: scatter the frame into class-sorted shared memory ----
+    for (int c = 0; c < nchunks; ++c) {
+      const int i = c * kThreads + tid;
+      int cls = -1;
+      uint8_t b = 0;
+      if (i < N) {
+        b = tmp[i];
+        cls = b >> 4;
+      }
+      int j = -1;
+#pragma unroll
+      for (int q = 0; q < C_COUNT; ++q) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == q);
+        if (cls == q) j = s_cnt[(q * kMaxChunks + c) * kWarps + warp] + __popc(m & ((1u << lane) - 1u));
+      }
+      if (i < N) {
+        xs[j * 3] = (double)pts[i * 3];
+        xs[j * 3 + 1] = (double)pts[i * 3 + 1];
+        xs[j * 3 + 2] = (double)pts[i * 3 + 2];
+        so[j * 3] = obs[i * 3];
+        so[j * 3 + 1] = obs[i * 3 + 1];
+        so[j * 3 + 2] = obs[i * 3 + 2];
+        sk[j] = asg[i];
+        perm[j] = (uint16_t)i;
+        soct[j] = oct[i];
+        fl[j] = b;
       }
     }
-    if (__syncthreads_or(need64 ? 1 : 0)) {
-      if (tid == 0) a.frame_list[atomicAdd(counters + 1, 1)] = f;
-      continue;
-    }
+    __syncthreads();
 
     const int iters = P.gn_iters;
     const int sweeps = (iters > 0) ? iters + 1 : 0;
@@ -316,35 +409,60 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
       float acc[kAcc];
 #pragma unroll
       for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
-      bool bad1 = false, bad2 = false;
-      for (int i = tid; i < N; i += kThreads) {
-        const uint8_t b = fl[i];
-        const bool free_pt = b & F_FREE, str = b & F_STR, stereo = b & F_STEREO;
-        const bool upd = do_update && free_pt;
-        const bool accp = do_acc && !(free_pt && !str);  // a free point without a structure edge contributes exactly zero
+      int bad = 0;  // bit 0: singular block while accumulating, bit 1: while updating
+      for (int j = tid; j < N; j += kThreads) {
+        const uint8_t b = fl[j];
+        const int cls = b >> 4;
+        const bool stereo = b & F_STEREO;
+        const bool upd = do_update && cls >= C_PLAIN;
+        const bool accp = do_acc && (cls == C_FIXED || cls >= C_STR) && !(cls == C_F64 && !(b & F_STR));
         if (!upd && !accp) continue;
-        double x0 = xs[i * 3], x1 = xs[i * 3 + 1], x2 = xs[i * 3 + 2];
-        const float ob[3] = {obs[i * 3], obs[i * 3 + 1], obs[i * 3 + 2]};
-        const float w = P.s2inv[oct[i] & 7];
-        StrF sc;
-        if (str) load_structure(a, gn_tab, asg[i], sc);
-        if (upd) {
-          const Lin L = linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, stereo);
-          S3f G;
-          V3f h;
-          reprojf(C, L, stereo, w, G, h);
-          S3f D = G;
-          V3f bl = h;
-          if (str) {
-            S3f S;
-            V3f s;
-            structuref(C, s_old.Rf, sc, b, x0, x1, x2, S, s);
-            D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
-            bl = {h.x + s.x, h.y + s.y, h.z + s.z};
+        double x0 = xs[j * 3], x1 = xs[j * 3 + 1], x2 = xs[j * 3 + 2];
+        const float ob[3] = {so[j * 3], so[j * 3 + 1], so[j * 3 + 2]};
+        const float w = P.s2inv[soct[j] & 7];
+        if (cls == C_F64) {
+          double x[3] = {x0, x1, x2};
+          V3f pcf, vf;
+          S3f Mf;
+          point_fp64(a, s_old, s_new, s_dxi, b & 15, sk[j], upd, accp, ob, (double)w, x, pcf, Mf, vf, bad);
+          if (upd) {
+            xs[j * 3] = x[0];
+            xs[j * 3 + 1] = x[1];
+            xs[j * 3 + 2] = x[2];
           }
+          if (accp) accumulate_posef(acc, pcf, Mf, vf);
+          continue;
+        }
+        if (cls == C_PLAIN) {
+          // free stereo point without structure edge: D = G = w P^T P with P square, so
+          // dc = G^-1 (h - G A dxi) = P^-1 e - A dxi in closed form (rows u and u_r of P differ only in the z column)
+          const Lin L = linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, true);
+          const float a_ = C.fx * L.iz, b_ = C.fy * L.iz;
+          const float c0 = -a_ * L.pc.x * L.iz, c1 = -b_ * L.pc.y * L.iz;
+          const float dz = (L.e.z - L.e.x) / (C.bf * L.iz * L.iz);
+          const float dx = (L.e.x - c0 * dz) / a_;
+          const float dy = (L.e.y - c1 * dz) / b_;
+          const V3f ad = {om.y * L.pc.z - om.z * L.pc.y + up.x, om.z * L.pc.x - om.x * L.pc.z + up.y,
+                          om.x * L.pc.y - om.y * L.pc.x + up.z};
+          const V3f dw = rotf_t(s_old.Rf, {dx - ad.x, dy - ad.y, dz - ad.z});
+          if (!(isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad |= 2;
+          xs[j * 3] = x0 + (double)dw.x;
+          xs[j * 3 + 1] = x1 + (double)dw.y;
+          xs[j * 3 + 2] = x2 + (double)dw.z;
+          continue;
+        }
+        StrF sc;
+        if (cls == C_STR) load_structure(a, gn_tab, sk[j], sc);
+        if (upd) {  // C_STR only
+          const Lin L = linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, stereo);
+          S3f G, S;
+          V3f h, s;
+          reprojf(C, L, stereo, w, G, h);
+          structuref(C, s_old.Rf, sc, b, x0, x1, x2, S, s);
+          const S3f D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
+          const V3f bl = {h.x + s.x, h.y + s.y, h.z + s.z};
           bool ok;
           const S3f Di = inv_symf(D, ok);
-          // A dxi = omega x pc + upsilon
           const V3f ad = {om.y * L.pc.z - om.z * L.pc.y + up.x, om.z * L.pc.x - om.x * L.pc.z + up.y,
                           om.x * L.pc.y - om.y * L.pc.x + up.z};
           const V3f ga = mulf(G, ad);
@@ -353,26 +471,26 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
           x0 += (double)dw.x;
           x1 += (double)dw.y;
           x2 += (double)dw.z;
-          if (!(ok && isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad2 = true;
-          xs[i * 3] = x0;
-          xs[i * 3 + 1] = x1;
-          xs[i * 3 + 2] = x2;
+          if (!(ok && isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad |= 2;
+          xs[j * 3] = x0;
+          xs[j * 3 + 1] = x1;
+          xs[j * 3 + 2] = x2;
         }
-        if (accp) {
+        if (accp) {  // C_FIXED or C_STR
           const Lin L = linearise(P, s_new.R, s_new.t, x0, x1, x2, ob, stereo);
           S3f G;
           V3f h;
           reprojf(C, L, stereo, w, G, h);
           S3f M = G;
           V3f v = h;
-          if (free_pt) {
+          if (cls == C_STR) {
             S3f S;
             V3f s;
             structuref(C, s_new.Rf, sc, b, x0, x1, x2, S, s);
             const S3f D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
             bool ok;
             const S3f Di = inv_symf(D, ok);
-            if (!ok) bad1 = true;
+            if (!ok) bad |= 1;
             const float T00 = G.xx * Di.xx + G.xy * Di.xy + G.xz * Di.xz, T01 = G.xx * Di.xy + G.xy * Di.yy + G.xz * Di.yz,
                         T02 = G.xx * Di.xz + G.xy * Di.yz + G.xz * Di.zz;
             const float T10 = G.xy * Di.xx + G.yy * Di.xy + G.yz * Di.xz, T11 = G.xy * Di.xy + G.yy * Di.yy + G.yz * Di.yz,
@@ -393,8 +511,8 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
           accumulate_posef(acc, L.pc, M, v);
         }
       }
-      if (bad2) s_fail2 = 1;
-      if (bad1) s_fail1 = 1;
+      if (bad & 2) s_fail2 = 1;
+      if (bad & 1) s_fail1 = 1;
       if (do_acc) {
 #pragma unroll
         for (int i = 0; i < kAcc; ++i) {
@@ -448,33 +566,39 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
     __syncthreads();
     if (tid < 7) a.pose_out[(size_t)f * 7 + tid] = s_pose[tid];
     if (tid == 0) a.status[f] = fail ? GMMLOC_FRAME_NUMERIC : 0;
-    if (a.pts_out != nullptr) {
-      float* po = a.pts_out + (size_t)f * N * 3;
-      for (int i = tid; i < N * 3; i += kThreads) po[i] = fail ? pts[i] : (float)xs[i];
-    }
-    if (a.outlier != nullptr) {
-      // post-check at the final estimate in fp64: chi2 > 5.991 / 7.815 or non-positive depth (localization_opt.cpp:857-881)
+    {
+      // outputs in the ORIGINAL point order; outlier post-check at the final estimate in fp64:
+      // chi2 > 5.991 / 7.815 or non-positive depth (localization_opt.cpp:857-881)
       double R[9], t[3];
 #pragma unroll
       for (int i = 0; i < 9; ++i) R[i] = s_new.R[i];
 #pragma unroll
       for (int i = 0; i < 3; ++i) t[i] = s_pose[4 + i];
-      uint8_t* out = a.outlier + (size_t)f * N;
-      for (int i = tid; i < N; i += kThreads) {
+      float* po = a.pts_out ? a.pts_out + (size_t)f * N * 3 : nullptr;
+      uint8_t* out = a.outlier ? a.outlier + (size_t)f * N : nullptr;
+      for (int j = tid; j < N; j += kThreads) {
+        const int i = perm[j];
         Vec3 xw;
         if (fail) xw = {(double)pts[i * 3], (double)pts[i * 3 + 1], (double)pts[i * 3 + 2]};
-        else xw = {xs[i * 3], xs[i * 3 + 1], xs[i * 3 + 2]};
-        Vec3 pc = rot(R, xw);
-        pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
-        const bool stereo = fl[i] & F_STEREO;
-        const double invz = 1.0 / pc.z;
-        const double u = pc.x * invz * P.fx + P.cx, v = pc.y * invz * P.fy + P.cy;
-        const double e0 = (double)obs[i * 3] - u, e1 = (double)obs[i * 3 + 1] - v;
-        double e2 = 0.0;
-        if (stereo) e2 = (double)obs[i * 3 + 2] - (u - P.bf * invz);
-        const double chi = (double)P.s2inv[oct[i] & 7] * (e0 * e0 + e1 * e1 + e2 * e2);
-        const double th = stereo ? P.chi2_stereo : P.chi2_mono;
-        out[i] = (chi > th || !(pc.z > 0.0)) ? 1 : 0;
+        else xw = {xs[j * 3], xs[j * 3 + 1], xs[j * 3 + 2]};
+        if (po != nullptr) {
+          po[i * 3] = fail ? pts[i * 3] : (float)xw.x;
+          po[i * 3 + 1] = fail ? pts[i * 3 + 1] : (float)xw.y;
+          po[i * 3 + 2] = fail ? pts[i * 3 + 2] : (float)xw.z;
+        }
+        if (out != nullptr) {
+          Vec3 pc = rot(R, xw);
+          pc.x += t[0]; pc.y += t[1]; pc.z += t[2];
+          const bool stereo = fl[j] & F_STEREO;
+          const double invz = 1.0 / pc.z;
+          const double u = pc.x * invz * P.fx + P.cx, v = pc.y * invz * P.fy + P.cy;
+          const double e0 = (double)so[j * 3] - u, e1 = (double)so[j * 3 + 1] - v;
+          double e2 = 0.0;
+          if (stereo) e2 = (double)so[j * 3 + 2] - (u - P.bf * invz);
+          const double chi = (double)P.s2inv[soct[j] & 7] * (e0 * e0 + e1 * e1 + e2 * e2);
+          const double th = stereo ? P.chi2_stereo : P.chi2_mono;
+          out[i] = (chi > th || !(pc.z > 0.0)) ? 1 : 0;
+        }
       }
     }
   }
@@ -482,24 +606,24 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
 
 }  // namespace
 
+size_t frame_gn_mixed_limit_points() {
+  const size_t by_smem = (size_t)(200 * 1024) / kBytesPerPoint;
+  return std::min(by_smem, (size_t)kMaxChunks * kThreads);
+}
+
 cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, cudaStream_t stream) {
-  size_t smem = 0;
   cudaError_t e;
-  if (a.xws == nullptr) {
-    smem = (size_t)a.N * 25 + 16;
-    if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)) != cudaSuccess)
-      return e;
-  }
-  static int ctas_per_sm = 0;  // resident CTAs per SM for the largest shared-memory footprint seen (benign race)
+  const size_t smem = (size_t)a.N * kBytesPerPoint + 16;
+  if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)) != cudaSuccess)
+    return e;
   int per_sm = 0;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel, kThreads, smem)) != cudaSuccess) return e;
   if (per_sm < 1) per_sm = 1;
-  ctas_per_sm = per_sm;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = std::min(a.B, sms * ctas_per_sm);
-  if ((e = cudaMemsetAsync(d_counters, 0, 2 * sizeof(int), stream)) != cudaSuccess) return e;
+  const int grid = std::min(a.B, sms * per_sm);
+  if ((e = cudaMemsetAsync(d_counters, 0, sizeof(int), stream)) != cudaSuccess) return e;
   frame_gn_mixed_kernel<<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters);
   return cudaGetLastError();
 }
