@@ -44,12 +44,17 @@ constexpr double kFarZ = 6.0;  // metres; cond(G) ~ (z fx / bf)^2 ~ 3e3 at the s
 // frame is loaded, so that a warp runs ONE code path per sweep (the unsorted fp64 kernel executes with ~25 of 32
 // lanes active) and the rare ill-conditioned blocks cost a few warp-iterations per sweep instead of stalling every warp.
 enum : int {
-  C_OFF = 0,    // takes no part (a held point when the pose is fixed)
-  C_FIXED = 1,  // held point: contributes G, h to the pose system
-  C_PLAIN = 2,  // free stereo point without structure edge: closed-form update, contributes exactly nothing to the pose
-  C_STR = 3,    // free stereo point with structure edge: update + Schur contribution, fp32 Hessian model
-  C_F64 = 4,    // free point whose block the fp32 model cannot represent (monocular: G has rank 2; beyond kFarZ): fp64
-  C_COUNT = 5
+  C_OFF = 0,     // takes no part (a held point when the pose is fixed)
+  C_FIXED = 1,   // held point: contributes G, h to the pose system
+  C_PLAIN = 2,   // free stereo point without structure edge: three equations, three unknowns — closed-form update,
+                 // contributes exactly nothing to the pose system
+  C_MPLANE = 3,  // free monocular point on a planar component: again three equations (u, v, plane distance) for three
+                 // unknowns — closed-form update, zero Schur contribution.  (As a 3x3 normal-equation block this is
+                 // the ill-conditioned case: G has rank 2 and the third direction comes from the plane alone.)
+  C_STR = 4,     // free stereo point with a structure edge: update + Schur contribution, fp32 Hessian model
+  C_F64 = 5,     // blocks the fp32 model should not be trusted with (monocular point with a full 3-D Gaussian edge,
+                 // any free point beyond kFarZ): fp64 path of frame_gn_kernel
+  C_COUNT = 6
 };
 constexpr int kMaxChunks = 18;                        // N <= kMaxChunks * kThreads
 constexpr int kBytesPerPoint = 24 + 12 + 4 + 2 + 1 + 1 + 1;  // xs, obs, asg, perm, oct, flags, tmp
@@ -336,7 +341,8 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
           cls = pose_free ? C_FIXED : C_OFF;
         } else {
           const double pz = s_new.R[6] * x0 + s_new.R[7] * x1 + s_new.R[8] * x2 + s_new.t[2];
-          if (!(b & F_STEREO) || !(pz < kFarZ)) cls = C_F64;
+          if (!(pz < kFarZ)) cls = C_F64;
+          else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_F64;  // a free monocular point always has F_STR
           else cls = (b & F_STR) ? C_STR : C_PLAIN;
         }
         tmp[i] = (uint8_t)(b | (cls << 4));
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
         const int cls = b >> 4;
         const bool stereo = b & F_STEREO;
         const bool upd = do_update && cls >= C_PLAIN;
-        const bool accp = do_acc && (cls == C_FIXED || cls >= C_STR) && !(cls == C_F64 && !(b & F_STR));
+        const bool accp = do_acc && (cls == C_FIXED || cls == C_STR || (cls == C_F64 && (b & F_STR)));
         if (!upd && !accp) continue;
         double x0 = xs[j * 3], x1 = xs[j * 3 + 1], x2 = xs[j * 3 + 2];
         const float ob[3] = {so[j * 3], so[j * 3 + 1], so[j * 3 + 2]};
@@ -452,7 +458,30 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
           continue;
         }
         StrF sc;
-        if (cls == C_STR) load_structure(a, gn_tab, sk[j], sc);
+        if (cls == C_MPLANE || cls == C_STR) load_structure(a, gn_tab, sk[j], sc);
+        if (cls == C_MPLANE) {
+          // rows u, v of P and the plane normal form a square system:  [P_uv ; nc^T] dc = [e - P_uv A dxi ; -es]
+          // (= D^-1 (h + s - G A dxi) of the general path; weights and the Huber factor cancel row by row)
+          const Lin L = linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, false);
+          const float a_ = C.fx * L.iz, b_ = C.fy * L.iz;
+          const float c0 = -a_ * L.pc.x * L.iz, c1 = -b_ * L.pc.y * L.iz;
+          const V3f d3 = {(float)(x0 - sc.mu[0]), (float)(x1 - sc.mu[1]), (float)(x2 - sc.mu[2])};
+          const float es = sc.c[0] * d3.x + sc.c[1] * d3.y + sc.c[2] * d3.z;
+          const V3f nc = rotf(s_old.Rf, {sc.c[0], sc.c[1], sc.c[2]});
+          const V3f ad = {om.y * L.pc.z - om.z * L.pc.y + up.x, om.z * L.pc.x - om.x * L.pc.z + up.y,
+                          om.x * L.pc.y - om.y * L.pc.x + up.z};
+          const float r0 = L.e.x - (a_ * ad.x + c0 * ad.z), r1 = L.e.y - (b_ * ad.y + c1 * ad.z), r2 = -es;
+          const float ia = 1.0f / a_, ib = 1.0f / b_;
+          const float den = nc.z - nc.x * c0 * ia - nc.y * c1 * ib;  // = (nc . pc) / z: bounded away from 0 by the view-cos cull
+          const float dz = (r2 - nc.x * r0 * ia - nc.y * r1 * ib) / den;
+          const float dx = (r0 - c0 * dz) * ia, dy = (r1 - c1 * dz) * ib;
+          const V3f dw = rotf_t(s_old.Rf, {dx, dy, dz});
+          if (!(isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad |= 2;
+          xs[j * 3] = x0 + (double)dw.x;
+          xs[j * 3 + 1] = x1 + (double)dw.y;
+          xs[j * 3 + 2] = x2 + (double)dw.z;
+          continue;
+        }
         if (upd) {  // C_STR only
           const Lin L = linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, stereo);
           S3f G, S;
@@ -525,28 +554,40 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
       __syncthreads();
       if (s_fail2) break;  // uniform
       if (do_acc) {
-        if (tid < kAcc) {
-          double s = s_red[0][tid];
+        if (warp == 0) {  // fixed-order cross-warp sum, then the 6x6 solve and the SE3 update on lane 0
+          if (lane < kAcc) {
+            double s = s_red[0][lane];
 #pragma unroll
-          for (int w2 = 1; w2 < kWarps; ++w2) s += s_red[w2][tid];
-          s_acc[tid] = s;
-        }
-        __syncthreads();
-        if (tid == 0) {
-          double dxi[6];
-          bool okf = !s_fail1;
-          for (int i = 0; i < kAcc && okf; ++i) okf = isfinite(s_acc[i]);
-          if (!okf || !solve6(s_acc, dxi)) {
-            s_fail1 = 1;
-          } else {
-            double np[7];
-            se3_oplus(dxi, s_pose, np);
-            s_old = s_new;
-            for (int i = 0; i < 6; ++i) s_dxi[i] = dxi[i];
-            for (int i = 0; i < 7; ++i) s_pose[i] = np[i];
-            quat_to_rot(np, s_new.R);
-            for (int i = 0; i < 9; ++i) s_new.Rf[i] = (float)s_new.R[i];
-            for (int i = 0; i < 3; ++i) s_new.t[i] = np[4 + i];
+            for (int w2 = 1; w2 < kWarps; ++w2) s += s_red[w2][lane];
+            s_acc[lane] = s;
+          }
+          __syncwarp();
+          if (lane == 0) {
+            double dxi[6];
+            bool okf = !s_fail1;
+#pragma unroll
+            for (int i = 0; i < kAcc; ++i) okf = okf && isfinite(s_acc[i]);
+            if (!okf || !solve6_ldlt(s_acc, dxi)) {
+              s_fail1 = 1;
+            } else {
+              double np[7];
+#pragma unroll
+              for (int i = 0; i < 9; ++i) {
+                s_old.R[i] = s_new.R[i];
+                s_old.Rf[i] = s_new.Rf[i];
+              }
+#pragma unroll
+              for (int i = 0; i < 3; ++i) s_old.t[i] = s_new.t[i];
+              se3_oplus_fast(dxi, s_pose, np, s_new.R);
+#pragma unroll
+              for (int i = 0; i < 6; ++i) s_dxi[i] = dxi[i];
+#pragma unroll
+              for (int i = 0; i < 7; ++i) s_pose[i] = np[i];
+#pragma unroll
+              for (int i = 0; i < 9; ++i) s_new.Rf[i] = (float)s_new.R[i];
+#pragma unroll
+              for (int i = 0; i < 3; ++i) s_new.t[i] = np[4 + i];
+            }
           }
         }
         __syncthreads();

@@ -228,6 +228,109 @@ __device__ inline bool solve6(const double* acc, double* x) {
   return true;
 }
 
+// ---- latency-optimised twins for the serial section of the mixed-precision frame GN (one thread per frame and
+// iteration; the other warps of the CTA wait for this dependent fp64 chain).  Same mathematics, different rounding:
+// a fully unrolled LDL^T (six reciprocals, no square roots, everything in registers) and an SE3 update that goes
+// straight from the rotation vector to the quaternion (one sincos, reciprocal square roots instead of divisions).
+__device__ __forceinline__ bool solve6_ldlt(const double* acc, double* x) {
+  double A[6][6];  // lower triangle; fully unrolled => registers
+  {
+    int n = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = r; c < 6; ++c) A[c][r] = acc[n++];
+  }
+  double inv[6];
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const double dk = A[k][k];
+    ok = ok && (dk > 0.0) && isfinite(dk);  // same acceptance as the Cholesky pivot test of solve6
+    inv[k] = 1.0 / dk;
+    double col[6], l[6];
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+      col[i] = A[i][k];        // L_ik d_k
+      l[i] = col[i] * inv[k];  // L_ik
+    }
+#pragma unroll
+    for (int i = k + 1; i < 6; ++i) {
+#pragma unroll
+      for (int j = k + 1; j <= i; ++j) A[i][j] -= l[i] * col[j];
+      A[i][k] = l[i];
+    }
+  }
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double t = acc[21 + i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) t -= A[i][j] * y[j];
+    y[i] = t;
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double t = y[i] * inv[i];
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) t -= A[j][i] * x[j];
+    x[i] = t;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) ok = ok && isfinite(x[i]);
+  return ok;
+}
+
+// pose <- exp(xi) * pose (VertexSE3Expmap::oplusImpl; SE3Quat::exp semantics as se3_oplus), R_out = rotation of the result
+__device__ __forceinline__ void se3_oplus_fast(const double* xi, const double* pose, double* out, double* R_out) {
+  const double w0 = xi[0], w1 = xi[1], w2 = xi[2];
+  const double th2 = w0 * w0 + w1 * w1 + w2 * w2;
+  double b, d, k, c2;  // b = (1 - cos t) / t^2, d = (t - sin t) / t^3, k = sin(t/2) / t, c2 = cos(t/2)
+  if (th2 < 1e-10) {
+    b = 0.5; d = 1.0 / 6.0;
+    k = 0.5 - th2 * (1.0 / 48.0);
+    c2 = 1.0 - th2 * 0.125;
+  } else {
+    const double it = rsqrt(th2), theta = th2 * it;
+    double s2;
+    sincos(0.5 * theta, &s2, &c2);
+    const double st = 2.0 * s2 * c2;
+    b = 2.0 * s2 * s2 * (it * it);
+    d = (theta - st) * (it * it * it);
+    k = s2 * it;
+  }
+  // V = I + b Om + d Om^2, t = V * upsilon  (Om^2 v = w (w.v) - |w|^2 v)
+  const double u0 = xi[3], u1 = xi[4], u2 = xi[5];
+  const double wu = w0 * u0 + w1 * u1 + w2 * u2;
+  const double t0 = u0 + b * (w1 * u2 - w2 * u1) + d * (w0 * wu - th2 * u0);
+  const double t1 = u1 + b * (w2 * u0 - w0 * u2) + d * (w1 * wu - th2 * u1);
+  const double t2 = u2 + b * (w0 * u1 - w1 * u0) + d * (w2 * wu - th2 * u2);
+  // rotation of exp(xi) as a unit quaternion (w >= 0 for |theta| < pi)
+  const double ax = w0 * k, ay = w1 * k, az = w2 * k, aw = c2;
+  double Rd[9];
+  {
+    const double qd[4] = {ax, ay, az, aw};
+    quat_to_rot(qd, Rd);
+  }
+  const double* p = pose + 4;
+  const double r0 = Rd[0] * p[0] + Rd[1] * p[1] + Rd[2] * p[2], r1 = Rd[3] * p[0] + Rd[4] * p[1] + Rd[5] * p[2],
+               r2 = Rd[6] * p[0] + Rd[7] * p[1] + Rd[8] * p[2];
+  const double bx = pose[0], by = pose[1], bz = pose[2], bw = pose[3];
+  double q[4];
+  q[3] = aw * bw - ax * bx - ay * by - az * bz;
+  q[0] = aw * bx + ax * bw + ay * bz - az * by;
+  q[1] = aw * by + ay * bw + az * bx - ax * bz;
+  q[2] = aw * bz + az * bw + ax * by - ay * bx;
+  double n = rsqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (q[3] < 0) n = -n;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) out[i] = q[i] * n;
+  out[4] = t0 + r0;
+  out[5] = t1 + r1;
+  out[6] = t2 + r2;
+  quat_to_rot(out, R_out);
+}
+
 
 }  // namespace
 }  // namespace gmmloc
