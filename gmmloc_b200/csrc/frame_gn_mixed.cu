@@ -51,10 +51,14 @@ enum : int {
   C_MPLANE = 3,  // free monocular point on a planar component: again three equations (u, v, plane distance) for three
                  // unknowns — closed-form update, zero Schur contribution.  (As a 3x3 normal-equation block this is
                  // the ill-conditioned case: G has rank 2 and the third direction comes from the plane alone.)
-  C_STR = 4,     // free stereo point with a structure edge: update + Schur contribution, fp32 Hessian model
-  C_F64 = 5,     // blocks the fp32 model should not be trusted with (monocular point with a full 3-D Gaussian edge,
+  C_STRP = 4,    // free stereo point on a planar component: the stereo edge alone determines the point (P is square),
+                 // the plane adds ONE scalar equation, so D = G + lam n n^T is inverted by Sherman-Morrison in closed
+                 // form: with pe = P^-1 e, z = G^-1 n, gamma = n.z, kappa = lam / (1 + lam gamma):
+                 //   M = kappa n n^T,  v = kappa (es + n.pe) n,  dc = u - kappa z (n.u),  u = pe - A dxi - lam es z
+  C_STR = 5,     // free stereo point with a full 3-D Gaussian edge: general 3x3 path, fp32 Hessian model
+  C_F64 = 6,     // blocks the fp32 model should not be trusted with (monocular point with a full 3-D Gaussian edge,
                  // any free point beyond kFarZ): fp64 path of frame_gn_kernel
-  C_COUNT = 6
+  C_COUNT = 7
 };
 constexpr int kMaxChunks = 18;                        // N <= kMaxChunks * kThreads
 constexpr int kBytesPerPoint = 24 + 12 + 4 + 2 + 1 + 1 + 1;  // xs, obs, asg, perm, oct, flags, tmp
@@ -226,6 +230,42 @@ __device__ __forceinline__ void accumulate_posef(float* acc, const V3f& pc, cons
 }
 
 
+// closed-form pieces of a free stereo point on a plane (class C_STRP), all in the camera frame of one linearisation
+struct PlaneLin {
+  V3f pc, nc;   // camera-frame point, plane normal
+  V3f pe;       // P^-1 e: the correction the stereo edge alone asks for
+  V3f z;        // G^-1 nc
+  float kappa;  // lam / (1 + lam nc.z)
+};
+__device__ __forceinline__ PlaneLin plane_lin(const CamF& C, const Lin& L, const V3f& nc, float w) {
+  PlaneLin Q;
+  Q.pc = L.pc;
+  Q.nc = nc;
+  // P = [[a, 0, c0], [0, b, c1], [a, 0, c0 + cz]]  (rows u, v, u_r)
+  const float a_ = C.fx * L.iz, b_ = C.fy * L.iz;
+  const float ia = 1.0f / a_, ib = 1.0f / b_;
+  const float c0 = -a_ * L.pc.x * L.iz, c1 = -b_ * L.pc.y * L.iz;
+  const float icz = 1.0f / (C.bf * L.iz * L.iz);
+  if (C.robust) {  // Huber weight of the reprojection edge (cancels in pe, scales G)
+    const float chi = w * (L.e.x * L.e.x + L.e.y * L.e.y + L.e.z * L.e.z);
+    if (chi > C.d_stereo * C.d_stereo) w *= C.d_stereo * rsqrtf(chi);
+  }
+  Q.pe.z = (L.e.z - L.e.x) * icz;
+  Q.pe.x = (L.e.x - c0 * Q.pe.z) * ia;
+  Q.pe.y = (L.e.y - c1 * Q.pe.z) * ib;
+  // q = P^-T nc
+  const float q1 = nc.y * ib;
+  const float q2 = (nc.z - c0 * nc.x * ia - c1 * q1) * icz;
+  const float q0 = nc.x * ia - q2;
+  // z = P^-1 q / w
+  const float iw = 1.0f / w;
+  const float zz = (q2 - q0) * icz;
+  Q.z = {(q0 - c0 * zz) * ia * iw, (q1 - c1 * zz) * ib * iw, zz * iw};
+  const float gamma = nc.x * Q.z.x + nc.y * Q.z.y + nc.z * Q.z.z;
+  Q.kappa = C.lam / (1.0f + C.lam * gamma);
+  return Q;
+}
+
 // fp64 treatment of one ill-conditioned point (class C_F64): the update and the Schur terms of frame_gn_kernel.
 // Deliberately not inlined: it runs for a few warp-iterations per sweep and must not raise the register count of
 // the fp32 path.
@@ -343,7 +383,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
           const double pz = s_new.R[6] * x0 + s_new.R[7] * x1 + s_new.R[8] * x2 + s_new.t[2];
           if (!(pz < kFarZ)) cls = C_F64;
           else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_F64;  // a free monocular point always has F_STR
-          else cls = (b & F_STR) ? C_STR : C_PLAIN;
+          else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
         }
         tmp[i] = (uint8_t)(b | (cls << 4));
       }
@@ -421,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
         const int cls = b >> 4;
         const bool stereo = b & F_STEREO;
         const bool upd = do_update && cls >= C_PLAIN;
-        const bool accp = do_acc && (cls == C_FIXED || cls == C_STR || (cls == C_F64 && (b & F_STR)));
+        const bool accp = do_acc && (cls == C_FIXED || cls == C_STRP || cls == C_STR || (cls == C_F64 && (b & F_STR)));
         if (!upd && !accp) continue;
         double x0 = xs[j * 3], x1 = xs[j * 3 + 1], x2 = xs[j * 3 + 2];
         const float ob[3] = {so[j * 3], so[j * 3 + 1], so[j * 3 + 2]};
@@ -458,7 +498,46 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
           continue;
         }
         StrF sc;
-        if (cls == C_MPLANE || cls == C_STR) load_structure(a, gn_tab, sk[j], sc);
+        if (cls == C_MPLANE || cls == C_STRP || cls == C_STR) load_structure(a, gn_tab, sk[j], sc);
+        if (cls == C_STRP) {
+          const V3f n = {sc.c[0], sc.c[1], sc.c[2]};
+          if (upd) {
+            const PlaneLin Q = plane_lin(C, linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, true), rotf(s_old.Rf, n), w);
+            const float es = n.x * (float)(x0 - sc.mu[0]) + n.y * (float)(x1 - sc.mu[1]) + n.z * (float)(x2 - sc.mu[2]);
+            const V3f ad = {om.y * Q.pc.z - om.z * Q.pc.y + up.x, om.z * Q.pc.x - om.x * Q.pc.z + up.y,
+                            om.x * Q.pc.y - om.y * Q.pc.x + up.z};
+            const float le = C.lam * es;
+            const V3f u = {Q.pe.x - ad.x - le * Q.z.x, Q.pe.y - ad.y - le * Q.z.y, Q.pe.z - ad.z - le * Q.z.z};
+            const float nu = Q.kappa * (Q.nc.x * u.x + Q.nc.y * u.y + Q.nc.z * u.z);
+            const V3f dw = rotf_t(s_old.Rf, {u.x - nu * Q.z.x, u.y - nu * Q.z.y, u.z - nu * Q.z.z});
+            if (!(isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad |= 2;
+            x0 += (double)dw.x;
+            x1 += (double)dw.y;
+            x2 += (double)dw.z;
+            xs[j * 3] = x0;
+            xs[j * 3 + 1] = x1;
+            xs[j * 3 + 2] = x2;
+          }
+          if (accp) {
+            const PlaneLin Q = plane_lin(C, linearise(P, s_new.R, s_new.t, x0, x1, x2, ob, true), rotf(s_new.Rf, n), w);
+            const float es = n.x * (float)(x0 - sc.mu[0]) + n.y * (float)(x1 - sc.mu[1]) + n.z * (float)(x2 - sc.mu[2]);
+            const float rho = Q.kappa * (es + Q.nc.x * Q.pe.x + Q.nc.y * Q.pe.y + Q.nc.z * Q.pe.z);
+            if (!isfinite(Q.kappa)) bad |= 1;
+            // g = A^T nc = [pc x nc ; nc]:  H += kappa g g^T,  rhs += kappa rho' g   (rho = kappa rho')
+            const float g[6] = {Q.pc.y * Q.nc.z - Q.pc.z * Q.nc.y, Q.pc.z * Q.nc.x - Q.pc.x * Q.nc.z, Q.pc.x * Q.nc.y - Q.pc.y * Q.nc.x,
+                                Q.nc.x, Q.nc.y, Q.nc.z};
+            int n_ = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+              const float kg = Q.kappa * g[r];
+#pragma unroll
+              for (int c = r; c < 6; ++c) acc[n_++] += kg * g[c];
+            }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) acc[21 + r] += rho * g[r];
+          }
+          continue;
+        }
         if (cls == C_MPLANE) {
           // rows u, v of P and the plane normal form a square system:  [P_uv ; nc^T] dc = [e - P_uv A dxi ; -es]
           // (= D^-1 (h + s - G A dxi) of the general path; weights and the Huber factor cancel row by row)
