@@ -30,14 +30,8 @@ namespace gmmloc {
 
 namespace {
 
-#ifndef GMMLOC_GNM_THREADS
-#define GMMLOC_GNM_THREADS 256
-#endif
-#ifndef GMMLOC_GNM_MINB
-#define GMMLOC_GNM_MINB 2
-#endif
-constexpr int kThreads = GMMLOC_GNM_THREADS;
-constexpr int kWarps = kThreads / 32;
+// Two instantiations: 256 threads x 2 CTAs per SM while two frames fit in shared memory, else 512 threads x 1 CTA
+// (128 registers per thread either way: 16 resident warps per SM).
 constexpr int kAcc = 27;
 constexpr double kFarZ = 6.0;  // metres; cond(G) ~ (z fx / bf)^2 ~ 3e3 at the shipped camera (v1.yaml:5-17)
 // Point classes (bits 4..6 of the per-point flag byte).  The points of a frame are stably sorted by class when the
@@ -60,8 +54,9 @@ enum : int {
                  // any free point beyond kFarZ): fp64 path of frame_gn_kernel
   C_COUNT = 7
 };
-constexpr int kMaxChunks = 18;                        // N <= kMaxChunks * kThreads
-constexpr int kBytesPerPoint = 24 + 12 + 4 + 2 + 1 + 1 + 1;  // xs, obs, asg, perm, oct, flags, tmp
+constexpr int kMaxChunks = 10;                        // N <= kMaxChunks * 256
+constexpr int kStore = 12;                            // floats of the stored linearisation per point: u0 (3), W (9)
+constexpr int kBytesPerPoint = 24 + 12 + 4 + 2 + 1 + 1 + 1 + 4 * kStore;  // xs, obs, asg, perm, oct, flags, tmp, store
 
 
 struct V3f {
@@ -93,7 +88,7 @@ __device__ __forceinline__ S3f inv_symf(const S3f& D, bool& ok) {
 // camera constants in fp32 + the pose of one linearisation point in both precisions
 struct PoseBoth {
   double R[9], t[3];
-  float Rf[9];
+  float Rf[9], tf[3];
 };
 
 // per-point constants of the structure edge (fp32 Hessian model; the mean stays fp64 for the offset x - mu)
@@ -290,15 +285,17 @@ __device__ __noinline__ void point_fp64(const FrameArgs& a, const PoseBoth& oldp
   }
 }
 
-__global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
-                                                                                   int* __restrict__ counters) {
+template <int kThreads, int kMinB>
+__global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
+                                                                         int* __restrict__ counters) {
+  constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[kWarps][kAcc];
   __shared__ double s_acc[kAcc];
   __shared__ double s_pose[7], s_dxi[6];
   __shared__ PoseBoth s_new, s_old;  // linearisation points: state sw (accumulate) and state sw-1 (update)
   __shared__ int s_fail1, s_fail2, s_frame;
-  __shared__ int s_cnt[C_COUNT * kMaxChunks * kWarps];  // class histogram per (class, chunk, warp) -> exclusive offsets
+  __shared__ int s_cnt[C_COUNT * kMaxChunks * 8];  // class histogram per (class, chunk, warp) -> exclusive offsets
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
@@ -319,6 +316,10 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
   uint8_t* soct = reinterpret_cast<uint8_t*>(perm + N);
   uint8_t* fl = soct + N;
   uint8_t* tmp = fl + N;  // flags by ORIGINAL index while the frame is being sorted
+  // stored linearisation of the structured free points (classes C_STRP / C_STR): the point step of iteration i is
+  // dc = u0 - W (A dxi) with u0 = D^-1 (h + s), W = D^-1 G from the SAME linearisation the pose system of iteration i
+  // was accumulated at, so the fused sweep linearises every such point once, not twice
+  float* store = reinterpret_cast<float*>(smem_raw + (((size_t)N * 45 + 15) & ~(size_t)15));
 
   // persistent CTAs: frames are handed out through a global counter (no tail wave)
   for (;;) {
@@ -345,7 +346,10 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
         s_old.R[i] = s_new.R[i];
         s_old.Rf[i] = s_new.Rf[i];
       }
-      for (int i = 0; i < 3; ++i) s_new.t[i] = s_old.t[i] = q[4 + i];
+      for (int i = 0; i < 3; ++i) {
+        s_new.t[i] = s_old.t[i] = q[4 + i];
+        s_new.tf[i] = s_old.tf[i] = (float)q[4 + i];
+      }
       s_fail1 = 0;
       s_fail2 = 0;
     }
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
 #pragma unroll
       for (int q = 0; q < C_COUNT; ++q) {
         const unsigned m = __ballot_sync(0xffffffffu, cls == q);
-        if (lane == 0) s_cnt[(q * kMaxChunks + c) * kWarps + warp] = __popc(m);
+        if (lane == 0) s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] = __popc(m);
       }
     }
     __syncthreads();
@@ -401,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
         const int n = nchunks * kWarps;
         for (int b0 = 0; b0 < n; b0 += 32) {
           const int e = b0 + lane;
-          const int idx = q * kMaxChunks * kWarps + e;
+          const int idx = q * (kMaxChunks * 8) + e;
           const int v = (e < n) ? s_cnt[idx] : 0;
           int inc = v;
 #pragma unroll
@@ -428,7 +432,7 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
 #pragma unroll
       for (int q = 0; q < C_COUNT; ++q) {
         const unsigned m = __ballot_sync(0xffffffffu, cls == q);
-        if (cls == q) j = s_cnt[(q * kMaxChunks + c) * kWarps + warp] + __popc(m & ((1u << lane) - 1u));
+        if (cls == q) j = s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] + __popc(m & ((1u << lane) - 1u));
       }
       if (i < N) {
         xs[j * 3] = (double)pts[i * 3];
@@ -449,8 +453,9 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
     const int sweeps = (iters > 0) ? iters + 1 : 0;
     for (int sw = 0; sw < sweeps; ++sw) {
       const bool do_update = pts_free && sw > 0;
-      const bool do_acc = pose_free && sw < iters;
-      if (!do_update && !do_acc) continue;
+      const bool do_lin = sw < iters;           // state sw is linearised (the update of sweep sw + 1 needs it)
+      const bool do_acc = pose_free && do_lin;  // ... and enters the pose system
+      if (!do_update && !do_acc && !(do_lin && pts_free)) continue;
       const V3f om = {(float)s_dxi[0], (float)s_dxi[1], (float)s_dxi[2]}, up = {(float)s_dxi[3], (float)s_dxi[4], (float)s_dxi[5]};
       float acc[kAcc];
 #pragma unroll
@@ -462,7 +467,8 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
         const bool stereo = b & F_STEREO;
         const bool upd = do_update && cls >= C_PLAIN;
         const bool accp = do_acc && (cls == C_FIXED || cls == C_STRP || cls == C_STR || (cls == C_F64 && (b & F_STR)));
-        if (!upd && !accp) continue;
+        const bool linp = do_lin && (cls == C_STRP || cls == C_STR);  // linearise + store (+ accumulate when accp)
+        if (!upd && !accp && !linp) continue;
         double x0 = xs[j * 3], x1 = xs[j * 3 + 1], x2 = xs[j * 3 + 2];
         const float ob[3] = {so[j * 3], so[j * 3 + 1], so[j * 3 + 2]};
         const float w = P.s2inv[soct[j] & 7];
@@ -499,17 +505,18 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
         }
         StrF sc;
         if (cls == C_MPLANE || cls == C_STRP || cls == C_STR) load_structure(a, gn_tab, sk[j], sc);
-        if (cls == C_STRP) {
-          const V3f n = {sc.c[0], sc.c[1], sc.c[2]};
-          if (upd) {
-            const PlaneLin Q = plane_lin(C, linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, true), rotf(s_old.Rf, n), w);
-            const float es = n.x * (float)(x0 - sc.mu[0]) + n.y * (float)(x1 - sc.mu[1]) + n.z * (float)(x2 - sc.mu[2]);
-            const V3f ad = {om.y * Q.pc.z - om.z * Q.pc.y + up.x, om.z * Q.pc.x - om.x * Q.pc.z + up.y,
-                            om.x * Q.pc.y - om.y * Q.pc.x + up.z};
-            const float le = C.lam * es;
-            const V3f u = {Q.pe.x - ad.x - le * Q.z.x, Q.pe.y - ad.y - le * Q.z.y, Q.pe.z - ad.z - le * Q.z.z};
-            const float nu = Q.kappa * (Q.nc.x * u.x + Q.nc.y * u.y + Q.nc.z * u.z);
-            const V3f dw = rotf_t(s_old.Rf, {u.x - nu * Q.z.x, u.y - nu * Q.z.y, u.z - nu * Q.z.z});
+        if (cls == C_STRP || cls == C_STR) {
+          float* sp = store + (size_t)j * kStore;
+          if (upd) {  // step from the stored linearisation (state sw - 1): dc = u0 - W (omega x pc + upsilon)
+            const V3f pc = rotf(s_old.Rf, {(float)x0, (float)x1, (float)x2});
+            const V3f pcs = {pc.x + s_old.tf[0], pc.y + s_old.tf[1], pc.z + s_old.tf[2]};
+            const V3f ad = {om.y * pcs.z - om.z * pcs.y + up.x, om.z * pcs.x - om.x * pcs.z + up.y,
+                            om.x * pcs.y - om.y * pcs.x + up.z};
+            const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4),
+                         s2 = *reinterpret_cast<const float4*>(sp + 8);
+            const V3f dc = {s0.x - (s0.w * ad.x + s1.x * ad.y + s1.y * ad.z), s0.y - (s1.z * ad.x + s1.w * ad.y + s2.x * ad.z),
+                            s0.z - (s2.y * ad.x + s2.z * ad.y + s2.w * ad.z)};
+            const V3f dw = rotf_t(s_old.Rf, dc);
             if (!(isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad |= 2;
             x0 += (double)dw.x;
             x1 += (double)dw.y;
@@ -518,87 +525,49 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
             xs[j * 3 + 1] = x1;
             xs[j * 3 + 2] = x2;
           }
-          if (accp) {
-            const PlaneLin Q = plane_lin(C, linearise(P, s_new.R, s_new.t, x0, x1, x2, ob, true), rotf(s_new.Rf, n), w);
+          if (!linp) continue;
+          const Lin L = linearise(P, s_new.R, s_new.t, x0, x1, x2, ob, true);
+          V3f u0;
+          float W[9];
+          if (cls == C_STRP) {
+            const V3f n = {sc.c[0], sc.c[1], sc.c[2]};
+            const PlaneLin Q = plane_lin(C, L, rotf(s_new.Rf, n), w);
             const float es = n.x * (float)(x0 - sc.mu[0]) + n.y * (float)(x1 - sc.mu[1]) + n.z * (float)(x2 - sc.mu[2]);
-            const float rho = Q.kappa * (es + Q.nc.x * Q.pe.x + Q.nc.y * Q.pe.y + Q.nc.z * Q.pe.z);
             if (!isfinite(Q.kappa)) bad |= 1;
-            // g = A^T nc = [pc x nc ; nc]:  H += kappa g g^T,  rhs += kappa rho' g   (rho = kappa rho')
-            const float g[6] = {Q.pc.y * Q.nc.z - Q.pc.z * Q.nc.y, Q.pc.z * Q.nc.x - Q.pc.x * Q.nc.z, Q.pc.x * Q.nc.y - Q.pc.y * Q.nc.x,
-                                Q.nc.x, Q.nc.y, Q.nc.z};
-            int n_ = 0;
+            // u0 = D^-1 (h + s) = u - kappa z (nc . u), u = pe - lam es z;   W = D^-1 G = I - kappa z nc^T
+            const float le = C.lam * es;
+            const V3f u = {Q.pe.x - le * Q.z.x, Q.pe.y - le * Q.z.y, Q.pe.z - le * Q.z.z};
+            const float nu = Q.kappa * (Q.nc.x * u.x + Q.nc.y * u.y + Q.nc.z * u.z);
+            u0 = {u.x - nu * Q.z.x, u.y - nu * Q.z.y, u.z - nu * Q.z.z};
+            const V3f kz = {Q.kappa * Q.z.x, Q.kappa * Q.z.y, Q.kappa * Q.z.z};
+            W[0] = 1.f - kz.x * Q.nc.x; W[1] = -kz.x * Q.nc.y; W[2] = -kz.x * Q.nc.z;
+            W[3] = -kz.y * Q.nc.x; W[4] = 1.f - kz.y * Q.nc.y; W[5] = -kz.y * Q.nc.z;
+            W[6] = -kz.z * Q.nc.x; W[7] = -kz.z * Q.nc.y; W[8] = 1.f - kz.z * Q.nc.z;
+            if (accp) {
+              const float rho = Q.kappa * (es + Q.nc.x * Q.pe.x + Q.nc.y * Q.pe.y + Q.nc.z * Q.pe.z);
+              // g = A^T nc = [pc x nc ; nc]:  H += kappa g g^T,  rhs += kappa (es + nc . pe) g
+              const float g[6] = {Q.pc.y * Q.nc.z - Q.pc.z * Q.nc.y, Q.pc.z * Q.nc.x - Q.pc.x * Q.nc.z,
+                                  Q.pc.x * Q.nc.y - Q.pc.y * Q.nc.x, Q.nc.x, Q.nc.y, Q.nc.z};
+              int n_ = 0;
 #pragma unroll
-            for (int r = 0; r < 6; ++r) {
-              const float kg = Q.kappa * g[r];
+              for (int r = 0; r < 6; ++r) {
+                const float kg = Q.kappa * g[r];
 #pragma unroll
-              for (int c = r; c < 6; ++c) acc[n_++] += kg * g[c];
+                for (int c = r; c < 6; ++c) acc[n_++] += kg * g[c];
+              }
+#pragma unroll
+              for (int r = 0; r < 6; ++r) acc[21 + r] += rho * g[r];
             }
-#pragma unroll
-            for (int r = 0; r < 6; ++r) acc[21 + r] += rho * g[r];
-          }
-          continue;
-        }
-        if (cls == C_MPLANE) {
-          // rows u, v of P and the plane normal form a square system:  [P_uv ; nc^T] dc = [e - P_uv A dxi ; -es]
-          // (= D^-1 (h + s - G A dxi) of the general path; weights and the Huber factor cancel row by row)
-          const Lin L = linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, false);
-          const float a_ = C.fx * L.iz, b_ = C.fy * L.iz;
-          const float c0 = -a_ * L.pc.x * L.iz, c1 = -b_ * L.pc.y * L.iz;
-          const V3f d3 = {(float)(x0 - sc.mu[0]), (float)(x1 - sc.mu[1]), (float)(x2 - sc.mu[2])};
-          const float es = sc.c[0] * d3.x + sc.c[1] * d3.y + sc.c[2] * d3.z;
-          const V3f nc = rotf(s_old.Rf, {sc.c[0], sc.c[1], sc.c[2]});
-          const V3f ad = {om.y * L.pc.z - om.z * L.pc.y + up.x, om.z * L.pc.x - om.x * L.pc.z + up.y,
-                          om.x * L.pc.y - om.y * L.pc.x + up.z};
-          const float r0 = L.e.x - (a_ * ad.x + c0 * ad.z), r1 = L.e.y - (b_ * ad.y + c1 * ad.z), r2 = -es;
-          const float ia = 1.0f / a_, ib = 1.0f / b_;
-          const float den = nc.z - nc.x * c0 * ia - nc.y * c1 * ib;  // = (nc . pc) / z: bounded away from 0 by the view-cos cull
-          const float dz = (r2 - nc.x * r0 * ia - nc.y * r1 * ib) / den;
-          const float dx = (r0 - c0 * dz) * ia, dy = (r1 - c1 * dz) * ib;
-          const V3f dw = rotf_t(s_old.Rf, {dx, dy, dz});
-          if (!(isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad |= 2;
-          xs[j * 3] = x0 + (double)dw.x;
-          xs[j * 3 + 1] = x1 + (double)dw.y;
-          xs[j * 3 + 2] = x2 + (double)dw.z;
-          continue;
-        }
-        if (upd) {  // C_STR only
-          const Lin L = linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, stereo);
-          S3f G, S;
-          V3f h, s;
-          reprojf(C, L, stereo, w, G, h);
-          structuref(C, s_old.Rf, sc, b, x0, x1, x2, S, s);
-          const S3f D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
-          const V3f bl = {h.x + s.x, h.y + s.y, h.z + s.z};
-          bool ok;
-          const S3f Di = inv_symf(D, ok);
-          const V3f ad = {om.y * L.pc.z - om.z * L.pc.y + up.x, om.z * L.pc.x - om.x * L.pc.z + up.y,
-                          om.x * L.pc.y - om.y * L.pc.x + up.z};
-          const V3f ga = mulf(G, ad);
-          const V3f dc = mulf(Di, {bl.x - ga.x, bl.y - ga.y, bl.z - ga.z});
-          const V3f dw = rotf_t(s_old.Rf, dc);
-          x0 += (double)dw.x;
-          x1 += (double)dw.y;
-          x2 += (double)dw.z;
-          if (!(ok && isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad |= 2;
-          xs[j * 3] = x0;
-          xs[j * 3 + 1] = x1;
-          xs[j * 3 + 2] = x2;
-        }
-        if (accp) {  // C_FIXED or C_STR
-          const Lin L = linearise(P, s_new.R, s_new.t, x0, x1, x2, ob, stereo);
-          S3f G;
-          V3f h;
-          reprojf(C, L, stereo, w, G, h);
-          S3f M = G;
-          V3f v = h;
-          if (cls == C_STR) {
-            S3f S;
-            V3f s;
+          } else {
+            S3f G, S;
+            V3f h, s;
+            reprojf(C, L, true, w, G, h);
             structuref(C, s_new.Rf, sc, b, x0, x1, x2, S, s);
             const S3f D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
             bool ok;
             const S3f Di = inv_symf(D, ok);
             if (!ok) bad |= 1;
+            // T = G D^-1;  W = D^-1 G = T^T
             const float T00 = G.xx * Di.xx + G.xy * Di.xy + G.xz * Di.xz, T01 = G.xx * Di.xy + G.xy * Di.yy + G.xz * Di.yz,
                         T02 = G.xx * Di.xz + G.xy * Di.yz + G.xz * Di.zz;
             const float T10 = G.xy * Di.xx + G.yy * Di.xy + G.yz * Di.xz, T11 = G.xy * Di.xy + G.yy * Di.yy + G.yz * Di.yz,
@@ -606,17 +575,33 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
             const float T20 = G.xz * Di.xx + G.yz * Di.xy + G.zz * Di.xz, T21 = G.xz * Di.xy + G.yz * Di.yy + G.zz * Di.yz,
                         T22 = G.xz * Di.xz + G.yz * Di.yz + G.zz * Di.zz;
             const V3f bl = {h.x + s.x, h.y + s.y, h.z + s.z};
-            // v = h - T (h + s): equals h at the fixed point (h + s = 0) whatever the rounding of D^-1
-            v = {h.x - (T00 * bl.x + T01 * bl.y + T02 * bl.z), h.y - (T10 * bl.x + T11 * bl.y + T12 * bl.z),
-                 h.z - (T20 * bl.x + T21 * bl.y + T22 * bl.z)};
-            M.xx = T00 * S.xx + T01 * S.xy + T02 * S.xz;
-            M.xy = T00 * S.xy + T01 * S.yy + T02 * S.yz;
-            M.xz = T00 * S.xz + T01 * S.yz + T02 * S.zz;
-            M.yy = T10 * S.xy + T11 * S.yy + T12 * S.yz;
-            M.yz = T10 * S.xz + T11 * S.yz + T12 * S.zz;
-            M.zz = T20 * S.xz + T21 * S.yz + T22 * S.zz;
+            u0 = mulf(Di, bl);
+            W[0] = T00; W[1] = T10; W[2] = T20; W[3] = T01; W[4] = T11; W[5] = T21; W[6] = T02; W[7] = T12; W[8] = T22;
+            if (accp) {
+              // v = h - T (h + s): equals h at the fixed point (h + s = 0) whatever the rounding of D^-1
+              const V3f v = {h.x - (T00 * bl.x + T01 * bl.y + T02 * bl.z), h.y - (T10 * bl.x + T11 * bl.y + T12 * bl.z),
+                             h.z - (T20 * bl.x + T21 * bl.y + T22 * bl.z)};
+              S3f M;
+              M.xx = T00 * S.xx + T01 * S.xy + T02 * S.xz;
+              M.xy = T00 * S.xy + T01 * S.yy + T02 * S.yz;
+              M.xz = T00 * S.xz + T01 * S.yz + T02 * S.zz;
+              M.yy = T10 * S.xy + T11 * S.yy + T12 * S.yz;
+              M.yz = T10 * S.xz + T11 * S.yz + T12 * S.zz;
+              M.zz = T20 * S.xz + T21 * S.yz + T22 * S.zz;
+              accumulate_posef(acc, L.pc, M, v);
+            }
           }
-          accumulate_posef(acc, L.pc, M, v);
+          *reinterpret_cast<float4*>(sp) = make_float4(u0.x, u0.y, u0.z, W[0]);
+          *reinterpret_cast<float4*>(sp + 4) = make_float4(W[1], W[2], W[3], W[4]);
+          *reinterpret_cast<float4*>(sp + 8) = make_float4(W[5], W[6], W[7], W[8]);
+          continue;
+        }
+        if (accp) {  // C_FIXED: a held point contributes G, h
+          const Lin L = linearise(P, s_new.R, s_new.t, x0, x1, x2, ob, stereo);
+          S3f G;
+          V3f h;
+          reprojf(C, L, stereo, w, G, h);
+          accumulate_posef(acc, L.pc, G, h);
         }
       }
       if (bad & 2) s_fail2 = 1;
@@ -656,7 +641,10 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
                 s_old.Rf[i] = s_new.Rf[i];
               }
 #pragma unroll
-              for (int i = 0; i < 3; ++i) s_old.t[i] = s_new.t[i];
+              for (int i = 0; i < 3; ++i) {
+                s_old.t[i] = s_new.t[i];
+                s_old.tf[i] = s_new.tf[i];
+              }
               se3_oplus_fast(dxi, s_pose, np, s_new.R);
 #pragma unroll
               for (int i = 0; i < 6; ++i) s_dxi[i] = dxi[i];
@@ -665,7 +653,10 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
 #pragma unroll
               for (int i = 0; i < 9; ++i) s_new.Rf[i] = (float)s_new.R[i];
 #pragma unroll
-              for (int i = 0; i < 3; ++i) s_new.t[i] = np[4 + i];
+              for (int i = 0; i < 3; ++i) {
+                s_new.t[i] = np[4 + i];
+                s_new.tf[i] = (float)np[4 + i];
+              }
             }
           }
         }
@@ -727,25 +718,34 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GNM_MINB) frame_gn_mixed_kern
 }  // namespace
 
 size_t frame_gn_mixed_limit_points() {
-  const size_t by_smem = (size_t)(200 * 1024) / kBytesPerPoint;
-  return std::min(by_smem, (size_t)kMaxChunks * kThreads);
+  const size_t by_smem = (size_t)(216 * 1024) / (kBytesPerPoint + 1);
+  return std::min(by_smem, (size_t)kMaxChunks * 256);
 }
 
-cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, cudaStream_t stream) {
+template <int kThreads, int kMinB>
+static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* d_counters, size_t smem, cudaStream_t stream) {
   cudaError_t e;
-  const size_t smem = (size_t)a.N * kBytesPerPoint + 16;
-  if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)) != cudaSuccess)
+  if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) !=
+      cudaSuccess)
     return e;
   int per_sm = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel, kThreads, smem)) != cudaSuccess) return e;
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel<kThreads, kMinB>, kThreads, smem)) != cudaSuccess)
+    return e;
   if (per_sm < 1) per_sm = 1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(a.B, sms * per_sm);
   if ((e = cudaMemsetAsync(d_counters, 0, sizeof(int), stream)) != cudaSuccess) return e;
-  frame_gn_mixed_kernel<<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters);
+  frame_gn_mixed_kernel<kThreads, kMinB><<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters);
   return cudaGetLastError();
+}
+
+cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, cudaStream_t stream) {
+  const size_t smem = (((size_t)a.N * 45 + 15) & ~(size_t)15) + (size_t)a.N * 4 * kStore + 16;
+  // two frames per SM (256 threads each) while they fit next to the static shared memory, else one CTA of 512 threads
+  if (2 * (smem + 8 * 1024) <= 227 * 1024) return launch_mixed_t<256, 2>(a, gn_tab, d_counters, smem, stream);
+  return launch_mixed_t<512, 1>(a, gn_tab, d_counters, smem, stream);
 }
 
 }  // namespace gmmloc
