@@ -285,7 +285,7 @@ __device__ __noinline__ void point_fp64(const FrameArgs& a, const PoseBoth& oldp
   }
 }
 
-template <int kThreads, int kMinB>
+template <int kThreads, int kMinB, bool kStoreLin>
 __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
                                                                          int* __restrict__ counters) {
   constexpr int kWarps = kThreads / 32;
@@ -505,6 +505,133 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const F
         }
         StrF sc;
         if (cls == C_MPLANE || cls == C_STRP || cls == C_STR) load_structure(a, gn_tab, sk[j], sc);
+        if (cls == C_MPLANE) {
+          // rows u, v of P and the plane normal form a square system:  [P_uv ; nc^T] dc = [e - P_uv A dxi ; -es]
+          // (= D^-1 (h + s - G A dxi) of the general path; weights and the Huber factor cancel row by row)
+          const Lin L = linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, false);
+          const float a_ = C.fx * L.iz, b_ = C.fy * L.iz;
+          const float c0 = -a_ * L.pc.x * L.iz, c1 = -b_ * L.pc.y * L.iz;
+          const V3f d3 = {(float)(x0 - sc.mu[0]), (float)(x1 - sc.mu[1]), (float)(x2 - sc.mu[2])};
+          const float es = sc.c[0] * d3.x + sc.c[1] * d3.y + sc.c[2] * d3.z;
+          const V3f nc = rotf(s_old.Rf, {sc.c[0], sc.c[1], sc.c[2]});
+          const V3f ad = {om.y * L.pc.z - om.z * L.pc.y + up.x, om.z * L.pc.x - om.x * L.pc.z + up.y,
+                          om.x * L.pc.y - om.y * L.pc.x + up.z};
+          const float r0 = L.e.x - (a_ * ad.x + c0 * ad.z), r1 = L.e.y - (b_ * ad.y + c1 * ad.z), r2 = -es;
+          const float ia = 1.0f / a_, ib = 1.0f / b_;
+          const float den = nc.z - nc.x * c0 * ia - nc.y * c1 * ib;  // = (nc . pc) / z: bounded away from 0 by the view-cos cull
+          const float dz = (r2 - nc.x * r0 * ia - nc.y * r1 * ib) / den;
+          const float dx = (r0 - c0 * dz) * ia, dy = (r1 - c1 * dz) * ib;
+          const V3f dw = rotf_t(s_old.Rf, {dx, dy, dz});
+          if (!(isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad |= 2;
+          xs[j * 3] = x0 + (double)dw.x;
+          xs[j * 3 + 1] = x1 + (double)dw.y;
+          xs[j * 3 + 2] = x2 + (double)dw.z;
+          continue;
+        }
+        if constexpr (!kStoreLin) {
+          // no room in shared memory for the stored linearisation: update at the old state, accumulate at the new one
+          if (cls == C_STRP || cls == C_STR) {
+          if (cls == C_STRP) {
+          const V3f n = {sc.c[0], sc.c[1], sc.c[2]};
+          if (upd) {
+            const PlaneLin Q = plane_lin(C, linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, true), rotf(s_old.Rf, n), w);
+            const float es = n.x * (float)(x0 - sc.mu[0]) + n.y * (float)(x1 - sc.mu[1]) + n.z * (float)(x2 - sc.mu[2]);
+            const V3f ad = {om.y * Q.pc.z - om.z * Q.pc.y + up.x, om.z * Q.pc.x - om.x * Q.pc.z + up.y,
+                            om.x * Q.pc.y - om.y * Q.pc.x + up.z};
+            const float le = C.lam * es;
+            const V3f u = {Q.pe.x - ad.x - le * Q.z.x, Q.pe.y - ad.y - le * Q.z.y, Q.pe.z - ad.z - le * Q.z.z};
+            const float nu = Q.kappa * (Q.nc.x * u.x + Q.nc.y * u.y + Q.nc.z * u.z);
+            const V3f dw = rotf_t(s_old.Rf, {u.x - nu * Q.z.x, u.y - nu * Q.z.y, u.z - nu * Q.z.z});
+            if (!(isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad |= 2;
+            x0 += (double)dw.x;
+            x1 += (double)dw.y;
+            x2 += (double)dw.z;
+            xs[j * 3] = x0;
+            xs[j * 3 + 1] = x1;
+            xs[j * 3 + 2] = x2;
+          }
+          if (accp) {
+            const PlaneLin Q = plane_lin(C, linearise(P, s_new.R, s_new.t, x0, x1, x2, ob, true), rotf(s_new.Rf, n), w);
+            const float es = n.x * (float)(x0 - sc.mu[0]) + n.y * (float)(x1 - sc.mu[1]) + n.z * (float)(x2 - sc.mu[2]);
+            const float rho = Q.kappa * (es + Q.nc.x * Q.pe.x + Q.nc.y * Q.pe.y + Q.nc.z * Q.pe.z);
+            if (!isfinite(Q.kappa)) bad |= 1;
+            // g = A^T nc = [pc x nc ; nc]:  H += kappa g g^T,  rhs += kappa rho' g   (rho = kappa rho')
+            const float g[6] = {Q.pc.y * Q.nc.z - Q.pc.z * Q.nc.y, Q.pc.z * Q.nc.x - Q.pc.x * Q.nc.z, Q.pc.x * Q.nc.y - Q.pc.y * Q.nc.x,
+                                Q.nc.x, Q.nc.y, Q.nc.z};
+            int n_ = 0;
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+              const float kg = Q.kappa * g[r];
+#pragma unroll
+              for (int c = r; c < 6; ++c) acc[n_++] += kg * g[c];
+            }
+#pragma unroll
+            for (int r = 0; r < 6; ++r) acc[21 + r] += rho * g[r];
+          }
+          continue;
+        }
+          {
+        if (upd) {  // C_STR only
+          const Lin L = linearise(P, s_old.R, s_old.t, x0, x1, x2, ob, stereo);
+          S3f G, S;
+          V3f h, s;
+          reprojf(C, L, stereo, w, G, h);
+          structuref(C, s_old.Rf, sc, b, x0, x1, x2, S, s);
+          const S3f D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
+          const V3f bl = {h.x + s.x, h.y + s.y, h.z + s.z};
+          bool ok;
+          const S3f Di = inv_symf(D, ok);
+          const V3f ad = {om.y * L.pc.z - om.z * L.pc.y + up.x, om.z * L.pc.x - om.x * L.pc.z + up.y,
+                          om.x * L.pc.y - om.y * L.pc.x + up.z};
+          const V3f ga = mulf(G, ad);
+          const V3f dc = mulf(Di, {bl.x - ga.x, bl.y - ga.y, bl.z - ga.z});
+          const V3f dw = rotf_t(s_old.Rf, dc);
+          x0 += (double)dw.x;
+          x1 += (double)dw.y;
+          x2 += (double)dw.z;
+          if (!(ok && isfinite(dw.x) && isfinite(dw.y) && isfinite(dw.z))) bad |= 2;
+          xs[j * 3] = x0;
+          xs[j * 3 + 1] = x1;
+          xs[j * 3 + 2] = x2;
+        }
+        if (accp) {  // C_STR (two linearisations per sweep: no room for the stored one)
+          const Lin L = linearise(P, s_new.R, s_new.t, x0, x1, x2, ob, stereo);
+          S3f G;
+          V3f h;
+          reprojf(C, L, stereo, w, G, h);
+          S3f M = G;
+          V3f v = h;
+          {
+            S3f S;
+            V3f s;
+            structuref(C, s_new.Rf, sc, b, x0, x1, x2, S, s);
+            const S3f D = {G.xx + S.xx, G.xy + S.xy, G.xz + S.xz, G.yy + S.yy, G.yz + S.yz, G.zz + S.zz};
+            bool ok;
+            const S3f Di = inv_symf(D, ok);
+            if (!ok) bad |= 1;
+            const float T00 = G.xx * Di.xx + G.xy * Di.xy + G.xz * Di.xz, T01 = G.xx * Di.xy + G.xy * Di.yy + G.xz * Di.yz,
+                        T02 = G.xx * Di.xz + G.xy * Di.yz + G.xz * Di.zz;
+            const float T10 = G.xy * Di.xx + G.yy * Di.xy + G.yz * Di.xz, T11 = G.xy * Di.xy + G.yy * Di.yy + G.yz * Di.yz,
+                        T12 = G.xy * Di.xz + G.yy * Di.yz + G.yz * Di.zz;
+            const float T20 = G.xz * Di.xx + G.yz * Di.xy + G.zz * Di.xz, T21 = G.xz * Di.xy + G.yz * Di.yy + G.zz * Di.yz,
+                        T22 = G.xz * Di.xz + G.yz * Di.yz + G.zz * Di.zz;
+            const V3f bl = {h.x + s.x, h.y + s.y, h.z + s.z};
+            // v = h - T (h + s): equals h at the fixed point (h + s = 0) whatever the rounding of D^-1
+            v = {h.x - (T00 * bl.x + T01 * bl.y + T02 * bl.z), h.y - (T10 * bl.x + T11 * bl.y + T12 * bl.z),
+                 h.z - (T20 * bl.x + T21 * bl.y + T22 * bl.z)};
+            M.xx = T00 * S.xx + T01 * S.xy + T02 * S.xz;
+            M.xy = T00 * S.xy + T01 * S.yy + T02 * S.yz;
+            M.xz = T00 * S.xz + T01 * S.yz + T02 * S.zz;
+            M.yy = T10 * S.xy + T11 * S.yy + T12 * S.yz;
+            M.yz = T10 * S.xz + T11 * S.yz + T12 * S.zz;
+            M.zz = T20 * S.xz + T21 * S.yz + T22 * S.zz;
+          }
+          accumulate_posef(acc, L.pc, M, v);
+        }
+                }
+          continue;
+          }
+        }
         if (cls == C_STRP || cls == C_STR) {
           float* sp = store + (size_t)j * kStore;
           if (upd) {  // step from the stored linearisation (state sw - 1): dc = u0 - W (omega x pc + upsilon)
@@ -608,11 +735,11 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const F
       if (bad & 1) s_fail1 = 1;
       if (do_acc) {
 #pragma unroll
-        for (int i = 0; i < kAcc; ++i) {
-          double s = (double)acc[i];
+        for (int i = 0; i < kAcc; ++i) {  // lanes in fp32 (fixed butterfly order), warps in fp64
+          float s = acc[i];
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-          if (lane == 0) s_red[warp][i] = s;
+          if (lane == 0) s_red[warp][i] = (double)s;
         }
       }
       __syncthreads();
@@ -722,14 +849,14 @@ size_t frame_gn_mixed_limit_points() {
   return std::min(by_smem, (size_t)kMaxChunks * 256);
 }
 
-template <int kThreads, int kMinB>
+template <int kThreads, int kMinB, bool kStoreLin>
 static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* d_counters, size_t smem, cudaStream_t stream) {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) !=
+  if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) !=
       cudaSuccess)
     return e;
   int per_sm = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel<kThreads, kMinB>, kThreads, smem)) != cudaSuccess)
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, kThreads, smem)) != cudaSuccess)
     return e;
   if (per_sm < 1) per_sm = 1;
   int dev = 0, sms = 148;
@@ -737,15 +864,18 @@ static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(a.B, sms * per_sm);
   if ((e = cudaMemsetAsync(d_counters, 0, sizeof(int), stream)) != cudaSuccess) return e;
-  frame_gn_mixed_kernel<kThreads, kMinB><<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters);
+  frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin><<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters);
   return cudaGetLastError();
 }
 
 cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, cudaStream_t stream) {
-  const size_t smem = (((size_t)a.N * 45 + 15) & ~(size_t)15) + (size_t)a.N * 4 * kStore + 16;
-  // two frames per SM (256 threads each) while they fit next to the static shared memory, else one CTA of 512 threads
-  if (2 * (smem + 8 * 1024) <= 227 * 1024) return launch_mixed_t<256, 2>(a, gn_tab, d_counters, smem, stream);
-  return launch_mixed_t<512, 1>(a, gn_tab, d_counters, smem, stream);
+  const size_t base = (((size_t)a.N * 45 + 15) & ~(size_t)15) + 16, with_store = base + (size_t)a.N * 4 * kStore;
+  const size_t two = 227 * 1024 / 2 - 8 * 1024;  // per-CTA dynamic budget when two CTAs share an SM
+  // Two frames per SM (256 threads each) hide each other's serial 6x6 solve and barriers: preferred whenever they fit,
+  // with the stored linearisation if that fits too; one CTA of 512 threads (with the store) for larger frames.
+  if (with_store <= two) return launch_mixed_t<256, 2, true>(a, gn_tab, d_counters, with_store, stream);
+  if (base <= two) return launch_mixed_t<256, 2, false>(a, gn_tab, d_counters, base, stream);
+  return launch_mixed_t<512, 1, true>(a, gn_tab, d_counters, with_store, stream);
 }
 
 }  // namespace gmmloc
