@@ -202,6 +202,7 @@ struct Lane {
   cudaStream_t stream = nullptr;
   DevBuf flag_count, flag_idx, flag_thr;  // association work lists
   DevBuf next_frame;                      // frame counter of the persistent frame-GN kernel
+  DevBuf sort_cnt, sort_perm;             // cell histogram / landmark order of the cell-sorted grid scan
   DevBuf xws, fws;                        // frame-GN global workspaces (N too large for shared memory)
   int* h_flag_count = nullptr;            // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // scan begin | scan end | re-rank end | GN end
@@ -560,7 +561,7 @@ void gmmloc_ctx_destroy(gmmloc_ctx_t* c) {
   cudaSetDevice(c->device);
   for (Lane& l : c->lanes) {
     if (l.stream) cudaStreamSynchronize(l.stream);
-    DevBuf* lb[] = {&l.flag_count, &l.flag_idx, &l.flag_thr, &l.xws, &l.fws, &l.next_frame};
+    DevBuf* lb[] = {&l.flag_count, &l.flag_idx, &l.flag_thr, &l.xws, &l.fws, &l.next_frame, &l.sort_cnt, &l.sort_perm};
     for (DevBuf* b : lb) b->release();
     if (l.h_flag_count) cudaFreeHost(l.h_flag_count);
     for (cudaEvent_t e : l.ev)
@@ -649,6 +650,15 @@ gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* ma
   CU(ctx->L().flag_idx.reserve(sizeof(int32_t) * 2 * (size_t)M));  // list A | list B (launch_associate)
   CU(ctx->L().flag_thr.reserve(sizeof(float) * 2 * (size_t)M));
   CU(cudaMemsetAsync(ctx->L().flag_count.p, 0, 2 * sizeof(int), ctx->L().stream));
+  int* sort_cnt = nullptr;
+  int32_t* sort_perm = nullptr;
+  if (map->d.grid.nlev > 0) {  // scratch of the cell-sorted grid scan
+    const GridLevel& G0 = map->d.grid.lev[0];
+    CU(ctx->L().sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2)));
+    CU(ctx->L().sort_perm.reserve(sizeof(int32_t) * (size_t)M));
+    sort_cnt = ctx->L().sort_cnt.as<int>();
+    sort_perm = ctx->L().sort_perm.as<int32_t>();
+  }
   int launches = 0;
   CU(cudaEventRecord(ctx->L().ev[0], ctx->L().stream));
   // kernel choice: variant 16 = tensor-core pruning scan, -1 = FFMA2 scan, 0 = launcher default
@@ -658,7 +668,8 @@ gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* ma
                                                               : 0;
   int used_tc = 0;
   CU(launch_associate(map->d, d_pts_w, M, gate, d_assign, d_d2, ctx->L().flag_count.as<int>(), ctx->L().flag_idx.as<int32_t>(),
-                      ctx->L().flag_thr.as<float>(), variant, ctx->L().stream, &launches, ctx->L().ev[1], &used_tc));
+                      ctx->L().flag_thr.as<float>(), variant, ctx->L().stream, &launches, ctx->L().ev[1], &used_tc, sort_cnt,
+                      sort_perm));
   ctx->last_assoc_tc = used_tc;
   CU(cudaEventRecord(ctx->L().ev[2], ctx->L().stream));
   ctx->L().ev_assoc = true;
@@ -801,6 +812,11 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     CU(ln.flag_idx.reserve(sizeof(int32_t) * 2 * mc));
     CU(ln.flag_thr.reserve(sizeof(float) * 2 * mc));
     CU(ln.next_frame.reserve(sizeof(int)));
+    if (map->d.grid.nlev > 0) {
+      const GridLevel& G0 = map->d.grid.lev[0];
+      CU(ln.sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2)));
+      CU(ln.sort_perm.reserve(sizeof(int32_t) * mc));
+    }
     if ((size_t)N > frame_gn_smem_limit_points()) {
       CU(ln.xws.reserve(24 * mc));
       CU(ln.fws.reserve(mc));

@@ -128,6 +128,7 @@ struct ScanArgs {
   int* ga_count;
   int32_t* ga_idx;
   float* ga_thr;   // sign bit = grid level of the re-rank
+  const int32_t* perm;  // landmark order of the cell-sorted grid scan (null: natural order)
   // tensor-core pruning scan only
   const uint16_t* tc_table;
   float cen[3];
@@ -442,11 +443,77 @@ __device__ __forceinline__ long long grid_cell(const GridLevel& G, float x0, flo
   return ((long long)(int)fz * G.ny + (int)fy) * G.nx + (int)fx;
 }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
-  const long long i = (long long)blockIdx.x * THREADS + threadIdx.x;
-  if (i >= a.M) return;
+// ---- landmark sort by level-0 cell (counting sort: histogram -> exclusive scan -> scatter).  With the landmarks of
+// a launch ordered by cell, a warp of the grid scan shares one cell list: list ids and component records are loaded
+// once per warp (broadcast, one L1 wavefront per request) instead of once per lane (the unsorted kernel is
+// L1-wavefront-bound at 8.6 wavefronts per request, profiles/assoc_grid_r01.txt). ----
+__device__ __forceinline__ long long sort_cell(const ScanArgs& a, long long i) {
   const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
+  const GridLevel& G = a.grid.lev[0];
+  const long long c = grid_cell(G, px, py, pz);
+  return c >= 0 ? c : (long long)G.nx * G.ny * G.nz;  // last bucket: outside the grid / non-finite
+}
+__global__ void __launch_bounds__(256) grid_hist_kernel(const ScanArgs a, int* __restrict__ hist) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < a.M) atomicAdd(hist + sort_cell(a, i), 1);
+}
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const ScanArgs a, int* __restrict__ cur, int32_t* __restrict__ perm) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i < a.M) perm[atomicAdd(cur + sort_cell(a, i), 1)] = (int32_t)i;
+}
+// in-place exclusive scan of n ints by one CTA (n <= ~4 M: a few tens of microseconds)
+__global__ void __launch_bounds__(1024) excl_scan_kernel(int* __restrict__ d, int n) {
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int carry = 0;
+  for (int base = 0; base < n; base += 4096) {
+    const int idx = base + tid * 4;
+    int v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = (idx + q < n) ? d[idx + q] : 0;
+    const int t = v[0] + v[1] + v[2] + v[3];
+    int inc = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, off);
+      if (lane >= off) inc += u;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      const int wv = wsum[lane];
+      int winc = wv;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, winc, off);
+        if (lane >= off) winc += u;
+      }
+      wsum[lane] = winc - wv;
+    }
+    __syncthreads();
+    int ex = carry + wsum[warp] + inc - t;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (idx + q < n) d[idx + q] = ex;
+      ex += v[q];
+    }
+    if (tid == 1023) carry_s = ex;
+    __syncthreads();
+    carry = carry_s;
+    __syncthreads();
+  }
+}
+
+template <int THREADS, bool SORTED>
+__global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
+  const long long w = (long long)blockIdx.x * THREADS + threadIdx.x;
+  const bool live = w < a.M;
+  if (!SORTED && !live) return;  // the sorted variant keeps whole warps alive for the shuffles
+  const long long i = live ? (SORTED ? (long long)a.perm[w] : w) : 0;
+  const float qnan = __int_as_float(0x7fc00000);
+  const float px = live ? __ldg(a.pts + i * 3 + 0) : qnan, py = live ? __ldg(a.pts + i * 3 + 1) : qnan,
+              pz = live ? __ldg(a.pts + i * 3 + 2) : qnan;
   const bool finite_in = (fabsf(px) <= a.xmax) && (fabsf(py) <= a.xmax) && (fabsf(pz) <= a.xmax);  // false for NaN
   float g1 = CUDART_INF_F, g2 = CUDART_INF_F;  // best / second best over the big list
   int gi = -1;
@@ -464,8 +531,42 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
   float b1 = g1, b2 = g2;
   int idx = gi, lev_ok = -1;
   double hi1 = CUDART_INF;
-  if (finite_in) {
-    for (int lev = 0; lev < a.grid.nlev; ++lev) {
+  int lev_first = 0;
+  if (SORTED) {
+    // level 0, one cell list per round for all the lanes that sit in that cell (usually the whole warp)
+    const GridLevel& G = a.grid.lev[0];
+    const long long cell = finite_in ? grid_cell(G, px, py, pz) : -1;
+    unsigned todo = __ballot_sync(0xffffffffu, cell >= 0);
+    while (todo) {
+      const int leader = __ffs(todo) - 1;
+      const long long c = __shfl_sync(0xffffffffu, cell, leader);
+      const bool mine = (cell == c);
+      const int e0 = __ldg(G.start + c), e1 = __ldg(G.start + c + 1);
+#pragma unroll 4
+      for (int e = e0; e < e1; ++e) {
+        const int k = __ldg(G.list + e);
+        const float s = score_rec(a.rec, k, px, py, pz);
+        if (mine) {
+          if (s < b1) {
+            b2 = b1;
+            b1 = s;
+            idx = k;
+          } else {
+            b2 = fminf(b2, s);
+          }
+        }
+      }
+      todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+    if (cell >= 0 && idx >= 0) {
+      hi1 = sqrt((double)b1) * (1.0 + kRelEps) + (double)a.alpha;
+      if (hi1 * hi1 <= (double)G.tmax) lev_ok = 0;
+    }
+    lev_first = 1;
+    if (!live) return;
+  }
+  if (finite_in && lev_ok < 0) {
+    for (int lev = lev_first; lev < a.grid.nlev; ++lev) {
       const GridLevel& G = a.grid.lev[lev];
       const long long cell = grid_cell(G, px, py, pz);
       if (cell < 0) continue;
@@ -563,9 +664,24 @@ __global__ void __launch_bounds__(128) assoc_grid_rerank_kernel(const ScanArgs a
   }
 }
 
-cudaError_t launch_scan_grid(const ScanArgs& a, cudaStream_t stream) {
-  const long long grid = (a.M + 255) / 256;
-  assoc_grid_kernel<256><<<(unsigned)grid, 256, 0, stream>>>(a);
+// sort_cnt: ncell0 + 1 ints, sort_perm: M ints — or null for the natural-order kernel
+cudaError_t launch_scan_grid(ScanArgs a, int* sort_cnt, int32_t* sort_perm, cudaStream_t stream, int* launches) {
+  const unsigned grid = (unsigned)((a.M + 255) / 256);
+  const GridLevel& G = a.grid.lev[0];
+  const long long ncell = (long long)G.nx * G.ny * G.nz;
+  if (sort_cnt != nullptr && sort_perm != nullptr && a.M >= 4 * ncell) {
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(sort_cnt, 0, sizeof(int) * (size_t)(ncell + 1), stream)) != cudaSuccess) return e;
+    grid_hist_kernel<<<grid, 256, 0, stream>>>(a, sort_cnt);
+    excl_scan_kernel<<<1, 1024, 0, stream>>>(sort_cnt, (int)(ncell + 1));
+    grid_scatter_kernel<<<grid, 256, 0, stream>>>(a, sort_cnt, sort_perm);
+    a.perm = sort_perm;
+    assoc_grid_kernel<256, true><<<grid, 256, 0, stream>>>(a);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+  }
+  a.perm = nullptr;
+  assoc_grid_kernel<256, false><<<grid, 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
 cudaError_t launch_rerank_grid(const ScanArgs& a, cudaStream_t stream) {
@@ -1003,7 +1119,8 @@ cudaError_t launch_scan_t(const ScanArgs& a, cudaStream_t stream) {
 // flag buffers hold M entries.  Returns the number of kernels launched through *launches.
 cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, double gate, int32_t* d_assign,
                              float* d_d2, int* d_flag_count, int32_t* d_flag_idx, float* d_flag_thr, int variant,
-                             cudaStream_t stream, int* launches, cudaEvent_t ev_between, int* used_tc) {
+                             cudaStream_t stream, int* launches, cudaEvent_t ev_between, int* used_tc, int* d_sort_cnt,
+                             int32_t* d_sort_perm) {
   ScanArgs a;
   a.scan = m.scan;
   a.mean = m.mean;
@@ -1027,6 +1144,8 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
   a.ga_thr = d_flag_thr;
   a.grid = m.grid;
   a.rec = reinterpret_cast<const float4*>(m.rec);
+  a.perm = nullptr;
+  int extra_launches = 0;
   a.tc_table = m.tc_table;
   a.cen[0] = m.tc_centre[0]; a.cen[1] = m.tc_centre[1]; a.cen[2] = m.tc_centre[2];
   {
@@ -1055,7 +1174,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
   const bool use_tc = !use_grid && tc_possible && (variant == 16 || (variant == 0 && kTcAutoDefault && M >= 148LL * 4 * kTcLm));
   if (used_tc) *used_tc = use_grid ? 2 : (use_tc ? 1 : 0);
   if (use_grid) {
-    if ((e = launch_scan_grid(a, stream)) != cudaSuccess) return e;
+    if ((e = launch_scan_grid(a, d_sort_cnt, d_sort_perm, stream, &extra_launches)) != cudaSuccess) return e;
     if (ev_between != nullptr && (e = cudaEventRecord(ev_between, stream)) != cudaSuccess) return e;
     ev_between = nullptr;
     if ((e = launch_rerank_grid(a, stream)) != cudaSuccess) return e;
@@ -1095,7 +1214,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
     const unsigned grid = (unsigned)(max_ctas < 148 * 4 ? max_ctas : 148 * 4);
     assoc_rerank_kernel<4, 128><<<grid, 128, smem, stream>>>(a);
   }
-  if (launches) *launches = use_grid ? 3 : 2;
+  if (launches) *launches = (use_grid ? 3 : 2) + extra_launches;
   return cudaGetLastError();
 }
 

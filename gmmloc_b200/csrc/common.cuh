@@ -103,7 +103,9 @@ cudaError_t launch_bh_neighbors(const MapDev& m, double thresh, int* d_counts, c
                                 double* d_dist, cudaStream_t stream);
 cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, double gate, int32_t* d_assign,
                              float* d_d2, int* d_flag_count, int32_t* d_flag_idx, float* d_flag_thr, int variant,
-                             cudaStream_t stream, int* launches, cudaEvent_t ev_between = nullptr, int* used_tc = nullptr);
+                             cudaStream_t stream, int* launches, cudaEvent_t ev_between = nullptr, int* used_tc = nullptr,
+                             int* d_sort_cnt = nullptr, int32_t* d_sort_perm = nullptr);  // scratch of the cell-sorted grid scan:
+                                                                                          // cells(level 0) + 1 ints, M ints
 struct FrameArgs {
   const double* mean;       // map constants (fp64)
   const double* cov_inv;
