@@ -127,7 +127,7 @@ struct ScanArgs {
   const float4* rec;
   int* ga_count;
   int32_t* ga_idx;
-  float* ga_thr;   // sign bit = grid level of the re-rank
+  float* ga_thr;
   const int32_t* perm;  // landmark order of the cell-sorted grid scan (null: natural order)
   // tensor-core pruning scan only
   const uint16_t* tc_table;
@@ -616,13 +616,13 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
     if ((double)thr < t2) thr = nextafterf(thr, CUDART_INF_F);
     // every component with score32 <= thr has a true distance <= hit: the grid re-rank needs them all listed
     const double hit = sqrt((double)thr) * (1.0 + kRelEps) + (double)a.alpha;
-    for (int lev = max(lev_ok, 0); lev < a.grid.nlev && lev_rr < 0; ++lev)
+    for (int lev = 0; lev < a.grid.nlev && lev_rr < 0; ++lev)
       if (hit * hit <= (double)a.grid.lev[lev].tmax && grid_cell(a.grid.lev[lev], px, py, pz) >= 0) lev_rr = lev;
   }
   if (lev_rr >= 0) {
     const int pos = atomicAdd(a.ga_count, 1);
     a.ga_idx[pos] = (int32_t)i;
-    a.ga_thr[pos] = lev_rr ? -thr : thr;
+    a.ga_thr[pos] = thr;
   } else {
     const int pos = atomicAdd(a.flag_count, 1);
     a.flag_idx[pos] = (int32_t)i;
@@ -636,10 +636,13 @@ __global__ void __launch_bounds__(128) assoc_grid_rerank_kernel(const ScanArgs a
   const int n = *a.ga_count;
   for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
     const long long i = a.ga_idx[w];
-    const float t = a.ga_thr[w];
-    const int lev = signbit(t) ? 1 : 0;
-    const float thr = fabsf(t);
+    const float thr = a.ga_thr[w];
     const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
+    // first level whose lists hold every component with score32 <= thr (K1-G made sure one exists)
+    const double hit = sqrt((double)thr) * (1.0 + kRelEps) + (double)a.alpha;
+    int lev = a.grid.nlev - 1;
+    for (int l = a.grid.nlev - 1; l >= 0; --l)
+      if (hit * hit <= (double)a.grid.lev[l].tmax && grid_cell(a.grid.lev[l], px, py, pz) >= 0) lev = l;
     const GridLevel& G = a.grid.lev[lev];
     const long long cell = grid_cell(G, px, py, pz);
     double best = CUDART_INF;

@@ -225,7 +225,7 @@ cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3]) 
   int nlev = 0;
   for (int l = 0; l < kGridLevels; ++l) {
     LevelBuild L;
-    L.h = h0 * (l == 0 ? 1.0 : 2.0);
+    L.h = h0 * (double)(1 << l);
     long long ncell;
     for (;;) {
       // the device computes the cell index in fp32 from (float)lo and (float)(1/h): build with exactly those values
