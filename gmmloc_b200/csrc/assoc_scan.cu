@@ -129,6 +129,8 @@ struct ScanArgs {
   int32_t* ga_idx;
   float* ga_thr;
   const int32_t* perm;  // landmark order of the cell-sorted grid scan (null: natural order)
+  int rerank_two_pass;  // K2: first find the fp32 minimum over all components, then re-rank inside ITS radius (the
+                        // thresholds of the grid path come from a cell-list candidate that may be far from the winner)
   // tensor-core pruning scan only
   const uint16_t* tc_table;
   float cen[3];
@@ -314,8 +316,10 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
   int g = 0;  // tiles consumed so far by this CTA (stage = g % kStages, parity = (g / kStages) & 1)
   for (long long base = (long long)blockIdx.x * per; base < nflag; base += (long long)gridDim.x * per) {
     if (tid == 0) {
-      for (int t = 0; t < kStages && t < ntiles; ++t) {
-        const int st = (g + t) % kStages;
+      const int total0 = a.rerank_two_pass ? 2 * ntiles : ntiles;
+      for (int q = 0; q < kStages && q < total0; ++q) {
+        const int st = (g + q) % kStages;
+        const int t = q % ntiles;
         const int ncomp = min(kTileComps, a.Kpad - t * kTileComps);
         const uint32_t bytes = (uint32_t)ncomp * kScanFloats * 4u;
         mbar_expect_tx(&full[st], bytes);
@@ -327,18 +331,21 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
     double best[P];
     int bi[P];
     long long pi[P];
+    bool finite_pt[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       const long long w = base + (long long)p * THREADS + tid;
       float x0 = 0.f, x1 = 0.f, x2 = 0.f;
       pi[p] = -1;
       thr[p] = -1.f;  // nothing passes: idle slot
+      finite_pt[p] = false;
       if (w < nflag) {
         pi[p] = a.flag_idx[w];
         thr[p] = a.flag_thr[w];
         x0 = __ldg(a.pts + pi[p] * 3 + 0);
         x1 = __ldg(a.pts + pi[p] * 3 + 1);
         x2 = __ldg(a.pts + pi[p] * 3 + 2);
+        finite_pt[p] = (fabsf(x0) <= a.xmax) && (fabsf(x1) <= a.xmax) && (fabsf(x2) <= a.xmax);  // alpha holds inside the box only
       }
       X0[p] = pack2(x0, x0);
       X1[p] = pack2(x1, x1);
@@ -346,9 +353,29 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
       best[p] = CUDART_INF;  // stands for numeric_limits<double>::max(): any finite d2 is smaller
       bi[p] = -1;
     }
-    for (int t = 0; t < ntiles; ++t) {
-      const int stage = (g + t) % kStages;
-      mbar_wait(&full[stage], (uint32_t)(((g + t) / kStages) & 1));
+    // one or two passes over the table: tile tt of the sequence is table tile tt % ntiles
+    const int total = a.rerank_two_pass ? 2 * ntiles : ntiles;
+    float fmin32[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) fmin32[p] = CUDART_INF_F;
+    for (int tt = 0; tt < total; ++tt) {
+      const int t = tt % ntiles;
+      const bool first_of_two = a.rerank_two_pass && tt < ntiles;
+      if (a.rerank_two_pass && tt == ntiles) {
+        // the fp32 minimum over ALL components bounds the winner's true distance: shrink the radius to it
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          if (pi[p] >= 0 && fmin32[p] < CUDART_INF_F && thr[p] == thr[p]) {
+            const double rt = (sqrt((double)fmin32[p]) * (1.0 + kRelEps) + 2.0 * (double)a.alpha) / (1.0 - kRelEps);
+            const double t2 = rt * rt;
+            float tn = (float)t2;
+            if ((double)tn < t2) tn = nextafterf(tn, CUDART_INF_F);
+            if (finite_pt[p]) thr[p] = fminf(thr[p], tn);
+          }
+        }
+      }
+      const int stage = (g + tt) % kStages;
+      mbar_wait(&full[stage], (uint32_t)(((g + tt) / kStages) & 1));
       const float* tf = tiles + (size_t)stage * kTileFloats;
       const ulonglong2* sp = reinterpret_cast<const ulonglong2*>(tf);
       const int nchunks = min(kTileComps, a.Kpad - t * kTileComps) / kChunk;
@@ -375,6 +402,11 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
             mch[p] = fminf(fminf(mch[p], s2), s3);
           }
         }
+        if (first_of_two) {
+#pragma unroll
+          for (int p = 0; p < P; ++p) fmin32[p] = fminf(fmin32[p], mch[p]);
+          continue;
+        }
 #pragma unroll
         for (int p = 0; p < P; ++p) {
           if (pi[p] >= 0 && !(mch[p] > thr[p])) {  // rare: a candidate (or a non-finite landmark) in this chunk
@@ -399,15 +431,15 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
         }
       }
       __syncthreads();  // every warp is done with this stage
-      if (tid == 0 && t + kStages < ntiles) {
-        const int tn = t + kStages;
+      if (tid == 0 && tt + kStages < total) {
+        const int tn = (tt + kStages) % ntiles;
         const int ncomp = min(kTileComps, a.Kpad - tn * kTileComps);
         const uint32_t bytes = (uint32_t)ncomp * kScanFloats * 4u;
         mbar_expect_tx(&full[stage], bytes);
         tma_bulk_g2s(tiles + (size_t)stage * kTileFloats, a.scan + (size_t)tn * kTileFloats, bytes, &full[stage]);
       }
     }
-    g += ntiles;
+    g += total;
 #pragma unroll
     for (int p = 0; p < P; ++p) {
       if (pi[p] < 0) continue;
@@ -1148,6 +1180,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
   a.grid = m.grid;
   a.rec = reinterpret_cast<const float4*>(m.rec);
   a.perm = nullptr;
+  a.rerank_two_pass = 0;
   int extra_launches = 0;
   a.tc_table = m.tc_table;
   a.cen[0] = m.tc_centre[0]; a.cen[1] = m.tc_centre[1]; a.cen[2] = m.tc_centre[2];
@@ -1181,6 +1214,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
     if (ev_between != nullptr && (e = cudaEventRecord(ev_between, stream)) != cudaSuccess) return e;
     ev_between = nullptr;
     if ((e = launch_rerank_grid(a, stream)) != cudaSuccess) return e;
+    a.rerank_two_pass = 1;
   }
   if (use_tc) {
     if ((e = launch_scan_tc(a, stream)) != cudaSuccess) return e;

@@ -198,7 +198,7 @@ cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3]) 
     vol *= ext[i];
   }
   const double h0 = env_double("GMMLOC_GRID_H", std::fmin(std::fmax(0.75 * std::cbrt(vol / m.K), 0.05), 4.0));
-  const double tmax[kGridLevels] = {env_double("GMMLOC_GRID_TMAX0", 36.0), env_double("GMMLOC_GRID_TMAX1", 196.0)};
+  const double tmax[kGridLevels] = {env_double("GMMLOC_GRID_TMAX0", 36.0), env_double("GMMLOC_GRID_TMAX1", 400.0)};
   const double margin[kGridLevels] = {1.0, 2.0};
 
   uint8_t* d_isbig = nullptr;
