@@ -203,6 +203,7 @@ struct Lane {
   DevBuf flag_count, flag_idx, flag_thr;  // association work lists
   DevBuf next_frame;                      // frame counter of the persistent frame-GN kernel
   DevBuf sort_cnt, sort_perm;             // cell histogram / landmark order of the cell-sorted grid scan
+  DevBuf gn_store;                        // stored linearisations of the mixed-precision frame GN (per resident CTA)
   DevBuf xws, fws;                        // frame-GN global workspaces (N too large for shared memory)
   int* h_flag_count = nullptr;            // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // scan begin | scan end | re-rank end | GN end
@@ -561,7 +562,7 @@ void gmmloc_ctx_destroy(gmmloc_ctx_t* c) {
   cudaSetDevice(c->device);
   for (Lane& l : c->lanes) {
     if (l.stream) cudaStreamSynchronize(l.stream);
-    DevBuf* lb[] = {&l.flag_count, &l.flag_idx, &l.flag_thr, &l.xws, &l.fws, &l.next_frame, &l.sort_cnt, &l.sort_perm};
+    DevBuf* lb[] = {&l.flag_count, &l.flag_idx, &l.flag_thr, &l.xws, &l.fws, &l.next_frame, &l.sort_cnt, &l.sort_perm, &l.gn_store};
     for (DevBuf* b : lb) b->release();
     if (l.h_flag_count) cudaFreeHost(l.h_flag_count);
     for (cudaEvent_t e : l.ev)
@@ -760,7 +761,9 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
   const int gn_prec = gn_forced >= 0 ? gn_forced : ctx->gn_precision;
   if (gn_prec == GMMLOC_GN_MIXED && map->d.gn_tab != nullptr && (size_t)N <= frame_gn_mixed_limit_points()) {
     CU(ctx->L().next_frame.reserve(sizeof(int)));
-    CU(launch_frame_gn_mixed(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().stream));
+    CU(ctx->L().gn_store.reserve(frame_gn_mixed_scratch_bytes(N)));
+    CU(launch_frame_gn_mixed(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().gn_store.as<float>(), ctx->L().gn_store.cap,
+                             ctx->L().stream));
   } else {
     CU(launch_frame_gn(a, ctx->L().stream));
   }
@@ -812,6 +815,7 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     CU(ln.flag_idx.reserve(sizeof(int32_t) * 2 * mc));
     CU(ln.flag_thr.reserve(sizeof(float) * 2 * mc));
     CU(ln.next_frame.reserve(sizeof(int)));
+    CU(ln.gn_store.reserve(frame_gn_mixed_scratch_bytes(N)));
     if (map->d.grid.nlev > 0) {
       const GridLevel& G0 = map->d.grid.lev[0];
       CU(ln.sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2)));

@@ -287,7 +287,7 @@ __device__ __noinline__ void point_fp64(const FrameArgs& a, const PoseBoth& oldp
 
 template <int kThreads, int kMinB, bool kStoreLin>
 __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
-                                                                         int* __restrict__ counters) {
+                                                                         int* __restrict__ counters, float* __restrict__ store_ws) {
   constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[kWarps][kAcc];
@@ -319,7 +319,10 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const F
   // stored linearisation of the structured free points (classes C_STRP / C_STR): the point step of iteration i is
   // dc = u0 - W (A dxi) with u0 = D^-1 (h + s), W = D^-1 G from the SAME linearisation the pose system of iteration i
   // was accumulated at, so the fused sweep linearises every such point once, not twice
-  float* store = reinterpret_cast<float*>(smem_raw + (((size_t)N * 45 + 15) & ~(size_t)15));
+  // (in shared memory when it fits next to a second resident frame, else in a per-CTA slice of a global scratch
+  // buffer: 2 x 148 CTAs x N x 48 B = 28 MB at C2, L2-resident and reused from frame to frame)
+  float* store = store_ws != nullptr ? store_ws + (size_t)blockIdx.x * N * kStore
+                                     : reinterpret_cast<float*>(smem_raw + (((size_t)N * 45 + 15) & ~(size_t)15));
 
   // persistent CTAs: frames are handed out through a global counter (no tail wave)
   for (;;) {
@@ -850,32 +853,56 @@ size_t frame_gn_mixed_limit_points() {
 }
 
 template <int kThreads, int kMinB, bool kStoreLin>
-static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* d_counters, size_t smem, cudaStream_t stream) {
+static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* d_counters, size_t smem, float* store_ws,
+                                  size_t store_ws_bytes, cudaStream_t stream, bool* fits) {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)) !=
-      cudaSuccess)
+  if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                220 * 1024)) != cudaSuccess)
     return e;
   int per_sm = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, kThreads, smem)) != cudaSuccess)
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, kThreads,
+                                                         smem)) != cudaSuccess)
     return e;
   if (per_sm < 1) per_sm = 1;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(a.B, sms * per_sm);
+  if (store_ws != nullptr && (size_t)grid * a.N * kStore * sizeof(float) > store_ws_bytes) {
+    *fits = false;  // scratch too small for this grid: the caller picks another variant
+    return cudaSuccess;
+  }
+  *fits = true;
   if ((e = cudaMemsetAsync(d_counters, 0, sizeof(int), stream)) != cudaSuccess) return e;
-  frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin><<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters);
+  frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin><<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters, store_ws);
   return cudaGetLastError();
 }
 
-cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, cudaStream_t stream) {
+size_t frame_gn_mixed_scratch_bytes(int N) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (size_t)2 * sms * (size_t)N * kStore * sizeof(float);
+}
+
+cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
+                                  cudaStream_t stream) {
   const size_t base = (((size_t)a.N * 45 + 15) & ~(size_t)15) + 16, with_store = base + (size_t)a.N * 4 * kStore;
   const size_t two = 227 * 1024 / 2 - 8 * 1024;  // per-CTA dynamic budget when two CTAs share an SM
-  // Two frames per SM (256 threads each) hide each other's serial 6x6 solve and barriers: preferred whenever they fit,
-  // with the stored linearisation if that fits too; one CTA of 512 threads (with the store) for larger frames.
-  if (with_store <= two) return launch_mixed_t<256, 2, true>(a, gn_tab, d_counters, with_store, stream);
-  if (base <= two) return launch_mixed_t<256, 2, false>(a, gn_tab, d_counters, base, stream);
-  return launch_mixed_t<512, 1, true>(a, gn_tab, d_counters, with_store, stream);
+  // Two frames per SM (256 threads each) hide each other's serial 6x6 solve and barriers: preferred whenever they fit.
+  // The stored linearisation lives in shared memory if that fits too, else in the L2-resident global scratch; one CTA
+  // of 512 threads (store in shared memory) for frames too large for two residents.
+  bool fits = true;
+  cudaError_t e;
+  if (with_store <= two) return launch_mixed_t<256, 2, true>(a, gn_tab, d_counters, with_store, nullptr, 0, stream, &fits);
+  if (base <= two) {
+    if (store_ws != nullptr) {
+      e = launch_mixed_t<256, 2, true>(a, gn_tab, d_counters, base, store_ws, store_ws_bytes, stream, &fits);
+      if (e != cudaSuccess || fits) return e;
+    }
+    return launch_mixed_t<256, 2, false>(a, gn_tab, d_counters, base, nullptr, 0, stream, &fits);
+  }
+  return launch_mixed_t<512, 1, true>(a, gn_tab, d_counters, with_store, nullptr, 0, stream, &fits);
 }
 
 }  // namespace gmmloc
