@@ -799,7 +799,9 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     const char* v = std::getenv("GMMLOC_E2E_CHUNK");
     return v ? std::atoi(v) : 0;
   }();
-  const int chunk = chunk_env > 0 ? std::min(chunk_env, B) : ((B >= 1024) ? 512 : B);
+  // 896 frames per chunk: measured best on the C2 frame size (tools/probe_e2e.py: 256 -> 463 k, 512 -> 537 k,
+  // 888 -> 574 k, 1024 -> 548 k, 2048 -> 506 k frames/s); PCIe moves 55 GB/s each way on this box
+  const int chunk = chunk_env > 0 ? std::min(chunk_env, B) : ((B >= 1024) ? 896 : B);
   const int nchunks = (B + chunk - 1) / chunk;
   while ((int)ctx->ev_in.size() < nchunks) {
     cudaEvent_t a = nullptr, b = nullptr;
