@@ -104,8 +104,6 @@ __device__ __forceinline__ void load_structure(const FrameArgs& a, const float* 
   sc.c[0] = t0.x; sc.c[1] = t0.y; sc.c[2] = t0.z; sc.c[3] = t0.w; sc.c[4] = t1.x; sc.c[5] = t1.y;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.L1 [%0];" ::"l"(p)); }
-
 // fp64 part of one linearisation: camera-frame point and reprojection residual (rounded to fp32 at the end)
 struct Lin {
   V3f pc;     // camera-frame point
@@ -467,21 +465,6 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const F
       for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
       int bad = 0;  // bit 0: singular block while accumulating, bit 1: while updating
       for (int j = tid; j < N; j += kThreads) {
-        {
-          // The sweep is bound by the L2 latency of the per-point gathers (component mean / structure table, stored
-          // linearisation) with 16 resident warps per SM: pull the NEXT point's lines into L1 while this one computes.
-          const int jn = j + kThreads;
-          if (jn < N) {
-            const int cn = fl[jn] >> 4;
-            if (cn == C_MPLANE || cn == C_STRP || cn == C_STR) {
-              const int kn = sk[jn];
-              prefetch_l1(a.mean + (size_t)kn * 3);
-              prefetch_l1(a.mean + (size_t)kn * 3 + 2);
-              prefetch_l1(gn_tab + (size_t)kn * 8);
-              if (kStoreLin && store_ws != nullptr && do_update && cn >= C_STRP) prefetch_l1(store + (size_t)jn * kStore);
-            }
-          }
-        }
         const uint8_t b = fl[j];
         const int cls = b >> 4;
         const bool stereo = b & F_STEREO;
