@@ -799,9 +799,13 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     const char* v = std::getenv("GMMLOC_E2E_CHUNK");
     return v ? std::atoi(v) : 0;
   }();
-  // 896 frames per chunk: measured best on the C2 frame size (tools/probe_e2e.py: 256 -> 463 k, 512 -> 537 k,
-  // 888 -> 574 k, 1024 -> 548 k, 2048 -> 506 k frames/s); PCIe moves 55 GB/s each way on this box
-  const int chunk = chunk_env > 0 ? std::min(chunk_env, B) : ((B >= 1024) ? 896 : B);
+  // Chunk = 3 frames per resident CTA of the persistent frame-GN kernel (2 CTAs x 148 SMs -> 888 frames on B200): a
+  // chunk that is not a multiple of the resident CTA count leaves most CTAs idle for a whole extra frame.  Measured on
+  // the C2 frame size (tools/probe_e2e.py): 256 -> 463 k, 512 -> 537 k, 888 -> 574 k, 1024 -> 548 k, 2048 -> 506 k
+  // frames/s; PCIe moves 55 GB/s each way on this box.
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int chunk = chunk_env > 0 ? std::min(chunk_env, B) : ((B >= 1024) ? 6 * sms : B);
   const int nchunks = (B + chunk - 1) / chunk;
   while ((int)ctx->ev_in.size() < nchunks) {
     cudaEvent_t a = nullptr, b = nullptr;
