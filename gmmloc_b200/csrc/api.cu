@@ -806,7 +806,19 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const int chunk = chunk_env > 0 ? std::min(chunk_env, B) : ((B >= 1024) ? 6 * sms : B);
-  const int nchunks = (B + chunk - 1) / chunk;
+  // chunk boundaries; the first chunk is a third of the others (one frame per resident CTA) so that the kernels start
+  // after a short H2D instead of a full chunk's
+  std::vector<int> cstart;
+  {
+    int f = 0;
+    const int first = (chunk_env <= 0 && B >= 1024) ? chunk / 3 : chunk;
+    while (f < B) {
+      cstart.push_back(f);
+      f += (f == 0) ? first : chunk;
+    }
+    cstart.push_back(B);
+  }
+  const int nchunks = (int)cstart.size() - 1;
   while ((int)ctx->ev_in.size() < nchunks) {
     cudaEvent_t a = nullptr, b = nullptr;
     CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -836,7 +848,7 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   for (int c = 0; c < nchunks && rc == GMMLOC_OK; ++c) {
     ctx->active = (nchunks > 1) ? (c & 1) : 0;
     cudaStream_t st = ctx->L().stream;
-    const size_t f0 = (size_t)c * chunk, nb = (size_t)std::min(chunk, B - c * chunk), m0 = f0 * N, nm = nb * N;
+    const size_t f0 = (size_t)cstart[c], nb = (size_t)(cstart[c + 1] - cstart[c]), m0 = f0 * N, nm = nb * N;
     CU(cudaMemcpyAsync(ctx->in_pose.as<double>() + 7 * f0, pose0 + 7 * f0, 56 * nb, cudaMemcpyHostToDevice, ctx->h2d));
     if (nm) {
       CU(cudaMemcpyAsync(ctx->in_pts.as<float>() + 3 * m0, pts_w + 3 * m0, 12 * nm, cudaMemcpyHostToDevice, ctx->h2d));
