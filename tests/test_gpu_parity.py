@@ -622,3 +622,13 @@ def test_frames_solve_fp64_kernel_and_mixed_kernel_agree(gpu, oracle, golden_map
     np.testing.assert_allclose(omx["pts"], o64["pts"], atol=1e-5)
     assert int((omx["outlier"] != o64["outlier"]).sum()) == 0
     print(f"mixed vs fp64 frame GN ({case}): {worst[0]:.2e} rad, {worst[1]:.2e} m")
+
+
+@pytest.mark.parametrize("N", [1130, 1131, 2340, 2350, 2354])
+def test_frames_solve_mixed_kernel_variant_boundaries(gpu, oracle, N):
+    """Frame sizes on both sides of every launch-variant switch of the mixed-precision frame GN: stored linearisation
+    in shared memory (N <= 1130) / in the global scratch (<= 2340) / one CTA of 512 threads (<= 2353) / fp64 kernel."""
+    g, ctx = gpu
+    mean, cov = synth.make_map(3000, 0.7, seed=17)
+    fr = synth.make_frames(mean, cov, 2, N, seed=N, mono_frac=0.15)
+    _check_frames(g, ctx, oracle, mean, cov, fr, robust=1)
