@@ -806,18 +806,11 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const int chunk = chunk_env > 0 ? std::min(chunk_env, B) : ((B >= 1024) ? 6 * sms : B);
-  // chunk boundaries; the first chunk is a third of the others (one frame per resident CTA) so that the kernels start
-  // after a short H2D instead of a full chunk's
+  // chunk boundaries (a shorter first chunk was tried: it starts the kernels earlier but leaves a small, inefficient
+  // last chunk — measured slower than uniform chunks)
   std::vector<int> cstart;
-  {
-    int f = 0;
-    const int first = (chunk_env <= 0 && B >= 1024) ? chunk / 3 : chunk;
-    while (f < B) {
-      cstart.push_back(f);
-      f += (f == 0) ? first : chunk;
-    }
-    cstart.push_back(B);
-  }
+  for (int f = 0; f < B; f += chunk) cstart.push_back(f);
+  cstart.push_back(B);
   const int nchunks = (int)cstart.size() - 1;
   while ((int)ctx->ev_in.size() < nchunks) {
     cudaEvent_t a = nullptr, b = nullptr;

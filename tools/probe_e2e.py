@@ -61,7 +61,7 @@ def main():
         b.record()
         torch.cuda.synchronize()
         print(f"{name} pinned 205 MiB: {5 * n / (a.elapsed_time(b) * 1e-3) / 1e9:.1f} GB/s", flush=True)
-    for chunk in (256, 444, 512, 888, 1024, 1332, 2048, 4096):
+    for chunk in [int(x) for x in os.environ.get("PROBE_CHUNKS", "256,444,512,888,1024,1332,2048,4096").split(",")]:
         env = dict(os.environ, GMMLOC_E2E_CHUNK=str(chunk))
         subprocess.run([sys.executable, __file__, str(chunk)], env=env, check=False)
 
