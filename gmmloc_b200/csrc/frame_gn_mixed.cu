@@ -21,6 +21,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "gn_common.cuh"
@@ -30,8 +31,8 @@ namespace gmmloc {
 
 namespace {
 
-// Two instantiations: 256 threads x 2 CTAs per SM while two frames fit in shared memory, else 512 threads x 1 CTA
-// (128 registers per thread either way: 16 resident warps per SM).
+// Instantiations: 192 threads x 2 CTAs per SM while two frames fit in shared memory, else 384 threads x 1 CTA
+// (168 registers per thread, no spills, 12 resident warps per SM).
 constexpr int kAcc = 27;
 constexpr double kFarZ = 6.0;  // metres; cond(G) ~ (z fx / bf)^2 ~ 3e3 at the shipped camera (v1.yaml:5-17)
 // Point classes (bits 4..6 of the per-point flag byte).  The points of a frame are stably sorted by class when the
@@ -54,7 +55,7 @@ enum : int {
                  // any free point beyond kFarZ): fp64 path of frame_gn_kernel
   C_COUNT = 7
 };
-constexpr int kMaxChunks = 10;                        // N <= kMaxChunks * 256
+constexpr int kMaxChunks = 12;                        // histogram stride per class = 8 kMaxChunks >= N / 32 + warps per CTA
 constexpr int kStore = 12;                            // floats of the stored linearisation per point: u0 (3), W (9)
 constexpr int kBytesPerPoint = 24 + 12 + 4 + 2 + 1 + 1 + 1 + 4 * kStore;  // xs, obs, asg, perm, oct, flags, tmp, store
 
@@ -849,7 +850,7 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const F
 
 size_t frame_gn_mixed_limit_points() {
   const size_t by_smem = (size_t)(216 * 1024) / (kBytesPerPoint + 1);
-  return std::min(by_smem, (size_t)kMaxChunks * 256);
+  return std::min(by_smem, (size_t)(8 * kMaxChunks - 12) * 32);
 }
 
 template <int kThreads, int kMinB, bool kStoreLin>
@@ -889,20 +890,22 @@ cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* 
                                   cudaStream_t stream) {
   const size_t base = (((size_t)a.N * 45 + 15) & ~(size_t)15) + 16, with_store = base + (size_t)a.N * 4 * kStore;
   const size_t two = 227 * 1024 / 2 - 8 * 1024;  // per-CTA dynamic budget when two CTAs share an SM
-  // Two frames per SM (256 threads each) hide each other's serial 6x6 solve and barriers: preferred whenever they fit.
+  // Two frames per SM (192 threads each) hide each other's serial 6x6 solve and barriers: preferred whenever they fit.
   // The stored linearisation lives in shared memory if that fits too, else in the L2-resident global scratch; one CTA
-  // of 512 threads (store in shared memory) for frames too large for two residents.
+  // of 384 threads (store in shared memory) for frames too large for two residents.
   bool fits = true;
   cudaError_t e;
-  if (with_store <= two) return launch_mixed_t<256, 2, true>(a, gn_tab, d_counters, with_store, nullptr, 0, stream, &fits);
+  // 192 threads per CTA: 168 registers per thread without spills (256 threads cap at 128 registers and spill ~300 B in
+  // the sweep loop; measured 4.25 ms vs 3.49 ms per 4 096 C2 frames; 160 / 128 threads: 3.78 / 4.12 ms)
+  if (with_store <= two) return launch_mixed_t<192, 2, true>(a, gn_tab, d_counters, with_store, nullptr, 0, stream, &fits);
   if (base <= two) {
     if (store_ws != nullptr) {
-      e = launch_mixed_t<256, 2, true>(a, gn_tab, d_counters, base, store_ws, store_ws_bytes, stream, &fits);
+      e = launch_mixed_t<192, 2, true>(a, gn_tab, d_counters, base, store_ws, store_ws_bytes, stream, &fits);
       if (e != cudaSuccess || fits) return e;
     }
-    return launch_mixed_t<256, 2, false>(a, gn_tab, d_counters, base, nullptr, 0, stream, &fits);
+    return launch_mixed_t<192, 2, false>(a, gn_tab, d_counters, base, nullptr, 0, stream, &fits);
   }
-  return launch_mixed_t<512, 1, true>(a, gn_tab, d_counters, with_store, nullptr, 0, stream, &fits);
+  return launch_mixed_t<384, 1, true>(a, gn_tab, d_counters, with_store, nullptr, 0, stream, &fits);
 }
 
 }  // namespace gmmloc
