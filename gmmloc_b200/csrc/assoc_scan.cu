@@ -539,6 +539,9 @@ __global__ void __launch_bounds__(1024) excl_scan_kernel(int* __restrict__ d, in
 
 template <int THREADS, bool SORTED>
 __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
+  __shared__ float4 stage[SORTED ? THREADS / 32 : 1][32][3];  // one staged record per lane and warp (sorted variant)
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  (void)lane; (void)wrp; (void)stage;
   const long long w = (long long)blockIdx.x * THREADS + threadIdx.x;
   const bool live = w < a.M;
   if (!SORTED && !live) return;  // the sorted variant keeps whole warps alive for the shuffles
@@ -574,19 +577,35 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
       const long long c = __shfl_sync(0xffffffffu, cell, leader);
       const bool mine = (cell == c);
       const int e0 = __ldg(G.start + c), e1 = __ldg(G.start + c + 1);
+      // the list is staged through shared memory 32 components at a time: every lane fetches ONE record (32 gathers in
+      // flight instead of a dependent id -> record chain per component), then all lanes read the staged records with
+      // broadcast LDS.128 and score their own landmark
+      for (int base = e0; base < e1; base += 32) {
+        const int n = min(32, e1 - base);
+        if (lane < n) {
+          const int k = __ldg(G.list + base + lane);
+          const float4 r0 = __ldg(a.rec + 3 * (size_t)k), r1 = __ldg(a.rec + 3 * (size_t)k + 1);
+          const float r2 = __ldg(reinterpret_cast<const float*>(a.rec + 3 * (size_t)k + 2));
+          stage[wrp][lane][0] = r0;
+          stage[wrp][lane][1] = r1;
+          stage[wrp][lane][2] = make_float4(r2, __int_as_float(k), 0.f, 0.f);
+        }
+        __syncwarp();
 #pragma unroll 4
-      for (int e = e0; e < e1; ++e) {
-        const int k = __ldg(G.list + e);
-        const float s = score_rec(a.rec, k, px, py, pz);
-        if (mine) {
-          if (s < b1) {
-            b2 = b1;
-            b1 = s;
-            idx = k;
-          } else {
-            b2 = fminf(b2, s);
+        for (int q = 0; q < n; ++q) {
+          const float4 r0 = stage[wrp][q][0], r1 = stage[wrp][q][1], r2 = stage[wrp][q][2];
+          const float s = score32(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, px, py, pz);
+          if (mine) {
+            if (s < b1) {
+              b2 = b1;
+              b1 = s;
+              idx = __float_as_int(r2.y);
+            } else {
+              b2 = fminf(b2, s);
+            }
           }
         }
+        __syncwarp();
       }
       todo &= ~__ballot_sync(0xffffffffu, mine);
     }
