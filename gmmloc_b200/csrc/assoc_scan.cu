@@ -684,8 +684,12 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
 // K2-G: exact re-rank of list A over the landmark's cell list (ascending ids; the big list interleaves, hence the
 // lexicographic (d2, id) minimum = the reference's strict '<' on an ascending scan, gmmloc_opt.cpp:209-217).
 __global__ void __launch_bounds__(128) assoc_grid_rerank_kernel(const ScanArgs a) {
+  // one WARP per flagged landmark: the lanes split the cell list (a thread per landmark leaves the kernel waiting for
+  // the few landmarks with a long level-1 list: 500 dependent gathers in one thread)
   const int n = *a.ga_count;
-  for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n; w += gridDim.x * blockDim.x) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += nwarps) {
     const long long i = a.ga_idx[w];
     const float thr = a.ga_thr[w];
     const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
@@ -700,7 +704,7 @@ __global__ void __launch_bounds__(128) assoc_grid_rerank_kernel(const ScanArgs a
     int bi = -1;
     const int e0 = __ldg(G.start + cell), e1 = __ldg(G.start + cell + 1);
     const int nl = e1 - e0;
-    for (int e = 0; e < nl + a.grid.nbig; ++e) {
+    for (int e = lane; e < nl + a.grid.nbig; e += 32) {
       const int k = e < nl ? __ldg(G.list + e0 + e) : __ldg(a.grid.big + (e - nl));
       const float s = score_rec(a.rec, k, px, py, pz);
       if (!(s > thr)) {
@@ -711,10 +715,22 @@ __global__ void __launch_bounds__(128) assoc_grid_rerank_kernel(const ScanArgs a
         }
       }
     }
-    int idx = bi;
-    if (a.gate > 0.0 && idx >= 0 && best > a.gate) idx = -1;
-    a.assign[i] = idx;
-    if (a.d2 != nullptr) a.d2[i] = (bi >= 0) ? (float)best : CUDART_INF_F;
+    // lexicographic (d2, id) minimum over the lanes
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int ok = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ok >= 0 && (bi < 0 || ob < best || (ob == best && ok < bi))) {
+        best = ob;
+        bi = ok;
+      }
+    }
+    if (lane == 0) {
+      int idx = bi;
+      if (a.gate > 0.0 && idx >= 0 && best > a.gate) idx = -1;
+      a.assign[i] = idx;
+      if (a.d2 != nullptr) a.d2[i] = (bi >= 0) ? (float)best : CUDART_INF_F;
+    }
   }
 }
 
