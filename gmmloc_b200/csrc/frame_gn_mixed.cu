@@ -55,9 +55,9 @@ enum : int {
                  // any free point beyond kFarZ): fp64 path of frame_gn_kernel
   C_COUNT = 7
 };
-constexpr int kMaxChunks = 12;                        // histogram stride per class = 8 kMaxChunks >= N / 32 + warps per CTA
+constexpr int kMaxChunks = 25;                        // histogram stride per class = 8 kMaxChunks >= N / 32 + warps per CTA
+constexpr int kScratchPerPoint = 4 * 12 + 8;          // global scratch per point and resident CTA: store 48 B, aux 7 B (+1)
 constexpr int kStore = 12;                            // floats of the stored linearisation per point: u0 (3), W (9)
-constexpr int kBytesPerPoint = 24 + 12 + 4 + 2 + 1 + 1 + 1 + 4 * kStore;  // xs, obs, asg, perm, oct, flags, tmp, store
 
 
 struct V3f {
@@ -288,7 +288,8 @@ __device__ __noinline__ void point_fp64(const FrameArgs& a, const PoseBoth& oldp
 
 template <int kThreads, int kMinB, bool kStoreLin>
 __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
-                                                                         int* __restrict__ counters, float* __restrict__ store_ws) {
+                                                                         int* __restrict__ counters, float* __restrict__ store_ws,
+                                                                         int aux_global) {
   constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[kWarps][kAcc];
@@ -312,18 +313,24 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const F
   // per-frame state, class-sorted position j: landmark (fp64), observation, component id, original index, octave, flags
   double* xs = reinterpret_cast<double*>(smem_raw);
   float* so = reinterpret_cast<float*>(xs + (size_t)N * 3);
-  int32_t* sk = reinterpret_cast<int32_t*>(so + (size_t)N * 3);
-  uint16_t* perm = reinterpret_cast<uint16_t*>(sk + N);
-  uint8_t* soct = reinterpret_cast<uint8_t*>(perm + N);
+  uint8_t* soct = reinterpret_cast<uint8_t*>(so + (size_t)N * 3);
   uint8_t* fl = soct + N;
-  uint8_t* tmp = fl + N;  // flags by ORIGINAL index while the frame is being sorted
+  // component id, original index and the flags by ORIGINAL index (used while the frame is being sorted): in shared
+  // memory, or — frames too large for that — behind the stored linearisation in this CTA's slice of the global scratch
+  const size_t slice = (size_t)N * kScratchPerPoint;  // bytes per CTA
+  unsigned char* aux = aux_global ? reinterpret_cast<unsigned char*>(store_ws) + (size_t)blockIdx.x * slice + (size_t)N * 4 * kStore
+                                  : smem_raw + (((size_t)N * 38 + 15) & ~(size_t)15);
+  int32_t* sk = reinterpret_cast<int32_t*>(aux);
+  uint16_t* perm = reinterpret_cast<uint16_t*>(sk + N);
+  uint8_t* tmp = reinterpret_cast<uint8_t*>(perm + N);
   // stored linearisation of the structured free points (classes C_STRP / C_STR): the point step of iteration i is
   // dc = u0 - W (A dxi) with u0 = D^-1 (h + s), W = D^-1 G from the SAME linearisation the pose system of iteration i
   // was accumulated at, so the fused sweep linearises every such point once, not twice
   // (in shared memory when it fits next to a second resident frame, else in a per-CTA slice of a global scratch
   // buffer: 2 x 148 CTAs x N x 48 B = 28 MB at C2, L2-resident and reused from frame to frame)
-  float* store = store_ws != nullptr ? store_ws + (size_t)blockIdx.x * N * kStore
-                                     : reinterpret_cast<float*>(smem_raw + (((size_t)N * 45 + 15) & ~(size_t)15));
+  float* store = store_ws != nullptr
+                     ? reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(store_ws) + (size_t)blockIdx.x * slice)
+                     : reinterpret_cast<float*>(smem_raw + (((size_t)N * 38 + 15) & ~(size_t)15) + (((size_t)N * 7 + 15) & ~(size_t)15));
 
   // persistent CTAs: frames are handed out through a global counter (no tail wave)
   for (;;) {
@@ -848,14 +855,19 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const F
 
 }  // namespace
 
+// shared-memory bytes of one frame: base state (38 B / point), aux arrays (7 B), stored linearisation (48 B)
+static size_t smem_base(int N) { return (((size_t)N * 38 + 15) & ~(size_t)15) + 16; }
+static size_t smem_aux(int N) { return (((size_t)N * 7 + 15) & ~(size_t)15); }
+static size_t smem_store(int N) { return (size_t)N * 4 * kStore; }
+
 size_t frame_gn_mixed_limit_points() {
-  const size_t by_smem = (size_t)(216 * 1024) / (kBytesPerPoint + 1);
+  const size_t by_smem = (size_t)(216 * 1024 - 32) / 38;
   return std::min(by_smem, (size_t)(8 * kMaxChunks - 12) * 32);
 }
 
 template <int kThreads, int kMinB, bool kStoreLin>
 static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* d_counters, size_t smem, float* store_ws,
-                                  size_t store_ws_bytes, cudaStream_t stream, bool* fits) {
+                                  size_t store_ws_bytes, int aux_global, cudaStream_t stream, bool* fits) {
   cudaError_t e;
   if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 220 * 1024)) != cudaSuccess)
@@ -869,13 +881,13 @@ static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(a.B, sms * per_sm);
-  if (store_ws != nullptr && (size_t)grid * a.N * kStore * sizeof(float) > store_ws_bytes) {
+  if (store_ws != nullptr && (size_t)grid * a.N * kScratchPerPoint > store_ws_bytes) {
     *fits = false;  // scratch too small for this grid: the caller picks another variant
     return cudaSuccess;
   }
   *fits = true;
   if ((e = cudaMemsetAsync(d_counters, 0, sizeof(int), stream)) != cudaSuccess) return e;
-  frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin><<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters, store_ws);
+  frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin><<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters, store_ws, aux_global);
   return cudaGetLastError();
 }
 
@@ -883,29 +895,36 @@ size_t frame_gn_mixed_scratch_bytes(int N) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return (size_t)2 * sms * (size_t)N * kStore * sizeof(float);
+  return (size_t)2 * sms * (size_t)N * kScratchPerPoint;
 }
 
 cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
                                   cudaStream_t stream) {
-  const size_t base = (((size_t)a.N * 45 + 15) & ~(size_t)15) + 16, with_store = base + (size_t)a.N * 4 * kStore;
+  const size_t base = smem_base(a.N) + smem_aux(a.N), with_store = base + smem_store(a.N);
   const size_t two = 227 * 1024 / 2 - 8 * 1024;  // per-CTA dynamic budget when two CTAs share an SM
+  const size_t one = 216 * 1024;                 // ... when a CTA has the SM to itself
   // Two frames per SM (192 threads each) hide each other's serial 6x6 solve and barriers: preferred whenever they fit.
-  // The stored linearisation lives in shared memory if that fits too, else in the L2-resident global scratch; one CTA
-  // of 384 threads (store in shared memory) for frames too large for two residents.
-  bool fits = true;
-  cudaError_t e;
+  // The stored linearisation lives in shared memory if that fits too, else in the L2-resident global scratch.  Frames too
+  // large for two residents run one CTA of 384 threads: everything in shared memory up to N = 2 353, beyond that the
+  // stored linearisation and the aux arrays (component id, original index) move to the global scratch (N <= 5 800).
   // 192 threads per CTA: 168 registers per thread without spills (256 threads cap at 128 registers and spill ~300 B in
   // the sweep loop; measured 4.25 ms vs 3.49 ms per 4 096 C2 frames; 160 / 128 threads: 3.78 / 4.12 ms)
-  if (with_store <= two) return launch_mixed_t<192, 2, true>(a, gn_tab, d_counters, with_store, nullptr, 0, stream, &fits);
+  bool fits = true;
+  cudaError_t e;
+  if (with_store <= two) return launch_mixed_t<192, 2, true>(a, gn_tab, d_counters, with_store, nullptr, 0, 0, stream, &fits);
   if (base <= two) {
     if (store_ws != nullptr) {
-      e = launch_mixed_t<192, 2, true>(a, gn_tab, d_counters, base, store_ws, store_ws_bytes, stream, &fits);
+      e = launch_mixed_t<192, 2, true>(a, gn_tab, d_counters, base, store_ws, store_ws_bytes, 0, stream, &fits);
       if (e != cudaSuccess || fits) return e;
     }
-    return launch_mixed_t<192, 2, false>(a, gn_tab, d_counters, base, nullptr, 0, stream, &fits);
+    return launch_mixed_t<192, 2, false>(a, gn_tab, d_counters, base, nullptr, 0, 0, stream, &fits);
   }
-  return launch_mixed_t<384, 1, true>(a, gn_tab, d_counters, with_store, nullptr, 0, stream, &fits);
+  if (with_store <= one) return launch_mixed_t<384, 1, true>(a, gn_tab, d_counters, with_store, nullptr, 0, 0, stream, &fits);
+  if (store_ws != nullptr) {
+    e = launch_mixed_t<384, 1, true>(a, gn_tab, d_counters, smem_base(a.N), store_ws, store_ws_bytes, 1, stream, &fits);
+    if (e != cudaSuccess || fits) return e;
+  }
+  return cudaErrorInvalidValue;  // the caller checks frame_gn_mixed_limit_points() and passes the scratch: not reached
 }
 
 }  // namespace gmmloc

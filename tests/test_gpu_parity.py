@@ -624,10 +624,11 @@ def test_frames_solve_fp64_kernel_and_mixed_kernel_agree(gpu, oracle, golden_map
     print(f"mixed vs fp64 frame GN ({case}): {worst[0]:.2e} rad, {worst[1]:.2e} m")
 
 
-@pytest.mark.parametrize("N", [1130, 1131, 2340, 2350, 2354])
+@pytest.mark.parametrize("N", [1130, 1131, 2340, 2350, 2354, 5000, 5819, 5820])
 def test_frames_solve_mixed_kernel_variant_boundaries(gpu, oracle, N):
-    """Frame sizes on both sides of every launch-variant switch of the mixed-precision frame GN: stored linearisation
-    in shared memory (N <= 1130) / in the global scratch (<= 2340) / one CTA of 512 threads (<= 2353) / fp64 kernel."""
+    """Frame sizes on both sides of every launch-variant switch of the mixed-precision frame GN: two resident frames with
+    the stored linearisation in shared memory / in the global scratch, one CTA of 384 threads with everything in shared
+    memory / with the store and the aux arrays in the global scratch (up to N = 5 819), then the fp64 kernel."""
     g, ctx = gpu
     mean, cov = synth.make_map(3000, 0.7, seed=17)
     fr = synth.make_frames(mean, cov, 2, N, seed=N, mono_frac=0.15)
