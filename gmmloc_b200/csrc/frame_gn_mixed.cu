@@ -33,6 +33,9 @@ namespace {
 
 // Instantiations: 192 threads x 2 CTAs per SM while two frames fit in shared memory, else 384 threads x 1 CTA
 // (168 registers per thread, no spills, 12 resident warps per SM).
+#ifndef GMMLOC_GNM_REVERSE
+#define GMMLOC_GNM_REVERSE 1
+#endif
 constexpr int kAcc = 27;
 constexpr double kFarZ = 6.0;  // metres; cond(G) ~ (z fx / bf)^2 ~ 3e3 at the shipped camera (v1.yaml:5-17)
 // Point classes (bits 4..6 of the per-point flag byte).  The points of a frame are stably sorted by class when the
@@ -472,7 +475,14 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const F
 #pragma unroll
       for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
       int bad = 0;  // bit 0: singular block while accumulating, bit 1: while updating
+      // The class-sorted order runs from the cheap classes (held / plain points) to the expensive ones (structured
+      // points).  Walking it BACKWARDS puts the partial last round of the strided loop (N mod kThreads points: only some
+      // of the warps have one) on the cheap end, so the warps that do have it reach the barrier sooner.
+#if GMMLOC_GNM_REVERSE
+      for (int j = N - 1 - tid; j >= 0; j -= kThreads) {
+#else
       for (int j = tid; j < N; j += kThreads) {
+#endif
         const uint8_t b = fl[j];
         const int cls = b >> 4;
         const bool stereo = b & F_STEREO;
@@ -869,8 +879,10 @@ template <int kThreads, int kMinB, bool kStoreLin>
 static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* d_counters, size_t smem, float* store_ws,
                                   size_t store_ws_bytes, int aux_global, cudaStream_t stream, bool* fits) {
   cudaError_t e;
+  // opt in to exactly what this launch needs: dynamic + the kernel's static shared memory must stay within the 227 KB
+  // per-CTA limit (a blanket 220 KB request fails with the ~8 KB of static state of the 384-thread variant)
   if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                220 * 1024)) != cudaSuccess)
+                                (int)smem)) != cudaSuccess)
     return e;
   int per_sm = 0;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, kThreads,
