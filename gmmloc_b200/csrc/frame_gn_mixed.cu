@@ -33,9 +33,6 @@ namespace {
 
 // Instantiations: 192 threads x 2 CTAs per SM while two frames fit in shared memory, else 384 threads x 1 CTA
 // (168 registers per thread, no spills, 12 resident warps per SM).
-#ifndef GMMLOC_GNM_REVERSE
-#define GMMLOC_GNM_REVERSE 1
-#endif
 constexpr int kAcc = 27;
 constexpr double kFarZ = 6.0;  // metres; cond(G) ~ (z fx / bf)^2 ~ 3e3 at the shipped camera (v1.yaml:5-17)
 // Point classes (bits 4..6 of the per-point flag byte).  The points of a frame are stably sorted by class when the
@@ -61,6 +58,9 @@ enum : int {
 constexpr int kMaxChunks = 25;                        // histogram stride per class = 8 kMaxChunks >= N / 32 + warps per CTA
 constexpr int kScratchPerPoint = 4 * 12 + 8;          // global scratch per point and resident CTA: store 48 B, aux 7 B (+1)
 constexpr int kStore = 12;                            // floats of the stored linearisation per point: u0 (3), W (9)
+// bytes of one resident CTA's slice of the global scratch: a multiple of 16 so that the float4 accesses of the stored
+// linearisation stay aligned for odd N
+__host__ __device__ inline size_t scratch_slice(int N) { return ((size_t)N * kScratchPerPoint + 15) & ~(size_t)15; }
 
 
 struct V3f {
@@ -320,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const F
   uint8_t* fl = soct + N;
   // component id, original index and the flags by ORIGINAL index (used while the frame is being sorted): in shared
   // memory, or — frames too large for that — behind the stored linearisation in this CTA's slice of the global scratch
-  const size_t slice = (size_t)N * kScratchPerPoint;  // bytes per CTA
+  const size_t slice = scratch_slice(N);  // bytes per CTA
   unsigned char* aux = aux_global ? reinterpret_cast<unsigned char*>(store_ws) + (size_t)blockIdx.x * slice + (size_t)N * 4 * kStore
                                   : smem_raw + (((size_t)N * 38 + 15) & ~(size_t)15);
   int32_t* sk = reinterpret_cast<int32_t*>(aux);
@@ -475,14 +475,10 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const F
 #pragma unroll
       for (int i = 0; i < kAcc; ++i) acc[i] = 0.f;
       int bad = 0;  // bit 0: singular block while accumulating, bit 1: while updating
-      // The class-sorted order runs from the cheap classes (held / plain points) to the expensive ones (structured
-      // points).  Walking it BACKWARDS puts the partial last round of the strided loop (N mod kThreads points: only some
-      // of the warps have one) on the cheap end, so the warps that do have it reach the barrier sooner.
-#if GMMLOC_GNM_REVERSE
-      for (int j = N - 1 - tid; j >= 0; j -= kThreads) {
-#else
+      // Measured alternatives to this plain strided walk (C2, 4 096 frames, 3.51 ms): walking the class-sorted order
+      // backwards 3.57 ms; dealing the 32-point chunks to the warps by estimated cost 3.56 ms (the second resident CTA
+      // already absorbs the imbalance); staging the next round's stored linearisation with cp.async 4.17 ms.
       for (int j = tid; j < N; j += kThreads) {
-#endif
         const uint8_t b = fl[j];
         const int cls = b >> 4;
         const bool stereo = b & F_STEREO;
@@ -893,7 +889,7 @@ static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = std::min(a.B, sms * per_sm);
-  if (store_ws != nullptr && (size_t)grid * a.N * kScratchPerPoint > store_ws_bytes) {
+  if (store_ws != nullptr && (size_t)grid * scratch_slice(a.N) > store_ws_bytes) {
     *fits = false;  // scratch too small for this grid: the caller picks another variant
     return cudaSuccess;
   }
@@ -907,14 +903,24 @@ size_t frame_gn_mixed_scratch_bytes(int N) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  return (size_t)2 * sms * (size_t)N * kScratchPerPoint;
+  return (size_t)2 * sms * scratch_slice(N);
 }
 
 cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
                                   cudaStream_t stream) {
   const size_t base = smem_base(a.N) + smem_aux(a.N), with_store = base + smem_store(a.N);
-  const size_t two = 227 * 1024 / 2 - 8 * 1024;  // per-CTA dynamic budget when two CTAs share an SM
-  const size_t one = 216 * 1024;                 // ... when a CTA has the SM to itself
+  // per-CTA dynamic budgets: an SM has 228 KB, every resident CTA costs its static shared memory + 1 KB of system
+  // reserve, and one CTA may opt in to at most 227 KB (static included)
+  static const size_t static192 = [] {
+    cudaFuncAttributes fa;
+    return cudaFuncGetAttributes(&fa, frame_gn_mixed_kernel<192, 2, true>) == cudaSuccess ? fa.sharedSizeBytes : (size_t)8192;
+  }();
+  static const size_t static384 = [] {
+    cudaFuncAttributes fa;
+    return cudaFuncGetAttributes(&fa, frame_gn_mixed_kernel<384, 1, true>) == cudaSuccess ? fa.sharedSizeBytes : (size_t)9728;
+  }();
+  const size_t two = ((228 * 1024 / 2 - 1024 - static192) & ~(size_t)15);  // when two CTAs share an SM
+  const size_t one = std::min<size_t>(216 * 1024, (227 * 1024 - static384) & ~(size_t)15);  // a CTA with the SM to itself
   // Two frames per SM (192 threads each) hide each other's serial 6x6 solve and barriers: preferred whenever they fit.
   // The stored linearisation lives in shared memory if that fits too, else in the L2-resident global scratch.  Frames too
   // large for two residents run one CTA of 384 threads: everything in shared memory up to N = 2 353, beyond that the

@@ -624,11 +624,13 @@ def test_frames_solve_fp64_kernel_and_mixed_kernel_agree(gpu, oracle, golden_map
     print(f"mixed vs fp64 frame GN ({case}): {worst[0]:.2e} rad, {worst[1]:.2e} m")
 
 
-@pytest.mark.parametrize("N", [1130, 1131, 2340, 2350, 2354, 5000, 5819, 5820])
+@pytest.mark.parametrize("N", [1163, 1164, 1999, 2403, 2404, 5001, 5819, 5820])
 def test_frames_solve_mixed_kernel_variant_boundaries(gpu, oracle, N):
     """Frame sizes on both sides of every launch-variant switch of the mixed-precision frame GN: two resident frames with
     the stored linearisation in shared memory / in the global scratch, one CTA of 384 threads with everything in shared
-    memory / with the store and the aux arrays in the global scratch (up to N = 5 819), then the fp64 kernel."""
+    memory / with the store and the aux arrays in the global scratch (up to N = 5 819), then the fp64 kernel.  Switches at
+    1163 | 1164 (store leaves shared memory), 2403 | 2404 (one CTA of 384 threads), 5819 | 5820 (fp64 kernel); odd sizes
+    exercise the 16-byte alignment of the per-CTA scratch slices."""
     g, ctx = gpu
     mean, cov = synth.make_map(3000, 0.7, seed=17)
     fr = synth.make_frames(mean, cov, 2, N, seed=N, mono_frac=0.15)
