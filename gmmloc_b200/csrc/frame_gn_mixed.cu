@@ -33,6 +33,15 @@ namespace {
 
 // Instantiations: 192 threads x 2 CTAs per SM while two frames fit in shared memory, else 384 threads x 1 CTA
 // (168 registers per thread, no spills, 12 resident warps per SM).
+// CTA shape of the two-resident-frames variants: threads per CTA and the register cap that lets two CTAs share an SM
+// (65 536 registers: 2 x 192 x 168 or 2 x 224 x 144)
+#ifndef GMMLOC_GNM_THREADS2
+#define GMMLOC_GNM_THREADS2 192
+#endif
+#ifndef GMMLOC_GNM_MAXREG2
+#define GMMLOC_GNM_MAXREG2 168
+#endif
+constexpr int kThreads2 = GMMLOC_GNM_THREADS2;
 constexpr int kAcc = 27;
 constexpr double kFarZ = 6.0;  // metres; cond(G) ~ (z fx / bf)^2 ~ 3e3 at the shipped camera (v1.yaml:5-17)
 // Point classes (bits 4..6 of the per-point flag byte).  The points of a frame are stably sorted by class when the
@@ -290,7 +299,7 @@ __device__ __noinline__ void point_fp64(const FrameArgs& a, const PoseBoth& oldp
 }
 
 template <int kThreads, int kMinB, bool kStoreLin>
-__global__ void __launch_bounds__(kThreads, kMinB) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
+__global__ void __launch_bounds__(kThreads) __maxnreg__(kMinB == 1 ? 168 : GMMLOC_GNM_MAXREG2) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
                                                                          int* __restrict__ counters, float* __restrict__ store_ws,
                                                                          int aux_global) {
   constexpr int kWarps = kThreads / 32;
@@ -913,7 +922,7 @@ cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* 
   // reserve, and one CTA may opt in to at most 227 KB (static included)
   static const size_t static192 = [] {
     cudaFuncAttributes fa;
-    return cudaFuncGetAttributes(&fa, frame_gn_mixed_kernel<192, 2, true>) == cudaSuccess ? fa.sharedSizeBytes : (size_t)8192;
+    return cudaFuncGetAttributes(&fa, frame_gn_mixed_kernel<kThreads2, 2, true>) == cudaSuccess ? fa.sharedSizeBytes : (size_t)8192;
   }();
   static const size_t static384 = [] {
     cudaFuncAttributes fa;
@@ -929,13 +938,13 @@ cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* 
   // the sweep loop; measured 4.25 ms vs 3.49 ms per 4 096 C2 frames; 160 / 128 threads: 3.78 / 4.12 ms)
   bool fits = true;
   cudaError_t e;
-  if (with_store <= two) return launch_mixed_t<192, 2, true>(a, gn_tab, d_counters, with_store, nullptr, 0, 0, stream, &fits);
+  if (with_store <= two) return launch_mixed_t<kThreads2, 2, true>(a, gn_tab, d_counters, with_store, nullptr, 0, 0, stream, &fits);
   if (base <= two) {
     if (store_ws != nullptr) {
-      e = launch_mixed_t<192, 2, true>(a, gn_tab, d_counters, base, store_ws, store_ws_bytes, 0, stream, &fits);
+      e = launch_mixed_t<kThreads2, 2, true>(a, gn_tab, d_counters, base, store_ws, store_ws_bytes, 0, stream, &fits);
       if (e != cudaSuccess || fits) return e;
     }
-    return launch_mixed_t<192, 2, false>(a, gn_tab, d_counters, base, nullptr, 0, 0, stream, &fits);
+    return launch_mixed_t<kThreads2, 2, false>(a, gn_tab, d_counters, base, nullptr, 0, 0, stream, &fits);
   }
   if (with_store <= one) return launch_mixed_t<384, 1, true>(a, gn_tab, d_counters, with_store, nullptr, 0, 0, stream, &fits);
   if (store_ws != nullptr) {
