@@ -303,8 +303,10 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
 
   const int tid = threadIdx.x;
   const int nflag = *a.flag_count;
-  const int per = THREADS * P;
-  if ((long long)blockIdx.x * per >= nflag) return;
+  // Slot p of CTA b in round r takes the block of THREADS flagged landmarks number (r P + p) gridDim.x + b: a short flag
+  // list is spread over ALL the CTAs of the launch with one active slot each (a CTA pays for its active slots only),
+  // instead of filling the P slots of the first few CTAs while the other SMs idle.
+  if ((long long)blockIdx.x * THREADS >= nflag) return;
   const int ntiles = (a.Kpad + kTileComps - 1) / kTileComps;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
@@ -314,7 +316,10 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
   __syncthreads();
 
   int g = 0;  // tiles consumed so far by this CTA (stage = g % kStages, parity = (g / kStages) & 1)
-  for (long long base = (long long)blockIdx.x * per; base < nflag; base += (long long)gridDim.x * per) {
+  for (long long round0 = 0; (round0 * gridDim.x + blockIdx.x) * THREADS < nflag; round0 += P) {
+    int pact = 0;  // active slots of this CTA in this round (uniform over the CTA)
+#pragma unroll
+    for (int p = 0; p < P; ++p) pact += (((round0 + p) * gridDim.x + blockIdx.x) * THREADS < nflag) ? 1 : 0;
     if (tid == 0) {
       const int total0 = a.rerank_two_pass ? 2 * ntiles : ntiles;
       for (int q = 0; q < kStages && q < total0; ++q) {
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
     bool finite_pt[P];
 #pragma unroll
     for (int p = 0; p < P; ++p) {
-      const long long w = base + (long long)p * THREADS + tid;
+      const long long w = ((round0 + p) * gridDim.x + blockIdx.x) * THREADS + tid;
       float x0 = 0.f, x1 = 0.f, x2 = 0.f;
       pi[p] = -1;
       thr[p] = -1.f;  // nothing passes: idle slot
@@ -395,6 +400,7 @@ __global__ void __launch_bounds__(THREADS) assoc_rerank_kernel(const ScanArgs a)
           }
 #pragma unroll
           for (int p = 0; p < P; ++p) {
+            if (p >= pact) continue;
             float s0, s1, s2, s3;
             unpack2(score2(ua, X0[p], X1[p], X2[p]), s0, s1);
             unpack2(score2(ub, X0[p], X1[p], X2[p]), s2, s3);
@@ -1282,7 +1288,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
       attr_set = true;
     }
     // persistent over the flag list (length known only on the device); no more CTAs than the list can use
-    const long long max_ctas = (M + 511) / 512;
+    const long long max_ctas = (M + 127) / 128;  // one block of 128 landmarks per slot; a CTA has up to 4 slots per round
     const unsigned grid = (unsigned)(max_ctas < 148 * 4 ? max_ctas : 148 * 4);
     assoc_rerank_kernel<4, 128><<<grid, 128, smem, stream>>>(a);
   }

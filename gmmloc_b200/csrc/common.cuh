@@ -32,10 +32,11 @@ constexpr int kTcTileBytes = kTcRows * kTcK * 2; // 6144 B for kChunk = 16
 // ---- association grid (assoc_grid kernels) --------------------------------------------------
 // Exact spatial index of the map for the association: cell c of level l lists every component k whose
 // ellipsoid {x : d2_k(x) <= tmax_l} can touch the cell (conservative separating-axis test at map build), so a
-// landmark that falls into c only has to score list(c): every other component has d2 > tmax_l.  Level 1 is a
-// coarser grid with a larger tmax for the landmarks level 0 cannot decide; what level 1 cannot decide takes the
-// brute-force exact path.  `big` lists the components too large to bin (scored for every landmark).
-constexpr int kGridLevels = 2;
+// landmark that falls into c only has to score list(c): every other component has d2 > tmax_l.  The next levels
+// have a larger tmax (and, the last one, a coarser grid) for the landmarks the level before cannot decide; what the
+// last level cannot decide takes the brute-force exact path.  `big` lists the components too large to bin (scored
+// for every landmark).
+constexpr int kGridLevels = 3;
 struct GridLevel {
   float lo[3] = {0.f, 0.f, 0.f};
   float inv_h = 0.f;

@@ -198,8 +198,21 @@ cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3]) 
     vol *= ext[i];
   }
   const double h0 = env_double("GMMLOC_GRID_H", std::fmin(std::fmax(0.75 * std::cbrt(vol / m.K), 0.05), 4.0));
-  const double tmax[kGridLevels] = {env_double("GMMLOC_GRID_TMAX0", 36.0), env_double("GMMLOC_GRID_TMAX1", 400.0)};
-  const double margin[kGridLevels] = {1.0, 2.0};
+  // Three levels: T = 36 and T = 144 on the fine grid, T = 400 on a grid of twice the cell size.  The middle level is
+  // what the shipped maps need: their planes are millimetres thin, so a stereo depth error of one or two centimetres
+  // puts a third of the landmarks beyond 6 sigma of their component (35 % of the C3 landmarks have a winner with
+  // d2 > 36, 7 % with d2 > 144, 1.3 % with d2 > 400); without it they all walk the long coarse lists.
+  // GMMLOC_GRID_LEVELS=2 builds the fine T = 36 and the coarse T = 400 level only.
+  const int want_levels = (int)env_double("GMMLOC_GRID_LEVELS", (double)kGridLevels) >= kGridLevels ? kGridLevels : 2;
+  double tmax[kGridLevels] = {env_double("GMMLOC_GRID_TMAX0", 36.0), env_double("GMMLOC_GRID_TMAX1", 144.0),
+                              env_double("GMMLOC_GRID_TMAX2", 400.0)};
+  double margin[kGridLevels] = {1.0, 1.0, 2.0};
+  int scale[kGridLevels] = {1, 1, 2};
+  if (want_levels == 2) {
+    tmax[1] = tmax[2];
+    margin[1] = margin[2];
+    scale[1] = scale[2];
+  }
 
   uint8_t* d_isbig = nullptr;
   int* d_misc = nullptr;  // [0] nbig, [1] bad flag
@@ -223,9 +236,9 @@ cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3]) 
 
   const unsigned blocks = (unsigned)(((long long)m.K * 32 + 255) / 256);
   int nlev = 0;
-  for (int l = 0; l < kGridLevels; ++l) {
+  for (int l = 0; l < want_levels; ++l) {
     LevelBuild L;
-    L.h = h0 * (double)(1 << l);
+    L.h = h0 * (double)scale[l];
     long long ncell;
     for (;;) {
       // the device computes the cell index in fp32 from (float)lo and (float)(1/h): build with exactly those values
@@ -271,9 +284,12 @@ cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3]) 
       total += h_cnt[(size_t)c];
       if (total > kMaxEntries) break;
     }
-    if (total > kMaxEntries) break;  // keep the levels built so far
+    if (total > kMaxEntries) {  // this level's lists would be too large: skip it (without level 0 there is no grid)
+      if (l == 0) break;
+      continue;
+    }
     h_start[(size_t)ncell] = (int32_t)total;
-    GridLevel& G = m.grid.lev[l];
+    GridLevel& G = m.grid.lev[nlev];
     if ((e = cudaMalloc((void**)&G.start, sizeof(int32_t) * ((size_t)ncell + 1))) != cudaSuccess) return cleanup(e, false);
     if ((e = cudaMalloc((void**)&G.list, sizeof(int32_t) * (size_t)std::max<long long>(total, 1))) != cudaSuccess)
       return cleanup(e, false);
@@ -294,7 +310,7 @@ cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3]) 
     if ((double)G.tmax > tmax[l]) G.tmax = nextafterf(G.tmax, 0.f);
     G.entries = total;
     if (l == 0) m.grid.nbig = h_misc[0];
-    nlev = l + 1;
+    ++nlev;
   }
   if (nlev == 0) {
     cudaFree(d_big);
