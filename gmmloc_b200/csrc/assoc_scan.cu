@@ -631,6 +631,7 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
       b2 = g2;
       idx = gi;
       const int e0 = __ldg(G.start + cell), e1 = __ldg(G.start + cell + 1);
+#pragma unroll 4
       for (int e = e0; e < e1; ++e) {
         const int k = __ldg(G.list + e);
         const float s = score_rec(a.rec, k, px, py, pz);
@@ -710,14 +711,28 @@ __global__ void __launch_bounds__(128) assoc_grid_rerank_kernel(const ScanArgs a
     int bi = -1;
     const int e0 = __ldg(G.start + cell), e1 = __ldg(G.start + cell + 1);
     const int nl = e1 - e0;
-    for (int e = lane; e < nl + a.grid.nbig; e += 32) {
-      const int k = e < nl ? __ldg(G.list + e0 + e) : __ldg(a.grid.big + (e - nl));
-      const float s = score_rec(a.rec, k, px, py, pz);
-      if (!(s > thr)) {
-        const double d = chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, (double)px, (double)py, (double)pz);
-        if (d < best || (d == best && k < bi)) {
-          best = d;
-          bi = k;
+    // four entries per lane and round: the id -> record gathers of a round are independent and issued back to back (the
+    // coarse lists of the shipped maps hold a thousand entries: one dependent gather chain at a time left the warp idle)
+    const int ntot = nl + a.grid.nbig;
+    for (int e = lane; e < ntot; e += 32 * 4) {
+      int kk[4];
+      float ss[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int ee = e + 32 * u;
+        kk[u] = ee < ntot ? (ee < nl ? __ldg(G.list + e0 + ee) : __ldg(a.grid.big + (ee - nl))) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) ss[u] = kk[u] >= 0 ? score_rec(a.rec, kk[u], px, py, pz) : CUDART_INF_F;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (kk[u] >= 0 && !(ss[u] > thr)) {
+          const int k = kk[u];
+          const double d = chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, (double)px, (double)py, (double)pz);
+          if (d < best || (d == best && k < bi)) {
+            best = d;
+            bi = k;
+          }
         }
       }
     }
