@@ -204,6 +204,7 @@ struct Lane {
   DevBuf next_frame;                      // frame counter of the persistent frame-GN kernel
   DevBuf sort_cnt, sort_perm;             // cell histogram / landmark order of the cell-sorted grid scan
   DevBuf gn_store;                        // stored linearisations of the mixed-precision frame GN (per resident CTA)
+  DevBuf gn_prep;                         // class-sorted frames written by frame_prep_kernel (32 B per point)
   DevBuf xws, fws;                        // frame-GN global workspaces (N too large for shared memory)
   int* h_flag_count = nullptr;            // pinned
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // scan begin | scan end | re-rank end | GN end
@@ -562,7 +563,7 @@ void gmmloc_ctx_destroy(gmmloc_ctx_t* c) {
   cudaSetDevice(c->device);
   for (Lane& l : c->lanes) {
     if (l.stream) cudaStreamSynchronize(l.stream);
-    DevBuf* lb[] = {&l.flag_count, &l.flag_idx, &l.flag_thr, &l.xws, &l.fws, &l.next_frame, &l.sort_cnt, &l.sort_perm, &l.gn_store};
+    DevBuf* lb[] = {&l.flag_count, &l.flag_idx, &l.flag_thr, &l.xws, &l.fws, &l.next_frame, &l.sort_cnt, &l.sort_perm, &l.gn_store, &l.gn_prep};
     for (DevBuf* b : lb) b->release();
     if (l.h_flag_count) cudaFreeHost(l.h_flag_count);
     for (cudaEvent_t e : l.ev)
@@ -762,8 +763,12 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
   if (gn_prec == GMMLOC_GN_MIXED && map->d.gn_tab != nullptr && (size_t)N <= frame_gn_mixed_limit_points()) {
     CU(ctx->L().next_frame.reserve(sizeof(int)));
     CU(ctx->L().gn_store.reserve(frame_gn_mixed_scratch_bytes(N)));
+    const size_t prep_bytes = frame_gn_mixed_prep_bytes(B, N);
+    if (prep_bytes) CU(ctx->L().gn_prep.reserve(prep_bytes));
     CU(launch_frame_gn_mixed(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().gn_store.as<float>(), ctx->L().gn_store.cap,
+                             prep_bytes ? ctx->L().gn_prep.as<unsigned char>() : nullptr, prep_bytes ? ctx->L().gn_prep.cap : 0,
                              ctx->L().stream));
+    if (prep_bytes) ctx->stats.kernel_launches += 1;
   } else {
     CU(launch_frame_gn(a, ctx->L().stream));
   }
@@ -842,6 +847,7 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     CU(ln.flag_thr.reserve(sizeof(float) * 2 * mc));
     CU(ln.next_frame.reserve(sizeof(int)));
     CU(ln.gn_store.reserve(frame_gn_mixed_scratch_bytes(N)));
+    if (frame_gn_mixed_prep_bytes(maxc, N)) CU(ln.gn_prep.reserve(frame_gn_mixed_prep_bytes(maxc, N)));
     if (map->d.grid.nlev > 0) {
       const GridLevel& G0 = map->d.grid.lev[0];
       CU(ln.sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2)));

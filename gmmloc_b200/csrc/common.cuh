@@ -130,9 +130,12 @@ cudaError_t launch_frame_gn(const FrameArgs& a, cudaStream_t stream);
 // mixed-precision twin (frame_gn_mixed.cu): fp64 state / residuals, fp32 Jacobian algebra; persistent CTAs fetch frames
 // through *d_next_frame (zeroed by the launcher on `stream`)
 // store_ws: optional global scratch for the stored linearisation (frame_gn_mixed_scratch_bytes(N) bytes)
+// prep_ws: optional global buffer (frame_gn_mixed_prep_bytes(B, N) bytes) for the class-sorted frames written by
+// frame_prep_kernel; without it the solver kernel classifies and sorts its frames itself
 cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_next_frame, float* store_ws, size_t store_ws_bytes,
-                                  cudaStream_t stream);
+                                  unsigned char* prep_ws, size_t prep_ws_bytes, cudaStream_t stream);
 size_t frame_gn_mixed_scratch_bytes(int N);
+size_t frame_gn_mixed_prep_bytes(int B, int N);  // 0: this batch is classified and sorted inside the solver kernel
 size_t frame_gn_mixed_limit_points();  // largest N the mixed kernel takes (class-sorted frame state in shared memory)
 size_t frame_gn_smem_limit_points();  // largest N whose per-frame state stays in shared memory
 

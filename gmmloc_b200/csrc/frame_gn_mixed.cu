@@ -21,6 +21,7 @@
 #include <math_constants.h>
 
 #include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -298,10 +299,150 @@ __device__ __noinline__ void point_fp64(const FrameArgs& a, const PoseBoth& oldp
   }
 }
 
-template <int kThreads, int kMinB, bool kStoreLin>
+// ---- frame preparation (K3p) ------------------------------------------------------------------------------------
+// Classifies the points of every frame (edge gates at iteration 0, point class) and writes the frame in class-sorted
+// order to a global buffer.  This used to be the first two passes of frame_gn_mixed_kernel, where each chunk of points
+// was a chain of dependent memory round trips (assignment -> degenerate flag -> component constants) on 12 resident
+// warps per SM: 12 % of that kernel's stall samples.  Here the same passes run with one CTA of 256 threads per frame
+// and no register or shared-memory pressure (up to 64 resident warps per SM hide the chains), and the solver starts
+// from a coalesced copy.  Layout of frame f (prep_stride(N) bytes, all arrays in class-sorted order):
+//   [0, 12N) landmarks f32 x 3 | [12N, 24N) observations f32 x 3 | [24N, 28N) component id i32 |
+//   [28N, 30N) original index u16 | [30N, 31N) octave u8 | [31N, 32N) flags u8 (class in bits 4..6)
+__host__ __device__ inline size_t prep_stride(int N) { return ((size_t)N * 32 + 15) & ~(size_t)15; }
+
+constexpr int kPrepThreads = 256;
+__global__ void __launch_bounds__(kPrepThreads) frame_prep_kernel(const FrameArgs a, unsigned char* __restrict__ prep) {
+  constexpr int kWarps = kPrepThreads / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];  // flags by ORIGINAL index while the frame is being sorted
+  __shared__ int s_cnt[C_COUNT * kMaxChunks * 8];
+  __shared__ double s_R[9], s_t[3];
+  uint8_t* tmp = smem_raw;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N;
+  const FrameParamsDev& P = a.prm;
+  const bool pose_free = P.factor_mode != GMMLOC_MODE_POINTS_ONLY;
+  const bool pts_free = P.factor_mode != GMMLOC_MODE_POSE_ONLY;
+  const double view_cos_thresh = cos(78.0 * 3.14159265358979323846 / 180.0);  // gaussian_mixture.cpp:284
+  const int nchunks = (N + kPrepThreads - 1) / kPrepThreads;
+  for (int f = blockIdx.x; f < a.B; f += gridDim.x) {
+    const float* pts = a.pts_w + (size_t)f * N * 3;
+    const float* obs = a.obs + (size_t)f * N * 3;
+    const uint8_t* oct = a.octave + (size_t)f * N;
+    const int32_t* asg = a.assign + (size_t)f * N;
+    unsigned char* pf = prep + (size_t)f * prep_stride(N);
+    float* gp = reinterpret_cast<float*>(pf);
+    float* go = reinterpret_cast<float*>(pf + (size_t)N * 12);
+    int32_t* gk = reinterpret_cast<int32_t*>(pf + (size_t)N * 24);
+    uint16_t* gperm = reinterpret_cast<uint16_t*>(pf + (size_t)N * 28);
+    uint8_t* goct = pf + (size_t)N * 30;
+    uint8_t* gfl = pf + (size_t)N * 31;
+    __syncthreads();  // the previous frame is done with s_R / s_cnt / tmp
+    if (tid == 0) {
+      double q[7];
+      for (int i = 0; i < 7; ++i) q[i] = a.pose0[(size_t)f * 7 + i];
+      quat_normalize(q);
+      quat_to_rot(q, s_R);
+      for (int i = 0; i < 3; ++i) s_t[i] = q[4 + i];
+    }
+    __syncthreads();
+    const double twc0 = -(s_R[0] * s_t[0] + s_R[3] * s_t[1] + s_R[6] * s_t[2]);
+    const double twc1 = -(s_R[1] * s_t[0] + s_R[4] * s_t[1] + s_R[7] * s_t[2]);
+    const double twc2 = -(s_R[2] * s_t[0] + s_R[5] * s_t[1] + s_R[8] * s_t[2]);
+    // pass A: flags and class of every point, class histogram per (chunk, warp)  [same arithmetic as the in-kernel pass]
+    for (int c = 0; c < nchunks; ++c) {
+      const int i = c * kPrepThreads + tid;
+      int cls = -1;
+      if (i < N) {
+        const double x0 = (double)pts[i * 3], x1 = (double)pts[i * 3 + 1], x2 = (double)pts[i * 3 + 2];
+        uint8_t b = (obs[i * 3 + 2] >= 0.0f) ? F_STEREO : 0;
+        const int k = asg[i];
+        if (k >= 0 && pts_free) {
+          if (a.is_deg[k]) {
+            b |= F_DEG;
+            const double* ax = a.axis + (size_t)k * 9;
+            const double* mu = a.mean + (size_t)k * 3;
+            const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
+            if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;
+            const double p0 = mu[0] - twc0, p1 = mu[1] - twc1, p2 = mu[2] - twc2;
+            const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
+            if (view_cos < view_cos_thresh) b &= ~F_STR;
+          } else {
+            if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;
+          }
+        }
+        if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
+        if (!(b & F_FREE)) {
+          cls = pose_free ? C_FIXED : C_OFF;
+        } else {
+          const double pz = s_R[6] * x0 + s_R[7] * x1 + s_R[8] * x2 + s_t[2];
+          if (!(pz < kFarZ)) cls = C_F64;
+          else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_F64;  // a free monocular point always has F_STR
+          else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
+        }
+        tmp[i] = (uint8_t)(b | (cls << 4));
+      }
+#pragma unroll
+      for (int q = 0; q < C_COUNT; ++q) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == q);
+        if (lane == 0) s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] = __popc(m);
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive scan in (class, chunk, warp) order = stable counting-sort offsets
+      int run = 0;
+      for (int q = 0; q < C_COUNT; ++q) {
+        const int n = nchunks * kWarps;
+        for (int b0 = 0; b0 < n; b0 += 32) {
+          const int e = b0 + lane;
+          const int idx = q * (kMaxChunks * 8) + e;
+          const int v = (e < n) ? s_cnt[idx] : 0;
+          int inc = v;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+          }
+          if (e < n) s_cnt[idx] = run + inc - v;
+          run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+      }
+    }
+    __syncthreads();
+    // pass B: scatter the frame into class-sorted order
+    for (int c = 0; c < nchunks; ++c) {
+      const int i = c * kPrepThreads + tid;
+      int cls = -1;
+      uint8_t b = 0;
+      if (i < N) {
+        b = tmp[i];
+        cls = b >> 4;
+      }
+      int j = -1;
+#pragma unroll
+      for (int q = 0; q < C_COUNT; ++q) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == q);
+        if (cls == q) j = s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] + __popc(m & ((1u << lane) - 1u));
+      }
+      if (i < N) {
+        gp[j * 3] = pts[i * 3];
+        gp[j * 3 + 1] = pts[i * 3 + 1];
+        gp[j * 3 + 2] = pts[i * 3 + 2];
+        go[j * 3] = obs[i * 3];
+        go[j * 3 + 1] = obs[i * 3 + 1];
+        go[j * 3 + 2] = obs[i * 3 + 2];
+        gk[j] = asg[i];
+        gperm[j] = (uint16_t)i;
+        goct[j] = oct[i];
+        gfl[j] = b;
+      }
+    }
+  }
+}
+
+template <int kThreads, int kMinB, bool kStoreLin, bool kPrep>
 __global__ void __launch_bounds__(kThreads) __maxnreg__(kMinB == 1 ? 168 : GMMLOC_GNM_MAXREG2) frame_gn_mixed_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
                                                                          int* __restrict__ counters, float* __restrict__ store_ws,
-                                                                         int aux_global) {
+                                                                         int aux_global, const unsigned char* __restrict__ prep) {
   constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ double s_red[kWarps][kAcc];
@@ -309,7 +450,6 @@ __global__ void __launch_bounds__(kThreads) __maxnreg__(kMinB == 1 ? 168 : GMMLO
   __shared__ double s_pose[7], s_dxi[6];
   __shared__ PoseBoth s_new, s_old;  // linearisation points: state sw (accumulate) and state sw-1 (update)
   __shared__ int s_fail1, s_fail2, s_frame;
-  __shared__ int s_cnt[C_COUNT * kMaxChunks * 8];  // class histogram per (class, chunk, warp) -> exclusive offsets
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
@@ -319,8 +459,6 @@ __global__ void __launch_bounds__(kThreads) __maxnreg__(kMinB == 1 ? 168 : GMMLO
   CamF C;
   C.fx = (float)P.fx; C.fy = (float)P.fy; C.bf = (float)P.bf; C.lam = (float)P.ba_lambda2;
   C.d_mono = (float)P.delta_mono; C.d_stereo = (float)P.delta_stereo; C.robust = P.robust;
-  const double view_cos_thresh = cos(78.0 * 3.14159265358979323846 / 180.0);  // gaussian_mixture.cpp:284
-  const int nchunks = (N + kThreads - 1) / kThreads;
 
   // per-frame state, class-sorted position j: landmark (fp64), observation, component id, original index, octave, flags
   double* xs = reinterpret_cast<double*>(smem_raw);
@@ -377,100 +515,129 @@ __global__ void __launch_bounds__(kThreads) __maxnreg__(kMinB == 1 ? 168 : GMMLO
       s_fail2 = 0;
     }
     __syncthreads();
-    const double twc0 = -(s_new.R[0] * s_pose[4] + s_new.R[3] * s_pose[5] + s_new.R[6] * s_pose[6]);
-    const double twc1 = -(s_new.R[1] * s_pose[4] + s_new.R[4] * s_pose[5] + s_new.R[7] * s_pose[6]);
-    const double twc2 = -(s_new.R[2] * s_pose[4] + s_new.R[5] * s_pose[5] + s_new.R[8] * s_pose[6]);
-    // ---- pass A: flags and class of every point (structure-edge gates fixed at iteration 0, in fp64 exactly as
-    // frame_gn_kernel), class histogram per (chunk, warp) ----
-    for (int c = 0; c < nchunks; ++c) {
-      const int i = c * kThreads + tid;
-      int cls = -1;
-      if (i < N) {
-        const double x0 = (double)pts[i * 3], x1 = (double)pts[i * 3 + 1], x2 = (double)pts[i * 3 + 2];
-        uint8_t b = (obs[i * 3 + 2] >= 0.0f) ? F_STEREO : 0;
-        const int k = asg[i];
-        if (k >= 0 && pts_free) {
-          if (a.is_deg[k]) {
-            b |= F_DEG;
-            const double* ax = a.axis + (size_t)k * 9;
-            const double* mu = a.mean + (size_t)k * 3;
-            const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
-            if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;
-            const double p0 = mu[0] - twc0, p1 = mu[1] - twc1, p2 = mu[2] - twc2;
-            const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
-            if (view_cos < view_cos_thresh) b &= ~F_STR;
+    if constexpr (kPrep) {
+      // the frame was classified and class-sorted by frame_prep_kernel: a plain coalesced copy into shared memory (every
+      // load independent of the others) replaces the two load passes, whose chunks were chains of dependent round trips
+      const unsigned char* pf = prep + (size_t)f * prep_stride(N);
+      const float* gp = reinterpret_cast<const float*>(pf);
+      const float* go = reinterpret_cast<const float*>(pf + (size_t)N * 12);
+      const int32_t* gk = reinterpret_cast<const int32_t*>(pf + (size_t)N * 24);
+      const uint16_t* gperm = reinterpret_cast<const uint16_t*>(pf + (size_t)N * 28);
+      const uint8_t* goct = pf + (size_t)N * 30;
+      const uint8_t* gfl = pf + (size_t)N * 31;
+#pragma unroll 4
+      for (int e = tid; e < 3 * N; e += kThreads) {
+        xs[e] = (double)gp[e];
+        so[e] = go[e];
+      }
+#pragma unroll 4
+      for (int j = tid; j < N; j += kThreads) {
+        sk[j] = gk[j];
+        perm[j] = gperm[j];
+        soct[j] = goct[j];
+        fl[j] = gfl[j];
+      }
+      __syncthreads();
+    } else {
+      __shared__ int s_cnt[C_COUNT * kMaxChunks * 8];  // class histogram per (class, chunk, warp) -> exclusive offsets
+      const double view_cos_thresh = cos(78.0 * 3.14159265358979323846 / 180.0);  // gaussian_mixture.cpp:284
+      const int nchunks = (N + kThreads - 1) / kThreads;
+      const double twc0 = -(s_new.R[0] * s_pose[4] + s_new.R[3] * s_pose[5] + s_new.R[6] * s_pose[6]);
+      const double twc1 = -(s_new.R[1] * s_pose[4] + s_new.R[4] * s_pose[5] + s_new.R[7] * s_pose[6]);
+      const double twc2 = -(s_new.R[2] * s_pose[4] + s_new.R[5] * s_pose[5] + s_new.R[8] * s_pose[6]);
+      // ---- pass A: flags and class of every point (structure-edge gates fixed at iteration 0, in fp64 exactly as
+      // frame_gn_kernel), class histogram per (chunk, warp) ----
+      for (int c = 0; c < nchunks; ++c) {
+        const int i = c * kThreads + tid;
+        int cls = -1;
+        if (i < N) {
+          const double x0 = (double)pts[i * 3], x1 = (double)pts[i * 3 + 1], x2 = (double)pts[i * 3 + 2];
+          uint8_t b = (obs[i * 3 + 2] >= 0.0f) ? F_STEREO : 0;
+          const int k = asg[i];
+          if (k >= 0 && pts_free) {
+            if (a.is_deg[k]) {
+              b |= F_DEG;
+              const double* ax = a.axis + (size_t)k * 9;
+              const double* mu = a.mean + (size_t)k * 3;
+              const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
+              if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;
+              const double p0 = mu[0] - twc0, p1 = mu[1] - twc1, p2 = mu[2] - twc2;
+              const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
+              if (view_cos < view_cos_thresh) b &= ~F_STR;
+            } else {
+              if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;
+            }
+          }
+          if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
+          if (!(b & F_FREE)) {
+            cls = pose_free ? C_FIXED : C_OFF;
           } else {
-            if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;
+            const double pz = s_new.R[6] * x0 + s_new.R[7] * x1 + s_new.R[8] * x2 + s_new.t[2];
+            if (!(pz < kFarZ)) cls = C_F64;
+            else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_F64;  // a free monocular point always has F_STR
+            else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
+          }
+          tmp[i] = (uint8_t)(b | (cls << 4));
+        }
+  #pragma unroll
+        for (int q = 0; q < C_COUNT; ++q) {
+          const unsigned m = __ballot_sync(0xffffffffu, cls == q);
+          if (lane == 0) s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] = __popc(m);
+        }
+      }
+      __syncthreads();
+      // exclusive scan of the histogram in (class, chunk, warp) order = stable counting sort offsets (one warp)
+      if (warp == 0) {
+        int run = 0;
+        for (int q = 0; q < C_COUNT; ++q) {
+          const int n = nchunks * kWarps;
+          for (int b0 = 0; b0 < n; b0 += 32) {
+            const int e = b0 + lane;
+            const int idx = q * (kMaxChunks * 8) + e;
+            const int v = (e < n) ? s_cnt[idx] : 0;
+            int inc = v;
+  #pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, inc, off);
+              if (lane >= off) inc += t;
+            }
+            if (e < n) s_cnt[idx] = run + inc - v;
+            run += __shfl_sync(0xffffffffu, inc, 31);
           }
         }
-        if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
-        if (!(b & F_FREE)) {
-          cls = pose_free ? C_FIXED : C_OFF;
-        } else {
-          const double pz = s_new.R[6] * x0 + s_new.R[7] * x1 + s_new.R[8] * x2 + s_new.t[2];
-          if (!(pz < kFarZ)) cls = C_F64;
-          else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_F64;  // a free monocular point always has F_STR
-          else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
+      }
+      __syncthreads();
+      // ---- pass B: scatter the frame into class-sorted shared memory ----
+      for (int c = 0; c < nchunks; ++c) {
+        const int i = c * kThreads + tid;
+        int cls = -1;
+        uint8_t b = 0;
+        if (i < N) {
+          b = tmp[i];
+          cls = b >> 4;
         }
-        tmp[i] = (uint8_t)(b | (cls << 4));
-      }
-#pragma unroll
-      for (int q = 0; q < C_COUNT; ++q) {
-        const unsigned m = __ballot_sync(0xffffffffu, cls == q);
-        if (lane == 0) s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] = __popc(m);
-      }
-    }
-    __syncthreads();
-    // exclusive scan of the histogram in (class, chunk, warp) order = stable counting sort offsets (one warp)
-    if (warp == 0) {
-      int run = 0;
-      for (int q = 0; q < C_COUNT; ++q) {
-        const int n = nchunks * kWarps;
-        for (int b0 = 0; b0 < n; b0 += 32) {
-          const int e = b0 + lane;
-          const int idx = q * (kMaxChunks * 8) + e;
-          const int v = (e < n) ? s_cnt[idx] : 0;
-          int inc = v;
-#pragma unroll
-          for (int off = 1; off < 32; off <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, off);
-            if (lane >= off) inc += t;
-          }
-          if (e < n) s_cnt[idx] = run + inc - v;
-          run += __shfl_sync(0xffffffffu, inc, 31);
+        int j = -1;
+  #pragma unroll
+        for (int q = 0; q < C_COUNT; ++q) {
+          const unsigned m = __ballot_sync(0xffffffffu, cls == q);
+          if (cls == q) j = s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] + __popc(m & ((1u << lane) - 1u));
+        }
+        if (i < N) {
+          xs[j * 3] = (double)pts[i * 3];
+          xs[j * 3 + 1] = (double)pts[i * 3 + 1];
+          xs[j * 3 + 2] = (double)pts[i * 3 + 2];
+          so[j * 3] = obs[i * 3];
+          so[j * 3 + 1] = obs[i * 3 + 1];
+          so[j * 3 + 2] = obs[i * 3 + 2];
+          sk[j] = asg[i];
+          perm[j] = (uint16_t)i;
+          soct[j] = oct[i];
+          fl[j] = b;
         }
       }
+      __syncthreads();
+
     }
-    __syncthreads();
-    // ---- pass B: scatter the frame into class-sorted shared memory ----
-    for (int c = 0; c < nchunks; ++c) {
-      const int i = c * kThreads + tid;
-      int cls = -1;
-      uint8_t b = 0;
-      if (i < N) {
-        b = tmp[i];
-        cls = b >> 4;
-      }
-      int j = -1;
-#pragma unroll
-      for (int q = 0; q < C_COUNT; ++q) {
-        const unsigned m = __ballot_sync(0xffffffffu, cls == q);
-        if (cls == q) j = s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] + __popc(m & ((1u << lane) - 1u));
-      }
-      if (i < N) {
-        xs[j * 3] = (double)pts[i * 3];
-        xs[j * 3 + 1] = (double)pts[i * 3 + 1];
-        xs[j * 3 + 2] = (double)pts[i * 3 + 2];
-        so[j * 3] = obs[i * 3];
-        so[j * 3 + 1] = obs[i * 3 + 1];
-        so[j * 3 + 2] = obs[i * 3 + 2];
-        sk[j] = asg[i];
-        perm[j] = (uint16_t)i;
-        soct[j] = oct[i];
-        fl[j] = b;
-      }
-    }
-    __syncthreads();
 
     const int iters = P.gn_iters;
     const int sweeps = (iters > 0) ? iters + 1 : 0;
@@ -880,17 +1047,17 @@ size_t frame_gn_mixed_limit_points() {
   return std::min(by_smem, (size_t)(8 * kMaxChunks - 12) * 32);
 }
 
-template <int kThreads, int kMinB, bool kStoreLin>
+template <int kThreads, int kMinB, bool kStoreLin, bool kPrep>
 static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* d_counters, size_t smem, float* store_ws,
-                                  size_t store_ws_bytes, int aux_global, cudaStream_t stream, bool* fits) {
+                                  size_t store_ws_bytes, int aux_global, const unsigned char* prep, cudaStream_t stream, bool* fits) {
   cudaError_t e;
   // opt in to exactly what this launch needs: dynamic + the kernel's static shared memory must stay within the 227 KB
   // per-CTA limit (a blanket 220 KB request fails with the ~8 KB of static state of the 384-thread variant)
-  if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin, kPrep>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)smem)) != cudaSuccess)
     return e;
   int per_sm = 0;
-  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin>, kThreads,
+  if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin, kPrep>, kThreads,
                                                          smem)) != cudaSuccess)
     return e;
   if (per_sm < 1) per_sm = 1;
@@ -904,7 +1071,8 @@ static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* 
   }
   *fits = true;
   if ((e = cudaMemsetAsync(d_counters, 0, sizeof(int), stream)) != cudaSuccess) return e;
-  frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin><<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters, store_ws, aux_global);
+  frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin, kPrep><<<grid, kThreads, smem, stream>>>(a, gn_tab, d_counters, store_ws, aux_global,
+                                                                                         prep);
   return cudaGetLastError();
 }
 
@@ -915,43 +1083,75 @@ size_t frame_gn_mixed_scratch_bytes(int N) {
   return (size_t)2 * sms * scratch_slice(N);
 }
 
-cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
-                                  cudaStream_t stream) {
+size_t frame_gn_mixed_prep_bytes(int B, int N) {
+  // GMMLOC_GN_PREP=0 / 1: never / always (A/B runs, tests; read on every call).  Default: batches of at least 2 M points.
+  // Measured on C2: 4 096-frame launches 3.51 -> 3.44 ms (the solver loses its two latency-bound load passes), but the
+  // 888-frame chunks of the pipelined host path get slower (e2e 682 k -> 672 k frames/s): there the extra launch and the
+  // round trip of the sorted frames through HBM cost more than the dependent loads they remove.
+  const char* v = std::getenv("GMMLOC_GN_PREP");
+  const bool off = v != nullptr && v[0] == '0', on = v != nullptr && v[0] == '1';
+  if (off || (!on && (size_t)B * (size_t)N < ((size_t)2 << 20))) return 0;
+  return (size_t)B * prep_stride(N) + 16;
+}
+
+template <bool kPrep>
+static cudaError_t launch_variants(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
+                                   const unsigned char* prep, cudaStream_t stream) {
   const size_t base = smem_base(a.N) + smem_aux(a.N), with_store = base + smem_store(a.N);
   // per-CTA dynamic budgets: an SM has 228 KB, every resident CTA costs its static shared memory + 1 KB of system
   // reserve, and one CTA may opt in to at most 227 KB (static included)
   static const size_t static192 = [] {
     cudaFuncAttributes fa;
-    return cudaFuncGetAttributes(&fa, frame_gn_mixed_kernel<kThreads2, 2, true>) == cudaSuccess ? fa.sharedSizeBytes : (size_t)8192;
+    return cudaFuncGetAttributes(&fa, frame_gn_mixed_kernel<kThreads2, 2, true, kPrep>) == cudaSuccess ? fa.sharedSizeBytes : (size_t)8192;
   }();
   static const size_t static384 = [] {
     cudaFuncAttributes fa;
-    return cudaFuncGetAttributes(&fa, frame_gn_mixed_kernel<384, 1, true>) == cudaSuccess ? fa.sharedSizeBytes : (size_t)9728;
+    return cudaFuncGetAttributes(&fa, frame_gn_mixed_kernel<384, 1, true, kPrep>) == cudaSuccess ? fa.sharedSizeBytes : (size_t)9728;
   }();
   const size_t two = ((228 * 1024 / 2 - 1024 - static192) & ~(size_t)15);  // when two CTAs share an SM
   const size_t one = std::min<size_t>(216 * 1024, (227 * 1024 - static384) & ~(size_t)15);  // a CTA with the SM to itself
   // Two frames per SM (192 threads each) hide each other's serial 6x6 solve and barriers: preferred whenever they fit.
   // The stored linearisation lives in shared memory if that fits too, else in the L2-resident global scratch.  Frames too
-  // large for two residents run one CTA of 384 threads: everything in shared memory up to N = 2 353, beyond that the
-  // stored linearisation and the aux arrays (component id, original index) move to the global scratch (N <= 5 800).
+  // large for two residents run one CTA of 384 threads with the stored linearisation and the aux arrays (component id,
+  // original index) in the global scratch (N <= 5 819).
   // 192 threads per CTA: 168 registers per thread without spills (256 threads cap at 128 registers and spill ~300 B in
   // the sweep loop; measured 4.25 ms vs 3.49 ms per 4 096 C2 frames; 160 / 128 threads: 3.78 / 4.12 ms)
   bool fits = true;
   cudaError_t e;
-  if (with_store <= two) return launch_mixed_t<kThreads2, 2, true>(a, gn_tab, d_counters, with_store, nullptr, 0, 0, stream, &fits);
+  if (with_store <= two)
+    return launch_mixed_t<kThreads2, 2, true, kPrep>(a, gn_tab, d_counters, with_store, nullptr, 0, 0, prep, stream, &fits);
   if (base <= two) {
     if (store_ws != nullptr) {
-      e = launch_mixed_t<kThreads2, 2, true>(a, gn_tab, d_counters, base, store_ws, store_ws_bytes, 0, stream, &fits);
+      e = launch_mixed_t<kThreads2, 2, true, kPrep>(a, gn_tab, d_counters, base, store_ws, store_ws_bytes, 0, prep, stream, &fits);
       if (e != cudaSuccess || fits) return e;
     }
-    return launch_mixed_t<kThreads2, 2, false>(a, gn_tab, d_counters, base, nullptr, 0, 0, stream, &fits);
+    return launch_mixed_t<kThreads2, 2, false, kPrep>(a, gn_tab, d_counters, base, nullptr, 0, 0, prep, stream, &fits);
   }
-  if (with_store <= one) return launch_mixed_t<384, 1, true>(a, gn_tab, d_counters, with_store, nullptr, 0, 0, stream, &fits);
+  if (with_store <= one) return launch_mixed_t<384, 1, true, kPrep>(a, gn_tab, d_counters, with_store, nullptr, 0, 0, prep, stream, &fits);
   if (store_ws != nullptr) {
-    e = launch_mixed_t<384, 1, true>(a, gn_tab, d_counters, smem_base(a.N), store_ws, store_ws_bytes, 1, stream, &fits);
+    e = launch_mixed_t<384, 1, true, kPrep>(a, gn_tab, d_counters, smem_base(a.N), store_ws, store_ws_bytes, 1, prep, stream, &fits);
     if (e != cudaSuccess || fits) return e;
   }
   return cudaErrorInvalidValue;  // the caller checks frame_gn_mixed_limit_points() and passes the scratch: not reached
+}
+
+cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
+                                  unsigned char* prep_ws, size_t prep_ws_bytes, cudaStream_t stream) {
+  const size_t need = (size_t)a.B * prep_stride(a.N);
+  if (prep_ws != nullptr && prep_ws_bytes >= need && need > 0) {
+    // K3p: classify + class-sort every frame into prep_ws, then the solver copies its frames from there
+    unsigned char* prep = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(prep_ws) + 15) & ~(uintptr_t)15);
+    if ((size_t)(prep - prep_ws) + need > prep_ws_bytes) return cudaErrorInvalidValue;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = std::min(a.B, sms * 8);
+    frame_prep_kernel<<<grid, kPrepThreads, (size_t)((a.N + 15) & ~15), stream>>>(a, prep);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_variants<true>(a, gn_tab, d_counters, store_ws, store_ws_bytes, prep, stream);
+  }
+  return launch_variants<false>(a, gn_tab, d_counters, store_ws, store_ws_bytes, nullptr, stream);
 }
 
 }  // namespace gmmloc

@@ -624,14 +624,32 @@ def test_frames_solve_fp64_kernel_and_mixed_kernel_agree(gpu, oracle, golden_map
     print(f"mixed vs fp64 frame GN ({case}): {worst[0]:.2e} rad, {worst[1]:.2e} m")
 
 
-@pytest.mark.parametrize("N", [1163, 1164, 1999, 2403, 2404, 5001, 5819, 5820])
-def test_frames_solve_mixed_kernel_variant_boundaries(gpu, oracle, N):
+@pytest.mark.parametrize("prep", ["1", "0"])
+@pytest.mark.parametrize("N", [1163, 1164, 1223, 1224, 1999, 2403, 2404, 2528, 2529, 5001, 5819, 5820])
+def test_frames_solve_mixed_kernel_variant_boundaries(gpu, oracle, N, prep, monkeypatch):
     """Frame sizes on both sides of every launch-variant switch of the mixed-precision frame GN: two resident frames with
-    the stored linearisation in shared memory / in the global scratch, one CTA of 384 threads with everything in shared
-    memory / with the store and the aux arrays in the global scratch (up to N = 5 819), then the fp64 kernel.  Switches at
-    1163 | 1164 (store leaves shared memory), 2403 | 2404 (one CTA of 384 threads), 5819 | 5820 (fp64 kernel); odd sizes
-    exercise the 16-byte alignment of the per-CTA scratch slices."""
+    the stored linearisation in shared memory / in the global scratch, one CTA of 384 threads with the store and the aux
+    arrays in the global scratch (up to N = 5 819), then the fp64 kernel.  With the frame-preparation kernel (prep = 1,
+    the default) the switches sit at 1223 | 1224 and 2528 | 2529, with the in-kernel sort (GMMLOC_GN_PREP=0) at
+    1163 | 1164 and 2403 | 2404; 5819 | 5820 is the fp64 kernel; odd sizes exercise the 16-byte alignment of the per-CTA
+    scratch slices and of the prepared frames."""
     g, ctx = gpu
+    monkeypatch.setenv("GMMLOC_GN_PREP", prep)
     mean, cov = synth.make_map(3000, 0.7, seed=17)
     fr = synth.make_frames(mean, cov, 2, N, seed=N, mono_frac=0.15)
     _check_frames(g, ctx, oracle, mean, cov, fr, robust=1)
+
+
+def test_frames_solve_prepared_frames_equal_in_kernel_sort(gpu, monkeypatch):
+    """frame_prep_kernel + the copying solver give bit-identical results to the solver that classifies and sorts its frames
+    itself (same stable class sort, same arithmetic), for a batch larger than the preparation grid."""
+    g, ctx = gpu
+    mean, cov = synth.make_map(2000, 0.6, seed=5)
+    fr = synth.make_frames(mean, cov, 1300, 301, seed=9, mono_frac=0.2)
+    m = g.GMM(mean, cov)
+    outs = []
+    for prep in ("1", "0"):
+        monkeypatch.setenv("GMMLOC_GN_PREP", prep)
+        outs.append(ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=g.default_params(robust=1)))
+    for k in ("pose", "pts", "assign", "outlier", "status"):
+        assert np.array_equal(outs[0][k], outs[1][k]), k
