@@ -1,18 +1,34 @@
-import sys; sys.path.insert(0,'/root/repo')
+"""GPU-box helper: a small tour of the hot path for `compute-sanitizer --tool memcheck python tools/memcheck_smoke.py`
+(every launch variant of the mixed frame GN with and without the preparation kernel, odd frame sizes, both association
+kernels with out-of-grid / non-finite landmarks, the pipelined host path)."""
+import os
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 import numpy as np
 import gmmloc_b200 as g
 from gmmloc_b200 import synth
+
 mean, cov = synth.make_map(1500, 0.5)
 m = g.GMM(mean, cov, device=0)
 ctx = g.Context(0)
-for B,N in ((3,500),(2,2000),(40,1200)):
-    fr = synth.make_frames(mean, cov, B, N, seed=B, mono_frac=0.2)
-    out = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
-    print(B,N,out["status"][:3], out["assign"][0,:5])
-pts,_ = synth.make_points_near(mean, cov, 300000, seed=3, spread=2.0)
-pts[::1000]+=50; pts[5::5000]=np.nan
+for prep in ("1", "0"):
+    os.environ["GMMLOC_GN_PREP"] = prep
+    for B, N in ((3, 501), (2, 1999), (2, 2451), (2, 5001), (40, 1201)):
+        fr = synth.make_frames(mean, cov, B, N, seed=B, mono_frac=0.2)
+        out = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=g.default_params(robust=1))
+        print(prep, B, N, out["status"][:3], out["assign"][0, :5], flush=True)
+os.environ.pop("GMMLOC_GN_PREP")
+pts, _ = synth.make_points_near(mean, cov, 300000, seed=3, spread=2.0)
+pts[::1000] += 50
+pts[5::5000] = np.nan
 for kind in (g.capi.ASSOC_GRID, g.capi.ASSOC_FFMA2):
-    ctx.set_assoc_kernel(kind); a,d = ctx.associate(m, pts); print(kind, ctx.last_assoc_kernel(), a[:5])
-fr = synth.make_frames(mean, cov, 1100, 60, seed=9)
-out = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"]); print(out["status"].sum())
+    ctx.set_assoc_kernel(kind)
+    a, d = ctx.associate(m, pts)
+    print(kind, ctx.last_assoc_kernel(), a[:5], flush=True)
+ctx.set_assoc_kernel(g.capi.ASSOC_GRID)
+fr = synth.make_frames(mean, cov, 1100, 61, seed=9)
+out = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
+print(out["status"].sum())
 print("memcheck script done")
