@@ -1,5 +1,5 @@
 """GPU-box helper: a small tour of the hot path for `compute-sanitizer --tool memcheck python tools/memcheck_smoke.py`
-(every launch variant of the mixed frame GN with and without the preparation kernel, odd frame sizes, both association
+(or `--tool racecheck` with MEMCHECK_LIGHT=1; every launch variant of the mixed frame GN with and without the preparation kernel, odd frame sizes, both association
 kernels with out-of-grid / non-finite landmarks, the pipelined host path)."""
 import os
 import sys
@@ -20,7 +20,8 @@ for prep in ("1", "0"):
         out = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=g.default_params(robust=1))
         print(prep, B, N, out["status"][:3], out["assign"][0, :5], flush=True)
 os.environ.pop("GMMLOC_GN_PREP")
-pts, _ = synth.make_points_near(mean, cov, 300000, seed=3, spread=2.0)
+LIGHT = os.environ.get("MEMCHECK_LIGHT") == "1"  # racecheck / initcheck runs: smaller workloads
+pts, _ = synth.make_points_near(mean, cov, 20000 if LIGHT else 300000, seed=3, spread=2.0)
 pts[::1000] += 50
 pts[5::5000] = np.nan
 for kind in (g.capi.ASSOC_GRID, g.capi.ASSOC_FFMA2):
@@ -28,7 +29,7 @@ for kind in (g.capi.ASSOC_GRID, g.capi.ASSOC_FFMA2):
     a, d = ctx.associate(m, pts)
     print(kind, ctx.last_assoc_kernel(), a[:5], flush=True)
 ctx.set_assoc_kernel(g.capi.ASSOC_GRID)
-fr = synth.make_frames(mean, cov, 1100, 61, seed=9)
+fr = synth.make_frames(mean, cov, 300 if LIGHT else 1100, 61, seed=9)
 out = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
 print(out["status"].sum())
 print("memcheck script done")
