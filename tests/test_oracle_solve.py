@@ -181,3 +181,68 @@ def test_optimize_triangulation_vs_numpy(oracle):
         assert res == (not rs > float(np.float32(0.0064)) * 400.0 and not (r1 > th1 or r2 > th2))
         n_ok += res
     assert n_ok > 20
+
+
+def test_world_frame_schur_formulation_equals_camera_frame():
+    """Design note for the next step of the frame GN, pinned numerically.
+
+    The kernels evaluate the per-point Schur complement in the CAMERA frame: G = w P^T P, h = w P^T e,
+    S_c = R S R^T, s_c = -R S (x - mu), D = G + S_c, T = G D^-1, A = [-[p_c]x  I], pose system sum A^T (T S_c) A and
+    sum A^T (h - T (h + s_c)), point step R^T D^-1 (h + s_c - G A xi).  Rotating S into the camera frame is a third of
+    the per-point work and has to be redone every sweep.  In the WORLD frame the structure block is constant:
+    with J = P R, G_w = w J^T J, h_w = w J^T e, s_w = -S (x - mu), D_w = G_w + S, T_w = G_w D_w^-1, A_w = [-[x_w]x  I]
+    the system sum A_w^T (T_w S) A_w, sum A_w^T (h_w - T_w (h_w + s_w)) is the camera-frame one expressed in the
+    world twist xi_w = (R^T omega, R^T (omega x t + upsilon)), because A(p_c) xi = R A_w(x_w) xi_w; the point step is
+    D_w^-1 (h_w + s_w - G_w A_w xi_w) with no rotation at all."""
+    rng = np.random.default_rng(11)
+
+    def skew(v):
+        return np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+
+    fx, fy, bf = 435.2, 435.2, 47.9
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    x, y, z, w_ = q
+    R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w_), 2 * (x * z + y * w_)],
+                  [2 * (x * y + z * w_), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w_)],
+                  [2 * (x * z - y * w_), 2 * (y * z + x * w_), 1 - 2 * (x * x + y * y)]])
+    t = rng.normal(size=3)
+    n = 40
+    pc = np.column_stack([rng.uniform(-1.5, 1.5, n), rng.uniform(-1, 1, n), rng.uniform(0.6, 3.5, n)])
+    xw = (pc - t) @ R  # x_w = R^T (p_c - t)
+    Hc, bc, Hw, bw = np.zeros((6, 6)), np.zeros(6), np.zeros((6, 6)), np.zeros(6)
+    per_point = []
+    for i in range(n):
+        X, Y, Z = pc[i]
+        P = np.array([[fx / Z, 0, -fx * X / Z**2], [0, fy / Z, -fy * Y / Z**2], [fx / Z, 0, -fx * X / Z**2 + bf / Z**2]])
+        e = rng.normal(size=3)
+        wgt = 1.0 / 1.44 ** rng.integers(0, 8)
+        Lm = rng.normal(size=(3, 3))
+        S = Lm @ Lm.T * 50 + np.eye(3)
+        d = rng.normal(size=3) * 0.02
+        # camera frame
+        G, h = wgt * P.T @ P, wgt * P.T @ e
+        Sc, sc = R @ S @ R.T, -R @ S @ d
+        D = G + Sc
+        T = G @ np.linalg.inv(D)
+        A = np.hstack([-skew(pc[i]), np.eye(3)])
+        Hc += A.T @ (T @ Sc) @ A
+        bc += A.T @ (h - T @ (h + sc))
+        # world frame
+        J = P @ R
+        Gw, hw, sw = wgt * J.T @ J, wgt * J.T @ e, -S @ d
+        Dw = Gw + S
+        Tw = Gw @ np.linalg.inv(Dw)
+        Aw = np.hstack([-skew(xw[i]), np.eye(3)])
+        Hw += Aw.T @ (Tw @ S) @ Aw
+        bw += Aw.T @ (hw - Tw @ (hw + sw))
+        per_point.append((G, h, Sc, sc, D, A, Gw, hw, sw, Dw, Aw))
+    xi = np.linalg.solve(Hc, bc)
+    xiw = np.linalg.solve(Hw, bw)
+    om = R @ xiw[:3]
+    up = R @ xiw[3:] - np.cross(om, t)
+    assert np.allclose(np.concatenate([om, up]), xi, rtol=1e-9, atol=1e-12)
+    for (G, h, Sc, sc, D, A, Gw, hw, sw, Dw, Aw) in per_point:
+        dx_c = R.T @ np.linalg.solve(D, h + sc - G @ (A @ xi))
+        dx_w = np.linalg.solve(Dw, hw + sw - Gw @ (Aw @ xiw))
+        assert np.allclose(dx_c, dx_w, rtol=1e-8, atol=1e-12)
