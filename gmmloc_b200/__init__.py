@@ -49,14 +49,18 @@ def _in(a, dtype, shape=None):
 class GMM:
     """Immutable GMM map resident on one GPU (shareable between contexts / host threads)."""
 
-    def __init__(self, mean, cov, deg_eps: float = 1e-4, device: int = 0):
+    def __init__(self, mean, cov, deg_eps: float = 1e-4, device: int = 0, grid: "capi.GridOptions | None" = None):
         mean = _in(mean, np.float64, (-1, 3))
         cov = _in(cov, np.float64, (-1, 9))
         if mean.shape[0] != cov.shape[0]:
             raise ValueError("mean / cov size mismatch")
         h = C.c_void_p()
-        capi.check(capi.lib().gmmloc_map_create(_ptr(mean), _ptr(cov), mean.shape[0], float(deg_eps), int(device),
-                                                C.byref(h)))
+        if grid is None:
+            capi.check(capi.lib().gmmloc_map_create(_ptr(mean), _ptr(cov), mean.shape[0], float(deg_eps), int(device),
+                                                    C.byref(h)))
+        else:  # explicit association-grid tuning (A/B runs): gmmloc_map_create_ex
+            capi.check(capi.lib().gmmloc_map_create_ex(_ptr(mean), _ptr(cov), mean.shape[0], float(deg_eps), int(device),
+                                                       C.byref(grid), C.byref(h)))
         self._h = h
 
     @classmethod
@@ -153,6 +157,20 @@ class Context:
     def set_assoc_kernel(self, kind: int) -> None:
         """capi.ASSOC_AUTO / ASSOC_FFMA2 / ASSOC_TENSOR (tcgen05 pruning scan) / ASSOC_GRID (grid-indexed scan); identical results."""
         capi.check(capi.lib().gmmloc_ctx_set_assoc_kernel(self._h, int(kind)))
+
+    def set_option(self, option: int, value: int) -> None:
+        """capi.OPT_GN_PREP (-1 auto / 0 / 1), capi.OPT_E2E_CHUNK (frames, 0 auto), capi.OPT_E2E_SHORT_FIRST; identical results."""
+        capi.check(capi.lib().gmmloc_ctx_set_option(self._h, int(option), int(value)))
+
+    def queryPoint(self, gmm: "GMM", pts) -> dict:
+        """Batched GMM::queryPoint (gaussian_mixture.cpp:545-576): nearest M (what the reference returns: the
+        Euclid-nearest mean), knn M x 5, min_mdist2 M (the Mahalanobis minimum the reference computes and discards)."""
+        pts = _in(pts, np.float64, (-1, 3))
+        M = pts.shape[0]
+        out = dict(nearest=np.empty(M, np.int32), knn=np.empty((M, 5), np.int32), min_mdist2=np.empty(M))
+        capi.check(capi.lib().gmmloc_map_query_point(self._h, gmm._h, _ptr(pts), M, _ptr(out["nearest"]), _ptr(out["knn"]),
+                                                     _ptr(out["min_mdist2"])))
+        return out
 
     def set_gn_precision(self, precision: int) -> None:
         """capi.GN_MIXED (default: fp64 state / residuals, fp32 Jacobian algebra) or capi.GN_FP64."""
@@ -366,11 +384,12 @@ class Context:
                                                          _ptr(out["vstatus"])))
         return out
 
-    def jointOptimization(self, gmm: GMM, windows, cam: Camera | None = None, params: Params | None = None):
+    def jointOptimization(self, gmm: GMM, windows, cam: Camera | None = None, params: Params | None = None, stop=None):
         """Batched Localization::jointOptimization (local BA, 3-stage LM; localization_opt.cpp:456-925).
         `windows`: list of dicts with pose P x 7, fixed P, pts L x 3, assoc L, obs_pt / obs_kf E (window-local,
         obs_pt non-decreasing), obs E x 3, octave E and optionally prior_idx.  Returns one dict per window:
-        pose, pts, obs_outlier, assoc_cleared, iters (3), status."""
+        pose, pts, obs_outlier, assoc_cleared, iters (3), status.  `stop`: the reference's pbStopFlag — an int, or a
+        one-element int32 numpy array another thread may set while the call runs (see gmmloc_local_ba)."""
         cam = cam or v1_camera()
         params = params or default_params()
         B = len(windows)
@@ -390,10 +409,12 @@ class Context:
         cleared = np.zeros(len(pts), np.uint8)
         iters = np.zeros((B, 3), np.int32)
         status = np.zeros(B, np.int32)
+        if stop is not None and not isinstance(stop, np.ndarray):
+            stop = np.array([int(stop)], np.int32)
         capi.check(capi.lib().gmmloc_local_ba(self._h, gmm._h, C.byref(cam), C.byref(params), B, _ptr(pose_ptr), _ptr(pose),
                                               _ptr(fixed), _ptr(prior), _ptr(pt_ptr), _ptr(pts), _ptr(assoc), _ptr(obs_ptr),
                                               _ptr(obs_pt), _ptr(obs_kf), _ptr(obs), _ptr(octave), _ptr(outl), _ptr(cleared),
-                                              _ptr(iters), _ptr(status)))
+                                              _ptr(iters), _ptr(status), _ptr(stop)))
         out = []
         for b in range(B):
             out.append(dict(pose=pose[pose_ptr[b]:pose_ptr[b + 1]], pts=pts[pt_ptr[b]:pt_ptr[b + 1]],

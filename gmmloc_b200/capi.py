@@ -17,6 +17,12 @@ FRAME_NUMERIC = 1
 VIEW_OVERFLOW = 1
 ASSOC_AUTO, ASSOC_FFMA2, ASSOC_TENSOR, ASSOC_GRID = 0, 1, 2, 3
 GN_FP64, GN_MIXED = 0, 1
+OPT_GN_PREP, OPT_E2E_CHUNK, OPT_E2E_SHORT_FIRST = 0, 1, 2
+
+
+class GridOptions(C.Structure):
+    """gmmloc_grid_options_t (gmmloc_map_create_ex)."""
+    _fields_ = [("enable", C.c_int32), ("levels", C.c_int32), ("cell_size", C.c_double), ("tmax", C.c_double * 3)]
 
 
 class Camera(C.Structure):
@@ -52,6 +58,9 @@ SYMBOLS = {
     "gmmloc_default_params": (None, [C.POINTER(Params)]),
     "gmmloc_sigma2_inv": (C.c_float, [_i]),
     "gmmloc_map_create": (_i, [_vp, _vp, _i, _d, _i, C.POINTER(_vp)]),
+    "gmmloc_map_create_ex": (_i, [_vp, _vp, _i, _d, _i, _vp, C.POINTER(_vp)]),
+    "gmmloc_map_query_point": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "gmmloc_ctx_set_option": (_i, [_vp, _i, _i64]),
     "gmmloc_map_load_gmm": (_i, [C.c_char_p, _d, _i, C.POINTER(_vp)]),
     "gmmloc_map_save_gmm": (_i, [_vp, C.c_char_p]),
     "gmmloc_map_destroy": (None, [_vp]),
@@ -82,7 +91,7 @@ SYMBOLS = {
     "gmmloc_search_correspondence": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "gmmloc_check_map_association": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i, _i, _vp, _vp]),
     "gmmloc_keyframes_associate": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 4 + [_i, _i, _i, _i] + [_vp] * 5),
-    "gmmloc_local_ba": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params), _i] + [_vp] * 16),
+    "gmmloc_local_ba": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params), _i] + [_vp] * 17),
     "gmmloc_points_solve": (_i, [_vp, _vp, C.POINTER(Camera), C.POINTER(Params)] + [_vp] * 6 + [_i, _i] + [_vp] * 4),
 }
 

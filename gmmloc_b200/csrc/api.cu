@@ -35,6 +35,13 @@ gmmloc_status_t fail(gmmloc_status_t s, const std::string& msg) {
     if (e__ != cudaSuccess) return fail_cuda(e__, #call);   \
   } while (0)
 
+// No exception may cross the C ABI: entry points that allocate host memory (std::vector / std::string) are
+// function-try-blocks closed by this handler.
+#define GMMLOC_ABI_CATCH                                                                                  \
+  catch (const std::bad_alloc&) { return fail(GMMLOC_ENOMEM, "host allocation failed"); }                 \
+  catch (const std::exception& ex__) { return fail(GMMLOC_EINVAL, std::string("exception: ") + ex__.what()); } \
+  catch (...) { return fail(GMMLOC_EINVAL, "unknown exception"); }
+
 // grow-only device buffer
 struct DevBuf {
   void* p = nullptr;
@@ -132,7 +139,7 @@ bool parse_component(const std::vector<unsigned char>& buf, size_t pos, size_t e
         break;
       }
       case 1: {
-        if (pos + 8 > end) return false;
+        if (end - pos < 8) return false;
         double v;
         std::memcpy(&v, &buf[pos], 8);
         take(field, v);
@@ -141,7 +148,7 @@ bool parse_component(const std::vector<unsigned char>& buf, size_t pos, size_t e
       }
       case 2: {
         uint64_t len;
-        if (!get_varint(buf, pos, len) || pos + len > end) return false;
+        if (!get_varint(buf, pos, len) || len > (uint64_t)(end - pos)) return false;
         if ((field == 3 || field == 4) && (len & 7u) == 0) {
           for (uint64_t off = 0; off < len; off += 8) {
             double v;
@@ -153,7 +160,7 @@ bool parse_component(const std::vector<unsigned char>& buf, size_t pos, size_t e
         break;
       }
       case 5:
-        if (pos + 4 > end) return false;
+        if (end - pos < 4) return false;
         pos += 4;
         break;
       default:
@@ -174,13 +181,16 @@ gmmloc_status_t read_gmm(const char* path, GmmFile& out) {
   size_t pos = 0;
   uint64_t count;
   if (!get_varint(buf, pos, count)) return fail(GMMLOC_EIO, "could not read the message count");
-  if (count == 0 || count > (1u << 30)) return fail(GMMLOC_EIO, "protobuf file empty");  // gmm_utils.cpp:32-35
+  if (count == 0) return fail(GMMLOC_EIO, "protobuf file empty");  // gmm_utils.cpp:32-35
+  // a component message holds at least 3 + 9 doubles: a count the file cannot hold is a corrupt header (the reference
+  // reads through protobuf's CodedInputStream, which fails on the first missing message instead of allocating)
+  if (count > buf.size() / 96) return fail(GMMLOC_EIO, "message count exceeds the file size");
   out.mean.resize(count * 3);
   out.cov.resize(count * 9);
   out.flags.resize(count * 2);
   for (uint64_t k = 0; k < count; ++k) {
     uint64_t len;
-    if (!get_varint(buf, pos, len) || len == 0 || pos + len > buf.size())
+    if (!get_varint(buf, pos, len) || len == 0 || len > (uint64_t)(buf.size() - pos))
       return fail(GMMLOC_EIO, "truncated component message " + std::to_string(k));
     if (!parse_component(buf, pos, pos + len, &out.mean[k * 3], &out.cov[k * 9], &out.flags[k * 2]))
       return fail(GMMLOC_EIO, "malformed component message " + std::to_string(k));
@@ -230,6 +240,11 @@ struct gmmloc_ctx {
   int assoc_kind = GMMLOC_ASSOC_AUTO;
   int gn_precision = GMMLOC_GN_MIXED;
   int last_assoc_tc = 0;
+  int32_t* h_stop = nullptr;     // page-locked, device-mapped mirror of the caller's BA stop flag (gmmloc_local_ba)
+  cudaEvent_t ev_ba = nullptr;   // end of the BA kernel (the host polls it while it mirrors the flag)
+  int opt_gn_prep = -1;          // GMMLOC_OPT_GN_PREP
+  int opt_e2e_chunk = 0;         // GMMLOC_OPT_E2E_CHUNK
+  int opt_e2e_short_first = 0;   // GMMLOC_OPT_E2E_SHORT_FIRST
 };
 
 extern "C" {
@@ -294,14 +309,24 @@ void gmmloc_map_destroy(gmmloc_map_t* m) {
 
 gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, double deg_eps, int device,
                                   gmmloc_map_t** out) {
+  return gmmloc_map_create_ex(mean, cov, K, deg_eps, device, nullptr, out);
+}
+
+gmmloc_status_t gmmloc_map_create_ex(const double* mean, const double* cov, int K, double deg_eps, int device,
+                                     const gmmloc_grid_options_t* grid_opt, gmmloc_map_t** out) try {
   if (!mean || !cov || !out || K <= 0) return fail(GMMLOC_EINVAL, "gmmloc_map_create: null pointer or K <= 0");
   *out = nullptr;
   CU(cudaSetDevice(device));
   gmmloc_map* m = new (std::nothrow) gmmloc_map();
   if (!m) return fail(GMMLOC_ENOMEM, "host allocation failed");
   m->device = device;
-  m->h_mean.assign(mean, mean + (size_t)K * 3);
-  m->h_cov.assign(cov, cov + (size_t)K * 9);
+  try {
+    m->h_mean.assign(mean, mean + (size_t)K * 3);
+    m->h_cov.assign(cov, cov + (size_t)K * 9);
+  } catch (const std::bad_alloc&) {
+    delete m;
+    return fail(GMMLOC_ENOMEM, "host allocation failed");
+  }
   MapDev& d = m->d;
   d.K = K;
   d.Kpad = (K + kChunk - 1) / kChunk * kChunk;
@@ -367,23 +392,23 @@ gmmloc_status_t gmmloc_map_create(const double* mean, const double* cov, int K, 
   std::memcpy(&d.tc_err, &h[2], 4);
   d.tc_ok = (d.tc_table != nullptr && h[3] == 0) ? 1 : 0;
   // exact spatial index for the association (grid_build.cu); a map it cannot index keeps the brute-force scan
-  if ((e = build_assoc_grid(d, lo, hi)) != cudaSuccess) {
+  if ((e = build_assoc_grid(d, lo, hi, grid_opt)) != cudaSuccess) {
     gmmloc_map_destroy(m);
     return fail_cuda(e, "build_assoc_grid");
   }
   *out = m;
   return GMMLOC_OK;
-}
+} GMMLOC_ABI_CATCH
 
-gmmloc_status_t gmmloc_map_load_gmm(const char* path, double deg_eps, int device, gmmloc_map_t** out) {
+gmmloc_status_t gmmloc_map_load_gmm(const char* path, double deg_eps, int device, gmmloc_map_t** out) try {
   if (!path || !out) return fail(GMMLOC_EINVAL, "gmmloc_map_load_gmm: null pointer");
   GmmFile f;
   gmmloc_status_t s = read_gmm(path, f);
   if (s != GMMLOC_OK) return s;  // bool false + LOG(ERROR) in the reference, gmm_utils.cpp:19-48
   return gmmloc_map_create(f.mean.data(), f.cov.data(), (int)(f.mean.size() / 3), deg_eps, device, out);
-}
+} GMMLOC_ABI_CATCH
 
-gmmloc_status_t gmmloc_map_save_gmm(const gmmloc_map_t* map, const char* path) {
+gmmloc_status_t gmmloc_map_save_gmm(const gmmloc_map_t* map, const char* path) try {
   if (!map || !path) return fail(GMMLOC_EINVAL, "gmmloc_map_save_gmm: null pointer");
   const int K = map->d.K;
   std::vector<uint8_t> deg(K), sal(K);
@@ -412,7 +437,7 @@ gmmloc_status_t gmmloc_map_save_gmm(const gmmloc_map_t* map, const char* path) {
   std::fclose(fp);
   if (w != s.size()) return fail(GMMLOC_EIO, "short write");
   return GMMLOC_OK;
-}
+} GMMLOC_ABI_CATCH
 
 int gmmloc_map_size(const gmmloc_map_t* map) { return map ? map->d.K : 0; }
 int gmmloc_map_device(const gmmloc_map_t* map) { return map ? map->device : -1; }
@@ -440,7 +465,7 @@ gmmloc_status_t gmmloc_map_get_components(const gmmloc_map_t* map, double* mean,
 
 // counting pass + host prefix sum + fill pass; on success rp / dcol (/ ddist) hold the CSR lists on the device
 static gmmloc_status_t neighbors_device(const gmmloc_map_t* map, double thresh, bool want_dist, DevBuf& rp, DevBuf& dcol,
-                                        DevBuf& ddist, std::vector<long long>& h_rp) {
+                                        DevBuf& ddist, std::vector<long long>& h_rp) try {
   const int K = map->d.K;
   DevBuf counts;
   cudaError_t e;
@@ -469,10 +494,10 @@ static gmmloc_status_t neighbors_device(const gmmloc_map_t* map, double thresh, 
     if ((e = cudaDeviceSynchronize()) != cudaSuccess) return done(fail_cuda(e, "bh_neighbors (fill)"));
   }
   return done(GMMLOC_OK);
-}
+} GMMLOC_ABI_CATCH
 
 gmmloc_status_t gmmloc_map_neighbors(const gmmloc_map_t* map, double thresh, int64_t* row_ptr, int32_t* col, double* dist,
-                                     int64_t cap, int64_t* count) {
+                                     int64_t cap, int64_t* count) try {
   if (!map || !row_ptr || !count) return fail(GMMLOC_EINVAL, "gmmloc_map_neighbors: null pointer");
   const int K = map->d.K;
   int prev = 0;
@@ -496,9 +521,9 @@ gmmloc_status_t gmmloc_map_neighbors(const gmmloc_map_t* map, double thresh, int
   if (dist && (e = cudaMemcpy(dist, ddist.p, sizeof(double) * n, cudaMemcpyDeviceToHost)) != cudaSuccess)
     return done(fail_cuda(e, "D2H dist"));
   return done(GMMLOC_OK);
-}
+} GMMLOC_ABI_CATCH
 
-gmmloc_status_t gmmloc_map_build_neighbors(gmmloc_map_t* map, double thresh, int64_t* count) {
+gmmloc_status_t gmmloc_map_build_neighbors(gmmloc_map_t* map, double thresh, int64_t* count) try {
   if (!map) return fail(GMMLOC_EINVAL, "gmmloc_map_build_neighbors: null map");
   int prev = 0;
   cudaGetDevice(&prev);
@@ -519,6 +544,32 @@ gmmloc_status_t gmmloc_map_build_neighbors(gmmloc_map_t* map, double thresh, int
   map->d.nbr_thresh = thresh;
   if (count) *count = map->d.nbr_count;
   cudaSetDevice(prev);
+  return GMMLOC_OK;
+} GMMLOC_ABI_CATCH
+
+gmmloc_status_t gmmloc_map_query_point(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const double* pts, int M, int32_t* nearest,
+                                       int32_t* knn, double* min_mdist2) {
+  if (!ctx || !map || M < 0) return fail(GMMLOC_EINVAL, "gmmloc_map_query_point: bad argument");
+  if (M == 0) return GMMLOC_OK;
+  if (!pts || !nearest) return fail(GMMLOC_EINVAL, "gmmloc_map_query_point: null pointer");
+  if (map->device != ctx->device) return fail(GMMLOC_EINVAL, "map and context live on different devices");
+  CU(cudaSetDevice(ctx->device));
+  ctx->active = 0;
+  cudaStream_t st = ctx->L().stream;
+  const size_t m = (size_t)M, nk = (size_t)query_point_knn();
+  // slabs: pts (24) | min_mdist2 (8) | nearest (4) | knn (4 nk)
+  const size_t o_md = 24 * m, o_nn = o_md + 8 * m, o_knn = o_nn + 4 * m, total = o_knn + 4 * nk * m;
+  CU(ctx->in_misc.reserve(total));
+  char* base = ctx->in_misc.as<char>();
+  CU(cudaMemcpyAsync(base, pts, 24 * m, cudaMemcpyHostToDevice, st));
+  CU(launch_query_point(map->d.mean, map->d.cov_inv, map->d.K, reinterpret_cast<const double*>(base), M,
+                        reinterpret_cast<int32_t*>(base + o_nn), reinterpret_cast<int32_t*>(base + o_knn),
+                        reinterpret_cast<double*>(base + o_md), st));
+  ctx->stats.kernel_launches += 1;
+  CU(cudaMemcpyAsync(nearest, base + o_nn, 4 * m, cudaMemcpyDeviceToHost, st));
+  if (knn) CU(cudaMemcpyAsync(knn, base + o_knn, 4 * nk * m, cudaMemcpyDeviceToHost, st));
+  if (min_mdist2) CU(cudaMemcpyAsync(min_mdist2, base + o_md, 8 * m, cudaMemcpyDeviceToHost, st));
+  CU(cudaStreamSynchronize(st));
   return GMMLOC_OK;
 }
 
@@ -545,6 +596,11 @@ gmmloc_status_t gmmloc_ctx_create(int device, gmmloc_ctx_t** out) {
     if (e == cudaSuccess) e = l.next_frame.reserve(sizeof(int));
     if (e == cudaSuccess) e = cudaMemset(l.flag_count.p, 0, 2 * sizeof(int));
     for (int i = 0; i < 4 && e == cudaSuccess; ++i) e = cudaEventCreate(&l.ev[i]);
+  }
+  if (e == cudaSuccess) e = cudaHostAlloc((void**)&c->h_stop, sizeof(int32_t), cudaHostAllocMapped);
+  if (e == cudaSuccess) {
+    *c->h_stop = 0;
+    e = cudaEventCreateWithFlags(&c->ev_ba, cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->h2d, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->d2h, cudaStreamNonBlocking);
@@ -579,6 +635,8 @@ void gmmloc_ctx_destroy(gmmloc_ctx_t* c) {
   for (cudaEvent_t e : c->ev_done) cudaEventDestroy(e);
   if (c->h2d) cudaStreamDestroy(c->h2d);
   if (c->d2h) cudaStreamDestroy(c->d2h);
+  if (c->h_stop) cudaFreeHost(c->h_stop);
+  if (c->ev_ba) cudaEventDestroy(c->ev_ba);
   cudaSetDevice(prev);
   delete c;
 }
@@ -628,6 +686,25 @@ gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int precision) {
     return fail(GMMLOC_EINVAL, "gmmloc_ctx_set_gn_precision: bad argument");
   ctx->gn_precision = precision;
   return GMMLOC_OK;
+}
+
+gmmloc_status_t gmmloc_ctx_set_option(gmmloc_ctx_t* ctx, int option, int64_t value) {
+  if (!ctx) return fail(GMMLOC_EINVAL, "gmmloc_ctx_set_option: null ctx");
+  switch (option) {
+    case GMMLOC_OPT_GN_PREP:
+      if (value < -1 || value > 1) return fail(GMMLOC_EINVAL, "GMMLOC_OPT_GN_PREP: -1, 0 or 1");
+      ctx->opt_gn_prep = (int)value;
+      return GMMLOC_OK;
+    case GMMLOC_OPT_E2E_CHUNK:
+      if (value < 0 || value > (1 << 24)) return fail(GMMLOC_EINVAL, "GMMLOC_OPT_E2E_CHUNK: 0 .. 2^24");
+      ctx->opt_e2e_chunk = (int)value;
+      return GMMLOC_OK;
+    case GMMLOC_OPT_E2E_SHORT_FIRST:
+      ctx->opt_e2e_short_first = value ? 1 : 0;
+      return GMMLOC_OK;
+    default:
+      return fail(GMMLOC_EINVAL, "gmmloc_ctx_set_option: unknown option");
+  }
 }
 
 gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out) {
@@ -753,7 +830,7 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
   }
   if (!ctx->L().ev_assoc) CU(cudaEventRecord(ctx->L().ev[2], ctx->L().stream));
   static const int gn_forced = [] {  // GMMLOC_GN_PRECISION=fp64|mixed overrides the context setting (A/B runs)
-    const char* v = std::getenv("GMMLOC_GN_PRECISION");
+    const char* v = debug_env("GMMLOC_GN_PRECISION");
     if (v == nullptr) return -1;
     if (std::strcmp(v, "fp64") == 0) return (int)GMMLOC_GN_FP64;
     if (std::strcmp(v, "mixed") == 0) return (int)GMMLOC_GN_MIXED;
@@ -763,7 +840,7 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
   if (gn_prec == GMMLOC_GN_MIXED && map->d.gn_tab != nullptr && (size_t)N <= frame_gn_mixed_limit_points()) {
     CU(ctx->L().next_frame.reserve(sizeof(int)));
     CU(ctx->L().gn_store.reserve(frame_gn_mixed_scratch_bytes(N)));
-    const size_t prep_bytes = frame_gn_mixed_prep_bytes(B, N);
+    const size_t prep_bytes = frame_gn_mixed_prep_bytes(B, N, ctx->opt_gn_prep);
     if (prep_bytes) CU(ctx->L().gn_prep.reserve(prep_bytes));
     CU(launch_frame_gn_mixed(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().gn_store.as<float>(), ctx->L().gn_store.cap,
                              prep_bytes ? ctx->L().gn_prep.as<unsigned char>() : nullptr, prep_bytes ? ctx->L().gn_prep.cap : 0,
@@ -781,7 +858,7 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
 gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
                                     const gmmloc_params_t* params, const double* pose0, const float* pts_w,
                                     const float* obs, const uint8_t* octave, int B, int N, double* pose_out, float* pts_out,
-                                    int32_t* assign, uint8_t* outlier, int32_t* status) {
+                                    int32_t* assign, uint8_t* outlier, int32_t* status) try {
   if (!ctx || !map || !cam || !params || B < 0 || N < 0) return fail(GMMLOC_EINVAL, "gmmloc_frames_solve: bad argument");
   if (B == 0) return GMMLOC_OK;
   if (!pose0 || !pose_out || !status || (N > 0 && (!pts_w || !obs || !octave)))
@@ -800,9 +877,9 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   // Pipelined over chunks of frames: H2D of chunk c+1 (copy stream) overlaps the kernels of chunk c
   // (compute stream) and the D2H of chunk c-1 (second copy stream); PCIe is full duplex.  With
   // page-locked caller buffers the copies are truly asynchronous; pageable buffers still work.
-  static const int chunk_env = [] {
-    const char* v = std::getenv("GMMLOC_E2E_CHUNK");
-    return v ? std::atoi(v) : 0;
+  const int chunk_env = [&] {
+    const char* v = debug_env("GMMLOC_E2E_CHUNK");
+    return v ? std::atoi(v) : ctx->opt_e2e_chunk;
   }();
   // Chunk = 3 frames per resident CTA of the persistent frame-GN kernel (2 CTAs x 148 SMs -> 888 frames on B200): a
   // chunk that is not a multiple of the resident CTA count leaves most CTAs idle for a whole extra frame.  Measured on
@@ -814,9 +891,9 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   // chunk boundaries: uniform chunks; a remainder smaller than half a chunk is merged into the last chunk instead of
   // running as a tiny one.  GMMLOC_E2E_SHORT_FIRST=1 makes the first chunk a third of the others (kernels start after a
   // shorter H2D) — measured no faster (652 k vs 658 k frames/s on C2), so it is off by default.
-  static const int short_first = [] {
-    const char* v = std::getenv("GMMLOC_E2E_SHORT_FIRST");
-    return v ? std::atoi(v) : 0;
+  const int short_first = [&] {
+    const char* v = debug_env("GMMLOC_E2E_SHORT_FIRST");
+    return v ? std::atoi(v) : ctx->opt_e2e_short_first;
   }();
   std::vector<int> cstart;
   {
@@ -847,7 +924,7 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     CU(ln.flag_thr.reserve(sizeof(float) * 2 * mc));
     CU(ln.next_frame.reserve(sizeof(int)));
     CU(ln.gn_store.reserve(frame_gn_mixed_scratch_bytes(N)));
-    if (frame_gn_mixed_prep_bytes(maxc, N)) CU(ln.gn_prep.reserve(frame_gn_mixed_prep_bytes(maxc, N)));
+    if (frame_gn_mixed_prep_bytes(maxc, N, ctx->opt_gn_prep)) CU(ln.gn_prep.reserve(frame_gn_mixed_prep_bytes(maxc, N, ctx->opt_gn_prep)));
     if (map->d.grid.nlev > 0) {
       const GridLevel& G0 = map->d.grid.lev[0];
       CU(ln.sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2)));
@@ -859,44 +936,55 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     }
   }
   gmmloc_status_t rc = GMMLOC_OK;
+  // an error inside the loop must not return while copies into the caller's buffers are in flight: CUB records the
+  // status and leaves the loop; every exit path then drains the four streams below and resets ctx->active
+#define CUB(call)                                       \
+  {                                                     \
+    const cudaError_t e__ = (call);                     \
+    if (e__ != cudaSuccess) {                           \
+      rc = fail_cuda(e__, #call);                       \
+      break;                                            \
+    }                                                   \
+  }
   for (int c = 0; c < nchunks && rc == GMMLOC_OK; ++c) {
     ctx->active = (nchunks > 1) ? (c & 1) : 0;
     cudaStream_t st = ctx->L().stream;
     const size_t f0 = (size_t)cstart[c], nb = (size_t)(cstart[c + 1] - cstart[c]), m0 = f0 * N, nm = nb * N;
-    CU(cudaMemcpyAsync(ctx->in_pose.as<double>() + 7 * f0, pose0 + 7 * f0, 56 * nb, cudaMemcpyHostToDevice, ctx->h2d));
+    CUB(cudaMemcpyAsync(ctx->in_pose.as<double>() + 7 * f0, pose0 + 7 * f0, 56 * nb, cudaMemcpyHostToDevice, ctx->h2d));
     if (nm) {
-      CU(cudaMemcpyAsync(ctx->in_pts.as<float>() + 3 * m0, pts_w + 3 * m0, 12 * nm, cudaMemcpyHostToDevice, ctx->h2d));
-      CU(cudaMemcpyAsync(ctx->in_obs.as<float>() + 3 * m0, obs + 3 * m0, 12 * nm, cudaMemcpyHostToDevice, ctx->h2d));
-      CU(cudaMemcpyAsync(ctx->in_oct.as<uint8_t>() + m0, octave + m0, nm, cudaMemcpyHostToDevice, ctx->h2d));
+      CUB(cudaMemcpyAsync(ctx->in_pts.as<float>() + 3 * m0, pts_w + 3 * m0, 12 * nm, cudaMemcpyHostToDevice, ctx->h2d));
+      CUB(cudaMemcpyAsync(ctx->in_obs.as<float>() + 3 * m0, obs + 3 * m0, 12 * nm, cudaMemcpyHostToDevice, ctx->h2d));
+      CUB(cudaMemcpyAsync(ctx->in_oct.as<uint8_t>() + m0, octave + m0, nm, cudaMemcpyHostToDevice, ctx->h2d));
     }
-    CU(cudaEventRecord(ctx->ev_in[c], ctx->h2d));
-    CU(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
+    CUB(cudaEventRecord(ctx->ev_in[c], ctx->h2d));
+    CUB(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
     rc = gmmloc_frames_solve_async(
         ctx, map, cam, params, ctx->in_pose.as<double>() + 7 * f0, ctx->in_pts.as<float>() + 3 * m0,
         ctx->in_obs.as<float>() + 3 * m0, ctx->in_oct.as<uint8_t>() + m0, (int)nb, N, ctx->out_pose.as<double>() + 7 * f0,
         pts_out ? ctx->out_pts.as<float>() + 3 * m0 : nullptr, ctx->out_assign.as<int32_t>() + m0,
         outlier ? ctx->out_outlier.as<uint8_t>() + m0 : nullptr, ctx->out_status.as<int32_t>() + f0);
     if (rc != GMMLOC_OK) break;
-    CU(cudaEventRecord(ctx->ev_done[c], st));
-    CU(cudaStreamWaitEvent(ctx->d2h, ctx->ev_done[c], 0));
-    CU(cudaMemcpyAsync(pose_out + 7 * f0, ctx->out_pose.as<double>() + 7 * f0, 56 * nb, cudaMemcpyDeviceToHost, ctx->d2h));
-    CU(cudaMemcpyAsync(status + f0, ctx->out_status.as<int32_t>() + f0, 4 * nb, cudaMemcpyDeviceToHost, ctx->d2h));
+    CUB(cudaEventRecord(ctx->ev_done[c], st));
+    CUB(cudaStreamWaitEvent(ctx->d2h, ctx->ev_done[c], 0));
+    CUB(cudaMemcpyAsync(pose_out + 7 * f0, ctx->out_pose.as<double>() + 7 * f0, 56 * nb, cudaMemcpyDeviceToHost, ctx->d2h));
+    CUB(cudaMemcpyAsync(status + f0, ctx->out_status.as<int32_t>() + f0, 4 * nb, cudaMemcpyDeviceToHost, ctx->d2h));
     if (nm) {
-      if (assign) CU(cudaMemcpyAsync(assign + m0, ctx->out_assign.as<int32_t>() + m0, 4 * nm, cudaMemcpyDeviceToHost, ctx->d2h));
-      if (pts_out) CU(cudaMemcpyAsync(pts_out + 3 * m0, ctx->out_pts.as<float>() + 3 * m0, 12 * nm, cudaMemcpyDeviceToHost, ctx->d2h));
-      if (outlier) CU(cudaMemcpyAsync(outlier + m0, ctx->out_outlier.as<uint8_t>() + m0, nm, cudaMemcpyDeviceToHost, ctx->d2h));
+      if (assign) CUB(cudaMemcpyAsync(assign + m0, ctx->out_assign.as<int32_t>() + m0, 4 * nm, cudaMemcpyDeviceToHost, ctx->d2h));
+      if (pts_out) CUB(cudaMemcpyAsync(pts_out + 3 * m0, ctx->out_pts.as<float>() + 3 * m0, 12 * nm, cudaMemcpyDeviceToHost, ctx->d2h));
+      if (outlier) CUB(cudaMemcpyAsync(outlier + m0, ctx->out_outlier.as<uint8_t>() + m0, nm, cudaMemcpyDeviceToHost, ctx->d2h));
     }
   }
   ctx->active = 0;
   const cudaError_t e0 = cudaStreamSynchronize(ctx->h2d), e1 = cudaStreamSynchronize(ctx->lanes[0].stream),
                     e2 = cudaStreamSynchronize(ctx->lanes[1].stream), e3 = cudaStreamSynchronize(ctx->d2h);
+#undef CUB
   if (rc != GMMLOC_OK) return rc;
   CU(e0);
   CU(e1);
   CU(e2);
   CU(e3);
   return GMMLOC_OK;
-}
+} GMMLOC_ABI_CATCH
 
 // ---- pose-only LM (Tracking::optimizeCurrentPose) --------------------------------------------------
 gmmloc_status_t gmmloc_poses_optimize(gmmloc_ctx_t* ctx, const gmmloc_camera_t* cam, const double* pose0, const float* pts_w,
@@ -1161,7 +1249,7 @@ gmmloc_status_t check_enqueue(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const 
 
 gmmloc_status_t gmmloc_render_views(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam, const double* pose,
                                     int B, int cap, int32_t* count, int32_t* status, int32_t* ids, double* mean2d,
-                                    double* cov2d, double* depth) {
+                                    double* cov2d, double* depth) try {
   if (!ctx || !map || !cam || B < 0 || cap <= 0) return fail(GMMLOC_EINVAL, "gmmloc_render_views: bad argument");
   if (map->device != ctx->device) return fail(GMMLOC_EINVAL, "map and context live on different devices");
   if (B == 0) {
@@ -1171,21 +1259,27 @@ gmmloc_status_t gmmloc_render_views(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
   if (!pose) return fail(GMMLOC_EINVAL, "gmmloc_render_views: null pose");
   CU(cudaSetDevice(ctx->device));
   ctx->active = 0;
-  if (cap > map->d.K) cap = map->d.K;
+  // The device keeps at most K components per view; the HOST outputs keep the caller's `cap` as their row stride
+  // (B x cap as documented), columns beyond the device capacity are padding (ids -1, records 0).
+  const int dcap = std::min(cap, map->d.K);
   cudaStream_t st = ctx->L().stream;
   CU(ctx->view_pose.reserve(56 * (size_t)B));
   CU(cudaMemcpyAsync(ctx->view_pose.p, pose, 56 * (size_t)B, cudaMemcpyHostToDevice, st));
-  gmmloc_status_t rc = render_enqueue(ctx, map, cam, B, cap);
+  gmmloc_status_t rc = render_enqueue(ctx, map, cam, B, dcap);
   if (rc != GMMLOC_OK) return rc;
   if (count) CU(cudaMemcpyAsync(count, ctx->view_count.p, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
   if (status) CU(cudaMemcpyAsync(status, ctx->view_status.p, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
-  if (ids) CU(cudaMemcpyAsync(ids, ctx->view_ids.p, 4 * (size_t)B * cap, cudaMemcpyDeviceToHost, st));
+  if (ids)
+    CU(cudaMemcpy2DAsync(ids, 4 * (size_t)cap, ctx->view_ids.p, 4 * (size_t)dcap, 4 * (size_t)dcap, (size_t)B, cudaMemcpyDeviceToHost, st));
   std::vector<double> rec;
   if (mean2d || cov2d || depth) {
-    rec.resize((size_t)B * cap * kViewRec);
+    rec.resize((size_t)B * dcap * kViewRec);
     CU(cudaMemcpyAsync(rec.data(), ctx->view_rec.p, 8 * rec.size(), cudaMemcpyDeviceToHost, st));
   }
   CU(cudaStreamSynchronize(st));
+  if (ids && cap > dcap)
+    for (size_t b = 0; b < (size_t)B; ++b)
+      for (int j = dcap; j < cap; ++j) ids[b * cap + j] = -1;
   if (!rec.empty()) {
     // entries past a view's count are unspecified on the device: zero them on the way out
     std::vector<int32_t> cnt((size_t)B);
@@ -1193,15 +1287,15 @@ gmmloc_status_t gmmloc_render_views(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     for (size_t b = 0; b < (size_t)B; ++b)
       for (size_t j = 0; j < (size_t)cap; ++j) {
         const size_t e = b * cap + j;
-        const bool live = (int)j < cnt[b];
-        const double* r = &rec[e * kViewRec];
+        const bool live = (int)j < cnt[b] && (int)j < dcap;
+        const double* r = &rec[(b * dcap + (live ? j : 0)) * kViewRec];
         if (mean2d) { mean2d[e * 2] = live ? r[0] : 0.0; mean2d[e * 2 + 1] = live ? r[1] : 0.0; }
         if (cov2d) for (int q = 0; q < 4; ++q) cov2d[e * 4 + q] = live ? r[2 + q] : 0.0;
         if (depth) depth[e] = live ? r[7] : 0.0;
       }
   }
   return GMMLOC_OK;
-}
+} GMMLOC_ABI_CATCH
 
 gmmloc_status_t gmmloc_search_correspondence(gmmloc_ctx_t* ctx, const float* obs, int B, int N, int num, int32_t* cand,
                                              int32_t* cand_pos) {
@@ -1313,7 +1407,7 @@ gmmloc_status_t gmmloc_local_ba(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, cons
                                 const int32_t* prior_idx, const int32_t* pt_ptr, double* pts, const int32_t* assoc,
                                 const int32_t* obs_ptr, const int32_t* obs_pt, const int32_t* obs_kf, const float* obs,
                                 const uint8_t* octave, uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters,
-                                int32_t* status) {
+                                int32_t* status, const volatile int32_t* stop) try {
   if (!ctx || !map || !cam || !params || B < 0) return fail(GMMLOC_EINVAL, "gmmloc_local_ba: bad argument");
   if (B == 0) return GMMLOC_OK;
   if (!pose_ptr || !pose || !fixed || !pt_ptr || !pts || !assoc || !obs_ptr || !obs_pt || !obs_kf || !obs || !octave)
@@ -1470,8 +1564,28 @@ gmmloc_status_t gmmloc_local_ba(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, cons
   a.assoc_cleared = reinterpret_cast<uint8_t*>(base + s_clr.off);
   a.iters = reinterpret_cast<int32_t*>(base + s_it.off);
   a.status = reinterpret_cast<int32_t*>(base + s_st.off);
+  a.stop = nullptr;
+  if (stop != nullptr) {
+    // Localization::jointOptimization(KeyFrame*, bool* pbStopFlag, Map*): another host thread raises the flag
+    // (Localization::insertKeyFrame -> interruptBA, localization.cpp:401-405) and g2o polls it.  The kernel polls a
+    // device-mapped mirror; this (blocked) calling thread keeps the mirror in step with *stop until the kernel ends.
+    int32_t* d_stop = nullptr;
+    CU(cudaHostGetDevicePointer((void**)&d_stop, ctx->h_stop, 0));
+    *reinterpret_cast<volatile int32_t*>(ctx->h_stop) = *stop;
+    a.stop = d_stop;
+  }
   CU(launch_local_ba(a, st));
   ctx->stats.kernel_launches += 1;
+  if (stop != nullptr) {
+    CU(cudaEventRecord(ctx->ev_ba, st));
+    cudaError_t q;
+    while ((q = cudaEventQuery(ctx->ev_ba)) == cudaErrorNotReady) {
+      const int32_t v = *stop;
+      volatile int32_t* m = reinterpret_cast<volatile int32_t*>(ctx->h_stop);
+      if (*m != v) *m = v;
+    }
+    if (q != cudaSuccess) return fail_cuda(q, "local_ba_kernel");
+  }
   CU(cudaMemcpyAsync(pose, base + s_pose.off, 56 * (size_t)sumP, cudaMemcpyDeviceToHost, st));
   if (sumL) CU(cudaMemcpyAsync(pts, base + s_pts.off, 24 * (size_t)sumL, cudaMemcpyDeviceToHost, st));
   if (obs_outlier && sumE) CU(cudaMemcpyAsync(obs_outlier, base + s_out.off, (size_t)sumE, cudaMemcpyDeviceToHost, st));
@@ -1480,6 +1594,6 @@ gmmloc_status_t gmmloc_local_ba(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, cons
   if (status) CU(cudaMemcpyAsync(status, base + s_st.off, 4 * (size_t)B, cudaMemcpyDeviceToHost, st));
   CU(cudaStreamSynchronize(st));
   return GMMLOC_OK;
-}
+} GMMLOC_ABI_CATCH
 
 }  // extern "C"

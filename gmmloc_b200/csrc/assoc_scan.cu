@@ -1251,7 +1251,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
   // variant: 0 auto, -1 FFMA2 scan, 1/2/4/8 FFMA2 scan with that many landmarks per thread, 16 tensor-core scan,
   // 32 grid-indexed scan.  GMMLOC_ASSOC_KERNEL=grid|tc|ffma2 overrides the automatic choice (A/B runs of the bench).
   static const int forced = [] {
-    const char* v = std::getenv("GMMLOC_ASSOC_KERNEL");
+    const char* v = debug_env("GMMLOC_ASSOC_KERNEL");
     if (v == nullptr) return 0;
     if (std::strcmp(v, "tc") == 0) return 16;
     if (std::strcmp(v, "ffma2") == 0) return -1;

@@ -3,9 +3,24 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "../../include/gmmloc_b200.h"
 
 namespace gmmloc {
+
+// Environment overrides (kernel selection, grid tuning, pipeline chunking) exist for A/B runs only: a production
+// library must not change the kernel it runs because of a stray variable, so they are compiled in only with
+// -DGMMLOC_DEBUG_ENV (python -m gmmloc_b200.build --debug-env).  The supported switches are the context / map
+// setters of include/gmmloc_b200.h (gmmloc_ctx_set_assoc_kernel, _set_gn_precision, _set_option, gmmloc_map_create_ex).
+inline const char* debug_env(const char* name) {
+#ifdef GMMLOC_DEBUG_ENV
+  return std::getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
 
 // fp32 scan table: 9 floats per component,
 //   c = 0..5 : rows of U = L^T (upper triangular, cov_inv = L L^T):  U00 U01 U02 U11 U12 U22
@@ -98,7 +113,7 @@ cudaError_t launch_map_build(const MapDev& m, double deg_eps, double xmax, int* 
                              cudaStream_t stream);  // d_err: [0] error flag, [1] alpha bits, [2] tc_err bits, [3] tc overflow flag
 // builds m.grid (levels, lists, big list) from the component constants already on the device; lo / hi = bounding box
 // of the means.  On any resource limit the grid is left empty (nlev = 0) and cudaSuccess is returned.
-cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3]);
+cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3], const gmmloc_grid_options_t* opt = nullptr);
 void free_assoc_grid(MapDev& m);
 cudaError_t launch_bh_neighbors(const MapDev& m, double thresh, int* d_counts, const long long* d_row_ptr, int32_t* d_col,
                                 double* d_dist, cudaStream_t stream);
@@ -135,7 +150,8 @@ cudaError_t launch_frame_gn(const FrameArgs& a, cudaStream_t stream);
 cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_next_frame, float* store_ws, size_t store_ws_bytes,
                                   unsigned char* prep_ws, size_t prep_ws_bytes, cudaStream_t stream);
 size_t frame_gn_mixed_scratch_bytes(int N);
-size_t frame_gn_mixed_prep_bytes(int B, int N);  // 0: this batch is classified and sorted inside the solver kernel
+size_t frame_gn_mixed_prep_bytes(int B, int N, int mode = -1);  // 0: this batch is classified and sorted inside the solver
+                                                                 // kernel; mode: GMMLOC_OPT_GN_PREP (-1 auto, 0 never, 1 always)
 size_t frame_gn_mixed_limit_points();  // largest N the mixed kernel takes (class-sorted frame state in shared memory)
 size_t frame_gn_smem_limit_points();  // largest N whose per-frame state stays in shared memory
 
@@ -227,6 +243,10 @@ struct SearchArgs {
   int32_t* cand_pos;     // B x N x num positions in the view list (optional)
 };
 cudaError_t launch_search_corr(const SearchArgs& a, cudaStream_t stream);
+// GMM::queryPoint for M device points: nearest M, knn M x query_point_knn() (optional), min_mdist2 M (optional)
+cudaError_t launch_query_point(const double* mean, const double* cov_inv, int K, const double* d_pts, int M, int32_t* d_nearest,
+                               int32_t* d_knn, double* d_min_mdist2, cudaStream_t stream);
+int query_point_knn();
 int search_corr_max_num();
 
 struct CheckArgs {
@@ -288,6 +308,7 @@ struct BaArgs {
   uint8_t* assoc_cleared;
   int32_t* iters;           // B x 3
   int32_t* status;          // B
+  const volatile int32_t* stop;  // force-stop flag in host-mapped memory (device pointer), or null
 };
 cudaError_t launch_local_ba(const BaArgs& a, cudaStream_t stream);
 int local_ba_obs_ws();

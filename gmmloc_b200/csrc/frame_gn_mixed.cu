@@ -1051,11 +1051,20 @@ template <int kThreads, int kMinB, bool kStoreLin, bool kPrep>
 static cudaError_t launch_mixed_t(const FrameArgs& a, const float* gn_tab, int* d_counters, size_t smem, float* store_ws,
                                   size_t store_ws_bytes, int aux_global, const unsigned char* prep, cudaStream_t stream, bool* fits) {
   cudaError_t e;
-  // opt in to exactly what this launch needs: dynamic + the kernel's static shared memory must stay within the 227 KB
-  // per-CTA limit (a blanket 220 KB request fails with the ~8 KB of static state of the 384-thread variant)
-  if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin, kPrep>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                (int)smem)) != cudaSuccess)
-    return e;
+  // The opt-in is per function and per device, i.e. state shared by every host thread that launches this variant
+  // (one gmmloc_ctx_t per thread): it is always set to the SAME value — the most this variant can use, 227 KB per CTA
+  // minus its static shared memory, halved (minus the 1 KB system reserve) when two CTAs share an SM — so concurrent
+  // callers with different N cannot shrink it under each other's launches.
+  {
+    cudaFuncAttributes fa;
+    if ((e = cudaFuncGetAttributes(&fa, frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin, kPrep>)) != cudaSuccess) return e;
+    const size_t max_dyn = kMinB == 2 ? ((228 * 1024 / 2 - 1024 - fa.sharedSizeBytes) & ~(size_t)15)
+                                      : ((227 * 1024 - fa.sharedSizeBytes) & ~(size_t)15);
+    if (smem > max_dyn) return cudaErrorInvalidValue;
+    if ((e = cudaFuncSetAttribute(frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin, kPrep>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)max_dyn)) != cudaSuccess)
+      return e;
+  }
   int per_sm = 0;
   if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, frame_gn_mixed_kernel<kThreads, kMinB, kStoreLin, kPrep>, kThreads,
                                                          smem)) != cudaSuccess)
@@ -1083,14 +1092,13 @@ size_t frame_gn_mixed_scratch_bytes(int N) {
   return (size_t)2 * sms * scratch_slice(N);
 }
 
-size_t frame_gn_mixed_prep_bytes(int B, int N) {
-  // GMMLOC_GN_PREP=0 / 1: never / always (A/B runs, tests; read on every call).  Default: batches of at least 2 M points.
-  // Measured on C2: 4 096-frame launches 3.51 -> 3.44 ms (the solver loses its two latency-bound load passes), but the
-  // 888-frame chunks of the pipelined host path get slower (e2e 682 k -> 672 k frames/s): there the extra launch and the
-  // round trip of the sorted frames through HBM cost more than the dependent loads they remove.
-  const char* v = std::getenv("GMMLOC_GN_PREP");
-  const bool off = v != nullptr && v[0] == '0', on = v != nullptr && v[0] == '1';
-  if (off || (!on && (size_t)B * (size_t)N < ((size_t)2 << 20))) return 0;
+size_t frame_gn_mixed_prep_bytes(int B, int N, int mode) {
+  // mode (gmmloc_ctx_set_option GMMLOC_OPT_GN_PREP): 0 / 1 = never / always (A/B runs, tests); -1 = batches of at least
+  // 2 M points.  Measured on C2: 4 096-frame launches 3.51 -> 3.44 ms (the solver loses its two latency-bound load passes),
+  // but the 888-frame chunks of the pipelined host path get slower (e2e 682 k -> 672 k frames/s): there the extra launch
+  // and the round trip of the sorted frames through HBM cost more than the dependent loads they remove.
+  if (const char* v = debug_env("GMMLOC_GN_PREP")) mode = (v[0] == '0') ? 0 : (v[0] == '1') ? 1 : mode;
+  if (mode == 0 || (mode < 0 && (size_t)B * (size_t)N < ((size_t)2 << 20))) return 0;
   return (size_t)B * prep_stride(N) + 16;
 }
 

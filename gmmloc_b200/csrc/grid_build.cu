@@ -163,7 +163,7 @@ __global__ void grid_sort_kernel(const int32_t* start, int32_t* list, long long 
 }
 
 double env_double(const char* name, double dflt) {
-  const char* v = std::getenv(name);
+  const char* v = debug_env(name);
   if (v == nullptr || *v == 0) return dflt;
   char* end = nullptr;
   const double x = std::strtod(v, &end);
@@ -184,12 +184,17 @@ void free_assoc_grid(MapDev& m) {
   m.grid.nlev = 0;
 }
 
-cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3]) {
+cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3], const gmmloc_grid_options_t* opt) {
   free_assoc_grid(m);
   if (m.rec == nullptr || m.K <= 0) return cudaSuccess;
-  if (const char* off = std::getenv("GMMLOC_GRID")) {
+  if (opt != nullptr && opt->enable == 0) return cudaSuccess;
+  if (const char* off = debug_env("GMMLOC_GRID")) {
     if (off[0] == '0') return cudaSuccess;
   }
+  // explicit options (gmmloc_map_create_ex) first, then the debug-build environment, then the defaults
+  auto pick = [&](double from_opt, const char* name, double dflt) {
+    return (opt != nullptr && from_opt > 0.0 && std::isfinite(from_opt)) ? from_opt : env_double(name, dflt);
+  };
   cudaError_t e;
   // cell size from the component density (about one component centre per 2.4 cells at level 0)
   double ext[3], vol = 1.0;
@@ -197,15 +202,15 @@ cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3]) 
     ext[i] = std::fmax(hi[i] - lo[i], 1.0);
     vol *= ext[i];
   }
-  const double h0 = env_double("GMMLOC_GRID_H", std::fmin(std::fmax(0.75 * std::cbrt(vol / m.K), 0.05), 4.0));
+  const double h0 = pick(opt ? opt->cell_size : 0.0, "GMMLOC_GRID_H", std::fmin(std::fmax(0.75 * std::cbrt(vol / m.K), 0.05), 4.0));
   // Three levels: T = 36 and T = 144 on the fine grid, T = 400 on a grid of twice the cell size.  The middle level is
   // what the shipped maps need: their planes are millimetres thin, so a stereo depth error of one or two centimetres
   // puts a third of the landmarks beyond 6 sigma of their component (35 % of the C3 landmarks have a winner with
   // d2 > 36, 7 % with d2 > 144, 1.3 % with d2 > 400); without it they all walk the long coarse lists.
   // GMMLOC_GRID_LEVELS=2 builds the fine T = 36 and the coarse T = 400 level only.
-  const int want_levels = (int)env_double("GMMLOC_GRID_LEVELS", (double)kGridLevels) >= kGridLevels ? kGridLevels : 2;
-  double tmax[kGridLevels] = {env_double("GMMLOC_GRID_TMAX0", 36.0), env_double("GMMLOC_GRID_TMAX1", 144.0),
-                              env_double("GMMLOC_GRID_TMAX2", 400.0)};
+  const int want_levels = (int)pick(opt ? (double)opt->levels : 0.0, "GMMLOC_GRID_LEVELS", (double)kGridLevels) >= kGridLevels ? kGridLevels : 2;
+  double tmax[kGridLevels] = {pick(opt ? opt->tmax[0] : 0.0, "GMMLOC_GRID_TMAX0", 36.0), pick(opt ? opt->tmax[1] : 0.0, "GMMLOC_GRID_TMAX1", 144.0),
+                              pick(opt ? opt->tmax[2] : 0.0, "GMMLOC_GRID_TMAX2", 400.0)};
   double margin[kGridLevels] = {1.0, 1.0, 2.0};
   int scale[kGridLevels] = {1, 1, 2};
   if (want_levels == 2) {

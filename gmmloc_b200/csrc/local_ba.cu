@@ -253,6 +253,37 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
   p.dxp = p.rhs + n;
   p.diag = p.dxp + n;
 
+  // g2o's force-stop flag (optimizer.setForceStopFlag(pbStopFlag), localization_opt.cpp:541-542).  a.stop points to
+  // host-mapped memory the calling thread keeps in step with the caller's flag while the kernel runs; thread 0 reads it
+  // wherever g2o calls terminate() and the CTA takes the same branch.  *stop > 0: raised; 0: not raised; -n: reads as
+  // raised from the n-th poll on (the deterministic replay hook the parity tests use).
+  __shared__ int s_polls, s_stop;
+  if (tid == 0) s_polls = 0;
+  auto terminate = [&]() -> bool {
+    if (a.stop == nullptr) return false;
+    __syncthreads();
+    if (tid == 0) {
+      const int v = *a.stop;
+      ++s_polls;
+      s_stop = (v > 0 || (v < 0 && s_polls >= -v)) ? 1 : 0;
+    }
+    __syncthreads();
+    return s_stop != 0;
+  };
+  // `if (pbStopFlag) if (*pbStopFlag) return;` ahead of the first optimize (:765-767): the window is left untouched
+  if (terminate()) {
+    if (a.assoc_cleared)
+      for (int l = tid; l < d.L; l += kBaT) a.assoc_cleared[d.pt_off + l] = 0;
+    if (a.obs_outlier)
+      for (int e = tid; e < d.E; e += kBaT) a.obs_outlier[d.obs_off + e] = 0;
+    if (tid == 0) {
+      if (a.iters)
+        for (int q = 0; q < 3; ++q) a.iters[(size_t)blockIdx.x * 3 + q] = 0;
+      if (a.status) a.status[blockIdx.x] = 0;
+    }
+    return;
+  }
+
   // ---- init: normalise poses, rotation cache, levels, prior measurement ----
   for (int i = tid; i < d.P; i += kBaT) {
     quat_normalize(p.pose + (size_t)i * 7);
@@ -283,7 +314,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
     double lambda = 0.0, ni = 2.0;
     bool ok = true;
     int it = 0;
-    for (; it < max_it && ok; ++it) {
+    for (; it < max_it && !terminate() && ok; ++it) {  // SparseOptimizer::optimize: i < iterations && !terminate() && ok
       double cur_chi = active_errors(a, p, red, p.pose, 7, p.wq + qR, kPoseWs, p.pts, 3, robust, s_prior_inv, s_prior_info);
       // ---- linearise every active edge at the current estimate ----
       for (int e = tid; e < d.E; e += kBaT) {
@@ -303,10 +334,20 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
         edge_err(P, pc, ob, stereo, er);
         const double z_2 = z * z;
         double Jl[9], Jp[18];
-        for (int j = 0; j < 3; ++j) {
-          Jl[j] = -P.fx * Ri[j] / z + P.fx * x * Ri[6 + j] / z_2;
-          Jl[3 + j] = -P.fy * Ri[3 + j] / z + P.fy * y * Ri[6 + j] / z_2;
-          Jl[6 + j] = stereo ? Jl[j] - P.bf * Ri[6 + j] / z_2 : 0.0;
+        if (stereo) {
+          for (int j = 0; j < 3; ++j) {
+            Jl[j] = -P.fx * Ri[j] / z + P.fx * x * Ri[6 + j] / z_2;
+            Jl[3 + j] = -P.fy * Ri[3 + j] / z + P.fy * y * Ri[6 + j] / z_2;
+            Jl[6 + j] = Jl[j] - P.bf * Ri[6 + j] / z_2;
+          }
+        } else {  // EdgeSE3ProjectXYZ: -1. / z * tmp * R (the expression of factors.cpp:84-107 and of g2o's stock edge)
+          const double sc = -1. / z;
+          const double T00 = sc * P.fx, T02 = sc * (-x / z * P.fx), T11 = sc * P.fy, T12 = sc * (-y / z * P.fy);
+          for (int j = 0; j < 3; ++j) {
+            Jl[j] = T00 * Ri[j] + T02 * Ri[6 + j];
+            Jl[3 + j] = T11 * Ri[3 + j] + T12 * Ri[6 + j];
+            Jl[6 + j] = 0.0;
+          }
         }
         Jp[0] = x * y / z_2 * P.fx;
         Jp[1] = -(1 + (x * x / z_2)) * P.fx;
@@ -688,7 +729,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
           if (!isfinite(lambda)) break;
         }
         ++qmax;
-      } while (rho < 0 && qmax < 10);
+      } while (rho < 0 && qmax < 10 && !terminate());  // OptimizationAlgorithmLevenberg::solve
       if (qmax == 10 || rho == 0 || !isfinite(lambda)) ok = false;
     }
     iters_run[stage] = it;
@@ -701,6 +742,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
         if (str_error(a, k, 1, p.pts + (size_t)l * 3, es) > P.tri_str_thresh * P.ba_lambda2) p.slevel[l] = 1;
       }
     } else if (stage == 1) {  // :797-823
+      if (terminate()) break;  // bDoMore = false (:791-795): no reprojection gating, no kernel removal, no stage 3
       for (int e = tid; e < d.E; e += kBaT) {
         const double* er = p.wo + (size_t)e * kObsWs + oErr;
         const float* ob = p.obs + (size_t)e * 3;

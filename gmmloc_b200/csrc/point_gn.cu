@@ -69,10 +69,21 @@ __device__ __forceinline__ void view_edge(const FrameParamsDev& P, const double*
     const double v = py / pz * P.fy + P.cy;
     e[0] = ob[0] - u; e[1] = ob[1] - v; e[2] = 0.0;
   }
-  for (int j = 0; j < 3; ++j) {
-    Jl[j] = -P.fx * R[j] / pz + P.fx * px * R[6 + j] / z_2;
-    Jl[3 + j] = -P.fy * R[3 + j] / pz + P.fy * py * R[6 + j] / z_2;
-    Jl[6 + j] = stereo ? Jl[j] - P.bf * R[6 + j] / z_2 : 0.0;
+  if (stereo) {  // element-wise form of EdgeProjectXYZOnlyStereo::linearizeOplus (factors.cpp:133-168)
+    for (int j = 0; j < 3; ++j) {
+      Jl[j] = -P.fx * R[j] / pz + P.fx * px * R[6 + j] / z_2;
+      Jl[3 + j] = -P.fy * R[3 + j] / pz + P.fy * py * R[6 + j] / z_2;
+      Jl[6 + j] = Jl[j] - P.bf * R[6 + j] / z_2;
+    }
+  } else {  // EdgeProjectXYZOnly::linearizeOplus: -1. / z * tmp * R (factors.cpp:84-107), Eigen's lazy-product order
+    const double s = -1. / pz;
+    const double T00 = s * P.fx, T01 = s * 0.0, T02 = s * (-px / pz * P.fx);
+    const double T10 = s * 0.0, T11 = s * P.fy, T12 = s * (-py / pz * P.fy);
+    for (int j = 0; j < 3; ++j) {
+      Jl[j] = (T00 * R[j] + T01 * R[3 + j]) + T02 * R[6 + j];
+      Jl[3 + j] = (T10 * R[j] + T11 * R[3 + j]) + T12 * R[6 + j];
+      Jl[6 + j] = 0.0;
+    }
   }
 }
 

@@ -467,6 +467,86 @@ __global__ void __launch_bounds__(kViewThreads) check_assoc_kernel(const CheckAr
   }
 }
 
+// ---- GMM::queryPoint (gaussian_mixture.cpp:545-576) ------------------------------------------------------------
+// One warp per query point: every lane keeps the kQn nearest means of its strided share of the components (sorted
+// insertion, (distance, index) lexicographic = lowest index first on equal distances), then kQn rounds of a warp-wide
+// lexicographic argmin over the lanes' list heads merge them — the list nanoflann's knnSearch(pt, 5) returns (pinned
+// against the reference's own kd-tree in tests/test_oracle_ref_nanoflann.py).  The reference then computes the minimum
+// Mahalanobis distance over the list and DISCARDS it: it returns ret_index[0], the Euclid-nearest mean (:574).
+constexpr int kQn = 5;
+__global__ void __launch_bounds__(128) query_point_kernel(const double* __restrict__ mean, const double* __restrict__ cov_inv, int K,
+                                                          const double* __restrict__ pts, int M, int32_t* __restrict__ nearest,
+                                                          int32_t* __restrict__ knn, double* __restrict__ min_mdist2) {
+  const int lane = threadIdx.x & 31;
+  const int q = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  if (q >= M) return;
+  const double p0 = pts[(size_t)q * 3], p1 = pts[(size_t)q * 3 + 1], p2 = pts[(size_t)q * 3 + 2];
+  double bd[kQn];
+  int bi[kQn];
+#pragma unroll
+  for (int r = 0; r < kQn; ++r) {
+    bd[r] = 1.7976931348623157e308;
+    bi[r] = 0x7fffffff;
+  }
+  for (int k = lane; k < K; k += 32) {
+    const double d0 = p0 - mean[(size_t)k * 3], d1 = p1 - mean[(size_t)k * 3 + 1], d2 = p2 - mean[(size_t)k * 3 + 2];
+    double d = d0 * d0 + d1 * d1 + d2 * d2;  // FLANNPoints3d::kdtree_distance (gaussian_mixture.h:33-39)
+    if (!(d < bd[kQn - 1])) continue;      // k ascends within a lane: an equal distance never displaces an earlier index
+    int ki = k;
+    bool ins = false;  // once inserted, the rest of the (sorted) list shifts down unconditionally
+#pragma unroll
+    for (int r = 0; r < kQn; ++r) {
+      if (ins || d < bd[r]) {
+        ins = true;
+        const double td = bd[r];
+        const int ti = bi[r];
+        bd[r] = d;
+        bi[r] = ki;
+        d = td;
+        ki = ti;
+      }
+    }
+  }
+  int out_i[kQn];
+#pragma unroll
+  for (int r = 0; r < kQn; ++r) {
+    double md = bd[0];
+    int mi = bi[0];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double od = __shfl_xor_sync(0xffffffffu, md, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, mi, off);
+      if (od < md || (od == md && oi < mi)) {
+        md = od;
+        mi = oi;
+      }
+    }
+    out_i[r] = (mi == 0x7fffffff) ? -1 : mi;
+    if (mi != 0x7fffffff && bi[0] == mi) {  // the owner pops its head
+#pragma unroll
+      for (int t = 0; t + 1 < kQn; ++t) {
+        bd[t] = bd[t + 1];
+        bi[t] = bi[t + 1];
+      }
+      bd[kQn - 1] = 1.7976931348623157e308;
+      bi[kQn - 1] = 0x7fffffff;
+    }
+  }
+  if (lane == 0) {
+    nearest[q] = out_i[0];
+    double mm = 1.7976931348623157e308;  // numeric_limits<double>::max(), :561
+#pragma unroll
+    for (int r = 0; r < kQn; ++r) {
+      if (knn != nullptr) knn[(size_t)q * kQn + r] = out_i[r];
+      if (out_i[r] >= 0) {
+        const double dist = chi2_exact(mean + (size_t)out_i[r] * 3, cov_inv + (size_t)out_i[r] * 9, p0, p1, p2);
+        if (dist < mm) mm = dist;
+      }
+    }
+    if (min_mdist2 != nullptr) min_mdist2[q] = mm;
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_render_views(const ViewArgs& a, cudaStream_t stream) {
@@ -483,6 +563,15 @@ cudaError_t launch_search_corr(const SearchArgs& a, cudaStream_t stream) {
 }
 
 int search_corr_max_num() { return kMaxNum; }
+
+cudaError_t launch_query_point(const double* mean, const double* cov_inv, int K, const double* d_pts, int M, int32_t* d_nearest,
+                               int32_t* d_knn, double* d_min_mdist2, cudaStream_t stream) {
+  if (M <= 0) return cudaSuccess;
+  const unsigned blocks = (unsigned)(((long long)M * 32 + 127) / 128);
+  query_point_kernel<<<blocks, 128, 0, stream>>>(mean, cov_inv, K, d_pts, M, d_nearest, d_knn, d_min_mdist2);
+  return cudaGetLastError();
+}
+int query_point_knn() { return kQn; }
 
 cudaError_t launch_check_assoc(const CheckArgs& a, cudaStream_t stream) {
   const long long total = (long long)a.B * a.N;

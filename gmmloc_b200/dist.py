@@ -68,6 +68,70 @@ def gather_rows(local: torch.Tensor, B: int, dst: int = 0, group=None) -> torch.
     return torch.cat(parts, dim=0)
 
 
+class FrameSharder:
+    """Pre-allocated plan for BASELINE configs[3]: ONE batch of B frames resident on rank `src` is scattered to the
+    ranks (contiguous shards, `dist.scatter` = grouped ncclSend / ncclRecv over NVLink on GPUs), every rank solves its
+    shard, and the per-frame results are gathered back to `src`.  All buffers are allocated once, so `scatter()` /
+    `gather()` only enqueue collectives (they may sit inside a timed region).  Works with NCCL on device tensors and
+    with gloo on CPU tensors (tests/test_dist_gloo.py).
+
+        plan = FrameSharder(B, N, device)
+        shard = plan.scatter(full)            # full: dict of B-leading tensors on rank src, None elsewhere
+        ... solve shard[...][:plan.count] ...
+        pose, status = plan.gather(pose_shard, status_shard)   # full-size tensors on rank src, (None, None) elsewhere
+    """
+
+    KEYS = {"pose0": ((7,), torch.float64), "pts_w": (None, torch.float32), "obs": (None, torch.float32), "octave": (None, torch.uint8)}
+
+    def __init__(self, B: int, N: int, device=None, src: int = 0, group=None):
+        self.B, self.N, self.src, self.group, self.device = B, N, src, group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.S = _max_shard(B, self.world)
+        self.lo, self.hi = shard_range(B, self.rank, self.world)
+        self.count = self.hi - self.lo
+        tails = {"pose0": (7,), "pts_w": (N, 3), "obs": (N, 3), "octave": (N,)}
+        self.recv = {k: torch.empty((self.S, *tails[k]), dtype=self.KEYS[k][1], device=device) for k in tails}
+        self._chunks = None
+        self._chunks_of = None
+        self._g_pose = self._g_status = None
+        if self.rank == src:
+            self._g_pose = [torch.empty((self.S, 7), dtype=torch.float64, device=device) for _ in range(self.world)]
+            self._g_status = [torch.empty((self.S,), dtype=torch.int32, device=device) for _ in range(self.world)]
+
+    def _make_chunks(self, full: dict):
+        chunks = {}
+        for k, buf in self.recv.items():
+            lst = []
+            for r in range(self.world):
+                a, b = shard_range(self.B, r, self.world)
+                if b - a == self.S:
+                    lst.append(full[k][a:b])  # a view of the resident batch: no copy on the source side
+                else:  # ragged tail: padded staging copy (made once per batch object)
+                    c = torch.zeros_like(buf)
+                    c[: b - a] = full[k][a:b]
+                    lst.append(c)
+            chunks[k] = lst
+        return chunks
+
+    def scatter(self, full: dict | None) -> dict:
+        if self.rank == self.src:
+            if self._chunks_of is not full:
+                self._chunks, self._chunks_of = self._make_chunks(full), full
+        for k, buf in self.recv.items():
+            dist.scatter(buf, self._chunks[k] if self.rank == self.src else None, src=self.src, group=self.group)
+        return self.recv
+
+    def gather(self, pose: torch.Tensor, status: torch.Tensor):
+        """pose S x 7 f64, status S i32 (rows >= count are padding).  Returns (B x 7, B) on rank src."""
+        dist.gather(pose, self._g_pose, dst=self.src, group=self.group)
+        dist.gather(status, self._g_status, dst=self.src, group=self.group)
+        if self.rank != self.src:
+            return None, None
+        spans = [shard_range(self.B, r, self.world) for r in range(self.world)]
+        return (torch.cat([self._g_pose[r][: b - a] for r, (a, b) in enumerate(spans)]),
+                torch.cat([self._g_status[r][: b - a] for r, (a, b) in enumerate(spans)]))
+
+
 def max_over_ranks(value: float, device=None, group=None) -> float:
     """Timing rule of the bench: the step time of a multi-GPU run is the max over ranks."""
     t = torch.tensor([value], dtype=torch.float64, device=device)

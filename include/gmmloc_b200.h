@@ -107,6 +107,18 @@ GMMLOC_API void gmmloc_map_destroy(gmmloc_map_t* map);
 /* GMM::countComponents, gaussian_mixture.h:153 */
 GMMLOC_API int gmmloc_map_size(const gmmloc_map_t* map);
 GMMLOC_API int gmmloc_map_device(const gmmloc_map_t* map);
+/* gmmloc_map_create with explicit tuning of the association grid built next to the map.  Every setting
+ * returns identical associations; the defaults (grid == NULL, or a field <= 0) are what gmmloc_map_create uses.
+ *  enable 0: no grid, the brute-force scan serves every association;  levels 2 or 3;  cell_size in metres (level 0);
+ *  tmax[l]: squared Mahalanobis radius covered by the lists of level l (36 / 144 / 400). */
+typedef struct {
+  int32_t enable;
+  int32_t levels;
+  double cell_size;
+  double tmax[3];
+} gmmloc_grid_options_t;
+GMMLOC_API gmmloc_status_t gmmloc_map_create_ex(const double* mean, const double* cov, int K, double deg_eps, int device,
+                                                const gmmloc_grid_options_t* grid, gmmloc_map_t** out);
 /* Device-built constants back to the host (any pointer may be NULL). Shapes: mean K x 3, cov K x 9,
  * cov_inv K x 9, det K, scale K x 3 (ascending), axis K x 9 (axis[r*3+c] = component r of eigenvector c),
  * sqrt_info K x 9 (lower L, cov_inv = L L^T), is_degenerated K, is_salient K.
@@ -127,6 +139,14 @@ GMMLOC_API gmmloc_status_t gmmloc_map_neighbors(const gmmloc_map_t* map, double 
  * gmmloc_check_map_association / gmmloc_keyframes_associate.  Not thread-safe: call it before the map is
  * shared.  *count (optional) receives the number of (i, j) pairs. */
 GMMLOC_API gmmloc_status_t gmmloc_map_build_neighbors(gmmloc_map_t* map, double thresh, int64_t* count);
+/* GMM::queryPoint(const Vector3d&, std::vector<int>&) (gaussian_mixture.h:169, gaussian_mixture.cpp:545-576) for M points:
+ * the 5 nearest component MEANS by squared Euclid distance (the reference asks its nanoflann kd-tree; here all K means
+ * are scanned, equal distances -> lower index first).  The reference then computes the minimum Mahalanobis distance
+ * over those five and discards it: res = { ret_index[0] }, the Euclid-nearest mean (:574) — the quirk is kept:
+ *  nearest M: what the reference returns in res[0];  knn M x 5 (optional): the list, ascending distance;
+ *  min_mdist2 M (optional): the discarded Mahalanobis minimum.   pts M x 3 (fp64, host). */
+GMMLOC_API gmmloc_status_t gmmloc_map_query_point(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const double* pts, int M,
+                                                  int32_t* nearest, int32_t* knn, double* min_mdist2);
 /* error bound of the fp32 scan in whitened units (|sqrt(s32) - sqrt(d2)| <= alpha for |x|_inf <= xmax) */
 GMMLOC_API gmmloc_status_t gmmloc_map_scan_bound(const gmmloc_map_t* map, double* alpha, double* xmax);
 
@@ -164,6 +184,16 @@ GMMLOC_API int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx);
  *   GMMLOC_GN_FP64             everything in fp64. */
 enum { GMMLOC_GN_FP64 = 0, GMMLOC_GN_MIXED = 1 };
 GMMLOC_API gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int precision);
+
+/* Tuning switches of a context for A/B measurements; every setting returns identical results.  (Environment variables
+ * are NOT consulted by a production build: they are compiled in only with -DGMMLOC_DEBUG_ENV.)
+ *   GMMLOC_OPT_GN_PREP          -1 automatic (default), 0 never, 1 always run the frame-preparation kernel ahead of the
+ *                               mixed-precision frame GN;
+ *   GMMLOC_OPT_E2E_CHUNK        frames per pipeline chunk of the host entry point gmmloc_frames_solve (0 = automatic:
+ *                               6 frames per SM);
+ *   GMMLOC_OPT_E2E_SHORT_FIRST  1: the first pipeline chunk is a third of the others (default 0). */
+enum { GMMLOC_OPT_GN_PREP = 0, GMMLOC_OPT_E2E_CHUNK = 1, GMMLOC_OPT_E2E_SHORT_FIRST = 2 };
+GMMLOC_API gmmloc_status_t gmmloc_ctx_set_option(gmmloc_ctx_t* ctx, int option, int64_t value);
 
 /* page-locked host memory for the host entry points (pageable buffers also work, via staging) */
 GMMLOC_API gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out);
@@ -301,13 +331,21 @@ GMMLOC_API gmmloc_status_t gmmloc_keyframes_associate(gmmloc_ctx_t* ctx, const g
  *  obs sum E x 3 (u v u_r; u_r < 0 => EdgeSE3ProjectXYZ, else EdgeStereoSE3ProjectXYZ), octave sum E.
  * Outputs (optional): obs_outlier sum E (the vToErase test, :857-881), assoc_cleared sum L (associations the
  * reference clears, :842-855), iters B x 3 (LM iterations run per stage), status B (GMMLOC_FRAME_NUMERIC when a
- * linear solve failed inside the LM loop; g2o carries on, and so does this). */
+ * linear solve failed inside the LM loop; g2o carries on, and so does this).
+ *  stop (optional, host pointer): the reference's `bool* pbStopFlag` (optimizer.setForceStopFlag, :541-542), raised by
+ *  another host thread to abort the BA (Localization::insertKeyFrame, localization.cpp:401-405).  It is read where the
+ *  reference / g2o read it: before the first stage (raised => the window is returned untouched, iters 0 0 0, :765-767),
+ *  ahead of every LM iteration and after every rejected LM trial (g2o's terminate()), and after stage 2 (raised => no
+ *  reprojection gating, no stage 3, :791-795; results are still written).  The calling thread mirrors *stop into
+ *  device-mapped memory while the kernel runs.  *stop > 0: raised; 0: not raised; a negative value -n is a deterministic
+ *  replay hook: the flag reads as raised from its n-th poll on (used by the parity tests). */
 GMMLOC_API gmmloc_status_t gmmloc_local_ba(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
                                            const gmmloc_params_t* params, int B, const int32_t* pose_ptr, double* pose,
                                            const uint8_t* fixed, const int32_t* prior_idx, const int32_t* pt_ptr, double* pts,
                                            const int32_t* assoc, const int32_t* obs_ptr, const int32_t* obs_pt,
                                            const int32_t* obs_kf, const float* obs, const uint8_t* octave,
-                                           uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters, int32_t* status);
+                                           uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters, int32_t* status,
+                                           const volatile int32_t* stop);
 
 #ifdef __cplusplus
 }

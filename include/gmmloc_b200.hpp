@@ -98,7 +98,22 @@ class GMM {
   explicit GMM(gmmloc_map_t* adopt) : h_(adopt) {}
   GMM(const GMM&) = delete;
   void operator=(const GMM&) = delete;
-  ~GMM() { gmmloc_map_destroy(h_); }
+  ~GMM() {
+    if (qctx_) gmmloc_ctx_destroy(qctx_);
+    gmmloc_map_destroy(h_);
+  }
+
+  // ≙ void GMM::queryPoint(const Eigen::Vector3d& pt, std::vector<int>& res)  (gaussian_mixture.h:169,
+  // gaussian_mixture.cpp:545-576): res = { index of the component whose mean is Euclid-nearest to pt } — the reference
+  // computes the Mahalanobis minimum over its 5-NN and then returns ret_index[0]; the quirk is kept.  Uses a private
+  // context created on first use: like renderView (which mutates components2d_), call it from one thread at a time.
+  void queryPoint(const Vector3d& pt, std::vector<int>& res) const {
+    if (!qctx_) check(gmmloc_ctx_create(gmmloc_map_device(h_), &qctx_));
+    int32_t nn = -1;
+    check(gmmloc_map_query_point(qctx_, h_, pt.data(), 1, &nn, nullptr, nullptr));
+    res.clear();
+    if (nn >= 0) res.push_back((int)nn);
+  }
 
   size_t countComponents() const { return (size_t)gmmloc_map_size(h_); }
 
@@ -139,6 +154,7 @@ class GMM {
 
  private:
   gmmloc_map_t* h_ = nullptr;
+  mutable gmmloc_ctx_t* qctx_ = nullptr;
   mutable std::vector<GaussianComponent> comps_;
 };
 
@@ -208,6 +224,18 @@ class Optimizer {
     if (d2) d2->resize((size_t)N);
     check(gmmloc_associate(ctx_, model_->handle(), pts_w, 1, N, gate, a.data(), d2 ? d2->data() : nullptr));
     return a;
+  }
+
+  // batched GMM::queryPoint on this context: nearest[i] = what the reference returns in res[0] for pts[i]
+  std::vector<int32_t> queryPoints(const std::vector<Vector3d>& pts, std::vector<std::array<int32_t, 5>>* knn = nullptr,
+                                   std::vector<double>* min_mdist2 = nullptr) {
+    const int M = (int)pts.size();
+    std::vector<int32_t> nn((size_t)M);
+    if (knn) knn->resize((size_t)M);
+    if (min_mdist2) min_mdist2->resize((size_t)M);
+    check(gmmloc_map_query_point(ctx_, model_->handle(), M ? pts[0].data() : nullptr, M, nn.data(),
+                                 knn && M ? (*knn)[0].data() : nullptr, min_mdist2 && M ? min_mdist2->data() : nullptr));
+    return nn;
   }
 
   // ≙ static StrOptStat GMMLoc::optimizePoint(pt3d, kp, Tcw, comp, proj_z)   (one problem)
@@ -355,7 +383,8 @@ class Optimizer {
 
   // ≙ void Localization::jointOptimization(KeyFrame*, bool* stop, Map*): the caller flattens the window (the
   // reference's graph construction, :460-766) and applies the results (:842-925); the 3-stage LM runs on the GPU.
-  void jointOptimization(LocalWindow& w) {
+  // `stop` is the reference's pbStopFlag (may be raised by another thread while this call runs; see gmmloc_local_ba).
+  void jointOptimization(LocalWindow& w, const volatile int32_t* stop = nullptr) {
     const int32_t P = (int32_t)w.poses.size(), L = (int32_t)w.points.size(), E = (int32_t)w.obs_pt.size();
     if ((int32_t)w.fixed.size() != P || (int32_t)w.assoc.size() != L || (int32_t)w.obs_kf.size() != E || (int32_t)w.obs.size() != E)
       throw Error(GMMLOC_EINVAL, "LocalWindow: size mismatch");
@@ -376,7 +405,7 @@ class Optimizer {
     int32_t status = 0;
     check(gmmloc_local_ba(ctx_, model_->handle(), &cam_, &params_, 1, pp, pose.data(), w.fixed.data(), &w.prior_idx, lp, pts.data(),
                           w.assoc.data(), ep, w.obs_pt.data(), w.obs_kf.data(), obs.data(), oct.data(), w.erase.data(),
-                          w.assoc_cleared.data(), w.iters.data(), &status));
+                          w.assoc_cleared.data(), w.iters.data(), &status, stop));
     for (int32_t i = 0; i < P; ++i)
       for (int j = 0; j < 7; ++j) w.poses[i].v[j] = pose[7 * (size_t)i + j];
     for (int32_t l = 0; l < L; ++l) w.points[l] = {pts[3 * (size_t)l], pts[3 * (size_t)l + 1], pts[3 * (size_t)l + 2]};

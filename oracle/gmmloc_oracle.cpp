@@ -252,8 +252,11 @@ const Sigma2Inv g_sigma2inv;
 struct Cam { double fx, fy, cx, cy, bf; };
 
 // reprojection residual + Jacobians at camera-frame point pc = R x + t.
-//  stereo: EdgeStereoSE3ProjectXYZ  (point Jacobian identical to factors.cpp:133-168)
-//  mono:   EdgeSE3ProjectXYZ        (point Jacobian identical to factors.cpp:84-107)
+//  stereo: EdgeStereoSE3ProjectXYZ / EdgeProjectXYZOnlyStereo: the element-wise point Jacobian of factors.cpp:133-168
+//  mono:   EdgeSE3ProjectXYZ / EdgeProjectXYZOnly: `_jacobianOplusXi = -1. / z * tmp * R` (factors.cpp:84-107), restated
+//          in the order Eigen evaluates a fixed-size lazy product (the scaled 2x3 `-1./z * tmp` is materialised first,
+//          every coefficient is then the left-to-right sum over k of T(i,k) * R(k,j)).  That evaluation order is
+//          recalled from Eigen 3.3, not verifiable here (no Eigen in the box): parity unpinned, like everything g2o.
 // Jl[m][3] point Jacobian, Jp[m][6] pose Jacobian ([omega; upsilon], SURVEY Appx B.2), e[m].
 inline void reproj_edge(const Cam& cam, const double* R, const double pc[3], const double obs[3], bool stereo,
                         double e[3], double Jl[9], double Jp[18]) {
@@ -270,11 +273,20 @@ inline void reproj_edge(const Cam& cam, const double* R, const double pc[3], con
     const double v = y / z * cam.fy + cam.cy;
     e[0] = obs[0] - u; e[1] = obs[1] - v; e[2] = 0.0;
   }
-  if (Jl) {
+  if (Jl && stereo) {
     for (int j = 0; j < 3; ++j) {
       Jl[0 * 3 + j] = -cam.fx * M(R, 0, j) / z + cam.fx * x * M(R, 2, j) / z_2;
       Jl[1 * 3 + j] = -cam.fy * M(R, 1, j) / z + cam.fy * y * M(R, 2, j) / z_2;
-      Jl[2 * 3 + j] = stereo ? Jl[0 * 3 + j] - cam.bf * M(R, 2, j) / z_2 : 0.0;
+      Jl[2 * 3 + j] = Jl[0 * 3 + j] - cam.bf * M(R, 2, j) / z_2;
+    }
+  } else if (Jl) {
+    const double s = -1. / z;
+    const double T00 = s * cam.fx, T01 = s * 0.0, T02 = s * (-x / z * cam.fx);
+    const double T10 = s * 0.0, T11 = s * cam.fy, T12 = s * (-y / z * cam.fy);
+    for (int j = 0; j < 3; ++j) {
+      Jl[0 * 3 + j] = (T00 * M(R, 0, j) + T01 * M(R, 1, j)) + T02 * M(R, 2, j);
+      Jl[1 * 3 + j] = (T10 * M(R, 0, j) + T11 * M(R, 1, j)) + T12 * M(R, 2, j);
+      Jl[2 * 3 + j] = 0.0;
     }
   }
   if (Jp) {
@@ -1268,6 +1280,39 @@ void oracle_search_correspondence(const oracle_comp2d_t* view, int V, const doub
   }
 }
 
+int oracle_query_point(const oracle_comp_t* comps, int K, const double pt[3], int num, int32_t* knn, double* min_mdist2) {
+  // GMM::queryPoint (gaussian_mixture.cpp:545-576): knnSearch(pt, 5) over the component means (ascending squared
+  // Euclid distance; nanoflann kd-tree in the reference, brute force here: equal distances -> lower index first),
+  // the minimum Mahalanobis distance over the neighbours is computed (:563-572) and DISCARDED: the function returns
+  // ret_index[0], the Euclid-nearest mean (:574) — quirk preserved.  Returns -1 for an empty map (res stays empty).
+  std::vector<double> bd(num);
+  std::vector<int> bi(num);
+  int n = 0;
+  for (int k = 0; k < K; ++k) {
+    const double d0 = pt[0] - comps[k].mean[0], d1 = pt[1] - comps[k].mean[1], d2 = pt[2] - comps[k].mean[2];
+    const double d = d0 * d0 + d1 * d1 + d2 * d2;  // FLANNPoints3d::kdtree_distance, gaussian_mixture.h:33-39
+    if (n == num && !(d < bd[num - 1])) continue;
+    int pos = (n < num) ? n : num - 1;
+    while (pos > 0 && d < bd[pos - 1]) {
+      bd[pos] = bd[pos - 1];
+      bi[pos] = bi[pos - 1];
+      --pos;
+    }
+    bd[pos] = d;
+    bi[pos] = k;
+    if (n < num) ++n;
+  }
+  double min_dist = std::numeric_limits<double>::max();
+  for (int r = 0; r < n; ++r) {
+    const double dist = oracle_chi2(&comps[bi[r]], pt);
+    if (dist < min_dist) min_dist = dist;
+  }
+  if (knn)
+    for (int r = 0; r < num; ++r) knn[r] = r < n ? bi[r] : -1;
+  if (min_mdist2) *min_mdist2 = min_dist;
+  return n ? bi[0] : -1;
+}
+
 void oracle_unproject3(const oracle_camera_t* cam, const double pose[7], const double uv[2], double depth, double pt_w[3]) {
   // pinhole_camera.cpp:20-33 then getTwc().map (SE3Quat::inverse: r = conj, t = r * (t * -1))
   const double pc[3] = {depth * (uv[0] - cam->cx) / cam->fx, depth * (uv[1] - cam->cy) / cam->fy, depth};
@@ -1732,12 +1777,24 @@ struct LocalBA {
     return true;
   }
 
-  // OptimizationAlgorithmLevenberg, `iters` iterations (SURVEY Appx B.7); returns the iterations run
+  // g2o's force-stop flag (SparseOptimizer::setForceStopFlag(pbStopFlag), localization_opt.cpp:541-542): terminate()
+  // reads *flag wherever g2o polls it.  stop > 0: raised; stop == 0 / no flag: never; stop == -n: the flag reads as
+  // raised from the n-th poll on (deterministic replay of an asynchronous stop, the parity tests' hook).
+  int32_t stop = 0;
+  int polls = 0;
+  bool terminate() {
+    ++polls;
+    return stop > 0 || (stop < 0 && polls >= -stop);
+  }
+
+  // OptimizationAlgorithmLevenberg, `iters` iterations (SURVEY Appx B.7); returns the iterations run.
+  // terminate() is polled where g2o does: `for (i < iterations && !terminate() && ok)` (SparseOptimizer::optimize)
+  // and `while (rho < 0 && qmax < maxTrials && !terminate())` (OptimizationAlgorithmLevenberg::solve).
   int optimize(int iters, std::vector<double>& pose, std::vector<double>& pts) {
     double lambda = 0.0, ni = 2.0;
     bool ok = true;
     int it = 0;
-    for (; it < iters && ok; ++it) {
+    for (; it < iters && !terminate() && ok; ++it) {
       double cur_chi = active_errors(pose, pts);
       build(pose, pts);
       if (it == 0) {
@@ -1780,7 +1837,7 @@ struct LocalBA {
           if (!std::isfinite(lambda)) break;
         }
         ++qmax;
-      } while (rho < 0 && qmax < 10);
+      } while (rho < 0 && qmax < 10 && !terminate());
       if (qmax == 10 || rho == 0 || !std::isfinite(lambda)) ok = false;
     }
     return it;
@@ -1802,12 +1859,28 @@ int oracle_local_ba(const oracle_comp_t* comps, int K, const oracle_camera_t* ca
                     double* pose_io, const uint8_t* fixed, int prior_idx, int L, double* pts_io, const int32_t* assoc, int E,
                     const int32_t* obs_pt, const int32_t* obs_kf, const float* obs, const uint8_t* octave,
                     uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters) {
+  return oracle_local_ba_stop(comps, K, camp, prm, P, pose_io, fixed, prior_idx, L, pts_io, assoc, E, obs_pt, obs_kf, obs, octave,
+                              obs_outlier, assoc_cleared, iters, 0);
+}
+
+int oracle_local_ba_stop(const oracle_comp_t* comps, int K, const oracle_camera_t* camp, const oracle_params_t* prm, int P,
+                         double* pose_io, const uint8_t* fixed, int prior_idx, int L, double* pts_io, const int32_t* assoc, int E,
+                         const int32_t* obs_pt, const int32_t* obs_kf, const float* obs, const uint8_t* octave,
+                         uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters, int32_t stop) {
   for (int e = 0; e < E; ++e)
     if (obs_pt[e] < 0 || obs_pt[e] >= L || obs_kf[e] < 0 || obs_kf[e] >= P) return -1;
   for (int l = 0; l < L; ++l)
     if (assoc[l] >= K) return -1;
   if (prior_idx >= P) return -1;
   LocalBA ba;
+  ba.stop = stop;
+  // `if (pbStopFlag) if (*pbStopFlag) return;` before the first optimize (:765-767): nothing is touched
+  if (ba.terminate()) {
+    if (obs_outlier) for (int e = 0; e < E; ++e) obs_outlier[e] = 0;
+    if (assoc_cleared) for (int l = 0; l < L; ++l) assoc_cleared[l] = 0;
+    if (iters) iters[0] = iters[1] = iters[2] = 0;
+    return 0;
+  }
   ba.comps = comps;
   ba.cam = Cam{camp->fx, camp->fy, camp->cx, camp->cy, camp->bf};
   ba.prm = prm;
@@ -1866,11 +1939,14 @@ int oracle_local_ba(const oracle_comp_t* comps, int K, const oracle_camera_t* ca
     const double* er = &ba.err[3 * (size_t)e];
     return ba.w[e] * ((er[0] * er[0] + er[1] * er[1]) + er[2] * er[2]);
   };
-  for (int e = 0; e < E; ++e)
-    if (edge_chi2(e) > (ba.stereo[e] ? 7.815 : 5.991) || !depth_positive(e)) ba.level[e] = 1;
-  ba.robust = false;  // e->setRobustKernel(0)
-  // stage 3: optimize(40)  (:826-828)
-  its[2] = ba.optimize(40, pose, pts);
+  // bDoMore = !*pbStopFlag (:791-795): a raised flag skips the reprojection gating, the kernel removal and stage 3
+  if (!ba.terminate()) {
+    for (int e = 0; e < E; ++e)
+      if (edge_chi2(e) > (ba.stereo[e] ? 7.815 : 5.991) || !depth_positive(e)) ba.level[e] = 1;
+    ba.robust = false;  // e->setRobustKernel(0)
+    // stage 3: optimize(40)  (:826-828)
+    its[2] = ba.optimize(40, pose, pts);
+  }
   // results (:834-881)
   if (assoc_cleared)
     for (int l = 0; l < L; ++l) {

@@ -164,6 +164,10 @@ int oracle_render_view(const oracle_comp_t* comps, int K, const oracle_camera_t*
  * position), keeping those with 2-D MDist2 < 9.0.  cand N x num: positions in the view list, -1 padded. */
 void oracle_search_correspondence(const oracle_comp2d_t* view, int V, const double* uv, int N, int num, int32_t* cand);
 
+/* GMM::queryPoint (gaussian_mixture.cpp:545-576): 5-NN of the component means, returns ret_index[0] (Euclid-nearest;
+ * the Mahalanobis minimum the reference computes is returned through min_mdist2 only).  knn: num entries, -1 padded. */
+int oracle_query_point(const oracle_comp_t* comps, int K, const double pt[3], int num, int32_t* knn, double* min_mdist2);
+
 /* a13: Frame::unproject3 (frame.cpp:27-36, pinhole_camera.cpp:20-33): pt_w = T_wc * [z (u-cx)/fx, z (v-cy)/fy, z]. */
 void oracle_unproject3(const oracle_camera_t* cam, const double pose[7], const double uv[2], double depth, double pt_w[3]);
 
@@ -208,6 +212,12 @@ int oracle_local_ba(const oracle_comp_t* comps, int K, const oracle_camera_t* ca
                     double* pose, const uint8_t* fixed, int prior_idx, int L, double* pts, const int32_t* assoc, int E,
                     const int32_t* obs_pt, const int32_t* obs_kf, const float* obs, const uint8_t* octave,
                     uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters);
+/* the same with g2o's force-stop flag (localization_opt.cpp:541-542, 765-767, 791-795): stop > 0 raised before the call,
+ * 0 never, -n raised from the n-th terminate() poll on (deterministic replay of an asynchronous stop). */
+int oracle_local_ba_stop(const oracle_comp_t* comps, int K, const oracle_camera_t* cam, const oracle_params_t* prm, int P,
+                    double* pose, const uint8_t* fixed, int prior_idx, int L, double* pts, const int32_t* assoc, int E,
+                    const int32_t* obs_pt, const int32_t* obs_kf, const float* obs, const uint8_t* octave,
+                    uint8_t* obs_outlier, uint8_t* assoc_cleared, int32_t* iters, int32_t stop);
 
 /* g2o SE3Quat::log (se3quat.h) of pose = qx qy qz qw tx ty tz -> [omega; upsilon] */
 void oracle_se3_log(const double pose[7], double xi[6]);

@@ -45,6 +45,47 @@ def build(force: bool = False) -> Path:
     return so
 
 
+REFERENCE = Path("/root/reference")
+_REF_SO = _HERE / "_ref" / "libref_nanoflann.so"
+
+
+def build_ref(force: bool = False) -> Path | None:
+    """oracle/_ref: the kNN harness compiled against the reference's own vendored nanoflann.hpp (the only part of the
+    reference's path that builds without Eigen / g2o).  Built where /root/reference exists (this container); elsewhere
+    (the GPU box) the prebuilt file that travelled with the snapshot is used.  Returns None when neither is possible."""
+    hdr = REFERENCE / "gmmloc" / "include" / "gmmloc" / "utils" / "nanoflann.hpp"
+    src = _HERE / "ref_nanoflann.cpp"
+    if hdr.exists() and (force or not _REF_SO.exists() or _REF_SO.stat().st_mtime < src.stat().st_mtime):
+        _REF_SO.parent.mkdir(exist_ok=True)
+        cxx = os.environ.get("CXX", "g++")
+        subprocess.run([cxx, "-O2", "-std=c++14", "-fPIC", "-shared", f"-I{REFERENCE / 'gmmloc' / 'include'}", "-o",
+                        str(_REF_SO) + ".tmp", str(src)], check=True, cwd=_HERE)
+        os.replace(str(_REF_SO) + ".tmp", _REF_SO)
+    return _REF_SO if _REF_SO.exists() else None
+
+
+_ref_lib = None
+
+
+def ref_knn(pts, queries, k: int):
+    """knnSearch of the reference's nanoflann kd-tree (leaf size 5, L2_Simple_Adaptor) over `pts` (n x 2 or n x 3):
+    returns (idx nq x k, squared distances nq x k, counts nq); idx is -1 padded.  None when oracle/_ref is unavailable."""
+    global _ref_lib
+    so = build_ref()
+    if so is None:
+        return None
+    if _ref_lib is None:
+        _ref_lib = C.CDLL(str(so))
+    pts = np.ascontiguousarray(pts, np.float64)
+    q = np.ascontiguousarray(queries, np.float64).reshape(-1, pts.shape[1])
+    fn = {2: _ref_lib.ref_knn2d, 3: _ref_lib.ref_knn3d}[pts.shape[1]]
+    idx = np.zeros((len(q), k), np.int64)
+    dist = np.zeros((len(q), k))
+    cnt = np.zeros(len(q), np.int32)
+    fn(_p(pts), C.c_int64(len(pts)), _p(q), C.c_int64(len(q)), C.c_int(k), _p(idx), _p(dist), _p(cnt))
+    return idx, dist, cnt
+
+
 class Comp(C.Structure):
     _fields_ = [("mean", C.c_double * 3), ("cov", C.c_double * 9), ("cov_inv", C.c_double * 9),
                 ("det", C.c_double), ("scale", C.c_double * 3), ("axis", C.c_double * 9),
@@ -311,6 +352,17 @@ def search_correspondence(view, uv, num=5) -> np.ndarray:
     return cand
 
 
+def query_point(comps, pt, num=5):
+    """GMM::queryPoint: (returned index = Euclid-nearest mean, the num-NN list, min Mahalanobis d2 over it)."""
+    pt = np.ascontiguousarray(pt, np.float64)
+    knn = np.zeros(num, np.int32)
+    md = C.c_double()
+    L = lib()
+    L.oracle_query_point.restype = C.c_int
+    r = L.oracle_query_point(_p(comps), C.c_int(len(comps)), _p(pt), C.c_int(num), _p(knn), C.byref(md))
+    return r, knn, md.value
+
+
 def unproject3(pose, uv, depth, cam=None) -> np.ndarray:
     cam = cam or v1_camera()
     pose = np.ascontiguousarray(pose, np.float64)
@@ -356,7 +408,7 @@ def keyframe_associate(comps, nbr, pose, obs, depth, octave, num=5, cam=None, pr
     return dict(assoc=assoc, pt3d=pt3d, cand=cand, nview=nview.value)
 
 
-def local_ba(comps, pose, fixed, pts, assoc, obs_pt, obs_kf, obs, octave, prior_idx=-1, cam=None, prm=None):
+def local_ba(comps, pose, fixed, pts, assoc, obs_pt, obs_kf, obs, octave, prior_idx=-1, cam=None, prm=None, stop=0):
     """Localization::jointOptimization (3-stage LM local BA): dict(pose, pts, obs_outlier, assoc_cleared, iters)."""
     cam = cam or v1_camera()
     prm = prm or default_params()
@@ -372,11 +424,11 @@ def local_ba(comps, pose, fixed, pts, assoc, obs_pt, obs_kf, obs, octave, prior_
     outl = np.zeros(E, np.uint8)
     cleared = np.zeros(L, np.uint8)
     iters = np.zeros(3, np.int32)
-    fn = lib().oracle_local_ba
+    fn = lib().oracle_local_ba_stop
     fn.restype = C.c_int
     rc = fn(_p(comps), C.c_int(len(comps)), C.byref(cam), C.byref(prm), C.c_int(P), _p(pose), _p(fixed), C.c_int(int(prior_idx)),
             C.c_int(L), _p(pts), _p(assoc), C.c_int(E), _p(obs_pt), _p(obs_kf), _p(obs), _p(octave), _p(outl), _p(cleared),
-            _p(iters))
+            _p(iters), C.c_int32(int(stop)))
     if rc != 0:
         raise ValueError("oracle_local_ba: invalid indices")
     return dict(pose=pose, pts=pts, obs_outlier=outl, assoc_cleared=cleared, iters=iters)

@@ -161,12 +161,55 @@ int main(int argc, char** argv) {
       w.obs_pt.push_back(i); w.obs_kf.push_back(0); w.obs.push_back(f0);
       w.obs_pt.push_back(i); w.obs_kf.push_back(1); w.obs.push_back(f1);
     }
+    {  // pbStopFlag raised before the call (localization_opt.cpp:765-767): the window comes back untouched
+      LocalWindow ws = w;
+      const volatile int32_t stop = 1;
+      opt.jointOptimization(ws, &stop);
+      REQUIRE(ws.iters[0] == 0 && ws.iters[1] == 0 && ws.iters[2] == 0);
+      REQUIRE(ws.poses[0].v == w.poses[0].v && ws.points[3] == w.points[3]);
+      const volatile int32_t go = 0;  // a flag that stays down changes nothing
+      LocalWindow wa = w, wb = w;
+      opt.jointOptimization(wa, &go);
+      opt.jointOptimization(wb);
+      REQUIRE(wa.poses[0].v == wb.poses[0].v && wa.iters == wb.iters);
+    }
     opt.jointOptimization(w);
     REQUIRE(w.iters[0] == 5 && w.iters[1] == 5 && w.iters[2] >= 1);
     REQUIRE(std::fabs(w.poses[0].v[4]) < 1e-4 && std::fabs(w.poses[0].v[5]) < 1e-4 && w.poses[1].v[4] == -0.2);
     int erased = 0;
     for (uint8_t e : w.erase) erased += e;
     REQUIRE(erased == 0);
+  }
+
+  // GMM::queryPoint: the Euclid-nearest mean (the reference's ret_index[0] quirk), also where another component is
+  // nearer in the Mahalanobis sense: 1 cm in front of the wall z = 3 but closer to the MEAN of a floor component
+  {
+    std::vector<int> res;
+    gmm->queryPoint({mean[15], mean[16], mean[17] + 0.01}, res);
+    REQUIRE(res.size() == 1 && res[0] == 5);
+    std::vector<std::array<int32_t, 5>> knn;
+    std::vector<double> md;
+    auto nn = opt.queryPoints({{mean[15], mean[16], mean[17] + 0.01}, {-1.05 + 0.05, 1.5 - 0.2, 3.0 + 0.05}}, &knn, &md);
+    REQUIRE(nn[0] == 5 && knn[0][0] == 5 && std::fabs(md[0] - 100.0) < 1e-6);  // 1 cm / 1 mm sigma
+    REQUIRE(nn[1] == 24 && knn[1][0] == 24);  // 20 cm above the floor component 24 (d2 = 4e4 there) — still returned
+  }
+
+  // gmmloc_render_views through the raw ABI with cap > K and B = 2: the host rows keep the caller's stride `cap`
+  {
+    const int cap = K + 7, B = 2;
+    std::vector<double> poses = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 1, 0.1, 0, 0};
+    std::vector<int32_t> cnt(B), ids((size_t)B * cap, -2);
+    std::vector<double> depth((size_t)B * cap, -2.0);
+    REQUIRE(gmmloc_render_views(opt.handle(), gmm->handle(), &cam, poses.data(), B, cap, cnt.data(), nullptr, ids.data(), nullptr,
+                                nullptr, depth.data()) == GMMLOC_OK);
+    for (int b = 0; b < B; ++b) {
+      REQUIRE(cnt[b] > 0 && cnt[b] <= K);
+      for (int j = 0; j < cap; ++j) {
+        if (j < cnt[b]) REQUIRE(ids[(size_t)b * cap + j] >= 0 && ids[(size_t)b * cap + j] < K && depth[(size_t)b * cap + j] > 0.0);
+        if (j >= K) REQUIRE(ids[(size_t)b * cap + j] == -1 && depth[(size_t)b * cap + j] == 0.0);
+      }
+      for (int j = 1; j < cnt[b]; ++j) REQUIRE(depth[(size_t)b * cap + j] <= depth[(size_t)b * cap + j - 1]);  // depth descending
+    }
   }
 
   // .gmm round trip through GMMUtility

@@ -38,6 +38,22 @@ def _worker(rank, world, port, B, N, q):
         full = gd.gather_rows(res, B, dst=0)
         tmax = gd.max_over_ranks(float(rank + 1))
         assert tmax == float(world)
+        # the pre-allocated plan bench.py / configs[3] uses: same shards, results back in frame order
+        plan = gd.FrameSharder(B, N)
+        for _ in range(2):  # reusable: the second round goes through the cached chunk views
+            sh = plan.scatter(batch)
+            assert plan.count == hi - lo
+            for k in ("pose0", "pts_w", "obs", "octave"):
+                assert torch.equal(sh[k][: plan.count], shard[k]), k
+            pose = torch.zeros((plan.S, 7), dtype=torch.float64)
+            pose[: plan.count] = sh["pose0"][: plan.count] * 2.0
+            status = torch.full((plan.S,), -7, dtype=torch.int32)
+            status[: plan.count] = torch.arange(lo, hi, dtype=torch.int32)
+            gp, gs = plan.gather(pose, status)
+            if rank == 0:
+                assert torch.equal(gp, batch["pose0"] * 2.0) and torch.equal(gs, torch.arange(B, dtype=torch.int32))
+            else:
+                assert gp is None and gs is None
         if rank == 0:
             assert full.shape == (B, 2)
             assert torch.equal(full[:, 0], torch.arange(B, dtype=torch.float64))

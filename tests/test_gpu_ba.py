@@ -89,3 +89,57 @@ def test_local_ba_argument_checks(gpu, ba_map):
     with pytest.raises(g.GmmlocError):
         ctx.jointOptimization(m, [bad])
     assert ctx.jointOptimization(m, []) == []
+
+
+@pytest.mark.parametrize("stop", [1, -1, -3, -7, -12, -14, -30, -1000])
+def test_local_ba_stop_flag(gpu, oracle, ba_map, stop):
+    """Localization::jointOptimization's pbStopFlag (localization_opt.cpp:541-542, 765-767, 791-795): raised before the call
+    (1, -1) the window comes back untouched; -n replays a flag that rises at its n-th poll — inside stage 1 (-3), at the
+    first iteration of stage 2 (-7), at the check after stage 2 (-12 when no LM trial was rejected: 1 + 5 + 5 polls, then
+    the 12th), inside stage 3 (-14, -30), or never (-1000)."""
+    g, ctx = gpu
+    m, comps, mean, cov = ba_map
+    pb = synth.make_ba_problem(mean, cov, 6, 2, 300, seed=77)
+    want = oracle.local_ba(comps, pb["pose"], pb["fixed"], pb["pts"], pb["assoc"], pb["obs_pt"], pb["obs_kf"], pb["obs"],
+                           pb["octave"], stop=stop)
+    out = ctx.jointOptimization(m, [pb], stop=stop)[0]
+    assert np.array_equal(out["iters"][:2], want["iters"][:2]), (out["iters"], want["iters"])
+    if stop in (1, -1):
+        assert list(out["iters"]) == [0, 0, 0]
+        assert np.array_equal(out["pose"], pb["pose"]) and np.array_equal(out["pts"], pb["pts"])  # untouched, not even normalised
+        assert not out["obs_outlier"].any() and not out["assoc_cleared"].any()
+        return
+    if stop > -1000 and want["iters"][2] < 40 and stop != -30:
+        assert out["iters"][2] == want["iters"][2]
+    assert np.array_equal(out["obs_outlier"], want["obs_outlier"])
+    assert np.array_equal(out["assoc_cleared"], want["assoc_cleared"])
+    for i in range(len(pb["pose"])):
+        ang, dt = _pose_err(out["pose"][i], want["pose"][i])
+        assert ang < TOL_RAD and dt < TOL_M, (i, ang, dt)
+    assert np.abs(out["pts"] - want["pts"]).max() < 1e-4
+    if stop == -3:
+        assert list(want["iters"]) == [1, 0, 0]  # poll 1 = entry, poll 2 admits iteration 0 of stage 1, poll 3 stops it
+    if stop == -12:
+        assert list(want["iters"][:2]) == [5, 5]
+
+
+def test_local_ba_stop_flag_raised_by_another_thread(gpu, ba_map):
+    """The asynchronous use the reference makes of the flag: another host thread raises it while the BA runs
+    (Localization::insertKeyFrame, localization.cpp:401-405).  Timing is not deterministic; the call must return, early."""
+    import threading
+    import time
+    g, ctx = gpu
+    m, comps, mean, cov = ba_map
+    pbs = [synth.make_ba_problem(mean, cov, 12, 3, 1500, seed=90 + j) for j in range(8)]
+    full = ctx.jointOptimization(m, pbs)
+    flag = np.zeros(1, np.int32)
+
+    def raise_it():
+        time.sleep(0.02)
+        flag[0] = 1
+
+    th = threading.Thread(target=raise_it)
+    th.start()
+    outs = ctx.jointOptimization(m, pbs, stop=flag)
+    th.join()
+    assert sum(int(o["iters"].sum()) for o in outs) < sum(int(o["iters"].sum()) for o in full)

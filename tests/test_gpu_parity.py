@@ -295,6 +295,29 @@ def test_frames_solve_shipped_map_v1_03_poses(gpu, oracle, golden_maps, gt_v1_03
     assert np.all(out["status"] == 0)
 
 
+def test_frames_solve_c3_full_v1_03_replay(gpu, oracle, golden_maps, gt_v1_03):
+    """BASELINE configs[2] at full size — every one of the 2 149 gt_sync poses of V1_03 x 1 200 landmarks on the shipped
+    v1.gmm, exactly the batch `bench.py --workload c3` times — against the oracle: assignments bit-exact, status and
+    outlier flags identical, poses within 1e-5 rad / 1e-4 m."""
+    g, ctx = gpu
+    gm = golden_maps["v1"]
+    fr = synth.make_frames(gm["mean"], gm["cov"], len(gt_v1_03), 1200, seed=0, poses_wc=gt_v1_03[:, 1:8])
+    out, exp, worst = _check_frames(g, ctx, oracle, gm["mean"], gm["cov"], fr)
+    assert len(out["status"]) == 2149 and np.all(out["status"] == 0)
+
+
+def test_frames_solve_c5_full_size(gpu, oracle):
+    """BASELINE configs[4] at its real shape (N = 5 000, K = 50 000, 95 % planar, 30 % monocular, Huber on): frames
+    24..31 of the batch `bench.py --workload c5` times.  Frame 29 is the one frame of that 512-frame batch that ends
+    with GMMLOC_FRAME_NUMERIC (a singular point block) — in the oracle as on the GPU; the others solve."""
+    g, ctx = gpu
+    mean, cov = synth.make_map(50000, 0.95)
+    fr = synth.make_frames(mean, cov, 8, 5000, seed=0, mono_frac=0.3, first_frame=24)
+    out, exp, worst = _check_frames(g, ctx, oracle, mean, cov, fr, robust=1)
+    assert list(np.nonzero(exp["status"])[0]) == [5]  # frame 29 of the bench batch
+    assert list(out["status"]) == [0, 0, 0, 0, 0, g.FRAME_NUMERIC, 0, 0]
+
+
 def test_frames_solve_iteration_counts(gpu, oracle):
     g, ctx = gpu
     mean, cov = synth.make_map(1500, 0.5, seed=6)

@@ -173,3 +173,54 @@ def test_associate_map_elements_synthetic_map(gpu, oracle):
         assert out["nview"][b] == want["nview"]
         assert np.array_equal(out["cand"][b], want["cand"]) and np.array_equal(out["assoc"][b], want["assoc"]), b
         assert _same(out["pt3d"][b], want["pt3d"]), b
+
+
+def test_query_point_matches_oracle_and_reference_kdtree(gpu, oracle, golden_maps):
+    """GMM::queryPoint (gaussian_mixture.cpp:545-576) through gmmloc_map_query_point: the returned index, the 5-NN list and
+    the (discarded) Mahalanobis minimum equal the oracle's; the list also equals the reference's own nanoflann kd-tree
+    where oracle/_ref is available."""
+    g, ctx = gpu
+    gm = golden_maps["v1"]
+    m = g.GMM(gm["mean"], gm["cov"])
+    comps = oracle.map_build(gm["mean"], gm["cov"])
+    pts, _ = synth.make_points_near(gm["mean"], gm["cov"], 3000, seed=8, spread=2.0)
+    pts = pts.astype(np.float64)
+    pts[:50] = gm["mean"][:50]  # exact hits: distance 0
+    out = ctx.queryPoint(m, pts)
+    for i in range(0, len(pts), 7):
+        r, knn, md = oracle.query_point(comps, pts[i], 5)
+        assert out["nearest"][i] == r and np.array_equal(out["knn"][i], knn), i
+        assert out["min_mdist2"][i] == md
+    ref = oracle.ref_knn(gm["mean"], pts, 5)
+    if ref is not None:
+        assert np.array_equal(out["knn"], ref[0].astype(np.int32))
+    # a map smaller than the list: -1 padded
+    small = g.GMM(gm["mean"][:3], gm["cov"][:3])
+    o = ctx.queryPoint(small, pts[:4])
+    assert np.all(o["knn"][:, 3:] == -1) and np.all(o["knn"][:, :3] >= 0)
+    # duplicated means: equal distances -> lower index first
+    dup = g.GMM(np.repeat(gm["mean"][:4], 2, axis=0), np.repeat(gm["cov"][:4], 2, axis=0))
+    o = ctx.queryPoint(dup, gm["mean"][2:3])
+    assert list(o["knn"][0, :2]) == [4, 5] and o["nearest"][0] == 4
+
+
+def test_render_views_keeps_the_callers_cap_as_row_stride(gpu, golden_maps, gt_v1_03):
+    g, ctx = gpu
+    import ctypes as C
+    gm = golden_maps["v1"]
+    K = 40
+    m = g.GMM(gm["mean"][:K], gm["cov"][:K])
+    pose = synth.make_frames(gm["mean"], gm["cov"], 2, 4, seed=1, poses_wc=gt_v1_03[[100, 900], 1:8])["pose0"]
+    cap = K + 7
+    cnt = np.zeros(2, np.int32)
+    ids = np.full((2, cap), -2, np.int32)
+    depth = np.full((2, cap), -2.0)
+    cam = g.v1_camera()
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    g.capi.check(g.capi.lib().gmmloc_render_views(ctx._h, m._h, C.byref(cam), p(pose), 2, cap, p(cnt), None, p(ids), None, None, p(depth)))
+    ref = ctx.renderView(m, pose)  # the wrapper clamps cap to K itself
+    for b in range(2):
+        assert cnt[b] == ref["count"][b]
+        assert np.array_equal(ids[b, :cnt[b]], ref["ids"][b, :cnt[b]])
+        assert np.array_equal(depth[b, :cnt[b]], ref["depth"][b, :cnt[b]])
+        assert np.all(ids[b, K:] == -1) and np.all(depth[b, cnt[b]:] == 0.0)

