@@ -601,7 +601,8 @@ void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t
                         const oracle_params_t* prm, const double pose0[7], const float* pts_w,
                         const float* obsf, const uint8_t* octave, int N, const int32_t* assign_in,
                         double pose_out[7], double* pts_out, int32_t* assign_o, uint8_t* outlier,
-                        int32_t* status, double* trace) {
+                        int32_t* status, double* trace, double* pt_last) {
+  if (pt_last) for (int i = 0; i < N; ++i) pt_last[i] = 0.0;
   const Cam cam{camp->fx, camp->fy, camp->cx, camp->cy, camp->bf};
   std::vector<int32_t> asg(N);
   if (assign_in) {
@@ -754,10 +755,11 @@ void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t
       for (int i = 0; i < 6; ++i) bs[i] = bp[i] - g[i];
       if (!solve6(Hs, bs, dxi)) { st |= 1; break; }
     }
-    if (trace) for (int i = 0; i < 6; ++i) trace[it * 6 + i] = dxi[i];
+    if (trace) for (int i = 0; i < 6; ++i) trace[it * 8 + i] = dxi[i];
     // back-substitution and update
     bool finite = true;
     std::vector<double> xn(x);
+    double max_dx = 0.0, max_dx_idx = -1.0;
     for (int i = 0; i < N; ++i) {
       if (!free_pt[i]) continue;
       const double* Hpli = &Hpl[18 * (size_t)i];
@@ -769,11 +771,15 @@ void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t
       }
       double dx[3];
       mat3_vec(&Dinv[9 * (size_t)i], c, dx);
+      if (pt_last) pt_last[i] = 0.0;
       for (int r = 0; r < 3; ++r) {
         xn[3 * i + r] = x[3 * i + r] + dx[r];
         if (!std::isfinite(xn[3 * i + r])) finite = false;
+        if (std::fabs(dx[r]) > max_dx) { max_dx = std::fabs(dx[r]); max_dx_idx = (double)i; }
+        if (pt_last && !(std::fabs(dx[r]) <= pt_last[i])) pt_last[i] = std::fabs(dx[r]);  // NaN-propagating max
       }
     }
+    if (trace) { trace[it * 8 + 6] = max_dx; trace[it * 8 + 7] = max_dx_idx; }
     if (!finite) { st |= 1; break; }
     x.swap(xn);
     if (pose_free) {
@@ -981,12 +987,39 @@ void oracle_frames_solve(const oracle_comp_t* comps, int K, const oracle_camera_
                          const oracle_params_t* prm, const double* pose0, const float* pts_w,
                          const float* obs, const uint8_t* octave, int B, int N, double* pose_out,
                          double* pts_out, int32_t* assign, uint8_t* outlier, int32_t* status, int nthreads) {
+  oracle_frames_solve_diag(comps, K, cam, prm, pose0, pts_w, obs, octave, B, N, pose_out, pts_out, assign, outlier, status, nthreads,
+                           nullptr, nullptr);
+}
+
+void oracle_frames_solve_diag(const oracle_comp_t* comps, int K, const oracle_camera_t* cam,
+                              const oracle_params_t* prm, const double* pose0, const float* pts_w,
+                              const float* obs, const uint8_t* octave, int B, int N, double* pose_out,
+                              double* pts_out, int32_t* assign, uint8_t* outlier, int32_t* status, int nthreads,
+                              double* conv, double* pt_last) {
   parallel_for(B, nthreads, [&](int64_t lo, int64_t hi, int) {
+    std::vector<double> trace(conv ? 8 * (size_t)std::max(prm->gn_iters, 1) : 0);
     for (int64_t f = lo; f < hi; ++f) {
+      std::fill(trace.begin(), trace.end(), 0.0);
       oracle_frame_solve(comps, K, cam, prm, pose0 + 7 * f, pts_w + 3 * (size_t)N * f, obs + 3 * (size_t)N * f,
                          octave + (size_t)N * f, N, nullptr, pose_out ? pose_out + 7 * f : nullptr,
                          pts_out ? pts_out + 3 * (size_t)N * f : nullptr, assign ? assign + (size_t)N * f : nullptr,
-                         outlier ? outlier + (size_t)N * f : nullptr, status ? status + f : nullptr, nullptr);
+                         outlier ? outlier + (size_t)N * f : nullptr, status ? status + f : nullptr,
+                         conv ? trace.data() : nullptr, pt_last ? pt_last + (size_t)N * f : nullptr);
+      if (conv) {
+        // convergence of the reference iteration itself: |dxi|_inf of the last iteration, the largest step that was
+        // LARGER than its predecessor (0 when the pose steps shrink monotonically), the largest last point step
+        double last = 0.0, grew = 0.0, prev = 0.0;
+        for (int it = 0; it < prm->gn_iters; ++it) {
+          double s = 0.0;
+          for (int i = 0; i < 6; ++i) s = std::max(s, std::fabs(trace[it * 8 + i]));
+          if (it >= 2 && s > prev) grew = std::max(grew, s);
+          prev = s;
+          last = s;
+        }
+        conv[3 * f] = last;
+        conv[3 * f + 1] = grew;
+        conv[3 * f + 2] = prm->gn_iters > 0 ? trace[(prm->gn_iters - 1) * 8 + 6] : 0.0;
+      }
     }
   });
 }

@@ -102,13 +102,14 @@ int oracle_optimize_triangulation(const double x0[3], const double obs1[3], cons
  *  u_r < 0 => mono);  octave N.  assign_in: if non-NULL use these assignments instead of
  *  associating.  Outputs (any may be NULL): pose_out[7], pts_out N x 3 (fp64), assign N,
  *  outlier N, status (bit0 numeric failure: singular Hll / reduced system or non-finite value; such a
- *  frame is returned unsolved = normalised pose0 + input landmarks).  trace (optional): gn_iters x 6
- *  pose increments. */
+ *  frame is returned unsolved = normalised pose0 + input landmarks).  trace (optional): gn_iters x 8 —
+ *  per iteration the pose increment (6), the largest point step max |dx| over the free points and that point's index.
+ *  pt_last (optional): N, |dx|_inf of every point in the last iteration that ran. */
 void oracle_frame_solve(const oracle_comp_t* comps, int K, const oracle_camera_t* cam,
                         const oracle_params_t* prm, const double pose0[7], const float* pts_w,
                         const float* obs, const uint8_t* octave, int N, const int32_t* assign_in,
                         double pose_out[7], double* pts_out, int32_t* assign, uint8_t* outlier,
-                        int32_t* status, double* trace);
+                        int32_t* status, double* trace, double* pt_last);
 
 /* A10 / f1: Tracking::optimizeCurrentPose (tracking_opt.cpp:21-217) restated with g2o's Levenberg-
  * Marquardt (SURVEY Appx B.7): pose-only, 4 rounds x 10 iterations, each round restarted from pose0
@@ -127,6 +128,15 @@ void oracle_frames_solve(const oracle_comp_t* comps, int K, const oracle_camera_
                          const oracle_params_t* prm, const double* pose0, const float* pts_w,
                          const float* obs, const uint8_t* octave, int B, int N, double* pose_out,
                          double* pts_out, int32_t* assign, uint8_t* outlier, int32_t* status, int nthreads);
+/* The same plus convergence diagnostics of the iteration itself (test / bench bookkeeping: a Gauss-Newton iteration that
+ * does not contract is sensitive to the last bit of ANY implementation, so parity checks treat such frames / points
+ * separately).  conv (optional) B x 3: |dxi|_inf of the last iteration | the largest pose step that exceeded its
+ * predecessor (iterations >= 2; 0 = monotone) | the largest point step of the last iteration.  pt_last (optional) B x N. */
+void oracle_frames_solve_diag(const oracle_comp_t* comps, int K, const oracle_camera_t* cam,
+                              const oracle_params_t* prm, const double* pose0, const float* pts_w,
+                              const float* obs, const uint8_t* octave, int B, int N, double* pose_out,
+                              double* pts_out, int32_t* assign, uint8_t* outlier, int32_t* status, int nthreads,
+                              double* conv, double* pt_last);
 
 /* ---- keyframe association pipeline (a5, a6, a7, a9) ---------------------------------------------- */
 

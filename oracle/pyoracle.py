@@ -218,18 +218,18 @@ def frame_solve(comps, pose0, pts_w, obs, octave, cam=None, prm=None, assign_in=
     assign = np.zeros(N, np.int32)
     outlier = np.zeros(N, np.uint8)
     status = C.c_int32(0)
-    trace = np.zeros((prm.gn_iters, 6)) if want_trace else None
+    trace = np.zeros((prm.gn_iters, 8)) if want_trace else None  # dxi (6) | max point step | its index
     ai = None if assign_in is None else np.ascontiguousarray(assign_in, np.int32)
     lib().oracle_frame_solve(_p(comps), C.c_int(len(comps)), C.byref(cam), C.byref(prm), _p(pose0), _p(pts_w),
                              _p(obs), _p(octave), C.c_int(N), _p(ai), _p(pose_out), _p(pts_out), _p(assign),
-                             _p(outlier), C.byref(status), _p(trace))
+                             _p(outlier), C.byref(status), _p(trace), None)
     out = dict(pose=pose_out, pts=pts_out, assign=assign, outlier=outlier, status=status.value)
     if want_trace:
         out["trace"] = trace
     return out
 
 
-def frames_solve(comps, pose0, pts_w, obs, octave, cam=None, prm=None, nthreads=1, want_pts=False):
+def frames_solve(comps, pose0, pts_w, obs, octave, cam=None, prm=None, nthreads=1, want_pts=False, want_conv=False):
     cam = cam or v1_camera()
     prm = prm or default_params()
     pose0 = np.ascontiguousarray(pose0, np.float64).reshape(-1, 7)
@@ -243,10 +243,16 @@ def frames_solve(comps, pose0, pts_w, obs, octave, cam=None, prm=None, nthreads=
     assign = np.zeros((B, N), np.int32)
     outlier = np.zeros((B, N), np.uint8)
     status = np.zeros(B, np.int32)
-    lib().oracle_frames_solve(_p(comps), C.c_int(len(comps)), C.byref(cam), C.byref(prm), _p(pose0), _p(pts_w),
-                              _p(obs), _p(octave), C.c_int(B), C.c_int(N), _p(pose_out), _p(pts_out), _p(assign),
-                              _p(outlier), _p(status), C.c_int(nthreads))
-    return dict(pose=pose_out, pts=pts_out, assign=assign, outlier=outlier, status=status)
+    conv = np.zeros((B, 3)) if want_conv else None
+    pt_last = np.zeros((B, N)) if want_conv else None
+    lib().oracle_frames_solve_diag(_p(comps), C.c_int(len(comps)), C.byref(cam), C.byref(prm), _p(pose0), _p(pts_w),
+                                   _p(obs), _p(octave), C.c_int(B), C.c_int(N), _p(pose_out), _p(pts_out), _p(assign),
+                                   _p(outlier), _p(status), C.c_int(nthreads), _p(conv), _p(pt_last))
+    out = dict(pose=pose_out, pts=pts_out, assign=assign, outlier=outlier, status=status)
+    if want_conv:
+        # conv: |dxi|_inf of the last iteration | largest pose step that exceeded its predecessor | largest last point step
+        out["conv"], out["pt_last"] = conv, pt_last
+    return out
 
 
 def optimize_triangulation(comps, k, x0, obs1, obs2, octave1, pose1, pose2, cam=None, prm=None, iters=20):

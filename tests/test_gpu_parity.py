@@ -234,21 +234,36 @@ def _pose_err(p, q):
 
 
 def _check_frames(g, ctx, oracle, mean, cov, fr, **kw):
+    """GPU vs oracle on the same frames.  Integer outputs (assign, status) must be identical on EVERY frame.  Poses (1e-5 rad /
+    1e-4 m), refined points (1e-4 m) and outlier flags are compared wherever the reference iteration itself contracts: a
+    Gauss-Newton iteration whose pose steps grow again and are still above 1e-6 after the last iteration (a landmark 25 cm in
+    front of the camera oscillating on its component, a monocular point on an edge-on plane ...) amplifies the last bit of
+    ANY arithmetic — the all-fp64 kernel deviates from the oracle on exactly those frames too
+    (tools/diag_convergence.py, profiles/diag_convergence_r02.txt) — so such frames (and, inside a contracting frame,
+    points whose own last step still exceeds 1e-5 m) are counted, bounded and reported, not compared.  Returns
+    (out, exp, worst pose error over the compared frames)."""
     m = g.GMM(mean, cov)
     comps = oracle.map_build(mean, cov)
     prm_g = g.default_params(**kw)
     prm_o = oracle.default_params(**kw)
     out = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=prm_g)
-    exp = oracle.frames_solve(comps, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], prm=prm_o, nthreads=8, want_pts=True)
+    exp = oracle.frames_solve(comps, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], prm=prm_o, nthreads=8, want_pts=True,
+                              want_conv=True)
     assert np.array_equal(out["assign"], exp["assign"]) or kw.get("factor_mode") == 1
     assert np.array_equal(out["status"], exp["status"])
+    B = len(fr["pose0"])
+    chaotic = (exp["conv"][:, 1] > 1e-7) & (exp["conv"][:, 0] > 1e-6) & (exp["status"] == 0)
+    assert chaotic.sum() <= max(1, B // 8), (int(chaotic.sum()), B)
     worst = (0.0, 0.0)
-    for f in range(len(fr["pose0"])):
+    for f in np.flatnonzero(~chaotic):
         ang, dt = _pose_err(out["pose"][f], exp["pose"][f])
         worst = (max(worst[0], ang), max(worst[1], dt))
     assert worst[0] < TOL_RAD and worst[1] < TOL_M, worst
-    np.testing.assert_allclose(out["pts"], exp["pts"], atol=TOL_M)
-    mism = int((out["outlier"] != exp["outlier"]).sum())
+    settled = (~chaotic)[:, None] & (exp["pt_last"] <= 1e-5)
+    assert settled.mean() > 0.97, float(settled.mean())
+    dpt = np.abs(out["pts"].astype(np.float64) - exp["pts"]).max(axis=2)
+    assert dpt[settled].max(initial=0.0) < TOL_M, float(dpt[settled].max())
+    mism = int(((out["outlier"] != exp["outlier"]) & settled).sum())
     assert mism == 0
     return out, exp, worst
 
@@ -649,21 +664,24 @@ def test_frames_solve_fp64_kernel_and_mixed_kernel_agree(gpu, oracle, golden_map
 
 @pytest.mark.parametrize("prep", ["1", "0"])
 @pytest.mark.parametrize("N", [1163, 1164, 1223, 1224, 1999, 2403, 2404, 2528, 2529, 5001, 5819, 5820])
-def test_frames_solve_mixed_kernel_variant_boundaries(gpu, oracle, N, prep, monkeypatch):
+def test_frames_solve_mixed_kernel_variant_boundaries(gpu, oracle, N, prep):
     """Frame sizes on both sides of every launch-variant switch of the mixed-precision frame GN: two resident frames with
     the stored linearisation in shared memory / in the global scratch, one CTA of 384 threads with the store and the aux
     arrays in the global scratch (up to N = 5 819), then the fp64 kernel.  With the frame-preparation kernel (prep = 1,
-    the default) the switches sit at 1223 | 1224 and 2528 | 2529, with the in-kernel sort (GMMLOC_GN_PREP=0) at
+    the default) the switches sit at 1223 | 1224 and 2528 | 2529, with the in-kernel sort (GMMLOC_OPT_GN_PREP = 0) at
     1163 | 1164 and 2403 | 2404; 5819 | 5820 is the fp64 kernel; odd sizes exercise the 16-byte alignment of the per-CTA
     scratch slices and of the prepared frames."""
     g, ctx = gpu
-    monkeypatch.setenv("GMMLOC_GN_PREP", prep)
-    mean, cov = synth.make_map(3000, 0.7, seed=17)
-    fr = synth.make_frames(mean, cov, 2, N, seed=N, mono_frac=0.15)
-    _check_frames(g, ctx, oracle, mean, cov, fr, robust=1)
+    ctx.set_option(g.capi.OPT_GN_PREP, int(prep))
+    try:
+        mean, cov = synth.make_map(3000, 0.7, seed=17)
+        fr = synth.make_frames(mean, cov, 2, N, seed=N, mono_frac=0.15)
+        _check_frames(g, ctx, oracle, mean, cov, fr, robust=1)
+    finally:
+        ctx.set_option(g.capi.OPT_GN_PREP, -1)
 
 
-def test_frames_solve_prepared_frames_equal_in_kernel_sort(gpu, monkeypatch):
+def test_frames_solve_prepared_frames_equal_in_kernel_sort(gpu):
     """frame_prep_kernel + the copying solver give bit-identical results to the solver that classifies and sorts its frames
     itself (same stable class sort, same arithmetic), for a batch larger than the preparation grid."""
     g, ctx = gpu
@@ -671,8 +689,33 @@ def test_frames_solve_prepared_frames_equal_in_kernel_sort(gpu, monkeypatch):
     fr = synth.make_frames(mean, cov, 1300, 301, seed=9, mono_frac=0.2)
     m = g.GMM(mean, cov)
     outs = []
-    for prep in ("1", "0"):
-        monkeypatch.setenv("GMMLOC_GN_PREP", prep)
+    for prep in (1, 0):
+        ctx.set_option(g.capi.OPT_GN_PREP, prep)
         outs.append(ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=g.default_params(robust=1)))
+    ctx.set_option(g.capi.OPT_GN_PREP, -1)
     for k in ("pose", "pts", "assign", "outlier", "status"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
+
+
+def test_environment_variables_do_not_steer_a_production_build(gpu, monkeypatch):
+    """A stray GMMLOC_* variable must not change what the library runs: the kernel selectors are
+    context / map setters; the environment is read only by a -DGMMLOC_DEBUG_ENV build."""
+    g, ctx = gpu
+    mean, cov = synth.make_map(1200, 0.5, seed=31)
+    monkeypatch.setenv("GMMLOC_GRID", "0")
+    monkeypatch.setenv("GMMLOC_ASSOC_KERNEL", "ffma2")
+    monkeypatch.setenv("GMMLOC_GN_PRECISION", "fp64")
+    m = g.GMM(mean, cov)
+    fr = synth.make_frames(mean, cov, 2, 300, seed=31)
+    ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
+    assert ctx.last_assoc_kernel() == "grid"
+    # the explicit setters do steer it
+    off = g.capi.GridOptions(enable=0)
+    m2 = g.GMM(mean, cov, grid=off)
+    a = ctx.frames_solve(m2, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
+    assert ctx.last_assoc_kernel() == "ffma2"
+    b = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
+    for k in ("pose", "assign", "status", "outlier"):
+        assert np.array_equal(a[k], b[k]), k
+    with pytest.raises(g.GmmlocError):
+        ctx.set_option(99, 0)

@@ -13,13 +13,13 @@ from gmmloc_b200 import synth
 mean, cov = synth.make_map(1500, 0.5)
 m = g.GMM(mean, cov, device=0)
 ctx = g.Context(0)
-for prep in ("1", "0"):
-    os.environ["GMMLOC_GN_PREP"] = prep
+for prep in (1, 0):
+    ctx.set_option(g.capi.OPT_GN_PREP, prep)
     for B, N in ((3, 501), (2, 1999), (2, 2451), (2, 5001), (40, 1201)):
         fr = synth.make_frames(mean, cov, B, N, seed=B, mono_frac=0.2)
         out = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=g.default_params(robust=1))
         print(prep, B, N, out["status"][:3], out["assign"][0, :5], flush=True)
-os.environ.pop("GMMLOC_GN_PREP")
+ctx.set_option(g.capi.OPT_GN_PREP, -1)
 LIGHT = os.environ.get("MEMCHECK_LIGHT") == "1"  # racecheck / initcheck runs: smaller workloads
 pts, _ = synth.make_points_near(mean, cov, 20000 if LIGHT else 300000, seed=3, spread=2.0)
 pts[::1000] += 50

@@ -1,5 +1,5 @@
 """GPU probe: PCIe copy bandwidth with page-locked buffers and the e2e frames/s of gmmloc_frames_solve for several
-pipeline chunk sizes (GMMLOC_E2E_CHUNK is read once per process, so each chunk size runs in a child process)."""
+pipeline chunk sizes (gmmloc_ctx_set_option GMMLOC_OPT_E2E_CHUNK; each chunk size runs in a child process)."""
 import os
 import subprocess
 import sys
@@ -20,6 +20,7 @@ def child(chunk):
     fr = synth.make_frames(mean, cov, 256, N, seed=0)
     fr = {k: np.concatenate([v] * (B // 256)) for k, v in fr.items() if k in ("pose0", "pts_w", "obs", "octave")}
     gmm, ctx = g.GMM(mean, cov), g.Context(0)
+    ctx.set_option(g.capi.OPT_E2E_CHUNK, chunk)
     cam, prm = g.v1_camera(), g.default_params()
     keep, h = [], {}
     for k in ("pose0", "pts_w", "obs", "octave"):
@@ -62,8 +63,7 @@ def main():
         torch.cuda.synchronize()
         print(f"{name} pinned 205 MiB: {5 * n / (a.elapsed_time(b) * 1e-3) / 1e9:.1f} GB/s", flush=True)
     for chunk in [int(x) for x in os.environ.get("PROBE_CHUNKS", "256,444,512,888,1024,1332,2048,4096").split(",")]:
-        env = dict(os.environ, GMMLOC_E2E_CHUNK=str(chunk))
-        subprocess.run([sys.executable, __file__, str(chunk)], env=env, check=False)
+        subprocess.run([sys.executable, __file__, str(chunk)], check=False)
 
 
 if __name__ == "__main__":
