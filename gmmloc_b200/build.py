@@ -32,6 +32,7 @@ SOURCES = {
     "assoc_scan.cu": [],
     "frame_gn.cu": [],
     "frame_gn_mixed.cu": [],
+    "frame_gn_world.cu": [],
     "pose_lm.cu": [],
     "local_ba.cu": [],
     "point_gn.cu": ["-fmad=false"],
@@ -58,6 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     jobs = []
     objs = []
     env_extra = os.environ.get("GMMLOC_NVCC_EXTRA", "").split()
+    if "--debug-env" in sys.argv:  # A/B builds: the library honours the GMMLOC_* environment overrides (common.cuh)
+        env_extra.append("-DGMMLOC_DEBUG_ENV")
     for src, extra in SOURCES.items():
         extra = list(extra) + env_extra
         s = CSRC / src

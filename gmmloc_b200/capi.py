@@ -8,16 +8,20 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libgmmloc_b200.so"
+# GMMLOC_B200_LIB: load another build of the SAME library (tools/build_variant.sh: A/B timing of compile-time variants)
+LIB_PATH = Path(os.environ.get("GMMLOC_B200_LIB") or (PKG / "lib" / "libgmmloc_b200.so"))
 
 OK, EINVAL, ENOMEM, ECUDA, ENUMERIC, EIO = range(6)
 MODE_JOINT, MODE_POSE_ONLY, MODE_POINTS_ONLY = 0, 1, 2
 FRAME_NUMERIC = 1
 VIEW_OVERFLOW = 1
 ASSOC_AUTO, ASSOC_FFMA2, ASSOC_TENSOR, ASSOC_GRID = 0, 1, 2, 3
-GN_FP64, GN_MIXED = 0, 1
-OPT_GN_PREP, OPT_E2E_CHUNK, OPT_E2E_SHORT_FIRST = 0, 1, 2
+GN_FP64, GN_MIXED, GN_WORLD = 0, 1, 2
+GN_DEFAULT = GN_MIXED  # what a new context runs (gmmloc_ctx_create)
+OPT_GN_PREP, OPT_E2E_CHUNK, OPT_E2E_SHORT_FIRST, OPT_BA_CLUSTER = 0, 1, 2, 3
 
 
 class GridOptions(C.Structure):

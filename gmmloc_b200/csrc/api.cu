@@ -245,6 +245,7 @@ struct gmmloc_ctx {
   int opt_gn_prep = -1;          // GMMLOC_OPT_GN_PREP
   int opt_e2e_chunk = 0;         // GMMLOC_OPT_E2E_CHUNK
   int opt_e2e_short_first = 0;   // GMMLOC_OPT_E2E_SHORT_FIRST
+  int opt_ba_cluster = 0;        // GMMLOC_OPT_BA_CLUSTER
 };
 
 extern "C" {
@@ -682,7 +683,7 @@ gmmloc_status_t gmmloc_ctx_set_assoc_kernel(gmmloc_ctx_t* ctx, int kind) {
 int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx) { return ctx ? ctx->last_assoc_tc : 0; }
 
 gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int precision) {
-  if (!ctx || (precision != GMMLOC_GN_FP64 && precision != GMMLOC_GN_MIXED))
+  if (!ctx || (precision != GMMLOC_GN_FP64 && precision != GMMLOC_GN_MIXED && precision != GMMLOC_GN_WORLD))
     return fail(GMMLOC_EINVAL, "gmmloc_ctx_set_gn_precision: bad argument");
   ctx->gn_precision = precision;
   return GMMLOC_OK;
@@ -701,6 +702,10 @@ gmmloc_status_t gmmloc_ctx_set_option(gmmloc_ctx_t* ctx, int option, int64_t val
       return GMMLOC_OK;
     case GMMLOC_OPT_E2E_SHORT_FIRST:
       ctx->opt_e2e_short_first = value ? 1 : 0;
+      return GMMLOC_OK;
+    case GMMLOC_OPT_BA_CLUSTER:
+      if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(GMMLOC_EINVAL, "GMMLOC_OPT_BA_CLUSTER: 0, 1, 2, 4 or 8");
+      ctx->opt_ba_cluster = (int)value;
       return GMMLOC_OK;
     default:
       return fail(GMMLOC_EINVAL, "gmmloc_ctx_set_option: unknown option");
@@ -734,7 +739,7 @@ gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* ma
   if (map->d.grid.nlev > 0) {  // scratch of the cell-sorted grid scan
     const GridLevel& G0 = map->d.grid.lev[0];
     CU(ctx->L().sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2)));
-    CU(ctx->L().sort_perm.reserve(sizeof(int32_t) * (size_t)M));
+    CU(ctx->L().sort_perm.reserve(16 * (size_t)M));  // one float4 per landmark
     sort_cnt = ctx->L().sort_cnt.as<int>();
     sort_perm = ctx->L().sort_perm.as<int32_t>();
   }
@@ -834,10 +839,18 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
     if (v == nullptr) return -1;
     if (std::strcmp(v, "fp64") == 0) return (int)GMMLOC_GN_FP64;
     if (std::strcmp(v, "mixed") == 0) return (int)GMMLOC_GN_MIXED;
+    if (std::strcmp(v, "world") == 0) return (int)GMMLOC_GN_WORLD;
     return -1;
   }();
   const int gn_prec = gn_forced >= 0 ? gn_forced : ctx->gn_precision;
-  if (gn_prec == GMMLOC_GN_MIXED && map->d.gn_tab != nullptr && (size_t)N <= frame_gn_mixed_limit_points()) {
+  if (gn_prec == GMMLOC_GN_WORLD && map->d.gn_tab != nullptr && N > 0 && (size_t)N <= frame_gn_world_limit_points()) {
+    CU(ctx->L().next_frame.reserve(sizeof(int)));
+    CU(ctx->L().gn_store.reserve(frame_gn_world_scratch_bytes(N)));
+    CU(ctx->L().gn_prep.reserve(frame_gn_world_prep_bytes(B, N)));
+    CU(launch_frame_gn_world(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().gn_store.as<float>(), ctx->L().gn_store.cap,
+                             ctx->L().gn_prep.as<unsigned char>(), ctx->L().gn_prep.cap, ctx->L().stream));
+    ctx->stats.kernel_launches += 1;
+  } else if (gn_prec != GMMLOC_GN_FP64 && map->d.gn_tab != nullptr && (size_t)N <= frame_gn_mixed_limit_points()) {
     CU(ctx->L().next_frame.reserve(sizeof(int)));
     CU(ctx->L().gn_store.reserve(frame_gn_mixed_scratch_bytes(N)));
     const size_t prep_bytes = frame_gn_mixed_prep_bytes(B, N, ctx->opt_gn_prep);
@@ -923,12 +936,13 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     CU(ln.flag_idx.reserve(sizeof(int32_t) * 2 * mc));
     CU(ln.flag_thr.reserve(sizeof(float) * 2 * mc));
     CU(ln.next_frame.reserve(sizeof(int)));
-    CU(ln.gn_store.reserve(frame_gn_mixed_scratch_bytes(N)));
+    CU(ln.gn_store.reserve(std::max(frame_gn_mixed_scratch_bytes(N), frame_gn_world_scratch_bytes(N))));
+    if (ctx->gn_precision == GMMLOC_GN_WORLD) CU(ln.gn_prep.reserve(frame_gn_world_prep_bytes(maxc, N)));
     if (frame_gn_mixed_prep_bytes(maxc, N, ctx->opt_gn_prep)) CU(ln.gn_prep.reserve(frame_gn_mixed_prep_bytes(maxc, N, ctx->opt_gn_prep)));
     if (map->d.grid.nlev > 0) {
       const GridLevel& G0 = map->d.grid.lev[0];
       CU(ln.sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2)));
-      CU(ln.sort_perm.reserve(sizeof(int32_t) * mc));
+      CU(ln.sort_perm.reserve(16 * mc));
     }
     if ((size_t)N > frame_gn_smem_limit_points()) {
       CU(ln.xws.reserve(24 * mc));
@@ -1574,7 +1588,7 @@ gmmloc_status_t gmmloc_local_ba(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, cons
     *reinterpret_cast<volatile int32_t*>(ctx->h_stop) = *stop;
     a.stop = d_stop;
   }
-  CU(launch_local_ba(a, st));
+  CU(launch_local_ba(a, st, ctx->opt_ba_cluster));
   ctx->stats.kernel_launches += 1;
   if (stop != nullptr) {
     CU(cudaEventRecord(ctx->ev_ba, st));

@@ -128,7 +128,7 @@ struct ScanArgs {
   int* ga_count;
   int32_t* ga_idx;
   float* ga_thr;
-  const int32_t* perm;  // landmark order of the cell-sorted grid scan (null: natural order)
+  const float4* sorted;  // cell-sorted landmarks of the grid scan: (x, y, z, original index as bits), or null: natural order
   int rerank_two_pass;  // K2: first find the fp32 minimum over all components, then re-rank inside ITS radius (the
                         // thresholds of the grid path come from a cell-list candidate that may be far from the winner)
   // tensor-core pruning scan only
@@ -495,9 +495,17 @@ __global__ void __launch_bounds__(256) grid_hist_kernel(const ScanArgs a, int* _
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i < a.M) atomicAdd(hist + sort_cell(a, i), 1);
 }
-__global__ void __launch_bounds__(256) grid_scatter_kernel(const ScanArgs a, int* __restrict__ cur, int32_t* __restrict__ perm) {
+// The scatter writes the landmark ITSELF next to its original index (one float4 per landmark) so that the scan streams
+// its input coalesced: with an index-only permutation the scan gathered 12 B out of every 32-byte sector it fetched
+// (510 MB of DRAM reads for 98 MB of landmarks, profiles/assoc_grid_r01.txt).
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const ScanArgs a, int* __restrict__ cur, float4* __restrict__ sorted) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i < a.M) perm[atomicAdd(cur + sort_cell(a, i), 1)] = (int32_t)i;
+  if (i >= a.M) return;
+  const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
+  const GridLevel& G = a.grid.lev[0];
+  long long c = grid_cell(G, px, py, pz);
+  if (c < 0) c = (long long)G.nx * G.ny * G.nz;
+  sorted[atomicAdd(cur + c, 1)] = make_float4(px, py, pz, __int_as_float((int)i));
 }
 // in-place exclusive scan of n ints by one CTA (n <= ~4 M: a few tens of microseconds)
 __global__ void __launch_bounds__(1024) excl_scan_kernel(int* __restrict__ d, int n) {
@@ -551,10 +559,18 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
   const long long w = (long long)blockIdx.x * THREADS + threadIdx.x;
   const bool live = w < a.M;
   if (!SORTED && !live) return;  // the sorted variant keeps whole warps alive for the shuffles
-  const long long i = live ? (SORTED ? (long long)a.perm[w] : w) : 0;
   const float qnan = __int_as_float(0x7fc00000);
-  const float px = live ? __ldg(a.pts + i * 3 + 0) : qnan, py = live ? __ldg(a.pts + i * 3 + 1) : qnan,
-              pz = live ? __ldg(a.pts + i * 3 + 2) : qnan;
+  long long i = live ? w : 0;
+  float px = qnan, py = qnan, pz = qnan;
+  if (SORTED) {
+    if (live) {  // streamed once: evict-first, so that the scattered assignment stores keep their sectors in L2
+      const float4 v = __ldcs(a.sorted + w);
+      px = v.x; py = v.y; pz = v.z;
+      i = (long long)__float_as_int(v.w);
+    }
+  } else if (live) {
+    px = __ldg(a.pts + i * 3 + 0); py = __ldg(a.pts + i * 3 + 1); pz = __ldg(a.pts + i * 3 + 2);
+  }
   const bool finite_in = (fabsf(px) <= a.xmax) && (fabsf(py) <= a.xmax) && (fabsf(pz) <= a.xmax);  // false for NaN
   float g1 = CUDART_INF_F, g2 = CUDART_INF_F;  // best / second best over the big list
   int gi = -1;
@@ -755,7 +771,7 @@ __global__ void __launch_bounds__(128) assoc_grid_rerank_kernel(const ScanArgs a
   }
 }
 
-// sort_cnt: ncell0 + 1 ints, sort_perm: M ints — or null for the natural-order kernel
+// sort_cnt: ncell0 + 1 ints, sort_perm: M x 16 bytes (one float4 per landmark) — or null for the natural-order kernel
 cudaError_t launch_scan_grid(ScanArgs a, int* sort_cnt, int32_t* sort_perm, cudaStream_t stream, int* launches) {
   const unsigned grid = (unsigned)((a.M + 255) / 256);
   const GridLevel& G = a.grid.lev[0];
@@ -765,13 +781,13 @@ cudaError_t launch_scan_grid(ScanArgs a, int* sort_cnt, int32_t* sort_perm, cuda
     if ((e = cudaMemsetAsync(sort_cnt, 0, sizeof(int) * (size_t)(ncell + 1), stream)) != cudaSuccess) return e;
     grid_hist_kernel<<<grid, 256, 0, stream>>>(a, sort_cnt);
     excl_scan_kernel<<<1, 1024, 0, stream>>>(sort_cnt, (int)(ncell + 1));
-    grid_scatter_kernel<<<grid, 256, 0, stream>>>(a, sort_cnt, sort_perm);
-    a.perm = sort_perm;
+    grid_scatter_kernel<<<grid, 256, 0, stream>>>(a, sort_cnt, reinterpret_cast<float4*>(sort_perm));
+    a.sorted = reinterpret_cast<const float4*>(sort_perm);
     assoc_grid_kernel<256, true><<<grid, 256, 0, stream>>>(a);
     if (launches) *launches += 3;
     return cudaGetLastError();
   }
-  a.perm = nullptr;
+  a.sorted = nullptr;
   assoc_grid_kernel<256, false><<<grid, 256, 0, stream>>>(a);
   return cudaGetLastError();
 }
@@ -1235,7 +1251,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
   a.ga_thr = d_flag_thr;
   a.grid = m.grid;
   a.rec = reinterpret_cast<const float4*>(m.rec);
-  a.perm = nullptr;
+  a.sorted = nullptr;
   a.rerank_two_pass = 0;
   int extra_launches = 0;
   a.tc_table = m.tc_table;

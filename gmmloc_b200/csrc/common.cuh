@@ -121,7 +121,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
                              float* d_d2, int* d_flag_count, int32_t* d_flag_idx, float* d_flag_thr, int variant,
                              cudaStream_t stream, int* launches, cudaEvent_t ev_between = nullptr, int* used_tc = nullptr,
                              int* d_sort_cnt = nullptr, int32_t* d_sort_perm = nullptr);  // scratch of the cell-sorted grid scan:
-                                                                                          // cells(level 0) + 1 ints, M ints
+                                                                                          // cells(level 0) + 1 ints, M x 16 bytes
 struct FrameArgs {
   const double* mean;       // map constants (fp64)
   const double* cov_inv;
@@ -152,6 +152,13 @@ cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* 
 size_t frame_gn_mixed_scratch_bytes(int N);
 size_t frame_gn_mixed_prep_bytes(int B, int N, int mode = -1);  // 0: this batch is classified and sorted inside the solver
                                                                  // kernel; mode: GMMLOC_OPT_GN_PREP (-1 auto, 0 never, 1 always)
+// world-frame twin (frame_gn_world.cu, K3w): always runs on frames prepared by frame_prep_kernel (prep_ws is mandatory:
+// frame_gn_world_prep_bytes(B, N) bytes); store_ws as above (frame_gn_world_scratch_bytes(N) bytes)
+cudaError_t launch_frame_gn_world(const FrameArgs& a, const float* gn_tab, int* d_next_frame, float* store_ws, size_t store_ws_bytes,
+                                  unsigned char* prep_ws, size_t prep_ws_bytes, cudaStream_t stream);
+size_t frame_gn_world_scratch_bytes(int N);
+size_t frame_gn_world_prep_bytes(int B, int N);
+size_t frame_gn_world_limit_points();
 size_t frame_gn_mixed_limit_points();  // largest N the mixed kernel takes (class-sorted frame state in shared memory)
 size_t frame_gn_smem_limit_points();  // largest N whose per-frame state stays in shared memory
 
@@ -310,7 +317,8 @@ struct BaArgs {
   int32_t* status;          // B
   const volatile int32_t* stop;  // force-stop flag in host-mapped memory (device pointer), or null
 };
-cudaError_t launch_local_ba(const BaArgs& a, cudaStream_t stream);
+// cluster: CTAs per window (1, 2, 4, 8), or 0 = chosen from the number of windows
+cudaError_t launch_local_ba(const BaArgs& a, cudaStream_t stream, int cluster = 0);
 int local_ba_obs_ws();
 int local_ba_pt_ws();
 int local_ba_pose_ws();

@@ -27,6 +27,7 @@
 #include "common.cuh"
 #include "gn_common.cuh"
 #include "frame_gn_point.cuh"
+#include "frame_gn_classes.cuh"
 
 namespace gmmloc {
 
@@ -44,28 +45,6 @@ namespace {
 #endif
 constexpr int kThreads2 = GMMLOC_GNM_THREADS2;
 constexpr int kAcc = 27;
-constexpr double kFarZ = 6.0;  // metres; cond(G) ~ (z fx / bf)^2 ~ 3e3 at the shipped camera (v1.yaml:5-17)
-// Point classes (bits 4..6 of the per-point flag byte).  The points of a frame are stably sorted by class when the
-// frame is loaded, so that a warp runs ONE code path per sweep (the unsorted fp64 kernel executes with ~25 of 32
-// lanes active) and the rare ill-conditioned blocks cost a few warp-iterations per sweep instead of stalling every warp.
-enum : int {
-  C_OFF = 0,     // takes no part (a held point when the pose is fixed)
-  C_FIXED = 1,   // held point: contributes G, h to the pose system
-  C_PLAIN = 2,   // free stereo point without structure edge: three equations, three unknowns — closed-form update,
-                 // contributes exactly nothing to the pose system
-  C_MPLANE = 3,  // free monocular point on a planar component: again three equations (u, v, plane distance) for three
-                 // unknowns — closed-form update, zero Schur contribution.  (As a 3x3 normal-equation block this is
-                 // the ill-conditioned case: G has rank 2 and the third direction comes from the plane alone.)
-  C_STRP = 4,    // free stereo point on a planar component: the stereo edge alone determines the point (P is square),
-                 // the plane adds ONE scalar equation, so D = G + lam n n^T is inverted by Sherman-Morrison in closed
-                 // form: with pe = P^-1 e, z = G^-1 n, gamma = n.z, kappa = lam / (1 + lam gamma):
-                 //   M = kappa n n^T,  v = kappa (es + n.pe) n,  dc = u - kappa z (n.u),  u = pe - A dxi - lam es z
-  C_STR = 5,     // free stereo point with a full 3-D Gaussian edge: general 3x3 path, fp32 Hessian model
-  C_F64 = 6,     // blocks the fp32 model should not be trusted with (monocular point with a full 3-D Gaussian edge,
-                 // any free point beyond kFarZ): fp64 path of frame_gn_kernel
-  C_COUNT = 7
-};
-constexpr int kMaxChunks = 25;                        // histogram stride per class = 8 kMaxChunks >= N / 32 + warps per CTA
 constexpr int kScratchPerPoint = 4 * 12 + 8;          // global scratch per point and resident CTA: store 48 B, aux 7 B (+1)
 constexpr int kStore = 12;                            // floats of the stored linearisation per point: u0 (3), W (9)
 // bytes of one resident CTA's slice of the global scratch: a multiple of 16 so that the float4 accesses of the stored
@@ -308,7 +287,6 @@ __device__ __noinline__ void point_fp64(const FrameArgs& a, const PoseBoth& oldp
 // from a coalesced copy.  Layout of frame f (prep_stride(N) bytes, all arrays in class-sorted order):
 //   [0, 12N) landmarks f32 x 3 | [12N, 24N) observations f32 x 3 | [24N, 28N) component id i32 |
 //   [28N, 30N) original index u16 | [30N, 31N) octave u8 | [31N, 32N) flags u8 (class in bits 4..6)
-__host__ __device__ inline size_t prep_stride(int N) { return ((size_t)N * 32 + 15) & ~(size_t)15; }
 
 constexpr int kPrepThreads = 256;
 __global__ void __launch_bounds__(kPrepThreads) frame_prep_kernel(const FrameArgs a, unsigned char* __restrict__ prep) {
@@ -376,7 +354,7 @@ __global__ void __launch_bounds__(kPrepThreads) frame_prep_kernel(const FrameArg
         } else {
           const double pz = s_R[6] * x0 + s_R[7] * x1 + s_R[8] * x2 + s_t[2];
           if (!(pz < kFarZ)) cls = C_F64;
-          else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_F64;  // a free monocular point always has F_STR
+          else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_MSTR;  // a free monocular point always has F_STR
           else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
         }
         tmp[i] = (uint8_t)(b | (cls << 4));
@@ -574,7 +552,7 @@ __global__ void __launch_bounds__(kThreads) __maxnreg__(kMinB == 1 ? 168 : GMMLO
           } else {
             const double pz = s_new.R[6] * x0 + s_new.R[7] * x1 + s_new.R[8] * x2 + s_new.t[2];
             if (!(pz < kFarZ)) cls = C_F64;
-            else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_F64;  // a free monocular point always has F_STR
+            else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_MSTR;  // a free monocular point always has F_STR
             else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
           }
           tmp[i] = (uint8_t)(b | (cls << 4));
@@ -656,7 +634,7 @@ __global__ void __launch_bounds__(kThreads) __maxnreg__(kMinB == 1 ? 168 : GMMLO
       // already absorbs the imbalance); staging the next round's stored linearisation with cp.async 4.17 ms.
       for (int j = tid; j < N; j += kThreads) {
         const uint8_t b = fl[j];
-        const int cls = b >> 4;
+        const int cls = (b >> 4) == C_MSTR ? (int)C_F64 : (b >> 4);  // this kernel keeps mono + full Gaussian on the fp64 path
         const bool stereo = b & F_STEREO;
         const bool upd = do_update && cls >= C_PLAIN;
         const bool accp = do_acc && (cls == C_FIXED || cls == C_STRP || cls == C_STR || (cls == C_F64 && (b & F_STR)));
@@ -1143,6 +1121,16 @@ static cudaError_t launch_variants(const FrameArgs& a, const float* gn_tab, int*
   return cudaErrorInvalidValue;  // the caller checks frame_gn_mixed_limit_points() and passes the scratch: not reached
 }
 
+cudaError_t launch_frame_prep(const FrameArgs& a, unsigned char* prep, cudaStream_t stream) {
+  if (a.B <= 0) return cudaSuccess;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = std::min(a.B, sms * 8);
+  frame_prep_kernel<<<grid, kPrepThreads, (size_t)((a.N + 15) & ~15), stream>>>(a, prep);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
                                   unsigned char* prep_ws, size_t prep_ws_bytes, cudaStream_t stream) {
   const size_t need = (size_t)a.B * prep_stride(a.N);
@@ -1150,12 +1138,7 @@ cudaError_t launch_frame_gn_mixed(const FrameArgs& a, const float* gn_tab, int* 
     // K3p: classify + class-sort every frame into prep_ws, then the solver copies its frames from there
     unsigned char* prep = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(prep_ws) + 15) & ~(uintptr_t)15);
     if ((size_t)(prep - prep_ws) + need > prep_ws_bytes) return cudaErrorInvalidValue;
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int grid = std::min(a.B, sms * 8);
-    frame_prep_kernel<<<grid, kPrepThreads, (size_t)((a.N + 15) & ~15), stream>>>(a, prep);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = launch_frame_prep(a, prep, stream);
     if (e != cudaSuccess) return e;
     return launch_variants<true>(a, gn_tab, d_counters, store_ws, store_ws_bytes, prep, stream);
   }

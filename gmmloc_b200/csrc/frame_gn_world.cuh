@@ -54,13 +54,20 @@ struct Cam {
   int robust;
 };
 
+// reciprocal / quotient of the fp32 Gauss-Newton MODEL (Jacobian scalings, D^-1, Sherman-Morrison factors): one MUFU.RCP
+// (1 ulp) instead of the ~10-instruction IEEE sequence with its slow-path branch.  Every use either multiplies a residual
+// that was formed in fp64 (the step it yields vanishes with the residual, so the fixed point is untouched) or shapes the
+// Hessian model (convergence rate only); 1 / z of the projection gets a Newton step in fp64 on top (linearise()).
 GNW_HD float rcpf(float x) {
 #if defined(__CUDA_ARCH__)
-  return __frcp_rn(x);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));  // bare MUFU.RCP (__fdividef adds a range-scaling guard)
+  return r;
 #else
   return 1.0f / x;
 #endif
 }
+GNW_HD float divf(float a, float b) { return a * rcpf(b); }
 GNW_HD float rsqf(float x) {
 #if defined(__CUDA_ARCH__)
   return rsqrtf(x);
@@ -86,7 +93,7 @@ GNW_HD S3f inv_sym(const S3f& D, bool& ok) {
   const float c01 = D.xz * D.yz - D.xy * D.zz;
   const float c02 = D.xy * D.yz - D.xz * D.yy;
   const float det = D.xx * c00 + D.xy * c01 + D.xz * c02;
-  const float id = 1.0f / det;
+  const float id = rcpf(det);
   ok = (det != 0.0f) && isfinite(id);
   return {c00 * id, c01 * id, c02 * id, (D.xx * D.zz - D.xz * D.xz) * id, (D.xy * D.xz - D.xx * D.yz) * id,
           (D.xx * D.yy - D.xy * D.xy) * id};
@@ -217,27 +224,29 @@ GNW_HD void accumulate_pose_rank1(float* acc, const V3f& p, const V3f& n, float 
 // what a sweep stores per free point: the step of the point is  dx = u0 - W a
 struct PointLin {
   V3f u0;
-  float W[9];  // row-major
+  float w0, w1, w2, w3, w4, w5, w6, w7, w8;  // W row-major (named scalars: an indexed array ends up in local memory)
 };
 
 // ---- class PLAIN: free stereo point without structure edge.  D = G, P square:  u0 = R^T P^-1 e,  W = I, no Schur term ----
 GNW_HD V3f lin_plain(const Cam& C, const Lin& L, const float* Rf) {
   const Proj P = proj_jac(C, L);
-  const float dz = (L.e.z - L.e.x) / P.cz;
-  const float dx = (L.e.x - P.c0 * dz) / P.a;
-  const float dy = (L.e.y - P.c1 * dz) / P.b;
+  const float dz = divf(L.e.z - L.e.x, P.cz);
+  const float dx = divf(L.e.x - P.c0 * dz, P.a);
+  const float dy = divf(L.e.y - P.c1 * dz, P.b);
   return rot_t(Rf, {dx, dy, dz});
 }
 
-// ---- class STR: free stereo point with a full 3-D Gaussian edge (EdgePt2Gaussian: Hessian cov_inv, rhs -cov_inv d) ----
+// ---- classes STR / MSTR: free stereo / monocular point with a full 3-D Gaussian edge (EdgePt2Gaussian: Hessian cov_inv,
+// rhs -cov_inv d).  For a monocular point G has rank 2; D = G + S stays as well conditioned as S (eigenvalues of cov_inv
+// between 1 / scale_max and 1e4 for a non-degenerate component), so the fp32 model serves it like the stereo case ----
 // Sw: the six unique entries of cov_inv (world frame, as stored in the map), d = x - mu (formed in fp64, rounded).
 // Returns false when D is singular.  M / v (the Schur terms) are produced only when `want_pose`.
-GNW_HD bool lin_str(const Cam& C, const Lin& L, const float* Rf, float w, const S3f& Sw, const V3f& d, PointLin& out, bool want_pose,
-                    S3f& M, V3f& v) {
+GNW_HD bool lin_str(const Cam& C, const Lin& L, const float* Rf, bool stereo, float w, const S3f& Sw, const V3f& d, PointLin& out,
+                    bool want_pose, S3f& M, V3f& v) {
   const Proj P = proj_jac(C, L);
   S3f G;
   V3f h;
-  reproj_world(P, L, Rf, true, huber(C, L, true, w), G, h);
+  reproj_world(P, L, Rf, stereo, huber(C, L, stereo, w), G, h);
   const V3f sd = mulf(Sw, d);
   const V3f bl = {h.x - sd.x, h.y - sd.y, h.z - sd.z};
   const S3f D = {G.xx + Sw.xx, G.xy + Sw.xy, G.xz + Sw.xz, G.yy + Sw.yy, G.yz + Sw.yz, G.zz + Sw.zz};
@@ -245,27 +254,26 @@ GNW_HD bool lin_str(const Cam& C, const Lin& L, const float* Rf, float w, const 
   const S3f Di = inv_sym(D, ok);
   out.u0 = mulf(Di, bl);
   // W = D^-1 G (general 3x3)
-  float* W = out.W;
-  W[0] = Di.xx * G.xx + Di.xy * G.xy + Di.xz * G.xz;
-  W[1] = Di.xx * G.xy + Di.xy * G.yy + Di.xz * G.yz;
-  W[2] = Di.xx * G.xz + Di.xy * G.yz + Di.xz * G.zz;
-  W[3] = Di.xy * G.xx + Di.yy * G.xy + Di.yz * G.xz;
-  W[4] = Di.xy * G.xy + Di.yy * G.yy + Di.yz * G.yz;
-  W[5] = Di.xy * G.xz + Di.yy * G.yz + Di.yz * G.zz;
-  W[6] = Di.xz * G.xx + Di.yz * G.xy + Di.zz * G.xz;
-  W[7] = Di.xz * G.xy + Di.yz * G.yy + Di.zz * G.yz;
-  W[8] = Di.xz * G.xz + Di.yz * G.yz + Di.zz * G.zz;
+  out.w0 = Di.xx * G.xx + Di.xy * G.xy + Di.xz * G.xz;
+  out.w1 = Di.xx * G.xy + Di.xy * G.yy + Di.xz * G.yz;
+  out.w2 = Di.xx * G.xz + Di.xy * G.yz + Di.xz * G.zz;
+  out.w3 = Di.xy * G.xx + Di.yy * G.xy + Di.yz * G.xz;
+  out.w4 = Di.xy * G.xy + Di.yy * G.yy + Di.yz * G.yz;
+  out.w5 = Di.xy * G.xz + Di.yy * G.yz + Di.yz * G.zz;
+  out.w6 = Di.xz * G.xx + Di.yz * G.xy + Di.zz * G.xz;
+  out.w7 = Di.xz * G.xy + Di.yz * G.yy + Di.zz * G.yz;
+  out.w8 = Di.xz * G.xz + Di.yz * G.yz + Di.zz * G.zz;
   if (want_pose) {
     // v = h - G u0: equals h at the fixed point (h + b = 0 => u0 = 0) whatever the rounding of D^-1
     const V3f gu = mulf(G, out.u0);
     v = {h.x - gu.x, h.y - gu.y, h.z - gu.z};
     // M = W^T S (= G D^-1 S = G - G D^-1 G without the cancellation; symmetric in exact arithmetic, upper triangle taken)
-    M.xx = W[0] * Sw.xx + W[3] * Sw.xy + W[6] * Sw.xz;
-    M.xy = W[0] * Sw.xy + W[3] * Sw.yy + W[6] * Sw.yz;
-    M.xz = W[0] * Sw.xz + W[3] * Sw.yz + W[6] * Sw.zz;
-    M.yy = W[1] * Sw.xy + W[4] * Sw.yy + W[7] * Sw.yz;
-    M.yz = W[1] * Sw.xz + W[4] * Sw.yz + W[7] * Sw.zz;
-    M.zz = W[2] * Sw.xz + W[5] * Sw.yz + W[8] * Sw.zz;
+    M.xx = out.w0 * Sw.xx + out.w3 * Sw.xy + out.w6 * Sw.xz;
+    M.xy = out.w0 * Sw.xy + out.w3 * Sw.yy + out.w6 * Sw.yz;
+    M.xz = out.w0 * Sw.xz + out.w3 * Sw.yz + out.w6 * Sw.zz;
+    M.yy = out.w1 * Sw.xy + out.w4 * Sw.yy + out.w7 * Sw.yz;
+    M.yz = out.w1 * Sw.xz + out.w4 * Sw.yz + out.w7 * Sw.zz;
+    M.zz = out.w2 * Sw.xz + out.w5 * Sw.yz + out.w8 * Sw.zz;
   }
   return ok;
 }
@@ -278,7 +286,7 @@ GNW_HD bool lin_str(const Cam& C, const Lin& L, const float* Rf, float w, const 
 GNW_HD bool lin_strp(const Cam& C, const Lin& L, const float* Rf, float w, const V3f& n, float es, PointLin& out, float& kappa, float& rho) {
   const Proj P = proj_jac(C, L);
   w = huber(C, L, true, w);
-  const float ia = 1.0f / P.a, ib = 1.0f / P.b, icz = 1.0f / P.cz;
+  const float ia = rcpf(P.a), ib = rcpf(P.b), icz = rcpf(P.cz);
   // pe_c = P^-1 e
   V3f pe;
   pe.z = (L.e.z - L.e.x) * icz;
@@ -289,22 +297,21 @@ GNW_HD bool lin_strp(const Cam& C, const Lin& L, const float* Rf, float w, const
   const float q1 = nc.y * ib;
   const float q2 = (nc.z - P.c0 * nc.x * ia - P.c1 * q1) * icz;
   const float q0 = nc.x * ia - q2;
-  const float iw = 1.0f / w;
+  const float iw = rcpf(w);
   const float zz = (q2 - q0) * icz;
   const V3f zc = {(q0 - P.c0 * zz) * ia * iw, (q1 - P.c1 * zz) * ib * iw, zz * iw};
   // into the world frame
   const V3f pw = rot_t(Rf, pe), zw = rot_t(Rf, zc);
   const float gamma = dotf(n, zw);
-  kappa = C.lam / (1.0f + C.lam * gamma);
+  kappa = divf(C.lam, 1.0f + C.lam * gamma);
   const float le = C.lam * es;
   const V3f u = {pw.x - le * zw.x, pw.y - le * zw.y, pw.z - le * zw.z};
   const float nu = kappa * dotf(n, u);
   out.u0 = {u.x - nu * zw.x, u.y - nu * zw.y, u.z - nu * zw.z};
   const V3f kz = {kappa * zw.x, kappa * zw.y, kappa * zw.z};
-  float* W = out.W;
-  W[0] = 1.f - kz.x * n.x; W[1] = -kz.x * n.y; W[2] = -kz.x * n.z;
-  W[3] = -kz.y * n.x; W[4] = 1.f - kz.y * n.y; W[5] = -kz.y * n.z;
-  W[6] = -kz.z * n.x; W[7] = -kz.z * n.y; W[8] = 1.f - kz.z * n.z;
+  out.w0 = 1.f - kz.x * n.x; out.w1 = -kz.x * n.y; out.w2 = -kz.x * n.z;
+  out.w3 = -kz.y * n.x; out.w4 = 1.f - kz.y * n.y; out.w5 = -kz.y * n.z;
+  out.w6 = -kz.z * n.x; out.w7 = -kz.z * n.y; out.w8 = 1.f - kz.z * n.z;
   rho = kappa * (es + dotf(n, pw));
   return isfinite(kappa);
 }
@@ -315,9 +322,9 @@ GNW_HD bool lin_strp(const Cam& C, const Lin& L, const float* Rf, float w, const
 GNW_HD bool lin_mplane(const Cam& C, const Lin& L, const float* Rf, const V3f& n, float es, PointLin& out) {
   const Proj P = proj_jac(C, L);
   const V3f nc = rot(Rf, n);
-  const float ia = 1.0f / P.a, ib = 1.0f / P.b;
+  const float ia = rcpf(P.a), ib = rcpf(P.b);
   const float den = nc.z - nc.x * P.c0 * ia - nc.y * P.c1 * ib;  // = (nc . pc) / z: bounded away from 0 by the view-cos cull
-  const float iden = 1.0f / den;
+  const float iden = rcpf(den);
   // u0_c = Q^-1 [e.x, e.y, -es]
   const float uz = (-es - nc.x * L.e.x * ia - nc.y * L.e.y * ib) * iden;
   const V3f u0c = {(L.e.x - P.c0 * uz) * ia, (L.e.y - P.c1 * uz) * ib, uz};
@@ -325,10 +332,9 @@ GNW_HD bool lin_mplane(const Cam& C, const Lin& L, const float* Rf, const V3f& n
   const V3f q3 = {-P.c0 * iden * ia, -P.c1 * iden * ib, iden};
   out.u0 = rot_t(Rf, u0c);
   const V3f qw = rot_t(Rf, q3);
-  float* W = out.W;
-  W[0] = 1.f - qw.x * n.x; W[1] = -qw.x * n.y; W[2] = -qw.x * n.z;
-  W[3] = -qw.y * n.x; W[4] = 1.f - qw.y * n.y; W[5] = -qw.y * n.z;
-  W[6] = -qw.z * n.x; W[7] = -qw.z * n.y; W[8] = 1.f - qw.z * n.z;
+  out.w0 = 1.f - qw.x * n.x; out.w1 = -qw.x * n.y; out.w2 = -qw.x * n.z;
+  out.w3 = -qw.y * n.x; out.w4 = 1.f - qw.y * n.y; out.w5 = -qw.y * n.z;
+  out.w6 = -qw.z * n.x; out.w7 = -qw.z * n.y; out.w8 = 1.f - qw.z * n.z;
   return finite3(out.u0) && isfinite(iden);
 }
 

@@ -108,13 +108,13 @@ __device__ __forceinline__ void accumulate_pose(double* acc, const Vec3& pc, con
 }
 
 // ---- SE3 (g2o SE3Quat semantics, SURVEY Appx B.1), thread-0 only ---------------------------------
-__device__ inline void quat_normalize(double* q) {
+__host__ __device__ inline void quat_normalize(double* q) {
   if (q[3] < 0)
     for (int i = 0; i < 4; ++i) q[i] = -q[i];
   const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   for (int i = 0; i < 4; ++i) q[i] /= n;
 }
-__device__ inline void quat_to_rot(const double* q, double* R) {
+__host__ __device__ inline void quat_to_rot(const double* q, double* R) {
   const double x = q[0], y = q[1], z = q[2], w = q[3];
   const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
   const double twx = tx * w, twy = ty * w, twz = tz * w;
@@ -232,7 +232,7 @@ __device__ inline bool solve6(const double* acc, double* x) {
 // iteration; the other warps of the CTA wait for this dependent fp64 chain).  Same mathematics, different rounding:
 // a fully unrolled LDL^T (six reciprocals, no square roots, everything in registers) and an SE3 update that goes
 // straight from the rotation vector to the quaternion (one sincos, reciprocal square roots instead of divisions).
-__device__ __forceinline__ bool solve6_ldlt(const double* acc, double* x) {
+__host__ __device__ __forceinline__ bool solve6_ldlt(const double* acc, double* x) {
   double A[6][6];  // lower triangle; fully unrolled => registers
   {
     int n = 0;
@@ -282,7 +282,7 @@ __device__ __forceinline__ bool solve6_ldlt(const double* acc, double* x) {
 }
 
 // pose <- exp(xi) * pose (VertexSE3Expmap::oplusImpl; SE3Quat::exp semantics as se3_oplus), R_out = rotation of the result
-__device__ __forceinline__ void se3_oplus_fast(const double* xi, const double* pose, double* out, double* R_out) {
+__host__ __device__ __forceinline__ void se3_oplus_fast(const double* xi, const double* pose, double* out, double* R_out) {
   const double w0 = xi[0], w1 = xi[1], w2 = xi[2];
   const double th2 = w0 * w0 + w1 * w1 + w2 * w2;
   double b, d, k, c2;  // b = (1 - cos t) / t^2, d = (t - sin t) / t^3, k = sin(t/2) / t, c2 = cos(t/2)

@@ -1,4 +1,5 @@
-// local_ba.cu — K9: Localization::jointOptimization (local bundle adjustment), one CTA per window, fp64.
+// local_ba.cu — K9: Localization::jointOptimization (local bundle adjustment), one CTA — or one thread-block CLUSTER of
+// up to 8 CTAs — per window, fp64.
 //
 // Replaces gmmloc/src/modules/localization_opt.cpp:456-925: g2o Levenberg-Marquardt over the free keyframe
 // poses (VertexSE3Expmap) and all marginalised map points (VertexSBAPointXYZ) of a covisibility window with
@@ -22,6 +23,16 @@
 //   * reduced system: left-looking dense Cholesky with the right-hand side carried as an extra row.
 // LM bookkeeping (g2o OptimizationAlgorithmLevenberg, SURVEY Appx B.7) is evaluated redundantly by all threads
 // from block-reduced values, so control flow stays uniform.
+//
+// Cluster variant (local_ba_kernel<kCl>, kCl = 2 / 4 / 8).  The localisation thread solves ONE window at a time
+// (Localization::run -> jointOptimization, localization.cpp:51,102), and a single CTA walks its 8 MB of per-observation
+// workspace at one SM's L2 rate (67 ms for 12 keyframes / 1 500 points, profiles/bench_ba_r01.jsonl).  With few windows
+// in flight a window is spread over a cluster: every sweep strides over the threads of ALL its CTAs, the sweeps are
+// separated by hardware cluster barriers (barrier.cluster, release / acquire at cluster scope, which also orders the
+// global-memory workspaces between the CTAs), block-wide reductions exchange one partial per CTA through distributed
+// shared memory and add them in rank order in every CTA (so all CTAs take the same branches, bit for bit), and the
+// dense Cholesky of the small reduced system stays inside CTA 0.
+#include <cooperative_groups.h>
 #include <math_constants.h>
 
 #include "gn_common.cuh"
@@ -46,8 +57,36 @@ __device__ __forceinline__ int sym6(int r, int c) {  // packed upper-triangle in
   return r * 6 - r * (r - 1) / 2 + (c - r);
 }
 
-struct Red {
-  double* s;  // kBaW doubles of shared memory
+namespace cg = cooperative_groups;
+
+// The threads that solve one window: one CTA (kCl = 1) or a thread-block cluster of kCl CTAs.
+template <int kCl>
+struct Team {
+  static constexpr int kThreads = kCl * kBaT, kWarps = kCl * kBaW;
+  double* s;      // kBaW doubles of this CTA's shared memory (warp partials)
+  double* s_tot;  // 2 doubles of this CTA's shared memory: its block totals, double-buffered across reductions
+  int* s_int;     // 2 ints, same use
+  int crank;      // rank of this CTA in its cluster
+  int gtid;       // thread index within the team
+  mutable int par = 0;
+
+  __device__ __forceinline__ void sync() const {
+    if (kCl == 1) __syncthreads();
+    else cg::this_cluster().sync();
+  }
+  // combine one value per CTA in rank order (identical in every CTA); `mine` is uniform within the CTA
+  template <class Op>
+  __device__ __forceinline__ double across(double mine, Op op) const {
+    if (kCl == 1) return mine;
+    cg::cluster_group cl = cg::this_cluster();
+    if (threadIdx.x == 0) s_tot[par] = mine;
+    cl.sync();
+    double t = *cl.map_shared_rank(s_tot + par, 0);
+#pragma unroll
+    for (int r = 1; r < kCl; ++r) t = op(t, *cl.map_shared_rank(s_tot + par, r));
+    par ^= 1;  // the next reduction writes the other slot: nobody can still be reading it (see the header comment)
+    return t;
+  }
   __device__ __forceinline__ double sum(double v) const {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -57,7 +96,7 @@ struct Red {
     double t = s[0];
 #pragma unroll
     for (int w = 1; w < kBaW; ++w) t += s[w];
-    return t;
+    return across(t, [](double a, double b) { return a + b; });
   }
   __device__ __forceinline__ double max(double v) const {
 #pragma unroll
@@ -68,11 +107,27 @@ struct Red {
     double t = s[0];
 #pragma unroll
     for (int w = 1; w < kBaW; ++w) t = fmax(t, s[w]);
-    return t;
+    return across(t, [](double a, double b) { return fmax(a, b); });
   }
-  __device__ __forceinline__ int all_ok(bool ok) const {  // block-wide AND
+  __device__ __forceinline__ int all_ok(bool ok) const {  // team-wide AND; also a team barrier
     const int r = __syncthreads_and(ok ? 1 : 0);
-    return r;
+    if (kCl == 1) return r;
+    return across(r ? 1.0 : 0.0, [](double a, double b) { return fmin(a, b); }) != 0.0;
+  }
+  // one value decided by thread 0 of the team, handed to every CTA (each CTA reads its own copy after the barrier)
+  __device__ __forceinline__ int broadcast_from_lead(int v) const {
+    if (kCl == 1) {
+      __syncthreads();
+      if (threadIdx.x == 0) s_int[0] = v;
+      __syncthreads();
+      return s_int[0];
+    }
+    cg::cluster_group cl = cg::this_cluster();
+    cl.sync();
+    if (gtid == 0)
+      for (int r = 0; r < kCl; ++r) *cl.map_shared_rank(s_int, r) = v;
+    cl.sync();
+    return s_int[0];
   }
 };
 
@@ -178,12 +233,13 @@ __device__ __forceinline__ double str_error(const BaArgs& a, int k, int type, co
 }
 
 // computeActiveErrors + activeRobustChi2 at (pose, R, pts); stores the per-edge errors
-__device__ double active_errors(const BaArgs& a, const Prob& p, const Red& red, const double* pose, int pose_stride,
+template <int kCl>
+__device__ double active_errors(const BaArgs& a, const Prob& p, const Team<kCl>& red, const double* pose, int pose_stride,
                                 const double* R, int r_stride, const double* pts, int pts_stride, bool robust,
                                 const double* prior_inv, const double* prior_info) {
   const FrameParamsDev& P = a.prm;
   double part = 0.0;
-  for (int e = threadIdx.x; e < p.d.E; e += kBaT) {
+  for (int e = red.gtid; e < p.d.E; e += Team<kCl>::kThreads) {
     if (p.level[e]) continue;
     const int i = p.obs_kf[e], l = p.obs_pt[e];
     const double* Ri = R + (size_t)i * r_stride;
@@ -203,14 +259,14 @@ __device__ double active_errors(const BaArgs& a, const Prob& p, const Red& red, 
       part += c2;
     }
   }
-  for (int l = threadIdx.x; l < p.d.L; l += kBaT) {
+  for (int l = red.gtid; l < p.d.L; l += Team<kCl>::kThreads) {
     const int k = p.assoc[l];
     const int type = str_type_of(a, k);
     if (!type || p.slevel[l]) continue;
     double es[3];
     part += str_error(a, k, type, pts + (size_t)l * pts_stride, es);
   }
-  if (threadIdx.x == 0 && p.d.prior >= 0) {
+  if (red.gtid == 0 && p.d.prior >= 0) {
     double delta[7], dv[6];
     se3_mul_d(prior_inv, pose + (size_t)p.d.prior * pose_stride, delta);
     se3_log_d(delta, dv);
@@ -219,14 +275,20 @@ __device__ double active_errors(const BaArgs& a, const Prob& p, const Red& red, 
   return red.sum(part);
 }
 
+template <int kCl>
 __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
-  __shared__ double s_red[kBaW];
+  __shared__ double s_red[kBaW], s_tot[2];
+  __shared__ int s_int[2];
   __shared__ double s_prior_inv[7], s_prior_info[6];
-  const Red red{s_red};
-  const int tid = threadIdx.x;
+  constexpr int kGT = Team<kCl>::kThreads, kGW = Team<kCl>::kWarps;
+  const int crank = (kCl == 1) ? 0 : (int)cg::this_cluster().block_rank();
+  const int win = blockIdx.x / kCl;  // window solved by this team
+  const int tid = threadIdx.x, gtid = crank * kBaT + tid;
+  Team<kCl> red;
+  red.s = s_red; red.s_tot = s_tot; red.s_int = s_int; red.crank = crank; red.gtid = gtid;
   const FrameParamsDev& P = a.prm;
   Prob p;
-  p.d = a.prob[blockIdx.x];
+  p.d = a.prob[win];
   const BaProb& d = p.d;
   p.pose = a.pose + d.pose_off * 7;
   p.fidx = a.fidx + d.pose_off;
@@ -236,8 +298,8 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
   p.obs_kf = a.obs_kf + d.obs_off;
   p.obs = a.obs + d.obs_off * 3;
   p.octave = a.octave + d.obs_off;
-  p.pt_ptr = a.pt_ptr + d.pt_off + blockIdx.x;  // L + 1 entries per problem
-  p.kf_ptr = a.kf_ptr + d.free_off + blockIdx.x;
+  p.pt_ptr = a.pt_ptr + d.pt_off + win;  // L + 1 entries per problem
+  p.kf_ptr = a.kf_ptr + d.free_off + win;
   p.kf_obs = a.kf_obs + d.kfo_off;
   p.blk_ptr = a.blk_ptr + d.blk_off;
   p.contrib = a.contrib + d.c_off;
@@ -257,44 +319,42 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
   // host-mapped memory the calling thread keeps in step with the caller's flag while the kernel runs; thread 0 reads it
   // wherever g2o calls terminate() and the CTA takes the same branch.  *stop > 0: raised; 0: not raised; -n: reads as
   // raised from the n-th poll on (the deterministic replay hook the parity tests use).
-  __shared__ int s_polls, s_stop;
-  if (tid == 0) s_polls = 0;
+  int polls = 0;  // counted by every thread alike (uniform control flow), used by the team's lead thread
   auto terminate = [&]() -> bool {
     if (a.stop == nullptr) return false;
-    __syncthreads();
-    if (tid == 0) {
-      const int v = *a.stop;
-      ++s_polls;
-      s_stop = (v > 0 || (v < 0 && s_polls >= -v)) ? 1 : 0;
+    ++polls;
+    int v = 0;
+    if (gtid == 0) {
+      const int raw = *a.stop;
+      v = (raw > 0 || (raw < 0 && polls >= -raw)) ? 1 : 0;
     }
-    __syncthreads();
-    return s_stop != 0;
+    return red.broadcast_from_lead(v) != 0;  // one read of the flag per poll: every CTA of the team takes the same branch
   };
   // `if (pbStopFlag) if (*pbStopFlag) return;` ahead of the first optimize (:765-767): the window is left untouched
   if (terminate()) {
     if (a.assoc_cleared)
-      for (int l = tid; l < d.L; l += kBaT) a.assoc_cleared[d.pt_off + l] = 0;
+      for (int l = gtid; l < d.L; l += kGT) a.assoc_cleared[d.pt_off + l] = 0;
     if (a.obs_outlier)
-      for (int e = tid; e < d.E; e += kBaT) a.obs_outlier[d.obs_off + e] = 0;
-    if (tid == 0) {
+      for (int e = gtid; e < d.E; e += kGT) a.obs_outlier[d.obs_off + e] = 0;
+    if (gtid == 0) {
       if (a.iters)
-        for (int q = 0; q < 3; ++q) a.iters[(size_t)blockIdx.x * 3 + q] = 0;
-      if (a.status) a.status[blockIdx.x] = 0;
+        for (int q = 0; q < 3; ++q) a.iters[(size_t)win * 3 + q] = 0;
+      if (a.status) a.status[win] = 0;
     }
     return;
   }
 
   // ---- init: normalise poses, rotation cache, levels, prior measurement ----
-  for (int i = tid; i < d.P; i += kBaT) {
+  for (int i = gtid; i < d.P; i += kGT) {
     quat_normalize(p.pose + (size_t)i * 7);
     quat_to_rot(p.pose + (size_t)i * 7, p.wq + (size_t)i * kPoseWs + qR);
   }
-  for (int e = tid; e < d.E; e += kBaT) {
+  for (int e = gtid; e < d.E; e += kGT) {
     p.level[e] = 0;
     for (int q = 0; q < 3; ++q) p.wo[(size_t)e * kObsWs + oErr + q] = 0.0;
   }
-  for (int l = tid; l < d.L; l += kBaT) p.slevel[l] = 0;
-  __syncthreads();
+  for (int l = gtid; l < d.L; l += kGT) p.slevel[l] = 0;
+  red.sync();
   if (tid == 0 && d.prior >= 0) {
     se3_inverse_d(p.pose + (size_t)d.prior * 7, s_prior_inv);  // setMeasurement(kfi_ptr->getTcw()), :566
     const double sigma_rot = 2.0 * CUDART_PI / 180.0;
@@ -303,7 +363,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
       s_prior_info[3 + q] = 1.0 / (0.01 * 0.01);
     }
   }
-  __syncthreads();
+  red.sync();
 
   bool robust = true;
   int iters_run[3] = {0, 0, 0};
@@ -317,7 +377,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
     for (; it < max_it && !terminate() && ok; ++it) {  // SparseOptimizer::optimize: i < iterations && !terminate() && ok
       double cur_chi = active_errors(a, p, red, p.pose, 7, p.wq + qR, kPoseWs, p.pts, 3, robust, s_prior_inv, s_prior_info);
       // ---- linearise every active edge at the current estimate ----
-      for (int e = tid; e < d.E; e += kBaT) {
+      for (int e = gtid; e < d.E; e += kGT) {
         if (p.level[e]) continue;
         const int i = p.obs_kf[e], l = p.obs_pt[e], f = p.fidx[i];
         const double* Ri = p.wq + (size_t)i * kPoseWs + qR;
@@ -412,10 +472,10 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
           }
         }
       }
-      __syncthreads();
+      red.sync();
       // ---- per point: Hll, bl (reprojection pieces of its observations + structure edge) ----
       double md = 0.0;
-      for (int l = tid; l < d.L; l += kBaT) {
+      for (int l = gtid; l < d.L; l += kGT) {
         double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
         for (int e = p.pt_ptr[l]; e < p.pt_ptr[l + 1]; ++e) {
           if (p.level[e]) continue;
@@ -452,7 +512,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
       }
       // ---- per free pose: Hpp (21) and bp (6) from its observations: one warp per pose, lanes stride over the
       // pose's observation list, fixed-shape shuffle tree (deterministic) ----
-      for (int f = tid >> 5; f < nf; f += kBaW) {
+      for (int f = gtid >> 5; f < nf; f += kGW) {
         double acc[kFreeWs];
 #pragma unroll
         for (int q = 0; q < kFreeWs; ++q) acc[q] = 0.0;
@@ -471,8 +531,8 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
           if ((tid & 31) == 0) p.wf[(size_t)f * kFreeWs + q] = v;
         }
       }
-      __syncthreads();
-      if (tid == 0 && d.prior >= 0 && p.fidx[d.prior] >= 0) {  // EdgeSE3QuatPrior, factors.cpp:31-53
+      red.sync();
+      if (gtid == 0 && d.prior >= 0 && p.fidx[d.prior] >= 0) {  // EdgeSE3QuatPrior, factors.cpp:31-53
         const int f = p.fidx[d.prior];
         double delta[7], dv[6], Jr[36], Tinv[7], Ad[36], J[36], Rinv[9];
         se3_mul_d(s_prior_inv, p.pose + (size_t)d.prior * 7, delta);
@@ -516,9 +576,9 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
           w[fB + r] -= s;
         }
       }
-      __syncthreads();
+      red.sync();
       if (it == 0) {  // computeLambdaInit: tau * max |diagonal|, tau = 1e-5
-        for (int f = tid; f < nf; f += kBaT) {
+        for (int f = gtid; f < nf; f += kGT) {
           const double* w = p.wf + (size_t)f * kFreeWs + fH;
           for (int r = 0; r < 6; ++r) md = fmax(md, fabs(w[sym6(r, r)]));
         }
@@ -530,7 +590,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
       do {
         // ---- Schur complement at damping lambda ----
         bool good = true;
-        for (int l = tid; l < d.L; l += kBaT) {
+        for (int l = gtid; l < d.L; l += kGT) {
           double* w = p.wp + (size_t)l * kPtWs;
           const double hxx = w[pH] + lambda, hxy = w[pH + 1], hxz = w[pH + 2], hyy = w[pH + 3] + lambda, hyz = w[pH + 4],
                        hzz = w[pH + 5] + lambda;
@@ -549,7 +609,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
         good = red.all_ok(good) != 0;  // also orders the Hinv writes before the block tasks
         if (good) {
           // per observation on a free pose: T = Hpl Hll^-1 (6x3) and Hpl (Hll^-1 bl) (6)
-          for (int e = tid; e < d.E; e += kBaT) {
+          for (int e = gtid; e < d.E; e += kGT) {
             if (p.level[e] || p.fidx[p.obs_kf[e]] < 0) continue;
             double* o = p.wo + (size_t)e * kObsWs;
             const double* w = p.wp + (size_t)p.obs_pt[e] * kPtWs;
@@ -564,22 +624,22 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
               o[oGy + r] = (w0 * yl[0] + w1 * yl[1]) + w2 * yl[2];
             }
           }
-          __syncthreads();
-          // reduced system: one thread per ROW of every lower 6x6 block walks the block's contribution list
+          red.sync();
+          // reduced system: one WARP per ROW of every lower 6x6 block; the lanes stride over the block's contribution list
+          // (a single thread per row walked ~2 500 pairs one dependent L2 round trip at a time: that loop, not the sweeps
+          // over observations, was the bulk of an LM iteration of a lone window) and fold with a fixed shuffle tree
           const int nblk = nf * (nf + 1) / 2;
-          for (int task = tid; task < nblk * 6; task += kBaT) {
+          for (int task = gtid >> 5; task < nblk * 6; task += kGW) {
             const int blk = task / 6, r = task % 6;
             // blk = fi (fi + 1) / 2 + fj, fj <= fi
             int fi = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
             while ((fi + 1) * (fi + 2) / 2 <= blk) ++fi;
             while (fi * (fi + 1) / 2 > blk) --fi;
             const int fj = blk - fi * (fi + 1) / 2;
-            double acc[6];
-#pragma unroll
-            for (int c = 0; c < 6; ++c) acc[c] = (fi == fj) ? p.wf[(size_t)fi * kFreeWs + fH + sym6(r, c)] + (r == c ? lambda : 0.0) : 0.0;
+            double acc[6] = {0, 0, 0, 0, 0, 0};
             const int j1 = p.blk_ptr[blk + 1];
 #pragma unroll 2
-            for (int j = p.blk_ptr[blk]; j < j1; ++j) {
+            for (int j = p.blk_ptr[blk] + (tid & 31); j < j1; j += 32) {
               const int2 ab = p.contrib[j];
               if (p.level[ab.x] | p.level[ab.y]) continue;
               const double* Ta = p.wo + (size_t)ab.x * kObsWs + oT + r * 3;
@@ -589,10 +649,18 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
               for (int c = 0; c < 6; ++c) acc[c] -= (t0 * Wb[c * 3] + t1 * Wb[c * 3 + 1]) + t2 * Wb[c * 3 + 2];
             }
 #pragma unroll
-            for (int c = 0; c < 6; ++c) p.S[(size_t)(6 * fi + r) * n + 6 * fj + c] = acc[c];
+            for (int c = 0; c < 6; ++c) {
+              double v = acc[c];
+#pragma unroll
+              for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+              if ((tid & 31) == 0) {
+                if (fi == fj) v += p.wf[(size_t)fi * kFreeWs + fH + sym6(r, c)] + (r == c ? lambda : 0.0);
+                p.S[(size_t)(6 * fi + r) * n + 6 * fj + c] = v;
+              }
+            }
           }
           // right-hand side: one warp per free pose
-          for (int f = tid >> 5; f < nf; f += kBaW) {
+          for (int f = gtid >> 5; f < nf; f += kGW) {
             double acc[6] = {0, 0, 0, 0, 0, 0};
             for (int j = p.kf_ptr[f] + (tid & 31); j < p.kf_ptr[f + 1]; j += 32) {
               const int e = p.kf_obs[j];
@@ -609,52 +677,57 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
               if ((tid & 31) == 0) p.rhs[6 * f + r] = p.wf[(size_t)f * kFreeWs + fB + r] - v;
             }
           }
-          __syncthreads();
+          red.sync();
           // ---- left-looking Cholesky of the lower triangle; the rhs rides along as row n (forward solve) ----
-          for (int k = 0; k < n && good; ++k) {
-            for (int i = k + tid; i <= n; i += kBaT) {
-              double* row = (i < n) ? p.S + (size_t)i * n : p.rhs;
-              const double* rk = p.S + (size_t)k * n;
-              double s = row[k];
-              for (int j = 0; j < k; ++j) s -= row[j] * rk[j];
-              row[k] = s;
-            }
-            __syncthreads();
-            const double dkk = p.S[(size_t)k * n + k];
-            good = (dkk > 0.0) && isfinite(dkk);  // uniform: every thread reads the same value
-            const double sd = sqrt(dkk);
-            __syncthreads();
-            if (good) {
+          // The reduced system is small (n = 6 free poses): its ~3 n barriers stay inside CTA 0 of the team; the other
+          // CTAs wait at the team-wide vote below.
+          if (crank == 0) {
+            for (int k = 0; k < n && good; ++k) {
               for (int i = k + tid; i <= n; i += kBaT) {
                 double* row = (i < n) ? p.S + (size_t)i * n : p.rhs;
-                if (i == k) {
-                  p.diag[k] = sd;
-                  row[k] = sd;
-                } else {
-                  row[k] = row[k] / sd;
+                const double* rk = p.S + (size_t)k * n;
+                double s = row[k];
+                for (int j = 0; j < k; ++j) s -= row[j] * rk[j];
+                row[k] = s;
+              }
+              __syncthreads();
+              const double dkk = p.S[(size_t)k * n + k];
+              good = (dkk > 0.0) && isfinite(dkk);  // uniform: every thread reads the same value
+              const double sd = sqrt(dkk);
+              __syncthreads();
+              if (good) {
+                for (int i = k + tid; i <= n; i += kBaT) {
+                  double* row = (i < n) ? p.S + (size_t)i * n : p.rhs;
+                  if (i == k) {
+                    p.diag[k] = sd;
+                    row[k] = sd;
+                  } else {
+                    row[k] = row[k] / sd;
+                  }
                 }
               }
-            }
-            __syncthreads();
-          }
-          // ---- back substitution L^T x = y (y is in rhs) ----
-          if (good) {
-            for (int k = n - 1; k >= 0; --k) {
-              if (tid == 0) p.dxp[k] = p.rhs[k] / p.diag[k];
-              __syncthreads();
-              const double xk = p.dxp[k];
-              for (int i = tid; i < k; i += kBaT) p.rhs[i] -= p.S[(size_t)k * n + i] * xk;
               __syncthreads();
             }
-            bool fin = true;
-            for (int i = tid; i < n; i += kBaT) fin = fin && isfinite(p.dxp[i]);
-            good = red.all_ok(fin) != 0;
+            // ---- back substitution L^T x = y (y is in rhs) ----
+            if (good) {
+              for (int k = n - 1; k >= 0; --k) {
+                if (tid == 0) p.dxp[k] = p.rhs[k] / p.diag[k];
+                __syncthreads();
+                const double xk = p.dxp[k];
+                for (int i = tid; i < k; i += kBaT) p.rhs[i] -= p.S[(size_t)k * n + i] * xk;
+                __syncthreads();
+              }
+              bool fin = true;
+              for (int i = tid; i < n; i += kBaT) fin = fin && isfinite(p.dxp[i]);
+              good = __syncthreads_and(fin ? 1 : 0) != 0;
+            }
           }
+          good = red.all_ok(good) != 0;  // CTA 0's verdict reaches the whole team; also publishes dxp
         }
         // ---- landmark back-substitution, trial state ----
         if (good) {
           bool fin = true;
-          for (int l = tid; l < d.L; l += kBaT) {
+          for (int l = gtid; l < d.L; l += kGT) {
             double* w = p.wp + (size_t)l * kPtWs;
             double c[3] = {w[pB], w[pB + 1], w[pB + 2]};
             for (int e = p.pt_ptr[l]; e < p.pt_ptr[l + 1]; ++e) {
@@ -682,7 +755,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
         }
         double tmp_chi = 1.7976931348623157e308, scale = 0.0;
         if (good) {
-          for (int i = tid; i < d.P; i += kBaT) {
+          for (int i = gtid; i < d.P; i += kGT) {
             double* w = p.wq + (size_t)i * kPoseWs;
             const int f = p.fidx[i];
             if (f >= 0) {
@@ -692,15 +765,15 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
             }
             quat_to_rot(w + qTr, w + qRt);
           }
-          __syncthreads();
+          red.sync();
           tmp_chi = active_errors(a, p, red, p.wq + qTr, kPoseWs, p.wq + qRt, kPoseWs, p.wp + pTr, kPtWs, robust, s_prior_inv,
                                   s_prior_info);
           double part = 0.0;
-          for (int i = tid; i < n; i += kBaT) {
+          for (int i = gtid; i < n; i += kGT) {
             const double dx = p.dxp[i];
             part += dx * (lambda * dx + p.wf[(size_t)(i / 6) * kFreeWs + fB + i % 6]);
           }
-          for (int l = tid; l < d.L; l += kBaT) {
+          for (int l = gtid; l < d.L; l += kGT) {
             const double* w = p.wp + (size_t)l * kPtWs;
             for (int q = 0; q < 3; ++q) part += w[pDx + q] * (lambda * w[pDx + q] + w[pB + q]);
           }
@@ -714,14 +787,14 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
           lambda *= fmax(1. / 3., alpha);
           ni = 2;
           cur_chi = tmp_chi;
-          for (int i = tid; i < d.P; i += kBaT) {
+          for (int i = gtid; i < d.P; i += kGT) {
             double* w = p.wq + (size_t)i * kPoseWs;
             for (int q = 0; q < 7; ++q) p.pose[(size_t)i * 7 + q] = w[qTr + q];
             for (int q = 0; q < 9; ++q) w[qR + q] = w[qRt + q];
           }
-          for (int l = tid; l < d.L; l += kBaT)
+          for (int l = gtid; l < d.L; l += kGT)
             for (int q = 0; q < 3; ++q) p.pts[(size_t)l * 3 + q] = p.wp[(size_t)l * kPtWs + pTr + q];
-          __syncthreads();
+          red.sync();
         } else {
           if (!good) numeric_trouble = true;
           lambda *= ni;
@@ -735,7 +808,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
     iters_run[stage] = it;
     // ---- edge gating between the stages ----
     if (stage == 0) {  // :774-786
-      for (int l = tid; l < d.L; l += kBaT) {
+      for (int l = gtid; l < d.L; l += kGT) {
         const int k = p.assoc[l];
         if (str_type_of(a, k) != 1) continue;
         double es[3];
@@ -743,7 +816,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
       }
     } else if (stage == 1) {  // :797-823
       if (terminate()) break;  // bDoMore = false (:791-795): no reprojection gating, no kernel removal, no stage 3
-      for (int e = tid; e < d.E; e += kBaT) {
+      for (int e = gtid; e < d.E; e += kGT) {
         const double* er = p.wo + (size_t)e * kObsWs + oErr;
         const float* ob = p.obs + (size_t)e * 3;
         const bool stereo = !(ob[2] < 0.0f);
@@ -756,11 +829,11 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
       }
       robust = false;
     }
-    __syncthreads();
+    red.sync();
   }
 
   // ---- results (:842-881) ----
-  for (int l = tid; l < d.L; l += kBaT) {
+  for (int l = gtid; l < d.L; l += kGT) {
     uint8_t cl = 0;
     const int k = p.assoc[l];
     if (str_type_of(a, k) == 1) {
@@ -770,7 +843,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
     if (a.assoc_cleared) a.assoc_cleared[d.pt_off + l] = cl;
   }
   if (a.obs_outlier) {
-    for (int e = tid; e < d.E; e += kBaT) {
+    for (int e = gtid; e < d.E; e += kGT) {
       const double* er = p.wo + (size_t)e * kObsWs + oErr;
       const float* ob = p.obs + (size_t)e * 3;
       const bool stereo = !(ob[2] < 0.0f);
@@ -782,19 +855,51 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
       a.obs_outlier[d.obs_off + e] = (c2 > (stereo ? 7.815 : 5.991) || !(z > 0.0)) ? 1 : 0;
     }
   }
-  if (tid == 0) {
+  if (gtid == 0) {
     if (a.iters)
-      for (int q = 0; q < 3; ++q) a.iters[(size_t)blockIdx.x * 3 + q] = iters_run[q];
-    if (a.status) a.status[blockIdx.x] = numeric_trouble ? GMMLOC_FRAME_NUMERIC : 0;
+      for (int q = 0; q < 3; ++q) a.iters[(size_t)win * 3 + q] = iters_run[q];
+    if (a.status) a.status[win] = numeric_trouble ? GMMLOC_FRAME_NUMERIC : 0;
   }
 }
 
 }  // namespace
 
-cudaError_t launch_local_ba(const BaArgs& a, cudaStream_t stream) {
+template <int kCl>
+static cudaError_t launch_ba_t(const BaArgs& a, cudaStream_t stream) {
+  if (kCl == 1) {
+    local_ba_kernel<1><<<a.B, kBaT, 0, stream>>>(a);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)a.B * kCl, 1, 1);
+  cfg.blockDim = dim3(kBaT, 1, 1);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCl;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, local_ba_kernel<kCl>, a);
+}
+
+cudaError_t launch_local_ba(const BaArgs& a, cudaStream_t stream, int cluster) {
   if (a.B <= 0) return cudaSuccess;
-  local_ba_kernel<<<a.B, kBaT, 0, stream>>>(a);
-  return cudaGetLastError();
+  // CTAs per window: as many as keep the machine busy with the windows of this call (148 SMs), at most the portable
+  // cluster size 8 — a single window (what the localisation thread solves per keyframe) gets 8 SMs, a batch of a
+  // hundred windows one CTA each (where the single-CTA kernel already fills the GPU)
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int cl = cluster > 0 ? cluster : (a.B * 8 <= sms ? 8 : a.B * 4 <= sms ? 4 : a.B * 2 <= sms ? 2 : 1);
+  switch (cl) {
+    case 8: return launch_ba_t<8>(a, stream);
+    case 4: return launch_ba_t<4>(a, stream);
+    case 2: return launch_ba_t<2>(a, stream);
+    default: return launch_ba_t<1>(a, stream);
+  }
 }
 
 int local_ba_obs_ws() { return kObsWs; }

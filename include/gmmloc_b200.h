@@ -181,8 +181,10 @@ GMMLOC_API int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx);
  * single free pose, localization_opt.cpp:456-925):
  *   GMMLOC_GN_MIXED (default)  state, residuals and the 6x6 reduced system in fp64, Jacobian / Hessian-model algebra
  *                              in fp32 — same fixed point (poses agree with the fp64 solve to ~1e-9), ~3x faster;
+ *   GMMLOC_GN_WORLD            the same precision split with the per-point blocks written in the world frame (the
+ *                              structure edge needs no rotation, the point step no pose; 16 instead of 12 warps per SM);
  *   GMMLOC_GN_FP64             everything in fp64. */
-enum { GMMLOC_GN_FP64 = 0, GMMLOC_GN_MIXED = 1 };
+enum { GMMLOC_GN_FP64 = 0, GMMLOC_GN_MIXED = 1, GMMLOC_GN_WORLD = 2 };
 GMMLOC_API gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int precision);
 
 /* Tuning switches of a context for A/B measurements; every setting returns identical results.  (Environment variables
@@ -191,8 +193,10 @@ GMMLOC_API gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int pr
  *                               mixed-precision frame GN;
  *   GMMLOC_OPT_E2E_CHUNK        frames per pipeline chunk of the host entry point gmmloc_frames_solve (0 = automatic:
  *                               6 frames per SM);
- *   GMMLOC_OPT_E2E_SHORT_FIRST  1: the first pipeline chunk is a third of the others (default 0). */
-enum { GMMLOC_OPT_GN_PREP = 0, GMMLOC_OPT_E2E_CHUNK = 1, GMMLOC_OPT_E2E_SHORT_FIRST = 2 };
+ *   GMMLOC_OPT_E2E_SHORT_FIRST  1: the first pipeline chunk is a third of the others (default 0);
+ *   GMMLOC_OPT_BA_CLUSTER       CTAs (SMs) per window of gmmloc_local_ba: 1, 2, 4 or 8 (thread-block cluster), 0 = automatic
+ *                               (8 for a single window ... 1 once the windows of a call fill the GPU). */
+enum { GMMLOC_OPT_GN_PREP = 0, GMMLOC_OPT_E2E_CHUNK = 1, GMMLOC_OPT_E2E_SHORT_FIRST = 2, GMMLOC_OPT_BA_CLUSTER = 3 };
 GMMLOC_API gmmloc_status_t gmmloc_ctx_set_option(gmmloc_ctx_t* ctx, int option, int64_t value);
 
 /* page-locked host memory for the host entry points (pageable buffers also work, via staging) */

@@ -1,0 +1,99 @@
+"""The algebra of the world-frame frame GN kernel (K3w, gmmloc_b200/csrc/frame_gn_world.cuh) checked on the CPU: tests/cpp/
+gnw_host_check.cu replays the kernel's sweep schedule on the host with the very functions the kernel compiles, and the
+result is compared with the oracle on contracting frames.  (The GPU parity tests do the same through the C ABI.)"""
+import ctypes as C
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from gmmloc_b200 import synth
+from tests import np_reference as ref
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+class FrameParamsDev(C.Structure):  # gmmloc_b200/csrc/common.cuh
+    _fields_ = [(n, C.c_double) for n in ("fx", "fy", "cx", "cy", "bf", "tri_lambda2", "ba_lambda2", "tri_str_thresh", "mdist2_gate",
+                                          "chi2_mono", "chi2_stereo", "delta_mono", "delta_stereo")] + \
+               [("s2inv", C.c_float * 8)] + [(n, C.c_int) for n in ("gn_iters", "robust", "factor_mode", "tri_check_str_chi2")]
+
+
+@pytest.fixture(scope="module")
+def host_lib(tmp_path_factory):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        pytest.skip("nvcc not available")
+    so = tmp_path_factory.mktemp("gnw") / "libgnw_host.so"
+    subprocess.run([nvcc, "-x", "cu", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr", "-w", "-o",
+                    str(so), str(ROOT / "tests" / "cpp" / "gnw_host_check.cu")], check=True, capture_output=True)
+    lib = C.CDLL(str(so))
+    lib.gnw_host_frame_solve.restype = C.c_int
+    return lib
+
+
+def _params(oracle, **kw):
+    o = oracle.default_params(**kw)
+    cam = oracle.v1_camera()
+    p = FrameParamsDev()
+    p.fx, p.fy, p.cx, p.cy, p.bf = cam.fx, cam.fy, cam.cx, cam.cy, cam.bf
+    p.tri_lambda2, p.ba_lambda2, p.tri_str_thresh, p.mdist2_gate = o.tri_lambda2, o.ba_lambda2, o.tri_str_thresh, o.mdist2_gate
+    p.chi2_mono, p.chi2_stereo = o.chi2_mono, o.chi2_stereo
+    p.delta_mono, p.delta_stereo = float(np.float32(np.sqrt(5.991))), float(np.float32(np.sqrt(7.815)))
+    for i in range(8):
+        p.s2inv[i] = oracle.sigma2_inv(i)
+    p.gn_iters, p.robust, p.factor_mode, p.tri_check_str_chi2 = o.gn_iters, o.robust, o.factor_mode, o.tri_check_str_chi2
+    return p, o
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+CASES = {
+    "c2": dict(K=10000, pdeg=0.5, N=2000, mono=0.0, kw={}),
+    "c5_style": dict(K=20000, pdeg=0.95, N=1500, mono=0.3, kw=dict(robust=1)),
+    "pose_only": dict(K=2000, pdeg=0.6, N=700, mono=0.25, kw=dict(factor_mode=1)),
+    "points_only": dict(K=2000, pdeg=0.6, N=700, mono=0.25, kw=dict(factor_mode=2)),
+    "three_iters": dict(K=1500, pdeg=0.5, N=400, mono=0.0, kw=dict(gn_iters=3)),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+def test_world_frame_host_replay_matches_oracle(host_lib, oracle, case):
+    c = CASES[case]
+    mean, cov = synth.make_map(c["K"], c["pdeg"], seed=11)
+    B = 6
+    fr = synth.make_frames(mean, cov, B, c["N"], seed=12, mono_frac=c["mono"])
+    comps = oracle.map_build(mean, cov)
+    p, oprm = _params(oracle, **c["kw"])
+    exp = oracle.frames_solve(comps, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], prm=oprm, nthreads=8, want_pts=True, want_conv=True)
+    cm, ci, ax = (np.ascontiguousarray(comps[k]) for k in ("mean", "cov_inv", "axis"))
+    dg = np.ascontiguousarray(comps["is_degenerated"].astype(np.uint8))
+    seen = set()
+    compared = 0
+    for f in range(B):
+        asg = exp["assign"][f] if oprm.factor_mode != 1 else np.full(c["N"], -1, np.int32)
+        pose = np.zeros(7)
+        pts = np.zeros((c["N"], 3))
+        cls = np.zeros(c["N"], np.uint8)
+        rc = host_lib.gnw_host_frame_solve(_ptr(cm), _ptr(ci), _ptr(ax), _ptr(dg), C.byref(p), _ptr(np.ascontiguousarray(fr["pose0"][f])),
+                                           _ptr(np.ascontiguousarray(fr["pts_w"][f])), _ptr(np.ascontiguousarray(fr["obs"][f])),
+                                           _ptr(np.ascontiguousarray(fr["octave"][f])), _ptr(np.ascontiguousarray(asg)), c["N"],
+                                           _ptr(pose), _ptr(pts), _ptr(cls))
+        assert rc == exp["status"][f]
+        seen |= set(np.unique(cls).tolist())
+        if exp["status"][f] or ((exp["conv"][f, 1] > 1e-7) and (exp["conv"][f, 0] > 1e-6)):
+            continue  # failed / non-contracting reference iteration: not comparable (see _check_frames in test_gpu_parity.py)
+        ang = ref.rot_angle(synth.quat_to_rot(pose[:4]), synth.quat_to_rot(exp["pose"][f, :4]))
+        dt = float(np.abs(pose[4:] - exp["pose"][f, 4:]).max())
+        assert ang < 1e-6 and dt < 1e-5, (case, f, ang, dt)
+        # after the full 10 iterations a point whose own last step still exceeds 1 mm is diverging: not comparable
+        ok = (exp["pt_last"][f] <= 1e-3) if oprm.gn_iters >= 8 else np.ones(c["N"], bool)
+        assert np.abs(pts - exp["pts"][f])[ok].max() < 1e-5, (case, f)
+        compared += 1
+    assert compared >= B - 2
+    if case == "c5_style":
+        assert {1, 2, 3, 4, 5, 6} <= seen  # every fp32 point class was exercised (7 = far points: the 'far' case)

@@ -143,3 +143,29 @@ def test_local_ba_stop_flag_raised_by_another_thread(gpu, ba_map):
     outs = ctx.jointOptimization(m, pbs, stop=flag)
     th.join()
     assert sum(int(o["iters"].sum()) for o in outs) < sum(int(o["iters"].sum()) for o in full)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_local_ba_cluster_variants(gpu, oracle, ba_map, cluster):
+    """A window spread over a thread-block cluster of 2 / 4 / 8 CTAs (distributed-shared-memory reductions, cluster barriers
+    between the sweeps) against the oracle and against the single-CTA kernel: same flags, poses within tolerance."""
+    g, ctx = gpu
+    m, comps, mean, cov = ba_map
+    pbs = [synth.make_ba_problem(mean, cov, 12, 3, 1500, seed=60), synth.make_ba_problem(mean, cov, 5, 2, 150, seed=61)]
+    pbs[1]["prior_idx"] = 0
+    ctx.set_option(g.capi.OPT_BA_CLUSTER, cluster)
+    try:
+        outs = ctx.jointOptimization(m, pbs)
+        again = ctx.jointOptimization(m, pbs)
+        stopped = ctx.jointOptimization(m, pbs[:1], stop=-9)[0]
+    finally:
+        ctx.set_option(g.capi.OPT_BA_CLUSTER, 0)
+    for pb, out in zip(pbs, outs):
+        want = oracle.local_ba(comps, pb["pose"], pb["fixed"], pb["pts"], pb["assoc"], pb["obs_pt"], pb["obs_kf"], pb["obs"],
+                               pb["octave"], prior_idx=pb.get("prior_idx", -1))
+        assert out["status"] == 0
+        _check(out, want, pb)
+    assert np.array_equal(again[0]["pose"], outs[0]["pose"]) and np.array_equal(again[0]["pts"], outs[0]["pts"])  # deterministic
+    want = oracle.local_ba(comps, pbs[0]["pose"], pbs[0]["fixed"], pbs[0]["pts"], pbs[0]["assoc"], pbs[0]["obs_pt"], pbs[0]["obs_kf"],
+                           pbs[0]["obs"], pbs[0]["octave"], stop=-9)
+    assert np.array_equal(stopped["iters"], want["iters"])

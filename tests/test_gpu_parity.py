@@ -240,7 +240,7 @@ def _check_frames(g, ctx, oracle, mean, cov, fr, **kw):
     front of the camera oscillating on its component, a monocular point on an edge-on plane ...) amplifies the last bit of
     ANY arithmetic — the all-fp64 kernel deviates from the oracle on exactly those frames too
     (tools/diag_convergence.py, profiles/diag_convergence_r02.txt) — so such frames (and, inside a contracting frame,
-    points whose own last step still exceeds 1e-5 m) are counted, bounded and reported, not compared.  Returns
+    points whose own last step still exceeds 1 mm: diverging) are counted, bounded and reported, not compared.  Returns
     (out, exp, worst pose error over the compared frames)."""
     m = g.GMM(mean, cov)
     comps = oracle.map_build(mean, cov)
@@ -259,9 +259,11 @@ def _check_frames(g, ctx, oracle, mean, cov, fr, **kw):
         ang, dt = _pose_err(out["pose"][f], exp["pose"][f])
         worst = (max(worst[0], ang), max(worst[1], dt))
     assert worst[0] < TOL_RAD and worst[1] < TOL_M, worst
-    settled = (~chaotic)[:, None] & (exp["pt_last"] <= 1e-5)
-    assert settled.mean() > 0.97, float(settled.mean())
-    dpt = np.abs(out["pts"].astype(np.float64) - exp["pts"]).max(axis=2)
+    # (the point filter only makes sense once the iteration had the time to settle: runs with fewer than 8 iterations compare all)
+    settled = (~chaotic)[:, None] & ((exp["pt_last"] <= 1e-3) | (prm_o.gn_iters < 8))
+    assert settled[~chaotic].mean() > 0.97, float(settled[~chaotic].mean())  # diverging points are rare
+    both_nan = np.isnan(out["pts"]) & np.isnan(exp["pts"])  # a non-finite input landmark comes back as it went in
+    dpt = np.where(both_nan, 0.0, np.abs(out["pts"].astype(np.float64) - exp["pts"])).max(axis=2)
     assert dpt[settled].max(initial=0.0) < TOL_M, float(dpt[settled].max())
     mism = int(((out["outlier"] != exp["outlier"]) & settled).sum())
     assert mism == 0
@@ -719,3 +721,100 @@ def test_environment_variables_do_not_steer_a_production_build(gpu, monkeypatch)
         assert np.array_equal(a[k], b[k]), k
     with pytest.raises(g.GmmlocError):
         ctx.set_option(99, 0)
+
+
+# ---------------------------------------------------------------- world-frame frame GN (K3w)
+import contextlib
+
+
+@contextlib.contextmanager
+def _gn(g, ctx, precision):
+    ctx.set_gn_precision(precision)
+    try:
+        yield
+    finally:
+        ctx.set_gn_precision(g.capi.GN_DEFAULT)
+
+
+@pytest.mark.parametrize("case", ["c1", "c2", "pose_only", "points_only", "c5_style", "shipped_v1", "iters", "nan"])
+def test_world_frame_kernel_matches_oracle(gpu, oracle, golden_maps, gt_v1_03, case):
+    """K3w (per-point blocks in the world frame, frame_gn_world.cu) against the oracle on the cases K3m is checked on."""
+    g, ctx = gpu
+    with _gn(g, ctx, g.capi.GN_WORLD):
+        if case == "c1":
+            mean, cov = synth.make_map(1000, 0.5)
+            _check_frames(g, ctx, oracle, mean, cov, synth.make_frames(mean, cov, 6, 500, seed=1))
+        elif case == "c2":
+            mean, cov = synth.make_map(10000, 0.5)
+            _check_frames(g, ctx, oracle, mean, cov, synth.make_frames(mean, cov, 8, 2000, seed=2))
+        elif case in ("pose_only", "points_only"):
+            mean, cov = synth.make_map(2000, 0.6, seed=3)
+            fr = synth.make_frames(mean, cov, 4, 700, seed=3, mono_frac=0.25)
+            _check_frames(g, ctx, oracle, mean, cov, fr, factor_mode=1 if case == "pose_only" else 2)
+        elif case == "c5_style":
+            mean, cov = synth.make_map(20000, 0.95, seed=4)
+            _check_frames(g, ctx, oracle, mean, cov, synth.make_frames(mean, cov, 3, 1500, seed=4, mono_frac=0.3), robust=1)
+        elif case == "shipped_v1":
+            gm = golden_maps["v1"]
+            idx = np.arange(0, len(gt_v1_03), 307)
+            fr = synth.make_frames(gm["mean"], gm["cov"], len(idx), 1200, seed=5, poses_wc=gt_v1_03[idx, 1:8])
+            _check_frames(g, ctx, oracle, gm["mean"], gm["cov"], fr)
+        elif case == "iters":
+            mean, cov = synth.make_map(1500, 0.5, seed=6)
+            fr = synth.make_frames(mean, cov, 2, 400, seed=6)
+            for it in (0, 1, 3):
+                _check_frames(g, ctx, oracle, mean, cov, fr, gn_iters=it)
+        else:
+            mean, cov = synth.make_map(1000, 0.5, seed=7)
+            fr = synth.make_frames(mean, cov, 3, 300, seed=7)
+            fr["pts_w"][1, 17] = np.nan
+            out, exp, _ = _check_frames(g, ctx, oracle, mean, cov, fr)
+            assert list(out["status"]) == [0, g.FRAME_NUMERIC, 0]
+
+
+@pytest.mark.parametrize("N", [1, 31, 1230, 1231, 1232, 1233, 2573, 2574, 2575, 2576, 5001, 5187, 5188, 5189, 5190, 5819, 5820])
+def test_world_frame_kernel_variant_boundaries(gpu, oracle, N):
+    """Frame sizes around every launch-variant switch of K3w: two resident frames of 256 threads with the stored
+    linearisation in shared memory (N <= ~1231) / in the global scratch (<= ~2574), one CTA of 512 threads with the aux arrays
+    in shared memory (<= ~5188) / in the scratch (<= 5819), then the fp64 kernel; odd sizes exercise the 16-byte alignment of
+    the scratch slices and of the prepared frames."""
+    g, ctx = gpu
+    mean, cov = synth.make_map(3000, 0.7, seed=17)
+    fr = synth.make_frames(mean, cov, 2, N, seed=N, mono_frac=0.15)
+    with _gn(g, ctx, g.capi.GN_WORLD):
+        _check_frames(g, ctx, oracle, mean, cov, fr, robust=1)
+
+
+@pytest.mark.parametrize("case", ["c2", "c5_style", "shipped"])
+def test_world_frame_kernel_agrees_with_the_other_kernels(gpu, golden_maps, gt_v1_03, case):
+    """Three implementations of the same iteration (fp64 camera frame, mixed camera frame, mixed world frame) on a batch larger
+    than the resident grid: same status / assignments, poses within 1e-6 rad / 1e-5 m of the fp64 kernel on contracting frames."""
+    g, ctx = gpu
+    if case == "c2":
+        mean, cov = synth.make_map(10000, 0.5)
+        fr, kw = synth.make_frames(mean, cov, 700, 2000, seed=23), {}
+    elif case == "c5_style":
+        mean, cov = synth.make_map(8000, 0.95, seed=4)
+        fr, kw = synth.make_frames(mean, cov, 320, 1500, seed=24, mono_frac=0.3), dict(robust=1)
+    else:
+        gm = golden_maps["v1"]
+        mean, cov = gm["mean"], gm["cov"]
+        fr, kw = synth.make_frames(mean, cov, 640, 1200, seed=25, poses_wc=gt_v1_03[np.arange(640) * 3, 1:8]), {}
+    m = g.GMM(mean, cov)
+    outs = {}
+    for name, prec in (("fp64", g.capi.GN_FP64), ("mixed", g.capi.GN_MIXED), ("world", g.capi.GN_WORLD)):
+        with _gn(g, ctx, prec):
+            outs[name] = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=g.default_params(**kw))
+    ok = outs["fp64"]["status"] == 0
+    for name in ("mixed", "world"):
+        assert np.array_equal(outs[name]["assign"], outs["fp64"]["assign"])
+        # a frame whose iteration diverges may end non-finite in one arithmetic and merely huge in another: rare, and not comparable
+        same = outs[name]["status"] == outs["fp64"]["status"]
+        assert same.mean() > 0.98, (name, float(same.mean()))
+        ok &= same
+    ang = np.array([_pose_err(outs["world"]["pose"][f], outs["fp64"]["pose"][f]) for f in range(len(ok))])
+    angm = np.array([_pose_err(outs["mixed"]["pose"][f], outs["fp64"]["pose"][f]) for f in range(len(ok))])
+    good = ok & (angm[:, 0] < 1e-6) & (angm[:, 1] < 1e-5)  # frames on which the iteration is not chaotic (K3m agrees with fp64)
+    assert good.mean() > 0.9
+    assert ang[good, 0].max() < 1e-6 and ang[good, 1].max() < 1e-5, (ang[good].max(axis=0))
+    print(f"world vs fp64 ({case}): {ang[good, 0].max():.2e} rad {ang[good, 1].max():.2e} m on {int(good.sum())} / {len(ok)} frames")
