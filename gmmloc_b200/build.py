@@ -33,6 +33,7 @@ SOURCES = {
     "frame_gn.cu": [],
     "frame_gn_mixed.cu": [],
     "frame_gn_world.cu": [],
+    "frame_gn_stream.cu": [],
     "pose_lm.cu": [],
     "local_ba.cu": [],
     "point_gn.cu": ["-fmad=false"],

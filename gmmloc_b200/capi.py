@@ -19,7 +19,7 @@ MODE_JOINT, MODE_POSE_ONLY, MODE_POINTS_ONLY = 0, 1, 2
 FRAME_NUMERIC = 1
 VIEW_OVERFLOW = 1
 ASSOC_AUTO, ASSOC_FFMA2, ASSOC_TENSOR, ASSOC_GRID = 0, 1, 2, 3
-GN_FP64, GN_MIXED, GN_WORLD = 0, 1, 2
+GN_FP64, GN_MIXED, GN_WORLD, GN_STREAM = 0, 1, 2, 3
 GN_DEFAULT = GN_MIXED  # what a new context runs (gmmloc_ctx_create)
 OPT_GN_PREP, OPT_E2E_CHUNK, OPT_E2E_SHORT_FIRST, OPT_BA_CLUSTER = 0, 1, 2, 3
 

@@ -683,7 +683,8 @@ gmmloc_status_t gmmloc_ctx_set_assoc_kernel(gmmloc_ctx_t* ctx, int kind) {
 int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx) { return ctx ? ctx->last_assoc_tc : 0; }
 
 gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int precision) {
-  if (!ctx || (precision != GMMLOC_GN_FP64 && precision != GMMLOC_GN_MIXED && precision != GMMLOC_GN_WORLD))
+  if (!ctx || (precision != GMMLOC_GN_FP64 && precision != GMMLOC_GN_MIXED && precision != GMMLOC_GN_WORLD &&
+               precision != GMMLOC_GN_STREAM))
     return fail(GMMLOC_EINVAL, "gmmloc_ctx_set_gn_precision: bad argument");
   ctx->gn_precision = precision;
   return GMMLOC_OK;
@@ -840,10 +841,18 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
     if (std::strcmp(v, "fp64") == 0) return (int)GMMLOC_GN_FP64;
     if (std::strcmp(v, "mixed") == 0) return (int)GMMLOC_GN_MIXED;
     if (std::strcmp(v, "world") == 0) return (int)GMMLOC_GN_WORLD;
+    if (std::strcmp(v, "stream") == 0) return (int)GMMLOC_GN_STREAM;
     return -1;
   }();
   const int gn_prec = gn_forced >= 0 ? gn_forced : ctx->gn_precision;
-  if (gn_prec == GMMLOC_GN_WORLD && map->d.gn_tab != nullptr && N > 0 && (size_t)N <= frame_gn_world_limit_points()) {
+  if (gn_prec == GMMLOC_GN_STREAM && map->d.gn_tab != nullptr && N > 0 && (size_t)N <= frame_gn_stream_limit_points()) {
+    CU(ctx->L().next_frame.reserve(sizeof(int)));
+    CU(ctx->L().gn_store.reserve(frame_gn_stream_scratch_bytes(N)));
+    CU(ctx->L().gn_prep.reserve(frame_gn_stream_prep_bytes(B, N)));
+    CU(launch_frame_gn_stream(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().gn_store.as<float>(), ctx->L().gn_store.cap,
+                              ctx->L().gn_prep.as<unsigned char>(), ctx->L().gn_prep.cap, ctx->L().stream));
+    ctx->stats.kernel_launches += 1;
+  } else if (gn_prec == GMMLOC_GN_WORLD && map->d.gn_tab != nullptr && N > 0 && (size_t)N <= frame_gn_world_limit_points()) {
     CU(ctx->L().next_frame.reserve(sizeof(int)));
     CU(ctx->L().gn_store.reserve(frame_gn_world_scratch_bytes(N)));
     CU(ctx->L().gn_prep.reserve(frame_gn_world_prep_bytes(B, N)));
@@ -936,8 +945,11 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     CU(ln.flag_idx.reserve(sizeof(int32_t) * 2 * mc));
     CU(ln.flag_thr.reserve(sizeof(float) * 2 * mc));
     CU(ln.next_frame.reserve(sizeof(int)));
-    CU(ln.gn_store.reserve(std::max(frame_gn_mixed_scratch_bytes(N), frame_gn_world_scratch_bytes(N))));
+    CU(ln.gn_store.reserve(std::max(std::max(frame_gn_mixed_scratch_bytes(N), frame_gn_world_scratch_bytes(N)),
+                                    frame_gn_stream_scratch_bytes(N))));
     if (ctx->gn_precision == GMMLOC_GN_WORLD) CU(ln.gn_prep.reserve(frame_gn_world_prep_bytes(maxc, N)));
+    if (ctx->gn_precision == GMMLOC_GN_STREAM && (size_t)N <= frame_gn_stream_limit_points())
+      CU(ln.gn_prep.reserve(frame_gn_stream_prep_bytes(maxc, N)));
     if (frame_gn_mixed_prep_bytes(maxc, N, ctx->opt_gn_prep)) CU(ln.gn_prep.reserve(frame_gn_mixed_prep_bytes(maxc, N, ctx->opt_gn_prep)));
     if (map->d.grid.nlev > 0) {
       const GridLevel& G0 = map->d.grid.lev[0];

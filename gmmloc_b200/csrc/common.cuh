@@ -159,6 +159,13 @@ cudaError_t launch_frame_gn_world(const FrameArgs& a, const float* gn_tab, int* 
 size_t frame_gn_world_scratch_bytes(int N);
 size_t frame_gn_world_prep_bytes(int B, int N);
 size_t frame_gn_world_limit_points();
+// streamed twin (frame_gn_stream.cu, K3q + K3s): frames packed by frame_pack_kernel (prep_ws: frame_gn_stream_prep_bytes(B, N)
+// bytes), every per-sweep operand staged through shared memory by TMA bulk copies (store_ws: frame_gn_stream_scratch_bytes(N))
+cudaError_t launch_frame_gn_stream(const FrameArgs& a, const float* gn_tab, int* d_next_frame, float* store_ws, size_t store_ws_bytes,
+                                   unsigned char* prep_ws, size_t prep_ws_bytes, cudaStream_t stream);
+size_t frame_gn_stream_scratch_bytes(int N);
+size_t frame_gn_stream_prep_bytes(int B, int N);
+size_t frame_gn_stream_limit_points();
 size_t frame_gn_mixed_limit_points();  // largest N the mixed kernel takes (class-sorted frame state in shared memory)
 size_t frame_gn_smem_limit_points();  // largest N whose per-frame state stays in shared memory
 

@@ -283,7 +283,13 @@ GNW_HD bool lin_str(const Cam& C, const Lin& L, const float* Rf, bool stereo, fl
 // Sherman-Morrison.  With pe = J^-1 e (the correction the stereo edge alone asks for), z = G^-1 n, kappa = lam/(1 + lam n.z):
 //   u0 = u - kappa z (n.u),  u = pe - lam e_s z;   W = I - kappa z n^T;   M = kappa n n^T,  v = kappa (e_s + n.pe) n
 // n: plane normal (world), es = n.(x - mu) (from the fp64 offset).  kappa / rho are returned for the rank-one accumulation.
-GNW_HD bool lin_strp(const Cam& C, const Lin& L, const float* Rf, float w, const V3f& n, float es, PointLin& out, float& kappa, float& rho) {
+// compact result of the two planar classes: W = I - kz n^T (n: the plane normal, known from the map), so that the step is
+// dx = u0 - a + kz (n . a)
+struct PlaneLin {
+  V3f u0, kz;
+};
+GNW_HD bool lin_strp_c(const Cam& C, const Lin& L, const float* Rf, float w, const V3f& n, float es, PlaneLin& out, float& kappa,
+                       float& rho) {
   const Proj P = proj_jac(C, L);
   w = huber(C, L, true, w);
   const float ia = rcpf(P.a), ib = rcpf(P.b), icz = rcpf(P.cz);
@@ -308,18 +314,27 @@ GNW_HD bool lin_strp(const Cam& C, const Lin& L, const float* Rf, float w, const
   const V3f u = {pw.x - le * zw.x, pw.y - le * zw.y, pw.z - le * zw.z};
   const float nu = kappa * dotf(n, u);
   out.u0 = {u.x - nu * zw.x, u.y - nu * zw.y, u.z - nu * zw.z};
-  const V3f kz = {kappa * zw.x, kappa * zw.y, kappa * zw.z};
-  out.w0 = 1.f - kz.x * n.x; out.w1 = -kz.x * n.y; out.w2 = -kz.x * n.z;
-  out.w3 = -kz.y * n.x; out.w4 = 1.f - kz.y * n.y; out.w5 = -kz.y * n.z;
-  out.w6 = -kz.z * n.x; out.w7 = -kz.z * n.y; out.w8 = 1.f - kz.z * n.z;
+  out.kz = {kappa * zw.x, kappa * zw.y, kappa * zw.z};
   rho = kappa * (es + dotf(n, pw));
   return isfinite(kappa);
+}
+GNW_HD void expand_plane(const PlaneLin& c, const V3f& n, PointLin& out) {
+  out.u0 = c.u0;
+  out.w0 = 1.f - c.kz.x * n.x; out.w1 = -c.kz.x * n.y; out.w2 = -c.kz.x * n.z;
+  out.w3 = -c.kz.y * n.x; out.w4 = 1.f - c.kz.y * n.y; out.w5 = -c.kz.y * n.z;
+  out.w6 = -c.kz.z * n.x; out.w7 = -c.kz.z * n.y; out.w8 = 1.f - c.kz.z * n.z;
+}
+GNW_HD bool lin_strp(const Cam& C, const Lin& L, const float* Rf, float w, const V3f& n, float es, PointLin& out, float& kappa, float& rho) {
+  PlaneLin c;
+  const bool ok = lin_strp_c(C, L, Rf, w, n, es, c, kappa, rho);
+  expand_plane(c, n, out);
+  return ok;
 }
 
 // ---- class MPLANE: free MONOCULAR point on a planar component.  Rows u, v of P and the plane normal form a square system
 //   Q dc = [e - P_uv A dxi ; -e_s],  Q = [P_uv ; nc^T]   =>   dc = u0_c - W_c (A dxi),  W_c = I - q3 nc^T  (q3 = Q^-1 e_3)
 // (= D^-1 (h + s - G A dxi) of the general path; weights and the Huber factor cancel row by row); zero Schur contribution.
-GNW_HD bool lin_mplane(const Cam& C, const Lin& L, const float* Rf, const V3f& n, float es, PointLin& out) {
+GNW_HD bool lin_mplane_c(const Cam& C, const Lin& L, const float* Rf, const V3f& n, float es, PlaneLin& out) {
   const Proj P = proj_jac(C, L);
   const V3f nc = rot(Rf, n);
   const float ia = rcpf(P.a), ib = rcpf(P.b);
@@ -331,11 +346,14 @@ GNW_HD bool lin_mplane(const Cam& C, const Lin& L, const float* Rf, const V3f& n
   // q3 = Q^-1 [0, 0, 1]
   const V3f q3 = {-P.c0 * iden * ia, -P.c1 * iden * ib, iden};
   out.u0 = rot_t(Rf, u0c);
-  const V3f qw = rot_t(Rf, q3);
-  out.w0 = 1.f - qw.x * n.x; out.w1 = -qw.x * n.y; out.w2 = -qw.x * n.z;
-  out.w3 = -qw.y * n.x; out.w4 = 1.f - qw.y * n.y; out.w5 = -qw.y * n.z;
-  out.w6 = -qw.z * n.x; out.w7 = -qw.z * n.y; out.w8 = 1.f - qw.z * n.z;
+  out.kz = rot_t(Rf, q3);
   return finite3(out.u0) && isfinite(iden);
+}
+GNW_HD bool lin_mplane(const Cam& C, const Lin& L, const float* Rf, const V3f& n, float es, PointLin& out) {
+  PlaneLin c;
+  const bool ok = lin_mplane_c(C, L, Rf, n, es, c);
+  expand_plane(c, n, out);
+  return ok;
 }
 
 // ---- class FIXED: a held point contributes G, h of its reprojection edge to the pose system ----
@@ -352,6 +370,12 @@ GNW_HD V3f twist_at(const V3f& om, const V3f& up, const V3f& xr) {
 GNW_HD V3f point_step(const V3f& u0, const float* W, const V3f& a) {
   return {u0.x - (W[0] * a.x + W[1] * a.y + W[2] * a.z), u0.y - (W[3] * a.x + W[4] * a.y + W[5] * a.z),
           u0.z - (W[6] * a.x + W[7] * a.y + W[8] * a.z)};
+}
+
+// planar classes: dx = u0 - (I - kz n^T) a
+GNW_HD V3f plane_step(const V3f& u0, const V3f& kz, const V3f& n, const V3f& a) {
+  const float na = dotf(n, a);
+  return {u0.x - a.x + kz.x * na, u0.y - a.y + kz.y * na, u0.z - a.z + kz.z * na};
 }
 
 // camera-frame Schur terms (pc, M_c, v_c) of the fp64 per-point path -> world-twist coordinates: M_w = R^T M_c R, v_w = R^T v_c

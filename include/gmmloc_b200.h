@@ -183,8 +183,10 @@ GMMLOC_API int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx);
  *                              in fp32 — same fixed point (poses agree with the fp64 solve to ~1e-9), ~3x faster;
  *   GMMLOC_GN_WORLD            the same precision split with the per-point blocks written in the world frame (the
  *                              structure edge needs no rotation, the point step no pose; 16 instead of 12 warps per SM);
- *   GMMLOC_GN_FP64             everything in fp64. */
-enum { GMMLOC_GN_FP64 = 0, GMMLOC_GN_MIXED = 1, GMMLOC_GN_WORLD = 2 };
+ *   GMMLOC_GN_FP64             everything in fp64;
+ *   GMMLOC_GN_STREAM           the world-frame kernel with every per-sweep operand (component constants resolved once per
+ *                              frame, stored linearisation) staged through shared memory by TMA bulk copies; */
+enum { GMMLOC_GN_FP64 = 0, GMMLOC_GN_MIXED = 1, GMMLOC_GN_WORLD = 2, GMMLOC_GN_STREAM = 3 };
 GMMLOC_API gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int precision);
 
 /* Tuning switches of a context for A/B measurements; every setting returns identical results.  (Environment variables
