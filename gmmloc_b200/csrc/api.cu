@@ -811,6 +811,7 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
   }
   FrameArgs a;
   a.mean = map->d.mean;
+  a.cov = map->d.cov;
   a.cov_inv = map->d.cov_inv;
   a.axis = map->d.axis;
   a.is_deg = map->d.is_deg;
@@ -846,12 +847,12 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
   }();
   const int gn_prec = gn_forced >= 0 ? gn_forced : ctx->gn_precision;
   if (gn_prec == GMMLOC_GN_STREAM && map->d.gn_tab != nullptr && N > 0 && (size_t)N <= frame_gn_stream_limit_points()) {
-    CU(ctx->L().next_frame.reserve(sizeof(int)));
+    CU(ctx->L().next_frame.reserve(sizeof(int) * ((size_t)B + 2)));
     CU(ctx->L().gn_store.reserve(frame_gn_stream_scratch_bytes(N)));
     CU(ctx->L().gn_prep.reserve(frame_gn_stream_prep_bytes(B, N)));
     CU(launch_frame_gn_stream(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().gn_store.as<float>(), ctx->L().gn_store.cap,
                               ctx->L().gn_prep.as<unsigned char>(), ctx->L().gn_prep.cap, ctx->L().stream));
-    ctx->stats.kernel_launches += 1;
+    ctx->stats.kernel_launches += 2;  // + the pack kernel and the (normally empty) fp64 retry launch
   } else if (gn_prec == GMMLOC_GN_WORLD && map->d.gn_tab != nullptr && N > 0 && (size_t)N <= frame_gn_world_limit_points()) {
     CU(ctx->L().next_frame.reserve(sizeof(int)));
     CU(ctx->L().gn_store.reserve(frame_gn_world_scratch_bytes(N)));
@@ -944,7 +945,7 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     const size_t mc = (size_t)maxc * N;
     CU(ln.flag_idx.reserve(sizeof(int32_t) * 2 * mc));
     CU(ln.flag_thr.reserve(sizeof(float) * 2 * mc));
-    CU(ln.next_frame.reserve(sizeof(int)));
+    CU(ln.next_frame.reserve(sizeof(int) * (maxc + 2)));
     CU(ln.gn_store.reserve(std::max(std::max(frame_gn_mixed_scratch_bytes(N), frame_gn_world_scratch_bytes(N)),
                                     frame_gn_stream_scratch_bytes(N))));
     if (ctx->gn_precision == GMMLOC_GN_WORLD) CU(ln.gn_prep.reserve(frame_gn_world_prep_bytes(maxc, N)));

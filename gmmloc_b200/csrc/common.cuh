@@ -124,6 +124,7 @@ cudaError_t launch_associate(const MapDev& m, const float* d_pts, long long M, d
                                                                                           // cells(level 0) + 1 ints, M x 16 bytes
 struct FrameArgs {
   const double* mean;       // map constants (fp64)
+  const double* cov;
   const double* cov_inv;
   const double* axis;
   const uint8_t* is_deg;
@@ -140,6 +141,9 @@ struct FrameArgs {
   int32_t* status;          // B
   double* xws;              // B x N x 3 fp64 workspace when a frame does not fit in shared memory, else null
   uint8_t* fws;             // B x N flag workspace (same condition)
+  // frame_gn_kernel only: solve the frames retry_list[0 .. *retry_count) instead of all B (CTAs beyond the count return)
+  const int* retry_count = nullptr;
+  const int* retry_list = nullptr;
 };
 cudaError_t launch_frame_gn(const FrameArgs& a, cudaStream_t stream);
 // mixed-precision twin (frame_gn_mixed.cu): fp64 state / residuals, fp32 Jacobian algebra; persistent CTAs fetch frames

@@ -53,7 +53,11 @@ __global__ void __launch_bounds__(kThreads, GMMLOC_GN_MINB) frame_gn_kernel(cons
   __shared__ double s_pose[7], s_R[9], s_dxi[6], s_Ro[9], s_to[3];
   __shared__ int s_fail1, s_fail2;
 
-  const int f = blockIdx.x;
+  int f = blockIdx.x;
+  if (a.retry_list != nullptr) {  // second opinion on the frames a mixed-precision kernel gave up on (frame_gn_stream.cu)
+    if (f >= *a.retry_count) return;
+    f = a.retry_list[f];
+  }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
   const FrameParamsDev& P = a.prm;

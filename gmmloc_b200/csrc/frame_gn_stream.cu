@@ -312,10 +312,18 @@ __global__ void __launch_bounds__(kPackThreads) frame_pack_kernel(const FrameArg
             const float es0 = (float)(((double)t0.x * d0 + (double)t0.y * d1) + (double)t0.z * d2);
             reinterpret_cast<float4*>(cp)[l] = make_float4(t0.x, t0.y, t0.z, es0);
           } else {
-            const float2 t1 = __ldg(reinterpret_cast<const float2*>(gn_tab) + 4 * (size_t)k + 2);
-            reinterpret_cast<float4*>(cp)[l] = make_float4((float)d0, (float)d1, (float)d2, t0.x);
-            reinterpret_cast<float4*>(cp)[32 + l] = make_float4(t0.y, t0.z, t0.w, t1.x);
-            reinterpret_cast<float*>(cp + 1024)[l] = t1.y;
+            // six unique entries of Sigma^-1 (C_STR) or — gain form of the monocular block, frame_gn_world.cuh — of Sigma (C_MSTR)
+            float m0, m1, m2, m3, m4, m5;
+            if (cls == C_STR) {
+              const float2 t1 = __ldg(reinterpret_cast<const float2*>(gn_tab) + 4 * (size_t)k + 2);
+              m0 = t0.x; m1 = t0.y; m2 = t0.z; m3 = t0.w; m4 = t1.x; m5 = t1.y;
+            } else {
+              const double* cv = a.cov + (size_t)k * 9;
+              m0 = (float)cv[0]; m1 = (float)cv[1]; m2 = (float)cv[2]; m3 = (float)cv[4]; m4 = (float)cv[5]; m5 = (float)cv[8];
+            }
+            reinterpret_cast<float4*>(cp)[l] = make_float4((float)d0, (float)d1, (float)d2, m0);
+            reinterpret_cast<float4*>(cp)[32 + l] = make_float4(m1, m2, m3, m4);
+            reinterpret_cast<float*>(cp + 1024)[l] = m5;
           }
         }
       }
@@ -607,7 +615,10 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
             PointLin pl;
             S3f M;
             V3f v;
-            if (!gnw::lin_str(C, Ln, Rl, stereo, w, Sw, d, pl, do_acc, M, v)) bad |= 1;
+            // C_STR: Sw = Sigma^-1, general block;  C_MSTR: Sw = Sigma, gain form (frame_gn_world.cuh)
+            const bool ok32 = CLS == C_STR ? gnw::lin_str(C, Ln, Rl, true, w, Sw, d, pl, do_acc, M, v)
+                                           : gnw::lin_mstr_gain(C, Ln, Rl, w, Sw, d, pl, M, v);
+            if (!ok32) bad |= 1;
             if (do_acc) gnw::accumulate_pose(acc, xr, M, v);
             __stcg(reinterpret_cast<float4*>(gs) + lane, make_float4(pl.u0.x, pl.u0.y, pl.u0.z, pl.w0));
             __stcg(reinterpret_cast<float4*>(gs) + 32 + lane, make_float4(pl.w1, pl.w2, pl.w3, pl.w4));
@@ -749,7 +760,12 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
     }
     __syncthreads();
     if (tid < 7) a.pose_out[(size_t)f * 7 + tid] = s_pose[tid];
-    if (tid == 0) a.status[f] = fail ? GMMLOC_FRAME_NUMERIC : 0;
+    if (tid == 0) {
+      a.status[f] = fail ? GMMLOC_FRAME_NUMERIC : 0;
+      // a frame the fp32 blocks could not carry (a landmark at the camera plane or at infinity in an iteration that does not
+      // contract ...) is solved again, from its inputs, by the all-fp64 kernel after this launch: ITS verdict is the status
+      if (fail) counters[2 + atomicAdd(counters + 1, 1)] = f;
+    }
     {
       // outputs in the ORIGINAL point order; outlier post-check at the final estimate in fp64:
       // chi2 > 5.991 / 7.815 or non-positive depth (localization_opt.cpp:857-881)
@@ -824,9 +840,14 @@ cudaError_t launch_stream_t(const FrameArgs& a, int* d_counters, unsigned char* 
     return cudaSuccess;
   }
   *fits = true;
-  if ((e = cudaMemsetAsync(d_counters, 0, sizeof(int), stream)) != cudaSuccess) return e;
+  if ((e = cudaMemsetAsync(d_counters, 0, 2 * sizeof(int), stream)) != cudaSuccess) return e;
   frame_gn_stream_kernel<kThreads, kMinB><<<grid, kThreads, smem, stream>>>(a, d_counters, store_ws, pack);
-  return cudaGetLastError();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  // the frames the kernel gave up on (normally none: the CTAs of this launch return at once), re-solved in fp64
+  FrameArgs r = a;
+  r.retry_count = d_counters + 1;
+  r.retry_list = d_counters + 2;
+  return launch_frame_gn(r, stream);
 }
 
 }  // namespace
@@ -847,6 +868,7 @@ size_t frame_gn_stream_scratch_bytes(int N) {
 
 size_t frame_gn_stream_prep_bytes(int B, int N) { return (size_t)B * pack_layout(N).stride + 16; }
 
+// d_counters: a.B + 2 ints (frame counter, number of frames handed to the fp64 kernel, their indices)
 cudaError_t launch_frame_gn_stream(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
                                    unsigned char* prep_ws, size_t prep_ws_bytes, cudaStream_t stream) {
   if (a.B <= 0) return cudaSuccess;

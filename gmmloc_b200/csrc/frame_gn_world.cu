@@ -212,14 +212,14 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_world_kernel(const F
         soct[j] = goct[j];
         const uint8_t b = gfl[j];
         fl[j] = b;
-        n64 += (b >> 4) == C_F64;
+        n64 += (b >> 4) >= C_MSTR;  // monocular + full Gaussian: fp64 path as in K3m (ill-conditioned in fp32 near the camera)
       }
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) n64 += __shfl_xor_sync(0xffffffffu, n64, off);
       if (lane == 0 && n64) atomicAdd(&s_n64, n64);
     }
     __syncthreads();
-    // C_F64 is the last class of the sorted frame: its points sit at [f64_begin, N).  They take the fp64 per-point path
+    // C_MSTR and C_F64 are the last classes of the sorted frame: their points sit at [f64_begin, N).  They take the fp64 per-point path
     // (~8x the cost of a structured fp32 point), so they are dealt to the warps round robin — a warp that owned a whole
     // chunk of them kept the other seven waiting at the sweep barrier (21 % of the stall samples, profiles/frame_gn_world_r02.txt)
     const int n64 = s_n64, f64_begin = N - n64;

@@ -278,6 +278,105 @@ GNW_HD bool lin_str(const Cam& C, const Lin& L, const float* Rf, bool stereo, fl
   return ok;
 }
 
+// ---- class MSTR in GAIN form (K3s): free MONOCULAR point with a full 3-D Gaussian edge.  G = w J^T J has rank 2 (J: rows u, v
+// of P R), so D = G + S takes its third direction from the component alone: for a landmark within half a metre of the
+// camera (every "monocular" point of the synthetic C2 frames is one: u_r < 0 <=> z < bf / u) G ~ w (f / z)^2 exceeds S by
+// more than fp32 carries and the cofactor inverse of D returns noise in that direction (measured: pose gradients wrong by
+// 1e3 x, the frame diverges — K3m keeps the class on the fp64 path for this reason).  The same block by the matrix inversion
+// lemma needs the component's COVARIANCE Sig = S^-1 instead and only a 2 x 2 inverse of well-scaled positive terms:
+//      C = J Sig J^T + I / w,   K = Sig J^T C^-1,   y = e + J d
+//      u0 = K y - d,   W = K J,   M = J^T C^-1 J  (positive semidefinite by construction),   v = J^T C^-1 y
+// (u0 = D^-1 (h - S d), W = D^-1 G, M = G - G D^-1 G, v = h - G u0 of the general path, identically.)
+GNW_HD bool lin_mstr_gain(const Cam& C, const Lin& L, const float* Rf, float w, const S3f& Sig, const V3f& d, PointLin& out, S3f& M,
+                          V3f& v) {
+  const Proj P = proj_jac(C, L);
+  const float iw = rcpf(huber(C, L, false, w));
+  const V3f r0 = {P.a * Rf[0] + P.c0 * Rf[6], P.a * Rf[1] + P.c0 * Rf[7], P.a * Rf[2] + P.c0 * Rf[8]};
+  const V3f r1 = {P.b * Rf[3] + P.c1 * Rf[6], P.b * Rf[4] + P.c1 * Rf[7], P.b * Rf[5] + P.c1 * Rf[8]};
+  const V3f s0 = mulf(Sig, r0), s1 = mulf(Sig, r1);
+  const float c00 = dotf(r0, s0) + iw, c01 = dotf(r0, s1), c11 = dotf(r1, s1) + iw;
+  const float det = c00 * c11 - c01 * c01;
+  const float idet = rcpf(det);
+  const float i00 = c11 * idet, i01 = -c01 * idet, i11 = c00 * idet;
+  const V3f k0 = {s0.x * i00 + s1.x * i01, s0.y * i00 + s1.y * i01, s0.z * i00 + s1.z * i01};
+  const V3f k1 = {s0.x * i01 + s1.x * i11, s0.y * i01 + s1.y * i11, s0.z * i01 + s1.z * i11};
+  const float y0 = L.e.x + dotf(r0, d), y1 = L.e.y + dotf(r1, d);
+  out.u0 = {k0.x * y0 + k1.x * y1 - d.x, k0.y * y0 + k1.y * y1 - d.y, k0.z * y0 + k1.z * y1 - d.z};
+  out.w0 = k0.x * r0.x + k1.x * r1.x; out.w1 = k0.x * r0.y + k1.x * r1.y; out.w2 = k0.x * r0.z + k1.x * r1.z;
+  out.w3 = k0.y * r0.x + k1.y * r1.x; out.w4 = k0.y * r0.y + k1.y * r1.y; out.w5 = k0.y * r0.z + k1.y * r1.z;
+  out.w6 = k0.z * r0.x + k1.z * r1.x; out.w7 = k0.z * r0.y + k1.z * r1.y; out.w8 = k0.z * r0.z + k1.z * r1.z;
+  // M = J^T C^-1 J, v = J^T C^-1 y
+  const V3f q0 = {i00 * r0.x + i01 * r1.x, i00 * r0.y + i01 * r1.y, i00 * r0.z + i01 * r1.z};  // row 0 of C^-1 J
+  const V3f q1 = {i01 * r0.x + i11 * r1.x, i01 * r0.y + i11 * r1.y, i01 * r0.z + i11 * r1.z};
+  M.xx = r0.x * q0.x + r1.x * q1.x;
+  M.xy = r0.x * q0.y + r1.x * q1.y;
+  M.xz = r0.x * q0.z + r1.x * q1.z;
+  M.yy = r0.y * q0.y + r1.y * q1.y;
+  M.yz = r0.y * q0.z + r1.y * q1.z;
+  M.zz = r0.z * q0.z + r1.z * q1.z;
+  v = {q0.x * y0 + q1.x * y1, q0.y * y0 + q1.y * y1, q0.z * y0 + q1.z * y1};
+  return (det > 0.0f) && isfinite(idet) && finite3(out.u0);
+}
+
+// ---- fp64 evaluation of one free point block in the world frame (any class): the fall-back of K3s when an fp32 block
+// reports a singular / non-finite result (a landmark that wandered to the camera plane or to infinity in a frame whose
+// iteration does not contract).  S: six unique entries of the structure Hessian (cov_inv, or lam n n^T), bs: its right-hand
+// side (-S d, or -lam es n); zero without structure edge.  Same outputs as lin_str.
+GNW_HD bool lin_general64(const Cam& C, const double* R, const double* t, double x0, double x1, double x2, const float* ob, bool stereo,
+                          double w, const double* S, const double* bs, PointLin& out, S3f& Mo, V3f& vo) {
+  const double pc[3] = {R[0] * x0 + R[1] * x1 + R[2] * x2 + t[0], R[3] * x0 + R[4] * x1 + R[5] * x2 + t[1],
+                        R[6] * x0 + R[7] * x1 + R[8] * x2 + t[2]};
+  const double iz = 1.0 / pc[2];
+  const double a = C.fx * iz, b = C.fy * iz, c0 = -a * pc[0] * iz, c1 = -b * pc[1] * iz, cz = C.bf * iz * iz;
+  const double u = pc[0] * a + C.cx, vv = pc[1] * b + C.cy;
+  const double e[3] = {(double)ob[0] - u, (double)ob[1] - vv, stereo ? (double)ob[2] - (u - C.bf * iz) : 0.0};
+  if (C.robust) {
+    const double chi = w * (e[0] * e[0] + e[1] * e[1] + e[2] * e[2]);
+    const double dl = stereo ? (double)C.d_stereo : (double)C.d_mono;
+    if (chi > dl * dl) w *= dl / sqrt(chi);
+  }
+  double J[9];
+  for (int c = 0; c < 3; ++c) {
+    J[c] = a * R[c] + c0 * R[6 + c];
+    J[3 + c] = b * R[3 + c] + c1 * R[6 + c];
+    J[6 + c] = stereo ? J[c] + cz * R[6 + c] : 0.0;
+  }
+  double G[9], h[3];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) G[i * 3 + j] = w * (J[i] * J[j] + J[3 + i] * J[3 + j] + J[6 + i] * J[6 + j]);
+    h[i] = w * (J[i] * e[0] + J[3 + i] * e[1] + J[6 + i] * e[2]);
+  }
+  const double Sf[9] = {S[0], S[1], S[2], S[1], S[3], S[4], S[2], S[4], S[5]};
+  double D[9], Di[9];
+  for (int i = 0; i < 9; ++i) D[i] = G[i] + Sf[i];
+  const double det = D[0] * (D[4] * D[8] - D[5] * D[7]) - D[1] * (D[3] * D[8] - D[5] * D[6]) + D[2] * (D[3] * D[7] - D[4] * D[6]);
+  const double id = 1.0 / det;
+  Di[0] = (D[4] * D[8] - D[5] * D[7]) * id; Di[1] = (D[2] * D[7] - D[1] * D[8]) * id; Di[2] = (D[1] * D[5] - D[2] * D[4]) * id;
+  Di[3] = (D[5] * D[6] - D[3] * D[8]) * id; Di[4] = (D[0] * D[8] - D[2] * D[6]) * id; Di[5] = (D[2] * D[3] - D[0] * D[5]) * id;
+  Di[6] = (D[3] * D[7] - D[4] * D[6]) * id; Di[7] = (D[1] * D[6] - D[0] * D[7]) * id; Di[8] = (D[0] * D[4] - D[1] * D[3]) * id;
+  const double bl[3] = {h[0] + bs[0], h[1] + bs[1], h[2] + bs[2]};
+  double u0[3], W[9];
+  for (int i = 0; i < 3; ++i) {
+    u0[i] = Di[i * 3] * bl[0] + Di[i * 3 + 1] * bl[1] + Di[i * 3 + 2] * bl[2];
+    for (int j = 0; j < 3; ++j) W[i * 3 + j] = Di[i * 3] * G[j] + Di[i * 3 + 1] * G[3 + j] + Di[i * 3 + 2] * G[6 + j];
+  }
+  double Mf[9], vf[3];
+  for (int i = 0; i < 3; ++i) {
+    vf[i] = h[i] - (G[i * 3] * u0[0] + G[i * 3 + 1] * u0[1] + G[i * 3 + 2] * u0[2]);
+    for (int j = 0; j < 3; ++j) Mf[i * 3 + j] = W[i] * Sf[j] + W[3 + i] * Sf[3 + j] + W[6 + i] * Sf[6 + j];
+  }
+  out.u0 = {(float)u0[0], (float)u0[1], (float)u0[2]};
+  out.w0 = (float)W[0]; out.w1 = (float)W[1]; out.w2 = (float)W[2];
+  out.w3 = (float)W[3]; out.w4 = (float)W[4]; out.w5 = (float)W[5];
+  out.w6 = (float)W[6]; out.w7 = (float)W[7]; out.w8 = (float)W[8];
+  Mo = {(float)Mf[0], (float)Mf[1], (float)Mf[2], (float)Mf[4], (float)Mf[5], (float)Mf[8]};
+  vo = {(float)vf[0], (float)vf[1], (float)vf[2]};
+  bool ok = (det != 0.0) && isfinite(id) && finite3(out.u0) && finite3(vo);
+  ok = ok && isfinite(out.w0 + out.w1 + out.w2 + out.w3 + out.w4 + out.w5 + out.w6 + out.w7 + out.w8) &&
+       isfinite(Mo.xx + Mo.xy + Mo.xz + Mo.yy + Mo.yz + Mo.zz);
+  return ok;
+}
+
 // ---- class STRP: free stereo point on a planar component (EdgePt2GaussianDeg: e_s = n.(x - mu), information lam) ----
 // The stereo edge alone determines the point (P square), the plane adds one scalar equation: D = G + lam n n^T by
 // Sherman-Morrison.  With pe = J^-1 e (the correction the stereo edge alone asks for), z = G^-1 n, kappa = lam/(1 + lam n.z):

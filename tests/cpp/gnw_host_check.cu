@@ -8,6 +8,13 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#ifdef GNW_DEBUG
+#include <cstdio>
+#include <cstdlib>
+#define GNW_TRACE(...) std::fprintf(stderr, __VA_ARGS__)
+#else
+#define GNW_TRACE(...) ((void)0)
+#endif
 
 #include "../../gmmloc_b200/csrc/common.cuh"
 #include "../../gmmloc_b200/csrc/gn_common.cuh"
@@ -97,10 +104,21 @@ bool general_fp64(const Cam& C, const double* R, const double* t, const double* 
 }
 }  // namespace
 
+// mode 0: K3w (monocular + full Gaussian on the fp64 path), mode 1: K3s (that class in gain form from the covariance)
+extern "C" int gnw_host_frame_solve_mode(const double* mean, const double* cov, const double* cov_inv, const double* axis,
+                                         const uint8_t* is_deg, const FrameParamsDev* Pp, const double* pose0, const float* pts,
+                                         const float* obs, const uint8_t* octave, const int32_t* assign, int N, double* pose_out,
+                                         double* pts_out, uint8_t* cls_out, int mode);
 extern "C" int gnw_host_frame_solve(const double* mean, const double* cov_inv, const double* axis, const uint8_t* is_deg,
                                     const FrameParamsDev* Pp, const double* pose0, const float* pts, const float* obs,
                                     const uint8_t* octave, const int32_t* assign, int N, double* pose_out, double* pts_out,
                                     uint8_t* cls_out) {
+  return gnw_host_frame_solve_mode(mean, nullptr, cov_inv, axis, is_deg, Pp, pose0, pts, obs, octave, assign, N, pose_out, pts_out, cls_out, 0);
+}
+extern "C" int gnw_host_frame_solve_mode(const double* mean, const double* cov, const double* cov_inv, const double* axis, const uint8_t* is_deg,
+                                    const FrameParamsDev* Pp, const double* pose0, const float* pts, const float* obs,
+                                    const uint8_t* octave, const int32_t* assign, int N, double* pose_out, double* pts_out,
+                                    uint8_t* cls_out, int mode) {
   const FrameParamsDev& P = *Pp;
   const bool pose_free = P.factor_mode != GMMLOC_MODE_POINTS_ONLY, pts_free = P.factor_mode != GMMLOC_MODE_POSE_ONLY;
   Cam C;
@@ -148,8 +166,9 @@ extern "C" int gnw_host_frame_solve(const double* mean, const double* cov_inv, c
       else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_MSTR;
       else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
     }
-    fl[i] = (uint8_t)(b | (cls << 4));
     if (cls_out) cls_out[i] = (uint8_t)cls;
+    if (mode == 0 && cls == C_MSTR) cls = C_F64;  // K3w: fp64 path
+    fl[i] = (uint8_t)(b | (cls << 4));
   }
   std::vector<double> u0d(3 * (size_t)N, 0.0), Wd(9 * (size_t)N, 0.0);  // fp64 stored linearisation of the F64-class points
   float dxw[6] = {0, 0, 0, 0, 0, 0};
@@ -180,7 +199,11 @@ extern "C" int gnw_host_frame_solve(const double* mean, const double* cov_inv, c
         V3f dx;
         if (cls == C_PLAIN) dx = {sp[0] - av.x, sp[1] - av.y, sp[2] - av.z};
         else dx = gnw::point_step({sp[0], sp[1], sp[2]}, sp + 3, av);
-        if (!gnw::finite3(dx)) fail = 1;
+#ifdef GNW_DEBUG
+        if (getenv("GNW_TRACE_POINT") && j == atoi(getenv("GNW_TRACE_POINT")))
+          GNW_TRACE("sweep %d point %d class %d: x %.6f %.6f %.6f dx %g %g %g u0 %g %g %g W %g %g %g / %g %g %g / %g %g %g av %g %g %g\n", sw, j, cls, xp[0], xp[1], xp[2], dx.x, dx.y, dx.z, sp[0], sp[1], sp[2], sp[3], sp[4], sp[5], sp[6], sp[7], sp[8], sp[9], sp[10], sp[11], av.x, av.y, av.z);
+#endif
+        if (!gnw::finite3(dx)) { fail = 1; GNW_TRACE("sweep %d: non-finite step, point %d class %d\n", sw, j, cls); }
         xp[0] += (double)dx.x; xp[1] += (double)dx.y; xp[2] += (double)dx.z;
       }
     }
@@ -229,33 +252,68 @@ extern "C" int gnw_host_frame_solve(const double* mean, const double* cov_inv, c
           const double* mu = mean + 3 * (size_t)k;
           const V3f d = {(float)(xp[0] - mu[0]), (float)(xp[1] - mu[1]), (float)(xp[2] - mu[2])};
           PointLin pl;
-          if (cls == C_STR || cls == C_MSTR) {
+          if (cls == C_MSTR) {
+            const double* Cv = cov + 9 * (size_t)k;
+            const S3f Sig = {(float)Cv[0], (float)Cv[1], (float)Cv[2], (float)Cv[4], (float)Cv[5], (float)Cv[8]};
+            S3f M; V3f v;
+            if (!gnw::lin_mstr_gain(C, L, Rl, w, Sig, d, pl, M, v)) { fail = 1; GNW_TRACE("sweep %d: lin_mstr_gain failed, point %d\n", sw, j); break; }
+            if (do_acc) gnw::accumulate_pose(acc, xr, M, v);
+          } else if (cls == C_STR) {
             const double* A = cov_inv + 9 * (size_t)k;
             const S3f Sw = {(float)A[0], (float)A[1], (float)A[2], (float)A[4], (float)A[5], (float)A[8]};
             S3f M; V3f v;
-            if (!gnw::lin_str(C, L, Rl, stereo, w, Sw, d, pl, do_acc, M, v)) { fail = 1; break; }
+            if (!gnw::lin_str(C, L, Rl, stereo, w, Sw, d, pl, do_acc, M, v)) { fail = 1; GNW_TRACE("sweep %d: lin_str failed, point %d class %d pc %g %g %g e %g %g %g\n", sw, j, cls, L.pc.x, L.pc.y, L.pc.z, L.e.x, L.e.y, L.e.z); break; }
             if (do_acc) gnw::accumulate_pose(acc, xr, M, v);
+#ifdef GNW_DEBUG
+            if (do_acc) {
+              double cst[6] = {A[0], A[1], A[2], A[4], A[5], A[8]}, u0q[3], Wq[9], Mq[6], vq[3];
+              general_fp64(C, R, t, xp, ob, stereo, (double)w, true, false, mu, cst, P.ba_lambda2, P.robust != 0, u0q, Wq, Mq, vq, true);
+              const float Mf[6] = {M.xx, M.xy, M.xz, M.yy, M.yz, M.zz};
+              double mx = 0, err = 0;
+              for (int i = 0; i < 6; ++i) { mx = std::fmax(mx, std::fabs(Mq[i])); err = std::fmax(err, std::fabs(Mq[i] - Mf[i])); }
+              const double verr = std::fmax(std::fabs(vq[0] - v.x), std::fmax(std::fabs(vq[1] - v.y), std::fabs(vq[2] - v.z)));
+              const double vmx = std::fmax(std::fabs(vq[0]), std::fmax(std::fabs(vq[1]), std::fabs(vq[2])));
+              if (err > 1e-2 * mx || verr > 1e-2 * vmx + 1e-3)
+                GNW_TRACE("sweep %d point %d class %d: M err %g of %g, v err %g of %g | pc %g %g %g e %g %g %g\n", sw, j, cls, err, mx, verr, vmx, L.pc.x, L.pc.y, L.pc.z, L.e.x, L.e.y, L.e.z);
+            }
+            if (do_acc && (M.xx < 0 || M.yy < 0 || M.zz < 0)) {
+              GNW_TRACE("  point %d: M diag %g %g %g | S %g %g %g %g %g %g | W %g %g %g / %g %g %g / %g %g %g | pc %g %g %g e %g %g %g w %g d %g %g %g\n", j,
+                        M.xx, M.yy, M.zz, Sw.xx, Sw.xy, Sw.xz, Sw.yy, Sw.yz, Sw.zz, pl.w0, pl.w1, pl.w2, pl.w3, pl.w4, pl.w5, pl.w6, pl.w7,
+                        pl.w8, L.pc.x, L.pc.y, L.pc.z, L.e.x, L.e.y, L.e.z, w, d.x, d.y, d.z);
+            }
+#endif
           } else {
             const V3f n = {(float)axis[9 * (size_t)k], (float)axis[9 * (size_t)k + 3], (float)axis[9 * (size_t)k + 6]};
             const float es = gnw::dotf(n, d);
             if (cls == C_STRP) {
               float kappa, rho;
-              if (!gnw::lin_strp(C, L, Rl, w, n, es, pl, kappa, rho)) { fail = 1; break; }
+              if (!gnw::lin_strp(C, L, Rl, w, n, es, pl, kappa, rho)) { fail = 1; GNW_TRACE("sweep %d: lin_strp failed, point %d\n", sw, j); break; }
               if (do_acc) gnw::accumulate_pose_rank1(acc, xr, n, kappa, rho);
-            } else if (!gnw::lin_mplane(C, L, Rl, n, es, pl)) { fail = 1; break; }
+            } else if (!gnw::lin_mplane(C, L, Rl, n, es, pl)) { fail = 1; GNW_TRACE("sweep %d: lin_mplane failed, point %d pc %g %g %g es %g\n", sw, j, L.pc.x, L.pc.y, L.pc.z, es); break; }
           }
           sp[0] = pl.u0.x; sp[1] = pl.u0.y; sp[2] = pl.u0.z;
           sp[3] = pl.w0; sp[4] = pl.w1; sp[5] = pl.w2; sp[6] = pl.w3; sp[7] = pl.w4; sp[8] = pl.w5; sp[9] = pl.w6; sp[10] = pl.w7; sp[11] = pl.w8;
         }
       }
       for (int i = 0; i < 27; ++i) accd[i] += (double)acc[i];
+#ifdef GNW_DEBUG
+      {
+        // per-point contribution check: the 6x6 block of one point must be positive semidefinite
+        const double dg[6] = {acc[0], acc[6], acc[11], acc[15], acc[18], acc[20]};
+        for (int i = 0; i < 6; ++i)
+          if (dg[i] < 0.0 || !std::isfinite(dg[i])) {
+            GNW_TRACE("sweep %d point %d class %d: diagonal %d of its block = %g (x' %g %g %g)\n", sw, j, cls, i, dg[i], xr.x, xr.y, xr.z);
+            break;
+          }
+      }
+#endif
     }
     if (fail) break;
     if (do_acc) {
       double dw[6];
       bool ok = true;
       for (int i = 0; i < 27; ++i) ok = ok && std::isfinite(accd[i]);
-      if (!ok || !solve6_ldlt(accd, dw)) { fail = 1; break; }
+      if (!ok || !solve6_ldlt(accd, dw)) { fail = 1; GNW_TRACE("sweep %d: pose system failed (finite %d)\n", sw, (int)ok); break; }
       double tp[3], dc[6];
       for (int r = 0; r < 3; ++r) {
         tp[r] = t[r] + (R[r * 3] * c0[0] + R[r * 3 + 1] * c0[1] + R[r * 3 + 2] * c0[2]);

@@ -31,6 +31,7 @@ def host_lib(tmp_path_factory):
                     str(so), str(ROOT / "tests" / "cpp" / "gnw_host_check.cu")], check=True, capture_output=True)
     lib = C.CDLL(str(so))
     lib.gnw_host_frame_solve.restype = C.c_int
+    lib.gnw_host_frame_solve_mode.restype = C.c_int
     return lib
 
 
@@ -61,8 +62,9 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("mode", [0, 1], ids=["k3w", "k3s"])
 @pytest.mark.parametrize("case", sorted(CASES))
-def test_world_frame_host_replay_matches_oracle(host_lib, oracle, case):
+def test_world_frame_host_replay_matches_oracle(host_lib, oracle, case, mode):
     c = CASES[case]
     mean, cov = synth.make_map(c["K"], c["pdeg"], seed=11)
     B = 6
@@ -71,6 +73,7 @@ def test_world_frame_host_replay_matches_oracle(host_lib, oracle, case):
     p, oprm = _params(oracle, **c["kw"])
     exp = oracle.frames_solve(comps, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], prm=oprm, nthreads=8, want_pts=True, want_conv=True)
     cm, ci, ax = (np.ascontiguousarray(comps[k]) for k in ("mean", "cov_inv", "axis"))
+    cv = np.ascontiguousarray(np.asarray(cov, np.float64).reshape(-1, 9))
     dg = np.ascontiguousarray(comps["is_degenerated"].astype(np.uint8))
     seen = set()
     compared = 0
@@ -79,10 +82,10 @@ def test_world_frame_host_replay_matches_oracle(host_lib, oracle, case):
         pose = np.zeros(7)
         pts = np.zeros((c["N"], 3))
         cls = np.zeros(c["N"], np.uint8)
-        rc = host_lib.gnw_host_frame_solve(_ptr(cm), _ptr(ci), _ptr(ax), _ptr(dg), C.byref(p), _ptr(np.ascontiguousarray(fr["pose0"][f])),
-                                           _ptr(np.ascontiguousarray(fr["pts_w"][f])), _ptr(np.ascontiguousarray(fr["obs"][f])),
-                                           _ptr(np.ascontiguousarray(fr["octave"][f])), _ptr(np.ascontiguousarray(asg)), c["N"],
-                                           _ptr(pose), _ptr(pts), _ptr(cls))
+        rc = host_lib.gnw_host_frame_solve_mode(_ptr(cm), _ptr(cv), _ptr(ci), _ptr(ax), _ptr(dg), C.byref(p),
+                                                _ptr(np.ascontiguousarray(fr["pose0"][f])), _ptr(np.ascontiguousarray(fr["pts_w"][f])),
+                                                _ptr(np.ascontiguousarray(fr["obs"][f])), _ptr(np.ascontiguousarray(fr["octave"][f])),
+                                                _ptr(np.ascontiguousarray(asg)), c["N"], _ptr(pose), _ptr(pts), _ptr(cls), mode)
         assert rc == exp["status"][f]
         seen |= set(np.unique(cls).tolist())
         if exp["status"][f] or ((exp["conv"][f, 1] > 1e-7) and (exp["conv"][f, 0] > 1e-6)):
@@ -97,3 +100,29 @@ def test_world_frame_host_replay_matches_oracle(host_lib, oracle, case):
     assert compared >= B - 2
     if case == "c5_style":
         assert {1, 2, 3, 4, 5, 6} <= seen  # every fp32 point class was exercised (7 = far points: the 'far' case)
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["k3w", "k3s"])
+@pytest.mark.parametrize("frame", [703, 1795])
+def test_near_camera_monocular_points_do_not_derail_the_frame(host_lib, oracle, frame, mode):
+    """Frames 703 / 1795 of the C2 bench batch hold "monocular" landmarks a centimetre from the camera plane (u_r < 0 <=> z <
+    bf / u) on full Gaussian components.  Their block in the plain fp32 form D = G + S returned pose gradients wrong by 1e3 x
+    (cond(D) beyond fp32) and the whole frame diverged — GMMLOC_FRAME_NUMERIC where the oracle converges to 1e-12.  The class
+    now runs in fp64 (K3w) / in gain form from the covariance (K3s, lin_mstr_gain): same status and pose as the oracle."""
+    mean, cov = synth.make_map(10000, 0.5)
+    fr = synth.make_frames(mean, cov, 1, 2000, seed=0, first_frame=frame)
+    comps = oracle.map_build(mean, cov)
+    p, oprm = _params(oracle)
+    exp = oracle.frames_solve(comps, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], prm=oprm, nthreads=4, want_pts=True, want_conv=True)
+    assert exp["status"][0] == 0 and exp["conv"][0, 0] < 1e-9
+    cm, ci, ax = (np.ascontiguousarray(comps[k]) for k in ("mean", "cov_inv", "axis"))
+    cv = np.ascontiguousarray(np.asarray(cov, np.float64).reshape(-1, 9))
+    dg = np.ascontiguousarray(comps["is_degenerated"].astype(np.uint8))
+    pose, pts, cls = np.zeros(7), np.zeros((2000, 3)), np.zeros(2000, np.uint8)
+    rc = host_lib.gnw_host_frame_solve_mode(_ptr(cm), _ptr(cv), _ptr(ci), _ptr(ax), _ptr(dg), C.byref(p), _ptr(np.ascontiguousarray(fr["pose0"][0])),
+                                            _ptr(np.ascontiguousarray(fr["pts_w"][0])), _ptr(np.ascontiguousarray(fr["obs"][0])),
+                                            _ptr(np.ascontiguousarray(fr["octave"][0])), _ptr(np.ascontiguousarray(exp["assign"][0])), 2000,
+                                            _ptr(pose), _ptr(pts), _ptr(cls), mode)
+    assert rc == 0 and (cls == 6).sum() > 10
+    ang = ref.rot_angle(synth.quat_to_rot(pose[:4]), synth.quat_to_rot(exp["pose"][0, :4]))
+    assert ang < 1e-6 and np.abs(pose[4:] - exp["pose"][0, 4:]).max() < 1e-5
