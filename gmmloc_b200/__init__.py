@@ -173,8 +173,13 @@ class Context:
         return out
 
     def set_gn_precision(self, precision: int) -> None:
-        """capi.GN_MIXED (default: fp64 state / residuals, fp32 Jacobian algebra) or capi.GN_FP64."""
+        """capi.GN_STREAM (default), GN_WORLD, GN_MIXED (fp64 state / residuals, fp32 Jacobian algebra) or capi.GN_FP64."""
         capi.check(capi.lib().gmmloc_ctx_set_gn_precision(self._h, int(precision)))
+
+    def last_gn_kernel(self) -> str:
+        """Frame-GN kernel the last frames_solve ran: "fp64", "mixed", "world" or "stream" ("none" before the first call)."""
+        k = capi.lib().gmmloc_ctx_last_gn_kernel(self._h)
+        return ("fp64", "mixed", "world", "stream")[k] if k >= 0 else "none"
 
     def last_assoc_kernel(self) -> str:
         return ("ffma2", "tensor", "grid")[capi.lib().gmmloc_ctx_last_assoc_kernel(self._h)]

@@ -20,7 +20,7 @@ FRAME_NUMERIC = 1
 VIEW_OVERFLOW = 1
 ASSOC_AUTO, ASSOC_FFMA2, ASSOC_TENSOR, ASSOC_GRID = 0, 1, 2, 3
 GN_FP64, GN_MIXED, GN_WORLD, GN_STREAM = 0, 1, 2, 3
-GN_DEFAULT = GN_MIXED  # what a new context runs (gmmloc_ctx_create)
+GN_DEFAULT = GN_STREAM  # what a new context runs (gmmloc_ctx_create)
 OPT_GN_PREP, OPT_E2E_CHUNK, OPT_E2E_SHORT_FIRST, OPT_BA_CLUSTER = 0, 1, 2, 3
 
 
@@ -82,6 +82,7 @@ SYMBOLS = {
     "gmmloc_ctx_kernel_times": (_i, [_vp, C.POINTER(C.c_float * 3)]),
     "gmmloc_ctx_set_assoc_kernel": (_i, [_vp, _i]),
     "gmmloc_ctx_last_assoc_kernel": (_i, [_vp]),
+    "gmmloc_ctx_last_gn_kernel": (_i, [_vp]),
     "gmmloc_ctx_set_gn_precision": (_i, [_vp, _i]),
     "gmmloc_host_alloc": (_i, [C.c_size_t, C.POINTER(_vp)]),
     "gmmloc_host_free": (None, [_vp]),

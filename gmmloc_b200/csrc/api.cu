@@ -238,8 +238,9 @@ struct gmmloc_ctx {
   std::vector<cudaEvent_t> ev_in, ev_done;          // per-chunk events (inputs landed / results ready)
   gmmloc_stats_t stats{};
   int assoc_kind = GMMLOC_ASSOC_AUTO;
-  int gn_precision = GMMLOC_GN_MIXED;
+  int gn_precision = GMMLOC_GN_STREAM;
   int last_assoc_tc = 0;
+  int last_gn = -1;              // GMMLOC_GN_* of the frame-GN kernel the last gmmloc_frames_solve[_async] ran
   int32_t* h_stop = nullptr;     // page-locked, device-mapped mirror of the caller's BA stop flag (gmmloc_local_ba)
   cudaEvent_t ev_ba = nullptr;   // end of the BA kernel (the host polls it while it mirrors the flag)
   int opt_gn_prep = -1;          // GMMLOC_OPT_GN_PREP
@@ -681,6 +682,7 @@ gmmloc_status_t gmmloc_ctx_set_assoc_kernel(gmmloc_ctx_t* ctx, int kind) {
   return GMMLOC_OK;
 }
 int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx) { return ctx ? ctx->last_assoc_tc : 0; }
+int gmmloc_ctx_last_gn_kernel(gmmloc_ctx_t* ctx) { return ctx ? ctx->last_gn : -1; }
 
 gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int precision) {
   if (!ctx || (precision != GMMLOC_GN_FP64 && precision != GMMLOC_GN_MIXED && precision != GMMLOC_GN_WORLD &&
@@ -852,13 +854,15 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
     CU(ctx->L().gn_prep.reserve(frame_gn_stream_prep_bytes(B, N)));
     CU(launch_frame_gn_stream(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().gn_store.as<float>(), ctx->L().gn_store.cap,
                               ctx->L().gn_prep.as<unsigned char>(), ctx->L().gn_prep.cap, ctx->L().stream));
-    ctx->stats.kernel_launches += 2;  // + the pack kernel and the (normally empty) fp64 retry launch
+    ctx->stats.kernel_launches += 4;  // + frame poses, classification, pack and the (normally empty) fp64 retry launch
+    ctx->last_gn = GMMLOC_GN_STREAM;
   } else if (gn_prec == GMMLOC_GN_WORLD && map->d.gn_tab != nullptr && N > 0 && (size_t)N <= frame_gn_world_limit_points()) {
     CU(ctx->L().next_frame.reserve(sizeof(int)));
     CU(ctx->L().gn_store.reserve(frame_gn_world_scratch_bytes(N)));
     CU(ctx->L().gn_prep.reserve(frame_gn_world_prep_bytes(B, N)));
     CU(launch_frame_gn_world(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().gn_store.as<float>(), ctx->L().gn_store.cap,
                              ctx->L().gn_prep.as<unsigned char>(), ctx->L().gn_prep.cap, ctx->L().stream));
+    ctx->last_gn = GMMLOC_GN_WORLD;
     ctx->stats.kernel_launches += 1;
   } else if (gn_prec != GMMLOC_GN_FP64 && map->d.gn_tab != nullptr && (size_t)N <= frame_gn_mixed_limit_points()) {
     CU(ctx->L().next_frame.reserve(sizeof(int)));
@@ -868,9 +872,11 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
     CU(launch_frame_gn_mixed(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().gn_store.as<float>(), ctx->L().gn_store.cap,
                              prep_bytes ? ctx->L().gn_prep.as<unsigned char>() : nullptr, prep_bytes ? ctx->L().gn_prep.cap : 0,
                              ctx->L().stream));
+    ctx->last_gn = GMMLOC_GN_MIXED;
     if (prep_bytes) ctx->stats.kernel_launches += 1;
   } else {
     CU(launch_frame_gn(a, ctx->L().stream));
+    ctx->last_gn = GMMLOC_GN_FP64;
   }
   CU(cudaEventRecord(ctx->L().ev[3], ctx->L().stream));
   ctx->L().ev_gn = true;

@@ -10,6 +10,13 @@ namespace gmmloc {
 namespace {
 
 constexpr double kFarZ = 6.0;  // metres; cond(G) ~ (z fx / bf)^2 ~ 3e3 at the shipped camera (v1.yaml:5-17)
+constexpr double kNearZ = 0.1;
+// Geometry the fp32 point blocks are trusted with.  The stereo projection Jacobian P has cond(P) ~ (1 + (x^2 + y^2) / z^2) z f / bf
+// = (r^2 / z) f / bf (r: distance from the camera centre): it grows with depth AND with the off-axis angle.  A landmark 36 cm in
+// front of the camera but 3 m to the side (frame 499 of the V1_03 replay: far outside the image, its association is a coincidence
+// of the synthetic landmarks) has cond(G) ~ 1e5; its fp32 block was wrong by 15 % and derailed the pose.  Such points, points
+// beyond kFarZ and points at or behind the camera plane take the fp64 path.
+__host__ __device__ inline bool fp32_geometry_ok(double pz, double r2) { return (pz > kNearZ) && (pz < kFarZ) && (r2 < 2.0 * kFarZ * pz); }
 // Point classes (bits 4..6 of the per-point flag byte).  The points of a frame are stably sorted by class when the
 // frame is loaded, so that a warp runs ONE code path per sweep (the unsorted fp64 kernel executes with ~25 of 32
 // lanes active) and the rare ill-conditioned blocks cost a few warp-iterations per sweep instead of stalling every warp.

@@ -353,7 +353,8 @@ __global__ void __launch_bounds__(kPrepThreads) frame_prep_kernel(const FrameArg
           cls = pose_free ? C_FIXED : C_OFF;
         } else {
           const double pz = s_R[6] * x0 + s_R[7] * x1 + s_R[8] * x2 + s_t[2];
-          if (!(pz < kFarZ)) cls = C_F64;
+          const double rx = x0 - twc0, ry = x1 - twc1, rz = x2 - twc2;
+          if (!fp32_geometry_ok(pz, rx * rx + ry * ry + rz * rz)) cls = C_F64;
           else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_MSTR;  // a free monocular point always has F_STR
           else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
         }
@@ -551,7 +552,8 @@ __global__ void __launch_bounds__(kThreads) __maxnreg__(kMinB == 1 ? 168 : GMMLO
             cls = pose_free ? C_FIXED : C_OFF;
           } else {
             const double pz = s_new.R[6] * x0 + s_new.R[7] * x1 + s_new.R[8] * x2 + s_new.t[2];
-            if (!(pz < kFarZ)) cls = C_F64;
+            const double rx = x0 - twc0, ry = x1 - twc1, rz = x2 - twc2;
+            if (!fp32_geometry_ok(pz, rx * rx + ry * ry + rz * rz)) cls = C_F64;
             else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_MSTR;  // a free monocular point always has F_STR
             else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
           }

@@ -86,14 +86,24 @@ __host__ __device__ inline PackLayout pack_layout(int N) {
   L.stride = o;
   return L;
 }
-__host__ __device__ inline size_t stream_slice(int N) { return (size_t)pack_max_chunks(N) * kStoreBytes; }
-
-__host__ __device__ inline uint32_t cst_bytes_of(int cls) {
-  return (cls == C_MPLANE || cls == C_STRP) ? 512u : (cls == C_STR || cls == C_MSTR) ? (uint32_t)kCstBytes : 0u;
+// the CTA's scratch slice holds, per chunk, the constants (copied there in the first sweep) AND the stored linearisation back
+// to back — [constants of the class | stored linearisation of the class] — so that every later sweep brings a chunk in with
+// ONE bulk copy
+__host__ __device__ inline size_t stream_slice(int N) { return (size_t)pack_max_chunks(N) * kSlotBytes; }
+// bytes of constants / of stored linearisation of one chunk of class c, in units of 128 B, five bits per class from class 1
+constexpr uint32_t lut5(int fixed, int plain, int mplane, int strp, int str, int mstr) {
+  return (uint32_t)fixed | ((uint32_t)plain << 5) | ((uint32_t)mplane << 10) | ((uint32_t)strp << 15) | ((uint32_t)str << 20) |
+         ((uint32_t)mstr << 25);
 }
-__host__ __device__ inline uint32_t store_bytes_of(int cls) {
-  return cls == C_PLAIN ? 384u : (cls == C_MPLANE || cls == C_STRP) ? 768u : (cls == C_STR || cls == C_MSTR) ? (uint32_t)kStoreBytes : 0u;
-}
+constexpr uint32_t kLutCst = lut5(0, 0, 4, 4, 9, 9);      // 0, 0, 512, 512, 1152, 1152 B
+constexpr uint32_t kLutStore = lut5(0, 3, 6, 6, 12, 12);  // 0, 384, 768, 768, 1536, 1536 B
+constexpr uint32_t kLutBoth = lut5(0, 3, 10, 10, 21, 21);
+constexpr uint32_t kLutPlanarCst = lut5(0, 0, 4, 4, 0, 0);
+__device__ __forceinline__ uint32_t lut_get(uint32_t lut, int cls) { return ((lut >> (5 * (cls - 1))) & 31u) << 7; }
+template <int CLS>
+struct ClsBytes {
+  static constexpr int cst = (CLS == C_MPLANE || CLS == C_STRP) ? 512 : (CLS == C_STR || CLS == C_MSTR) ? kCstBytes : 0;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -143,21 +153,86 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 // ================================================================================================================
 // K3q: classification + stable class sort (the arithmetic of frame_prep_kernel, frame_gn_mixed.cu) + chunk table +
 // per-chunk component constants.  One CTA of 256 threads per frame.
-constexpr int kPackThreads = 256;
-__global__ void __launch_bounds__(kPackThreads) frame_pack_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
-                                                                  unsigned char* __restrict__ pack) {
-  constexpr int kWarps = kPackThreads / 32;
-  extern __shared__ __align__(16) unsigned char smem_raw[];  // flags by ORIGINAL index while the frame is being sorted
-  __shared__ int s_cnt[C_COUNT * kMaxChunks * 8];
-  __shared__ double s_R[9], s_t[3];
-  __shared__ int s_start[C_COUNT + 1], s_cb[C_COUNT + 1];  // first sorted position / first chunk of every class
-  uint8_t* tmp = smem_raw;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+// K3c: flags and class of every point of the batch, ONE THREAD PER POINT (structure-edge gates fixed at iteration 0, in fp64
+// exactly as frame_gn_kernel).  The gate needs three dependent round trips per point (assignment -> degenerate flag ->
+// component constants); inside the per-frame pack kernel, whose threads walk eight points one after the other, they held 17
+// stall cycles per issued instruction.  Here every point is its own thread at full occupancy.
+#ifndef GMMLOC_CLS_MINB
+#define GMMLOC_CLS_MINB 4
+#endif
+// per-frame constants of the classification (the normalised initial pose): third row of R, t_z, camera centre -R^T t
+__global__ void __launch_bounds__(128) frame_pose_kernel(const FrameArgs a, double* __restrict__ fpose) {
+  const int f = blockIdx.x * 128 + threadIdx.x;
+  if (f >= a.B) return;
+  double q[7], R[9];
+  for (int i = 0; i < 7; ++i) q[i] = a.pose0[(size_t)f * 7 + i];
+  quat_normalize(q);
+  quat_to_rot(q, R);
+  double* o = fpose + (size_t)f * 8;
+  o[0] = R[6]; o[1] = R[7]; o[2] = R[8]; o[3] = q[6];
+  o[4] = -(R[0] * q[4] + R[3] * q[5] + R[6] * q[6]);
+  o[5] = -(R[1] * q[4] + R[4] * q[5] + R[7] * q[6]);
+  o[6] = -(R[2] * q[4] + R[5] * q[5] + R[8] * q[6]);
+  o[7] = 0.0;
+}
+__global__ void __launch_bounds__(256, GMMLOC_CLS_MINB) frame_classify_kernel(const FrameArgs a, const double* __restrict__ fpose,
+                                                                               uint8_t* __restrict__ flags) {
   const int N = a.N;
   const FrameParamsDev& P = a.prm;
   const bool pose_free = P.factor_mode != GMMLOC_MODE_POINTS_ONLY;
   const bool pts_free = P.factor_mode != GMMLOC_MODE_POSE_ONLY;
   const double view_cos_thresh = cos(78.0 * 3.14159265358979323846 / 180.0);  // gaussian_mixture.cpp:284
+  const long long total = (long long)a.B * N;
+  for (long long gi = (long long)blockIdx.x * 256 + threadIdx.x; gi < total; gi += (long long)gridDim.x * 256) {
+    const int f = (int)(gi / N);
+    const float px = __ldg(a.pts_w + gi * 3), py = __ldg(a.pts_w + gi * 3 + 1), pz = __ldg(a.pts_w + gi * 3 + 2);
+    const float our = __ldg(a.obs + gi * 3 + 2);
+    const int k = __ldg(a.assign + gi);
+    // per-frame constants written by frame_pose_kernel: third row of R (0..2), t_z (3), camera centre (4..6)
+    double fp[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) fp[i] = __ldg(fpose + (size_t)f * 8 + i);
+    const double x0 = (double)px, x1 = (double)py, x2 = (double)pz;
+    uint8_t b = (our >= 0.0f) ? F_STEREO : 0;
+    if (k >= 0 && pts_free) {
+      if (a.is_deg[k]) {
+        b |= F_DEG;
+        const double* ax = a.axis + (size_t)k * 9;
+        const double* mu = a.mean + (size_t)k * 3;
+        const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
+        if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;
+        const double p0 = mu[0] - fp[4], p1 = mu[1] - fp[5], p2 = mu[2] - fp[6];  // from the camera centre -R^T t
+        const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
+        if (view_cos < view_cos_thresh) b &= ~F_STR;
+      } else {
+        if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;
+      }
+    }
+    if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
+    int cls;
+    if (!(b & F_FREE)) {
+      cls = pose_free ? C_FIXED : C_OFF;
+    } else {
+      const double pzc = fp[0] * x0 + fp[1] * x1 + fp[2] * x2 + fp[3];
+      const double rx = x0 - fp[4], ry = x1 - fp[5], rz = x2 - fp[6];
+      if (!fp32_geometry_ok(pzc, rx * rx + ry * ry + rz * rz)) cls = C_F64;
+      else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_MSTR;  // a free monocular point always has F_STR
+      else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
+    }
+    flags[gi] = (uint8_t)(b | (cls << 4));
+  }
+}
+
+constexpr int kPackThreads = 256;
+__global__ void __launch_bounds__(kPackThreads) frame_pack_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
+                                                                  const uint8_t* __restrict__ flags, unsigned char* __restrict__ pack) {
+  constexpr int kWarps = kPackThreads / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];  // flags by ORIGINAL index while the frame is being sorted
+  __shared__ int s_cnt[C_COUNT * kMaxChunks * 8];
+  __shared__ int s_start[C_COUNT + 1], s_cb[C_COUNT + 1];  // first sorted position / first chunk of every class
+  uint8_t* tmp = smem_raw;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = a.N;
   const int nblocks = (N + kPackThreads - 1) / kPackThreads;
   const PackLayout L = pack_layout(N);
   for (int f = blockIdx.x; f < a.B; f += gridDim.x) {
@@ -172,51 +247,16 @@ __global__ void __launch_bounds__(kPackThreads) frame_pack_kernel(const FrameArg
     uint8_t* goct = pf + L.oct;
     uint8_t* gfl = pf + L.fl;
     unsigned char* gcst = pf + L.cst;
+    const uint8_t* gflag = flags + (size_t)f * N;
     __syncthreads();  // the previous frame is done with the shared arrays
-    if (tid == 0) {
-      double q[7];
-      for (int i = 0; i < 7; ++i) q[i] = a.pose0[(size_t)f * 7 + i];
-      quat_normalize(q);
-      quat_to_rot(q, s_R);
-      for (int i = 0; i < 3; ++i) s_t[i] = q[4 + i];
-    }
-    __syncthreads();
-    const double twc0 = -(s_R[0] * s_t[0] + s_R[3] * s_t[1] + s_R[6] * s_t[2]);
-    const double twc1 = -(s_R[1] * s_t[0] + s_R[4] * s_t[1] + s_R[7] * s_t[2]);
-    const double twc2 = -(s_R[2] * s_t[0] + s_R[5] * s_t[1] + s_R[8] * s_t[2]);
-    // pass A: flags and class of every point (structure-edge gates fixed at iteration 0, in fp64 exactly as
-    // frame_gn_kernel), class histogram per (block, warp)
+    // pass A: class histogram per (block, warp) from the flags frame_classify_kernel wrote
     for (int c = 0; c < nblocks; ++c) {
       const int i = c * kPackThreads + tid;
       int cls = -1;
       if (i < N) {
-        const double x0 = (double)pts[i * 3], x1 = (double)pts[i * 3 + 1], x2 = (double)pts[i * 3 + 2];
-        uint8_t b = (obs[i * 3 + 2] >= 0.0f) ? F_STEREO : 0;
-        const int k = asg[i];
-        if (k >= 0 && pts_free) {
-          if (a.is_deg[k]) {
-            b |= F_DEG;
-            const double* ax = a.axis + (size_t)k * 9;
-            const double* mu = a.mean + (size_t)k * 3;
-            const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
-            if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;
-            const double p0 = mu[0] - twc0, p1 = mu[1] - twc1, p2 = mu[2] - twc2;
-            const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
-            if (view_cos < view_cos_thresh) b &= ~F_STR;
-          } else {
-            if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;
-          }
-        }
-        if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
-        if (!(b & F_FREE)) {
-          cls = pose_free ? C_FIXED : C_OFF;
-        } else {
-          const double pz = s_R[6] * x0 + s_R[7] * x1 + s_R[8] * x2 + s_t[2];
-          if (!(pz < kFarZ)) cls = C_F64;
-          else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_MSTR;  // a free monocular point always has F_STR
-          else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
-        }
-        tmp[i] = (uint8_t)(b | (cls << 4));
+        const uint8_t b = gflag[i];
+        tmp[i] = b;
+        cls = b >> 4;
       }
 #pragma unroll
       for (int q = 0; q < C_COUNT; ++q) {
@@ -387,6 +427,7 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
   __shared__ double s_acc[kAccS];
   __shared__ double s_pose[7], s_dxc[6], s_c0[3];
   __shared__ float s_dxw[8];  // omega_w (3), upsilon_w (3): the pose step in world-twist coordinates about c0
+  __shared__ float s_c0f[4];
   __shared__ PoseS s_new, s_old;
   __shared__ int s_fail1, s_fail2, s_frame;
   __shared__ int s_hdr[4];
@@ -458,7 +499,10 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
         s_new.t[r] = s_old.t[r] = q[4 + r];
       }
       // reference point of the world twist: the camera centre of the initial pose, c0 = -R^T t
-      for (int c = 0; c < 3; ++c) s_c0[c] = -(s_new.R[c] * q[4] + s_new.R[3 + c] * q[5] + s_new.R[6 + c] * q[6]);
+      for (int c = 0; c < 3; ++c) {
+        s_c0[c] = -(s_new.R[c] * q[4] + s_new.R[3 + c] * q[5] + s_new.R[6 + c] * q[6]);
+        s_c0f[c] = (float)s_c0[c];
+      }
       s_fail1 = 0;
       s_fail2 = 0;
     }
@@ -489,6 +533,7 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
       const volatile double* vR = s_new.R;
       const volatile double* vt = s_new.t;
       const volatile float* vdx = s_dxw;
+      const volatile float* vc0f = s_c0f;
 
       float acc[kAccS];
 #pragma unroll
@@ -498,29 +543,24 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
       // bytes a chunk of class c brings in this sweep, in units of 128 B, one nibble per class (warp-uniform look-up):
       // constants when the chunk is linearised (the planar classes need their normal for the update too: W = I - kz n^T),
       // the stored linearisation when it is updated
-      uint32_t lut_c = 0u, lut_s = 0u;
-      if (do_lin && pts_free) lut_c |= (4u << (4 * C_MPLANE)) | (4u << (4 * C_STRP)) | (9u << (4 * C_STR)) | (9u << (4 * C_MSTR));
-      if (do_update) {
-        lut_c |= (4u << (4 * C_MPLANE)) | (4u << (4 * C_STRP));
-        lut_s = (3u << (4 * C_PLAIN)) | (6u << (4 * C_MPLANE)) | (6u << (4 * C_STRP)) | (12u << (4 * C_STR)) | (12u << (4 * C_MSTR));
-      }
+      // three kinds of sweep:  first (linearise only): the constants come from the packed frame and are copied into the slice;
+      // middle (update + linearise): constants + stored linearisation from the slice;  last (update only): the stored
+      // linearisation, and the normal of the planar classes (W = I - kz n^T), from the slice
+      const bool from_pack = !do_update;
+      const uint32_t lut_n = from_pack ? ((do_lin && pts_free) ? kLutCst : 0u) : (do_lin ? kLutBoth : kLutStore + kLutPlanarCst);
+      const uint32_t lut_o = (do_update && !do_lin) ? lut5(0, 0, 0, 0, 9, 9) : 0u;  // offset of the copy inside the chunk record
       auto issue = [&](int g) {  // warp-uniform bookkeeping, lane 0 issues
-        const uint32_t sh = (s_chunk[g] >> 24) * 4u;
-        const uint32_t cb = ((lut_c >> sh) & 15u) << 7, sb = ((lut_s >> sh) & 15u) << 7;
-        if (cb + sb == 0u) return;
+        const int cls = (int)(s_chunk[g] >> 24);
+        const uint32_t nb = lut_get(lut_n, cls);
+        if (nb == 0u) return;
         if (lane == 0) {
-          const uint32_t slot = n_iss & 1u;
-          const uint32_t bar = bar_a + slot * 8u, dst = ring_a + slot * kSlotBytes;
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(cb + sb) : "memory");
-          if (cb)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                         "l"(gcst + (size_t)g * kCstBytes), "r"(cb), "r"(bar)
-                         : "memory");
-          if (sb)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             dst + kCstBytes),
-                         "l"(gstore + (size_t)g * kStoreBytes), "r"(sb), "r"(bar)
-                         : "memory");
+          const uint32_t slot = n_iss & 1u, off = lut_get(lut_o, cls);
+          const uint32_t bar = bar_a + slot * 8u, dst = ring_a + slot * kSlotBytes + off;
+          const unsigned char* src = from_pack ? gcst + (size_t)g * kCstBytes : gstore + (size_t)g * kSlotBytes + off;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nb) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                       "r"(nb), "r"(bar)
+                       : "memory");
         }
         ++n_iss;
       };
@@ -529,14 +569,15 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
         constexpr int CLS = decltype(cls_tag)::value;
         constexpr bool kStereo = CLS == C_PLAIN || CLS == C_STRP || CLS == C_STR;
         const float4* cst4 = reinterpret_cast<const float4*>(slot);
-        const float4* st4 = reinterpret_cast<const float4*>(slot + kCstBytes);
+        const float4* st4 = reinterpret_cast<const float4*>(slot + ClsBytes<CLS>::cst);
+        unsigned char* gst = gs + ClsBytes<CLS>::cst;  // this chunk's stored linearisation in the slice
         float d0 = 0.f, d1 = 0.f, d2 = 0.f;
         if (CLS != C_FIXED) {
           d0 = dl[j * 3]; d1 = dl[j * 3 + 1]; d2 = dl[j * 3 + 2];
         }
         const double X0 = (double)x0s[j * 3], X1 = (double)x0s[j * 3 + 1], X2 = (double)x0s[j * 3 + 2];
-        // x' = x - c0 for the Jacobian side (fp32): (x0 - c0) rounded once, + delta
-        const V3f xr0 = {(float)(X0 - vc0[0]), (float)(X1 - vc0[1]), (float)(X2 - vc0[2])};
+        // x' = x - c0 for the Jacobian side, formed in fp32 (it only ever multiplies fp32 quantities)
+        const V3f xr0 = {x0s[j * 3] - vc0f[0], x0s[j * 3 + 1] - vc0f[1], x0s[j * 3 + 2] - vc0f[2]};
         // ---- update: delta += u0 - W (omega_w x x' + upsilon_w) from the linearisation stored by the previous sweep ----
         if (CLS != C_FIXED && do_update) {
           const V3f om = {vdx[0], vdx[1], vdx[2]}, up = {vdx[3], vdx[4], vdx[5]};
@@ -589,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
             gnw::accumulate_pose(acc, xr, G, h);
           } else if (CLS == C_PLAIN) {
             const V3f u0 = gnw::lin_plain(C, Ln, Rl);
-            float* gf = reinterpret_cast<float*>(gs);
+            float* gf = reinterpret_cast<float*>(gst);
             __stcg(gf + lane, u0.x);
             __stcg(gf + 32 + lane, u0.y);
             __stcg(gf + 64 + lane, u0.z);
@@ -605,8 +646,9 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
             } else {
               if (!gnw::lin_mplane_c(C, Ln, Rl, n, es, pl)) bad |= 2;
             }
-            __stcg(reinterpret_cast<float4*>(gs) + lane, make_float4(pl.u0.x, pl.u0.y, pl.u0.z, pl.kz.x));
-            __stcg(reinterpret_cast<float2*>(gs + 512) + lane, make_float2(pl.kz.y, pl.kz.z));
+            if (from_pack) __stcg(reinterpret_cast<float4*>(gs) + lane, c0v);  // constants into the slice, once per frame
+            __stcg(reinterpret_cast<float4*>(gst) + lane, make_float4(pl.u0.x, pl.u0.y, pl.u0.z, pl.kz.x));
+            __stcg(reinterpret_cast<float2*>(gst + 512) + lane, make_float2(pl.kz.y, pl.kz.z));
           } else {  // C_STR / C_MSTR
             const float4 c0v = cst4[lane], c1v = cst4[32 + lane];
             const float c2v = reinterpret_cast<const float*>(slot + 1024)[lane];
@@ -620,9 +662,14 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
                                            : gnw::lin_mstr_gain(C, Ln, Rl, w, Sw, d, pl, M, v);
             if (!ok32) bad |= 1;
             if (do_acc) gnw::accumulate_pose(acc, xr, M, v);
-            __stcg(reinterpret_cast<float4*>(gs) + lane, make_float4(pl.u0.x, pl.u0.y, pl.u0.z, pl.w0));
-            __stcg(reinterpret_cast<float4*>(gs) + 32 + lane, make_float4(pl.w1, pl.w2, pl.w3, pl.w4));
-            __stcg(reinterpret_cast<float4*>(gs) + 64 + lane, make_float4(pl.w5, pl.w6, pl.w7, pl.w8));
+            if (from_pack) {  // constants into the slice, once per frame
+              __stcg(reinterpret_cast<float4*>(gs) + lane, c0v);
+              __stcg(reinterpret_cast<float4*>(gs) + 32 + lane, c1v);
+              __stcg(reinterpret_cast<float*>(gs + 1024) + lane, c2v);
+            }
+            __stcg(reinterpret_cast<float4*>(gst) + lane, make_float4(pl.u0.x, pl.u0.y, pl.u0.z, pl.w0));
+            __stcg(reinterpret_cast<float4*>(gst) + 32 + lane, make_float4(pl.w1, pl.w2, pl.w3, pl.w4));
+            __stcg(reinterpret_cast<float4*>(gst) + 64 + lane, make_float4(pl.w5, pl.w6, pl.w7, pl.w8));
           }
         }
       };
@@ -632,14 +679,14 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
         const uint32_t ent = s_chunk[g];
         const int cls = (int)(ent >> 24);
         const unsigned char* slot = ring + (n_con & 1u) * kSlotBytes;
-        if ((((lut_c | lut_s) >> (cls * 4)) & 15u) != 0u) {
+        if (lut_get(lut_n, cls) != 0u) {
           mbar_wait_a(bar_a + (n_con & 1u) * 8u, (n_con >> 1) & 1u);
           ++n_con;
         }
         const bool work = (cls == C_FIXED) ? do_acc : (do_update || do_lin);
         if (work && lane < (int)((ent >> 16) & 0xffu)) {
           const int j = (int)(ent & 0xffffu) + lane;
-          unsigned char* gs = gstore + (size_t)g * kStoreBytes;
+          unsigned char* gs = gstore + (size_t)g * kSlotBytes;
           switch (cls) {
             case C_FIXED: point(std::integral_constant<int, C_FIXED>{}, j, slot, gs); break;
             case C_PLAIN: point(std::integral_constant<int, C_PLAIN>{}, j, slot, gs); break;
@@ -866,7 +913,7 @@ size_t frame_gn_stream_scratch_bytes(int N) {
   return (size_t)2 * sms * stream_slice(N) + 16;
 }
 
-size_t frame_gn_stream_prep_bytes(int B, int N) { return (size_t)B * pack_layout(N).stride + 16; }
+size_t frame_gn_stream_prep_bytes(int B, int N) { return (size_t)B * pack_layout(N).stride + (size_t)B * N + (size_t)B * 64 + 64; }
 
 // d_counters: a.B + 2 ints (frame counter, number of frames handed to the fp64 kernel, their indices)
 cudaError_t launch_frame_gn_stream(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
@@ -875,13 +922,21 @@ cudaError_t launch_frame_gn_stream(const FrameArgs& a, const float* gn_tab, int*
   const size_t need = (size_t)a.B * pack_layout(a.N).stride;
   if (prep_ws == nullptr || store_ws == nullptr || need == 0) return cudaErrorInvalidValue;
   unsigned char* pack = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(prep_ws) + 15) & ~(uintptr_t)15);
-  if ((size_t)(pack - prep_ws) + need > prep_ws_bytes) return cudaErrorInvalidValue;
+  if ((size_t)(pack - prep_ws) + need + (size_t)a.B * a.N + 16 + (size_t)a.B * 64 > prep_ws_bytes) return cudaErrorInvalidValue;
   unsigned char* st = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(store_ws) + 15) & ~(uintptr_t)15);
   const size_t st_bytes = store_ws_bytes - (size_t)(st - reinterpret_cast<unsigned char*>(store_ws));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  frame_pack_kernel<<<std::min(a.B, sms * 8), kPackThreads, (size_t)((a.N + 15) & ~15), stream>>>(a, gn_tab, pack);
+  uint8_t* flags = pack + need;  // B x N class bytes behind the packed frames, then 8 doubles per frame
+  double* fpose = reinterpret_cast<double*>(flags + (((size_t)a.B * a.N + 15) & ~(size_t)15));
+  frame_pose_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a, fpose);
+  {
+    const long long total = (long long)a.B * a.N;
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 64);
+    frame_classify_kernel<<<grid, 256, 0, stream>>>(a, fpose, flags);
+  }
+  frame_pack_kernel<<<std::min(a.B, sms * 8), kPackThreads, (size_t)((a.N + 15) & ~15), stream>>>(a, gn_tab, flags, pack);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   bool fits = false;

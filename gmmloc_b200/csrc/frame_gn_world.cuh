@@ -274,6 +274,10 @@ GNW_HD bool lin_str(const Cam& C, const Lin& L, const float* Rf, bool stereo, fl
     M.yy = out.w1 * Sw.xy + out.w4 * Sw.yy + out.w7 * Sw.yz;
     M.yz = out.w1 * Sw.xz + out.w4 * Sw.yz + out.w7 * Sw.zz;
     M.zz = out.w2 * Sw.xz + out.w5 * Sw.yz + out.w8 * Sw.zz;
+    // M = (G^-1 + S^-1)^-1 is positive semidefinite; a diagonal entry that comes out clearly negative means D was too
+    // ill-conditioned for the fp32 inverse: report it (the frame is then solved by the fp64 kernel)
+    const float tol = 1e-3f * (fabsf(M.xx) + fabsf(M.yy) + fabsf(M.zz));
+    ok = ok && (M.xx >= -tol) && (M.yy >= -tol) && (M.zz >= -tol);
   }
   return ok;
 }

@@ -179,15 +179,19 @@ GMMLOC_API gmmloc_status_t gmmloc_ctx_set_assoc_kernel(gmmloc_ctx_t* ctx, int ki
 GMMLOC_API int gmmloc_ctx_last_assoc_kernel(gmmloc_ctx_t* ctx);
 /* Arithmetic of the per-frame Gauss-Newton kernel behind gmmloc_frames_solve (Localization::jointOptimization with a
  * single free pose, localization_opt.cpp:456-925):
- *   GMMLOC_GN_MIXED (default)  state, residuals and the 6x6 reduced system in fp64, Jacobian / Hessian-model algebra
+ *   GMMLOC_GN_MIXED            state, residuals and the 6x6 reduced system in fp64, Jacobian / Hessian-model algebra
  *                              in fp32 — same fixed point (poses agree with the fp64 solve to ~1e-9), ~3x faster;
  *   GMMLOC_GN_WORLD            the same precision split with the per-point blocks written in the world frame (the
  *                              structure edge needs no rotation, the point step no pose; 16 instead of 12 warps per SM);
  *   GMMLOC_GN_FP64             everything in fp64;
- *   GMMLOC_GN_STREAM           the world-frame kernel with every per-sweep operand (component constants resolved once per
- *                              frame, stored linearisation) staged through shared memory by TMA bulk copies; */
+ *   GMMLOC_GN_STREAM (default) the world-frame kernel with every per-sweep operand (component constants resolved once per
+ *                              frame, stored linearisation) staged through shared memory by TMA bulk copies; frames of more
+ *                              than ~4 300 landmarks run GMMLOC_GN_MIXED. */
 enum { GMMLOC_GN_FP64 = 0, GMMLOC_GN_MIXED = 1, GMMLOC_GN_WORLD = 2, GMMLOC_GN_STREAM = 3 };
 GMMLOC_API gmmloc_status_t gmmloc_ctx_set_gn_precision(gmmloc_ctx_t* ctx, int precision);
+/* GMMLOC_GN_* of the kernel the last gmmloc_frames_solve[_async] on ctx ran (frame size decides between the selected kernel
+ * and its fall-backs), -1 before the first call */
+GMMLOC_API int gmmloc_ctx_last_gn_kernel(gmmloc_ctx_t* ctx);
 
 /* Tuning switches of a context for A/B measurements; every setting returns identical results.  (Environment variables
  * are NOT consulted by a production build: they are compiled in only with -DGMMLOC_DEBUG_ENV.)

@@ -162,7 +162,8 @@ extern "C" int gnw_host_frame_solve_mode(const double* mean, const double* cov, 
     if (!(b & F_FREE)) cls = pose_free ? C_FIXED : C_OFF;
     else {
       const double pz = R[6] * x0 + R[7] * x1 + R[8] * x2 + t[2];
-      if (!(pz < kFarZ)) cls = C_F64;
+      const double rx = x0 - c0[0], ry = x1 - c0[1], rz = x2 - c0[2];
+      if (!((pz > 0.1) && (pz < kFarZ) && (rx * rx + ry * ry + rz * rz < 2.0 * kFarZ * pz))) cls = C_F64;  // fp32_geometry_ok()
       else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_MSTR;
       else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
     }

@@ -126,3 +126,30 @@ def test_near_camera_monocular_points_do_not_derail_the_frame(host_lib, oracle, 
     assert rc == 0 and (cls == 6).sum() > 10
     ang = ref.rot_angle(synth.quat_to_rot(pose[:4]), synth.quat_to_rot(exp["pose"][0, :4]))
     assert ang < 1e-6 and np.abs(pose[4:] - exp["pose"][0, 4:]).max() < 1e-5
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["k3w", "k3s"])
+@pytest.mark.parametrize("frame", [499, 1865])
+def test_off_axis_landmarks_of_the_v1_03_replay_take_the_fp64_path(host_lib, oracle, frame, mode):
+    """Frames 499 / 1865 of the V1_03 replay (shipped v1.gmm, BASELINE configs[2]) hold a landmark 36 cm in front of the camera
+    and 3 m to its side: cond(G) ~ 1e5, the fp32 block was wrong by 15 % and the pose ended 1e-2 rad off (K3w / first K3s).
+    fp32_geometry_ok() (frame_gn_classes.cuh) now sends such geometry to the fp64 path: pose within 1e-6 rad / 1e-5 m."""
+    z = np.load(ROOT / "tests" / "golden" / "v1_gmm.npz")
+    gt = np.load(ROOT / "tests" / "golden" / "v1_03_gt_sync.npz")["gt"]
+    mean, cov = z["mean"], z["cov"]
+    fr = synth.make_frames(mean, cov, 1, 1200, seed=0, poses_wc=gt[frame:frame + 1, 1:8], first_frame=frame)
+    comps = oracle.map_build(mean, cov)
+    p, oprm = _params(oracle)
+    exp = oracle.frames_solve(comps, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], prm=oprm, nthreads=4, want_pts=True, want_conv=True)
+    assert exp["status"][0] == 0
+    cm, ci, ax = (np.ascontiguousarray(comps[k]) for k in ("mean", "cov_inv", "axis"))
+    cv = np.ascontiguousarray(np.asarray(cov, np.float64).reshape(-1, 9))
+    dg = np.ascontiguousarray(comps["is_degenerated"].astype(np.uint8))
+    pose, pts, cls = np.zeros(7), np.zeros((1200, 3)), np.zeros(1200, np.uint8)
+    rc = host_lib.gnw_host_frame_solve_mode(_ptr(cm), _ptr(cv), _ptr(ci), _ptr(ax), _ptr(dg), C.byref(p), _ptr(np.ascontiguousarray(fr["pose0"][0])),
+                                            _ptr(np.ascontiguousarray(fr["pts_w"][0])), _ptr(np.ascontiguousarray(fr["obs"][0])),
+                                            _ptr(np.ascontiguousarray(fr["octave"][0])), _ptr(np.ascontiguousarray(exp["assign"][0])), 1200,
+                                            _ptr(pose), _ptr(pts), _ptr(cls), mode)
+    assert rc == 0 and (cls == 7).sum() >= 1
+    ang = ref.rot_angle(synth.quat_to_rot(pose[:4]), synth.quat_to_rot(exp["pose"][0, :4]))
+    assert ang < 1e-6 and np.abs(pose[4:] - exp["pose"][0, 4:]).max() < 1e-5

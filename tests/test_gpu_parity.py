@@ -227,6 +227,18 @@ def test_optimize_point_bit_exact(gpu, oracle, golden_maps):
         assert n_ok > 10
 
 
+import contextlib
+
+
+@contextlib.contextmanager
+def _gn(g, ctx, precision):
+    ctx.set_gn_precision(precision)
+    try:
+        yield
+    finally:
+        ctx.set_gn_precision(g.capi.GN_DEFAULT)
+
+
 # ---------------------------------------------------------------- frame solve (a11/a12)
 def _pose_err(p, q):
     ang = ref.rot_angle(synth.quat_to_rot(p[:4]), synth.quat_to_rot(q[:4]))
@@ -654,7 +666,7 @@ def test_frames_solve_fp64_kernel_and_mixed_kernel_agree(gpu, oracle, golden_map
         ctx.set_gn_precision(g.capi.GN_MIXED)
         omx = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=prm)
     finally:
-        ctx.set_gn_precision(g.capi.GN_MIXED)
+        ctx.set_gn_precision(g.capi.GN_DEFAULT)
     worst = (0.0, 0.0)
     for f in range(len(fr["pose0"])):
         ang, dt = _pose_err(omx["pose"][f], o64["pose"][f])
@@ -680,7 +692,8 @@ def test_frames_solve_mixed_kernel_variant_boundaries(gpu, oracle, N, prep):
     try:
         mean, cov = synth.make_map(3000, 0.7, seed=17)
         fr = synth.make_frames(mean, cov, 2, N, seed=N, mono_frac=0.15)
-        _check_frames(g, ctx, oracle, mean, cov, fr, robust=1)
+        with _gn(g, ctx, g.capi.GN_MIXED):
+            _check_frames(g, ctx, oracle, mean, cov, fr, robust=1)
     finally:
         ctx.set_option(g.capi.OPT_GN_PREP, -1)
 
@@ -693,9 +706,10 @@ def test_frames_solve_prepared_frames_equal_in_kernel_sort(gpu):
     fr = synth.make_frames(mean, cov, 1300, 301, seed=9, mono_frac=0.2)
     m = g.GMM(mean, cov)
     outs = []
-    for prep in (1, 0):
-        ctx.set_option(g.capi.OPT_GN_PREP, prep)
-        outs.append(ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=g.default_params(robust=1)))
+    with _gn(g, ctx, g.capi.GN_MIXED):
+        for prep in (1, 0):
+            ctx.set_option(g.capi.OPT_GN_PREP, prep)
+            outs.append(ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"], params=g.default_params(robust=1)))
     ctx.set_option(g.capi.OPT_GN_PREP, -1)
     for k in ("pose", "pts", "assign", "outlier", "status"):
         assert np.array_equal(outs[0][k], outs[1][k]), k
@@ -726,18 +740,6 @@ def test_environment_variables_do_not_steer_a_production_build(gpu, monkeypatch)
 
 
 # ---------------------------------------------------------------- world-frame frame GN (K3w)
-import contextlib
-
-
-@contextlib.contextmanager
-def _gn(g, ctx, precision):
-    ctx.set_gn_precision(precision)
-    try:
-        yield
-    finally:
-        ctx.set_gn_precision(g.capi.GN_DEFAULT)
-
-
 @pytest.mark.parametrize("kind", ["world", "stream"])
 @pytest.mark.parametrize("case", ["c1", "c2", "pose_only", "points_only", "c5_style", "shipped_v1", "iters", "nan"])
 def test_world_frame_kernel_matches_oracle(gpu, oracle, golden_maps, gt_v1_03, case, kind):
