@@ -21,7 +21,7 @@ VIEW_OVERFLOW = 1
 ASSOC_AUTO, ASSOC_FFMA2, ASSOC_TENSOR, ASSOC_GRID = 0, 1, 2, 3
 GN_FP64, GN_MIXED, GN_WORLD, GN_STREAM = 0, 1, 2, 3
 GN_DEFAULT = GN_STREAM  # what a new context runs (gmmloc_ctx_create)
-OPT_GN_PREP, OPT_E2E_CHUNK, OPT_E2E_SHORT_FIRST, OPT_BA_CLUSTER = 0, 1, 2, 3
+OPT_GN_PREP, OPT_E2E_CHUNK, OPT_E2E_SHORT_FIRST, OPT_BA_CLUSTER, OPT_E2E_TAPER = 0, 1, 2, 3, 4
 
 
 class GridOptions(C.Structure):

@@ -246,6 +246,7 @@ struct gmmloc_ctx {
   int opt_gn_prep = -1;          // GMMLOC_OPT_GN_PREP
   int opt_e2e_chunk = 0;         // GMMLOC_OPT_E2E_CHUNK
   int opt_e2e_short_first = 0;   // GMMLOC_OPT_E2E_SHORT_FIRST
+  int opt_e2e_taper = 1;         // GMMLOC_OPT_E2E_TAPER
   int opt_ba_cluster = 0;        // GMMLOC_OPT_BA_CLUSTER
 };
 
@@ -706,6 +707,9 @@ gmmloc_status_t gmmloc_ctx_set_option(gmmloc_ctx_t* ctx, int option, int64_t val
     case GMMLOC_OPT_E2E_SHORT_FIRST:
       ctx->opt_e2e_short_first = value ? 1 : 0;
       return GMMLOC_OK;
+    case GMMLOC_OPT_E2E_TAPER:
+      ctx->opt_e2e_taper = value ? 1 : 0;
+      return GMMLOC_OK;
     case GMMLOC_OPT_BA_CLUSTER:
       if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return fail(GMMLOC_EINVAL, "GMMLOC_OPT_BA_CLUSTER: 0, 1, 2, 4 or 8");
       ctx->opt_ba_cluster = (int)value;
@@ -925,7 +929,31 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     return v ? std::atoi(v) : ctx->opt_e2e_short_first;
   }();
   std::vector<int> cstart;
-  {
+  if (ctx->opt_e2e_taper && chunk_env <= 0 && !short_first && B >= 4 * chunk) {
+    // Tapered schedule (default for large batches): the call ends when the LAST chunk has been copied in, solved and copied
+    // out, and it cannot start computing before the FIRST chunk has arrived — so both ends are short (one and two frames
+    // per resident CTA) and only the middle runs full 6-frames-per-SM chunks.  With the copy-in as the longer stream
+    // (205 MB per 4 096 C2 frames at 46-55 GB/s against 3.8 ms of kernels) the step costs H2D(total) + solve(last chunk)
+    // instead of H2D(total) + solve(888 frames).
+    const int unit = 2 * sms;
+    std::vector<int> sizes = {unit, 2 * unit};
+    int mid = B - 6 * unit;
+    std::vector<int> middle;
+    while (mid >= chunk + chunk / 2) {
+      middle.push_back(chunk);
+      mid -= chunk;
+    }
+    if (mid > 0) middle.insert(middle.begin(), mid);
+    sizes.insert(sizes.end(), middle.begin(), middle.end());
+    sizes.push_back(2 * unit);
+    sizes.push_back(unit);
+    int f = 0;
+    for (int sz : sizes) {
+      cstart.push_back(f);
+      f += sz;
+    }
+    cstart.push_back(B);
+  } else {
     int f = 0;
     const int first = (short_first && chunk_env <= 0 && B >= 4 * chunk) ? chunk / 3 : chunk;
     while (f < B) {
@@ -979,6 +1007,14 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
       break;                                            \
     }                                                   \
   }
+  // -DGMMLOC_DEBUG_ENV builds only: GMMLOC_E2E_TRACE=1 prints the timeline of the pipeline (ms since the first copy was issued)
+  const bool trace = debug_env("GMMLOC_E2E_TRACE") != nullptr;
+  std::vector<cudaEvent_t> tev;  // per chunk: copy-in done, kernels started, kernels done, copy-out done; [4 n]: start
+  if (trace) {
+    tev.resize(4 * (size_t)nchunks + 1);
+    for (auto& e : tev) cudaEventCreate(&e);
+    cudaEventRecord(tev[4 * (size_t)nchunks], ctx->h2d);
+  }
   for (int c = 0; c < nchunks && rc == GMMLOC_OK; ++c) {
     ctx->active = (nchunks > 1) ? (c & 1) : 0;
     cudaStream_t st = ctx->L().stream;
@@ -990,7 +1026,9 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
       CUB(cudaMemcpyAsync(ctx->in_oct.as<uint8_t>() + m0, octave + m0, nm, cudaMemcpyHostToDevice, ctx->h2d));
     }
     CUB(cudaEventRecord(ctx->ev_in[c], ctx->h2d));
+    if (trace) cudaEventRecord(tev[4 * c], ctx->h2d);
     CUB(cudaStreamWaitEvent(st, ctx->ev_in[c], 0));
+    if (trace) cudaEventRecord(tev[4 * c + 1], st);
     rc = gmmloc_frames_solve_async(
         ctx, map, cam, params, ctx->in_pose.as<double>() + 7 * f0, ctx->in_pts.as<float>() + 3 * m0,
         ctx->in_obs.as<float>() + 3 * m0, ctx->in_oct.as<uint8_t>() + m0, (int)nb, N, ctx->out_pose.as<double>() + 7 * f0,
@@ -998,6 +1036,7 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
         outlier ? ctx->out_outlier.as<uint8_t>() + m0 : nullptr, ctx->out_status.as<int32_t>() + f0);
     if (rc != GMMLOC_OK) break;
     CUB(cudaEventRecord(ctx->ev_done[c], st));
+    if (trace) cudaEventRecord(tev[4 * c + 2], st);
     CUB(cudaStreamWaitEvent(ctx->d2h, ctx->ev_done[c], 0));
     CUB(cudaMemcpyAsync(pose_out + 7 * f0, ctx->out_pose.as<double>() + 7 * f0, 56 * nb, cudaMemcpyDeviceToHost, ctx->d2h));
     CUB(cudaMemcpyAsync(status + f0, ctx->out_status.as<int32_t>() + f0, 4 * nb, cudaMemcpyDeviceToHost, ctx->d2h));
@@ -1006,10 +1045,20 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
       if (pts_out) CUB(cudaMemcpyAsync(pts_out + 3 * m0, ctx->out_pts.as<float>() + 3 * m0, 12 * nm, cudaMemcpyDeviceToHost, ctx->d2h));
       if (outlier) CUB(cudaMemcpyAsync(outlier + m0, ctx->out_outlier.as<uint8_t>() + m0, nm, cudaMemcpyDeviceToHost, ctx->d2h));
     }
+    if (trace) cudaEventRecord(tev[4 * c + 3], ctx->d2h);
   }
   ctx->active = 0;
   const cudaError_t e0 = cudaStreamSynchronize(ctx->h2d), e1 = cudaStreamSynchronize(ctx->lanes[0].stream),
                     e2 = cudaStreamSynchronize(ctx->lanes[1].stream), e3 = cudaStreamSynchronize(ctx->d2h);
+  if (trace) {
+    for (int c = 0; c < nchunks; ++c) {
+      float t[4] = {0, 0, 0, 0};
+      for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], tev[4 * (size_t)nchunks], tev[4 * c + i]);
+      std::fprintf(stderr, "chunk %d: %d frames | in done %.3f | kernels %.3f .. %.3f | out done %.3f ms\n", c, cstart[c + 1] - cstart[c],
+                   t[0], t[1], t[2], t[3]);
+    }
+    for (auto& e : tev) cudaEventDestroy(e);
+  }
 #undef CUB
   if (rc != GMMLOC_OK) return rc;
   CU(e0);

@@ -374,15 +374,17 @@ def test_frames_solve_large_n_uses_global_workspace(gpu, oracle):
     _check_frames(g, ctx, oracle, mean, cov, fr)
 
 
-def test_frames_solve_pipelined_host_path_equals_single_chunks(gpu):
-    # B >= 1024 takes the chunked H2D / compute / D2H pipeline of gmmloc_frames_solve: same results as
-    # frame-by-frame calls (and therefore as the oracle, checked above)
+@pytest.mark.parametrize("B", [1100, 3700])
+def test_frames_solve_pipelined_host_path_equals_single_chunks(gpu, B):
+    # B >= 1024 takes the chunked H2D / compute / D2H pipeline of gmmloc_frames_solve (uniform chunks; from 24 frames per SM
+    # on the tapered schedule with short chunks at both ends): same results as frame-by-frame calls (and therefore as the
+    # oracle, checked above)
     g, ctx = gpu
     mean, cov = synth.make_map(800, 0.5, seed=12)
     m = g.GMM(mean, cov)
-    fr = synth.make_frames(mean, cov, 1100, 40, seed=12)
+    fr = synth.make_frames(mean, cov, B, 40, seed=12)
     big = ctx.frames_solve(m, fr["pose0"], fr["pts_w"], fr["obs"], fr["octave"])
-    for lo, hi in ((0, 3), (510, 515), (1023, 1100)):
+    for lo, hi in ((0, 3), (294, 299), (510, 515), (886, 890), (1023, 1100), (B - 300, B - 290), (B - 3, B)):
         part = ctx.frames_solve(m, fr["pose0"][lo:hi], fr["pts_w"][lo:hi], fr["obs"][lo:hi], fr["octave"][lo:hi])
         for k in ("pose", "pts", "assign", "outlier", "status"):
             assert np.array_equal(big[k][lo:hi], part[k]), (k, lo)
