@@ -616,16 +616,13 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
 #pragma unroll 4
         for (int q = 0; q < n; ++q) {
           const float4 r0 = stage[wrp][q][0], r1 = stage[wrp][q][1], r2 = stage[wrp][q][2];
-          const float s = score32(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, px, py, pz);
-          if (mine) {
-            if (s < b1) {
-              b2 = b1;
-              b1 = s;
-              idx = __float_as_int(r2.y);
-            } else {
-              b2 = fminf(b2, s);
-            }
-          }
+          // branch-free best / second-best (the branchy form spent more instructions here than on the score itself:
+          // profiles/assoc_grid_r02.txt).  A lane that is not in this cell scores +inf: nothing changes for it.
+          // Strict < keeps the first (lowest) id on equal scores, as the reference's ascending scan.
+          const float s = mine ? score32(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, px, py, pz) : CUDART_INF_F;
+          idx = (s < b1) ? __float_as_int(r2.y) : idx;
+          b2 = fminf(b2, fmaxf(b1, s));  // s < b1: the old best becomes second; else min(b2, s)
+          b1 = fminf(b1, s);
         }
         __syncwarp();
       }
