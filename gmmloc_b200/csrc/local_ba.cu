@@ -33,6 +33,7 @@
 // shared memory and add them in rank order in every CTA (so all CTAs take the same branches, bit for bit), and the
 // dense Cholesky of the small reduced system stays inside CTA 0.
 #include <cooperative_groups.h>
+#include <cstdio>
 #include <math_constants.h>
 
 #include "gn_common.cuh"
@@ -51,6 +52,8 @@ constexpr int pH = 0, pB = 6, pHi = 9, pY = 15, pDx = 18, pTr = 21, kPtWs = 24;
 constexpr int qR = 0, qRt = 9, qTr = 18, kPoseWs = 25;
 // per-free-pose workspace layout
 constexpr int fH = 0, fB = 21, kFreeWs = 27;
+constexpr int kFoldParts = 8;                          // warps that share one free pose's observation list
+constexpr int kFreeStride = kFreeWs * (1 + kFoldParts);  // per free pose: Hpp / bp, then the partial sums of the fold
 
 __device__ __forceinline__ int sym6(int r, int c) {  // packed upper-triangle index of a symmetric 6x6
   if (r > c) { const int t = r; r = c; c = t; }
@@ -58,6 +61,25 @@ __device__ __forceinline__ int sym6(int r, int c) {  // packed upper-triangle in
 }
 
 namespace cg = cooperative_groups;
+
+#ifdef GMMLOC_BA_PROFILE
+// phase timers of one window (debug builds: tools/build_variant.sh baprof -DGMMLOC_BA_PROFILE): nanoseconds per phase,
+// accumulated by thread 0 of the team, printed by the launcher
+__device__ unsigned long long g_ba_prof[16];
+__device__ __forceinline__ unsigned long long ba_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define BA_T(i)                                 \
+  if (gtid == 0) {                              \
+    const unsigned long long t1__ = ba_now();   \
+    g_ba_prof[i] += t1__ - ba_t0;               \
+    ba_t0 = t1__;                               \
+  }
+#else
+#define BA_T(i)
+#endif
 
 // The threads that solve one window: one CTA (kCl = 1) or a thread-block cluster of kCl CTAs.
 template <int kCl>
@@ -308,7 +330,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
   p.wp = a.w_pt + d.pt_off * kPtWs;
   p.slevel = a.str_level + d.pt_off;
   p.wq = a.w_pose + d.pose_off * kPoseWs;
-  p.wf = a.w_free + d.free_off * kFreeWs;
+  p.wf = a.w_free + d.free_off * kFreeStride;
   p.S = a.S + d.S_off;
   const int n = d.n, nf = d.nf;
   p.rhs = p.S + (size_t)n * n;
@@ -374,8 +396,12 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
     double lambda = 0.0, ni = 2.0;
     bool ok = true;
     int it = 0;
+#ifdef GMMLOC_BA_PROFILE
+    unsigned long long ba_t0 = ba_now();
+#endif
     for (; it < max_it && !terminate() && ok; ++it) {  // SparseOptimizer::optimize: i < iterations && !terminate() && ok
       double cur_chi = active_errors(a, p, red, p.pose, 7, p.wq + qR, kPoseWs, p.pts, 3, robust, s_prior_inv, s_prior_info);
+      BA_T(0)
       // ---- linearise every active edge at the current estimate ----
       for (int e = gtid; e < d.E; e += kGT) {
         if (p.level[e]) continue;
@@ -473,6 +499,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
         }
       }
       red.sync();
+      BA_T(1)
       // ---- per point: Hll, bl (reprojection pieces of its observations + structure edge) ----
       double md = 0.0;
       for (int l = gtid; l < d.L; l += kGT) {
@@ -510,28 +537,42 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
         for (int q = 0; q < 3; ++q) w[pB + q] = b[q];
         md = fmax(md, fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5]))));
       }
-      // ---- per free pose: Hpp (21) and bp (6) from its observations: one warp per pose, lanes stride over the
-      // pose's observation list, fixed-shape shuffle tree (deterministic) ----
-      for (int f = gtid >> 5; f < nf; f += kGW) {
+      // ---- per free pose: Hpp (21) and bp (6) from its observations.  The walk over a pose's observation list is a chain of
+      // dependent L2 round trips (index -> level -> 27 doubles): with one warp per pose nine warps worked for 47 us of every
+      // LM iteration of a lone window while the rest of the team waited.  kFoldParts warps now share a list (warp `part`
+      // takes the entries part * 32 + lane, + 32 kFoldParts, ...), write their 27 partial sums, and after a team barrier
+      // one thread per value adds the partials in part order: deterministic, independent of the cluster size ----
+      for (int task = gtid >> 5; task < nf * kFoldParts; task += kGW) {
+        const int f = task / kFoldParts, part = task % kFoldParts;
         double acc[kFreeWs];
 #pragma unroll
         for (int q = 0; q < kFreeWs; ++q) acc[q] = 0.0;
-        for (int j = p.kf_ptr[f] + (tid & 31); j < p.kf_ptr[f + 1]; j += 32) {
+        for (int j = p.kf_ptr[f] + part * 32 + (tid & 31); j < p.kf_ptr[f + 1]; j += 32 * kFoldParts) {
           const int e = p.kf_obs[j];
-          if (p.level[e]) continue;
           const double* o = p.wo + (size_t)e * kObsWs;  // oA = 0 .. 20, oG = 21 .. 26: same order as fH, fB
+          const bool on = !p.level[e];
 #pragma unroll
-          for (int q = 0; q < kFreeWs; ++q) acc[q] += o[q];
+          for (int q = 0; q < kFreeWs; ++q) acc[q] += on ? o[q] : 0.0;
         }
 #pragma unroll
         for (int q = 0; q < kFreeWs; ++q) {
           double v = acc[q];
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-          if ((tid & 31) == 0) p.wf[(size_t)f * kFreeWs + q] = v;
+          if ((tid & 31) == 0) p.wf[(size_t)f * kFreeStride + kFreeWs * (1 + part) + q] = v;
         }
       }
       red.sync();
+      for (int i = gtid; i < nf * kFreeWs; i += kGT) {
+        const int f = i / kFreeWs, q = i % kFreeWs;
+        const double* pp = p.wf + (size_t)f * kFreeStride + kFreeWs + q;
+        double v = pp[0];
+#pragma unroll
+        for (int part = 1; part < kFoldParts; ++part) v += pp[kFreeWs * part];
+        p.wf[(size_t)f * kFreeStride + q] = v;
+      }
+      red.sync();
+      BA_T(2)
       if (gtid == 0 && d.prior >= 0 && p.fidx[d.prior] >= 0) {  // EdgeSE3QuatPrior, factors.cpp:31-53
         const int f = p.fidx[d.prior];
         double delta[7], dv[6], Jr[36], Tinv[7], Ad[36], J[36], Rinv[9];
@@ -563,7 +604,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
             for (int k = 0; k < 6; ++k) s += Jr[r * 6 + k] * Ad[k * 6 + c];
             J[r * 6 + c] = s;
           }
-        double* w = p.wf + (size_t)f * kFreeWs;
+        double* w = p.wf + (size_t)f * kFreeStride;
         int q = 0;
         for (int r = 0; r < 6; ++r) {
           for (int c = r; c < 6; ++c) {
@@ -579,7 +620,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
       red.sync();
       if (it == 0) {  // computeLambdaInit: tau * max |diagonal|, tau = 1e-5
         for (int f = gtid; f < nf; f += kGT) {
-          const double* w = p.wf + (size_t)f * kFreeWs + fH;
+          const double* w = p.wf + (size_t)f * kFreeStride + fH;
           for (int r = 0; r < 6; ++r) md = fmax(md, fabs(w[sym6(r, r)]));
         }
         lambda = 1e-5 * red.max(md);
@@ -588,6 +629,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
       double rho = 0.0;
       int qmax = 0;
       do {
+        BA_T(3)
         // ---- Schur complement at damping lambda ----
         bool good = true;
         for (int l = gtid; l < d.L; l += kGT) {
@@ -608,6 +650,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
         }
         good = red.all_ok(good) != 0;  // also orders the Hinv writes before the block tasks
         if (good) {
+          BA_T(4)
           // per observation on a free pose: T = Hpl Hll^-1 (6x3) and Hpl (Hll^-1 bl) (6)
           for (int e = gtid; e < d.E; e += kGT) {
             if (p.level[e] || p.fidx[p.obs_kf[e]] < 0) continue;
@@ -625,63 +668,102 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
             }
           }
           red.sync();
-          // reduced system: one WARP per ROW of every lower 6x6 block; the lanes stride over the block's contribution list
-          // (a single thread per row walked ~2 500 pairs one dependent L2 round trip at a time: that loop, not the sweeps
-          // over observations, was the bulk of an LM iteration of a lone window) and fold with a fixed shuffle tree
+          BA_T(5)
+          // reduced system: one WARP per HALF (three rows) of every lower 6x6 block; the lanes stride over the block's
+          // contribution list and fold with a fixed shuffle tree.  (History: one thread per row walked ~2 500 pairs one
+          // dependent L2 round trip at a time; one warp per row then read every pair's 6x3 W block six times over and still
+          // took 8.9 of the 20.9 ms of a lone 12-keyframe window — the walk is latency-bound, so a task now carries three
+          // rows' worth of independent loads per list entry and the whole system is one round of warps.)  The order of the
+          // additions per entry of S is unchanged: lane l sums entries l, l + 32, ... in list order, then the tree.
           const int nblk = nf * (nf + 1) / 2;
-          for (int task = gtid >> 5; task < nblk * 6; task += kGW) {
-            const int blk = task / 6, r = task % 6;
+          for (int task = gtid >> 5; task < nblk * 2; task += kGW) {
+            const int blk = task >> 1, r0 = 3 * (task & 1);
             // blk = fi (fi + 1) / 2 + fj, fj <= fi
             int fi = (int)((sqrt(8.0 * blk + 1.0) - 1.0) * 0.5);
             while ((fi + 1) * (fi + 2) / 2 <= blk) ++fi;
             while (fi * (fi + 1) / 2 > blk) --fi;
             const int fj = blk - fi * (fi + 1) / 2;
-            double acc[6] = {0, 0, 0, 0, 0, 0};
-            const int j1 = p.blk_ptr[blk + 1];
-#pragma unroll 2
-            for (int j = p.blk_ptr[blk] + (tid & 31); j < j1; j += 32) {
-              const int2 ab = p.contrib[j];
-              if (p.level[ab.x] | p.level[ab.y]) continue;
-              const double* Ta = p.wo + (size_t)ab.x * kObsWs + oT + r * 3;
-              const double* Wb = p.wo + (size_t)ab.y * kObsWs + oW;
-              const double t0 = Ta[0], t1 = Ta[1], t2 = Ta[2];
+            double acc[18];
 #pragma unroll
-              for (int c = 0; c < 6; ++c) acc[c] -= (t0 * Wb[c * 3] + t1 * Wb[c * 3 + 1]) + t2 * Wb[c * 3 + 2];
+            for (int q = 0; q < 18; ++q) acc[q] = 0.0;
+            const int j1 = p.blk_ptr[blk + 1];
+            // the next entry's observation pair is requested while this one is worked on, and the data are loaded next to
+            // the level flags instead of behind them: one dependent round trip per entry instead of three
+            int j = p.blk_ptr[blk] + (tid & 31);
+            int2 ab = (j < j1) ? p.contrib[j] : make_int2(0, 0);
+            while (j < j1) {
+              const int jn = j + 32;
+              const int2 abn = (jn < j1) ? p.contrib[jn] : ab;
+              const bool on = !(p.level[ab.x] | p.level[ab.y]);
+              const double* Ta = p.wo + (size_t)ab.x * kObsWs + oT + r0 * 3;
+              const double* Wb = p.wo + (size_t)ab.y * kObsWs + oW;
+              double wb[18], ta[9];
+#pragma unroll
+              for (int q = 0; q < 18; ++q) wb[q] = Wb[q];
+#pragma unroll
+              for (int q = 0; q < 9; ++q) ta[q] = Ta[q];
+              if (on) {
+#pragma unroll
+                for (int rr = 0; rr < 3; ++rr) {
+                  const double t0 = ta[rr * 3], t1 = ta[rr * 3 + 1], t2 = ta[rr * 3 + 2];
+#pragma unroll
+                  for (int c = 0; c < 6; ++c) acc[rr * 6 + c] -= (t0 * wb[c * 3] + t1 * wb[c * 3 + 1]) + t2 * wb[c * 3 + 2];
+                }
+              }
+              j = jn;
+              ab = abn;
             }
 #pragma unroll
-            for (int c = 0; c < 6; ++c) {
-              double v = acc[c];
+            for (int rr = 0; rr < 3; ++rr) {
+              const int r = r0 + rr;
 #pragma unroll
-              for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-              if ((tid & 31) == 0) {
-                if (fi == fj) v += p.wf[(size_t)fi * kFreeWs + fH + sym6(r, c)] + (r == c ? lambda : 0.0);
-                p.S[(size_t)(6 * fi + r) * n + 6 * fj + c] = v;
+              for (int c = 0; c < 6; ++c) {
+                double v = acc[rr * 6 + c];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if ((tid & 31) == 0) {
+                  if (fi == fj) v += p.wf[(size_t)fi * kFreeStride + fH + sym6(r, c)] + (r == c ? lambda : 0.0);
+                  p.S[(size_t)(6 * fi + r) * n + 6 * fj + c] = v;
+                }
               }
             }
           }
-          // right-hand side: one warp per free pose
-          for (int f = gtid >> 5; f < nf; f += kGW) {
+          // right-hand side: kFoldParts warps per free pose sum their share of the pose's observation list (partials into
+          // the fold scratch of w_free, free again by now); CTA 0 adds them in part order before it factorises
+          for (int task = gtid >> 5; task < nblk * 2 + nf * kFoldParts; task += kGW) {  // one task list with the blocks above
+            if (task < nblk * 2) continue;
+            const int t = task - nblk * 2, f = t / kFoldParts, part = t % kFoldParts;
             double acc[6] = {0, 0, 0, 0, 0, 0};
-            for (int j = p.kf_ptr[f] + (tid & 31); j < p.kf_ptr[f + 1]; j += 32) {
+            for (int j = p.kf_ptr[f] + part * 32 + (tid & 31); j < p.kf_ptr[f + 1]; j += 32 * kFoldParts) {
               const int e = p.kf_obs[j];
-              if (p.level[e]) continue;
               const double* gy = p.wo + (size_t)e * kObsWs + oGy;
+              const bool on = !p.level[e];
 #pragma unroll
-              for (int r = 0; r < 6; ++r) acc[r] += gy[r];
+              for (int r = 0; r < 6; ++r) acc[r] += on ? gy[r] : 0.0;
             }
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
               double v = acc[r];
 #pragma unroll
               for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-              if ((tid & 31) == 0) p.rhs[6 * f + r] = p.wf[(size_t)f * kFreeWs + fB + r] - v;
+              if ((tid & 31) == 0) p.wf[(size_t)f * kFreeStride + kFreeWs * (1 + part) + r] = v;
             }
           }
           red.sync();
+          BA_T(6)
           // ---- left-looking Cholesky of the lower triangle; the rhs rides along as row n (forward solve) ----
           // The reduced system is small (n = 6 free poses): its ~3 n barriers stay inside CTA 0 of the team; the other
           // CTAs wait at the team-wide vote below.
           if (crank == 0) {
+            for (int i = tid; i < n; i += kBaT) {
+              const int f = i / 6, r = i % 6;
+              const double* pp = p.wf + (size_t)f * kFreeStride + kFreeWs + r;
+              double v = pp[0];
+#pragma unroll
+              for (int part = 1; part < kFoldParts; ++part) v += pp[kFreeWs * part];
+              p.rhs[i] = p.wf[(size_t)f * kFreeStride + fB + r] - v;
+            }
+            __syncthreads();
             for (int k = 0; k < n && good; ++k) {
               for (int i = k + tid; i <= n; i += kBaT) {
                 double* row = (i < n) ? p.S + (size_t)i * n : p.rhs;
@@ -724,6 +806,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
           }
           good = red.all_ok(good) != 0;  // CTA 0's verdict reaches the whole team; also publishes dxp
         }
+        BA_T(7)
         // ---- landmark back-substitution, trial state ----
         if (good) {
           bool fin = true;
@@ -753,6 +836,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
           }
           good = red.all_ok(fin) != 0;
         }
+        BA_T(8)
         double tmp_chi = 1.7976931348623157e308, scale = 0.0;
         if (good) {
           for (int i = gtid; i < d.P; i += kGT) {
@@ -771,7 +855,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
           double part = 0.0;
           for (int i = gtid; i < n; i += kGT) {
             const double dx = p.dxp[i];
-            part += dx * (lambda * dx + p.wf[(size_t)(i / 6) * kFreeWs + fB + i % 6]);
+            part += dx * (lambda * dx + p.wf[(size_t)(i / 6) * kFreeStride + fB + i % 6]);
           }
           for (int l = gtid; l < d.L; l += kGT) {
             const double* w = p.wp + (size_t)l * kPtWs;
@@ -779,6 +863,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
           }
           scale = red.sum(part);
         }
+        BA_T(9)
         rho = cur_chi - tmp_chi;
         rho /= scale + 1e-3;
         if (rho > 0 && isfinite(tmp_chi) && good) {
@@ -802,6 +887,7 @@ __global__ void __launch_bounds__(kBaT) local_ba_kernel(const BaArgs a) {
           if (!isfinite(lambda)) break;
         }
         ++qmax;
+        BA_T(10)
       } while (rho < 0 && qmax < 10 && !terminate());  // OptimizationAlgorithmLevenberg::solve
       if (qmax == 10 || rho == 0 || !isfinite(lambda)) ok = false;
     }
@@ -894,17 +980,37 @@ cudaError_t launch_local_ba(const BaArgs& a, cudaStream_t stream, int cluster) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   int cl = cluster > 0 ? cluster : (a.B * 8 <= sms ? 8 : a.B * 4 <= sms ? 4 : a.B * 2 <= sms ? 2 : 1);
-  switch (cl) {
-    case 8: return launch_ba_t<8>(a, stream);
-    case 4: return launch_ba_t<4>(a, stream);
-    case 2: return launch_ba_t<2>(a, stream);
-    default: return launch_ba_t<1>(a, stream);
+#ifdef GMMLOC_BA_PROFILE
+  {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_ba_prof, z, sizeof z);
   }
+#endif
+  cudaError_t e;
+  switch (cl) {
+    case 8: e = launch_ba_t<8>(a, stream); break;
+    case 4: e = launch_ba_t<4>(a, stream); break;
+    case 2: e = launch_ba_t<2>(a, stream); break;
+    default: e = launch_ba_t<1>(a, stream); break;
+  }
+#ifdef GMMLOC_BA_PROFILE
+  if (e == cudaSuccess) {
+    cudaStreamSynchronize(stream);
+    unsigned long long t[16];
+    cudaMemcpyFromSymbol(t, g_ba_prof, sizeof t);
+    static const char* names[11] = {"poll+active_errors", "linearise", "Hll/Hpp", "prior+lambda0", "Hll inverse", "T per obs",
+                                    "block rows+rhs", "cholesky+backsub", "landmark backsub", "trial errors+scale", "accept/reject"};
+    std::fprintf(stderr, "BA profile (cluster %d):", cl);
+    for (int i = 0; i < 11; ++i) std::fprintf(stderr, " %s %.3f ms |", names[i], t[i] * 1e-6);
+    std::fprintf(stderr, "\n");
+  }
+#endif
+  return e;
 }
 
 int local_ba_obs_ws() { return kObsWs; }
 int local_ba_pt_ws() { return kPtWs; }
 int local_ba_pose_ws() { return kPoseWs; }
-int local_ba_free_ws() { return kFreeWs; }
+int local_ba_free_ws() { return kFreeStride; }
 
 }  // namespace gmmloc
