@@ -913,21 +913,17 @@ size_t frame_gn_stream_scratch_bytes(int N) {
   return (size_t)2 * sms * stream_slice(N) + 16;
 }
 
-size_t frame_gn_stream_prep_bytes(int B, int N) { return (size_t)B * pack_layout(N).stride + (size_t)B * N + (size_t)B * 64 + 64; }
+// Batches beyond kSubBatch frames run as consecutive sub-batches on the stream, so the packed-frame buffer is bounded
+// (kSubBatch x ~69 B per landmark: 1.1 GB at N = 2 000) however large B is.
+constexpr int kSubBatch = 8192;
+size_t frame_gn_stream_prep_bytes(int B, int N) {
+  const size_t b = (size_t)std::min(B, kSubBatch);
+  return b * pack_layout(N).stride + b * N + b * 64 + 64;
+}
 
-// d_counters: a.B + 2 ints (frame counter, number of frames handed to the fp64 kernel, their indices)
-cudaError_t launch_frame_gn_stream(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
-                                   unsigned char* prep_ws, size_t prep_ws_bytes, cudaStream_t stream) {
-  if (a.B <= 0) return cudaSuccess;
+static cudaError_t launch_stream_sub(const FrameArgs& a, const float* gn_tab, int* d_counters, unsigned char* st, size_t st_bytes,
+                                     unsigned char* pack, int sms, cudaStream_t stream) {
   const size_t need = (size_t)a.B * pack_layout(a.N).stride;
-  if (prep_ws == nullptr || store_ws == nullptr || need == 0) return cudaErrorInvalidValue;
-  unsigned char* pack = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(prep_ws) + 15) & ~(uintptr_t)15);
-  if ((size_t)(pack - prep_ws) + need + (size_t)a.B * a.N + 16 + (size_t)a.B * 64 > prep_ws_bytes) return cudaErrorInvalidValue;
-  unsigned char* st = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(store_ws) + 15) & ~(uintptr_t)15);
-  const size_t st_bytes = store_ws_bytes - (size_t)(st - reinterpret_cast<unsigned char*>(store_ws));
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   uint8_t* flags = pack + need;  // B x N class bytes behind the packed frames, then 8 doubles per frame
   double* fpose = reinterpret_cast<double*>(flags + (((size_t)a.B * a.N + 15) & ~(size_t)15));
   frame_pose_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a, fpose);
@@ -945,6 +941,37 @@ cudaError_t launch_frame_gn_stream(const FrameArgs& a, const float* gn_tab, int*
   e = launch_stream_t<384, 1>(a, d_counters, st, st_bytes, pack, stream, &fits);
   if (e != cudaSuccess || fits) return e;
   return cudaErrorInvalidValue;  // the caller checks frame_gn_stream_limit_points() and sizes the scratch: not reached
+}
+
+// d_counters: min(a.B, kSubBatch) + 2 ints (frame counter, number of frames handed to the fp64 kernel, their indices)
+cudaError_t launch_frame_gn_stream(const FrameArgs& a, const float* gn_tab, int* d_counters, float* store_ws, size_t store_ws_bytes,
+                                   unsigned char* prep_ws, size_t prep_ws_bytes, cudaStream_t stream) {
+  if (a.B <= 0) return cudaSuccess;
+  if (prep_ws == nullptr || store_ws == nullptr || a.N <= 0) return cudaErrorInvalidValue;
+  unsigned char* pack = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(prep_ws) + 15) & ~(uintptr_t)15);
+  if ((size_t)(pack - prep_ws) + frame_gn_stream_prep_bytes(a.B, a.N) - 64 + 16 > prep_ws_bytes) return cudaErrorInvalidValue;
+  unsigned char* st = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(store_ws) + 15) & ~(uintptr_t)15);
+  const size_t st_bytes = store_ws_bytes - (size_t)(st - reinterpret_cast<unsigned char*>(store_ws));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  for (int f0 = 0; f0 < a.B; f0 += kSubBatch) {
+    FrameArgs s = a;
+    s.B = std::min(kSubBatch, a.B - f0);
+    const size_t m0 = (size_t)f0 * a.N;
+    s.pose0 = a.pose0 + (size_t)f0 * 7;
+    s.pts_w = a.pts_w + 3 * m0;
+    s.obs = a.obs + 3 * m0;
+    s.octave = a.octave + m0;
+    s.assign = a.assign + m0;
+    s.pose_out = a.pose_out + (size_t)f0 * 7;
+    s.pts_out = a.pts_out ? a.pts_out + 3 * m0 : nullptr;
+    s.outlier = a.outlier ? a.outlier + m0 : nullptr;
+    s.status = a.status + f0;
+    const cudaError_t e = launch_stream_sub(s, gn_tab, d_counters, st, st_bytes, pack, sms, stream);
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
 }
 
 }  // namespace gmmloc

@@ -390,6 +390,36 @@ def test_frames_solve_pipelined_host_path_equals_single_chunks(gpu, B):
             assert np.array_equal(big[k][lo:hi], part[k]), (k, lo)
 
 
+def test_frames_solve_async_runs_large_batches_in_sub_batches(gpu):
+    """More than 8 192 frames in one gmmloc_frames_solve_async call: the streamed frame GN packs and solves them in
+    sub-batches (bounded workspace); results equal those of separate calls on the parts."""
+    import torch
+    g, ctx = gpu
+    B, N = 8300, 24
+    mean, cov = synth.make_map(600, 0.5, seed=13)
+    m = g.GMM(mean, cov)
+    fr = synth.make_frames(mean, cov, 100, N, seed=13)
+    fr = {k: np.concatenate([fr[k]] * (B // 100)) for k in ("pose0", "pts_w", "obs", "octave")}
+    fr["pose0"][8250, 4] += 0.01  # a frame beyond the first sub-batch that is not a copy of an earlier one
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in fr.items()}
+    o_pose = torch.zeros((B, 7), dtype=torch.float64, device=dev)
+    o_assign = torch.empty((B, N), dtype=torch.int32, device=dev)
+    o_outl = torch.empty((B, N), dtype=torch.uint8, device=dev)
+    o_status = torch.full((B,), -7, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ctx.frames_solve_async(m, g.v1_camera(), g.default_params(), d["pose0"].data_ptr(), d["pts_w"].data_ptr(), d["obs"].data_ptr(),
+                           d["octave"].data_ptr(), B, N, o_pose.data_ptr(), 0, o_assign.data_ptr(), o_outl.data_ptr(), o_status.data_ptr())
+    torch.cuda.synchronize()
+    assert ctx.last_gn_kernel() == "stream"
+    for lo, hi in ((0, 4), (8188, 8196), (8248, 8252), (B - 3, B)):
+        part = ctx.frames_solve(m, fr["pose0"][lo:hi], fr["pts_w"][lo:hi], fr["obs"][lo:hi], fr["octave"][lo:hi])
+        assert np.array_equal(o_pose[lo:hi].cpu().numpy(), part["pose"]), lo
+        assert np.array_equal(o_assign[lo:hi].cpu().numpy(), part["assign"])
+        assert np.array_equal(o_outl[lo:hi].cpu().numpy(), part["outlier"])
+        assert np.array_equal(o_status[lo:hi].cpu().numpy(), part["status"])
+
+
 # ---------------------------------------------------------------- triangulation solves (a10)
 def test_optimize_triangulation_bit_exact(gpu, oracle, golden_maps):
     g, ctx = gpu
