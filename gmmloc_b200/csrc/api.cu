@@ -745,7 +745,7 @@ gmmloc_status_t gmmloc_associate_async(gmmloc_ctx_t* ctx, const gmmloc_map_t* ma
   int32_t* sort_perm = nullptr;
   if (map->d.grid.nlev > 0) {  // scratch of the cell-sorted grid scan
     const GridLevel& G0 = map->d.grid.lev[0];
-    CU(ctx->L().sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2)));
+    CU(ctx->L().sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2 + ((size_t)G0.nx * G0.ny * G0.nz + 1) / 4096 + 4)));
     CU(ctx->L().sort_perm.reserve(16 * (size_t)M));  // one float4 per landmark
     sort_cnt = ctx->L().sort_cnt.as<int>();
     sort_perm = ctx->L().sort_perm.as<int32_t>();
@@ -988,7 +988,7 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     if (frame_gn_mixed_prep_bytes(maxc, N, ctx->opt_gn_prep)) CU(ln.gn_prep.reserve(frame_gn_mixed_prep_bytes(maxc, N, ctx->opt_gn_prep)));
     if (map->d.grid.nlev > 0) {
       const GridLevel& G0 = map->d.grid.lev[0];
-      CU(ln.sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2)));
+      CU(ln.sort_cnt.reserve(sizeof(int) * ((size_t)G0.nx * G0.ny * G0.nz + 2 + ((size_t)G0.nx * G0.ny * G0.nz + 1) / 4096 + 4)));
       CU(ln.sort_perm.reserve(16 * mc));
     }
     if ((size_t)N > frame_gn_smem_limit_points()) {

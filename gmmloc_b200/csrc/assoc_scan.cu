@@ -507,48 +507,67 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const ScanArgs a, int
   if (c < 0) c = (long long)G.nx * G.ny * G.nz;
   sorted[atomicAdd(cur + c, 1)] = make_float4(px, py, pz, __int_as_float((int)i));
 }
-// in-place exclusive scan of n ints by one CTA (n <= ~4 M: a few tens of microseconds)
-__global__ void __launch_bounds__(1024) excl_scan_kernel(int* __restrict__ d, int n) {
+// In-place exclusive scan of n ints in two launches of one CTA per 4 096-entry tile: (1) every tile is scanned on its own
+// and leaves its total in tile_tot; (2) every tile adds the sum of the totals before it.  (One CTA walking all the tiles
+// took 30 us for the 94 k cells of the C2 grid — a fixed cost paid by every pipeline chunk of the host entry point.)
+__global__ void __launch_bounds__(1024) excl_scan_tiles_kernel(int* __restrict__ d, int n, int* __restrict__ tile_tot) {
   __shared__ int wsum[32];
-  __shared__ int carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int carry = 0;
-  for (int base = 0; base < n; base += 4096) {
-    const int idx = base + tid * 4;
-    int v[4];
+  const int idx = blockIdx.x * 4096 + tid * 4;
+  int v[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = (idx + q < n) ? d[idx + q] : 0;
-    const int t = v[0] + v[1] + v[2] + v[3];
-    int inc = t;
+  for (int q = 0; q < 4; ++q) v[q] = (idx + q < n) ? d[idx + q] : 0;
+  const int t = v[0] + v[1] + v[2] + v[3];
+  int inc = t;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, off);
+    if (lane >= off) inc += u;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    const int wv = wsum[lane];
+    int winc = wv;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-      const int u = __shfl_up_sync(0xffffffffu, inc, off);
-      if (lane >= off) inc += u;
+      const int u = __shfl_up_sync(0xffffffffu, winc, off);
+      if (lane >= off) winc += u;
     }
-    if (lane == 31) wsum[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-      const int wv = wsum[lane];
-      int winc = wv;
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, winc, off);
-        if (lane >= off) winc += u;
-      }
-      wsum[lane] = winc - wv;
-    }
-    __syncthreads();
-    int ex = carry + wsum[warp] + inc - t;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (idx + q < n) d[idx + q] = ex;
-      ex += v[q];
-    }
-    if (tid == 1023) carry_s = ex;
-    __syncthreads();
-    carry = carry_s;
-    __syncthreads();
+    wsum[lane] = winc - wv;
+    if (lane == 31) tile_tot[blockIdx.x] = winc;
   }
+  __syncthreads();
+  int ex = wsum[warp] + inc - t;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (idx + q < n) d[idx + q] = ex;
+    ex += v[q];
+  }
+}
+__global__ void __launch_bounds__(1024) excl_scan_add_kernel(int* __restrict__ d, int n, const int* __restrict__ tile_tot) {
+  __shared__ int wsum[32];
+  __shared__ int s_off;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int part = 0;
+  for (int u = tid; u < (int)blockIdx.x; u += 1024) part += tile_tot[u];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+  if (lane == 0) wsum[warp] = part;
+  __syncthreads();
+  if (warp == 0) {
+    int w = wsum[lane];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) w += __shfl_xor_sync(0xffffffffu, w, off);
+    if (lane == 0) s_off = w;
+  }
+  __syncthreads();
+  const int off = s_off;
+  if (off == 0) return;
+  const int idx = blockIdx.x * 4096 + tid * 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (idx + q < n) d[idx + q] += off;
 }
 
 template <int THREADS, bool SORTED>
@@ -768,7 +787,8 @@ __global__ void __launch_bounds__(128) assoc_grid_rerank_kernel(const ScanArgs a
   }
 }
 
-// sort_cnt: ncell0 + 1 ints, sort_perm: M x 16 bytes (one float4 per landmark) — or null for the natural-order kernel
+// sort_cnt: ncell0 + 2 ints + one int per 4 096 cells (tile totals of the scan), sort_perm: M x 16 bytes (one float4 per
+// landmark) — or null for the natural-order kernel
 cudaError_t launch_scan_grid(ScanArgs a, int* sort_cnt, int32_t* sort_perm, cudaStream_t stream, int* launches) {
   const unsigned grid = (unsigned)((a.M + 255) / 256);
   const GridLevel& G = a.grid.lev[0];
@@ -777,11 +797,16 @@ cudaError_t launch_scan_grid(ScanArgs a, int* sort_cnt, int32_t* sort_perm, cuda
     cudaError_t e;
     if ((e = cudaMemsetAsync(sort_cnt, 0, sizeof(int) * (size_t)(ncell + 1), stream)) != cudaSuccess) return e;
     grid_hist_kernel<<<grid, 256, 0, stream>>>(a, sort_cnt);
-    excl_scan_kernel<<<1, 1024, 0, stream>>>(sort_cnt, (int)(ncell + 1));
+    {
+      const int n = (int)(ncell + 1), tiles = (n + 4095) / 4096;
+      int* tile_tot = sort_cnt + ncell + 2;  // behind the counters (api.cu reserves the room)
+      excl_scan_tiles_kernel<<<tiles, 1024, 0, stream>>>(sort_cnt, n, tile_tot);
+      excl_scan_add_kernel<<<tiles, 1024, 0, stream>>>(sort_cnt, n, tile_tot);
+    }
     grid_scatter_kernel<<<grid, 256, 0, stream>>>(a, sort_cnt, reinterpret_cast<float4*>(sort_perm));
     a.sorted = reinterpret_cast<const float4*>(sort_perm);
     assoc_grid_kernel<256, true><<<grid, 256, 0, stream>>>(a);
-    if (launches) *launches += 3;
+    if (launches) *launches += 4;
     return cudaGetLastError();
   }
   a.sorted = nullptr;

@@ -700,7 +700,8 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
       }
 
       // ---- fp64 points (last class of the sorted frame), dealt round robin over the warps ----
-      for (int q = lane * kWarps + warp; q < n64; q += 32 * kWarps) {
+      // (from the LAST warp backwards: the chunks are dealt from warp 0, so the last warps are the ones with a chunk less)
+      for (int q = lane * kWarps + (kWarps - 1 - warp); q < n64; q += 32 * kWarps) {
         const int j = f64_begin + q;
         const uint8_t b = fl[j];
         const bool upd = do_update, accp = do_acc && (b & F_STR);
