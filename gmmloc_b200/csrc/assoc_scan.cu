@@ -491,21 +491,23 @@ __device__ __forceinline__ long long sort_cell(const ScanArgs& a, long long i) {
   const long long c = grid_cell(G, px, py, pz);
   return c >= 0 ? c : (long long)G.nx * G.ny * G.nz;  // last bucket: outside the grid / non-finite
 }
+// The histogram pass keeps what its atomic returns — the landmark's rank inside its cell — in the (not yet written)
+// assignment array, so that the scatter needs no second round of 8 M atomics: position = cell start + rank.
 __global__ void __launch_bounds__(256) grid_hist_kernel(const ScanArgs a, int* __restrict__ hist) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i < a.M) atomicAdd(hist + sort_cell(a, i), 1);
+  if (i < a.M) a.assign[i] = atomicAdd(hist + sort_cell(a, i), 1);
 }
 // The scatter writes the landmark ITSELF next to its original index (one float4 per landmark) so that the scan streams
 // its input coalesced: with an index-only permutation the scan gathered 12 B out of every 32-byte sector it fetched
 // (510 MB of DRAM reads for 98 MB of landmarks, profiles/assoc_grid_r01.txt).
-__global__ void __launch_bounds__(256) grid_scatter_kernel(const ScanArgs a, int* __restrict__ cur, float4* __restrict__ sorted) {
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const ScanArgs a, const int* __restrict__ cur, float4* __restrict__ sorted) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= a.M) return;
   const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
   const GridLevel& G = a.grid.lev[0];
   long long c = grid_cell(G, px, py, pz);
   if (c < 0) c = (long long)G.nx * G.ny * G.nz;
-  sorted[atomicAdd(cur + c, 1)] = make_float4(px, py, pz, __int_as_float((int)i));
+  sorted[__ldg(cur + c) + a.assign[i]] = make_float4(px, py, pz, __int_as_float((int)i));
 }
 // In-place exclusive scan of n ints in two launches of one CTA per 4 096-entry tile: (1) every tile is scanned on its own
 // and leaves its total in tile_tot; (2) every tile adds the sum of the totals before it.  (One CTA walking all the tiles
