@@ -858,7 +858,7 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
     CU(ctx->L().gn_prep.reserve(frame_gn_stream_prep_bytes(B, N)));
     CU(launch_frame_gn_stream(a, map->d.gn_tab, ctx->L().next_frame.as<int>(), ctx->L().gn_store.as<float>(), ctx->L().gn_store.cap,
                               ctx->L().gn_prep.as<unsigned char>(), ctx->L().gn_prep.cap, ctx->L().stream));
-    ctx->stats.kernel_launches += 4;  // + frame poses, classification, pack and the (normally empty) fp64 retry launch
+    ctx->stats.kernel_launches += 2;  // + the pack kernel and the (normally empty) fp64 retry launch
     ctx->last_gn = GMMLOC_GN_STREAM;
   } else if (gn_prec == GMMLOC_GN_WORLD && map->d.gn_tab != nullptr && N > 0 && (size_t)N <= frame_gn_world_limit_points()) {
     CU(ctx->L().next_frame.reserve(sizeof(int)));

@@ -160,6 +160,13 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 #ifndef GMMLOC_CLS_MINB
 #define GMMLOC_CLS_MINB 4
 #endif
+// Classification as its own one-thread-per-point kernel (1) or inside the per-frame pack kernel (0, default).  Measured on
+// C2 (4 096 frames): split 0.19 + 0.25 ms, fused 0.40 ms — the pack kernel's scattered stores, not the gate's dependent
+// gathers, set its pace, and the split pays a second pass over the landmarks.
+#ifndef GMMLOC_GNS_SPLIT_CLASSIFY
+#define GMMLOC_GNS_SPLIT_CLASSIFY 0
+#endif
+#if GMMLOC_GNS_SPLIT_CLASSIFY
 // per-frame constants of the classification (the normalised initial pose): third row of R, t_z, camera centre -R^T t
 __global__ void __launch_bounds__(128) frame_pose_kernel(const FrameArgs a, double* __restrict__ fpose) {
   const int f = blockIdx.x * 128 + threadIdx.x;
@@ -175,53 +182,57 @@ __global__ void __launch_bounds__(128) frame_pose_kernel(const FrameArgs a, doub
   o[6] = -(R[2] * q[4] + R[5] * q[5] + R[8] * q[6]);
   o[7] = 0.0;
 }
-__global__ void __launch_bounds__(256, GMMLOC_CLS_MINB) frame_classify_kernel(const FrameArgs a, const double* __restrict__ fpose,
-                                                                               uint8_t* __restrict__ flags) {
-  const int N = a.N;
+#endif
+// flag byte (low nibble) and class (bits 4..6) of one point; fp = the per-frame constants of frame_pose_kernel
+__device__ __forceinline__ uint8_t classify_point(const FrameArgs& a, const double* fp, float px, float py, float pz, float our, int k) {
   const FrameParamsDev& P = a.prm;
   const bool pose_free = P.factor_mode != GMMLOC_MODE_POINTS_ONLY;
   const bool pts_free = P.factor_mode != GMMLOC_MODE_POSE_ONLY;
-  const double view_cos_thresh = cos(78.0 * 3.14159265358979323846 / 180.0);  // gaussian_mixture.cpp:284
+  const double view_cos_thresh = 0.20791169081775934;  // cos(78 deg), gaussian_mixture.cpp:284
+  const double x0 = (double)px, x1 = (double)py, x2 = (double)pz;
+  uint8_t b = (our >= 0.0f) ? F_STEREO : 0;
+  if (k >= 0 && pts_free) {
+    if (a.is_deg[k]) {
+      b |= F_DEG;
+      const double* ax = a.axis + (size_t)k * 9;
+      const double* mu = a.mean + (size_t)k * 3;
+      const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
+      if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;
+      const double p0 = mu[0] - fp[4], p1 = mu[1] - fp[5], p2 = mu[2] - fp[6];  // from the camera centre -R^T t
+      const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
+      if (view_cos < view_cos_thresh) b &= ~F_STR;
+    } else {
+      if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;
+    }
+  }
+  if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
+  int cls;
+  if (!(b & F_FREE)) {
+    cls = pose_free ? C_FIXED : C_OFF;
+  } else {
+    const double pzc = fp[0] * x0 + fp[1] * x1 + fp[2] * x2 + fp[3];
+    const double rx = x0 - fp[4], ry = x1 - fp[5], rz = x2 - fp[6];
+    if (!fp32_geometry_ok(pzc, rx * rx + ry * ry + rz * rz)) cls = C_F64;
+    else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_MSTR;  // a free monocular point always has F_STR
+    else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
+  }
+  return (uint8_t)(b | (cls << 4));
+}
+#if GMMLOC_GNS_SPLIT_CLASSIFY
+__global__ void __launch_bounds__(256, GMMLOC_CLS_MINB) frame_classify_kernel(const FrameArgs a, const double* __restrict__ fpose,
+                                                                               uint8_t* __restrict__ flags) {
+  const int N = a.N;
   const long long total = (long long)a.B * N;
   for (long long gi = (long long)blockIdx.x * 256 + threadIdx.x; gi < total; gi += (long long)gridDim.x * 256) {
     const int f = (int)(gi / N);
-    const float px = __ldg(a.pts_w + gi * 3), py = __ldg(a.pts_w + gi * 3 + 1), pz = __ldg(a.pts_w + gi * 3 + 2);
-    const float our = __ldg(a.obs + gi * 3 + 2);
-    const int k = __ldg(a.assign + gi);
-    // per-frame constants written by frame_pose_kernel: third row of R (0..2), t_z (3), camera centre (4..6)
     double fp[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) fp[i] = __ldg(fpose + (size_t)f * 8 + i);
-    const double x0 = (double)px, x1 = (double)py, x2 = (double)pz;
-    uint8_t b = (our >= 0.0f) ? F_STEREO : 0;
-    if (k >= 0 && pts_free) {
-      if (a.is_deg[k]) {
-        b |= F_DEG;
-        const double* ax = a.axis + (size_t)k * 9;
-        const double* mu = a.mean + (size_t)k * 3;
-        const double e = dadd(dadd(dmul(ax[0], dsub(x0, mu[0])), dmul(ax[3], dsub(x1, mu[1]))), dmul(ax[6], dsub(x2, mu[2])));
-        if (dmul(e, e) <= P.tri_str_thresh) b |= F_STR;
-        const double p0 = mu[0] - fp[4], p1 = mu[1] - fp[5], p2 = mu[2] - fp[6];  // from the camera centre -R^T t
-        const double view_cos = fabs(p0 * ax[0] + p1 * ax[3] + p2 * ax[6]) / sqrt(p0 * p0 + p1 * p1 + p2 * p2);
-        if (view_cos < view_cos_thresh) b &= ~F_STR;
-      } else {
-        if (chi2_exact(a.mean + (size_t)k * 3, a.cov_inv + (size_t)k * 9, x0, x1, x2) <= P.mdist2_gate) b |= F_STR;
-      }
-    }
-    if (pts_free && ((b & F_STEREO) || (b & F_STR))) b |= F_FREE;
-    int cls;
-    if (!(b & F_FREE)) {
-      cls = pose_free ? C_FIXED : C_OFF;
-    } else {
-      const double pzc = fp[0] * x0 + fp[1] * x1 + fp[2] * x2 + fp[3];
-      const double rx = x0 - fp[4], ry = x1 - fp[5], rz = x2 - fp[6];
-      if (!fp32_geometry_ok(pzc, rx * rx + ry * ry + rz * rz)) cls = C_F64;
-      else if (!(b & F_STEREO)) cls = (b & F_DEG) ? C_MPLANE : C_MSTR;  // a free monocular point always has F_STR
-      else cls = (b & F_STR) ? ((b & F_DEG) ? C_STRP : C_STR) : C_PLAIN;
-    }
-    flags[gi] = (uint8_t)(b | (cls << 4));
+    flags[gi] = classify_point(a, fp, __ldg(a.pts_w + gi * 3), __ldg(a.pts_w + gi * 3 + 1), __ldg(a.pts_w + gi * 3 + 2),
+                               __ldg(a.obs + gi * 3 + 2), __ldg(a.assign + gi));
   }
 }
+#endif
 
 constexpr int kPackThreads = 256;
 __global__ void __launch_bounds__(kPackThreads) frame_pack_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
@@ -229,6 +240,7 @@ __global__ void __launch_bounds__(kPackThreads) frame_pack_kernel(const FrameArg
   constexpr int kWarps = kPackThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];  // flags by ORIGINAL index while the frame is being sorted
   __shared__ int s_cnt[C_COUNT * kMaxChunks * 8];
+  __shared__ double s_fp[8];                                // fused classification: third row of R, t_z, camera centre
   __shared__ int s_start[C_COUNT + 1], s_cb[C_COUNT + 1];  // first sorted position / first chunk of every class
   uint8_t* tmp = smem_raw;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -247,14 +259,28 @@ __global__ void __launch_bounds__(kPackThreads) frame_pack_kernel(const FrameArg
     uint8_t* goct = pf + L.oct;
     uint8_t* gfl = pf + L.fl;
     unsigned char* gcst = pf + L.cst;
-    const uint8_t* gflag = flags + (size_t)f * N;
+    const uint8_t* gflag = flags ? flags + (size_t)f * N : nullptr;
     __syncthreads();  // the previous frame is done with the shared arrays
-    // pass A: class histogram per (block, warp) from the flags frame_classify_kernel wrote
+    if (flags == nullptr) {  // fused classification (the default): per-frame constants as frame_pose_kernel computes them
+      if (tid == 0) {
+        double q[7], R[9];
+        for (int i = 0; i < 7; ++i) q[i] = a.pose0[(size_t)f * 7 + i];
+        quat_normalize(q);
+        quat_to_rot(q, R);
+        s_fp[0] = R[6]; s_fp[1] = R[7]; s_fp[2] = R[8]; s_fp[3] = q[6];
+        s_fp[4] = -(R[0] * q[4] + R[3] * q[5] + R[6] * q[6]);
+        s_fp[5] = -(R[1] * q[4] + R[4] * q[5] + R[7] * q[6]);
+        s_fp[6] = -(R[2] * q[4] + R[5] * q[5] + R[8] * q[6]);
+      }
+      __syncthreads();
+    }
+    // pass A: flags and class of every point — computed here (classify_point, the arithmetic of frame_classify_kernel) or
+    // read from the flags that kernel wrote — and the class histogram per (block, warp)
     for (int c = 0; c < nblocks; ++c) {
       const int i = c * kPackThreads + tid;
       int cls = -1;
       if (i < N) {
-        const uint8_t b = gflag[i];
+        const uint8_t b = gflag ? gflag[i] : classify_point(a, s_fp, pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], obs[i * 3 + 2], asg[i]);
         tmp[i] = b;
         cls = b >> 4;
       }
@@ -926,6 +952,7 @@ static cudaError_t launch_stream_sub(const FrameArgs& a, const float* gn_tab, in
                                      unsigned char* pack, int sms, cudaStream_t stream) {
   const size_t need = (size_t)a.B * pack_layout(a.N).stride;
   uint8_t* flags = pack + need;  // B x N class bytes behind the packed frames, then 8 doubles per frame
+#if GMMLOC_GNS_SPLIT_CLASSIFY
   double* fpose = reinterpret_cast<double*>(flags + (((size_t)a.B * a.N + 15) & ~(size_t)15));
   frame_pose_kernel<<<(a.B + 127) / 128, 128, 0, stream>>>(a, fpose);
   {
@@ -933,6 +960,9 @@ static cudaError_t launch_stream_sub(const FrameArgs& a, const float* gn_tab, in
     const int grid = (int)std::min<long long>((total + 255) / 256, (long long)sms * 64);
     frame_classify_kernel<<<grid, 256, 0, stream>>>(a, fpose, flags);
   }
+#else
+  flags = nullptr;  // classification inside the pack kernel
+#endif
   frame_pack_kernel<<<std::min(a.B, sms * 8), kPackThreads, (size_t)((a.N + 15) & ~15), stream>>>(a, gn_tab, flags, pack);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
