@@ -235,7 +235,10 @@ __global__ void __launch_bounds__(256, GMMLOC_CLS_MINB) frame_classify_kernel(co
 #endif
 
 constexpr int kPackThreads = 256;
-__global__ void __launch_bounds__(kPackThreads) frame_pack_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
+#ifndef GMMLOC_PACK_MINB
+#define GMMLOC_PACK_MINB 5  // 51 registers: five CTAs per SM; measured 2.96 ms for the stage against 3.02 (four CTAs) and 3.00 (six, spills)
+#endif
+__global__ void __launch_bounds__(kPackThreads, GMMLOC_PACK_MINB) frame_pack_kernel(const FrameArgs a, const float* __restrict__ gn_tab,
                                                                   const uint8_t* __restrict__ flags, unsigned char* __restrict__ pack) {
   constexpr int kWarps = kPackThreads / 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];  // flags by ORIGINAL index while the frame is being sorted
