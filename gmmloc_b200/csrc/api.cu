@@ -929,7 +929,7 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     return v ? std::atoi(v) : ctx->opt_e2e_short_first;
   }();
   std::vector<int> cstart;
-  if (ctx->opt_e2e_taper && chunk_env <= 0 && !short_first && B >= 4 * chunk) {
+  if (ctx->opt_e2e_taper && !short_first && B >= 6 * 2 * sms + 2 * chunk) {
     // Tapered schedule (default for large batches): the call ends when the LAST chunk has been copied in, solved and copied
     // out, and it cannot start computing before the FIRST chunk has arrived — so both ends are short (one and two frames
     // per resident CTA) and only the middle runs full 6-frames-per-SM chunks.  With the copy-in as the longer stream
