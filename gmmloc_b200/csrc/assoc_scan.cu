@@ -491,11 +491,18 @@ __device__ __forceinline__ long long sort_cell(const ScanArgs& a, long long i) {
   const long long c = grid_cell(G, px, py, pz);
   return c >= 0 ? c : (long long)G.nx * G.ny * G.nz;  // last bucket: outside the grid / non-finite
 }
+#ifndef GMMLOC_SORT_RANK
+#define GMMLOC_SORT_RANK 1
+#endif
 // The histogram pass keeps what its atomic returns — the landmark's rank inside its cell — in the (not yet written)
 // assignment array, so that the scatter needs no second round of 8 M atomics: position = cell start + rank.
 __global__ void __launch_bounds__(256) grid_hist_kernel(const ScanArgs a, int* __restrict__ hist) {
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+#if GMMLOC_SORT_RANK
   if (i < a.M) a.assign[i] = atomicAdd(hist + sort_cell(a, i), 1);
+#else
+  if (i < a.M) atomicAdd(hist + sort_cell(a, i), 1);
+#endif
 }
 // The scatter writes the landmark ITSELF next to its original index (one float4 per landmark) so that the scan streams
 // its input coalesced: with an index-only permutation the scan gathered 12 B out of every 32-byte sector it fetched
@@ -507,7 +514,11 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const ScanArgs a, con
   const GridLevel& G = a.grid.lev[0];
   long long c = grid_cell(G, px, py, pz);
   if (c < 0) c = (long long)G.nx * G.ny * G.nz;
+#if GMMLOC_SORT_RANK
   sorted[__ldg(cur + c) + a.assign[i]] = make_float4(px, py, pz, __int_as_float((int)i));
+#else
+  sorted[atomicAdd(const_cast<int*>(cur) + c, 1)] = make_float4(px, py, pz, __int_as_float((int)i));
+#endif
 }
 // In-place exclusive scan of n ints in two launches of one CTA per 4 096-entry tile: (1) every tile is scanned on its own
 // and leaves its total in tile_tot; (2) every tile adds the sum of the totals before it.  (One CTA walking all the tiles
