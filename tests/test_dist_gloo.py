@@ -54,6 +54,17 @@ def _worker(rank, world, port, B, N, q):
                 assert torch.equal(gp, batch["pose0"] * 2.0) and torch.equal(gs, torch.arange(B, dtype=torch.int32))
             else:
                 assert gp is None and gs is None
+        # the same shards scattered piece by piece (what bench.py --workload c4 pipelines against the solve)
+        plan2 = gd.FrameSharder(B, N)
+        for nsub in (1, 2, 3):
+            for buf in plan2.recv.values():
+                buf.zero_()
+            pieces = plan2.sub_ranges(nsub)
+            assert pieces[0][0] == 0 and pieces[-1][1] == plan2.S and all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+            for a, b in pieces:
+                plan2.scatter_piece(batch, a, b)
+            for k in ("pose0", "pts_w", "obs", "octave"):
+                assert torch.equal(plan2.recv[k][: plan2.count], shard[k]), (k, nsub)
         if rank == 0:
             assert full.shape == (B, 2)
             assert torch.equal(full[:, 0], torch.arange(B, dtype=torch.float64))
