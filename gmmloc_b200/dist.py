@@ -137,6 +137,31 @@ class FrameSharder:
             dist.scatter(buf[lo:hi], [c[lo:hi] for c in self._chunks[k]] if self.rank == self.src else None, src=self.src,
                          group=self.group)
 
+    # ---- peer-memory scatter: every rank PULLS its shard out of rank src's HBM over NVLink with the copy engines ----
+    def share(self, full: dict | None) -> None:
+        """Rank `src` exports the resident batch through CUDA IPC handles (broadcast as picklable objects), the other ranks
+        map it.  One process per GPU, one node.  After this, pull_piece() needs no collective and no SM: the copies are
+        peer-to-peer cudaMemcpyAsync on the copy engines, so — unlike NCCL's send / receive kernels — they overlap a
+        persistent compute kernel that holds every SM."""
+        from torch.multiprocessing.reductions import reduce_tensor
+        objs = [None]
+        if self.rank == self.src:
+            objs = [{k: reduce_tensor(full[k]) for k in self.recv}]
+        dist.broadcast_object_list(objs, src=self.src, group=self.group)
+        if self.rank == self.src:
+            self._peer = {k: full[k] for k in self.recv}
+        else:
+            self._peer = {k: fn(*args) for k, (fn, args) in objs[0].items()}
+
+    def pull_piece(self, lo: int, hi: int) -> None:
+        """Copies rows [lo, hi) of THIS rank's shard from the shared batch into the receive buffers (current stream)."""
+        hi = min(hi, self.count)
+        if hi <= lo:
+            return
+        a = self.lo
+        for k, buf in self.recv.items():
+            buf[lo:hi].copy_(self._peer[k][a + lo:a + hi], non_blocking=True)
+
     def gather(self, pose: torch.Tensor, status: torch.Tensor):
         """pose S x 7 f64, status S i32 (rows >= count are padding).  Returns (B x 7, B) on rank src."""
         dist.gather(pose, self._g_pose, dst=self.src, group=self.group)

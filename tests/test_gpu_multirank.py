@@ -17,7 +17,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, B, N, q):
+def _worker(rank, world, port, B, N, q, mode="nccl"):
     import torch.distributed as dist
     import gmmloc_b200 as g
     from gmmloc_b200 import dist as gd
@@ -40,8 +40,17 @@ def _worker(rank, world, port, B, N, q):
         o_pose = torch.zeros((plan.S, 7), dtype=torch.float64, device=dev)
         o_status = torch.zeros((plan.S,), dtype=torch.int32, device=dev)
         o_assign = torch.empty((plan.S, N), dtype=torch.int32, device=dev)
+        if mode == "p2p":  # peer-memory pull over CUDA IPC instead of the NCCL scatter (same receive buffers)
+            plan.share(full)
+            torch.cuda.synchronize()
+            dist.barrier()
         with torch.cuda.stream(stream):
-            sh = plan.scatter(full)
+            if mode == "p2p":
+                for lo, hi in plan.sub_ranges(3):
+                    plan.pull_piece(lo, hi)
+                sh = plan.recv
+            else:
+                sh = plan.scatter(full)
             if plan.count:
                 ctx.frames_solve_async(gmm, cam, prm, sh["pose0"].data_ptr(), sh["pts_w"].data_ptr(), sh["obs"].data_ptr(),
                                        sh["octave"].data_ptr(), plan.count, N, o_pose.data_ptr(), 0, o_assign.data_ptr(), 0,
@@ -61,15 +70,16 @@ def _worker(rank, world, port, B, N, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mode", ["nccl", "p2p"])
 @pytest.mark.parametrize("B", [64, 37])
-def test_scatter_solve_gather_equals_single_gpu(B):
+def test_scatter_solve_gather_equals_single_gpu(B, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.SimpleQueue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, 600, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, B, 600, q, mode)) for r in range(2)]
     [p.start() for p in procs]
     [p.join(600) for p in procs]
     assert all(p.exitcode == 0 for p in procs)

@@ -1,11 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
 run() {  # name, lib
-  GMMLOC_B200_LIB=$2 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/r2z_bench_$1.json 2> gpurun_out/r2z_bench_$1.err
+  GMMLOC_B200_LIB=$2 timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/ab_bench_$1.json 2> gpurun_out/ab_bench_$1.err
   python - <<PY
 import json
 try:
-    d=json.loads(open('gpurun_out/r2z_bench_$1.json').read().strip().splitlines()[-1])
+    d=json.loads(open('gpurun_out/ab_bench_$1.json').read().strip().splitlines()[-1])
     print('$1', 'value', round(d['value']), 'e2e', round(d['e2e']['value']), {k: round(v, 3) for k, v in d['kernel_ms'].items()}, d.get('frames_numeric_failure'))
 except Exception as e:
     print('$1', 'FAILED', e)
