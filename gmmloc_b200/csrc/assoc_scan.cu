@@ -485,40 +485,76 @@ __device__ __forceinline__ long long grid_cell(const GridLevel& G, float x0, flo
 // a launch ordered by cell, a warp of the grid scan shares one cell list: list ids and component records are loaded
 // once per warp (broadcast, one L1 wavefront per request) instead of once per lane (the unsorted kernel is
 // L1-wavefront-bound at 8.6 wavefronts per request, profiles/assoc_grid_r01.txt). ----
-__device__ __forceinline__ long long sort_cell(const ScanArgs& a, long long i) {
-  const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
-  const GridLevel& G = a.grid.lev[0];
-  const long long c = grid_cell(G, px, py, pz);
-  return c >= 0 ? c : (long long)G.nx * G.ny * G.nz;  // last bucket: outside the grid / non-finite
-}
 #ifndef GMMLOC_SORT_RANK
 #define GMMLOC_SORT_RANK 1
 #endif
 // The histogram pass keeps what its atomic returns — the landmark's rank inside its cell — in the (not yet written)
 // assignment array, so that the scatter needs no second round of 8 M atomics: position = cell start + rank.
+// A thread can carry kSortU independent landmarks (all loads before the first atomic, all atomics before the first store);
+// more than one does not pay: the kernels wait on the L2 atomic units (8.2 M counter updates on 94 k addresses per launch).
+#ifndef GMMLOC_SORT_UNROLL
+#define GMMLOC_SORT_UNROLL 1  // measured on C2: 1 -> 0.698 ms (sort + scan), 4 -> 0.730, 8 -> 0.746: the L2 atomic units, not latency, set the pace
+#endif
+constexpr int kSortU = GMMLOC_SORT_UNROLL;
+__device__ __forceinline__ long long sort_cell_of(const GridLevel& G, float px, float py, float pz) {
+  const long long c = grid_cell(G, px, py, pz);
+  return c >= 0 ? c : (long long)G.nx * G.ny * G.nz;  // last bucket: outside the grid / non-finite
+}
 __global__ void __launch_bounds__(256) grid_hist_kernel(const ScanArgs a, int* __restrict__ hist) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long i0 = (long long)blockIdx.x * (256 * kSortU) + threadIdx.x;
+  const GridLevel& G = a.grid.lev[0];
+  float p[kSortU][3];
+#pragma unroll
+  for (int u = 0; u < kSortU; ++u) {
+    const long long i = i0 + u * 256;
+    if (i < a.M) {
+      p[u][0] = __ldg(a.pts + i * 3 + 0); p[u][1] = __ldg(a.pts + i * 3 + 1); p[u][2] = __ldg(a.pts + i * 3 + 2);
+    }
+  }
+  int r[kSortU];
+#pragma unroll
+  for (int u = 0; u < kSortU; ++u)
+    if (i0 + u * 256 < a.M) r[u] = atomicAdd(hist + sort_cell_of(G, p[u][0], p[u][1], p[u][2]), 1);
 #if GMMLOC_SORT_RANK
-  if (i < a.M) a.assign[i] = atomicAdd(hist + sort_cell(a, i), 1);
-#else
-  if (i < a.M) atomicAdd(hist + sort_cell(a, i), 1);
+#pragma unroll
+  for (int u = 0; u < kSortU; ++u)
+    if (i0 + u * 256 < a.M) a.assign[i0 + u * 256] = r[u];
 #endif
 }
 // The scatter writes the landmark ITSELF next to its original index (one float4 per landmark) so that the scan streams
 // its input coalesced: with an index-only permutation the scan gathered 12 B out of every 32-byte sector it fetched
 // (510 MB of DRAM reads for 98 MB of landmarks, profiles/assoc_grid_r01.txt).
 __global__ void __launch_bounds__(256) grid_scatter_kernel(const ScanArgs a, const int* __restrict__ cur, float4* __restrict__ sorted) {
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (i >= a.M) return;
-  const float px = __ldg(a.pts + i * 3 + 0), py = __ldg(a.pts + i * 3 + 1), pz = __ldg(a.pts + i * 3 + 2);
+  const long long i0 = (long long)blockIdx.x * (256 * kSortU) + threadIdx.x;
   const GridLevel& G = a.grid.lev[0];
-  long long c = grid_cell(G, px, py, pz);
-  if (c < 0) c = (long long)G.nx * G.ny * G.nz;
+  float p[kSortU][3];
+  int r[kSortU];
+#pragma unroll
+  for (int u = 0; u < kSortU; ++u) {
+    const long long i = i0 + u * 256;
+    r[u] = 0;
+    if (i < a.M) {
+      p[u][0] = __ldg(a.pts + i * 3 + 0); p[u][1] = __ldg(a.pts + i * 3 + 1); p[u][2] = __ldg(a.pts + i * 3 + 2);
 #if GMMLOC_SORT_RANK
-  sorted[__ldg(cur + c) + a.assign[i]] = make_float4(px, py, pz, __int_as_float((int)i));
-#else
-  sorted[atomicAdd(const_cast<int*>(cur) + c, 1)] = make_float4(px, py, pz, __int_as_float((int)i));
+      r[u] = a.assign[i];
 #endif
+    }
+  }
+  int pos[kSortU];
+#pragma unroll
+  for (int u = 0; u < kSortU; ++u) {
+    if (i0 + u * 256 < a.M) {
+      const long long c = sort_cell_of(G, p[u][0], p[u][1], p[u][2]);
+#if GMMLOC_SORT_RANK
+      pos[u] = __ldg(cur + c) + r[u];
+#else
+      pos[u] = atomicAdd(const_cast<int*>(cur) + c, 1);
+#endif
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kSortU; ++u)
+    if (i0 + u * 256 < a.M) sorted[pos[u]] = make_float4(p[u][0], p[u][1], p[u][2], __int_as_float((int)(i0 + u * 256)));
 }
 // In-place exclusive scan of n ints in two launches of one CTA per 4 096-entry tile: (1) every tile is scanned on its own
 // and leaves its total in tile_tot; (2) every tile adds the sum of the totals before it.  (One CTA walking all the tiles
@@ -583,6 +619,31 @@ __global__ void __launch_bounds__(1024) excl_scan_add_kernel(int* __restrict__ d
     if (idx + q < n) d[idx + q] += off;
 }
 
+// scores the n staged records (3 float4 each: U, -U mu, id) against one landmark; PEN: `pen` (0 or +inf) is added to every score
+#ifndef GMMLOC_GRID_THREADS
+#define GMMLOC_GRID_THREADS 128  // C2 sort + scan: 256 -> 0.665 ms, 128 -> 0.648, 512 -> 0.700
+#endif
+#ifndef GMMLOC_GRID_UNROLL
+#define GMMLOC_GRID_UNROLL 4
+#endif
+constexpr int kGridUnroll = GMMLOC_GRID_UNROLL;
+#ifndef GMMLOC_GRID_F32_CERT
+#define GMMLOC_GRID_F32_CERT 1
+#endif
+template <bool PEN>
+__device__ __forceinline__ void score_staged(const float4* __restrict__ st, int n, float px, float py, float pz, float pen, float& b1,
+                                             float& b2, int& idx) {
+#pragma unroll kGridUnroll
+  for (int q = 0; q < n; ++q) {
+    const float4 r0 = st[3 * q], r1 = st[3 * q + 1], r2 = st[3 * q + 2];
+    float s = score32(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, px, py, pz);
+    if (PEN) s = __fadd_rn(s, pen);  // s >= 0 or NaN: s + 0 == s exactly
+    idx = (s < b1) ? __float_as_int(r2.y) : idx;
+    b2 = fminf(b2, fmaxf(b1, s));  // s < b1: the old best becomes second; else min(b2, s)
+    b1 = fminf(b1, s);
+  }
+}
+
 template <int THREADS, bool SORTED>
 __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
   __shared__ float4 stage[SORTED ? THREADS / 32 : 1][32][3];  // one staged record per lane and warp (sorted variant)
@@ -630,6 +691,8 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
       const int leader = __ffs(todo) - 1;
       const long long c = __shfl_sync(0xffffffffu, cell, leader);
       const bool mine = (cell == c);
+      const bool all_mine = __all_sync(0xffffffffu, mine);
+      const float pen = mine ? 0.f : CUDART_INF_F;
       const int e0 = __ldg(G.start + c), e1 = __ldg(G.start + c + 1);
       // the list is staged through shared memory 32 components at a time: every lane fetches ONE record (32 gathers in
       // flight instead of a dependent id -> record chain per component), then all lanes read the staged records with
@@ -645,21 +708,33 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
           stage[wrp][lane][2] = make_float4(r2, __int_as_float(k), 0.f, 0.f);
         }
         __syncwarp();
-#pragma unroll 4
-        for (int q = 0; q < n; ++q) {
-          const float4 r0 = stage[wrp][q][0], r1 = stage[wrp][q][1], r2 = stage[wrp][q][2];
-          // branch-free best / second-best (the branchy form spent more instructions here than on the score itself:
-          // profiles/assoc_grid_r02.txt).  A lane that is not in this cell scores +inf: nothing changes for it.
-          // Strict < keeps the first (lowest) id on equal scores, as the reference's ascending scan.
-          const float s = mine ? score32(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, px, py, pz) : CUDART_INF_F;
-          idx = (s < b1) ? __float_as_int(r2.y) : idx;
-          b2 = fminf(b2, fmaxf(b1, s));  // s < b1: the old best becomes second; else min(b2, s)
-          b1 = fminf(b1, s);
-        }
+        // branch-free best / second-best (the branchy form spent more instructions here than on the score itself:
+        // profiles/assoc_grid_r02.txt).  Strict < keeps the first (lowest) id on equal scores, as the reference's ascending scan.
+        // A lane that is not in this cell adds +inf to its score (nothing changes for it); written as `mine ? score : inf` the
+        // compiler put a branch (BSSY / BRA / BSYNC, four instructions of 21 per record, and a scheduling fence between the
+        // staged loads of consecutive records) around every score.  When the whole warp sits in the cell — the usual case —
+        // the penalty is not even added.
+        if (all_mine) score_staged<false>(&stage[wrp][0][0], n, px, py, pz, 0.f, b1, b2, idx);
+        else score_staged<true>(&stage[wrp][0][0], n, px, py, pz, pen, b1, b2, idx);
         __syncwarp();
       }
       todo &= ~__ballot_sync(0xffffffffu, mine);
     }
+#if GMMLOC_GRID_F32_CERT
+    // The certificate below costs ~110 instructions per landmark in fp64 (two square roots).  A conservative fp32 form of the
+    // same two tests decides almost every landmark: with correctly rounded sqrtf and the factors 1 +- 2e-6 (against kRelEps =
+    // 2.4e-7 and three fp32 roundings of 6e-8 each) `hi` is an upper bound of the fp64 hi1 and `lo` a lower bound of the fp64
+    // lo2, so  lo > hi  and  hi <= sqrt(tmax) (1 - 1e-6)  imply the fp64 tests: the SAME assignment is written, and what the
+    // fp32 form cannot decide still goes through the fp64 form.
+    if (live && cell >= 0 && idx >= 0 && a.d2 == nullptr && !(a.gate > 0.0)) {
+      const float al = a.alpha * (1.0f + 1e-6f);
+      const float hi = __fmaf_rn(__fsqrt_rn(b1), 1.0f + 2e-6f, al), lo = __fmaf_rn(__fsqrt_rn(b2), 1.0f - 2e-6f, -al);
+      if (lo > hi && hi <= __fsqrt_rn((float)G.tmax) * (1.0f - 1e-6f)) {
+        a.assign[i] = idx;
+        return;
+      }
+    }
+#endif
     if (cell >= 0 && idx >= 0) {
       hi1 = sqrt((double)b1) * (1.0 + kRelEps) + (double)a.alpha;
       if (hi1 * hi1 <= (double)G.tmax) lev_ok = 0;
@@ -809,16 +884,18 @@ cudaError_t launch_scan_grid(ScanArgs a, int* sort_cnt, int32_t* sort_perm, cuda
   if (sort_cnt != nullptr && sort_perm != nullptr && a.M >= 4 * ncell) {
     cudaError_t e;
     if ((e = cudaMemsetAsync(sort_cnt, 0, sizeof(int) * (size_t)(ncell + 1), stream)) != cudaSuccess) return e;
-    grid_hist_kernel<<<grid, 256, 0, stream>>>(a, sort_cnt);
+    const unsigned sgrid = (unsigned)((a.M + 256 * kSortU - 1) / (256 * kSortU));
+    grid_hist_kernel<<<sgrid, 256, 0, stream>>>(a, sort_cnt);
     {
       const int n = (int)(ncell + 1), tiles = (n + 4095) / 4096;
       int* tile_tot = sort_cnt + ncell + 2;  // behind the counters (api.cu reserves the room)
       excl_scan_tiles_kernel<<<tiles, 1024, 0, stream>>>(sort_cnt, n, tile_tot);
       excl_scan_add_kernel<<<tiles, 1024, 0, stream>>>(sort_cnt, n, tile_tot);
     }
-    grid_scatter_kernel<<<grid, 256, 0, stream>>>(a, sort_cnt, reinterpret_cast<float4*>(sort_perm));
+    grid_scatter_kernel<<<sgrid, 256, 0, stream>>>(a, sort_cnt, reinterpret_cast<float4*>(sort_perm));
     a.sorted = reinterpret_cast<const float4*>(sort_perm);
-    assoc_grid_kernel<256, true><<<grid, 256, 0, stream>>>(a);
+    assoc_grid_kernel<GMMLOC_GRID_THREADS, true><<<(unsigned)((a.M + GMMLOC_GRID_THREADS - 1) / GMMLOC_GRID_THREADS), GMMLOC_GRID_THREADS, 0,
+                                                   stream>>>(a);
     if (launches) *launches += 4;
     return cudaGetLastError();
   }

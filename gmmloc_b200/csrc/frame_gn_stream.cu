@@ -147,6 +147,20 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Volatile vector loads from shared memory.  The sweep re-reads the pose, the pose step and the reference point at every
+// point (carrying them would cost ~40 registers across the whole class dispatch); read as 128-bit words they are 12 LDS per
+// point instead of 30.  asm volatile: never hoisted out of the chunk loop or merged, exactly like the volatile views they replace.
+#ifndef GMMLOC_GNS_VEC_LDS
+#define GMMLOC_GNS_VEC_LDS 1
+#endif
+__device__ __forceinline__ void lds_v2f64(uint32_t addr, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ float4 lds_v4f32(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 // generic-proxy writes to global memory (the stored linearisation) ordered before later async-proxy (TMA) reads of them
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
@@ -184,7 +198,10 @@ __global__ void __launch_bounds__(128) frame_pose_kernel(const FrameArgs a, doub
 }
 #endif
 // flag byte (low nibble) and class (bits 4..6) of one point; fp = the per-frame constants of frame_pose_kernel
-__device__ __forceinline__ uint8_t classify_point(const FrameArgs& a, const double* fp, float px, float py, float pz, float our, int k) {
+// deg: the component's degenerate flag (a.is_deg[k]) when k >= 0 and the points are free, else unused — the callers load it so
+// that they can have several of these first-level gathers in flight
+__device__ __forceinline__ uint8_t classify_point(const FrameArgs& a, const double* fp, float px, float py, float pz, float our, int k,
+                                                  int deg) {
   const FrameParamsDev& P = a.prm;
   const bool pose_free = P.factor_mode != GMMLOC_MODE_POINTS_ONLY;
   const bool pts_free = P.factor_mode != GMMLOC_MODE_POSE_ONLY;
@@ -192,7 +209,7 @@ __device__ __forceinline__ uint8_t classify_point(const FrameArgs& a, const doub
   const double x0 = (double)px, x1 = (double)py, x2 = (double)pz;
   uint8_t b = (our >= 0.0f) ? F_STEREO : 0;
   if (k >= 0 && pts_free) {
-    if (a.is_deg[k]) {
+    if (deg) {
       b |= F_DEG;
       const double* ax = a.axis + (size_t)k * 9;
       const double* mu = a.mean + (size_t)k * 3;
@@ -228,13 +245,22 @@ __global__ void __launch_bounds__(256, GMMLOC_CLS_MINB) frame_classify_kernel(co
     double fp[7];
 #pragma unroll
     for (int i = 0; i < 7; ++i) fp[i] = __ldg(fpose + (size_t)f * 8 + i);
+    const int k = __ldg(a.assign + gi);
+    const int deg = (k >= 0 && a.prm.factor_mode != GMMLOC_MODE_POSE_ONLY) ? (int)a.is_deg[k] : 0;
     flags[gi] = classify_point(a, fp, __ldg(a.pts_w + gi * 3), __ldg(a.pts_w + gi * 3 + 1), __ldg(a.pts_w + gi * 3 + 2),
-                               __ldg(a.obs + gi * 3 + 2), __ldg(a.assign + gi));
+                               __ldg(a.obs + gi * 3 + 2), k, deg);
   }
 }
 #endif
 
 constexpr int kPackThreads = 256;
+#ifndef GMMLOC_PACK_GROUP
+#define GMMLOC_PACK_GROUP 8
+#endif
+constexpr int kPackG = GMMLOC_PACK_GROUP;  // points per thread whose first-level gathers are in flight together
+#ifndef GMMLOC_PACK_GRID
+#define GMMLOC_PACK_GRID GMMLOC_PACK_MINB  // CTAs per SM the grid is sized for: the resident count (one wave, no tail of a partial one)
+#endif
 #ifndef GMMLOC_PACK_MINB
 #define GMMLOC_PACK_MINB 5  // 51 registers: five CTAs per SM; measured 2.96 ms for the stage against 3.02 (four CTAs) and 3.00 (six, spills)
 #endif
@@ -250,6 +276,7 @@ __global__ void __launch_bounds__(kPackThreads, GMMLOC_PACK_MINB) frame_pack_ker
   const int N = a.N;
   const int nblocks = (N + kPackThreads - 1) / kPackThreads;
   const PackLayout L = pack_layout(N);
+  int kk[kPackG];  // component ids of the thread's current group of points
   for (int f = blockIdx.x; f < a.B; f += gridDim.x) {
     const float* pts = a.pts_w + (size_t)f * N * 3;
     const float* obs = a.obs + (size_t)f * N * 3;
@@ -279,18 +306,40 @@ __global__ void __launch_bounds__(kPackThreads, GMMLOC_PACK_MINB) frame_pack_ker
     }
     // pass A: flags and class of every point — computed here (classify_point, the arithmetic of frame_classify_kernel) or
     // read from the flags that kernel wrote — and the class histogram per (block, warp)
-    for (int c = 0; c < nblocks; ++c) {
-      const int i = c * kPackThreads + tid;
-      int cls = -1;
-      if (i < N) {
-        const uint8_t b = gflag ? gflag[i] : classify_point(a, s_fp, pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], obs[i * 3 + 2], asg[i]);
-        tmp[i] = b;
-        cls = b >> 4;
+    // The gate is a chain of dependent gathers (assignment -> degenerate flag -> component constants) and a thread walks its
+    // points one after the other, so the first two levels are issued for a whole group of kPackG points at once (component ids
+    // kept in registers for pass B): one serialised round trip per point instead of three.
+    for (int c0 = 0; c0 < nblocks; c0 += kPackG) {
+      unsigned dg = 0;
+      if (gflag == nullptr) {
+#pragma unroll
+        for (int u = 0; u < kPackG; ++u) {
+          const int i = (c0 + u) * kPackThreads + tid;
+          kk[u] = (c0 + u < nblocks && i < N) ? asg[i] : -1;
+        }
+        if (a.prm.factor_mode != GMMLOC_MODE_POSE_ONLY) {
+#pragma unroll
+          for (int u = 0; u < kPackG; ++u)
+            if (kk[u] >= 0) dg |= (unsigned)(a.is_deg[kk[u]] != 0) << u;
+        }
       }
 #pragma unroll
-      for (int q = 0; q < C_COUNT; ++q) {
-        const unsigned m = __ballot_sync(0xffffffffu, cls == q);
-        if (lane == 0) s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] = __popc(m);
+      for (int u = 0; u < kPackG; ++u) {
+        const int c = c0 + u;
+        if (c >= nblocks) break;  // uniform
+        const int i = c * kPackThreads + tid;
+        int cls = -1;
+        if (i < N) {
+          const uint8_t b = gflag ? gflag[i]
+                                  : classify_point(a, s_fp, pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], obs[i * 3 + 2], kk[u], (dg >> u) & 1u);
+          tmp[i] = b;
+          cls = b >> 4;
+        }
+#pragma unroll
+        for (int q = 0; q < C_COUNT; ++q) {
+          const unsigned m = __ballot_sync(0xffffffffu, cls == q);
+          if (lane == 0) s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] = __popc(m);
+        }
       }
     }
     __syncthreads();
@@ -343,56 +392,68 @@ __global__ void __launch_bounds__(kPackThreads, GMMLOC_PACK_MINB) frame_pack_ker
       }
     }
     // pass B: scatter the frame into class-sorted order, resolve the component constants of the structured classes
-    for (int c = 0; c < nblocks; ++c) {
-      const int i = c * kPackThreads + tid;
-      int cls = -1;
-      uint8_t b = 0;
-      if (i < N) {
-        b = tmp[i];
-        cls = b >> 4;
-      }
-      int j = -1;
+    for (int c0 = 0; c0 < nblocks; c0 += kPackG) {
+      if (gflag != nullptr || nblocks > kPackG) {  // (a frame of at most kPackG blocks still has pass A's ids in registers)
 #pragma unroll
-      for (int q = 0; q < C_COUNT; ++q) {
-        const unsigned m = __ballot_sync(0xffffffffu, cls == q);
-        if (cls == q) j = s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] + __popc(m & ((1u << lane) - 1u));
+        for (int u = 0; u < kPackG; ++u) {
+          const int i = (c0 + u) * kPackThreads + tid;
+          kk[u] = (c0 + u < nblocks && i < N) ? asg[i] : -1;
+        }
       }
-      if (i < N) {
-        const float p0 = pts[i * 3], p1 = pts[i * 3 + 1], p2 = pts[i * 3 + 2];
-        gp[j * 3] = p0;
-        gp[j * 3 + 1] = p1;
-        gp[j * 3 + 2] = p2;
-        go[j * 3] = obs[i * 3];
-        go[j * 3 + 1] = obs[i * 3 + 1];
-        go[j * 3 + 2] = obs[i * 3 + 2];
-        gperm[j] = (uint16_t)i;
-        goct[j] = oct[i];
-        gfl[j] = b;
-        if (cls >= C_MPLANE && cls <= C_MSTR) {
-          const int k = asg[i];
-          const double* mu = a.mean + (size_t)k * 3;
-          const double d0 = (double)p0 - mu[0], d1 = (double)p1 - mu[1], d2 = (double)p2 - mu[2];
-          const int r = j - s_start[cls];
-          unsigned char* cp = gcst + (size_t)(s_cb[cls] + (r >> 5)) * kCstBytes;
-          const int l = r & 31;
-          const float4 t0 = __ldg(reinterpret_cast<const float4*>(gn_tab) + 2 * (size_t)k);
-          if (cls == C_MPLANE || cls == C_STRP) {
-            // es0 = n . (x0 - mu) with the fp32 normal the solver uses, evaluated in fp64 and rounded once
-            const float es0 = (float)(((double)t0.x * d0 + (double)t0.y * d1) + (double)t0.z * d2);
-            reinterpret_cast<float4*>(cp)[l] = make_float4(t0.x, t0.y, t0.z, es0);
-          } else {
-            // six unique entries of Sigma^-1 (C_STR) or — gain form of the monocular block, frame_gn_world.cuh — of Sigma (C_MSTR)
-            float m0, m1, m2, m3, m4, m5;
-            if (cls == C_STR) {
-              const float2 t1 = __ldg(reinterpret_cast<const float2*>(gn_tab) + 4 * (size_t)k + 2);
-              m0 = t0.x; m1 = t0.y; m2 = t0.z; m3 = t0.w; m4 = t1.x; m5 = t1.y;
+#pragma unroll
+      for (int u = 0; u < kPackG; ++u) {
+        const int c = c0 + u;
+        if (c >= nblocks) break;  // uniform
+        const int i = c * kPackThreads + tid;
+        int cls = -1;
+        uint8_t b = 0;
+        if (i < N) {
+          b = tmp[i];
+          cls = b >> 4;
+        }
+        int j = -1;
+#pragma unroll
+        for (int q = 0; q < C_COUNT; ++q) {
+          const unsigned m = __ballot_sync(0xffffffffu, cls == q);
+          if (cls == q) j = s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] + __popc(m & ((1u << lane) - 1u));
+        }
+        if (i < N) {
+          const float p0 = pts[i * 3], p1 = pts[i * 3 + 1], p2 = pts[i * 3 + 2];
+          gp[j * 3] = p0;
+          gp[j * 3 + 1] = p1;
+          gp[j * 3 + 2] = p2;
+          go[j * 3] = obs[i * 3];
+          go[j * 3 + 1] = obs[i * 3 + 1];
+          go[j * 3 + 2] = obs[i * 3 + 2];
+          gperm[j] = (uint16_t)i;
+          goct[j] = oct[i];
+          gfl[j] = b;
+          if (cls >= C_MPLANE && cls <= C_MSTR) {
+            const int k = kk[u];
+            const double* mu = a.mean + (size_t)k * 3;
+            const double d0 = (double)p0 - mu[0], d1 = (double)p1 - mu[1], d2 = (double)p2 - mu[2];
+            const int r = j - s_start[cls];
+            unsigned char* cp = gcst + (size_t)(s_cb[cls] + (r >> 5)) * kCstBytes;
+            const int l = r & 31;
+            const float4 t0 = __ldg(reinterpret_cast<const float4*>(gn_tab) + 2 * (size_t)k);
+            if (cls == C_MPLANE || cls == C_STRP) {
+              // es0 = n . (x0 - mu) with the fp32 normal the solver uses, evaluated in fp64 and rounded once
+              const float es0 = (float)(((double)t0.x * d0 + (double)t0.y * d1) + (double)t0.z * d2);
+              reinterpret_cast<float4*>(cp)[l] = make_float4(t0.x, t0.y, t0.z, es0);
             } else {
-              const double* cv = a.cov + (size_t)k * 9;
-              m0 = (float)cv[0]; m1 = (float)cv[1]; m2 = (float)cv[2]; m3 = (float)cv[4]; m4 = (float)cv[5]; m5 = (float)cv[8];
+              // six unique entries of Sigma^-1 (C_STR) or — gain form of the monocular block, frame_gn_world.cuh — of Sigma (C_MSTR)
+              float m0, m1, m2, m3, m4, m5;
+              if (cls == C_STR) {
+                const float2 t1 = __ldg(reinterpret_cast<const float2*>(gn_tab) + 4 * (size_t)k + 2);
+                m0 = t0.x; m1 = t0.y; m2 = t0.z; m3 = t0.w; m4 = t1.x; m5 = t1.y;
+              } else {
+                const double* cv = a.cov + (size_t)k * 9;
+                m0 = (float)cv[0]; m1 = (float)cv[1]; m2 = (float)cv[2]; m3 = (float)cv[4]; m4 = (float)cv[5]; m5 = (float)cv[8];
+              }
+              reinterpret_cast<float4*>(cp)[l] = make_float4((float)d0, (float)d1, (float)d2, m0);
+              reinterpret_cast<float4*>(cp)[32 + l] = make_float4(m1, m2, m3, m4);
+              reinterpret_cast<float*>(cp + 1024)[l] = m5;
             }
-            reinterpret_cast<float4*>(cp)[l] = make_float4((float)d0, (float)d1, (float)d2, m0);
-            reinterpret_cast<float4*>(cp)[32 + l] = make_float4(m1, m2, m3, m4);
-            reinterpret_cast<float*>(cp + 1024)[l] = m5;
           }
         }
       }
@@ -455,8 +516,8 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
   __shared__ double s_red[kWarps][kAccS];
   __shared__ double s_acc[kAccS];
   __shared__ double s_pose[7], s_dxc[6], s_c0[3];
-  __shared__ float s_dxw[8];  // omega_w (3), upsilon_w (3): the pose step in world-twist coordinates about c0
-  __shared__ float s_c0f[4];
+  __shared__ __align__(16) float s_dxw[8];  // omega_w (3), upsilon_w (3): the pose step in world-twist coordinates about c0
+  __shared__ __align__(16) float s_c0f[4];
   __shared__ PoseS s_new, s_old;
   __shared__ int s_fail1, s_fail2, s_frame;
   __shared__ int s_hdr[4];
@@ -563,6 +624,10 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
       const volatile double* vt = s_new.t;
       const volatile float* vdx = s_dxw;
       const volatile float* vc0f = s_c0f;
+#if GMMLOC_GNS_VEC_LDS
+      const uint32_t a_pose = smem_u32(&s_new), a_rf = smem_u32(s_new.Rf), a_dxw = smem_u32(s_dxw), a_c0f = smem_u32(s_c0f);
+      (void)vR; (void)vt; (void)vdx;
+#endif
 
       float acc[kAccS];
 #pragma unroll
@@ -606,10 +671,20 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
         }
         const double X0 = (double)x0s[j * 3], X1 = (double)x0s[j * 3 + 1], X2 = (double)x0s[j * 3 + 2];
         // x' = x - c0 for the Jacobian side, formed in fp32 (it only ever multiplies fp32 quantities)
+#if GMMLOC_GNS_VEC_LDS
+        const float4 c0q = lds_v4f32(a_c0f);
+        const V3f xr0 = {x0s[j * 3] - c0q.x, x0s[j * 3 + 1] - c0q.y, x0s[j * 3 + 2] - c0q.z};
+#else
         const V3f xr0 = {x0s[j * 3] - vc0f[0], x0s[j * 3 + 1] - vc0f[1], x0s[j * 3 + 2] - vc0f[2]};
+#endif
         // ---- update: delta += u0 - W (omega_w x x' + upsilon_w) from the linearisation stored by the previous sweep ----
         if (CLS != C_FIXED && do_update) {
+#if GMMLOC_GNS_VEC_LDS
+          const float4 dq0 = lds_v4f32(a_dxw), dq1 = lds_v4f32(a_dxw + 16u);
+          const V3f om = {dq0.x, dq0.y, dq0.z}, up = {dq0.w, dq1.x, dq1.y};
+#else
           const V3f om = {vdx[0], vdx[1], vdx[2]}, up = {vdx[3], vdx[4], vdx[5]};
+#endif
           const V3f av = gnw::twist_at(om, up, {xr0.x + d0, xr0.y + d1, xr0.z + d2});
           V3f dx;
           if (CLS == C_PLAIN) {
@@ -638,13 +713,28 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
           Lin Ln;
           {
             double Rq[9], tq[3];
+#if GMMLOC_GNS_VEC_LDS
+            lds_v2f64(a_pose, Rq[0], Rq[1]);
+            lds_v2f64(a_pose + 16u, Rq[2], Rq[3]);
+            lds_v2f64(a_pose + 32u, Rq[4], Rq[5]);
+            lds_v2f64(a_pose + 48u, Rq[6], Rq[7]);
+            lds_v2f64(a_pose + 64u, Rq[8], tq[0]);
+            lds_v2f64(a_pose + 80u, tq[1], tq[2]);
+#else
 #pragma unroll
             for (int i = 0; i < 9; ++i) Rq[i] = vR[i];
 #pragma unroll
             for (int i = 0; i < 3; ++i) tq[i] = vt[i];
+#endif
             Ln = gnw::linearise(C, Rq, tq, X0 + (double)d0, X1 + (double)d1, X2 + (double)d2, ob, stereo);
           }
           float Rl[9];
+#if GMMLOC_GNS_VEC_LDS
+          {
+            const float4 r0 = lds_v4f32(a_rf), r1 = lds_v4f32(a_rf + 16u), r2 = lds_v4f32(a_rf + 32u);
+            Rl[0] = r0.x; Rl[1] = r0.y; Rl[2] = r0.z; Rl[3] = r1.x; Rl[4] = r1.y; Rl[5] = r1.z; Rl[6] = r2.x; Rl[7] = r2.y; Rl[8] = r2.z;
+          }
+#else
           {
             const volatile float* vRf = s_new.Rf;
 #pragma unroll
@@ -652,6 +742,7 @@ __global__ void __launch_bounds__(kThreads, kMinB) frame_gn_stream_kernel(const 
 #pragma unroll
               for (int c = 0; c < 3; ++c) Rl[r * 3 + c] = vRf[r * 4 + c];
           }
+#endif
           if (CLS == C_FIXED) {
             S3f G;
             V3f h;
@@ -966,7 +1057,7 @@ static cudaError_t launch_stream_sub(const FrameArgs& a, const float* gn_tab, in
 #else
   flags = nullptr;  // classification inside the pack kernel
 #endif
-  frame_pack_kernel<<<std::min(a.B, sms * 8), kPackThreads, (size_t)((a.N + 15) & ~15), stream>>>(a, gn_tab, flags, pack);
+  frame_pack_kernel<<<std::min(a.B, sms * GMMLOC_PACK_GRID), kPackThreads, (size_t)((a.N + 15) & ~15), stream>>>(a, gn_tab, flags, pack);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   bool fits = false;
