@@ -929,24 +929,42 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     return v ? std::atoi(v) : ctx->opt_e2e_short_first;
   }();
   std::vector<int> cstart;
-  if (ctx->opt_e2e_taper && !short_first && B >= 6 * 2 * sms + 2 * chunk) {
-    // Tapered schedule (default for large batches): the call ends when the LAST chunk has been copied in, solved and copied
-    // out, and it cannot start computing before the FIRST chunk has arrived — so both ends are short (one and two frames
-    // per resident CTA) and only the middle runs full 6-frames-per-SM chunks.  With the copy-in as the longer stream
-    // (205 MB per 4 096 C2 frames at 46-55 GB/s against 3.8 ms of kernels) the step costs H2D(total) + solve(last chunk)
-    // instead of H2D(total) + solve(888 frames).
-    const int unit = 2 * sms;
-    std::vector<int> sizes = {unit, 2 * unit};
-    int mid = B - 6 * unit;
-    std::vector<int> middle;
-    while (mid >= chunk + chunk / 2) {
-      middle.push_back(chunk);
-      mid -= chunk;
+  // -DGMMLOC_DEBUG_ENV builds only: GMMLOC_E2E_SCHEDULE="296,444,592,..." sets the chunk sizes (the last one takes the rest)
+  if (const char* sch = debug_env("GMMLOC_E2E_SCHEDULE")) {
+    int f = 0;
+    for (const char* q = sch; *q && f < B;) {
+      const int sz = std::atoi(q);
+      if (sz <= 0) break;
+      cstart.push_back(f);
+      f += sz;
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
     }
-    if (mid > 0) middle.insert(middle.begin(), mid);
-    sizes.insert(sizes.end(), middle.begin(), middle.end());
-    sizes.push_back(2 * unit);
-    sizes.push_back(unit);
+    if (cstart.empty()) cstart.push_back(0);
+    cstart.push_back(B);
+  } else
+  if (ctx->opt_e2e_taper && !short_first && B >= 6 * 2 * sms + 2 * chunk) {
+    // Graded schedule (default for large batches).  The pipeline is bound by the kernels, not by the copy-in: a chunk of n
+    // frames costs ~0.22 ms + 0.84 us n on the device (the sort + grid scan loses its cell sharing on small launches, the
+    // persistent solver runs whole waves of 2 x SMs frames) against 0.99 us n of copy-in at 50 GB/s, so chunk i + 1 has
+    // arrived long before chunk i is solved whenever it is not much larger.  The chunks therefore start at one frame per
+    // resident solver CTA (the kernels start after 0.3 ms of copy-in) and GROW by half a wave each — fewer chunks, less fixed
+    // cost — and the last one takes the rest.  Measured on C2 (4 096 frames, tools/gpu_sched.sh): 296, 444, 592, 740, 888, 1 136
+    // -> 775 k frames/s; the round-1 taper 296, 592, 544, 888, 888, 592, 296 -> 765 k; 296, 592, 1 184, 2 024 -> 667 k.
+    const int unit = 2 * sms;
+    std::vector<int> sizes;
+    int left = B, next = unit;
+    while (left > 0) {
+      if (left < 2 * next + sms) {  // the rest would be a chunk smaller than this one: merge
+        sizes.push_back(left);
+        break;
+      }
+      sizes.push_back(next);
+      left -= next;
+      // growth capped at 12 frames per SM (GMMLOC_OPT_E2E_CHUNK: at twice that option): beyond ~1 800 frames a chunk's copy-in
+      // takes longer than the kernels of the chunk before it and the pipeline would wait on PCIe with a long last chunk
+      next = std::min(next + sms, std::max(2 * chunk, unit));
+    }
     int f = 0;
     for (int sz : sizes) {
       cstart.push_back(f);

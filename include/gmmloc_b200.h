@@ -202,8 +202,9 @@ GMMLOC_API int gmmloc_ctx_last_gn_kernel(gmmloc_ctx_t* ctx);
  *   GMMLOC_OPT_E2E_SHORT_FIRST  1: the first pipeline chunk is a third of the others (default 0);
  *   GMMLOC_OPT_BA_CLUSTER       CTAs (SMs) per window of gmmloc_local_ba: 1, 2, 4 or 8 (thread-block cluster), 0 = automatic
  *                               (8 for a single window ... 1 once the windows of a call fill the GPU);
- *   GMMLOC_OPT_E2E_TAPER        1 (default): large batches run short chunks at both ends of the pipeline of
- *                               gmmloc_frames_solve (2 and 4 frames per SM) around the full ones; 0: uniform chunks. */
+ *   GMMLOC_OPT_E2E_TAPER        1 (default): large batches run a graded chunk schedule in gmmloc_frames_solve — the first
+ *                               chunk is 2 frames per SM, every next one a frame per SM longer (up to twice
+ *                               GMMLOC_OPT_E2E_CHUNK), the last takes the rest; 0: uniform chunks. */
 enum { GMMLOC_OPT_GN_PREP = 0, GMMLOC_OPT_E2E_CHUNK = 1, GMMLOC_OPT_E2E_SHORT_FIRST = 2, GMMLOC_OPT_BA_CLUSTER = 3, GMMLOC_OPT_E2E_TAPER = 4 };
 GMMLOC_API gmmloc_status_t gmmloc_ctx_set_option(gmmloc_ctx_t* ctx, int option, int64_t value);
 
