@@ -627,6 +627,12 @@ __global__ void __launch_bounds__(1024) excl_scan_add_kernel(int* __restrict__ d
 #define GMMLOC_GRID_UNROLL 4
 #endif
 constexpr int kGridUnroll = GMMLOC_GRID_UNROLL;
+#ifndef GMMLOC_SORT_MIN_PER_CELL
+#define GMMLOC_SORT_MIN_PER_CELL 2  // launches with fewer landmarks per level-0 cell keep the natural-order kernel
+#endif
+#ifndef GMMLOC_GRID_COOP
+#define GMMLOC_GRID_COOP 1
+#endif
 #ifndef GMMLOC_GRID_F32_CERT
 #define GMMLOC_GRID_F32_CERT 1
 #endif
@@ -647,6 +653,8 @@ __device__ __forceinline__ void score_staged(const float4* __restrict__ st, int 
 template <int THREADS, bool SORTED>
 __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
   __shared__ float4 stage[SORTED ? THREADS / 32 : 1][32][3];  // one staged record per lane and warp (sorted variant)
+  __shared__ float4 memb[SORTED ? THREADS / 32 : 1][16];      // landmarks of the members of a sparsely filled round
+  (void)memb;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   (void)lane; (void)wrp; (void)stage;
   const long long w = (long long)blockIdx.x * THREADS + threadIdx.x;
@@ -683,9 +691,21 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
   double hi1 = CUDART_INF;
   int lev_first = 0;
   if (SORTED) {
-    // level 0, one cell list per round for all the lanes that sit in that cell (usually the whole warp)
-    const GridLevel& G = a.grid.lev[0];
-    const long long cell = finite_in ? grid_cell(G, px, py, pz) : -1;
+    // Level by level, one cell list per round for all the lanes that sit in that cell.  Level 0 is the sort key, so a round
+    // usually serves the whole warp; the lanes a level cannot decide (winner not provably inside its radius) meet again at the
+    // next level, where the rounds run over THEIR cells — warp-cooperatively (below) instead of one lane walking a long list
+    // with the other 31 idle, which is what held up the shipped maps (35 % of the C3 landmarks lie beyond level 0).
+    bool fin = false;  // assignment written
+    for (int lev = 0; lev < a.grid.nlev; ++lev) {
+    const GridLevel& G = a.grid.lev[lev];
+    const bool need = live && finite_in && lev_ok < 0 && !fin;
+    if (!__any_sync(0xffffffffu, need)) break;
+    const long long cell = need ? grid_cell(G, px, py, pz) : -1;
+    if (lev > 0 && cell >= 0) {
+      b1 = g1;
+      b2 = g2;
+      idx = gi;
+    }
     unsigned todo = __ballot_sync(0xffffffffu, cell >= 0);
     while (todo) {
       const int leader = __ffs(todo) - 1;
@@ -697,6 +717,65 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
       // the list is staged through shared memory 32 components at a time: every lane fetches ONE record (32 gathers in
       // flight instead of a dependent id -> record chain per component), then all lanes read the staged records with
       // broadcast LDS.128 and score their own landmark
+#if GMMLOC_GRID_COOP
+      // Few lanes of the warp in this cell (the tail of a cell in a large launch; EVERY round of a small launch, where a cell
+      // holds a handful of landmarks): instead of all 32 lanes walking the whole list for m members, the (member, record)
+      // pairs are dealt over the lanes — m' = 2, 4, 8 or 16 member slots x 32 / m' records in parallel — and the per-slot
+      // (best, second best, id) triples are merged with xor shuffles.  Same score32() values, so the same (b1, b2); which of two
+      // EQUAL best scores names the id is immaterial: b2 == b1 then, and the certificate sends the landmark to the exact re-rank.
+      const unsigned mm = __ballot_sync(0xffffffffu, mine);
+      const int m = __popc(mm);
+      if (m <= 16) {
+        const int sh = m <= 2 ? 1 : m <= 4 ? 2 : m <= 8 ? 3 : 4;
+        const int mp = 1 << sh, slot = lane & (mp - 1), sub = lane >> sh, nsub = 32 >> sh;
+        const int rank = __popc(mm & ((1u << lane) - 1u));
+        if (mine) memb[wrp][rank] = make_float4(px, py, pz, 0.f);
+        __syncwarp();
+        const float4 qv = memb[wrp][slot < m ? slot : 0];
+        float c1 = CUDART_INF_F, c2 = CUDART_INF_F;
+        int ci = -1;
+        for (int base = e0; base < e1; base += 32) {
+          const int n = min(32, e1 - base);
+          if (lane < n) {
+            const int k = __ldg(G.list + base + lane);
+            const float4 r0 = __ldg(a.rec + 3 * (size_t)k), r1 = __ldg(a.rec + 3 * (size_t)k + 1);
+            const float r2 = __ldg(reinterpret_cast<const float*>(a.rec + 3 * (size_t)k + 2));
+            stage[wrp][lane][0] = r0;
+            stage[wrp][lane][1] = r1;
+            stage[wrp][lane][2] = make_float4(r2, __int_as_float(k), 0.f, 0.f);
+          }
+          __syncwarp();
+#pragma unroll 2
+          for (int q = sub; q < n; q += nsub) {
+            const float4 r0 = stage[wrp][q][0], r1 = stage[wrp][q][1], r2 = stage[wrp][q][2];
+            const float sc = score32(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, qv.x, qv.y, qv.z);
+            ci = (sc < c1) ? __float_as_int(r2.y) : ci;
+            c2 = fminf(c2, fmaxf(c1, sc));
+            c1 = fminf(c1, sc);
+          }
+          __syncwarp();
+        }
+        for (int off = mp; off < 32; off <<= 1) {  // lanes of one slot: lane bits sh..4
+          const float o1 = __shfl_xor_sync(0xffffffffu, c1, off), o2 = __shfl_xor_sync(0xffffffffu, c2, off);
+          const int oi = __shfl_xor_sync(0xffffffffu, ci, off);
+          c2 = fminf(fmaxf(c1, o1), fminf(c2, o2));
+          ci = (o1 < c1) ? oi : ci;
+          c1 = fminf(c1, o1);
+        }
+        // the member of rank r finds its triple in lane r (slot r, sub 0)
+        const int from = mine ? rank : 0;
+        const float m1 = __shfl_sync(0xffffffffu, c1, from), m2 = __shfl_sync(0xffffffffu, c2, from);
+        const int mi = __shfl_sync(0xffffffffu, ci, from);
+        if (mine) {
+          b2 = fminf(fmaxf(b1, m1), fminf(b2, m2));
+          idx = (m1 < b1) ? mi : idx;
+          b1 = fminf(b1, m1);
+        }
+        todo &= ~mm;
+        __syncwarp();  // memb is rewritten by the next sparse round
+        continue;
+      }
+#endif
       for (int base = e0; base < e1; base += 32) {
         const int n = min(32, e1 - base);
         if (lane < n) {
@@ -726,21 +805,22 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
     // 2.4e-7 and three fp32 roundings of 6e-8 each) `hi` is an upper bound of the fp64 hi1 and `lo` a lower bound of the fp64
     // lo2, so  lo > hi  and  hi <= sqrt(tmax) (1 - 1e-6)  imply the fp64 tests: the SAME assignment is written, and what the
     // fp32 form cannot decide still goes through the fp64 form.
-    if (live && cell >= 0 && idx >= 0 && a.d2 == nullptr && !(a.gate > 0.0)) {
+    if (cell >= 0 && idx >= 0 && a.d2 == nullptr && !(a.gate > 0.0)) {
       const float al = a.alpha * (1.0f + 1e-6f);
       const float hi = __fmaf_rn(__fsqrt_rn(b1), 1.0f + 2e-6f, al), lo = __fmaf_rn(__fsqrt_rn(b2), 1.0f - 2e-6f, -al);
-      if (lo > hi && hi <= __fsqrt_rn((float)G.tmax) * (1.0f - 1e-6f)) {
+      if (lo > hi && hi <= __fsqrt_rn(G.tmax) * (1.0f - 1e-6f)) {
         a.assign[i] = idx;
-        return;
+        fin = true;
       }
     }
 #endif
-    if (cell >= 0 && idx >= 0) {
+    if (cell >= 0 && idx >= 0 && !fin) {
       hi1 = sqrt((double)b1) * (1.0 + kRelEps) + (double)a.alpha;
-      if (hi1 * hi1 <= (double)G.tmax) lev_ok = 0;
+      if (hi1 * hi1 <= (double)G.tmax) lev_ok = lev;
     }
-    lev_first = 1;
-    if (!live) return;
+    }  // levels
+    lev_first = a.grid.nlev;  // nothing left for the per-lane walk below
+    if (!live || fin) return;
   }
   if (finite_in && lev_ok < 0) {
     for (int lev = lev_first; lev < a.grid.nlev; ++lev) {
@@ -881,7 +961,7 @@ cudaError_t launch_scan_grid(ScanArgs a, int* sort_cnt, int32_t* sort_perm, cuda
   const unsigned grid = (unsigned)((a.M + 255) / 256);
   const GridLevel& G = a.grid.lev[0];
   const long long ncell = (long long)G.nx * G.ny * G.nz;
-  if (sort_cnt != nullptr && sort_perm != nullptr && a.M >= 4 * ncell) {
+  if (sort_cnt != nullptr && sort_perm != nullptr && a.M >= GMMLOC_SORT_MIN_PER_CELL * ncell) {
     cudaError_t e;
     if ((e = cudaMemsetAsync(sort_cnt, 0, sizeof(int) * (size_t)(ncell + 1), stream)) != cudaSuccess) return e;
     const unsigned sgrid = (unsigned)((a.M + 256 * kSortU - 1) / (256 * kSortU));

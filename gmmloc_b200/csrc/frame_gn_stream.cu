@@ -254,6 +254,12 @@ __global__ void __launch_bounds__(256, GMMLOC_CLS_MINB) frame_classify_kernel(co
 #endif
 
 constexpr int kPackThreads = 256;
+#ifndef GMMLOC_PACK_MATCH
+#define GMMLOC_PACK_MATCH 1
+#endif
+#ifndef GMMLOC_PACK_PSCAN
+#define GMMLOC_PACK_PSCAN 1
+#endif
 #ifndef GMMLOC_PACK_GROUP
 #define GMMLOC_PACK_GROUP 8
 #endif
@@ -271,6 +277,8 @@ __global__ void __launch_bounds__(kPackThreads, GMMLOC_PACK_MINB) frame_pack_ker
   __shared__ int s_cnt[C_COUNT * kMaxChunks * 8];
   __shared__ double s_fp[8];                                // fused classification: third row of R, t_z, camera centre
   __shared__ int s_start[C_COUNT + 1], s_cb[C_COUNT + 1];  // first sorted position / first chunk of every class
+  __shared__ int s_tot[C_COUNT];                            // points per class
+  (void)s_tot;
   uint8_t* tmp = smem_raw;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = a.N;
@@ -291,19 +299,22 @@ __global__ void __launch_bounds__(kPackThreads, GMMLOC_PACK_MINB) frame_pack_ker
     unsigned char* gcst = pf + L.cst;
     const uint8_t* gflag = flags ? flags + (size_t)f * N : nullptr;
     __syncthreads();  // the previous frame is done with the shared arrays
-    if (flags == nullptr) {  // fused classification (the default): per-frame constants as frame_pose_kernel computes them
-      if (tid == 0) {
-        double q[7], R[9];
-        for (int i = 0; i < 7; ++i) q[i] = a.pose0[(size_t)f * 7 + i];
-        quat_normalize(q);
-        quat_to_rot(q, R);
-        s_fp[0] = R[6]; s_fp[1] = R[7]; s_fp[2] = R[8]; s_fp[3] = q[6];
-        s_fp[4] = -(R[0] * q[4] + R[3] * q[5] + R[6] * q[6]);
-        s_fp[5] = -(R[1] * q[4] + R[4] * q[5] + R[7] * q[6]);
-        s_fp[6] = -(R[2] * q[4] + R[5] * q[5] + R[8] * q[6]);
-      }
-      __syncthreads();
+#if GMMLOC_PACK_MATCH
+    // the histogram below is written by the leader of every group of same-class lanes only: absent classes must read zero
+    for (int e = tid; e < C_COUNT * nblocks * kWarps; e += kPackThreads)
+      s_cnt[(e / (nblocks * kWarps)) * (kMaxChunks * 8) + e % (nblocks * kWarps)] = 0;
+#endif
+    if (flags == nullptr && tid == 0) {  // fused classification (the default): per-frame constants as frame_pose_kernel computes them
+      double q[7], R[9];
+      for (int i = 0; i < 7; ++i) q[i] = a.pose0[(size_t)f * 7 + i];
+      quat_normalize(q);
+      quat_to_rot(q, R);
+      s_fp[0] = R[6]; s_fp[1] = R[7]; s_fp[2] = R[8]; s_fp[3] = q[6];
+      s_fp[4] = -(R[0] * q[4] + R[3] * q[5] + R[6] * q[6]);
+      s_fp[5] = -(R[1] * q[4] + R[4] * q[5] + R[7] * q[6]);
+      s_fp[6] = -(R[2] * q[4] + R[5] * q[5] + R[8] * q[6]);
     }
+    __syncthreads();
     // pass A: flags and class of every point — computed here (classify_point, the arithmetic of frame_classify_kernel) or
     // read from the flags that kernel wrote — and the class histogram per (block, warp)
     // The gate is a chain of dependent gathers (assignment -> degenerate flag -> component constants) and a thread walks its
@@ -335,14 +346,55 @@ __global__ void __launch_bounds__(kPackThreads, GMMLOC_PACK_MINB) frame_pack_ker
           tmp[i] = b;
           cls = b >> 4;
         }
+#if GMMLOC_PACK_MATCH
+        {  // one MATCH instead of a ballot per class: the lowest lane of every group of same-class lanes writes the group's size
+          const unsigned mk = __match_any_sync(0xffffffffu, cls);
+          if (cls >= 0 && lane == __ffs(mk) - 1) s_cnt[cls * (kMaxChunks * 8) + c * kWarps + warp] = __popc(mk);
+        }
+#else
 #pragma unroll
         for (int q = 0; q < C_COUNT; ++q) {
           const unsigned m = __ballot_sync(0xffffffffu, cls == q);
           if (lane == 0) s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] = __popc(m);
         }
+#endif
       }
     }
     __syncthreads();
+#if GMMLOC_PACK_PSCAN
+    {  // exclusive scan in (block, warp) order INSIDE every class, one warp per class (one warp walking all eight classes kept
+       // the other seven waiting at the barrier: 6.5 % of the kernel's stall samples); the class offsets follow below
+      static_assert(kWarps == C_COUNT, "one warp per class");
+      const int q = warp, n = nblocks * kWarps;
+      int run = 0;
+      for (int b0 = 0; b0 < n; b0 += 32) {
+        const int e = b0 + lane;
+        const int idx = q * (kMaxChunks * 8) + e;
+        const int v = (e < n) ? s_cnt[idx] : 0;
+        int inc = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, inc, off);
+          if (lane >= off) inc += t;
+        }
+        if (e < n) s_cnt[idx] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (lane == 0) s_tot[q] = run;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0, cb = 0;
+      for (int q = 0; q < C_COUNT; ++q) {
+        s_start[q] = run;
+        s_cb[q] = cb;
+        if (q >= C_FIXED && q < C_F64) cb += (s_tot[q] + 31) / 32;
+        run += s_tot[q];
+      }
+      s_start[C_COUNT] = run;  // = N
+      s_cb[C_COUNT] = cb;
+    }
+#else
     if (warp == 0) {  // exclusive scan in (class, block, warp) order = stable counting-sort offsets
       int run = 0;
       for (int q = 0; q < C_COUNT; ++q) {
@@ -372,6 +424,7 @@ __global__ void __launch_bounds__(kPackThreads, GMMLOC_PACK_MINB) frame_pack_ker
         s_cb[C_COUNT] = cb;
       }
     }
+#endif
     __syncthreads();
     {  // header + chunk table
       const int nch = s_cb[C_COUNT];
@@ -412,11 +465,21 @@ __global__ void __launch_bounds__(kPackThreads, GMMLOC_PACK_MINB) frame_pack_ker
           cls = b >> 4;
         }
         int j = -1;
+#if GMMLOC_PACK_MATCH
+        {
+          const unsigned mk = __match_any_sync(0xffffffffu, cls);
+          if (cls >= 0) j = s_cnt[cls * (kMaxChunks * 8) + c * kWarps + warp] + __popc(mk & ((1u << lane) - 1u));
+        }
+#else
 #pragma unroll
         for (int q = 0; q < C_COUNT; ++q) {
           const unsigned m = __ballot_sync(0xffffffffu, cls == q);
           if (cls == q) j = s_cnt[q * (kMaxChunks * 8) + c * kWarps + warp] + __popc(m & ((1u << lane) - 1u));
         }
+#endif
+#if GMMLOC_PACK_PSCAN
+        if (cls >= 0) j += s_start[cls];  // the per-class scan left offsets relative to the class
+#endif
         if (i < N) {
           const float p0 = pts[i * 3], p1 = pts[i * 3 + 1], p2 = pts[i * 3 + 2];
           gp[j * 3] = p0;

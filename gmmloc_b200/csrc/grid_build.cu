@@ -196,20 +196,26 @@ cudaError_t build_assoc_grid(MapDev& m, const double lo[3], const double hi[3], 
     return (opt != nullptr && from_opt > 0.0 && std::isfinite(from_opt)) ? from_opt : env_double(name, dflt);
   };
   cudaError_t e;
-  // cell size from the component density (about one component centre per 2.4 cells at level 0)
+  // cell size from the component density: 0.6 (V / K)^(1/3), about one component centre per 4.6 cells at level 0.  (Round 1
+  // used 0.75: with the warp-cooperative rounds of the sorted scan, which no longer need a cell full of landmarks to be
+  // efficient, finer cells with shorter lists win — C2 sort + scan 0.615 -> 0.576 ms, C3 0.408 -> 0.357 ms; at 0.5 the
+  // C5 map (50 000 components) outgrows the entry budget.)
   double ext[3], vol = 1.0;
   for (int i = 0; i < 3; ++i) {
     ext[i] = std::fmax(hi[i] - lo[i], 1.0);
     vol *= ext[i];
   }
-  const double h0 = pick(opt ? opt->cell_size : 0.0, "GMMLOC_GRID_H", std::fmin(std::fmax(0.75 * std::cbrt(vol / m.K), 0.05), 4.0));
-  // Three levels: T = 36 and T = 144 on the fine grid, T = 400 on a grid of twice the cell size.  The middle level is
+  const double h0 = pick(opt ? opt->cell_size : 0.0, "GMMLOC_GRID_H",
+                         std::fmin(std::fmax(env_double("GMMLOC_GRID_HSCALE", 0.6) * std::cbrt(vol / m.K), 0.05), 4.0));
+  // Three levels: T = 25 and T = 144 on the fine grid, T = 400 on a grid of twice the cell size.  (T0 was 36 while the
+  // lanes level 0 could not decide walked the next list one by one; now that they meet warp-cooperatively at level 1 the
+  // shorter T = 25 lists pay although 1.4 % of the C2 landmarks move on: C2 0.652 -> 0.615 ms; 20 / 30: 0.626 / 0.628.)  The middle level is
   // what the shipped maps need: their planes are millimetres thin, so a stereo depth error of one or two centimetres
   // puts a third of the landmarks beyond 6 sigma of their component (35 % of the C3 landmarks have a winner with
   // d2 > 36, 7 % with d2 > 144, 1.3 % with d2 > 400); without it they all walk the long coarse lists.
-  // GMMLOC_GRID_LEVELS=2 builds the fine T = 36 and the coarse T = 400 level only.
+  // GMMLOC_GRID_LEVELS=2 builds the fine T = 25 and the coarse T = 400 level only.
   const int want_levels = (int)pick(opt ? (double)opt->levels : 0.0, "GMMLOC_GRID_LEVELS", (double)kGridLevels) >= kGridLevels ? kGridLevels : 2;
-  double tmax[kGridLevels] = {pick(opt ? opt->tmax[0] : 0.0, "GMMLOC_GRID_TMAX0", 36.0), pick(opt ? opt->tmax[1] : 0.0, "GMMLOC_GRID_TMAX1", 144.0),
+  double tmax[kGridLevels] = {pick(opt ? opt->tmax[0] : 0.0, "GMMLOC_GRID_TMAX0", 25.0), pick(opt ? opt->tmax[1] : 0.0, "GMMLOC_GRID_TMAX1", 144.0),
                               pick(opt ? opt->tmax[2] : 0.0, "GMMLOC_GRID_TMAX2", 400.0)};
   double margin[kGridLevels] = {1.0, 1.0, 2.0};
   int scale[kGridLevels] = {1, 1, 2};

@@ -110,7 +110,7 @@ GMMLOC_API int gmmloc_map_device(const gmmloc_map_t* map);
 /* gmmloc_map_create with explicit tuning of the association grid built next to the map.  Every setting
  * returns identical associations; the defaults (grid == NULL, or a field <= 0) are what gmmloc_map_create uses.
  *  enable 0: no grid, the brute-force scan serves every association;  levels 2 or 3;  cell_size in metres (level 0);
- *  tmax[l]: squared Mahalanobis radius covered by the lists of level l (36 / 144 / 400). */
+ *  tmax[l]: squared Mahalanobis radius covered by the lists of level l (25 / 144 / 400). */
 typedef struct {
   int32_t enable;
   int32_t levels;
