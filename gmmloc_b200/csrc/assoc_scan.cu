@@ -697,43 +697,85 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
     // with the other 31 idle, which is what held up the shipped maps (35 % of the C3 landmarks lie beyond level 0).
     bool fin = false;  // assignment written
     for (int lev = 0; lev < a.grid.nlev; ++lev) {
-    const GridLevel& G = a.grid.lev[lev];
-    const bool need = live && finite_in && lev_ok < 0 && !fin;
-    if (!__any_sync(0xffffffffu, need)) break;
-    const long long cell = need ? grid_cell(G, px, py, pz) : -1;
-    if (lev > 0 && cell >= 0) {
-      b1 = g1;
-      b2 = g2;
-      idx = gi;
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, cell >= 0);
-    while (todo) {
-      const int leader = __ffs(todo) - 1;
-      const long long c = __shfl_sync(0xffffffffu, cell, leader);
-      const bool mine = (cell == c);
-      const bool all_mine = __all_sync(0xffffffffu, mine);
-      const float pen = mine ? 0.f : CUDART_INF_F;
-      const int e0 = __ldg(G.start + c), e1 = __ldg(G.start + c + 1);
-      // the list is staged through shared memory 32 components at a time: every lane fetches ONE record (32 gathers in
-      // flight instead of a dependent id -> record chain per component), then all lanes read the staged records with
-      // broadcast LDS.128 and score their own landmark
+      const GridLevel& G = a.grid.lev[lev];
+      const bool need = live && finite_in && lev_ok < 0 && !fin;
+      if (!__any_sync(0xffffffffu, need)) break;
+      const long long cell = need ? grid_cell(G, px, py, pz) : -1;
+      if (lev > 0 && cell >= 0) {
+        b1 = g1;
+        b2 = g2;
+        idx = gi;
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, cell >= 0);
+      while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const long long c = __shfl_sync(0xffffffffu, cell, leader);
+        const bool mine = (cell == c);
+        const bool all_mine = __all_sync(0xffffffffu, mine);
+        const float pen = mine ? 0.f : CUDART_INF_F;
+        const int e0 = __ldg(G.start + c), e1 = __ldg(G.start + c + 1);
+        // the list is staged through shared memory 32 components at a time: every lane fetches ONE record (32 gathers in
+        // flight instead of a dependent id -> record chain per component), then all lanes read the staged records with
+        // broadcast LDS.128 and score their own landmark
 #if GMMLOC_GRID_COOP
-      // Few lanes of the warp in this cell (the tail of a cell in a large launch; EVERY round of a small launch, where a cell
-      // holds a handful of landmarks): instead of all 32 lanes walking the whole list for m members, the (member, record)
-      // pairs are dealt over the lanes — m' = 2, 4, 8 or 16 member slots x 32 / m' records in parallel — and the per-slot
-      // (best, second best, id) triples are merged with xor shuffles.  Same score32() values, so the same (b1, b2); which of two
-      // EQUAL best scores names the id is immaterial: b2 == b1 then, and the certificate sends the landmark to the exact re-rank.
-      const unsigned mm = __ballot_sync(0xffffffffu, mine);
-      const int m = __popc(mm);
-      if (m <= 16) {
-        const int sh = m <= 2 ? 1 : m <= 4 ? 2 : m <= 8 ? 3 : 4;
-        const int mp = 1 << sh, slot = lane & (mp - 1), sub = lane >> sh, nsub = 32 >> sh;
-        const int rank = __popc(mm & ((1u << lane) - 1u));
-        if (mine) memb[wrp][rank] = make_float4(px, py, pz, 0.f);
-        __syncwarp();
-        const float4 qv = memb[wrp][slot < m ? slot : 0];
-        float c1 = CUDART_INF_F, c2 = CUDART_INF_F;
-        int ci = -1;
+        // Few lanes of the warp in this cell (the tail of a cell in a large launch; EVERY round of a small launch, where a cell
+        // holds a handful of landmarks): instead of all 32 lanes walking the whole list for m members, the (member, record)
+        // pairs are dealt over the lanes — m' = 2, 4, 8 or 16 member slots x 32 / m' records in parallel — and the per-slot
+        // (best, second best, id) triples are merged with xor shuffles.  Same score32() values, so the same (b1, b2); which of two
+        // EQUAL best scores names the id is immaterial: b2 == b1 then, and the certificate sends the landmark to the exact re-rank.
+        const unsigned mm = __ballot_sync(0xffffffffu, mine);
+        const int m = __popc(mm);
+        if (m <= 16) {
+          const int sh = m <= 2 ? 1 : m <= 4 ? 2 : m <= 8 ? 3 : 4;
+          const int mp = 1 << sh, slot = lane & (mp - 1), sub = lane >> sh, nsub = 32 >> sh;
+          const int rank = __popc(mm & ((1u << lane) - 1u));
+          if (mine) memb[wrp][rank] = make_float4(px, py, pz, 0.f);
+          __syncwarp();
+          const float4 qv = memb[wrp][slot < m ? slot : 0];
+          float c1 = CUDART_INF_F, c2 = CUDART_INF_F;
+          int ci = -1;
+          for (int base = e0; base < e1; base += 32) {
+            const int n = min(32, e1 - base);
+            if (lane < n) {
+              const int k = __ldg(G.list + base + lane);
+              const float4 r0 = __ldg(a.rec + 3 * (size_t)k), r1 = __ldg(a.rec + 3 * (size_t)k + 1);
+              const float r2 = __ldg(reinterpret_cast<const float*>(a.rec + 3 * (size_t)k + 2));
+              stage[wrp][lane][0] = r0;
+              stage[wrp][lane][1] = r1;
+              stage[wrp][lane][2] = make_float4(r2, __int_as_float(k), 0.f, 0.f);
+            }
+            __syncwarp();
+#pragma unroll 2
+            for (int q = sub; q < n; q += nsub) {
+              const float4 r0 = stage[wrp][q][0], r1 = stage[wrp][q][1], r2 = stage[wrp][q][2];
+              const float sc = score32(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, qv.x, qv.y, qv.z);
+              ci = (sc < c1) ? __float_as_int(r2.y) : ci;
+              c2 = fminf(c2, fmaxf(c1, sc));
+              c1 = fminf(c1, sc);
+            }
+            __syncwarp();
+          }
+          for (int off = mp; off < 32; off <<= 1) {  // lanes of one slot: lane bits sh..4
+            const float o1 = __shfl_xor_sync(0xffffffffu, c1, off), o2 = __shfl_xor_sync(0xffffffffu, c2, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, ci, off);
+            c2 = fminf(fmaxf(c1, o1), fminf(c2, o2));
+            ci = (o1 < c1) ? oi : ci;
+            c1 = fminf(c1, o1);
+          }
+          // the member of rank r finds its triple in lane r (slot r, sub 0)
+          const int from = mine ? rank : 0;
+          const float m1 = __shfl_sync(0xffffffffu, c1, from), m2 = __shfl_sync(0xffffffffu, c2, from);
+          const int mi = __shfl_sync(0xffffffffu, ci, from);
+          if (mine) {
+            b2 = fminf(fmaxf(b1, m1), fminf(b2, m2));
+            idx = (m1 < b1) ? mi : idx;
+            b1 = fminf(b1, m1);
+          }
+          todo &= ~mm;
+          __syncwarp();  // memb is rewritten by the next sparse round
+          continue;
+        }
+#endif
         for (int base = e0; base < e1; base += 32) {
           const int n = min(32, e1 - base);
           if (lane < n) {
@@ -745,80 +787,38 @@ __global__ void __launch_bounds__(THREADS) assoc_grid_kernel(const ScanArgs a) {
             stage[wrp][lane][2] = make_float4(r2, __int_as_float(k), 0.f, 0.f);
           }
           __syncwarp();
-#pragma unroll 2
-          for (int q = sub; q < n; q += nsub) {
-            const float4 r0 = stage[wrp][q][0], r1 = stage[wrp][q][1], r2 = stage[wrp][q][2];
-            const float sc = score32(r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x, qv.x, qv.y, qv.z);
-            ci = (sc < c1) ? __float_as_int(r2.y) : ci;
-            c2 = fminf(c2, fmaxf(c1, sc));
-            c1 = fminf(c1, sc);
-          }
+          // branch-free best / second-best (the branchy form spent more instructions here than on the score itself:
+          // profiles/assoc_grid_r02.txt).  Strict < keeps the first (lowest) id on equal scores, as the reference's ascending scan.
+          // A lane that is not in this cell adds +inf to its score (nothing changes for it); written as `mine ? score : inf` the
+          // compiler put a branch (BSSY / BRA / BSYNC, four instructions of 21 per record, and a scheduling fence between the
+          // staged loads of consecutive records) around every score.  When the whole warp sits in the cell — the usual case —
+          // the penalty is not even added.
+          if (all_mine) score_staged<false>(&stage[wrp][0][0], n, px, py, pz, 0.f, b1, b2, idx);
+          else score_staged<true>(&stage[wrp][0][0], n, px, py, pz, pen, b1, b2, idx);
           __syncwarp();
         }
-        for (int off = mp; off < 32; off <<= 1) {  // lanes of one slot: lane bits sh..4
-          const float o1 = __shfl_xor_sync(0xffffffffu, c1, off), o2 = __shfl_xor_sync(0xffffffffu, c2, off);
-          const int oi = __shfl_xor_sync(0xffffffffu, ci, off);
-          c2 = fminf(fmaxf(c1, o1), fminf(c2, o2));
-          ci = (o1 < c1) ? oi : ci;
-          c1 = fminf(c1, o1);
-        }
-        // the member of rank r finds its triple in lane r (slot r, sub 0)
-        const int from = mine ? rank : 0;
-        const float m1 = __shfl_sync(0xffffffffu, c1, from), m2 = __shfl_sync(0xffffffffu, c2, from);
-        const int mi = __shfl_sync(0xffffffffu, ci, from);
-        if (mine) {
-          b2 = fminf(fmaxf(b1, m1), fminf(b2, m2));
-          idx = (m1 < b1) ? mi : idx;
-          b1 = fminf(b1, m1);
-        }
-        todo &= ~mm;
-        __syncwarp();  // memb is rewritten by the next sparse round
-        continue;
+        todo &= ~__ballot_sync(0xffffffffu, mine);
       }
-#endif
-      for (int base = e0; base < e1; base += 32) {
-        const int n = min(32, e1 - base);
-        if (lane < n) {
-          const int k = __ldg(G.list + base + lane);
-          const float4 r0 = __ldg(a.rec + 3 * (size_t)k), r1 = __ldg(a.rec + 3 * (size_t)k + 1);
-          const float r2 = __ldg(reinterpret_cast<const float*>(a.rec + 3 * (size_t)k + 2));
-          stage[wrp][lane][0] = r0;
-          stage[wrp][lane][1] = r1;
-          stage[wrp][lane][2] = make_float4(r2, __int_as_float(k), 0.f, 0.f);
-        }
-        __syncwarp();
-        // branch-free best / second-best (the branchy form spent more instructions here than on the score itself:
-        // profiles/assoc_grid_r02.txt).  Strict < keeps the first (lowest) id on equal scores, as the reference's ascending scan.
-        // A lane that is not in this cell adds +inf to its score (nothing changes for it); written as `mine ? score : inf` the
-        // compiler put a branch (BSSY / BRA / BSYNC, four instructions of 21 per record, and a scheduling fence between the
-        // staged loads of consecutive records) around every score.  When the whole warp sits in the cell — the usual case —
-        // the penalty is not even added.
-        if (all_mine) score_staged<false>(&stage[wrp][0][0], n, px, py, pz, 0.f, b1, b2, idx);
-        else score_staged<true>(&stage[wrp][0][0], n, px, py, pz, pen, b1, b2, idx);
-        __syncwarp();
-      }
-      todo &= ~__ballot_sync(0xffffffffu, mine);
-    }
 #if GMMLOC_GRID_F32_CERT
-    // The certificate below costs ~110 instructions per landmark in fp64 (two square roots).  A conservative fp32 form of the
-    // same two tests decides almost every landmark: with correctly rounded sqrtf and the factors 1 +- 2e-6 (against kRelEps =
-    // 2.4e-7 and three fp32 roundings of 6e-8 each) `hi` is an upper bound of the fp64 hi1 and `lo` a lower bound of the fp64
-    // lo2, so  lo > hi  and  hi <= sqrt(tmax) (1 - 1e-6)  imply the fp64 tests: the SAME assignment is written, and what the
-    // fp32 form cannot decide still goes through the fp64 form.
-    if (cell >= 0 && idx >= 0 && a.d2 == nullptr && !(a.gate > 0.0)) {
-      const float al = a.alpha * (1.0f + 1e-6f);
-      const float hi = __fmaf_rn(__fsqrt_rn(b1), 1.0f + 2e-6f, al), lo = __fmaf_rn(__fsqrt_rn(b2), 1.0f - 2e-6f, -al);
-      if (lo > hi && hi <= __fsqrt_rn(G.tmax) * (1.0f - 1e-6f)) {
-        a.assign[i] = idx;
-        fin = true;
+      // The certificate below costs ~110 instructions per landmark in fp64 (two square roots).  A conservative fp32 form of the
+      // same two tests decides almost every landmark: with correctly rounded sqrtf and the factors 1 +- 2e-6 (against kRelEps =
+      // 2.4e-7 and three fp32 roundings of 6e-8 each) `hi` is an upper bound of the fp64 hi1 and `lo` a lower bound of the fp64
+      // lo2, so  lo > hi  and  hi <= sqrt(tmax) (1 - 1e-6)  imply the fp64 tests: the SAME assignment is written, and what the
+      // fp32 form cannot decide still goes through the fp64 form.
+      if (cell >= 0 && idx >= 0 && a.d2 == nullptr && !(a.gate > 0.0)) {
+        const float al = a.alpha * (1.0f + 1e-6f);
+        const float hi = __fmaf_rn(__fsqrt_rn(b1), 1.0f + 2e-6f, al), lo = __fmaf_rn(__fsqrt_rn(b2), 1.0f - 2e-6f, -al);
+        if (lo > hi && hi <= __fsqrt_rn(G.tmax) * (1.0f - 1e-6f)) {
+          a.assign[i] = idx;
+          fin = true;
+        }
+      }
+#endif
+      if (cell >= 0 && idx >= 0 && !fin) {
+        hi1 = sqrt((double)b1) * (1.0 + kRelEps) + (double)a.alpha;
+        if (hi1 * hi1 <= (double)G.tmax) lev_ok = lev;
       }
     }
-#endif
-    if (cell >= 0 && idx >= 0 && !fin) {
-      hi1 = sqrt((double)b1) * (1.0 + kRelEps) + (double)a.alpha;
-      if (hi1 * hi1 <= (double)G.tmax) lev_ok = lev;
-    }
-    }  // levels
     lev_first = a.grid.nlev;  // nothing left for the per-lane walk below
     if (!live || fin) return;
   }
