@@ -377,7 +377,7 @@ def test_frames_solve_large_n_uses_global_workspace(gpu, oracle):
 @pytest.mark.parametrize("B", [1100, 3700])
 def test_frames_solve_pipelined_host_path_equals_single_chunks(gpu, B):
     # B >= 1024 takes the chunked H2D / compute / D2H pipeline of gmmloc_frames_solve (uniform chunks; from 24 frames per SM
-    # on the tapered schedule with short chunks at both ends): same results as frame-by-frame calls (and therefore as the
+    # on the graded schedule 296, 444, 592, ... frames): same results as frame-by-frame calls (and therefore as the
     # oracle, checked above)
     g, ctx = gpu
     mean, cov = synth.make_map(800, 0.5, seed=12)
