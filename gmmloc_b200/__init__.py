@@ -35,6 +35,17 @@ def sigma2_inv(octave: int) -> float:
     return float(capi.lib().gmmloc_sigma2_inv(int(octave)))
 
 
+def frames_solve_chunks(B: int, sms: int = 148, chunk: int = 0, taper: int = 1, short_first: int = 0) -> list:
+    """Chunk sizes of the host pipeline of gmmloc_frames_solve for a batch of B frames (gmmloc_frames_solve_chunks: pure
+    host arithmetic, no device)."""
+    cap = max(8, B)
+    sizes = (C.c_int32 * cap)()
+    n = capi.lib().gmmloc_frames_solve_chunks(int(B), int(sms), int(chunk), int(taper), int(short_first), sizes, cap)
+    if n < 0:
+        raise ValueError("gmmloc_frames_solve_chunks: bad argument")
+    return [int(sizes[i]) for i in range(min(n, cap))]
+
+
 def _ptr(a):
     return None if a is None else C.c_void_p(a.ctypes.data)
 

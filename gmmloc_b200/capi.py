@@ -65,6 +65,7 @@ SYMBOLS = {
     "gmmloc_map_create_ex": (_i, [_vp, _vp, _i, _d, _i, _vp, C.POINTER(_vp)]),
     "gmmloc_map_query_point": (_i, [_vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "gmmloc_ctx_set_option": (_i, [_vp, _i, _i64]),
+    "gmmloc_frames_solve_chunks": (C.c_int32, [C.c_int32] * 5 + [_vp, C.c_int32]),
     "gmmloc_map_load_gmm": (_i, [C.c_char_p, _d, _i, C.POINTER(_vp)]),
     "gmmloc_map_save_gmm": (_i, [_vp, C.c_char_p]),
     "gmmloc_map_destroy": (None, [_vp]),

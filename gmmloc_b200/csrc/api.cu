@@ -888,62 +888,20 @@ gmmloc_status_t gmmloc_frames_solve_async(gmmloc_ctx_t* ctx, const gmmloc_map_t*
   return GMMLOC_OK;
 }
 
-gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
-                                    const gmmloc_params_t* params, const double* pose0, const float* pts_w,
-                                    const float* obs, const uint8_t* octave, int B, int N, double* pose_out, float* pts_out,
-                                    int32_t* assign, uint8_t* outlier, int32_t* status) try {
-  if (!ctx || !map || !cam || !params || B < 0 || N < 0) return fail(GMMLOC_EINVAL, "gmmloc_frames_solve: bad argument");
-  if (B == 0) return GMMLOC_OK;
-  if (!pose0 || !pose_out || !status || (N > 0 && (!pts_w || !obs || !octave)))
-    return fail(GMMLOC_EINVAL, "gmmloc_frames_solve: null pointer");
-  CU(cudaSetDevice(ctx->device));
-  const size_t M = (size_t)B * N;
-  CU(ctx->in_pose.reserve(56 * (size_t)B));
-  CU(ctx->in_pts.reserve(12 * M + 16));
-  CU(ctx->in_obs.reserve(12 * M + 16));
-  CU(ctx->in_oct.reserve(M + 16));
-  CU(ctx->out_pose.reserve(56 * (size_t)B));
-  CU(ctx->out_assign.reserve(4 * M + 16));
-  CU(ctx->out_status.reserve(4 * (size_t)B));
-  if (pts_out) CU(ctx->out_pts.reserve(12 * M + 16));
-  if (outlier) CU(ctx->out_outlier.reserve(M + 16));
-  // Pipelined over chunks of frames: H2D of chunk c+1 (copy stream) overlaps the kernels of chunk c
-  // (compute stream) and the D2H of chunk c-1 (second copy stream); PCIe is full duplex.  With
-  // page-locked caller buffers the copies are truly asynchronous; pageable buffers still work.
-  const int chunk_env = [&] {
-    const char* v = debug_env("GMMLOC_E2E_CHUNK");
-    return v ? std::atoi(v) : ctx->opt_e2e_chunk;
-  }();
+// Chunk boundaries of the host pipeline of gmmloc_frames_solve: a pure function of the batch size, the SM count and the
+// context options (exported as gmmloc_frames_solve_chunks so that the schedule is testable without a device).
+// chunk_opt: GMMLOC_OPT_E2E_CHUNK (0 = automatic), taper: GMMLOC_OPT_E2E_TAPER, short_first: GMMLOC_OPT_E2E_SHORT_FIRST.
+static std::vector<int> frames_solve_chunk_starts(int B, int sms, int chunk_env, int taper, int short_first) {
   // Chunk = 3 frames per resident CTA of the persistent frame-GN kernel (2 CTAs x 148 SMs -> 888 frames on B200): a
   // chunk that is not a multiple of the resident CTA count leaves most CTAs idle for a whole extra frame.  Measured on
   // the C2 frame size (tools/probe_e2e.py): 256 -> 463 k, 512 -> 537 k, 888 -> 574 k, 1024 -> 548 k, 2048 -> 506 k
   // frames/s; PCIe moves 55 GB/s each way on this box.
-  int sms = 148;
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const int chunk = chunk_env > 0 ? std::min(chunk_env, B) : ((B >= 1024) ? 6 * sms : B);
   // chunk boundaries: uniform chunks; a remainder smaller than half a chunk is merged into the last chunk instead of
   // running as a tiny one.  GMMLOC_E2E_SHORT_FIRST=1 makes the first chunk a third of the others (kernels start after a
   // shorter H2D) — measured no faster (652 k vs 658 k frames/s on C2), so it is off by default.
-  const int short_first = [&] {
-    const char* v = debug_env("GMMLOC_E2E_SHORT_FIRST");
-    return v ? std::atoi(v) : ctx->opt_e2e_short_first;
-  }();
   std::vector<int> cstart;
-  // -DGMMLOC_DEBUG_ENV builds only: GMMLOC_E2E_SCHEDULE="296,444,592,..." sets the chunk sizes (the last one takes the rest)
-  if (const char* sch = debug_env("GMMLOC_E2E_SCHEDULE")) {
-    int f = 0;
-    for (const char* q = sch; *q && f < B;) {
-      const int sz = std::atoi(q);
-      if (sz <= 0) break;
-      cstart.push_back(f);
-      f += sz;
-      while (*q && *q != ',') ++q;
-      if (*q == ',') ++q;
-    }
-    if (cstart.empty()) cstart.push_back(0);
-    cstart.push_back(B);
-  } else
-  if (ctx->opt_e2e_taper && !short_first && B >= 6 * 2 * sms + 2 * chunk) {
+  if (taper && !short_first && B >= 6 * 2 * sms + 2 * chunk) {
     // Graded schedule (default for large batches).  The pipeline is bound by the kernels, not by the copy-in: a chunk of n
     // frames costs ~0.22 ms + 0.84 us n on the device (the sort + grid scan loses its cell sharing on small launches, the
     // persistent solver runs whole waves of 2 x SMs frames) against 0.99 us n of copy-in at 50 GB/s, so chunk i + 1 has
@@ -980,6 +938,70 @@ gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, 
     }
     if (cstart.size() >= 2 && B - cstart.back() < chunk / 2) cstart.pop_back();
     cstart.push_back(B);
+  }
+  return cstart;
+}
+
+int32_t gmmloc_frames_solve_chunks(int32_t B, int32_t sms, int32_t chunk_opt, int32_t taper, int32_t short_first, int32_t* sizes,
+                                   int32_t cap) try {
+  if (B <= 0 || sms <= 0 || cap < 0 || (cap > 0 && sizes == nullptr)) return -1;
+  const std::vector<int> cs = frames_solve_chunk_starts(B, sms, chunk_opt, taper, short_first);
+  const int n = (int)cs.size() - 1;
+  for (int i = 0; i < n && i < cap; ++i) sizes[i] = cs[i + 1] - cs[i];
+  return n;
+} catch (...) {
+  return -1;
+}
+
+gmmloc_status_t gmmloc_frames_solve(gmmloc_ctx_t* ctx, const gmmloc_map_t* map, const gmmloc_camera_t* cam,
+                                    const gmmloc_params_t* params, const double* pose0, const float* pts_w,
+                                    const float* obs, const uint8_t* octave, int B, int N, double* pose_out, float* pts_out,
+                                    int32_t* assign, uint8_t* outlier, int32_t* status) try {
+  if (!ctx || !map || !cam || !params || B < 0 || N < 0) return fail(GMMLOC_EINVAL, "gmmloc_frames_solve: bad argument");
+  if (B == 0) return GMMLOC_OK;
+  if (!pose0 || !pose_out || !status || (N > 0 && (!pts_w || !obs || !octave)))
+    return fail(GMMLOC_EINVAL, "gmmloc_frames_solve: null pointer");
+  CU(cudaSetDevice(ctx->device));
+  const size_t M = (size_t)B * N;
+  CU(ctx->in_pose.reserve(56 * (size_t)B));
+  CU(ctx->in_pts.reserve(12 * M + 16));
+  CU(ctx->in_obs.reserve(12 * M + 16));
+  CU(ctx->in_oct.reserve(M + 16));
+  CU(ctx->out_pose.reserve(56 * (size_t)B));
+  CU(ctx->out_assign.reserve(4 * M + 16));
+  CU(ctx->out_status.reserve(4 * (size_t)B));
+  if (pts_out) CU(ctx->out_pts.reserve(12 * M + 16));
+  if (outlier) CU(ctx->out_outlier.reserve(M + 16));
+  // Pipelined over chunks of frames: H2D of chunk c+1 (copy stream) overlaps the kernels of chunk c
+  // (compute stream) and the D2H of chunk c-1 (second copy stream); PCIe is full duplex.  With
+  // page-locked caller buffers the copies are truly asynchronous; pageable buffers still work.
+  const int chunk_env = [&] {
+    const char* v = debug_env("GMMLOC_E2E_CHUNK");
+    return v ? std::atoi(v) : ctx->opt_e2e_chunk;
+  }();
+  // (chunk boundaries: frames_solve_chunk_starts above)
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int short_first = [&] {
+    const char* v = debug_env("GMMLOC_E2E_SHORT_FIRST");
+    return v ? std::atoi(v) : ctx->opt_e2e_short_first;
+  }();
+  std::vector<int> cstart;
+  // -DGMMLOC_DEBUG_ENV builds only: GMMLOC_E2E_SCHEDULE="296,444,592,..." sets the chunk sizes (the last one takes the rest)
+  if (const char* sch = debug_env("GMMLOC_E2E_SCHEDULE")) {
+    int f = 0;
+    for (const char* q = sch; *q && f < B;) {
+      const int sz = std::atoi(q);
+      if (sz <= 0) break;
+      cstart.push_back(f);
+      f += sz;
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    if (cstart.empty()) cstart.push_back(0);
+    cstart.push_back(B);
+  } else {
+    cstart = frames_solve_chunk_starts(B, sms, chunk_env, ctx->opt_e2e_taper, short_first);
   }
   const int nchunks = (int)cstart.size() - 1;
   while ((int)ctx->ev_in.size() < nchunks) {

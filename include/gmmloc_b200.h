@@ -207,6 +207,12 @@ GMMLOC_API int gmmloc_ctx_last_gn_kernel(gmmloc_ctx_t* ctx);
  *                               GMMLOC_OPT_E2E_CHUNK), the last takes the rest; 0: uniform chunks. */
 enum { GMMLOC_OPT_GN_PREP = 0, GMMLOC_OPT_E2E_CHUNK = 1, GMMLOC_OPT_E2E_SHORT_FIRST = 2, GMMLOC_OPT_BA_CLUSTER = 3, GMMLOC_OPT_E2E_TAPER = 4 };
 GMMLOC_API gmmloc_status_t gmmloc_ctx_set_option(gmmloc_ctx_t* ctx, int option, int64_t value);
+/* The chunk schedule gmmloc_frames_solve would run for a batch of B frames on a device with `sms` multiprocessors under the
+ * options above (chunk_opt = GMMLOC_OPT_E2E_CHUNK, taper = GMMLOC_OPT_E2E_TAPER, short_first = GMMLOC_OPT_E2E_SHORT_FIRST):
+ * writes up to `cap` chunk sizes (frames, in pipeline order; they sum to B) and returns the number of chunks, -1 on a bad
+ * argument.  Pure host arithmetic — no device, no context; results of gmmloc_frames_solve do not depend on the schedule. */
+GMMLOC_API int32_t gmmloc_frames_solve_chunks(int32_t B, int32_t sms, int32_t chunk_opt, int32_t taper, int32_t short_first,
+                                              int32_t* sizes, int32_t cap);
 
 /* page-locked host memory for the host entry points (pageable buffers also work, via staging) */
 GMMLOC_API gmmloc_status_t gmmloc_host_alloc(size_t bytes, void** out);

@@ -91,3 +91,29 @@ def test_product_never_imports_the_oracle():
             assert "pyoracle" not in txt and "gmmloc_oracle" not in txt, p
     for p in (ROOT / "include").glob("*"):
         assert "oracle" not in p.read_text().lower(), p
+
+
+def test_host_pipeline_chunk_schedule_needs_no_device():
+    """gmmloc_frames_solve_chunks: the chunk schedule of the host pipeline is pure host arithmetic (api.cu,
+    frames_solve_chunk_starts).  Every schedule covers the batch exactly; large batches run the graded schedule
+    (2, 3, 4, ... frames per SM, growth capped at twice the chunk option), small ones one chunk."""
+    import gmmloc_b200 as g
+    assert g.frames_solve_chunks(4096) == [296, 444, 592, 740, 888, 1136]  # the C2 step measured in DESIGN.md 5
+    assert g.frames_solve_chunks(1) == [1] and g.frames_solve_chunks(1023) == [1023]
+    assert g.frames_solve_chunks(1100) == [1100]           # 1100 - 888 < half a chunk: merged
+    assert g.frames_solve_chunks(2149) == [888, 1261]      # below 24 frames per SM: uniform chunks, short rest merged
+    for sms in (1, 4, 132, 148, 160):
+        for B in (1, 7, 1023, 1024, 1500, 3551, 3552, 3700, 4096, 8192, 50000):
+            for chunk in (0, 100, 888, 3000):
+                for taper in (0, 1):
+                    for short_first in (0, 1):
+                        sz = g.frames_solve_chunks(B, sms, chunk, taper, short_first)
+                        assert sum(sz) == B and all(x > 0 for x in sz), (sms, B, chunk, taper, short_first, sz)
+    big = g.frames_solve_chunks(50000)
+    assert big[0] == 296 and big[1] == 444 and max(big[:-1]) == 1776  # capped at 12 frames per SM
+    assert all(b >= a for a, b in zip(big[:-2], big[1:-1]))
+    assert g.frames_solve_chunks(50000, chunk=400)[5] == 800  # the option caps the growth at twice its value
+    assert g.frames_solve_chunks(4096, taper=0) == [888, 888, 888, 888, 544]
+    from gmmloc_b200 import capi
+    assert capi.lib().gmmloc_frames_solve_chunks(0, 148, 0, 1, 0, None, 0) == -1
+    assert capi.lib().gmmloc_frames_solve_chunks(4096, 148, 0, 1, 0, None, 0) == 6  # count only
